@@ -1,0 +1,46 @@
+"""Builds the oracle's native pieces.  TEST INFRASTRUCTURE.
+
+* ``oracle/_build/liboracle.so``      <- oracle/c/uyd_oracle.c (our C restatement)
+* ``oracle/_ref/libref_postprocess.so`` <- the reference's own postprocess.hpp compiled
+  *where it lies* under /root/reference (only when that mount exists; the GPU box uses
+  the prebuilt file that travels with the snapshot).
+"""
+from __future__ import annotations
+
+import subprocess
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+REF_INC = Path("/root/reference/unina_yolo_dla/ros2_ws/src/perception/include")
+ORACLE_SO = HERE / "_build" / "liboracle.so"
+REF_SO = HERE / "_ref" / "libref_postprocess.so"
+
+
+def _stale(out: Path, srcs) -> bool:
+    return (not out.exists()) or any(Path(s).stat().st_mtime > out.stat().st_mtime for s in srcs)
+
+
+def build_oracle(force: bool = False) -> Path:
+    src = HERE / "c" / "uyd_oracle.c"
+    if force or _stale(ORACLE_SO, [src]):
+        ORACLE_SO.parent.mkdir(exist_ok=True)
+        subprocess.check_call(
+            ["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c11", str(src), "-o", str(ORACLE_SO), "-lm"]
+        )
+    return ORACLE_SO
+
+
+def build_ref(force: bool = False):
+    """Returns the path of the compiled reference header shim, or None if unavailable."""
+    src = HERE / "c" / "ref_postprocess_harness.cpp"
+    if REF_INC.exists() and (force or _stale(REF_SO, [src, REF_INC / "postprocess.hpp"])):
+        REF_SO.parent.mkdir(exist_ok=True)
+        subprocess.check_call(
+            ["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", f"-I{REF_INC}", str(src), "-o", str(REF_SO)]
+        )
+    return REF_SO if REF_SO.exists() else None
+
+
+if __name__ == "__main__":
+    print(build_oracle(True))
+    print(build_ref(True))
