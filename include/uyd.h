@@ -1,0 +1,177 @@
+/* libuyd.so -- C ABI of the B200-native UNINA-YOLO-DLA inference hot path.
+ *
+ * Conventions (same as the reference's extern "C" surface,
+ * ros2_ws/src/perception/include/gpu_postprocess.h:42-80): every entry point returns an
+ * int that is a cudaError_t-compatible code (0 = success; UYD_E_* below for argument /
+ * state errors), never throws, takes the cudaStream_t LAST, works on caller-owned device
+ * pointers and allocates nothing after create/finalize.  No host synchronisation happens
+ * inside any call; counts stay on the device.
+ *
+ * What each group replaces in the reference:
+ *   uyd_create/destroy      <- init_postprocess_resources / cleanup_postprocess_resources
+ *                              (gpu_postprocess.h:45,50; global singleton gpu_postprocess.cu:56
+ *                              becomes a per-device handle)
+ *   uyd_plan_*              <- the conv stack the reference runs through TensorRT
+ *                              (perception_node.cpp:611-624) / PyTorch (DetectionModel.forward,
+ *                              trainer.py:156; model.py:347-365)
+ *   uyd_decode_dfl          <- Ultralytics Detect._inference + DFL
+ *   uyd_decode_tlbr         <- decode_yolo_head (gpu_postprocess.h:62-65,
+ *                              gpu_postprocess.cu:102-199, postprocess.hpp:94-145)
+ *   uyd_nms                 <- Ultralytics non_max_suppression + torchvision.ops.nms
+ *                              (train.py:396-405) and run_gpu_nms + copy_valid_detections_to_host
+ *                              (gpu_postprocess.h:70-78)
+ */
+#ifndef UYD_H
+#define UYD_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct uyd_ctx uyd_ctx;   /* per-device handle: workspaces, TMA encoder, SM count */
+typedef struct uyd_plan uyd_plan; /* a compiled layer list with its activation buffers    */
+typedef void *uyd_stream;         /* cudaStream_t */
+
+enum {
+  UYD_OK = 0,
+  UYD_E_ARG = 10001,     /* bad argument                      */
+  UYD_E_STATE = 10002,   /* call order / plan not finalized   */
+  UYD_E_UNSUPPORTED = 10003,
+  UYD_E_NOGPU = 10004    /* no sm_100 device                  */
+};
+
+enum { UYD_BF16 = 0, UYD_F32 = 1, UYD_S8 = 2 };
+
+/* Which kernel family executes a convolution. AUTO picks tensor cores when the shape
+ * allows it.  DIRECT = CUDA-core reference kernel (used for tiny channel counts and as an
+ * on-device cross-check). */
+enum { UYD_IMPL_AUTO = 0, UYD_IMPL_DIRECT = 1, UYD_IMPL_TC = 2 };
+
+int uyd_version(void);
+const char *uyd_last_error(void);
+int uyd_create(int device, uyd_ctx **out);
+int uyd_destroy(uyd_ctx *ctx);
+int uyd_sm_count(const uyd_ctx *ctx);
+
+/* ------------------------------------------------------------------------------------
+ * Plan: activation buffers (NHWC, bf16 unless stated) + an ordered list of ops.
+ * Buffers are addressed as (id, channel offset): producers write straight into channel
+ * slices of wider buffers, so concat / chunk never materialise.
+ * ---------------------------------------------------------------------------------- */
+int uyd_plan_create(uyd_ctx *ctx, int max_batch, uyd_plan **out);
+int uyd_plan_destroy(uyd_plan *plan);
+
+/* Declares an activation buffer [max_batch, h, w, c] of dtype; returns its id (>= 0) in *id. */
+int uyd_plan_add_buffer(uyd_plan *plan, int h, int w, int c, int dtype, int *id);
+
+typedef struct uyd_conv {
+  int in_buf, in_coff;     /* input slice; in_buf = -1: the network input x (NCHW fp32)   */
+  int out_buf, out_coff;   /* output slice                                                 */
+  int res_buf, res_coff;   /* residual slice added AFTER the activation, -1 = none         */
+  int cin, cout;           /* logical channels                                             */
+  int k, stride;           /* 1|3 , 1|2 ; padding k/2                                      */
+  int depthwise;           /* 1: groups == cin == cout                                     */
+  int relu;                /* 1: ReLU after (folded BN) bias                               */
+  int impl;                /* UYD_IMPL_*                                                   */
+  int reserved;
+} uyd_conv;
+
+/* weight: host fp32 [cout][cin/groups][k][k] (PyTorch layout, BN already folded);
+ * bias: host fp32 [cout].  Packed to the kernel's layout and uploaded here. */
+int uyd_plan_add_conv(uyd_plan *plan, const uyd_conv *desc, const float *weight, const float *bias);
+
+/* SPPF cascade: reads slice [coff, coff+c) of buf and writes pool5, pool5^2, pool5^3 to
+ * slices [coff+c, coff+2c), [coff+2c, ..), [coff+3c, ..) of the same buffer
+ * (trainer.py:119-124; -inf padding). */
+int uyd_plan_add_sppf_pool(uyd_plan *plan, int buf, int coff, int c);
+
+/* nearest x2 upsample of a slice into a slice of a buffer with twice the extent. */
+int uyd_plan_add_upsample2x(uyd_plan *plan, int in_buf, int in_coff, int out_buf, int out_coff, int c);
+
+/* Marks the three raw head buffers ([B,H,W,no] fp32, box logits first then class logits)
+ * in level order (stride 4, 8, 16 ...) for uyd_plan_run_decode. */
+int uyd_plan_set_heads(uyd_plan *plan, const int *head_bufs, const int *strides, int nl, int reg_max, int nc);
+
+int uyd_plan_finalize(uyd_plan *plan);
+size_t uyd_plan_bytes(const uyd_plan *plan);
+int uyd_plan_num_launches(const uyd_plan *plan);
+
+/* Device pointer of a buffer (valid after finalize); for layer-level parity checks. */
+int uyd_plan_buffer_ptr(uyd_plan *plan, int id, void **ptr);
+
+/* Runs every op for `batch` images.  x: device NCHW fp32 [batch,3,H,W] (the reference
+ * forward signature, model.py:347 / DetectionModel.forward).  */
+int uyd_plan_run(uyd_plan *plan, const float *x, int batch, uyd_stream stream);
+
+/* DFL decode of the plan's heads -> y [batch, 4+nc, A] fp32 (cx,cy,w,h in pixels, sigmoid
+ * class scores), A = sum of H_l*W_l, levels concatenated in head order. */
+int uyd_plan_run_decode(uyd_plan *plan, float *y, int batch, uyd_stream stream);
+
+/* Optional: raw heads as the reference returns them, NCHW fp32 [batch, no, H_l, W_l]. */
+int uyd_plan_export_head_nchw(uyd_plan *plan, int level, float *out, int batch, uyd_stream stream);
+
+/* ------------------------------------------------------------------------------------
+ * Stand-alone post-processing on caller-owned device memory.
+ * ---------------------------------------------------------------------------------- */
+
+/* DFL decode of one level.  head: [batch,H,W,4*reg_max+nc] fp32 (NHWC).
+ * Writes y[b, :, a_off + i] for i in [0,H*W), y laid out [batch, 4+nc, a_total]. */
+int uyd_decode_dfl(uyd_ctx *ctx, const float *head, int batch, int h, int w, int reg_max, int nc,
+                   float stride, float *y, int a_total, int a_off, uyd_stream stream);
+
+/* 32-byte detection record, layout-identical to GpuDetection (gpu_postprocess.h:27-33). */
+typedef struct uyd_detection {
+  float x1, y1, x2, y2;
+  float confidence;
+  int class_id;
+  int valid;
+  int _pad;
+} uyd_detection;
+
+/* TLBR decode of one level (signature-compatible superset of decode_yolo_head):
+ * cls [nc,H,W], reg [4,H,W] CHW fp32 per image; appends to dets (capacity cap) through the
+ * device counter d_count (caller zeroes it); keeps a cell iff conf > thr (strict=1,
+ * postprocess.hpp:116) or conf >= thr (strict=0, gpu_postprocess.cu:132). Also writes the
+ * flat cell index of every detection to cell_idx when non-NULL (for deterministic order). */
+int uyd_decode_tlbr(uyd_ctx *ctx, const float *d_cls, const float *d_reg, uyd_detection *dets,
+                    int *cell_idx, int *d_count, int cap, int grid_w, int grid_h, int stride,
+                    int num_classes, float conf_thr, float conformal_q, int strict,
+                    uyd_stream stream);
+
+/* Workspace size needed by uyd_nms for (batch, anchors). */
+size_t uyd_nms_workspace_bytes(int batch, int anchors);
+
+/* Ultralytics non_max_suppression on y [batch, 4+nc, anchors] fp32:
+ *   keep conf > conf_thr, best class, stable score-descending order (ties: lower anchor
+ *   first), top max_nms, class-offset (cls*max_wh) greedy NMS with IoU > iou_thr
+ *   (fp32 IoU compared against the double threshold, like torchvision), first max_det.
+ * out_det [batch, max_det, 6] fp32 rows (x1,y1,x2,y2,conf,cls); out_idx [batch, max_det]
+ * anchor index of every kept row (may be NULL); out_count [batch]. */
+int uyd_nms(uyd_ctx *ctx, const float *y, int batch, int nc, int anchors, float conf_thr,
+            double iou_thr, int max_nms, int max_det, float max_wh, void *workspace,
+            size_t workspace_bytes, float *out_det, int *out_idx, int *out_count,
+            uyd_stream stream);
+
+/* Greedy class-aware NMS over uyd_detection records (postprocess.hpp:44-67 semantics:
+ * confidence-descending, same class, IoU > thr; ties broken by cell_idx ascending, or by
+ * slot when cell_idx is NULL).  Replaces run_gpu_nms + copy_valid_detections_to_host's
+ * compaction (gpu_postprocess.h:70-78): `dets` (first min(*d_count, cap) records) is left
+ * untouched; survivors are written compacted, in kept order, to `out` (at most 1024, the
+ * reference's MAX_DETECTIONS) and their number to *d_out_count (device). */
+size_t uyd_nms_detections_workspace_bytes(int cap);
+int uyd_nms_detections(uyd_ctx *ctx, const uyd_detection *dets, const int *cell_idx,
+                       const int *d_count, int cap, float iou_thr, void *workspace,
+                       size_t workspace_bytes, uyd_detection *out, int *d_out_count,
+                       uyd_stream stream);
+
+/* Plain device-to-device copy on `stream` (lets a host binding without a CUDA runtime of
+ * its own read plan buffers into memory it owns). */
+int uyd_memcpy_d2d(void *dst, const void *src, size_t bytes, uyd_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UYD_H */

@@ -1,0 +1,183 @@
+"""GPU parity tests (run on the B200 box): the CUDA path through the C ABI vs the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def T():
+    import uyd_testlib
+    return uyd_testlib
+
+
+DIRECT_CASES = [
+    # cin, cout, k, stride, H, W, kwargs
+    (4, 4, 3, 1, 24, 40, dict(residual=True, in_total=8, in_coff=4, out_total=8, out_coff=4)),
+    (8, 4, 1, 1, 16, 16, dict()),
+    (8, 8, 3, 1, 20, 20, dict(residual=True, in_total=32, in_coff=8, out_total=32, out_coff=16)),
+    (16, 16, 3, 1, 12, 20, dict()),
+    (32, 16, 1, 1, 16, 24, dict(out_total=32, out_coff=16)),
+    (16, 32, 3, 2, 32, 32, dict()),
+    (64, 64, 3, 1, 16, 16, dict()),
+    (96, 16, 1, 1, 16, 16, dict()),
+    (32, 4, 1, 1, 16, 16, dict(relu=False, out_f32=True, out_total=68, out_coff=64)),
+    (64, 64, 1, 1, 8, 8, dict(relu=False, out_f32=True, out_total=68, out_coff=0)),
+]
+
+
+@pytest.mark.parametrize("case", DIRECT_CASES, ids=lambda c: f"{c[0]}-{c[1]}-k{c[2]}s{c[3]}")
+def test_direct_conv_matches_torch(T, case):
+    cin, cout, k, s, H, W, kw = case
+    got, ref = T.run_single_conv(cin, cout, k, s, H, W, impl=T.IMPL_DIRECT, **kw)
+    assert T.rel_err(got, ref) < 6e-3
+
+
+def test_depthwise_conv_matches_torch(T):
+    for c in (32, 64, 128):
+        got, ref = T.run_single_conv(c, c, 3, 1, 20, 28, impl=T.IMPL_DIRECT, depthwise=True)
+        assert T.rel_err(got, ref) < 6e-3
+
+
+TC_CASES = [
+    # flat 1x1
+    (64, 64, 1, 1, 16, 24, dict()),
+    (32, 16, 1, 1, 20, 20, dict(out_total=32, out_coff=16)),
+    (16, 32, 1, 1, 16, 16, dict()),
+    (192, 32, 1, 1, 16, 16, dict()),
+    (96, 16, 1, 1, 24, 24, dict(out_total=32)),
+    (80, 64, 1, 1, 16, 16, dict()),
+    (160, 128, 1, 1, 8, 8, dict()),
+    (256, 128, 1, 1, 8, 8, dict()),
+    (64, 64, 1, 1, 8, 8, dict(relu=False, out_f32=True, out_total=68)),
+    (32, 4, 1, 1, 16, 16, dict(relu=False, out_f32=True, out_total=68, out_coff=64)),
+    (64, 32, 1, 1, 16, 16, dict(in_total=192, in_coff=128)),
+    # 3x3 stride 1 (halo) incl. partial tiles and residual
+    (64, 64, 3, 1, 32, 16, dict()),
+    (64, 64, 3, 1, 40, 40, dict()),
+    (128, 64, 3, 1, 24, 24, dict()),
+    (32, 64, 3, 1, 32, 32, dict()),
+    (16, 16, 3, 1, 40, 40, dict(residual=True)),
+    # 3x3 stride 2 (per-tap, TMA traversal stride)
+    (16, 32, 3, 2, 64, 64, dict()),
+    (32, 64, 3, 2, 32, 48, dict()),
+    (64, 128, 3, 2, 32, 32, dict()),
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES, ids=lambda c: f"{c[0]}-{c[1]}-k{c[2]}s{c[3]}-{c[4]}x{c[5]}")
+def test_tensor_core_conv_matches_torch(T, case):
+    cin, cout, k, s, H, W, kw = case
+    got, ref = T.run_single_conv(cin, cout, k, s, H, W, batch=3, impl=T.IMPL_TC, **kw)
+    assert T.rel_err(got, ref) < 6e-3
+
+
+def test_tensor_core_conv_many_tiles_and_partial_batch(T):
+    # more tiles than SMs (persistent loop, both TMEM accumulators, stage wrap-around) and
+    # a run with fewer images than the plan was built for
+    got, ref = T.run_single_conv(64, 64, 3, 1, 160, 160, batch=2, impl=T.IMPL_TC, max_batch=4)
+    assert T.rel_err(got, ref) < 6e-3
+    got, ref = T.run_single_conv(64, 64, 1, 1, 160, 160, batch=3, impl=T.IMPL_TC, max_batch=4)
+    assert T.rel_err(got, ref) < 6e-3
+
+
+def test_sppf_pool_and_upsample_are_exact(T):
+    import torch.nn.functional as F
+    import unina_yolo_dla_b200 as uyd
+
+    g = torch.Generator().manual_seed(1)
+    x = T.bf16_round(torch.randn(2, 64, 40, 40, generator=g))
+    p = uyd.Plan(0, 2)
+    cat = p.buffer(40, 40, 256)
+    up = p.buffer(80, 80, 96)
+    p.sppf_pool(cat, 64)
+    p.upsample2x(cat.sub(0, 64), up.sub(32, 64))
+    p.finalize()
+    p.write(cat.sub(0, 64), x)
+    p.run_no_input(2)
+    y1 = F.max_pool2d(x, 5, 1, 2)
+    y2 = F.max_pool2d(y1, 5, 1, 2)
+    y3 = F.max_pool2d(y2, 5, 1, 2)
+    got = p.read(cat, 2).cpu()
+    assert torch.equal(got, torch.cat((x, y1, y2, y3), 1))
+    assert torch.equal(p.read(up.sub(32, 64), 2).cpu(), F.interpolate(x, scale_factor=2, mode="nearest"))
+
+
+def test_dfl_decode_matches_oracle(T):
+    import ctypes as C
+    import unina_yolo_dla_b200 as uyd
+    from unina_yolo_dla_b200 import _lib
+    from oracle import yolo_graph as yg
+
+    det = yg.Detect(4, (32, 64, 128))
+    det.stride = torch.tensor([4.0, 8.0, 16.0])
+    g = torch.Generator().manual_seed(2)
+    B = 3
+    raws = [torch.randn(B, 68, s, s, generator=g) * 2 for s in (20, 10, 5)]
+    want = det.decode(raws)
+    A = want.shape[2]
+    y = torch.empty(B, 8, A, device="cuda")
+    off = 0
+    for r, st in zip(raws, (4.0, 8.0, 16.0)):
+        nhwc = r.permute(0, 2, 3, 1).contiguous().cuda()
+        _lib.check(_lib.lib().uyd_decode_dfl(_lib.context(0), C.c_void_p(nhwc.data_ptr()), B, r.shape[2], r.shape[3], 16, 4,
+                                             st, C.c_void_p(y.data_ptr()), A, off, None))
+        off += r.shape[2] * r.shape[3]
+    torch.cuda.synchronize()
+    got = y.cpu()
+    assert float((got[:, :4] - want[:, :4]).abs().max()) < 2e-3  # pixels; fp32 exp differences only
+    assert float((got[:, 4:] - want[:, 4:]).abs().max()) < 2e-6
+
+
+NMS_CASES = [
+    dict(B=4, nc=4, A=33600, frac=0.05, conf=0.25, iou=0.7, cluster=False),
+    dict(B=3, nc=4, A=33600, frac=0.9, conf=0.25, iou=0.45, cluster=True),      # > 300 kept and heavy suppression
+    dict(B=2, nc=4, A=33600, frac=1.0, conf=0.001, iou=0.7, cluster=True, max_nms=3000),  # top-max_nms truncation
+    dict(B=2, nc=1, A=2100, frac=0.5, conf=0.25, iou=0.5, cluster=True),
+    dict(B=2, nc=4, A=600, frac=0.0, conf=0.25, iou=0.7, cluster=False),         # empty images
+]
+
+
+@pytest.mark.parametrize("cfg", NMS_CASES, ids=lambda c: f"A{c['A']}-f{c['frac']}-iou{c['iou']}")
+def test_nms_is_bit_exact_vs_oracle(T, cfg):
+    import unina_yolo_dla_b200 as uyd
+    from oracle import postproc as pp
+
+    y = T.synth_predictions(cfg["B"], cfg["nc"], cfg["A"], seed=3, frac_conf=cfg["frac"], cluster=cfg["cluster"])
+    # exact ties in score and coordinates on purpose
+    y[:, :, 100:140] = y[:, :, 60:100]
+    max_nms = cfg.get("max_nms", 30000)
+    want, widx = pp.non_max_suppression(y, cfg["conf"], cfg["iou"], 300, max_nms, return_index=True)
+    m = uyd.UninaYoloB200.from_yaml(nc=cfg["nc"])
+    det, cnt, idx = m.nms(torch.from_numpy(y).cuda(), cfg["conf"], cfg["iou"], 300, max_nms, return_index=True)
+    det, cnt, idx = det.cpu().numpy(), cnt.cpu().numpy(), idx.cpu().numpy()
+    for b in range(cfg["B"]):
+        n = len(want[b])
+        assert cnt[b] == n
+        np.testing.assert_array_equal(idx[b, :n], widx[b])          # kept-index sets, in order
+        assert det[b, :n].tobytes() == want[b].tobytes()            # rows bit-exact
+
+
+def test_full_forward_matches_oracle_bf16(T):
+    import unina_yolo_dla_b200 as uyd
+    from oracle import init as oi
+
+    ref = oi.build_yolo(seed=0, cls_bias=-2.0)
+    m = uyd.UninaYoloB200.from_yaml()
+    m.load_state_dict(ref.state_dict(), strict=True)
+    m = m.cuda()
+    x = oi.seeded_frames(2, 640, seed=5)
+    with torch.no_grad():
+        y_ref, raw_ref = ref(x)
+    y, raws = m(x.cuda())
+    torch.cuda.synchronize()
+    for a, b in zip(raws, raw_ref):
+        assert a.shape == b.shape
+        # north-star tolerance: max relative error on head logits <= 1e-2 (relative to the tensor's range)
+        assert T.rel_err(a.cpu()[:, :64], b[:, :64]) <= 1e-2
+        assert T.rel_err(a.cpu()[:, 64:], b[:, 64:]) <= 1e-2
+    assert T.rel_err(y.cpu()[:, :4], y_ref[:, :4]) <= 1e-2
+    assert float((y.cpu()[:, 4:] - y_ref[:, 4:]).abs().max()) <= 1e-2

@@ -1,0 +1,98 @@
+"""ctypes binding of libuyd.so (include/uyd.h).  No fallback: if the CUDA library is not
+built or no sm_100 GPU is present, every use raises."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+LIB_PATH = HERE / "libuyd.so"
+
+UYD_BF16, UYD_F32, UYD_S8 = 0, 1, 2
+IMPL_AUTO, IMPL_DIRECT, IMPL_TC = 0, 1, 2
+
+
+class UydError(RuntimeError):
+    pass
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [(n, C.c_int) for n in (
+        "in_buf", "in_coff", "out_buf", "out_coff", "res_buf", "res_coff", "cin", "cout",
+        "k", "stride", "depthwise", "relu", "impl", "reserved")]
+
+
+class Detection(C.Structure):
+    """Layout-identical to the reference GpuDetection (gpu_postprocess.h:27-33)."""
+    _fields_ = [("x1", C.c_float), ("y1", C.c_float), ("x2", C.c_float), ("y2", C.c_float),
+                ("confidence", C.c_float), ("class_id", C.c_int), ("valid", C.c_int), ("_pad", C.c_int)]
+
+
+# name -> (restype, argtypes): every symbol include/uyd.h declares
+SIGNATURES = {
+    "uyd_version": (C.c_int, []),
+    "uyd_last_error": (C.c_char_p, []),
+    "uyd_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "uyd_destroy": (C.c_int, [C.c_void_p]),
+    "uyd_sm_count": (C.c_int, [C.c_void_p]),
+    "uyd_plan_create": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "uyd_plan_destroy": (C.c_int, [C.c_void_p]),
+    "uyd_plan_add_buffer": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "uyd_plan_add_conv": (C.c_int, [C.c_void_p, C.POINTER(ConvDesc), C.c_void_p, C.c_void_p]),
+    "uyd_plan_add_sppf_pool": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "uyd_plan_add_upsample2x": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "uyd_plan_set_heads": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int]),
+    "uyd_plan_finalize": (C.c_int, [C.c_void_p]),
+    "uyd_plan_bytes": (C.c_size_t, [C.c_void_p]),
+    "uyd_plan_num_launches": (C.c_int, [C.c_void_p]),
+    "uyd_plan_buffer_ptr": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "uyd_plan_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "uyd_plan_run_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "uyd_plan_export_head_nchw": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "uyd_decode_dfl": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                 C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "uyd_decode_tlbr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p]),
+    "uyd_nms_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "uyd_nms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_double, C.c_int, C.c_int,
+                          C.c_float, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "uyd_nms_detections_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "uyd_nms_detections": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p,
+                                     C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "uyd_memcpy_d2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise UydError(
+                f"{LIB_PATH} is missing: build it with `python __graft_entry__.py` "
+                "(nvcc, sm_100a).  There is no CPU or PyTorch fallback for this path.")
+        L = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(code: int, what: str = "") -> None:
+    if code != 0:
+        msg = lib().uyd_last_error().decode(errors="replace")
+        raise UydError(f"{what or 'libuyd'} failed with code {code}: {msg}")
+
+
+_ctx = {}
+
+
+def context(device: int) -> C.c_void_p:
+    """One handle per device (replaces the reference's global singleton, gpu_postprocess.cu:56)."""
+    if device not in _ctx:
+        h = C.c_void_p()
+        check(lib().uyd_create(device, C.byref(h)), "uyd_create")
+        _ctx[device] = h
+    return _ctx[device]

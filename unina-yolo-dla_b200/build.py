@@ -1,0 +1,51 @@
+"""Builds libuyd.so in-tree with nvcc for sm_100a (no torch involved)."""
+from __future__ import annotations
+
+import os
+import subprocess
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+CSRC = HERE / "csrc"
+LIB = HERE / "libuyd.so"
+SOURCES = ["api.cu", "conv_direct.cu", "conv_tc.cu", "pool_upsample.cu", "decode.cu", "nms.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
+]
+
+
+def _nvcc() -> str:
+    for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if c and (os.path.sep not in c or Path(c).exists()):
+            return c
+    raise RuntimeError("nvcc not found")
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    srcs = [CSRC / s for s in SOURCES]
+    deps = srcs + [CSRC / "common.cuh", HERE.parent / "include" / "uyd.h"]
+    if not force and LIB.exists() and all(d.stat().st_mtime <= LIB.stat().st_mtime for d in deps):
+        return LIB
+    objs = []
+    (HERE / "build").mkdir(exist_ok=True)
+    logs = []
+    for s in srcs:
+        o = HERE / "build" / (s.stem + ".o")
+        if force or not o.exists() or any(d.stat().st_mtime > o.stat().st_mtime for d in (s, deps[-2], deps[-1])):
+            r = subprocess.run([_nvcc(), *NVCC_FLAGS, "-c", str(s), "-o", str(o)], capture_output=True, text=True)
+            logs.append(r.stderr)
+            if r.returncode != 0:
+                raise RuntimeError(f"nvcc failed on {s.name}:\n{r.stdout}\n{r.stderr}")
+        objs.append(str(o))
+    r = subprocess.run([_nvcc(), "-shared", "-o", str(LIB), *objs, "-cudart", "static"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    (HERE / "build" / "ptxas.log").write_text("\n".join(logs))
+    if verbose:
+        print("\n".join(logs))
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

@@ -1,0 +1,362 @@
+// C-ABI boundary of libuyd: handle, plan (buffers + ops), run, decode, head export.
+#include <cstdarg>
+#include <cstdlib>
+#include <memory>
+
+#include "common.cuh"
+
+namespace uyd {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// conv_tc.cu
+struct TcConv;
+bool tc_supported(const uyd_conv &d, int in_pitch, int in_coff, int out_pitch, int out_coff, bool in_is_network_input);
+size_t tc_weight_bytes(const uyd_conv &d);
+void tc_pack_weights(const uyd_conv &d, const float *w, void *dst_host);
+int tc_prepare(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int ih, int iw, int max_batch, void *out_base,
+               int out_pitch, int out_f32, const void *res_base, int res_pitch, void *w_dev, const float *bias_dev,
+               int mode_override, int base_offset_mode, int stages_override);
+int tc_launch(const TcConv *tc, int n0, int nb, int sm_count, cudaStream_t s);
+TcConv *tc_new();
+void tc_delete(TcConv *);
+const char *tc_mode_name(const TcConv *);
+
+static int env_int(const char *name, int dflt) {
+  const char *v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
+}  // namespace uyd
+
+using namespace uyd;
+
+struct uyd_ctx {
+  int device = 0;
+  int sm_count = 0;
+};
+
+enum OpKind { OP_CONV = 0, OP_SPPF = 1, OP_UPSAMPLE = 2 };
+
+struct Op {
+  OpKind kind;
+  uyd_conv conv{};
+  bool use_tc = false;
+  std::vector<unsigned char> w_host;  // packed weights (until finalize)
+  std::vector<float> b_host;
+  void *w_dev = nullptr;
+  float *b_dev = nullptr;
+  TcConv *tc = nullptr;
+  // sppf / upsample
+  int buf = -1, coff = 0, c = 0, out_buf = -1, out_coff = 0;
+};
+
+struct uyd_plan {
+  uyd_ctx *ctx = nullptr;
+  int max_batch = 0;
+  bool finalized = false;
+  std::vector<Buffer> bufs;
+  std::vector<Op> ops;
+  std::vector<int> heads, head_strides;
+  int reg_max = 16, nc = 0;
+  int in_c = 0, in_h = 0, in_w = 0;  // network input extent (derived from the first conv)
+  size_t bytes = 0;
+  void *arena = nullptr;
+};
+
+extern "C" int uyd_version(void) { return 100; }
+extern "C" const char *uyd_last_error(void) { return g_err; }
+
+extern "C" int uyd_create(int device, uyd_ctx **out) {
+  UYD_REQUIRE(out, UYD_E_ARG, "uyd_create: out is NULL");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  UYD_REQUIRE(e == cudaSuccess && count > 0, UYD_E_NOGPU, "uyd_create: no CUDA device (%s)", cudaGetErrorString(e));
+  UYD_REQUIRE(device >= 0 && device < count, UYD_E_ARG, "uyd_create: device %d out of range", device);
+  cudaDeviceProp prop;
+  UYD_CUDA(cudaGetDeviceProperties(&prop, device));
+  UYD_REQUIRE(prop.major == 10, UYD_E_NOGPU, "uyd_create: device %d is sm_%d%d; this library is sm_100a only", device,
+              prop.major, prop.minor);
+  UYD_CUDA(cudaSetDevice(device));
+  uyd_ctx *c = new uyd_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  *out = c;
+  return UYD_OK;
+}
+
+extern "C" int uyd_destroy(uyd_ctx *ctx) {
+  delete ctx;
+  return UYD_OK;
+}
+
+extern "C" int uyd_sm_count(const uyd_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
+
+extern "C" int uyd_plan_create(uyd_ctx *ctx, int max_batch, uyd_plan **out) {
+  UYD_REQUIRE(ctx && out && max_batch > 0, UYD_E_ARG, "uyd_plan_create: bad arguments");
+  uyd_plan *p = new uyd_plan();
+  p->ctx = ctx;
+  p->max_batch = max_batch;
+  *out = p;
+  return UYD_OK;
+}
+
+extern "C" int uyd_plan_destroy(uyd_plan *plan) {
+  if (!plan) return UYD_OK;
+  cudaSetDevice(plan->ctx->device);
+  for (Op &o : plan->ops) {
+    if (o.w_dev) cudaFree(o.w_dev);
+    if (o.b_dev) cudaFree(o.b_dev);
+    if (o.tc) tc_delete(o.tc);
+  }
+  if (plan->arena) cudaFree(plan->arena);
+  delete plan;
+  return UYD_OK;
+}
+
+extern "C" int uyd_plan_add_buffer(uyd_plan *plan, int h, int w, int c, int dtype, int *id) {
+  UYD_REQUIRE(plan && id && h > 0 && w > 0 && c > 0, UYD_E_ARG, "uyd_plan_add_buffer: bad arguments");
+  UYD_REQUIRE(!plan->finalized, UYD_E_STATE, "plan already finalized");
+  UYD_REQUIRE(dtype == UYD_BF16 || dtype == UYD_F32 || dtype == UYD_S8, UYD_E_ARG, "unknown dtype %d", dtype);
+  Buffer b;
+  b.h = h; b.w = w; b.c = c; b.dtype = dtype;
+  plan->bufs.push_back(b);
+  *id = (int)plan->bufs.size() - 1;
+  return UYD_OK;
+}
+
+static int check_slice(const uyd_plan *p, int buf, int coff, int c, const char *what) {
+  UYD_REQUIRE(buf >= 0 && buf < (int)p->bufs.size(), UYD_E_ARG, "%s: buffer id %d out of range", what, buf);
+  UYD_REQUIRE(coff >= 0 && c > 0 && coff + c <= p->bufs[buf].c, UYD_E_ARG, "%s: channel slice [%d,%d) exceeds buffer width %d",
+              what, coff, coff + c, p->bufs[buf].c);
+  return UYD_OK;
+}
+
+extern "C" int uyd_plan_add_conv(uyd_plan *plan, const uyd_conv *d, const float *weight, const float *bias) {
+  UYD_REQUIRE(plan && d && weight && bias, UYD_E_ARG, "uyd_plan_add_conv: NULL argument");
+  UYD_REQUIRE(!plan->finalized, UYD_E_STATE, "plan already finalized");
+  UYD_REQUIRE((d->k == 1 || d->k == 3) && (d->stride == 1 || d->stride == 2), UYD_E_UNSUPPORTED, "conv k=%d s=%d unsupported",
+              d->k, d->stride);
+  UYD_REQUIRE(!d->depthwise || d->cin == d->cout, UYD_E_ARG, "depthwise conv needs cin == cout");
+  int e;
+  int ih, iw, in_pitch = 0;
+  if (d->in_buf < 0) {
+    UYD_REQUIRE(plan->ops.empty(), UYD_E_ARG, "only the first op may read the network input");
+    const Buffer &ob = plan->bufs.at(d->out_buf);
+    ih = ob.h * d->stride; iw = ob.w * d->stride;
+    plan->in_c = d->cin; plan->in_h = ih; plan->in_w = iw;
+  } else {
+    if ((e = check_slice(plan, d->in_buf, d->in_coff, d->cin, "conv input"))) return e;
+    UYD_REQUIRE(plan->bufs[d->in_buf].dtype == UYD_BF16, UYD_E_UNSUPPORTED, "conv input must be bf16");
+    ih = plan->bufs[d->in_buf].h; iw = plan->bufs[d->in_buf].w; in_pitch = plan->bufs[d->in_buf].c;
+  }
+  if ((e = check_slice(plan, d->out_buf, d->out_coff, d->cout, "conv output"))) return e;
+  const Buffer &ob = plan->bufs[d->out_buf];
+  const int pad = d->k / 2;
+  UYD_REQUIRE(ob.h == (ih + 2 * pad - d->k) / d->stride + 1 && ob.w == (iw + 2 * pad - d->k) / d->stride + 1, UYD_E_ARG,
+              "conv output buffer is %dx%d but the conv produces %dx%d", ob.h, ob.w, (ih + 2 * pad - d->k) / d->stride + 1,
+              (iw + 2 * pad - d->k) / d->stride + 1);
+  UYD_REQUIRE(ob.dtype == UYD_BF16 || ob.dtype == UYD_F32, UYD_E_UNSUPPORTED, "conv output must be bf16 or fp32");
+  if (d->res_buf >= 0) {
+    if ((e = check_slice(plan, d->res_buf, d->res_coff, d->cout, "conv residual"))) return e;
+    UYD_REQUIRE(plan->bufs[d->res_buf].h == ob.h && plan->bufs[d->res_buf].w == ob.w && plan->bufs[d->res_buf].dtype == UYD_BF16,
+                UYD_E_ARG, "residual slice must match the output extent (bf16)");
+  }
+  Op op;
+  op.kind = OP_CONV;
+  op.conv = *d;
+  const bool f32 = ob.dtype == UYD_F32;
+  bool tc_ok = tc_supported(*d, in_pitch, d->in_coff, ob.c, d->out_coff, d->in_buf < 0);
+  if (tc_ok && !f32 && d->cout >= 16 && (ob.c % 8 || d->out_coff % 8)) tc_ok = false;
+  if (tc_ok && d->res_buf >= 0 && (plan->bufs[d->res_buf].c % 8 || d->res_coff % 8)) tc_ok = false;
+  const int min_c = env_int("UYD_TC_MIN_CIN", 16);
+  if (d->impl == UYD_IMPL_TC) {
+    UYD_REQUIRE(tc_ok, UYD_E_UNSUPPORTED, "conv %d->%d k%d s%d cannot run on the tensor-core path", d->cin, d->cout, d->k, d->stride);
+    op.use_tc = true;
+  } else if (d->impl == UYD_IMPL_AUTO) {
+    op.use_tc = tc_ok && d->cin >= min_c && env_int("UYD_DISABLE_TC", 0) == 0;
+  }
+  if (op.use_tc) {
+    op.w_host.resize(tc_weight_bytes(*d));
+    tc_pack_weights(*d, weight, op.w_host.data());
+  } else {
+    op.w_host.resize(direct_weight_bytes(*d));
+    direct_pack_weights(*d, weight, op.w_host.data());
+  }
+  op.b_host.assign(bias, bias + d->cout);
+  plan->ops.push_back(std::move(op));
+  return UYD_OK;
+}
+
+extern "C" int uyd_plan_add_sppf_pool(uyd_plan *plan, int buf, int coff, int c) {
+  UYD_REQUIRE(plan && !plan->finalized, UYD_E_STATE, "plan missing or finalized");
+  int e;
+  if ((e = check_slice(plan, buf, coff, 4 * c, "sppf"))) return e;
+  UYD_REQUIRE(plan->bufs[buf].dtype == UYD_BF16, UYD_E_UNSUPPORTED, "sppf works on bf16");
+  Op op;
+  op.kind = OP_SPPF;
+  op.buf = buf; op.coff = coff; op.c = c;
+  plan->ops.push_back(std::move(op));
+  return UYD_OK;
+}
+
+extern "C" int uyd_plan_add_upsample2x(uyd_plan *plan, int in_buf, int in_coff, int out_buf, int out_coff, int c) {
+  UYD_REQUIRE(plan && !plan->finalized, UYD_E_STATE, "plan missing or finalized");
+  int e;
+  if ((e = check_slice(plan, in_buf, in_coff, c, "upsample input"))) return e;
+  if ((e = check_slice(plan, out_buf, out_coff, c, "upsample output"))) return e;
+  const Buffer &a = plan->bufs[in_buf], &b = plan->bufs[out_buf];
+  UYD_REQUIRE(b.h == 2 * a.h && b.w == 2 * a.w && a.dtype == UYD_BF16 && b.dtype == UYD_BF16, UYD_E_ARG,
+              "upsample output must be 2x the input extent (bf16)");
+  Op op;
+  op.kind = OP_UPSAMPLE;
+  op.buf = in_buf; op.coff = in_coff; op.c = c; op.out_buf = out_buf; op.out_coff = out_coff;
+  plan->ops.push_back(std::move(op));
+  return UYD_OK;
+}
+
+extern "C" int uyd_plan_set_heads(uyd_plan *plan, const int *head_bufs, const int *strides, int nl, int reg_max, int nc) {
+  UYD_REQUIRE(plan && head_bufs && strides && nl > 0 && nl <= 8, UYD_E_ARG, "uyd_plan_set_heads: bad arguments");
+  for (int i = 0; i < nl; ++i) {
+    UYD_REQUIRE(head_bufs[i] >= 0 && head_bufs[i] < (int)plan->bufs.size(), UYD_E_ARG, "head buffer id out of range");
+    const Buffer &b = plan->bufs[head_bufs[i]];
+    UYD_REQUIRE(b.dtype == UYD_F32 && b.c == 4 * reg_max + nc, UYD_E_ARG, "head buffer %d must be fp32 with %d channels", i,
+                4 * reg_max + nc);
+  }
+  plan->heads.assign(head_bufs, head_bufs + nl);
+  plan->head_strides.assign(strides, strides + nl);
+  plan->reg_max = reg_max;
+  plan->nc = nc;
+  return UYD_OK;
+}
+
+static void *slice_ptr(const uyd_plan *p, int buf, int coff) {
+  const Buffer &b = p->bufs[buf];
+  return (char *)b.ptr + (size_t)coff * b.elem_bytes();
+}
+
+extern "C" int uyd_plan_finalize(uyd_plan *plan) {
+  UYD_REQUIRE(plan && !plan->finalized, UYD_E_STATE, "plan missing or already finalized");
+  UYD_CUDA(cudaSetDevice(plan->ctx->device));
+  size_t total = 0;
+  std::vector<size_t> offs;
+  for (Buffer &b : plan->bufs) {
+    offs.push_back(total);
+    total += (b.bytes_per_image() * plan->max_batch + 1023) & ~(size_t)1023;
+  }
+  UYD_CUDA(cudaMalloc(&plan->arena, total ? total : 1024));
+  UYD_CUDA(cudaMemset(plan->arena, 0, total ? total : 1024));
+  for (size_t i = 0; i < plan->bufs.size(); ++i) plan->bufs[i].ptr = (char *)plan->arena + offs[i];
+  plan->bytes = total;
+  const int halo_fallback = env_int("UYD_TC_NO_HALO", 0);
+  const int bo_mode = env_int("UYD_TC_BASE_OFFSET", 1);
+  const int stages = env_int("UYD_TC_STAGES", 0);
+  for (Op &o : plan->ops) {
+    if (o.kind != OP_CONV) continue;
+    UYD_CUDA(cudaMalloc(&o.w_dev, o.w_host.size()));
+    UYD_CUDA(cudaMemcpy(o.w_dev, o.w_host.data(), o.w_host.size(), cudaMemcpyHostToDevice));
+    UYD_CUDA(cudaMalloc((void **)&o.b_dev, o.b_host.size() * 4));
+    UYD_CUDA(cudaMemcpy(o.b_dev, o.b_host.data(), o.b_host.size() * 4, cudaMemcpyHostToDevice));
+    plan->bytes += o.w_host.size() + o.b_host.size() * 4;
+    o.w_host.clear();
+    o.w_host.shrink_to_fit();
+    if (o.use_tc) {
+      const uyd_conv &d = o.conv;
+      const Buffer &ib = plan->bufs[d.in_buf], &ob = plan->bufs[d.out_buf];
+      o.tc = tc_new();
+      const void *res = d.res_buf >= 0 ? slice_ptr(plan, d.res_buf, d.res_coff) : nullptr;
+      int e = tc_prepare(o.tc, d, slice_ptr(plan, d.in_buf, d.in_coff), ib.c, ib.h, ib.w, plan->max_batch,
+                         slice_ptr(plan, d.out_buf, d.out_coff), ob.c, ob.dtype == UYD_F32, res,
+                         d.res_buf >= 0 ? plan->bufs[d.res_buf].c : 0, o.w_dev, o.b_dev, halo_fallback ? 2 : -1, bo_mode, stages);
+      if (e) return e;
+    }
+  }
+  plan->finalized = true;
+  return UYD_OK;
+}
+
+extern "C" size_t uyd_plan_bytes(const uyd_plan *plan) { return plan ? plan->bytes : 0; }
+extern "C" int uyd_plan_num_launches(const uyd_plan *plan) { return plan ? (int)plan->ops.size() : 0; }
+
+extern "C" int uyd_plan_buffer_ptr(uyd_plan *plan, int id, void **ptr) {
+  UYD_REQUIRE(plan && ptr && plan->finalized, UYD_E_STATE, "plan not finalized");
+  UYD_REQUIRE(id >= 0 && id < (int)plan->bufs.size(), UYD_E_ARG, "buffer id %d out of range", id);
+  *ptr = plan->bufs[id].ptr;
+  return UYD_OK;
+}
+
+extern "C" int uyd_plan_run(uyd_plan *plan, const float *x, int batch, uyd_stream stream) {
+  UYD_REQUIRE(plan && plan->finalized, UYD_E_STATE, "plan not finalized");
+  UYD_REQUIRE(batch > 0 && batch <= plan->max_batch, UYD_E_ARG, "batch %d outside (0, %d]", batch, plan->max_batch);
+  cudaStream_t s = (cudaStream_t)stream;
+  for (const Op &o : plan->ops) {
+    int e = UYD_OK;
+    if (o.kind == OP_CONV) {
+      const uyd_conv &d = o.conv;
+      if (o.use_tc) {
+        e = tc_launch(o.tc, 0, batch, plan->ctx->sm_count, s);
+      } else {
+        const Buffer &ob = plan->bufs[d.out_buf];
+        ConvArgs a{};
+        a.n = batch;
+        if (d.in_buf < 0) {
+          UYD_REQUIRE(x, UYD_E_ARG, "uyd_plan_run: x is NULL");
+          a.in = x; a.ih = plan->in_h; a.iw = plan->in_w; a.in_pitch = 0; a.in_nchw_f32 = 1;
+        } else {
+          const Buffer &ib = plan->bufs[d.in_buf];
+          a.in = slice_ptr(plan, d.in_buf, d.in_coff); a.ih = ib.h; a.iw = ib.w; a.in_pitch = ib.c;
+        }
+        a.out = slice_ptr(plan, d.out_buf, d.out_coff);
+        a.oh = ob.h; a.ow = ob.w; a.out_pitch = ob.c; a.out_f32 = ob.dtype == UYD_F32;
+        if (d.res_buf >= 0) { a.res = slice_ptr(plan, d.res_buf, d.res_coff); a.res_pitch = plan->bufs[d.res_buf].c; }
+        a.w = o.w_dev; a.bias = o.b_dev; a.cin = d.cin; a.cout = d.cout; a.k = d.k; a.stride = d.stride; a.relu = d.relu;
+        e = direct_conv_launch(a, d.depthwise != 0, s);
+      }
+    } else if (o.kind == OP_SPPF) {
+      const Buffer &b = plan->bufs[o.buf];
+      e = sppf_pool_launch((__nv_bfloat16 *)slice_ptr(plan, o.buf, o.coff), batch, b.h, b.w, b.c, o.c, s);
+    } else {
+      const Buffer &a = plan->bufs[o.buf], &b = plan->bufs[o.out_buf];
+      e = upsample2x_launch((const __nv_bfloat16 *)slice_ptr(plan, o.buf, o.coff), a.c,
+                            (__nv_bfloat16 *)slice_ptr(plan, o.out_buf, o.out_coff), b.c, batch, a.h, a.w, o.c, s);
+    }
+    if (e) return e;
+  }
+  return UYD_OK;
+}
+
+extern "C" int uyd_plan_run_decode(uyd_plan *plan, float *y, int batch, uyd_stream stream) {
+  UYD_REQUIRE(plan && plan->finalized && !plan->heads.empty(), UYD_E_STATE, "plan has no heads / not finalized");
+  UYD_REQUIRE(y && batch > 0 && batch <= plan->max_batch, UYD_E_ARG, "uyd_plan_run_decode: bad arguments");
+  int a_total = 0;
+  for (int h : plan->heads) a_total += plan->bufs[h].h * plan->bufs[h].w;
+  int a_off = 0;
+  for (size_t i = 0; i < plan->heads.size(); ++i) {
+    const Buffer &b = plan->bufs[plan->heads[i]];
+    int e = decode_dfl_launch((const float *)b.ptr, batch, b.h, b.w, plan->reg_max, plan->nc, (float)plan->head_strides[i], y,
+                              a_total, a_off, (cudaStream_t)stream);
+    if (e) return e;
+    a_off += b.h * b.w;
+  }
+  return UYD_OK;
+}
+
+extern "C" int uyd_plan_export_head_nchw(uyd_plan *plan, int level, float *out, int batch, uyd_stream stream) {
+  UYD_REQUIRE(plan && plan->finalized && level >= 0 && level < (int)plan->heads.size() && out, UYD_E_ARG,
+              "uyd_plan_export_head_nchw: bad arguments");
+  const Buffer &b = plan->bufs[plan->heads[level]];
+  return nhwc_to_nchw_f32_launch((const float *)b.ptr, out, batch, b.h, b.w, b.c, (cudaStream_t)stream);
+}
+
+extern "C" int uyd_memcpy_d2d(void *dst, const void *src, size_t bytes, uyd_stream stream) {
+  UYD_REQUIRE(dst && src, UYD_E_ARG, "uyd_memcpy_d2d: NULL pointer");
+  UYD_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return UYD_OK;
+}

@@ -1,0 +1,80 @@
+// Shared host/device helpers for libuyd (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/uyd.h"
+
+namespace uyd {
+
+void set_error(const char *fmt, ...);
+
+#define UYD_CUDA(expr)                                                             \
+  do {                                                                             \
+    cudaError_t _e = (expr);                                                       \
+    if (_e != cudaSuccess) {                                                       \
+      uyd::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return (int)_e;                                                              \
+    }                                                                              \
+  } while (0)
+
+#define UYD_REQUIRE(cond, code, ...)   \
+  do {                                 \
+    if (!(cond)) {                     \
+      uyd::set_error(__VA_ARGS__);     \
+      return (code);                   \
+    }                                  \
+  } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------------------
+// Plan-level data structures shared by the kernel translation units.
+// ---------------------------------------------------------------------------------------
+struct Buffer {
+  int h = 0, w = 0, c = 0, dtype = UYD_BF16;
+  void *ptr = nullptr;
+  size_t elem_bytes() const { return dtype == UYD_F32 ? 4 : (dtype == UYD_S8 ? 1 : 2); }
+  size_t bytes_per_image() const { return (size_t)h * w * c * elem_bytes(); }
+};
+
+// Arguments every convolution kernel understands (device pointers already offset to the
+// first image; pitches in elements).
+struct ConvArgs {
+  const void *in;       // NHWC bf16 slice base (or NCHW fp32 network input)
+  void *out;            // NHWC slice base (bf16 or fp32)
+  const void *res;      // residual slice base or nullptr (bf16)
+  const void *w;        // packed weights (layout depends on kernel family)
+  const float *bias;    // [cout]
+  int n, ih, iw, oh, ow;
+  int cin, cout;
+  int in_pitch, out_pitch, res_pitch;
+  int k, stride, relu, out_f32, in_nchw_f32;
+};
+
+struct ctx_impl;  // defined in api.cu
+
+// ---- kernel family entry points (each in its own .cu) ----------------------------------
+// conv_direct.cu
+size_t direct_weight_bytes(const uyd_conv &d);
+void direct_pack_weights(const uyd_conv &d, const float *w, void *dst_host);
+int direct_conv_launch(const ConvArgs &a, bool depthwise, cudaStream_t s);
+
+// pool_upsample.cu
+int sppf_pool_launch(__nv_bfloat16 *base, int n, int h, int w, int pitch, int c, cudaStream_t s);
+int upsample2x_launch(const __nv_bfloat16 *in, int in_pitch, __nv_bfloat16 *out, int out_pitch, int n,
+                      int ih, int iw, int c, cudaStream_t s);
+int nhwc_to_nchw_f32_launch(const float *in, float *out, int n, int h, int w, int c, cudaStream_t s);
+
+// decode.cu
+int decode_dfl_launch(const float *head, int batch, int h, int w, int reg_max, int nc, float stride,
+                      float *y, int a_total, int a_off, cudaStream_t s);
+
+}  // namespace uyd

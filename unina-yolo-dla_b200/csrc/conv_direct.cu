@@ -1,0 +1,294 @@
+// CUDA-core direct convolution (NHWC bf16, fp32 accumulate).
+//
+// Role: (1) the tiny-channel layers of the C3k interiors (C = 4/8/16) and the 3-channel
+// stem, which cannot feed tcgen05 (N >= 16, K % 16 == 0); (2) the depth-wise 3x3 convs of
+// the Detect cls branch; (3) the on-device cross-check for the tensor-core kernels.
+// Arithmetic follows ConvBlock.forward (model.py:49-50) / Ultralytics Conv with BN folded:
+//   out = [res +] relu(sum_{tap,ci} x * w + bias)
+// One thread = one output pixel x CO_T output channels.
+#include "common.cuh"
+
+namespace uyd {
+
+namespace {
+
+constexpr int kThreads = 128;
+constexpr size_t kSmemWeightLimit = 96 * 1024;
+
+__device__ __forceinline__ float bf2f(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <int V>
+struct Vec;
+template <>
+struct Vec<8> { using T = uint4; };
+template <>
+struct Vec<4> { using T = uint2; };
+
+template <int V>
+__device__ __forceinline__ void load_bf16(const __nv_bfloat16 *p, float (&x)[V]) {
+  typename Vec<V>::T raw = *reinterpret_cast<const typename Vec<V>::T *>(p);
+  const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&raw);
+#pragma unroll
+  for (int i = 0; i < V / 2; ++i) {
+    float2 f = __bfloat1622float2(h[i]);
+    x[2 * i] = f.x;
+    x[2 * i + 1] = f.y;
+  }
+}
+
+// weights: bf16 [tap][ci][co]
+template <int CO_T, int IN_VEC, bool W_SMEM>
+__global__ void __launch_bounds__(kThreads) conv_direct_kernel(ConvArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const __nv_bfloat16 *wg = reinterpret_cast<const __nv_bfloat16 *>(a.w);
+  const int taps = a.k * a.k;
+  if (W_SMEM) {
+    __nv_bfloat16 *ws = reinterpret_cast<__nv_bfloat16 *>(smem_raw);
+    const int total = taps * a.cin * a.cout;
+    for (int i = threadIdx.x; i < total; i += kThreads) ws[i] = wg[i];
+    __syncthreads();
+    wg = ws;
+  }
+  const long long npix = (long long)a.n * a.oh * a.ow;
+  const long long p = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (p >= npix) return;
+  const int co0 = blockIdx.y * CO_T;
+  const int ox = (int)(p % a.ow);
+  const int oy = (int)((p / a.ow) % a.oh);
+  const int n = (int)(p / ((long long)a.ow * a.oh));
+  const int pad = a.k / 2;
+
+  float acc[CO_T];
+#pragma unroll
+  for (int i = 0; i < CO_T; ++i) acc[i] = 0.f;
+
+  const __nv_bfloat16 *in = reinterpret_cast<const __nv_bfloat16 *>(a.in);
+  for (int ky = 0; ky < a.k; ++ky) {
+    const int iy = oy * a.stride + ky - pad;
+    if (iy < 0 || iy >= a.ih) continue;
+    for (int kx = 0; kx < a.k; ++kx) {
+      const int ix = ox * a.stride + kx - pad;
+      if (ix < 0 || ix >= a.iw) continue;
+      const __nv_bfloat16 *px = in + (((long long)n * a.ih + iy) * a.iw + ix) * a.in_pitch;
+      const __nv_bfloat16 *wt = wg + (size_t)(ky * a.k + kx) * a.cin * a.cout + co0;
+      for (int ci = 0; ci < a.cin; ci += IN_VEC) {
+        float x[IN_VEC];
+        load_bf16<IN_VEC>(px + ci, x);
+#pragma unroll
+        for (int v = 0; v < IN_VEC; ++v) {
+          const __nv_bfloat16 *wr = wt + (size_t)(ci + v) * a.cout;
+          if (CO_T >= 8) {
+#pragma unroll
+            for (int c8 = 0; c8 < CO_T; c8 += 8) {
+              float wv[8];
+              load_bf16<8>(wr + c8, wv);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[c8 + j] = fmaf(x[v], wv[j], acc[c8 + j]);
+            }
+          } else {
+            float wv[4];
+            load_bf16<4>(wr, wv);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j] = fmaf(x[v], wv[j], acc[j]);
+          }
+        }
+      }
+    }
+  }
+
+  const long long opix = ((long long)n * a.oh + oy) * a.ow + ox;
+  float r[CO_T];
+#pragma unroll
+  for (int i = 0; i < CO_T; ++i) {
+    float v = acc[i] + a.bias[co0 + i];
+    if (a.relu) v = fmaxf(v, 0.f);
+    r[i] = v;
+  }
+  if (a.res) {
+    const __nv_bfloat16 *rp = reinterpret_cast<const __nv_bfloat16 *>(a.res) + opix * a.res_pitch + co0;
+#pragma unroll
+    for (int i = 0; i < CO_T; ++i) r[i] += bf2f(rp[i]);
+  }
+  if (a.out_f32) {
+    float *op = reinterpret_cast<float *>(a.out) + opix * a.out_pitch + co0;
+#pragma unroll
+    for (int i = 0; i < CO_T; ++i) op[i] = r[i];
+  } else {
+    __nv_bfloat16 *op = reinterpret_cast<__nv_bfloat16 *>(a.out) + opix * a.out_pitch + co0;
+    if (CO_T % 4 == 0 && (reinterpret_cast<uintptr_t>(op) & 7) == 0) {
+#pragma unroll
+      for (int i = 0; i < CO_T; i += 4) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(r[i], r[i + 1]);
+        __nv_bfloat162 hi = __floats2bfloat162_rn(r[i + 2], r[i + 3]);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t *>(&lo);
+        pk.y = *reinterpret_cast<uint32_t *>(&hi);
+        *reinterpret_cast<uint2 *>(op + i) = pk;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < CO_T; ++i) op[i] = __float2bfloat16_rn(r[i]);
+    }
+  }
+}
+
+// Stem: network input NCHW fp32 (the reference forward signature), Cin = 3.
+// weights bf16 [tap][ci][co]; one thread = one output pixel x CO_T channels.
+template <int CO_T>
+__global__ void __launch_bounds__(kThreads) conv_stem_nchw_kernel(ConvArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __nv_bfloat16 *ws = reinterpret_cast<__nv_bfloat16 *>(smem_raw);
+  const int total = a.k * a.k * a.cin * a.cout;
+  for (int i = threadIdx.x; i < total; i += kThreads) ws[i] = reinterpret_cast<const __nv_bfloat16 *>(a.w)[i];
+  __syncthreads();
+  const long long npix = (long long)a.n * a.oh * a.ow;
+  const long long p = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (p >= npix) return;
+  const int co0 = blockIdx.y * CO_T;
+  const int ox = (int)(p % a.ow);
+  const int oy = (int)((p / a.ow) % a.oh);
+  const int n = (int)(p / ((long long)a.ow * a.oh));
+  const int pad = a.k / 2;
+  const float *in = reinterpret_cast<const float *>(a.in);
+  float acc[CO_T];
+#pragma unroll
+  for (int i = 0; i < CO_T; ++i) acc[i] = 0.f;
+  for (int ky = 0; ky < a.k; ++ky) {
+    const int iy = oy * a.stride + ky - pad;
+    if (iy < 0 || iy >= a.ih) continue;
+    for (int kx = 0; kx < a.k; ++kx) {
+      const int ix = ox * a.stride + kx - pad;
+      if (ix < 0 || ix >= a.iw) continue;
+      for (int ci = 0; ci < a.cin; ++ci) {
+        // the frame stays fp32 (fp32 x bf16-weight -> fp32): no input rounding at all
+        const float x = in[(((long long)n * a.cin + ci) * a.ih + iy) * a.iw + ix];
+        const __nv_bfloat16 *wr = ws + (size_t)((ky * a.k + kx) * a.cin + ci) * a.cout + co0;
+#pragma unroll
+        for (int j = 0; j < CO_T; ++j) acc[j] = fmaf(x, bf2f(wr[j]), acc[j]);
+      }
+    }
+  }
+  const long long opix = ((long long)n * a.oh + oy) * a.ow + ox;
+  __nv_bfloat16 *op = reinterpret_cast<__nv_bfloat16 *>(a.out) + opix * a.out_pitch + co0;
+#pragma unroll
+  for (int i = 0; i < CO_T; ++i) {
+    float v = acc[i] + a.bias[co0 + i];
+    if (a.relu) v = fmaxf(v, 0.f);
+    op[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// Depth-wise 3x3 (Detect cv3 branch, DWConv): weights bf16 [tap][c]; thread = pixel x 8 ch.
+__global__ void __launch_bounds__(kThreads) conv_dw_kernel(ConvArgs a) {
+  const int cg = a.cin / 8;
+  const long long total = (long long)a.n * a.oh * a.ow * cg;
+  const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (t >= total) return;
+  const int c0 = (int)(t % cg) * 8;
+  const long long p = t / cg;
+  const int ox = (int)(p % a.ow);
+  const int oy = (int)((p / a.ow) % a.oh);
+  const int n = (int)(p / ((long long)a.ow * a.oh));
+  const int pad = a.k / 2;
+  const __nv_bfloat16 *in = reinterpret_cast<const __nv_bfloat16 *>(a.in);
+  const __nv_bfloat16 *w = reinterpret_cast<const __nv_bfloat16 *>(a.w);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int ky = 0; ky < a.k; ++ky) {
+    const int iy = oy * a.stride + ky - pad;
+    if (iy < 0 || iy >= a.ih) continue;
+    for (int kx = 0; kx < a.k; ++kx) {
+      const int ix = ox * a.stride + kx - pad;
+      if (ix < 0 || ix >= a.iw) continue;
+      float x[8], wv[8];
+      load_bf16<8>(in + (((long long)n * a.ih + iy) * a.iw + ix) * a.in_pitch + c0, x);
+      load_bf16<8>(w + (size_t)(ky * a.k + kx) * a.cin + c0, wv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(x[j], wv[j], acc[j]);
+    }
+  }
+  __nv_bfloat16 *op = reinterpret_cast<__nv_bfloat16 *>(a.out) + (((long long)n * a.oh + oy) * a.ow + ox) * a.out_pitch + c0;
+  uint4 pk;
+  uint32_t *pw = reinterpret_cast<uint32_t *>(&pk);
+#pragma unroll
+  for (int i = 0; i < 8; i += 2) {
+    float v0 = acc[i] + a.bias[c0 + i], v1 = acc[i + 1] + a.bias[c0 + i + 1];
+    if (a.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+    __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+    pw[i / 2] = *reinterpret_cast<uint32_t *>(&h);
+  }
+  *reinterpret_cast<uint4 *>(op) = pk;
+}
+
+template <int CO_T, int IN_VEC>
+int launch_generic(const ConvArgs &a, cudaStream_t s) {
+  const long long npix = (long long)a.n * a.oh * a.ow;
+  dim3 grid((unsigned)((npix + kThreads - 1) / kThreads), a.cout / CO_T);
+  const size_t wbytes = (size_t)a.k * a.k * a.cin * a.cout * 2;
+  if (wbytes <= kSmemWeightLimit) {
+    auto kern = conv_direct_kernel<CO_T, IN_VEC, true>;
+    if (wbytes > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemWeightLimit);
+    kern<<<grid, kThreads, wbytes, s>>>(a);
+  } else {
+    conv_direct_kernel<CO_T, IN_VEC, false><<<grid, kThreads, 0, s>>>(a);
+  }
+  return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+size_t direct_weight_bytes(const uyd_conv &d) {
+  return d.depthwise ? (size_t)d.k * d.k * d.cin * 2 : (size_t)d.k * d.k * d.cin * d.cout * 2;
+}
+
+// PyTorch [cout][cin/g][k][k] fp32 -> bf16 [tap][ci][co]  (depth-wise: [tap][c])
+void direct_pack_weights(const uyd_conv &d, const float *w, void *dst_host) {
+  __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(dst_host);
+  const int taps = d.k * d.k;
+  if (d.depthwise) {
+    for (int t = 0; t < taps; ++t)
+      for (int c = 0; c < d.cin; ++c) o[(size_t)t * d.cin + c] = __float2bfloat16_rn(w[(size_t)c * taps + t]);
+    return;
+  }
+  for (int t = 0; t < taps; ++t)
+    for (int ci = 0; ci < d.cin; ++ci)
+      for (int co = 0; co < d.cout; ++co)
+        o[((size_t)t * d.cin + ci) * d.cout + co] = __float2bfloat16_rn(w[((size_t)co * d.cin + ci) * taps + t]);
+}
+
+int direct_conv_launch(const ConvArgs &a, bool depthwise, cudaStream_t s) {
+  if (depthwise) {
+    UYD_REQUIRE(a.cin % 8 == 0 && a.in_pitch % 8 == 0 && a.out_pitch % 8 == 0 && !a.out_f32 && !a.res &&
+                    (reinterpret_cast<uintptr_t>(a.in) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0,
+                UYD_E_UNSUPPORTED, "depthwise conv needs C %% 8 == 0 and 16-byte aligned slices");
+    const long long total = (long long)a.n * a.oh * a.ow * (a.cin / 8);
+    conv_dw_kernel<<<(unsigned)((total + kThreads - 1) / kThreads), kThreads, 0, s>>>(a);
+    return (int)cudaGetLastError();
+  }
+  if (a.in_nchw_f32) {
+    UYD_REQUIRE(!a.out_f32 && !a.res, UYD_E_UNSUPPORTED, "stem conv writes bf16 without residual");
+    const long long npix = (long long)a.n * a.oh * a.ow;
+    const size_t wbytes = (size_t)a.k * a.k * a.cin * a.cout * 2;
+    UYD_REQUIRE(wbytes <= 48 * 1024, UYD_E_UNSUPPORTED, "stem weights too large");
+    if (a.cout % 16 == 0) {
+      dim3 grid((unsigned)((npix + kThreads - 1) / kThreads), a.cout / 16);
+      conv_stem_nchw_kernel<16><<<grid, kThreads, wbytes, s>>>(a);
+    } else {
+      UYD_REQUIRE(a.cout % 4 == 0, UYD_E_UNSUPPORTED, "stem cout must be a multiple of 4");
+      dim3 grid((unsigned)((npix + kThreads - 1) / kThreads), a.cout / 4);
+      conv_stem_nchw_kernel<4><<<grid, kThreads, wbytes, s>>>(a);
+    }
+    return (int)cudaGetLastError();
+  }
+  UYD_REQUIRE(a.cin % 4 == 0 && a.cout % 4 == 0, UYD_E_UNSUPPORTED, "direct conv needs cin, cout %% 4 == 0 (got %d, %d)", a.cin, a.cout);
+  const bool in16 = a.cin % 8 == 0 && a.in_pitch % 8 == 0 && (reinterpret_cast<uintptr_t>(a.in) & 15) == 0;
+  UYD_REQUIRE(in16 || (a.in_pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(a.in) & 7) == 0), UYD_E_UNSUPPORTED,
+              "input slice must be 8-byte aligned");
+  // weight rows are read as 8-byte (CO_T=4) or 16-byte vectors
+  if (a.cout % 16 == 0) return in16 ? launch_generic<16, 8>(a, s) : launch_generic<16, 4>(a, s);
+  if (a.cout % 8 == 0) return in16 ? launch_generic<8, 8>(a, s) : launch_generic<8, 4>(a, s);
+  return in16 ? launch_generic<4, 8>(a, s) : launch_generic<4, 4>(a, s);
+}
+
+}  // namespace uyd

@@ -1,0 +1,541 @@
+// Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a), NHWC bf16, fp32 accumulate in
+// TMEM, TMA-staged activation and weight tiles.  Replaces the Conv+BN(folded)+ReLU layers the
+// reference runs through TensorRT / cuDNN (ConvBlock.forward model.py:49-50, Ultralytics Conv).
+//
+// GEMM view: D[M = 128 output pixels, N = Cout] += A[M, K] * B[N, K]^T, K = taps * Cin.
+// Both operands are K-major in shared memory in the canonical UMMA swizzled layout whose row
+// width equals one channel block (CB channels = 32/64/128 bytes -> SWIZZLE_32B/64B/128B).
+//
+// Three ways of forming A (all im2col-free, the activation tensor is only ever read by TMA):
+//   FLAT   (1x1)        : a tile is 128 consecutive pixels of the flattened [N*H*W, C] view;
+//                         one 2-D TMA box per channel block.
+//   HALO   (3x3, s = 1) : a tile is 16 rows x 8 columns of output pixels.  The (16+2) x (8+2)
+//                         input halo of one channel block is loaded ONCE (18 row TMAs, each row
+//                         padded to a 16-pixel pitch so every 8-pixel group stays inside one
+//                         swizzle atom); the nine filter taps are nine UMMA descriptors that
+//                         start at (r * pitch + s) pixels into that halo.  Activation bytes
+//                         cross L2->SMEM 1.4x instead of 9x.
+//   PERTAP (3x3, any s) : one TMA box per (channel block, tap); stride 2 uses the TMA
+//                         traversal stride.  Always swizzle-atom aligned; also the fallback
+//                         for HALO.
+//
+// Warp roles (192 threads, one persistent CTA per SM): warp 0 = TMA producer, warp 1 = TMEM
+// allocator + single-thread tcgen05.mma issuer, warps 2..5 = epilogue (tcgen05.ld -> bias ->
+// ReLU -> residual -> bf16/fp32 -> global).  Three mbarrier pipelines: smem full/empty,
+// TMEM full/empty (two accumulators), weights-resident.
+#include "common.cuh"
+
+namespace uyd {
+
+enum { TC_FLAT = 0, TC_HALO = 1, TC_PERTAP = 2 };
+
+struct TcParams {
+  int mode;
+  int H, W;              // output extent
+  int n0, nb;            // image range handled by this launch
+  int ncb, cb_bytes;     // channel blocks, bytes per block row (32/64/128)
+  int taps;              // 1 or 9
+  int stride;            // conv stride (PERTAP)
+  int N;                 // UMMA N (cout padded to a multiple of 16)
+  int cout;
+  int tiles_x, tiles_y;  // HALO / PERTAP tiling of one image
+  long long total_tiles;
+  int stages;
+  uint32_t blk_bytes;    // one A block in shared memory
+  uint32_t tx_bytes;     // bytes TMA delivers per A block
+  uint32_t w_bytes;      // resident weights
+  uint32_t sbo_a;        // stride between 8-row groups of A
+  uint32_t idesc;
+  uint32_t layout_type;  // UMMA smem-descriptor swizzle code
+  int base_offset_mode;  // HALO: 1 = descriptor base_offset = (addr >> 7) & 7, 0 = always 0
+  void *out;
+  int out_pitch, out_f32;
+  const __nv_bfloat16 *res;
+  int res_pitch;
+  const float *bias;
+  int relu;
+};
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kHaloRows = 18, kHaloPitch = 16, kTileH = 16, kTileW = 8;
+
+// ---- PTX wrappers ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it) {
+    if (it > (1u << 26)) {
+      printf("uyd conv_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(tm), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo, uint32_t layout_type, uint32_t base_offset) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;                   // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;                   // descriptor version (sm_100)
+  d |= (uint64_t)(base_offset & 7u) << 49;
+  d |= (uint64_t)(layout_type & 7u) << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in,
+                                                              const __grid_constant__ CUtensorMap tm_w, const TcParams p) {
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t raw = smem_u32(smem_dyn);
+  const uint32_t base = (raw + 1023u) & ~1023u;  // swizzle atoms need 1024-byte alignment
+  const uint32_t w_s = base;
+  const uint32_t a_s = base + ((p.w_bytes + 1023u) & ~1023u);
+  const uint32_t bar0 = a_s + (uint32_t)p.stages * p.blk_bytes;
+  // barrier map: full[stages] | empty[stages] | wfull | tfull[2] | tempty[2] | tmem slot
+  const uint32_t full0 = bar0, empty0 = bar0 + 8u * p.stages;
+  const uint32_t wfull = empty0 + 8u * p.stages;
+  const uint32_t tfull0 = wfull + 8, tempty0 = tfull0 + 16, slot = tempty0 + 16;
+  uint32_t *slot_ptr = reinterpret_cast<uint32_t *>(smem_dyn + (slot - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < 2u * p.N) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full0 + 8u * s, 1);
+      mbar_init(empty0 + 8u * s, 1);
+    }
+    mbar_init(wfull, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull0 + 8u * a, 1);
+      mbar_init(tempty0 + 8u * a, 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *slot_ptr;
+
+  const int blocks_per_tile = p.mode == TC_PERTAP ? p.ncb * p.taps : p.ncb;
+  const int taps_in_block = p.mode == TC_HALO ? p.taps : 1;
+  const int ksteps = p.cb_bytes / 32;
+  const int cb_elems = p.cb_bytes / 2;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      mbar_expect_tx(wfull, p.w_bytes);
+      const int nblk = p.ncb * p.taps;
+      for (int i = 0; i < nblk; ++i) tma_load_2d(w_s + (uint32_t)i * p.N * p.cb_bytes, &tm_w, wfull, 0, i * p.N);
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int n = 0, x0 = 0, y0 = 0;
+      if (p.mode != TC_FLAT) {
+        n = p.n0 + (int)(tile / tiles_per_img);
+        const int t = (int)(tile % tiles_per_img);
+        y0 = (t / p.tiles_x) * kTileH;
+        x0 = (t % p.tiles_x) * kTileW;
+      }
+      for (int j = 0; j < blocks_per_tile; ++j) {
+        mbar_wait(empty0 + 8u * stage, phase ^ 1u);
+        const uint32_t dst = a_s + (uint32_t)stage * p.blk_bytes;
+        const uint32_t fb = full0 + 8u * stage;
+        if (lane == 0) mbar_expect_tx(fb, p.tx_bytes);
+        __syncwarp();
+        if (p.mode == TC_FLAT) {
+          if (lane == 0) {
+            const long long row0 = ((long long)p.n0 * p.H * p.W) + tile * 128;
+            tma_load_2d(dst, &tm_in, fb, j * cb_elems, (int)row0);
+          }
+        } else if (p.mode == TC_HALO) {
+          if (lane < kHaloRows)
+            tma_load_4d(dst + (uint32_t)lane * kHaloPitch * p.cb_bytes, &tm_in, fb, j * cb_elems, x0 - 1, y0 - 1 + lane, n);
+        } else {
+          if (lane == 0) {
+            const int cb = j / p.taps, tap = j % p.taps;
+            const int r = tap / 3, s = tap % 3;
+            tma_load_4d(dst, &tm_in, fb, cb * cb_elems, x0 * p.stride + s - 1, y0 * p.stride + r - 1, n);
+          }
+        }
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    mbar_wait(wfull, 0);
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(tempty0 + 8u * acc, acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)acc * p.N;
+      for (int j = 0; j < blocks_per_tile; ++j) {
+        mbar_wait(full0 + 8u * stage, phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t ablk = a_s + (uint32_t)stage * p.blk_bytes;
+          for (int t = 0; t < taps_in_block; ++t) {
+            uint32_t a_tap = ablk, wblk;
+            if (p.mode == TC_HALO) {
+              const int r = t / 3, s = t % 3;
+              a_tap = ablk + (uint32_t)(r * kHaloPitch + s) * p.cb_bytes;
+              wblk = w_s + (uint32_t)(j * p.taps + t) * p.N * p.cb_bytes;
+            } else {
+              wblk = w_s + (uint32_t)j * p.N * p.cb_bytes;  // FLAT: j = cb ; PERTAP: j = cb*taps + tap
+            }
+            for (int k = 0; k < ksteps; ++k) {
+              const uint32_t aaddr = a_tap + 32u * k;
+              const uint32_t bo = p.base_offset_mode ? ((aaddr >> 7) & 7u) : 0u;
+              const uint64_t ad = make_desc(aaddr, p.sbo_a, p.layout_type, bo);
+              const uint64_t bd = make_desc(wblk + 32u * k, 8u * p.cb_bytes, p.layout_type, 0);
+              umma_bf16(d_tmem, ad, bd, p.idesc, (uint32_t)((j | t | k) != 0));
+            }
+          }
+          umma_commit(empty0 + 8u * stage);  // smem slot is free once these MMAs retire
+          if (j == blocks_per_tile - 1) umma_commit(tfull0 + 8u * acc);
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  } else {
+    // ================= epilogue =================
+    const int q = warp & 3;  // TMEM lane quarter this warp may touch
+    const int m = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      long long pix;  // flattened output pixel (n, oy, ox) or -1
+      if (p.mode == TC_FLAT) {
+        const long long row = tile * 128 + m;
+        pix = row < (long long)p.nb * p.H * p.W ? (long long)p.n0 * p.H * p.W + row : -1;
+      } else {
+        const int n = p.n0 + (int)(tile / tiles_per_img);
+        const int t = (int)(tile % tiles_per_img);
+        const int oy = (t / p.tiles_x) * kTileH + (m >> 3), ox = (t % p.tiles_x) * kTileW + (m & 7);
+        pix = (oy < p.H && ox < p.W) ? ((long long)n * p.H + oy) * p.W + ox : -1;
+      }
+      mbar_wait(tfull0 + 8u * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * p.N;
+      for (int c0 = 0; c0 < p.N; c0 += 16) {
+        float v[16];
+        tmem_ld16(taddr + c0, v);
+        if (pix >= 0 && c0 < p.cout) {
+          const int nvalid = min(16, p.cout - c0);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float x = v[i] + (i < nvalid ? p.bias[c0 + i] : 0.f);
+            if (p.relu) x = fmaxf(x, 0.f);
+            v[i] = x;
+          }
+          if (p.res) {
+            const __nv_bfloat16 *rp = p.res + pix * p.res_pitch + c0;
+            if (nvalid == 16) {
+              uint4 r0 = *reinterpret_cast<const uint4 *>(rp), r1 = *reinterpret_cast<const uint4 *>(rp + 8);
+              const __nv_bfloat162 *h0 = reinterpret_cast<const __nv_bfloat162 *>(&r0);
+              const __nv_bfloat162 *h1 = reinterpret_cast<const __nv_bfloat162 *>(&r1);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                float2 f0 = __bfloat1622float2(h0[i]), f1 = __bfloat1622float2(h1[i]);
+                v[2 * i] += f0.x; v[2 * i + 1] += f0.y; v[8 + 2 * i] += f1.x; v[8 + 2 * i + 1] += f1.y;
+              }
+            } else {
+              for (int i = 0; i < nvalid; ++i) v[i] += __bfloat162float(rp[i]);
+            }
+          }
+          if (p.out_f32) {
+            float *op = reinterpret_cast<float *>(p.out) + pix * p.out_pitch + c0;
+            if (nvalid == 16) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4 *>(op + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            } else {
+              for (int i = 0; i < nvalid; ++i) op[i] = v[i];
+            }
+          } else {
+            __nv_bfloat16 *op = reinterpret_cast<__nv_bfloat16 *>(p.out) + pix * p.out_pitch + c0;
+            if (nvalid == 16) {
+              uint4 o0, o1;
+              uint32_t *w0 = reinterpret_cast<uint32_t *>(&o0), *w1 = reinterpret_cast<uint32_t *>(&o1);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                __nv_bfloat162 a = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                __nv_bfloat162 b = __floats2bfloat162_rn(v[8 + 2 * i], v[8 + 2 * i + 1]);
+                w0[i] = *reinterpret_cast<uint32_t *>(&a);
+                w1[i] = *reinterpret_cast<uint32_t *>(&b);
+              }
+              *reinterpret_cast<uint4 *>(op) = o0;
+              *reinterpret_cast<uint4 *>(op + 8) = o1;
+            } else {
+              for (int i = 0; i < nvalid; ++i) op[i] = __float2bfloat16_rn(v[i]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty0 + 8u * acc);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+}  // namespace
+
+// ---- host side -----------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static CUtensorMapSwizzle swizzle_of(int cb_bytes) {
+  return cb_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : cb_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+}
+
+static int encode(CUtensorMap *tm, void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides_bytes,
+                  const cuuint32_t *box, const cuuint32_t *estr, int cb_bytes) {
+  EncodeTiledFn fn = get_encode();
+  UYD_REQUIRE(fn, UYD_E_NOGPU, "cuTensorMapEncodeTiled is not available (no CUDA driver)");
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, dims, strides_bytes, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_of(cb_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  UYD_REQUIRE(r == CUDA_SUCCESS, UYD_E_ARG, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank);
+  return UYD_OK;
+}
+
+struct TcConv {  // everything a launch needs, prepared once at plan finalize
+  CUtensorMap tm_in, tm_w;
+  TcParams p;
+  size_t smem;
+  void *w_dev = nullptr;
+};
+
+static int pick_cb(int cin) { return cin % 64 == 0 ? 64 : (cin % 32 == 0 ? 32 : (cin % 16 == 0 ? 16 : 0)); }
+
+bool tc_supported(const uyd_conv &d, int in_pitch, int in_coff, int out_pitch, int out_coff, bool in_is_network_input) {
+  if (in_is_network_input || d.depthwise) return false;
+  if (!(d.k == 1 || d.k == 3) || !(d.stride == 1 || d.stride == 2)) return false;
+  if (d.k == 1 && d.stride != 1) return false;
+  if (pick_cb(d.cin) == 0 || d.cout > 128 || d.cout < 4) return false;
+  if (in_pitch % 8 || in_coff % 8 || out_pitch % 4 || out_coff % 4) return false;
+  const int N = (d.cout + 15) / 16 * 16;
+  if ((size_t)d.cin * d.k * d.k * N * 2 > 150 * 1024) return false;
+  return true;
+}
+
+size_t tc_weight_bytes(const uyd_conv &d) {
+  const int N = (d.cout + 15) / 16 * 16;
+  return (size_t)d.cin * d.k * d.k * N * 2;
+}
+
+// PyTorch [cout][cin][k][k] fp32 -> bf16 [cb][tap][n (padded to N)][CB]
+void tc_pack_weights(const uyd_conv &d, const float *w, void *dst_host) {
+  const int CB = pick_cb(d.cin), ncb = d.cin / CB, taps = d.k * d.k, N = (d.cout + 15) / 16 * 16;
+  __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(dst_host);
+  for (int cb = 0; cb < ncb; ++cb)
+    for (int t = 0; t < taps; ++t)
+      for (int n = 0; n < N; ++n)
+        for (int c = 0; c < CB; ++c) {
+          const float v = n < d.cout ? w[((size_t)n * d.cin + cb * CB + c) * taps + t] : 0.f;
+          o[(((size_t)cb * taps + t) * N + n) * CB + c] = __float2bfloat16_rn(v);
+        }
+}
+
+// mode_override: -1 auto, else TC_*.  in_base/out_base/res_base: slice bases of image 0.
+int tc_prepare(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int ih, int iw, int max_batch, void *out_base,
+               int out_pitch, int out_f32, const void *res_base, int res_pitch, void *w_dev, const float *bias_dev,
+               int mode_override, int base_offset_mode, int stages_override) {
+  TcParams &p = tc->p;
+  memset(&p, 0, sizeof(p));
+  const int CB = pick_cb(d.cin);
+  UYD_REQUIRE(CB, UYD_E_UNSUPPORTED, "conv_tc: cin %d is not a multiple of 16", d.cin);
+  p.cb_bytes = CB * 2;
+  p.ncb = d.cin / CB;
+  p.taps = d.k * d.k;
+  p.stride = d.stride;
+  p.N = (d.cout + 15) / 16 * 16;
+  p.cout = d.cout;
+  p.H = d.k == 1 ? ih : (ih + 2 * 1 - 3) / d.stride + 1;
+  p.W = d.k == 1 ? iw : (iw + 2 * 1 - 3) / d.stride + 1;
+  p.mode = d.k == 1 ? TC_FLAT : (d.stride == 1 ? TC_HALO : TC_PERTAP);
+  if (mode_override >= 0 && d.k == 3) p.mode = mode_override;
+  UYD_REQUIRE(!(p.mode == TC_HALO && d.stride != 1), UYD_E_UNSUPPORTED, "conv_tc: HALO mode needs stride 1");
+  p.base_offset_mode = base_offset_mode;
+  p.layout_type = p.cb_bytes == 128 ? 2u : (p.cb_bytes == 64 ? 4u : 6u);
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  p.w_bytes = (uint32_t)tc_weight_bytes(d);
+  p.tiles_x = ceil_div(p.W, kTileW);
+  p.tiles_y = ceil_div(p.H, kTileH);
+  if (p.mode == TC_HALO) {
+    p.blk_bytes = (uint32_t)kHaloRows * kHaloPitch * p.cb_bytes;
+    p.tx_bytes = (uint32_t)kHaloRows * (kTileW + 2) * p.cb_bytes;
+    p.sbo_a = (uint32_t)kHaloPitch * p.cb_bytes;
+  } else {
+    p.blk_bytes = 128u * p.cb_bytes;
+    p.tx_bytes = p.blk_bytes;
+    p.sbo_a = 8u * p.cb_bytes;
+  }
+  // blocks must keep 1024-byte alignment so every swizzle mode stays atom-aligned
+  p.blk_bytes = (p.blk_bytes + 1023u) & ~1023u;
+  const size_t budget = 227 * 1024 - 1024 - 256;
+  const size_t wres = (p.w_bytes + 1023u) & ~1023u;
+  UYD_REQUIRE(wres + 2 * (size_t)p.blk_bytes <= budget, UYD_E_UNSUPPORTED, "conv_tc: weights (%u B) leave no room for 2 stages",
+              p.w_bytes);
+  int stages = (int)((budget - wres) / p.blk_bytes);
+  const int want = p.mode == TC_HALO ? 4 : 12;
+  if (stages > want) stages = want;
+  if (stages_override > 0 && stages_override < stages) stages = stages_override;
+  p.stages = stages;
+  tc->smem = 1024 + wres + (size_t)stages * p.blk_bytes + 256;
+  p.out = out_base;
+  p.out_pitch = out_pitch;
+  p.out_f32 = out_f32;
+  p.res = reinterpret_cast<const __nv_bfloat16 *>(res_base);
+  p.res_pitch = res_pitch;
+  p.bias = bias_dev;
+  p.relu = d.relu;
+  tc->w_dev = w_dev;
+
+  const cuuint32_t one4[4] = {1, 1, 1, 1};
+  {  // weights: [rows = ncb*taps*N][CB]
+    const cuuint64_t dims[2] = {(cuuint64_t)CB, (cuuint64_t)p.ncb * p.taps * p.N};
+    const cuuint64_t str[1] = {(cuuint64_t)p.cb_bytes};
+    const cuuint32_t box[2] = {(cuuint32_t)CB, (cuuint32_t)p.N};
+    int e = encode(&tc->tm_w, w_dev, 2, dims, str, box, one4, p.cb_bytes);
+    if (e) return e;
+  }
+  if (p.mode == TC_FLAT) {
+    const cuuint64_t dims[2] = {(cuuint64_t)d.cin, (cuuint64_t)max_batch * ih * iw};
+    const cuuint64_t str[1] = {(cuuint64_t)in_pitch * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)CB, 128};
+    int e = encode(&tc->tm_in, in_base, 2, dims, str, box, one4, p.cb_bytes);
+    if (e) return e;
+  } else {
+    const cuuint64_t dims[4] = {(cuuint64_t)d.cin, (cuuint64_t)iw, (cuuint64_t)ih, (cuuint64_t)max_batch};
+    const cuuint64_t str[3] = {(cuuint64_t)in_pitch * 2, (cuuint64_t)iw * in_pitch * 2, (cuuint64_t)ih * iw * in_pitch * 2};
+    if (p.mode == TC_HALO) {
+      const cuuint32_t box[4] = {(cuuint32_t)CB, (cuuint32_t)(kTileW + 2), 1, 1};
+      int e = encode(&tc->tm_in, in_base, 4, dims, str, box, one4, p.cb_bytes);
+      if (e) return e;
+    } else {
+      const cuuint32_t s = (cuuint32_t)d.stride;
+      const cuuint32_t box[4] = {(cuuint32_t)CB, (cuuint32_t)kTileW * s, (cuuint32_t)kTileH * s, 1};
+      const cuuint32_t estr[4] = {1, s, s, 1};
+      int e = encode(&tc->tm_in, in_base, 4, dims, str, box, estr, p.cb_bytes);
+      if (e) return e;
+    }
+  }
+  static bool attr = false;
+  if (!attr) {
+    UYD_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  return UYD_OK;
+}
+
+int tc_launch(const TcConv *tc, int n0, int nb, int sm_count, cudaStream_t s) {
+  TcParams p = tc->p;
+  p.n0 = n0;
+  p.nb = nb;
+  p.total_tiles = p.mode == TC_FLAT ? ((long long)nb * p.H * p.W + 127) / 128 : (long long)nb * p.tiles_x * p.tiles_y;
+  if (p.total_tiles == 0) return UYD_OK;
+  const unsigned grid = (unsigned)(p.total_tiles < sm_count ? p.total_tiles : sm_count);
+  conv_tc_kernel<<<grid, kThreads, tc->smem, s>>>(tc->tm_in, tc->tm_w, p);
+  return (int)cudaGetLastError();
+}
+
+TcConv *tc_new() { return new TcConv(); }
+void tc_delete(TcConv *t) { delete t; }
+const char *tc_mode_name(const TcConv *t) { return t->p.mode == TC_FLAT ? "flat" : (t->p.mode == TC_HALO ? "halo" : "pertap"); }
+
+}  // namespace uyd

@@ -1,0 +1,421 @@
+// Class-aware NMS, bit-exact with the CPU statement.
+//
+// Pipeline (Ultralytics non_max_suppression + torchvision.ops.nms, SURVEY.md A.3/A.4;
+// reference call sites train.py:396-405, eval.py:32):
+//   1. nms_key_kernel     : per anchor best class / score, conf filter, 64-bit sort key
+//                           (image | ~score bits | anchor) -> ties resolve to the lower anchor
+//   2. cub radix sort     : one sort over the whole batch; image segments come out contiguous,
+//                           each in stable score-descending order
+//   3. nms_gather_kernel  : top max_nms candidates per image -> xyxy, class-offset boxes
+//   4. nms_greedy_kernel  : one CTA per image.  Candidates are consumed in chunks of 512:
+//                           (a) every candidate is tested against the boxes kept so far,
+//                           (b) survivors are compacted with warp ballots,
+//                           (c) a 512x512 IoU bitmask among survivors is built in shared memory,
+//                           (d) one warp resolves the chunk serially (suppression words are
+//                               OR-ed across lanes), appending to the kept list.
+//                           Stops after max_det boxes -- greedy kept order is score order, so the
+//                           first max_det kept boxes never depend on later candidates.
+//   5. emit kernel        : rows (x1,y1,x2,y2,conf,cls) / detection records in kept order.
+// All IoU arithmetic uses explicit round-to-nearest fp32 intrinsics in the operand order of
+// the CPU code it mirrors.  Two IoU policies:
+//   TV  : torchvision nms_kernel_impl on class-offset boxes; the fp32 IoU is compared against
+//         the largest float <= the double threshold (== torchvision's float-vs-double compare).
+//   HPP : the reference's own postprocess.hpp:28-67 (same class only, early-out on empty
+//         intersection, float threshold).
+#include <cub/cub.cuh>
+
+#include <cmath>
+
+#include "common.cuh"
+
+namespace uyd {
+namespace {
+
+constexpr int kChunk = 512;
+constexpr int kGreedyThreads = 512;
+constexpr int kMaxDetCap = 1024;
+constexpr int kAnchorBits = 22;
+constexpr int kScoreShift = kAnchorBits;
+constexpr int kImageShift = kAnchorBits + 32;
+constexpr uint64_t kInvalidKey = ~0ull;
+
+size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct Carver {
+  char *base;
+  size_t off = 0;
+  explicit Carver(void *ws) : base((char *)ws) {}
+  template <class T>
+  T *take(size_t count) {
+    T *p = base ? (T *)(base + off) : nullptr;
+    off += align_up(count * sizeof(T));
+    return p;
+  }
+};
+
+struct Layout {  // carve-up of the caller's workspace for uyd_nms
+  uint64_t *keys_in, *keys_out;
+  int *count, *offset;  // [batch]
+  float4 *box, *boxoff; // [batch][cap]
+  float *conf;
+  int *cls, *anchor;
+  int *kept_rank;       // [batch][kMaxDetCap]
+  void *cub_tmp;
+  size_t cub_bytes, total;
+};
+
+Layout carve(void *ws, int batch, int anchors) {
+  Layout L;
+  Carver c(ws);
+  const size_t n = (size_t)batch * anchors;
+  L.keys_in = c.take<uint64_t>(n);
+  L.keys_out = c.take<uint64_t>(n);
+  L.count = c.take<int>(batch);
+  L.offset = c.take<int>(batch);
+  L.box = c.take<float4>(n);
+  L.boxoff = c.take<float4>(n);
+  L.conf = c.take<float>(n);
+  L.cls = c.take<int>(n);
+  L.anchor = c.take<int>(n);
+  L.kept_rank = c.take<int>((size_t)batch * kMaxDetCap);
+  L.cub_bytes = 0;
+  cub::DeviceRadixSort::SortKeys(nullptr, L.cub_bytes, (uint64_t *)nullptr, (uint64_t *)nullptr, (int)n, 0, 64);
+  L.cub_tmp = c.take<char>(L.cub_bytes);
+  L.total = c.off;
+  return L;
+}
+
+// y: [batch, 4+nc, A].  One thread per (image, anchor).
+__global__ void __launch_bounds__(256) nms_key_kernel(const float *__restrict__ y, int batch, int nc, int A, float thr,
+                                                      uint64_t *__restrict__ keys, int *__restrict__ count) {
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long total = (long long)batch * A;
+  bool ok = false;
+  int b = 0;
+  if (t < total) {
+    b = (int)(t / A);
+    const int a = (int)(t % A);
+    const float *p = y + ((long long)b * (4 + nc) + 4) * A + a;
+    float best = p[0];
+    for (int c = 1; c < nc; ++c) {
+      const float v = p[(long long)c * A];
+      if (v > best) best = v;  // first maximum wins
+    }
+    ok = best > thr;
+    keys[t] = ok ? (((uint64_t)b << kImageShift) | ((uint64_t)(~__float_as_uint(best)) << kScoreShift) | (uint64_t)a)
+                 : kInvalidKey;
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, ok);
+  if (m) {  // per-image counts: one atomic per warp (plus stragglers across an image boundary)
+    const int lane = threadIdx.x & 31;
+    const int b0 = __shfl_sync(0xffffffffu, b, __ffs(m) - 1);
+    const unsigned same = __ballot_sync(0xffffffffu, ok && b == b0);
+    if (lane == __ffs(same) - 1) atomicAdd(&count[b0], __popc(same));
+    if (ok && b != b0) atomicAdd(&count[b], 1);
+  }
+}
+
+__global__ void nms_scan_kernel(const int *count, int *offset, int batch) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int acc = 0;
+    for (int b = 0; b < batch; ++b) {
+      offset[b] = acc;
+      acc += count[b];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) nms_gather_kernel(const float *__restrict__ y, int nc, int A, int max_nms,
+                                                         float max_wh, const uint64_t *__restrict__ keys, Layout L) {
+  const int b = blockIdx.y;
+  const int r = blockIdx.x * 256 + threadIdx.x;
+  const int n = min(L.count[b], max_nms);
+  if (r >= n) return;
+  const uint64_t key = keys[(long long)L.offset[b] + r];
+  const int a = (int)(key & ((1ull << kAnchorBits) - 1));
+  const float *p = y + (long long)b * (4 + nc) * A + a;
+  const float cx = p[0], cy = p[A], w = p[2ll * A], h = p[3ll * A];
+  const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);  // == w / 2 exactly
+  float4 bx;
+  bx.x = __fsub_rn(cx, hw); bx.y = __fsub_rn(cy, hh); bx.z = __fadd_rn(cx, hw); bx.w = __fadd_rn(cy, hh);
+  float best = p[4ll * A];
+  int j = 0;
+  for (int c = 1; c < nc; ++c) {
+    const float v = p[(long long)(4 + c) * A];
+    if (v > best) { best = v; j = c; }
+  }
+  const float off = __fmul_rn((float)j, max_wh);
+  float4 bo;
+  bo.x = __fadd_rn(bx.x, off); bo.y = __fadd_rn(bx.y, off); bo.z = __fadd_rn(bx.z, off); bo.w = __fadd_rn(bx.w, off);
+  const long long o = (long long)b * A + r;
+  L.box[o] = bx; L.boxoff[o] = bo; L.conf[o] = best; L.cls[o] = j; L.anchor[o] = a;
+}
+
+__device__ __forceinline__ float box_area(const float4 &b) { return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y)); }
+
+template <bool HPP>
+__device__ __forceinline__ bool suppresses(const float4 &a, float aa, int ca, const float4 &b, float ab, int cb, float thr) {
+  if (HPP) {  // postprocess.hpp:28-39,58-62
+    if (ca != cb) return false;
+    const float ix1 = fmaxf(a.x, b.x), iy1 = fmaxf(a.y, b.y), ix2 = fminf(a.z, b.z), iy2 = fminf(a.w, b.w);
+    if (ix1 >= ix2 || iy1 >= iy2) return 0.0f > thr;
+    const float inter = __fmul_rn(__fsub_rn(ix2, ix1), __fsub_rn(iy2, iy1));
+    return __fdiv_rn(inter, __fsub_rn(__fadd_rn(aa, ab), inter)) > thr;
+  }
+  // torchvision nms_kernel_impl operand order
+  const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y), xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+  const float w = fmaxf(0.f, __fsub_rn(xx2, xx1)), h = fmaxf(0.f, __fsub_rn(yy2, yy1));
+  const float inter = __fmul_rn(w, h);
+  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(aa, ab), inter)) > thr;
+}
+
+// boxes/cls: candidates of image b at [b * cand_stride, ...), in processing order.
+// n_ptr[b] candidates (clamped to n_cap).  Writes kept ranks (<= max_det) and their number.
+template <bool HPP>
+__global__ void __launch_bounds__(kGreedyThreads) nms_greedy_kernel(const float4 *__restrict__ boxes,
+                                                                    const int *__restrict__ cls, long long cand_stride,
+                                                                    const int *__restrict__ n_ptr, int n_cap, int max_det,
+                                                                    float thr, int *__restrict__ kept_rank,
+                                                                    int *__restrict__ out_count) {
+  extern __shared__ __align__(16) unsigned char nms_smem[];
+  float4 *kbox = reinterpret_cast<float4 *>(nms_smem);      // [kMaxDetCap] kept boxes
+  float4 *abox = kbox + kMaxDetCap;                         // [kChunk] survivors of this chunk
+  float *karea = reinterpret_cast<float *>(abox + kChunk);  // [kMaxDetCap]
+  float *aarea = karea + kMaxDetCap;                        // [kChunk]
+  int *kcls = reinterpret_cast<int *>(aarea + kChunk);      // [kMaxDetCap]
+  int *acls = kcls + kMaxDetCap;                            // [kChunk]
+  int *ksrc = acls + kChunk;                                // [kMaxDetCap] rank of every kept box
+  int *asrc = ksrc + kMaxDetCap;                            // [kChunk] rank of each survivor
+  unsigned(*mask)[kChunk / 32] = reinterpret_cast<unsigned(*)[kChunk / 32]>(asrc + kChunk);
+  __shared__ int warp_cnt[kGreedyThreads / 32];
+  __shared__ int s_kept, s_alive;
+
+  const int b = blockIdx.x;
+  const int n = min(n_ptr[b], n_cap);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const float4 *cbox = boxes + (long long)b * cand_stride;
+  const int *ccls = cls + (long long)b * cand_stride;
+  if (tid == 0) s_kept = 0;
+  __syncthreads();
+
+  for (int c0 = 0; c0 < n; c0 += kChunk) {
+    const int kept = s_kept;
+    if (kept >= max_det) break;
+    // (a) test against the kept list
+    const int i = c0 + tid;
+    bool alive = i < n;
+    float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+    float ar = 0.f;
+    int cl = 0;
+    if (alive) {
+      bx = cbox[i];
+      cl = ccls[i];
+      ar = box_area(bx);
+      for (int k = 0; k < kept; ++k)
+        if (suppresses<HPP>(kbox[k], karea[k], kcls[k], bx, ar, cl, thr)) { alive = false; break; }
+    }
+    // (b) ordered compaction of survivors
+    const unsigned bal = __ballot_sync(0xffffffffu, alive);
+    if (lane == 0) warp_cnt[wid] = __popc(bal);
+    __syncthreads();
+    int base = 0;
+    for (int w2 = 0; w2 < wid; ++w2) base += warp_cnt[w2];
+    if (tid == kGreedyThreads - 1) s_alive = base + __popc(bal);
+    if (alive) {
+      const int slot = base + __popc(bal & ((1u << lane) - 1));
+      abox[slot] = bx; aarea[slot] = ar; acls[slot] = cl; asrc[slot] = i;
+    }
+    __syncthreads();
+    const int m = s_alive;
+    const int words = (m + 31) >> 5;
+    // (c) suppression bitmask among survivors (upper triangle)
+    for (int item = tid; item < m * words; item += kGreedyThreads) {
+      const int r = item / words, cw = item % words;
+      unsigned bits = 0;
+      if (cw * 32 + 31 > r) {
+        const float4 rb = abox[r];
+        const float ra = aarea[r];
+        const int rc = acls[r];
+        const int j0 = cw * 32;
+#pragma unroll 4
+        for (int jj = 0; jj < 32; ++jj) {
+          const int j = j0 + jj;
+          if (j > r && j < m && suppresses<HPP>(rb, ra, rc, abox[j], aarea[j], acls[j], thr)) bits |= 1u << jj;
+        }
+      }
+      mask[r][cw] = bits;
+    }
+    __syncthreads();
+    // (d) serial resolution by warp 0: lane l owns suppression word l
+    if (wid == 0) {
+      unsigned remv = 0;
+      int k = kept;
+      for (int r = 0; r < m && k < max_det; ++r) {
+        const unsigned wbits = __shfl_sync(0xffffffffu, remv, r >> 5);
+        if ((wbits >> (r & 31)) & 1u) continue;
+        if (lane == 0) {
+          kbox[k] = abox[r]; karea[k] = aarea[r]; kcls[k] = acls[r]; ksrc[k] = asrc[r];
+        }
+        ++k;
+        if (lane < words) remv |= mask[r][lane];
+      }
+      if (lane == 0) s_kept = k;
+    }
+    __syncthreads();
+  }
+  const int kept = s_kept;
+  for (int k = tid; k < kept; k += kGreedyThreads) kept_rank[(long long)b * kMaxDetCap + k] = ksrc[k];
+  if (tid == 0) out_count[b] = kept;
+}
+
+constexpr size_t kGreedySmem = (size_t)(kMaxDetCap + kChunk) * (16 + 4 + 4 + 4) + (size_t)kChunk * (kChunk / 32) * 4;
+
+template <bool HPP>
+int launch_greedy(const float4 *boxes, const int *cls, long long cand_stride, const int *n_ptr, int n_cap, int max_det,
+                  float thr, int *kept_rank, int *out_count, int batch, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    UYD_CUDA(cudaFuncSetAttribute(nms_greedy_kernel<HPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGreedySmem));
+    attr_set = true;
+  }
+  nms_greedy_kernel<HPP><<<batch, kGreedyThreads, kGreedySmem, s>>>(boxes, cls, cand_stride, n_ptr, n_cap, max_det, thr,
+                                                                   kept_rank, out_count);
+  return (int)cudaGetLastError();
+}
+
+__global__ void nms_emit_rows_kernel(Layout L, int A, int max_det, const int *__restrict__ out_count,
+                                     float *__restrict__ out_det, int *__restrict__ out_idx) {
+  const int b = blockIdx.x;
+  for (int k = threadIdx.x; k < out_count[b]; k += blockDim.x) {
+    const long long src = (long long)b * A + L.kept_rank[(long long)b * kMaxDetCap + k];
+    const float4 ob = L.box[src];
+    float *o = out_det + ((long long)b * max_det + k) * 6;
+    o[0] = ob.x; o[1] = ob.y; o[2] = ob.z; o[3] = ob.w; o[4] = L.conf[src]; o[5] = (float)L.cls[src];
+    if (out_idx) out_idx[(long long)b * max_det + k] = L.anchor[src];
+  }
+}
+
+// ---- detection-record variant (custom head, postprocess.hpp semantics) ----------------------
+struct DetLayout {
+  uint64_t *keys_in, *keys_out;
+  int *slot_in, *slot_out;
+  float4 *box;
+  int *cls;
+  int *kept_rank;
+  void *cub_tmp;
+  size_t cub_bytes, total;
+};
+
+DetLayout carve_det(void *ws, int cap) {
+  DetLayout L;
+  Carver c(ws);
+  L.keys_in = c.take<uint64_t>(cap);
+  L.keys_out = c.take<uint64_t>(cap);
+  L.slot_in = c.take<int>(cap);
+  L.slot_out = c.take<int>(cap);
+  L.box = c.take<float4>(cap);
+  L.cls = c.take<int>(cap);
+  L.kept_rank = c.take<int>(kMaxDetCap);
+  L.cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, L.cub_bytes, (uint64_t *)nullptr, (uint64_t *)nullptr, (int *)nullptr,
+                                  (int *)nullptr, cap, 0, 64);
+  L.cub_tmp = c.take<char>(L.cub_bytes);
+  L.total = c.off;
+  return L;
+}
+
+__global__ void det_key_kernel(const uyd_detection *dets, const int *cell_idx, const int *d_count, int cap, DetLayout L) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cap) return;
+  const int n = min(*d_count, cap);
+  L.slot_in[i] = i;
+  if (i < n) {
+    const uint32_t tie = cell_idx ? (uint32_t)cell_idx[i] : (uint32_t)i;
+    L.keys_in[i] = ((uint64_t)(~__float_as_uint(dets[i].confidence)) << 32) | tie;
+  } else {
+    L.keys_in[i] = kInvalidKey;
+  }
+}
+
+__global__ void det_gather_kernel(const uyd_detection *dets, const int *d_count, int cap, DetLayout L) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= min(*d_count, cap)) return;
+  const uyd_detection d = dets[L.slot_out[r]];
+  L.box[r] = make_float4(d.x1, d.y1, d.x2, d.y2);
+  L.cls[r] = d.class_id;
+}
+
+__global__ void det_emit_kernel(const uyd_detection *dets, DetLayout L, const int *out_count, uyd_detection *out) {
+  for (int k = threadIdx.x; k < *out_count; k += blockDim.x) {
+    uyd_detection d = dets[L.slot_out[L.kept_rank[k]]];
+    d.valid = 1;
+    out[k] = d;
+  }
+}
+
+}  // namespace
+}  // namespace uyd
+
+extern "C" size_t uyd_nms_workspace_bytes(int batch, int anchors) {
+  if (batch <= 0 || anchors <= 0) return 0;
+  return uyd::carve(nullptr, batch, anchors).total;
+}
+
+extern "C" int uyd_nms(uyd_ctx *ctx, const float *y, int batch, int nc, int anchors, float conf_thr, double iou_thr,
+                       int max_nms, int max_det, float max_wh, void *workspace, size_t workspace_bytes, float *out_det,
+                       int *out_idx, int *out_count, uyd_stream stream) {
+  using namespace uyd;
+  (void)ctx;
+  UYD_REQUIRE(y && workspace && out_det && out_count && batch > 0 && nc > 0 && anchors > 0, UYD_E_ARG, "uyd_nms: bad arguments");
+  UYD_REQUIRE(batch < (1 << 10) && anchors < (1 << kAnchorBits), UYD_E_UNSUPPORTED,
+              "uyd_nms: batch < 1024 and anchors < 4M per call");
+  UYD_REQUIRE(max_det > 0 && max_det <= kMaxDetCap, UYD_E_UNSUPPORTED, "uyd_nms: max_det <= %d", kMaxDetCap);
+  if (max_nms > anchors) max_nms = anchors;
+  UYD_REQUIRE(max_nms > 0, UYD_E_ARG, "uyd_nms: max_nms must be positive");
+  Layout L = carve(workspace, batch, anchors);
+  UYD_REQUIRE(L.total <= workspace_bytes, UYD_E_ARG, "uyd_nms: workspace too small (%zu < %zu)", workspace_bytes, L.total);
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long total = (long long)batch * anchors;
+  float thr_f = (float)iou_thr;  // largest float <= the double threshold
+  if ((double)thr_f > iou_thr) thr_f = nextafterf(thr_f, -INFINITY);
+
+  UYD_CUDA(cudaMemsetAsync(L.count, 0, (size_t)batch * 4, s));
+  nms_key_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(y, batch, nc, anchors, conf_thr, L.keys_in, L.count);
+  UYD_CUDA(cudaGetLastError());
+  nms_scan_kernel<<<1, 32, 0, s>>>(L.count, L.offset, batch);
+  size_t tmp = L.cub_bytes;
+  UYD_CUDA(cub::DeviceRadixSort::SortKeys(L.cub_tmp, tmp, L.keys_in, L.keys_out, (int)total, 0, 64, s));
+  dim3 ggrid((unsigned)ceil_div(max_nms, 256), (unsigned)batch);
+  nms_gather_kernel<<<ggrid, 256, 0, s>>>(y, nc, anchors, max_nms, max_wh, L.keys_out, L);
+  UYD_CUDA(cudaGetLastError());
+  int e = launch_greedy<false>(L.boxoff, L.cls, anchors, L.count, max_nms, max_det, thr_f, L.kept_rank, out_count, batch, s);
+  if (e) return e;
+  nms_emit_rows_kernel<<<batch, 128, 0, s>>>(L, anchors, max_det, out_count, out_det, out_idx);
+  UYD_CUDA(cudaGetLastError());
+  return UYD_OK;
+}
+
+extern "C" size_t uyd_nms_detections_workspace_bytes(int cap) { return cap > 0 ? uyd::carve_det(nullptr, cap).total : 0; }
+
+extern "C" int uyd_nms_detections(uyd_ctx *ctx, const uyd_detection *dets, const int *cell_idx, const int *d_count, int cap,
+                                  float iou_thr, void *workspace, size_t workspace_bytes, uyd_detection *out,
+                                  int *d_out_count, uyd_stream stream) {
+  using namespace uyd;
+  (void)ctx;
+  UYD_REQUIRE(dets && d_count && workspace && out && d_out_count && cap > 0, UYD_E_ARG, "uyd_nms_detections: bad arguments");
+  DetLayout L = carve_det(workspace, cap);
+  UYD_REQUIRE(L.total <= workspace_bytes, UYD_E_ARG, "uyd_nms_detections: workspace too small (%zu < %zu)", workspace_bytes,
+              L.total);
+  cudaStream_t s = (cudaStream_t)stream;
+  det_key_kernel<<<ceil_div(cap, 256), 256, 0, s>>>(dets, cell_idx, d_count, cap, L);
+  UYD_CUDA(cudaGetLastError());
+  size_t tmp = L.cub_bytes;
+  UYD_CUDA(cub::DeviceRadixSort::SortPairs(L.cub_tmp, tmp, L.keys_in, L.keys_out, L.slot_in, L.slot_out, cap, 0, 64, s));
+  det_gather_kernel<<<ceil_div(cap, 256), 256, 0, s>>>(dets, d_count, cap, L);
+  UYD_CUDA(cudaGetLastError());
+  int e = launch_greedy<true>(L.box, L.cls, cap, d_count, cap, kMaxDetCap, iou_thr, L.kept_rank, d_out_count, 1, s);
+  if (e) return e;
+  det_emit_kernel<<<1, 256, 0, s>>>(dets, L, d_out_count, out);
+  UYD_CUDA(cudaGetLastError());
+  return UYD_OK;
+}

@@ -1,0 +1,131 @@
+// Memory-bound helpers of the conv stack: SPPF max-pool cascade, nearest x2 upsample,
+// NHWC -> NCHW export of the raw heads.
+#include "common.cuh"
+
+namespace uyd {
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ uint4 max8(uint4 a, uint4 b) {
+  uint4 r;
+  const __nv_bfloat162 *pa = reinterpret_cast<const __nv_bfloat162 *>(&a);
+  const __nv_bfloat162 *pb = reinterpret_cast<const __nv_bfloat162 *>(&b);
+  __nv_bfloat162 *pr = reinterpret_cast<__nv_bfloat162 *>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
+  return r;
+}
+
+// SPPF_DLA (trainer.py:119-124 / model.py:127-132): y1 = P(x), y2 = P(y1), y3 = P(y2) with
+// P = MaxPool2d(5, 1, 2) and -inf padding.  Cascading clipped windows composes exactly:
+// y1 = max over the clipped 5x5, y2 = 9x9, y3 = 13x13 window of x.  One CTA handles one
+// image row x 8-channel group: the 13 input rows are reduced column-wise into shared memory
+// (vertical maxima for radius 2/4/6), then each thread reduces horizontally.
+__global__ void __launch_bounds__(kThreads) sppf_pool_kernel(__nv_bfloat16 *base, int h, int w, int pitch, int c) {
+  extern __shared__ uint4 col[];  // [3][w][cg] vertical maxima
+  const int cg = c / 8;
+  const int y = blockIdx.x % h;
+  const int n = blockIdx.x / h;
+  const __nv_bfloat16 *img = base + (long long)n * h * w * pitch;
+  const int items = w * cg;
+  const uint4 ninf = make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u);  // bf16 -inf x8
+  for (int it = threadIdx.x; it < items; it += kThreads) {
+    const int x = it / cg, g = it % cg;
+    uint4 m2 = ninf, m4 = ninf, m6 = ninf;
+#pragma unroll
+    for (int dy = -6; dy <= 6; ++dy) {
+      const int yy = y + dy;
+      if (yy < 0 || yy >= h) continue;
+      const uint4 v = *reinterpret_cast<const uint4 *>(img + ((long long)yy * w + x) * pitch + g * 8);
+      m6 = max8(m6, v);
+      if (dy >= -4 && dy <= 4) m4 = max8(m4, v);
+      if (dy >= -2 && dy <= 2) m2 = max8(m2, v);
+    }
+    col[it] = m2;
+    col[items + it] = m4;
+    col[2 * items + it] = m6;
+  }
+  __syncthreads();
+  __nv_bfloat16 *row = base + ((long long)n * h + y) * w * pitch;
+  for (int it = threadIdx.x; it < items; it += kThreads) {
+    const int x = it / cg, g = it % cg;
+    uint4 r2 = ninf, r4 = ninf, r6 = ninf;
+#pragma unroll
+    for (int dx = -6; dx <= 6; ++dx) {
+      const int xx = x + dx;
+      if (xx < 0 || xx >= w) continue;
+      const int j = xx * cg + g;
+      r6 = max8(r6, col[2 * items + j]);
+      if (dx >= -4 && dx <= 4) r4 = max8(r4, col[items + j]);
+      if (dx >= -2 && dx <= 2) r2 = max8(r2, col[j]);
+    }
+    __nv_bfloat16 *o = row + (long long)x * pitch + g * 8;
+    *reinterpret_cast<uint4 *>(o + c) = r2;
+    *reinterpret_cast<uint4 *>(o + 2 * c) = r4;
+    *reinterpret_cast<uint4 *>(o + 3 * c) = r6;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) upsample2x_kernel(const __nv_bfloat16 *in, int in_pitch, __nv_bfloat16 *out,
+                                                              int out_pitch, long long total, int oh, int ow, int cg) {
+  const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (t >= total) return;
+  const int g = (int)(t % cg);
+  const long long p = t / cg;
+  const int ox = (int)(p % ow);
+  const int oy = (int)((p / ow) % oh);
+  const long long n = p / ((long long)ow * oh);
+  const int ih = oh / 2, iw = ow / 2;
+  const uint4 v = *reinterpret_cast<const uint4 *>(in + ((n * ih + oy / 2) * iw + ox / 2) * in_pitch + g * 8);
+  *reinterpret_cast<uint4 *>(out + p * out_pitch + g * 8) = v;
+}
+
+// [n,h,w,c] fp32 -> [n,c,h,w] fp32 through a 32x32 shared-memory transpose of (hw, c).
+__global__ void nhwc_to_nchw_kernel(const float *in, float *out, int hw, int c) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const float *src = in + (long long)n * hw * c;
+  float *dst = out + (long long)n * hw * c;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int p = p0 + i, cc = c0 + threadIdx.x;
+    if (p < hw && cc < c) tile[i][threadIdx.x] = src[(long long)p * c + cc];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int cc = c0 + i, p = p0 + threadIdx.x;
+    if (p < hw && cc < c) dst[(long long)cc * hw + p] = tile[threadIdx.x][i];
+  }
+}
+
+}  // namespace
+
+int sppf_pool_launch(__nv_bfloat16 *base, int n, int h, int w, int pitch, int c, cudaStream_t s) {
+  UYD_REQUIRE(c % 8 == 0 && pitch % 8 == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0, UYD_E_UNSUPPORTED,
+              "sppf pool needs C %% 8 == 0 and 16-byte aligned slices");
+  const size_t smem = (size_t)3 * w * (c / 8) * sizeof(uint4);
+  UYD_REQUIRE(smem <= 200 * 1024, UYD_E_UNSUPPORTED, "sppf row does not fit shared memory");
+  if (smem > 48 * 1024) cudaFuncSetAttribute(sppf_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  sppf_pool_kernel<<<n * h, kThreads, smem, s>>>(base, h, w, pitch, c);
+  return (int)cudaGetLastError();
+}
+
+int upsample2x_launch(const __nv_bfloat16 *in, int in_pitch, __nv_bfloat16 *out, int out_pitch, int n, int ih, int iw,
+                      int c, cudaStream_t s) {
+  UYD_REQUIRE(c % 8 == 0 && in_pitch % 8 == 0 && out_pitch % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+              UYD_E_UNSUPPORTED, "upsample needs C %% 8 == 0 and 16-byte aligned slices");
+  const long long total = (long long)n * ih * 2 * iw * 2 * (c / 8);
+  upsample2x_kernel<<<(unsigned)((total + kThreads - 1) / kThreads), kThreads, 0, s>>>(in, in_pitch, out, out_pitch,
+                                                                                        total, ih * 2, iw * 2, c / 8);
+  return (int)cudaGetLastError();
+}
+
+int nhwc_to_nchw_f32_launch(const float *in, float *out, int n, int h, int w, int c, cudaStream_t s) {
+  dim3 grid(ceil_div(h * w, 32), ceil_div(c, 32), n), block(32, 8);
+  nhwc_to_nchw_kernel<<<grid, block, 0, s>>>(in, out, h * w, c);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace uyd

@@ -1,0 +1,153 @@
+"""Thin object layer over the libuyd plan API (include/uyd.h): buffers, channel slices, ops."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import IMPL_AUTO, UYD_BF16, UYD_F32, ConvDesc, check
+
+
+@dataclass(frozen=True)
+class Slice:
+    """Channels [coff, coff + c) of activation buffer `buf` ([B, h, w, C_total] NHWC)."""
+    buf: int
+    coff: int
+    c: int
+    h: int
+    w: int
+
+    def sub(self, off: int, c: int) -> "Slice":
+        assert 0 <= off and off + c <= self.c
+        return Slice(self.buf, self.coff + off, c, self.h, self.w)
+
+
+NETWORK_INPUT = Slice(-1, 0, 3, 0, 0)
+
+
+def fold_bn(conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d):
+    """fuse_conv_and_bn: W' = diag(g/sqrt(var+eps)) W, b' = beta - mu*g/sqrt(var+eps)."""
+    w = conv.weight.detach().double().cpu()
+    s = bn.weight.detach().double().cpu() / torch.sqrt(bn.running_var.detach().double().cpu() + bn.eps)
+    b = bn.bias.detach().double().cpu() - bn.running_mean.detach().double().cpu() * s
+    if conv.bias is not None:
+        b = b + conv.bias.detach().double().cpu() * s
+    return (w * s.view(-1, 1, 1, 1)).float().numpy(), b.float().numpy()
+
+
+class Plan:
+    def __init__(self, device: int, max_batch: int):
+        self.device = device
+        self.max_batch = max_batch
+        self.ctx = _lib.context(device)
+        self.handle = C.c_void_p()
+        check(_lib.lib().uyd_plan_create(self.ctx, max_batch, C.byref(self.handle)), "uyd_plan_create")
+        self.shapes = {}
+        self.heads = []
+        self.finalized = False
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _lib.lib().uyd_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # ---- construction ------------------------------------------------------------------
+    def buffer(self, h: int, w: int, c: int, dtype: int = UYD_BF16) -> Slice:
+        bid = C.c_int()
+        check(_lib.lib().uyd_plan_add_buffer(self.handle, h, w, c, dtype, C.byref(bid)), "uyd_plan_add_buffer")
+        self.shapes[bid.value] = (h, w, c, dtype)
+        return Slice(bid.value, 0, c, h, w)
+
+    def conv(self, src: Slice, dst: Slice, weight: np.ndarray, bias: np.ndarray, k: int, stride: int = 1,
+             relu: bool = True, depthwise: bool = False, res: Slice | None = None, impl: int = IMPL_AUTO) -> Slice:
+        weight = np.ascontiguousarray(weight, dtype=np.float32)
+        bias = np.ascontiguousarray(bias, dtype=np.float32)
+        cout = weight.shape[0]
+        cin = cout if depthwise else weight.shape[1]
+        assert weight.shape[2] == k and weight.shape[3] == k and bias.shape == (cout,)
+        assert dst.c == cout and (src.buf < 0 or src.c == cin), (src, dst, weight.shape)
+        d = ConvDesc(src.buf, src.coff, dst.buf, dst.coff, res.buf if res else -1, res.coff if res else 0,
+                     cin, cout, k, stride, int(depthwise), int(relu), impl, 0)
+        check(_lib.lib().uyd_plan_add_conv(self.handle, C.byref(d), weight.ctypes.data_as(C.c_void_p),
+                                           bias.ctypes.data_as(C.c_void_p)), "uyd_plan_add_conv")
+        return dst
+
+    def sppf_pool(self, s: Slice, c: int) -> None:
+        check(_lib.lib().uyd_plan_add_sppf_pool(self.handle, s.buf, s.coff, c), "uyd_plan_add_sppf_pool")
+
+    def upsample2x(self, src: Slice, dst: Slice) -> Slice:
+        check(_lib.lib().uyd_plan_add_upsample2x(self.handle, src.buf, src.coff, dst.buf, dst.coff, src.c),
+              "uyd_plan_add_upsample2x")
+        return dst
+
+    def set_heads(self, heads: list[Slice], strides: list[int], reg_max: int, nc: int) -> None:
+        n = len(heads)
+        ids = (C.c_int * n)(*[h.buf for h in heads])
+        st = (C.c_int * n)(*strides)
+        check(_lib.lib().uyd_plan_set_heads(self.handle, ids, st, n, reg_max, nc), "uyd_plan_set_heads")
+        self.heads = heads
+
+    def finalize(self) -> "Plan":
+        check(_lib.lib().uyd_plan_finalize(self.handle), "uyd_plan_finalize")
+        self.finalized = True
+        return self
+
+    # ---- execution ---------------------------------------------------------------------
+    @staticmethod
+    def _stream() -> C.c_void_p:
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def run(self, x: torch.Tensor) -> None:
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+        check(_lib.lib().uyd_plan_run(self.handle, C.c_void_p(x.data_ptr()), x.shape[0], self._stream()), "uyd_plan_run")
+
+    def run_no_input(self, batch: int) -> None:
+        """Runs a plan whose first op does not read the network input (layer-level tests)."""
+        check(_lib.lib().uyd_plan_run(self.handle, None, batch, self._stream()), "uyd_plan_run")
+
+    def write(self, s: Slice, nchw: torch.Tensor) -> None:
+        """Stores an NCHW tensor into a slice of a bf16 buffer (layer-level tests)."""
+        h, w, ctot, dtype = self.shapes[s.buf]
+        assert dtype == UYD_BF16
+        batch = nchw.shape[0]
+        ptr = C.c_void_p()
+        check(_lib.lib().uyd_plan_buffer_ptr(self.handle, s.buf, C.byref(ptr)), "uyd_plan_buffer_ptr")
+        full = torch.empty(batch, h, w, ctot, dtype=torch.bfloat16, device=f"cuda:{self.device}")
+        nbytes = full.numel() * 2
+        check(_lib.lib().uyd_memcpy_d2d(C.c_void_p(full.data_ptr()), ptr, nbytes, self._stream()), "uyd_memcpy_d2d")
+        full[..., s.coff:s.coff + s.c] = nchw.to(full.device).permute(0, 2, 3, 1).to(torch.bfloat16)
+        check(_lib.lib().uyd_memcpy_d2d(ptr, C.c_void_p(full.data_ptr()), nbytes, self._stream()), "uyd_memcpy_d2d")
+        torch.cuda.current_stream().synchronize()
+
+    def decode(self, y: torch.Tensor, batch: int) -> None:
+        check(_lib.lib().uyd_plan_run_decode(self.handle, C.c_void_p(y.data_ptr()), batch, self._stream()),
+              "uyd_plan_run_decode")
+
+    def export_head(self, level: int, out: torch.Tensor, batch: int) -> None:
+        check(_lib.lib().uyd_plan_export_head_nchw(self.handle, level, C.c_void_p(out.data_ptr()), batch, self._stream()),
+              "uyd_plan_export_head_nchw")
+
+    def read(self, s: Slice, batch: int) -> torch.Tensor:
+        """Copies a slice out as an NCHW fp32 tensor (layer-level parity checks)."""
+        h, w, ctot, dtype = self.shapes[s.buf]
+        tdt = torch.float32 if dtype == UYD_F32 else torch.bfloat16
+        full = torch.empty(batch, h, w, ctot, dtype=tdt, device=f"cuda:{self.device}")
+        ptr = C.c_void_p()
+        check(_lib.lib().uyd_plan_buffer_ptr(self.handle, s.buf, C.byref(ptr)), "uyd_plan_buffer_ptr")
+        check(_lib.lib().uyd_memcpy_d2d(C.c_void_p(full.data_ptr()), ptr, full.numel() * full.element_size(), self._stream()),
+              "uyd_memcpy_d2d")
+        return full[..., s.coff:s.coff + s.c].permute(0, 3, 1, 2).float().contiguous()
+
+    @property
+    def bytes(self) -> int:
+        return int(_lib.lib().uyd_plan_bytes(self.handle))
+
+    @property
+    def launches(self) -> int:
+        return int(_lib.lib().uyd_plan_num_launches(self.handle))

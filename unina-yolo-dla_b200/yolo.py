@@ -1,0 +1,432 @@
+"""``UninaYoloB200``: the YAML-built detector (reference: ``DetectionModel(cfg, nc)`` after
+``apply_dla_patches`` + ``replace_silu_with_relu``, trainer.py:31-136,146-158) as a drop-in
+``nn.Module`` whose forward runs entirely through libuyd's CUDA plan.
+
+Same construction from ``unina-yolo-dla-m.yaml`` (unina-yolo-dla-m.yaml:14-62), same
+``state_dict`` keys/shapes (925 entries), same eval output ``(y[B,4+nc,A], [x_l])`` and
+``predict`` -> per-image ``[N,6]`` rows ``(x1,y1,x2,y2,conf,cls)`` (train.py:396-423,
+trainer.py:237-240).  The modules below only *hold* parameters under the reference's names and
+know how to emit themselves into a plan; they never compute with torch.
+"""
+from __future__ import annotations
+
+import ast
+import ctypes as C
+import math
+from math import gcd
+from pathlib import Path
+
+import torch
+import torch.nn as nn
+import yaml
+
+from . import _lib
+from ._lib import UYD_BF16, UYD_F32, check
+from .plan import NETWORK_INPUT, Plan, Slice, fold_bn
+
+DEFAULT_YAML = Path(__file__).resolve().parent / "unina-yolo-dla-m.yaml"
+
+
+def _make_divisible(x, d):
+    return int(math.ceil(x / d) * d)
+
+
+class Conv(nn.Module):
+    """Conv2d(bias=False) + BatchNorm2d(eps 1e-3) + ReLU, parameters under ``conv.*`` / ``bn.*``."""
+
+    def __init__(self, c1, c2, k=1, s=1, g=1):
+        super().__init__()
+        self.conv = nn.Conv2d(c1, c2, k, s, k // 2, groups=g, bias=False)
+        self.bn = nn.BatchNorm2d(c2, eps=1e-3, momentum=0.03)
+        self.act = nn.ReLU(inplace=True)
+        self.k, self.s, self.g, self.c1, self.c2 = k, s, g, c1, c2
+
+    def emit(self, p: Plan, src: Slice, dst: Slice | None = None, res: Slice | None = None) -> Slice:
+        oh, ow = (p.in_hw[0] // self.s, p.in_hw[1] // self.s) if src.buf < 0 else (
+            (src.h + 2 * (self.k // 2) - self.k) // self.s + 1, (src.w + 2 * (self.k // 2) - self.k) // self.s + 1)
+        if dst is None:
+            dst = p.buffer(oh, ow, self.c2)
+        w, b = fold_bn(self.conv, self.bn)
+        dw = self.g > 1
+        assert not dw or self.g == self.c1 == self.c2, "only depth-wise grouped convs occur in this graph"
+        return p.conv(src, dst, w, b, self.k, self.s, relu=True, depthwise=dw, res=res)
+
+
+def DWConv(c1, c2, k=1, s=1):
+    return Conv(c1, c2, k, s, g=gcd(c1, c2))
+
+
+def emit_plain_conv(p: Plan, conv: nn.Conv2d, src: Slice, dst: Slice) -> Slice:
+    """Final biased 1x1 convs of the heads (no BN, no activation)."""
+    w = conv.weight.detach().float().cpu().numpy()
+    b = conv.bias.detach().float().cpu().numpy()
+    return p.conv(src, dst, w, b, conv.kernel_size[0], conv.stride[0], relu=False)
+
+
+class Bottleneck(nn.Module):
+    def __init__(self, c1, c2, shortcut=True, g=1, k=(3, 3), e=0.5):
+        super().__init__()
+        c_ = int(c2 * e)
+        self.cv1 = Conv(c1, c_, k[0], 1)
+        self.cv2 = Conv(c_, c2, k[1], 1, g=g)
+        self.add = shortcut and c1 == c2
+
+    def emit(self, p, src, dst=None):
+        t = self.cv1.emit(p, src)
+        return self.cv2.emit(p, t, dst, res=src if self.add else None)
+
+
+class C3k(nn.Module):
+    """cv3(cat(m(cv1(x)), cv2(x))) -- the cat buffer is written in place by both branches."""
+
+    def __init__(self, c1, c2, n=1, shortcut=True, g=1, e=0.5, k=3):
+        super().__init__()
+        c_ = int(c2 * e)
+        self.c_ = c_
+        self.cv1 = Conv(c1, c_, 1, 1)
+        self.cv2 = Conv(c1, c_, 1, 1)
+        self.cv3 = Conv(2 * c_, c2, 1)
+        self.m = nn.Sequential(*(Bottleneck(c_, c_, shortcut, g, k=(k, k), e=1.0) for _ in range(n)))
+
+    def emit(self, p, src, dst=None):
+        cat = p.buffer(src.h, src.w, 2 * self.c_)
+        t = self.cv1.emit(p, src)
+        for i, b in enumerate(self.m):
+            t = b.emit(p, t, cat.sub(0, self.c_) if i == len(self.m) - 1 else None)
+        self.cv2.emit(p, src, cat.sub(self.c_, self.c_))
+        return self.cv3.emit(p, cat, dst)
+
+
+class C3k2(nn.Module):
+    """C2f: cv1 -> chunk(2) -> n blocks chained on the last chunk -> cat -> cv2.  cv1 writes
+    straight into the first 2c channels of the cat buffer; each block appends its c channels."""
+
+    def __init__(self, c1, c2, n=1, c3k=False, e=0.5, g=1, shortcut=True):
+        super().__init__()
+        self.c = int(c2 * e)
+        self.cv1 = Conv(c1, 2 * self.c, 1, 1)
+        self.cv2 = Conv((2 + n) * self.c, c2, 1)
+        self.m = nn.ModuleList(
+            C3k(self.c, self.c, 2, shortcut, g) if c3k else Bottleneck(self.c, self.c, shortcut, g) for _ in range(n))
+
+    def emit(self, p, src, dst=None):
+        c, n = self.c, len(self.m)
+        cat = p.buffer(src.h, src.w, (2 + n) * c)
+        self.cv1.emit(p, src, cat.sub(0, 2 * c))
+        for i, m in enumerate(self.m):
+            m.emit(p, cat.sub((1 + i) * c, c), cat.sub((2 + i) * c, c))
+        return self.cv2.emit(p, cat, dst)
+
+
+class SPPF_DLA(nn.Module):
+    """trainer.py:108-124 (incl. the (c1, 5) argument repair)."""
+
+    def __init__(self, c1, c2, k=5):
+        super().__init__()
+        if c2 == k and c2 < 16:
+            c2 = c1
+        c_ = c1 // 2
+        self.c_ = c_
+        self.cv1 = Conv(c1, c_, 1, 1)
+        self.cv2 = Conv(c_ * 4, c2, 1, 1)
+        self.m = nn.MaxPool2d(kernel_size=k, stride=1, padding=k // 2)
+        self.k = k
+
+    def emit(self, p, src, dst=None):
+        assert self.k == 5, "the pool cascade kernel is built for k = 5"
+        cat = p.buffer(src.h, src.w, 4 * self.c_)
+        self.cv1.emit(p, src, cat.sub(0, self.c_))
+        p.sppf_pool(cat, self.c_)
+        return self.cv2.emit(p, cat, dst)
+
+
+class Concat(nn.Module):
+    def __init__(self, dimension=1):
+        super().__init__()
+        self.d = dimension
+
+
+class DFL(nn.Module):
+    def __init__(self, c1=16):
+        super().__init__()
+        self.conv = nn.Conv2d(c1, 1, 1, bias=False).requires_grad_(False)
+        self.conv.weight.data[:] = torch.arange(c1, dtype=torch.float).view(1, c1, 1, 1)
+        self.c1 = c1
+
+
+class Detect(nn.Module):
+    """Attribute contract used by the reference (mine_data.py:110-161): nl, nc, reg_max, stride,
+    cv2[i] (box branch), cv3[i] (cls branch), dfl."""
+
+    def __init__(self, nc=80, ch=()):
+        super().__init__()
+        self.nc, self.nl, self.reg_max = nc, len(ch), 16
+        self.no = nc + self.reg_max * 4
+        self.stride = torch.zeros(self.nl)
+        c2 = max(16, ch[0] // 4, self.reg_max * 4)
+        c3 = max(ch[0], min(nc, 100))
+        self.cv2 = nn.ModuleList(
+            nn.Sequential(Conv(x, c2, 3), Conv(c2, c2, 3), nn.Conv2d(c2, 4 * self.reg_max, 1)) for x in ch)
+        self.cv3 = nn.ModuleList(
+            nn.Sequential(nn.Sequential(DWConv(x, x, 3), Conv(x, c3, 1)),
+                          nn.Sequential(DWConv(c3, c3, 3), Conv(c3, c3, 1)),
+                          nn.Conv2d(c3, nc, 1)) for x in ch)
+        self.dfl = DFL(self.reg_max)
+
+    def bias_init(self):
+        for a, b, s in zip(self.cv2, self.cv3, self.stride):
+            a[-1].bias.data[:] = 1.0
+            b[-1].bias.data[: self.nc] = math.log(5 / self.nc / (640 / float(s)) ** 2)
+
+    def emit(self, p, feats):
+        heads = []
+        for i, f in enumerate(feats):
+            head = p.buffer(f.h, f.w, self.no, UYD_F32)
+            t = self.cv2[i][0].emit(p, f)
+            t = self.cv2[i][1].emit(p, t)
+            emit_plain_conv(p, self.cv2[i][2], t, head.sub(0, 4 * self.reg_max))
+            t = f
+            for blk in (self.cv3[i][0], self.cv3[i][1]):
+                t = blk[1].emit(p, blk[0].emit(p, t))
+            emit_plain_conv(p, self.cv3[i][2], t, head.sub(4 * self.reg_max, self.nc))
+            heads.append(head)
+        return heads
+
+
+def _literal(a):
+    if isinstance(a, str):
+        try:
+            return ast.literal_eval(a)
+        except (ValueError, SyntaxError):
+            return a
+    return a
+
+
+def parse_model(d: dict, ch: int = 3):
+    """YAML -> holder modules (parse_model semantics restated in SURVEY.md appendix A.1,
+    with the scale/scales defaults injected by trainer.py:85-94)."""
+    nc = d["nc"]
+    scale = d.get("scale", "m")
+    depth, width, max_ch = d.get("scales", {scale: [1.0, 1.0, 1024]})[scale]
+    chs, layers, save = [ch], [], []
+    for i, (f, n, m, args) in enumerate(d["backbone"] + d["head"]):
+        args = [nc if a == "nc" else _literal(a) for a in args]
+        n = max(round(n * depth), 1) if n > 1 else n
+        if m in ("Conv", "C3k2"):
+            c1, c2 = chs[f], args[0]
+            if c2 != nc:
+                c2 = _make_divisible(min(c2, max_ch) * width, 8)
+            args = [c1, c2, *args[1:]]
+            if m == "C3k2":
+                args.insert(2, n)
+                if scale in "mlx":
+                    args[3] = True
+            mod = Conv(*args) if m == "Conv" else C3k2(*args)
+        elif m == "SPPF_DLA":
+            c2 = chs[f]
+            mod = SPPF_DLA(*args)
+        elif m == "nn.Upsample":
+            c2 = chs[f]
+            mod = nn.Upsample(*args)
+            if not (mod.scale_factor == 2 and mod.mode == "nearest"):
+                raise NotImplementedError("only nearest x2 upsampling is on the hot path")
+        elif m == "Concat":
+            c2 = sum(chs[x] for x in f)
+            mod = Concat(*args)
+        elif m == "Detect":
+            c2 = None
+            mod = Detect(args[0], [chs[x] for x in f])
+        else:
+            raise NotImplementedError(f"module {m} is not part of the UNINA-YOLO-DLA graph")
+        mod.i, mod.f, mod.c_out = i, f, c2
+        save.extend(x % i for x in ([f] if isinstance(f, int) else f) if x != -1)
+        layers.append(mod)
+        if i == 0:
+            chs = []
+        chs.append(c2)
+    return nn.Sequential(*layers), sorted(save)
+
+
+class UninaYoloB200(nn.Module):
+    def __init__(self, cfg=DEFAULT_YAML, ch: int = 3, nc: int | None = None, verbose: bool = False):
+        super().__init__()
+        self.yaml = dict(cfg) if isinstance(cfg, dict) else yaml.safe_load(Path(cfg).read_text())
+        if nc is not None:
+            self.yaml["nc"] = nc
+        self.model, self.save = parse_model(self.yaml, ch)
+        self.nc = self.yaml["nc"]
+        self.names = {i: str(i) for i in range(self.nc)}
+        det = self.model[-1]
+        # strides of the detect inputs: product of the conv strides on the path (dry-run result)
+        det.stride = torch.tensor([float(s) for s in self._level_strides()])
+        self.stride = det.stride
+        det.bias_init()
+        self._plans = {}
+        self._nms_ws = {}
+        self.eval()
+
+    @classmethod
+    def from_yaml(cls, path=DEFAULT_YAML, nc: int | None = None) -> "UninaYoloB200":
+        return cls(path, nc=nc)
+
+    # ---- graph bookkeeping -------------------------------------------------------------
+    def _level_strides(self):
+        st = []
+        for m in self.model:
+            fi = m.f if isinstance(m.f, int) else m.f[0]
+            s_in = 1 if (m.i == 0) else st[fi if fi != -1 else m.i - 1]
+            if isinstance(m, Conv):
+                st.append(s_in * m.s)
+            elif isinstance(m, nn.Upsample):
+                st.append(s_in // 2)
+            elif isinstance(m, Detect):
+                st.append(0)
+                return [st[j] for j in m.f]
+            else:
+                st.append(s_in)
+        raise ValueError("graph has no Detect layer")
+
+    def refresh(self) -> None:
+        """Drop compiled plans (call after mutating parameters in place)."""
+        self._plans.clear()
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        out = super().load_state_dict(state_dict, strict=strict, assign=assign)
+        self.refresh()
+        return out
+
+    def _apply(self, fn, recurse=True):
+        self._plans.clear()
+        return super()._apply(fn, recurse)
+
+    # ---- plan construction -------------------------------------------------------------
+    def _build_plan(self, device: int, max_batch: int, H: int, W: int) -> Plan:
+        p = Plan(device, max_batch)
+        p.in_hw = (H, W)
+        layers = list(self.model)
+        # pass 1: extents of every layer output
+        shape = []
+        for m in layers:
+            src = None if m.i == 0 else (m.f if isinstance(m.f, int) else m.f[0])
+            ih, iw = (H, W) if m.i == 0 else shape[src if src != -1 else m.i - 1][1:]
+            if isinstance(m, Conv):
+                shape.append((m.c2, ih // m.s, iw // m.s))
+            elif isinstance(m, nn.Upsample):
+                shape.append((m.c_out, ih * 2, iw * 2))
+            elif isinstance(m, Detect):
+                shape.append(None)
+            else:
+                shape.append((m.c_out, ih, iw))
+        # pass 2: every tensor consumed by a Concat lives inside that Concat's buffer
+        home = {}
+        for m in layers:
+            if isinstance(m, Concat):
+                c, h, w = shape[m.i]
+                cat = p.buffer(h, w, c)
+                home[m.i] = cat
+                off = 0
+                for j in m.f:
+                    j = m.i - 1 if j == -1 else j
+                    assert j not in home, "a tensor feeding two Concat layers would need a copy"
+                    home[j] = cat.sub(off, shape[j][0])
+                    off += shape[j][0]
+        # pass 3: emit
+        outs = []
+        for m in layers:
+            def src_of(j):
+                return outs[m.i - 1] if j == -1 else outs[j]
+            dst = home.get(m.i)
+            if m.i == 0:
+                assert isinstance(m, Conv), "the first layer must be a Conv reading the frame"
+                outs.append(m.emit(p, NETWORK_INPUT, dst))
+            elif isinstance(m, (Conv, C3k2, SPPF_DLA)):
+                outs.append(m.emit(p, src_of(m.f), dst))
+            elif isinstance(m, nn.Upsample):
+                s = src_of(m.f)
+                dst = dst or p.buffer(s.h * 2, s.w * 2, s.c)
+                outs.append(p.upsample2x(s, dst))
+            elif isinstance(m, Concat):
+                outs.append(home[m.i])
+            elif isinstance(m, Detect):
+                feats = [src_of(j) for j in m.f]
+                heads = m.emit(p, feats)
+                p.set_heads(heads, [int(s) for s in m.stride.tolist()], m.reg_max, m.nc)
+                outs.append(None)
+        p.layer_outputs = outs
+        return p.finalize()
+
+    def plan_for(self, x: torch.Tensor) -> Plan:
+        B, _, H, W = x.shape
+        dev = x.device.index if x.device.index is not None else torch.cuda.current_device()
+        key = (dev, H, W)
+        p = self._plans.get(key)
+        if p is None or p.max_batch < B:
+            if H % 32 or W % 32:
+                raise ValueError("frame height/width must be multiples of 32")
+            p = self._build_plan(dev, B, H, W)
+            self._plans[key] = p
+        return p
+
+    # ---- execution ---------------------------------------------------------------------
+    def _prep(self, x: torch.Tensor) -> torch.Tensor:
+        if self.training:
+            raise RuntimeError("UninaYoloB200 implements the inference path only: call .eval()")
+        if not torch.cuda.is_available():
+            raise _lib.UydError("no CUDA device: the B200 path has no CPU fallback")
+        if not x.is_cuda:
+            x = x.to(next(self.parameters()).device if next(self.parameters()).is_cuda else "cuda", non_blocking=True)
+        return x.float().contiguous()
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, raw_heads: bool = True):
+        """Eval forward of DetectionModel: ``(y[B,4+nc,A], [x_l[B,no,H_l,W_l]])``."""
+        x = self._prep(x)
+        p = self.plan_for(x)
+        B = x.shape[0]
+        p.run(x)
+        A = sum(h.h * h.w for h in p.heads)
+        y = torch.empty(B, 4 + self.nc, A, dtype=torch.float32, device=x.device)
+        p.decode(y, B)
+        if not raw_heads:
+            return y
+        xs = []
+        for lvl, h in enumerate(p.heads):
+            t = torch.empty(B, h.c, h.h, h.w, dtype=torch.float32, device=x.device)
+            p.export_head(lvl, t, B)
+            xs.append(t)
+        return y, xs
+
+    @torch.no_grad()
+    def nms(self, y: torch.Tensor, conf: float = 0.25, iou: float = 0.7, max_det: int = 300, max_nms: int = 30000,
+            max_wh: float = 7680.0, return_index: bool = False):
+        """Ultralytics ``non_max_suppression`` on ``y[B,4+nc,A]`` -> (det[B,max_det,6], count[B])."""
+        assert y.is_cuda and y.dtype == torch.float32 and y.is_contiguous()
+        B, no, A = y.shape
+        dev = y.device.index if y.device.index is not None else torch.cuda.current_device()
+        need = int(_lib.lib().uyd_nms_workspace_bytes(B, A))
+        ws = self._nms_ws.get(dev)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(need, dtype=torch.uint8, device=y.device)
+            self._nms_ws[dev] = ws
+        det = torch.zeros(B, max_det, 6, dtype=torch.float32, device=y.device)
+        idx = torch.full((B, max_det), -1, dtype=torch.int32, device=y.device)
+        cnt = torch.zeros(B, dtype=torch.int32, device=y.device)
+        check(_lib.lib().uyd_nms(_lib.context(dev), C.c_void_p(y.data_ptr()), B, no - 4, A, conf, iou, max_nms, max_det,
+                                 max_wh, C.c_void_p(ws.data_ptr()), ws.numel(), C.c_void_p(det.data_ptr()),
+                                 C.c_void_p(idx.data_ptr()), C.c_void_p(cnt.data_ptr()),
+                                 C.c_void_p(torch.cuda.current_stream().cuda_stream)), "uyd_nms")
+        return (det, cnt, idx) if return_index else (det, cnt)
+
+    @torch.no_grad()
+    def predict_batched(self, x: torch.Tensor, conf: float = 0.25, iou: float = 0.7, max_det: int = 300,
+                        max_nms: int = 30000):
+        """Forward + decode + NMS, everything left on the device: (det[B,max_det,6], count[B])."""
+        y = self.forward(x, raw_heads=False)
+        return self.nms(y, conf, iou, max_det, max_nms)
+
+    @torch.no_grad()
+    def predict(self, x: torch.Tensor, conf: float = 0.25, iou: float = 0.7, max_det: int = 300, max_nms: int = 30000):
+        """Per-image ``[N_i, 6]`` tensors ``(x1,y1,x2,y2,conf,cls)`` like ``result.boxes.data``."""
+        det, cnt = self.predict_batched(x, conf, iou, max_det, max_nms)
+        counts = cnt.tolist()
+        return [det[b, :n] for b, n in enumerate(counts)]
