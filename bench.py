@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of the UNINA-YOLO-DLA inference hot path on B200.
+
+Contract (driver): python bench.py --gpus N --steps K --warmup W [--impl reference]
+prints ONE JSON line on rank 0.
+
+Workload (BASELINE.json configs[1]): unina-yolo-dla-m, bf16 forward + DFL decode + NMS,
+640x640, batch 64 per GPU, seeded synthetic weights (UninaYoloB200.init_synthetic) and frames.
+A step = one pass of the hot path over one batch.
+  value : images/s, frames already resident in HBM as NCHW fp32 (the reference forward signature)
+  e2e   : images/s through the public predict call with HOST frames: pinned uint8 NCHW frames
+          -> H2D -> forward(+/255 fused in the stem) -> decode -> NMS -> D2H of [B,300,6]+counts
+          (+ NCCL all_gather of the detections when N > 1: the batched-eval gather)
+  roofline    : the dominant kernel, timed live with CUDA events inside the timed steps
+  cpu_baseline: the oracle (restated reference path) on the host cores, bounded sample
+Multi-GPU: frames shard data-parallel, no collective on the forward path ("weak" scaling).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "images/sec @640x640 (forward + DFL decode + NMS)"
+UNIT = "images/s"
+CONF, IOU, MAX_DET = 0.25, 0.7, 300
+CANDIDATES_PER_IMAGE = 1500
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step")
+    ap.add_argument("--size", type=int, default=640)
+    ap.add_argument("--cpu-sample", type=int, default=32, help="frames of the bounded CPU sample")
+    ap.add_argument("--profile-out", default="", help="write the per-op table (markdown) here")
+    return ap.parse_args()
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "src": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        mx = next((int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()), None)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_models(size: int, need_oracle: bool):
+    import unina_yolo_dla_b200 as uyd
+
+    model = uyd.UninaYoloB200.from_yaml().init_synthetic(seed=0)
+    return model
+
+
+def oracle_from(model):
+    """The CPU oracle carrying the product's weights (cpu_baseline / --impl reference only)."""
+    from oracle import yolo_graph as yg
+
+    ref = yg.DetectionModel(yg.default_yaml_path())
+    ref.load_state_dict({k: v.detach().cpu() for k, v in model.state_dict().items()}, strict=True)
+    return ref.eval()
+
+
+def cpu_pass(ref, frames: torch.Tensor):
+    """Reference path on the host: fp32 forward + DFL decode + Ultralytics-style NMS."""
+    from oracle import postproc as pp
+
+    with torch.no_grad():
+        y, _ = ref(frames)
+    return pp.non_max_suppression(y.numpy(), CONF, IOU, MAX_DET)
+
+
+def cpu_baseline(model, size: int, sample: int, chunk: int = 8):
+    torch.set_num_threads(os.cpu_count() or 1)
+    ref = oracle_from(model)
+    g = torch.Generator().manual_seed(1)
+    frames = torch.rand(chunk, 3, size, size, generator=g)
+    cpu_pass(ref, frames[:2])  # warm-up
+    t0 = time.perf_counter()
+    done = 0
+    while done < sample:
+        cpu_pass(ref, frames)
+        done += chunk
+    dt = time.perf_counter() - t0
+    return {"value": done / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{done} frames of the same workload in chunks of {chunk} (oracle fp32 forward + DFL decode + NMS)"}
+
+
+def run_reference(a):
+    """--impl reference: the reference's CPU implementation of the path on the host cores.
+    ultralytics is not installable here (no network, unpinned, not vendored) and model.py is a
+    different network, so this is the oracle port (kind = "port")."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = build_models(a.size, True)
+    if torch.cuda.is_available():  # same NMS load as the GPU arm
+        try:
+            model = model.cuda()
+            g = torch.Generator(device="cuda").manual_seed(0)
+            model.calibrate_cls_bias(torch.rand(8, 3, a.size, a.size, device="cuda", generator=g), CANDIDATES_PER_IMAGE, CONF)
+        except Exception:
+            pass
+    ref = oracle_from(model)
+    chunk = 8
+    frames = torch.rand(chunk, 3, a.size, a.size, generator=torch.Generator().manual_seed(1))
+    for _ in range(max(1, min(a.warmup, 2))):
+        cpu_pass(ref, frames)
+    steps = max(1, min(a.steps, 8))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_pass(ref, frames)
+    dt = time.perf_counter() - t0
+    v = steps * chunk / dt
+    cores = torch.get_num_threads()
+    sample = f"{chunk} frames per step ({steps} timed steps; bounded sample of the batch-{a.batch} workload)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": steps, "warmup": a.warmup,
+        "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": f"unina-yolo-dla-m fp32 CPU forward + DFL decode + NMS, {a.size}x{a.size}, bounded sample"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return run_reference(a)
+
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    B, S = a.batch, a.size
+
+    model = build_models(S, False).to(dev)
+    gen = torch.Generator(device=dev).manual_seed(100 + rank)
+    x_dev = torch.rand(B, 3, S, S, device=dev, generator=gen)                       # resident fp32 frames
+    x_host = (torch.rand(B, 3, S, S, generator=torch.Generator().manual_seed(200 + rank)) * 255).to(torch.uint8).pin_memory()
+    x_u8 = torch.empty_like(x_host, device=dev)
+    model.calibrate_cls_bias(x_dev[: min(B, 8)], CANDIDATES_PER_IMAGE, CONF)
+    plan = model.plan_for(x_dev)
+    det_host = torch.empty(B, MAX_DET, 6).pin_memory()
+    cnt_host = torch.empty(B, dtype=torch.int32).pin_memory()
+
+    def step_resident():
+        return model.predict_batched(x_dev, CONF, IOU, MAX_DET)
+
+    def step_e2e():
+        x_u8.copy_(x_host, non_blocking=True)
+        det, cnt = model.predict_batched(x_u8, CONF, IOU, MAX_DET)
+        if world > 1:  # batched-eval gather of the detections (the only collective of the path)
+            gd = torch.empty(world * B, MAX_DET, 6, device=dev)
+            gc = torch.empty(world * B, dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(gd, det)
+            dist.all_gather_into_tensor(gc, cnt)
+        det_host.copy_(det, non_blocking=True)
+        cnt_host.copy_(cnt, non_blocking=True)
+
+    warm = max(3, a.warmup)
+    for _ in range(warm):
+        step_resident()
+    torch.cuda.synchronize()
+    # per-op profile (outside the timed region) -> dominant kernel
+    ms = plan.profile(x_dev)
+    top = max(range(len(ms)), key=lambda i: ms[i])
+    top_text, top_flops, top_bytes = plan.op_info(top)
+    plan.set_timed_op(top, a.steps)
+
+    def timed(fn, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(step_resident, a.steps)
+    if rank == 0:
+        sampler.stop_flag = True
+    top_ms_total, top_n = plan.timed_op_read()
+    plan.set_timed_op(-1, 0)
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, a.steps)
+    n_det = int(cnt_host.sum().item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    top_ms = top_ms_total / max(top_n, 1)
+    tensor_bound = top_flops / max(top_bytes, 1.0) > 100.0  # FLOP/B well above 1: judged on the tensor pipe
+    if tensor_bound:
+        achieved, peak, unit = top_flops * B / (top_ms * 1e-3) / 1e12, pk["tflops"], "TFLOP/s"
+    else:
+        achieved, peak, unit = top_bytes * B / (top_ms * 1e-3) / 1e9, pk["hbm_gbs"], "GB/s"
+    traffic = None
+    tj = ROOT / "profiles" / "roofline_traffic.json"
+    if tj.exists():
+        traffic = json.loads(tj.read_text()).get(top_text)
+    kernels_per_step = plan.launches + len(plan.heads) + 5  # conv stack + DFL decode per level + 5 NMS kernels (cub sort excluded)
+    conv_flops = sum(plan.op_info(i)[1] for i in range(plan.launches))
+    out = {
+        "metric": METRIC, "value": world * B * a.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
+        "warmup": warm, "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"unina-yolo-dla-m bf16 forward + DFL decode + NMS, {S}x{S}, batch {B} per GPU",
+                   "global_batch": world * B, "parallelism": f"dp{world}", "conf": CONF, "iou": IOU, "max_det": MAX_DET,
+                   "candidates_per_image_target": CANDIDATES_PER_IMAGE, "detections_last_step": n_det,
+                   "weights": "seeded synthetic (init_synthetic seed 0)",
+                   "l2": f"inputs larger than L2 ({x_dev.numel() * 4 / 1e6:.0f} MB fp32 frames + {plan.bytes / 1e6:.0f} MB activations per step)",
+                   "conv_gflop_per_image": conv_flops / 1e9},
+        "e2e": {"value": world * B * a.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": x_host.numel(),
+                "d2h_bytes_per_step": det_host.numel() * 4 + cnt_host.numel() * 4, "ms_per_step": ms_e2e / a.steps,
+                "api": "UninaYoloB200.predict_batched(uint8 NCHW frames from pinned host memory)"},
+        "gpu_launches": kernels_per_step * a.steps,
+        "roofline": {"kernel": top_text, "bound": "tensor" if tensor_bound else "hbm", "achieved": achieved, "peak": peak,
+                     "unit": unit, "frac": achieved / peak, "traffic": traffic, "peak_source": pk["src"],
+                     "avg_launch_ms": top_ms, "launches_timed": top_n,
+                     "share_of_conv_stack": ms[top] / sum(ms)},
+        "conv_stack": {"ms_per_step_profiled": sum(ms), "tflops": conv_flops * B / (sum(ms) * 1e-3) / 1e12,
+                       "frac_of_tensor_peak": conv_flops * B / (sum(ms) * 1e-3) / 1e12 / pk["tflops"]},
+        "clocks": sampler.summary(),
+    }
+    if world == 1:
+        out["cpu_baseline"] = cpu_baseline(model, S, a.cpu_sample)
+    if a.profile_out:
+        rows = ["| # | op | ms | share | TFLOP/s | GB/s |", "|---|---|---|---|---|---|"]
+        for i in sorted(range(len(ms)), key=lambda i: -ms[i]):
+            t, fl, by = plan.op_info(i)
+            rows.append(f"| {i} | {t} | {ms[i]:.4f} | {100 * ms[i] / sum(ms):.1f}% | {fl * B / (ms[i] * 1e-3) / 1e12:.1f} | {by * B / (ms[i] * 1e-3) / 1e9:.0f} |")
+        Path(a.profile_out).write_text(f"per-op CUDA-event times, batch {B}, {S}x{S} (one pass, ops serialised)\n\n" + "\n".join(rows) + "\n")
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -106,6 +106,20 @@ int uyd_plan_buffer_ptr(uyd_plan *plan, int id, void **ptr);
  * forward signature, model.py:347 / DetectionModel.forward).  */
 int uyd_plan_run(uyd_plan *plan, const float *x, int batch, uyd_stream stream);
 
+/* Same, for uint8 NCHW frames [batch,3,H,W]: the stem divides by 255 on load, which is the
+ * reference predictor's pre-process (im.float() / 255) fused into the first conv. */
+int uyd_plan_run_u8(uyd_plan *plan, const uint8_t *x, int batch, uyd_stream stream);
+
+/* Measurement hooks (CUDA events on `stream`, no effect on results):
+ *  - uyd_plan_profile: one pass with every op bracketed; ms[uyd_plan_num_launches]; syncs.
+ *  - uyd_plan_set_timed_op / _read: bracket ONE op inside normal uyd_plan_run calls.
+ *  - uyd_plan_op_info: description + algorithmic flops / compulsory bytes per image. */
+int uyd_plan_profile(uyd_plan *plan, const float *x, int batch, uyd_stream stream, float *ms);
+int uyd_plan_set_timed_op(uyd_plan *plan, int op, int max_samples);
+int uyd_plan_timed_op_read(uyd_plan *plan, float *total_ms, int *samples);
+int uyd_plan_op_info(uyd_plan *plan, int op, char *text, size_t text_len, double *flops_per_image,
+                     double *bytes_per_image);
+
 /* DFL decode of the plan's heads -> y [batch, 4+nc, A] fp32 (cx,cy,w,h in pixels, sigmoid
  * class scores), A = sum of H_l*W_l, levels concatenated in head order. */
 int uyd_plan_run_decode(uyd_plan *plan, float *y, int batch, uyd_stream stream);

@@ -1,0 +1,66 @@
+"""A torch-fp32 stand-in for the libuyd plan, used ONLY by CPU tests to check the host-side
+graph emission (slices, in-place concat, residual wiring).  It has the same construction
+interface as unina_yolo_dla_b200.plan.Plan; nothing in the product imports it."""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from unina_yolo_dla_b200.plan import Slice
+
+
+class FakePlan:
+    def __init__(self, device=0, max_batch=1):
+        self.max_batch = max_batch
+        self.specs = []       # (h, w, c)
+        self.ops = []
+        self.heads = []
+        self.in_hw = None
+
+    def buffer(self, h, w, c, dtype=0):
+        self.specs.append((h, w, c))
+        return Slice(len(self.specs) - 1, 0, c, h, w)
+
+    def conv(self, src, dst, weight, bias, k, stride=1, relu=True, depthwise=False, res=None, impl=0):
+        self.ops.append(("conv", src, dst, torch.from_numpy(weight), torch.from_numpy(bias), k, stride, relu, depthwise, res))
+        return dst
+
+    def sppf_pool(self, s, c):
+        self.ops.append(("sppf", s, c))
+
+    def upsample2x(self, src, dst):
+        self.ops.append(("up", src, dst))
+        return dst
+
+    def set_heads(self, heads, strides, reg_max, nc):
+        self.heads = heads
+
+    def finalize(self):
+        return self
+
+    def execute(self, x):
+        B = x.shape[0]
+        bufs = [torch.zeros(B, c, h, w) for (h, w, c) in self.specs]
+
+        def get(s):
+            return x if s.buf < 0 else bufs[s.buf][:, s.coff:s.coff + s.c]
+
+        for op in self.ops:
+            if op[0] == "conv":
+                _, src, dst, w, b, k, stride, relu, dw, res = op
+                y = F.conv2d(get(src), w, b, stride=stride, padding=k // 2, groups=w.shape[0] if dw else 1)
+                if relu:
+                    y = y.relu()
+                if res is not None:
+                    y = y + get(res)
+                bufs[dst.buf][:, dst.coff:dst.coff + dst.c] = y
+            elif op[0] == "sppf":
+                _, s, c = op
+                t = get(s.sub(0, c))
+                for i in range(1, 4):
+                    t = F.max_pool2d(t, 5, 1, 2)
+                    bufs[s.buf][:, s.coff + i * c:s.coff + (i + 1) * c] = t
+            else:
+                _, src, dst = op
+                bufs[dst.buf][:, dst.coff:dst.coff + dst.c] = F.interpolate(get(src), scale_factor=2, mode="nearest")
+        return bufs

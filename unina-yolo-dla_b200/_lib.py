@@ -47,6 +47,12 @@ SIGNATURES = {
     "uyd_plan_num_launches": (C.c_int, [C.c_void_p]),
     "uyd_plan_buffer_ptr": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "uyd_plan_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "uyd_plan_run_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "uyd_plan_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_float)]),
+    "uyd_plan_set_timed_op": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "uyd_plan_timed_op_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
+    "uyd_plan_op_info": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_double),
+                                   C.POINTER(C.c_double)]),
     "uyd_plan_run_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "uyd_plan_export_head_nchw": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "uyd_decode_dfl": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,

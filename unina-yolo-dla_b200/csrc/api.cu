@@ -69,6 +69,8 @@ struct uyd_plan {
   int in_c = 0, in_h = 0, in_w = 0;  // network input extent (derived from the first conv)
   size_t bytes = 0;
   void *arena = nullptr;
+  int timed_op = -1, timed_used = 0;  // uyd_plan_set_timed_op
+  std::vector<cudaEvent_t> timed_ev;
 };
 
 extern "C" int uyd_version(void) { return 100; }
@@ -117,6 +119,7 @@ extern "C" int uyd_plan_destroy(uyd_plan *plan) {
     if (o.tc) tc_delete(o.tc);
   }
   if (plan->arena) cudaFree(plan->arena);
+  for (cudaEvent_t e : plan->timed_ev) cudaEventDestroy(e);
   delete plan;
   return UYD_OK;
 }
@@ -256,7 +259,10 @@ extern "C" int uyd_plan_finalize(uyd_plan *plan) {
   for (size_t i = 0; i < plan->bufs.size(); ++i) plan->bufs[i].ptr = (char *)plan->arena + offs[i];
   plan->bytes = total;
   const int halo_fallback = env_int("UYD_TC_NO_HALO", 0);
-  const int bo_mode = env_int("UYD_TC_BASE_OFFSET", 1);
+  // Measured on B200 (profiles/r01_probe.md): the UMMA swizzle XOR is a function of the absolute
+  // shared-memory address, so tap-shifted HALO descriptors need base_offset = 0 (mode 1, the
+  // "(addr >> 7) & 7" reading of the PTX text, produces wrong results and is kept as a probe).
+  const int bo_mode = env_int("UYD_TC_BASE_OFFSET", 0);
   const int stages = env_int("UYD_TC_STAGES", 0);
   for (Op &o : plan->ops) {
     if (o.kind != OP_CONV) continue;
@@ -292,11 +298,9 @@ extern "C" int uyd_plan_buffer_ptr(uyd_plan *plan, int id, void **ptr) {
   return UYD_OK;
 }
 
-extern "C" int uyd_plan_run(uyd_plan *plan, const float *x, int batch, uyd_stream stream) {
-  UYD_REQUIRE(plan && plan->finalized, UYD_E_STATE, "plan not finalized");
-  UYD_REQUIRE(batch > 0 && batch <= plan->max_batch, UYD_E_ARG, "batch %d outside (0, %d]", batch, plan->max_batch);
-  cudaStream_t s = (cudaStream_t)stream;
-  for (const Op &o : plan->ops) {
+// x_kind: 1 = NCHW fp32 frames, 2 = NCHW uint8 frames (divided by 255 on load)
+static int launch_op(uyd_plan *plan, const Op &o, const void *x, int x_kind, int batch, cudaStream_t s) {
+  {
     int e = UYD_OK;
     if (o.kind == OP_CONV) {
       const uyd_conv &d = o.conv;
@@ -308,7 +312,7 @@ extern "C" int uyd_plan_run(uyd_plan *plan, const float *x, int batch, uyd_strea
         a.n = batch;
         if (d.in_buf < 0) {
           UYD_REQUIRE(x, UYD_E_ARG, "uyd_plan_run: x is NULL");
-          a.in = x; a.ih = plan->in_h; a.iw = plan->in_w; a.in_pitch = 0; a.in_nchw_f32 = 1;
+          a.in = x; a.ih = plan->in_h; a.iw = plan->in_w; a.in_pitch = 0; a.in_nchw_f32 = x_kind;
         } else {
           const Buffer &ib = plan->bufs[d.in_buf];
           a.in = slice_ptr(plan, d.in_buf, d.in_coff); a.ih = ib.h; a.iw = ib.w; a.in_pitch = ib.c;
@@ -327,8 +331,112 @@ extern "C" int uyd_plan_run(uyd_plan *plan, const float *x, int batch, uyd_strea
       e = upsample2x_launch((const __nv_bfloat16 *)slice_ptr(plan, o.buf, o.coff), a.c,
                             (__nv_bfloat16 *)slice_ptr(plan, o.out_buf, o.out_coff), b.c, batch, a.h, a.w, o.c, s);
     }
-    if (e) return e;
+    return e;
   }
+}
+
+static int run_ops(uyd_plan *plan, const void *x, int x_kind, int batch, uyd_stream stream) {
+  UYD_REQUIRE(plan && plan->finalized, UYD_E_STATE, "plan not finalized");
+  UYD_REQUIRE(batch > 0 && batch <= plan->max_batch, UYD_E_ARG, "batch %d outside (0, %d]", batch, plan->max_batch);
+  cudaStream_t s = (cudaStream_t)stream;
+  for (size_t i = 0; i < plan->ops.size(); ++i) {
+    const bool timed = (int)i == plan->timed_op && plan->timed_used < (int)plan->timed_ev.size() / 2;
+    if (timed) UYD_CUDA(cudaEventRecord(plan->timed_ev[2 * plan->timed_used], s));
+    int e = launch_op(plan, plan->ops[i], x, x_kind, batch, s);
+    if (e) return e;
+    if (timed) UYD_CUDA(cudaEventRecord(plan->timed_ev[2 * plan->timed_used++ + 1], s));
+  }
+  return UYD_OK;
+}
+
+extern "C" int uyd_plan_run(uyd_plan *plan, const float *x, int batch, uyd_stream stream) {
+  return run_ops(plan, x, 1, batch, stream);
+}
+
+extern "C" int uyd_plan_run_u8(uyd_plan *plan, const uint8_t *x, int batch, uyd_stream stream) {
+  return run_ops(plan, x, 2, batch, stream);
+}
+
+// Times every op separately with CUDA events on `stream` (one pass, ops serialised as in a
+// normal run).  ms: [uyd_plan_num_launches].  Synchronises the stream.
+extern "C" int uyd_plan_profile(uyd_plan *plan, const float *x, int batch, uyd_stream stream, float *ms) {
+  UYD_REQUIRE(plan && plan->finalized && ms, UYD_E_STATE, "uyd_plan_profile: plan not finalized / ms NULL");
+  UYD_REQUIRE(batch > 0 && batch <= plan->max_batch, UYD_E_ARG, "batch %d outside (0, %d]", batch, plan->max_batch);
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t n = plan->ops.size();
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto &e : ev) UYD_CUDA(cudaEventCreate(&e));
+  UYD_CUDA(cudaEventRecord(ev[0], s));
+  for (size_t i = 0; i < n; ++i) {
+    int e = launch_op(plan, plan->ops[i], x, 1, batch, s);
+    if (e) return e;
+    UYD_CUDA(cudaEventRecord(ev[i + 1], s));
+  }
+  UYD_CUDA(cudaStreamSynchronize(s));
+  for (size_t i = 0; i < n; ++i) UYD_CUDA(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+  for (auto &e : ev) cudaEventDestroy(e);
+  return UYD_OK;
+}
+
+// Brackets op `op` with CUDA events in every following uyd_plan_run (up to `max_samples`
+// runs); op = -1 switches it off.  uyd_plan_timed_op_read synchronises those events.
+extern "C" int uyd_plan_set_timed_op(uyd_plan *plan, int op, int max_samples) {
+  UYD_REQUIRE(plan && plan->finalized, UYD_E_STATE, "plan not finalized");
+  UYD_REQUIRE(op >= -1 && op < (int)plan->ops.size() && max_samples >= 0 && max_samples <= 4096, UYD_E_ARG,
+              "uyd_plan_set_timed_op: bad arguments");
+  for (cudaEvent_t e : plan->timed_ev) cudaEventDestroy(e);
+  plan->timed_ev.clear();
+  plan->timed_used = 0;
+  plan->timed_op = op;
+  if (op >= 0) {
+    plan->timed_ev.resize(2 * (size_t)max_samples);
+    for (auto &e : plan->timed_ev) UYD_CUDA(cudaEventCreate(&e));
+  }
+  return UYD_OK;
+}
+
+extern "C" int uyd_plan_timed_op_read(uyd_plan *plan, float *total_ms, int *samples) {
+  UYD_REQUIRE(plan && total_ms && samples, UYD_E_ARG, "uyd_plan_timed_op_read: NULL argument");
+  float tot = 0.f;
+  for (int i = 0; i < plan->timed_used; ++i) {
+    float ms = 0.f;
+    UYD_CUDA(cudaEventSynchronize(plan->timed_ev[2 * i + 1]));
+    UYD_CUDA(cudaEventElapsedTime(&ms, plan->timed_ev[2 * i], plan->timed_ev[2 * i + 1]));
+    tot += ms;
+  }
+  *total_ms = tot;
+  *samples = plan->timed_used;
+  return UYD_OK;
+}
+
+// Human-readable description of op `op` plus its algorithmic work per image:
+// flops (2*MAC) and compulsory bytes (input slice + output slice, weights excluded).
+extern "C" int uyd_plan_op_info(uyd_plan *plan, int op, char *text, size_t text_len, double *flops_per_image,
+                                double *bytes_per_image) {
+  UYD_REQUIRE(plan && op >= 0 && op < (int)plan->ops.size() && text && text_len > 0, UYD_E_ARG, "uyd_plan_op_info: bad arguments");
+  const Op &o = plan->ops[op];
+  double fl = 0, by = 0;
+  if (o.kind == OP_CONV) {
+    const uyd_conv &d = o.conv;
+    const Buffer &ob = plan->bufs[d.out_buf];
+    const int ih = d.in_buf < 0 ? plan->in_h : plan->bufs[d.in_buf].h, iw = d.in_buf < 0 ? plan->in_w : plan->bufs[d.in_buf].w;
+    const double macs = (double)ob.h * ob.w * d.cout * d.k * d.k * (d.depthwise ? 1 : d.cin);
+    fl = 2 * macs;
+    by = (double)ih * iw * d.cin * (d.in_buf < 0 ? 4 : 2) + (double)ob.h * ob.w * d.cout * ob.elem_bytes() +
+         (d.res_buf >= 0 ? (double)ob.h * ob.w * d.cout * 2 : 0);
+    snprintf(text, text_len, "conv %d->%d k%d s%d%s %dx%d %s%s%s", d.cin, d.cout, d.k, d.stride, d.depthwise ? " dw" : "", ob.h,
+             ob.w, o.use_tc ? "tc:" : "direct", o.use_tc ? tc_mode_name(o.tc) : "", d.res_buf >= 0 ? " +res" : "");
+  } else if (o.kind == OP_SPPF) {
+    const Buffer &b = plan->bufs[o.buf];
+    by = (double)b.h * b.w * o.c * 2 * 4;
+    snprintf(text, text_len, "sppf_pool c%d %dx%d", o.c, b.h, b.w);
+  } else {
+    const Buffer &b = plan->bufs[o.out_buf];
+    by = (double)b.h * b.w * o.c * 2 * 1.25;
+    snprintf(text, text_len, "upsample2x c%d -> %dx%d", o.c, b.h, b.w);
+  }
+  if (flops_per_image) *flops_per_image = fl;
+  if (bytes_per_image) *bytes_per_image = by;
   return UYD_OK;
 }
 

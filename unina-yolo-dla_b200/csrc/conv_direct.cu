@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(kThreads) conv_direct_kernel(ConvArgs a) {
 
 // Stem: network input NCHW fp32 (the reference forward signature), Cin = 3.
 // weights bf16 [tap][ci][co]; one thread = one output pixel x CO_T channels.
-template <int CO_T>
+template <int CO_T, typename TIn>
 __global__ void __launch_bounds__(kThreads) conv_stem_nchw_kernel(ConvArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __nv_bfloat16 *ws = reinterpret_cast<__nv_bfloat16 *>(smem_raw);
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(kThreads) conv_stem_nchw_kernel(ConvArgs a) {
   const int oy = (int)((p / a.ow) % a.oh);
   const int n = (int)(p / ((long long)a.ow * a.oh));
   const int pad = a.k / 2;
-  const float *in = reinterpret_cast<const float *>(a.in);
+  const TIn *in = reinterpret_cast<const TIn *>(a.in);
   float acc[CO_T];
 #pragma unroll
   for (int i = 0; i < CO_T; ++i) acc[i] = 0.f;
@@ -160,8 +160,10 @@ __global__ void __launch_bounds__(kThreads) conv_stem_nchw_kernel(ConvArgs a) {
       const int ix = ox * a.stride + kx - pad;
       if (ix < 0 || ix >= a.iw) continue;
       for (int ci = 0; ci < a.cin; ++ci) {
-        // the frame stays fp32 (fp32 x bf16-weight -> fp32): no input rounding at all
-        const float x = in[(((long long)n * a.cin + ci) * a.ih + iy) * a.iw + ix];
+        // the frame stays fp32 (fp32 x bf16-weight -> fp32): no input rounding at all.
+        // uint8 frames are normalised exactly like the reference pre-process (x / 255).
+        float x = (float)in[(((long long)n * a.cin + ci) * a.ih + iy) * a.iw + ix];
+        if (sizeof(TIn) == 1) x = __fdiv_rn(x, 255.0f);
         const __nv_bfloat16 *wr = ws + (size_t)((ky * a.k + kx) * a.cin + ci) * a.cout + co0;
 #pragma unroll
         for (int j = 0; j < CO_T; ++j) acc[j] = fmaf(x, bf2f(wr[j]), acc[j]);
@@ -271,13 +273,16 @@ int direct_conv_launch(const ConvArgs &a, bool depthwise, cudaStream_t s) {
     const long long npix = (long long)a.n * a.oh * a.ow;
     const size_t wbytes = (size_t)a.k * a.k * a.cin * a.cout * 2;
     UYD_REQUIRE(wbytes <= 48 * 1024, UYD_E_UNSUPPORTED, "stem weights too large");
+    const bool u8 = a.in_nchw_f32 == 2;
     if (a.cout % 16 == 0) {
       dim3 grid((unsigned)((npix + kThreads - 1) / kThreads), a.cout / 16);
-      conv_stem_nchw_kernel<16><<<grid, kThreads, wbytes, s>>>(a);
+      if (u8) conv_stem_nchw_kernel<16, uint8_t><<<grid, kThreads, wbytes, s>>>(a);
+      else conv_stem_nchw_kernel<16, float><<<grid, kThreads, wbytes, s>>>(a);
     } else {
       UYD_REQUIRE(a.cout % 4 == 0, UYD_E_UNSUPPORTED, "stem cout must be a multiple of 4");
       dim3 grid((unsigned)((npix + kThreads - 1) / kThreads), a.cout / 4);
-      conv_stem_nchw_kernel<4><<<grid, kThreads, wbytes, s>>>(a);
+      if (u8) conv_stem_nchw_kernel<4, uint8_t><<<grid, kThreads, wbytes, s>>>(a);
+      else conv_stem_nchw_kernel<4, float><<<grid, kThreads, wbytes, s>>>(a);
     }
     return (int)cudaGetLastError();
   }

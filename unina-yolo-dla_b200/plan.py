@@ -104,8 +104,31 @@ class Plan:
         return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
     def run(self, x: torch.Tensor) -> None:
+        assert x.is_cuda and x.is_contiguous() and x.dtype in (torch.float32, torch.uint8)
+        fn = _lib.lib().uyd_plan_run if x.dtype == torch.float32 else _lib.lib().uyd_plan_run_u8
+        check(fn(self.handle, C.c_void_p(x.data_ptr()), x.shape[0], self._stream()), "uyd_plan_run")
+
+    def profile(self, x: torch.Tensor) -> list[float]:
+        """Per-op milliseconds of one pass (CUDA events around every op)."""
         assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
-        check(_lib.lib().uyd_plan_run(self.handle, C.c_void_p(x.data_ptr()), x.shape[0], self._stream()), "uyd_plan_run")
+        ms = (C.c_float * self.launches)()
+        check(_lib.lib().uyd_plan_profile(self.handle, C.c_void_p(x.data_ptr()), x.shape[0], self._stream(), ms),
+              "uyd_plan_profile")
+        return list(ms)
+
+    def op_info(self, op: int):
+        buf = C.create_string_buffer(160)
+        fl, by = C.c_double(), C.c_double()
+        check(_lib.lib().uyd_plan_op_info(self.handle, op, buf, 160, C.byref(fl), C.byref(by)), "uyd_plan_op_info")
+        return buf.value.decode(), fl.value, by.value
+
+    def set_timed_op(self, op: int, max_samples: int = 256) -> None:
+        check(_lib.lib().uyd_plan_set_timed_op(self.handle, op, max_samples), "uyd_plan_set_timed_op")
+
+    def timed_op_read(self):
+        tot, n = C.c_float(), C.c_int()
+        check(_lib.lib().uyd_plan_timed_op_read(self.handle, C.byref(tot), C.byref(n)), "uyd_plan_timed_op_read")
+        return tot.value, n.value
 
     def run_no_input(self, batch: int) -> None:
         """Runs a plan whose first op does not read the network input (layer-level tests)."""

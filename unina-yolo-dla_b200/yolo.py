@@ -375,7 +375,53 @@ class UninaYoloB200(nn.Module):
             raise _lib.UydError("no CUDA device: the B200 path has no CPU fallback")
         if not x.is_cuda:
             x = x.to(next(self.parameters()).device if next(self.parameters()).is_cuda else "cuda", non_blocking=True)
-        return x.float().contiguous()
+        # uint8 frames go to the GPU as they are: the stem conv divides by 255 on load
+        return x.contiguous() if x.dtype == torch.uint8 else x.float().contiguous()
+
+    @torch.no_grad()
+    def init_synthetic(self, seed: int = 0, cls_bias: float = -1.1, gain: float = 1.0) -> "UninaYoloB200":
+        """Seeded, data-free initialisation for parity runs and benchmarks: normal conv weights
+        with variance gain/fan_in and non-trivial BN statistics, so BN folding is exercised and
+        every layer output still depends on the frame (torch's default init decays ~10x per
+        stage and makes every score equal to the head bias, SURVEY.md header fact 3).
+        gain = 1 (LeCun) gives a contractive, well-conditioned network: 2^-9 bf16 rounding noise
+        is not amplified with depth.  gain = 2 (He) amplifies it ~4x, and BN statistics
+        calibrated on random data make the net chaotic (>50 % deviation even in fp16) --
+        DESIGN.md "Numerics" has the measurements."""
+        g = torch.Generator().manual_seed(seed)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d) and m.weight.requires_grad:
+                fan_in = m.weight.shape[1] * m.weight.shape[2] * m.weight.shape[3]
+                m.weight.copy_(torch.randn(m.weight.shape, generator=g) * (gain / fan_in) ** 0.5)
+                if m.bias is not None:
+                    m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+            elif isinstance(m, nn.BatchNorm2d):
+                m.weight.copy_(0.8 + 0.4 * torch.rand(m.weight.shape, generator=g))
+                m.bias.copy_(0.2 * (torch.rand(m.bias.shape, generator=g) - 0.5))
+                m.running_mean.copy_(0.2 * torch.randn(m.running_mean.shape, generator=g))
+                m.running_var.copy_(0.8 + 0.4 * torch.rand(m.running_var.shape, generator=g))
+        det = self.model[-1]
+        for box, cls in zip(det.cv2, det.cv3):
+            box[-1].bias.fill_(1.0)
+            cls[-1].bias.fill_(cls_bias)
+        self.refresh()
+        return self
+
+    @torch.no_grad()
+    def calibrate_cls_bias(self, x: torch.Tensor, per_image: int, conf: float = 0.25) -> float:
+        """Shifts the class-branch biases so that about ``per_image`` anchors per frame clear
+        ``conf`` on the frames ``x`` (synthetic-weight benchmarks need a realistic NMS load).
+        Runs the CUDA forward once; returns the applied shift."""
+        _, xs = self.forward(x)
+        det = self.model[-1]
+        best = torch.cat([t[:, 4 * det.reg_max:].amax(1).flatten(1) for t in xs], 1)  # [B, A] logits
+        k = max(1, min(best.shape[1] - 1, per_image))
+        kth = best.topk(k, dim=1).values[:, -1].mean().item()
+        shift = math.log(conf / (1 - conf)) - kth
+        for cls in det.cv3:
+            cls[-1].bias.add_(shift)
+        self.refresh()
+        return shift
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor, raw_heads: bool = True):
