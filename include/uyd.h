@@ -149,11 +149,12 @@ typedef struct uyd_detection {
  * cls [nc,H,W], reg [4,H,W] CHW fp32 per image; appends to dets (capacity cap) through the
  * device counter d_count (caller zeroes it); keeps a cell iff conf > thr (strict=1,
  * postprocess.hpp:116) or conf >= thr (strict=0, gpu_postprocess.cu:132). Also writes the
- * flat cell index of every detection to cell_idx when non-NULL (for deterministic order). */
+ * flat cell index (+ cell_base, so that levels get disjoint ranges) of every detection to
+ * cell_idx when non-NULL: the NMS uses it as a deterministic tie-break. */
 int uyd_decode_tlbr(uyd_ctx *ctx, const float *d_cls, const float *d_reg, uyd_detection *dets,
                     int *cell_idx, int *d_count, int cap, int grid_w, int grid_h, int stride,
                     int num_classes, float conf_thr, float conformal_q, int strict,
-                    uyd_stream stream);
+                    int cell_base, uyd_stream stream);
 
 /* Workspace size needed by uyd_nms for (batch, anchors). */
 size_t uyd_nms_workspace_bytes(int batch, int anchors);

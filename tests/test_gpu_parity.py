@@ -190,3 +190,30 @@ def test_full_forward_matches_oracle_bf16(T):
         assert T.rel_err(a.cpu()[:, 64:], b[:, 64:]) <= 1e-2
     assert T.rel_err(y.cpu()[:, :4], y_ref[:, :4]) <= 1e-2
     assert float((y.cpu()[:, 4:] - y_ref[:, 4:]).abs().max()) <= 1e-2
+
+
+def test_uint8_frames_equal_float_frames_divided_by_255(T):
+    """The stem's fused pre-process (x / 255, reference predictor semantics) is exact."""
+    m, _ = _paired_models(seed=2)
+    g = torch.Generator().manual_seed(4)
+    u8 = (torch.rand(2, 3, 320, 320, generator=g) * 255).to(torch.uint8)
+    y8 = m(u8.cuda(), raw_heads=False)
+    yf = m((u8.float() / 255).cuda(), raw_heads=False)
+    torch.cuda.synchronize()
+    assert torch.equal(y8, yf)
+
+
+def test_predict_returns_reference_rows(T):
+    from oracle import postproc as pp
+
+    m, ref = _paired_models(seed=0)
+    from oracle import init as oi
+    x = oi.seeded_frames(2, 640, seed=5).cuda()
+    m.calibrate_cls_bias(x, 800, 0.25)
+    y = m(x, raw_heads=False)
+    res = m.predict(x, conf=0.25, iou=0.7)
+    want = pp.non_max_suppression(y.cpu().numpy(), 0.25, 0.7, 300)
+    assert len(res) == 2
+    for r, w in zip(res, want):
+        assert r.shape[1] == 6 and r.cpu().numpy().tobytes() == w.tobytes()
+        assert 0 < len(w) <= 300

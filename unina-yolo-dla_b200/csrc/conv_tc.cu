@@ -41,6 +41,7 @@ struct TcParams {
   int tiles_x, tiles_y;  // HALO / PERTAP tiling of one image
   long long total_tiles;
   int stages;
+  int nacc;              // TMEM accumulator stages (nacc * N columns)
   uint32_t blk_bytes;    // one A block in shared memory
   uint32_t tx_bytes;     // bytes TMA delivers per A block
   uint32_t w_bytes;      // resident weights
@@ -60,6 +61,7 @@ namespace {
 
 constexpr int kThreads = 192;
 constexpr int kHaloRows = 18, kHaloPitch = 16, kTileH = 16, kTileW = 8;
+constexpr int kMaxAcc = 4;  // TMEM accumulator stages
 
 // ---- PTX wrappers ------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -126,29 +128,78 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo, uint32_t layout_type, uint32_t base_offset) {
+// K-major swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout) with
+// a zero start address; the 14-bit address field is added per MMA.
+__device__ __forceinline__ uint64_t make_desc_base(uint32_t sbo, uint32_t layout_type) {
   uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
   d |= (uint64_t)1 << 16;                   // leading byte offset (unused for swizzled K-major)
   d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
   d |= (uint64_t)1 << 46;                   // descriptor version (sm_100)
-  d |= (uint64_t)(base_offset & 7u) << 49;
   d |= (uint64_t)(layout_type & 7u) << 61;
   return d;
+}
+
+// One 16-column chunk of one accumulator row: bias -> ReLU -> residual -> store.
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&raw)[16], const float *bias_s, int c0, long long pix,
+                                               const TcParams &p) {
+  float v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float x = __uint_as_float(raw[i]) + bias_s[c0 + i];
+    v[i] = p.relu ? fmaxf(x, 0.f) : x;
+  }
+  const int nvalid = p.cout - c0;
+  if (nvalid >= 16) {
+    if (p.res) {
+      const __nv_bfloat16 *rp = p.res + pix * p.res_pitch + c0;
+      const uint4 r0 = *reinterpret_cast<const uint4 *>(rp), r1 = *reinterpret_cast<const uint4 *>(rp + 8);
+      const __nv_bfloat162 *h0 = reinterpret_cast<const __nv_bfloat162 *>(&r0);
+      const __nv_bfloat162 *h1 = reinterpret_cast<const __nv_bfloat162 *>(&r1);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f0 = __bfloat1622float2(h0[i]), f1 = __bfloat1622float2(h1[i]);
+        v[2 * i] += f0.x; v[2 * i + 1] += f0.y; v[8 + 2 * i] += f1.x; v[8 + 2 * i + 1] += f1.y;
+      }
+    }
+    if (p.out_f32) {
+      float *op = reinterpret_cast<float *>(p.out) + pix * p.out_pitch + c0;
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4 *>(op + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    } else {
+      __nv_bfloat16 *op = reinterpret_cast<__nv_bfloat16 *>(p.out) + pix * p.out_pitch + c0;
+      uint4 o0, o1;
+      uint32_t *w0 = reinterpret_cast<uint32_t *>(&o0), *w1 = reinterpret_cast<uint32_t *>(&o1);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        __nv_bfloat162 b = __floats2bfloat162_rn(v[8 + 2 * i], v[8 + 2 * i + 1]);
+        w0[i] = *reinterpret_cast<uint32_t *>(&a);
+        w1[i] = *reinterpret_cast<uint32_t *>(&b);
+      }
+      *reinterpret_cast<uint4 *>(op) = o0;
+      *reinterpret_cast<uint4 *>(op + 8) = o1;
+    }
+  } else {  // ragged tail (Cout not a multiple of 16): predicated scalar stores, static indices
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (i < nvalid) {
+        float x = v[i];
+        if (p.res) x += __bfloat162float(p.res[pix * p.res_pitch + c0 + i]);
+        if (p.out_f32) reinterpret_cast<float *>(p.out)[pix * p.out_pitch + c0 + i] = x;
+        else reinterpret_cast<__nv_bfloat16 *>(p.out)[pix * p.out_pitch + c0 + i] = __float2bfloat16_rn(x);
+      }
+    }
+  }
 }
 
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in,
@@ -159,15 +210,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t w_s = base;
   const uint32_t a_s = base + ((p.w_bytes + 1023u) & ~1023u);
   const uint32_t bar0 = a_s + (uint32_t)p.stages * p.blk_bytes;
-  // barrier map: full[stages] | empty[stages] | wfull | tfull[2] | tempty[2] | tmem slot
+  // barrier map: full[stages] | empty[stages] | wfull | tfull[4] | tempty[4] | tmem slot | bias[N]
   const uint32_t full0 = bar0, empty0 = bar0 + 8u * p.stages;
   const uint32_t wfull = empty0 + 8u * p.stages;
-  const uint32_t tfull0 = wfull + 8, tempty0 = tfull0 + 16, slot = tempty0 + 16;
+  const uint32_t tfull0 = wfull + 8, tempty0 = tfull0 + 8u * kMaxAcc, slot = tempty0 + 8u * kMaxAcc;
   uint32_t *slot_ptr = reinterpret_cast<uint32_t *>(smem_dyn + (slot - raw));
+  float *bias_s = reinterpret_cast<float *>(smem_dyn + (bar0 + 512u - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nacc = p.nacc;
   uint32_t tmem_cols = 32;
-  while (tmem_cols < 2u * p.N) tmem_cols <<= 1;
+  while (tmem_cols < (uint32_t)nacc * p.N) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -175,12 +228,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       mbar_init(empty0 + 8u * s, 1);
     }
     mbar_init(wfull, 1);
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < nacc; ++a) {
       mbar_init(tfull0 + 8u * a, 1);
       mbar_init(tempty0 + 8u * a, 128);
     }
     fence_barrier_init();
   }
+  for (int i = threadIdx.x; i < p.N; i += kThreads) bias_s[i] = i < p.cout ? p.bias[i] : 0.f;
   if (warp == 1) tmem_alloc(slot, tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -192,13 +246,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const int ksteps = p.cb_bytes / 32;
   const int cb_elems = p.cb_bytes / 2;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int stages = p.stages;
+  const uint32_t blk_bytes = p.blk_bytes, cb_bytes = p.cb_bytes;
 
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
       mbar_expect_tx(wfull, p.w_bytes);
       const int nblk = p.ncb * p.taps;
-      for (int i = 0; i < nblk; ++i) tma_load_2d(w_s + (uint32_t)i * p.N * p.cb_bytes, &tm_w, wfull, 0, i * p.N);
+      for (int i = 0; i < nblk; ++i) tma_load_2d(w_s + (uint32_t)i * p.N * cb_bytes, &tm_w, wfull, 0, i * p.N);
     }
     int stage = 0;
     uint32_t phase = 0;
@@ -212,7 +268,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
       for (int j = 0; j < blocks_per_tile; ++j) {
         mbar_wait(empty0 + 8u * stage, phase ^ 1u);
-        const uint32_t dst = a_s + (uint32_t)stage * p.blk_bytes;
+        const uint32_t dst = a_s + (uint32_t)stage * blk_bytes;
         const uint32_t fb = full0 + 8u * stage;
         if (lane == 0) mbar_expect_tx(fb, p.tx_bytes);
         __syncwarp();
@@ -223,7 +279,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           }
         } else if (p.mode == TC_HALO) {
           if (lane < kHaloRows)
-            tma_load_4d(dst + (uint32_t)lane * kHaloPitch * p.cb_bytes, &tm_in, fb, j * cb_elems, x0 - 1, y0 - 1 + lane, n);
+            tma_load_4d(dst + (uint32_t)lane * kHaloPitch * cb_bytes, &tm_in, fb, j * cb_elems, x0 - 1, y0 - 1 + lane, n);
         } else {
           if (lane == 0) {
             const int cb = j / p.taps, tap = j % p.taps;
@@ -231,7 +287,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             tma_load_4d(dst, &tm_in, fb, cb * cb_elems, x0 * p.stride + s - 1, y0 * p.stride + r - 1, n);
           }
         }
-        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        if (++stage == stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -239,6 +295,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     mbar_wait(wfull, 0);
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
+    const uint64_t adesc0 = make_desc_base(p.sbo_a, p.layout_type);
+    const uint64_t bdesc0 = make_desc_base(8u * cb_bytes, p.layout_type);
+    const uint32_t wblk_bytes = (uint32_t)p.N * cb_bytes;
+    const uint32_t idesc = p.idesc;
+    const bool halo = p.mode == TC_HALO;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       mbar_wait(tempty0 + 8u * acc, acc_phase ^ 1u);
       tc_fence_after();
@@ -247,37 +308,33 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         mbar_wait(full0 + 8u * stage, phase);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t ablk = a_s + (uint32_t)stage * p.blk_bytes;
+          const uint32_t ablk = a_s + (uint32_t)stage * blk_bytes;
+          uint32_t wblk = w_s + (uint32_t)(halo ? j * p.taps : j) * wblk_bytes;
+          uint32_t accum = j != 0;
           for (int t = 0; t < taps_in_block; ++t) {
-            uint32_t a_tap = ablk, wblk;
-            if (p.mode == TC_HALO) {
-              const int r = t / 3, s = t % 3;
-              a_tap = ablk + (uint32_t)(r * kHaloPitch + s) * p.cb_bytes;
-              wblk = w_s + (uint32_t)(j * p.taps + t) * p.N * p.cb_bytes;
-            } else {
-              wblk = w_s + (uint32_t)j * p.N * p.cb_bytes;  // FLAT: j = cb ; PERTAP: j = cb*taps + tap
-            }
+            // HALO: tap (r, s) starts (r * pitch + s) pixels into the halo block
+            const uint32_t a_tap = halo ? ablk + (uint32_t)((t / 3) * kHaloPitch + (t % 3)) * cb_bytes : ablk;
             for (int k = 0; k < ksteps; ++k) {
-              const uint32_t aaddr = a_tap + 32u * k;
-              const uint32_t bo = p.base_offset_mode ? ((aaddr >> 7) & 7u) : 0u;
-              const uint64_t ad = make_desc(aaddr, p.sbo_a, p.layout_type, bo);
-              const uint64_t bd = make_desc(wblk + 32u * k, 8u * p.cb_bytes, p.layout_type, 0);
-              umma_bf16(d_tmem, ad, bd, p.idesc, (uint32_t)((j | t | k) != 0));
+              const uint64_t ad = adesc0 + (uint64_t)(((a_tap + 32u * k) & 0x3FFFFu) >> 4);
+              const uint64_t bd = bdesc0 + (uint64_t)(((wblk + 32u * k) & 0x3FFFFu) >> 4);
+              umma_bf16(d_tmem, ad, bd, idesc, accum);
+              accum = 1;
             }
+            wblk += wblk_bytes;
           }
           umma_commit(empty0 + 8u * stage);  // smem slot is free once these MMAs retire
           if (j == blocks_per_tile - 1) umma_commit(tfull0 + 8u * acc);
         }
         __syncwarp();
-        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        if (++stage == stages) { stage = 0; phase ^= 1u; }
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
+      if (++acc == nacc) { acc = 0; acc_phase ^= 1u; }
     }
   } else {
     // ================= epilogue =================
     const int q = warp & 3;  // TMEM lane quarter this warp may touch
     const int m = q * 32 + lane;
+    const int nchunks = p.N >> 4;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -294,64 +351,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       mbar_wait(tfull0 + 8u * acc, acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * p.N;
-      for (int c0 = 0; c0 < p.N; c0 += 16) {
-        float v[16];
-        tmem_ld16(taddr + c0, v);
-        if (pix >= 0 && c0 < p.cout) {
-          const int nvalid = min(16, p.cout - c0);
+      uint32_t cur[16], nxt[16];
+      tmem_ld16_issue(taddr, cur);
+      tmem_ld_wait();
+      for (int c = 0; c < nchunks; ++c) {
+        const bool more = c + 1 < nchunks;
+        if (more) {
+          tmem_ld16_issue(taddr + 16u * (c + 1), nxt);  // in flight while this chunk is stored
+        } else {
+          tc_fence_before();
+          mbar_arrive(tempty0 + 8u * acc);  // every TMEM read of this accumulator has completed
+        }
+        if (pix >= 0 && c * 16 < p.cout) epilogue_chunk(cur, bias_s, c * 16, pix, p);
+        if (more) {
+          tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float x = v[i] + (i < nvalid ? p.bias[c0 + i] : 0.f);
-            if (p.relu) x = fmaxf(x, 0.f);
-            v[i] = x;
-          }
-          if (p.res) {
-            const __nv_bfloat16 *rp = p.res + pix * p.res_pitch + c0;
-            if (nvalid == 16) {
-              uint4 r0 = *reinterpret_cast<const uint4 *>(rp), r1 = *reinterpret_cast<const uint4 *>(rp + 8);
-              const __nv_bfloat162 *h0 = reinterpret_cast<const __nv_bfloat162 *>(&r0);
-              const __nv_bfloat162 *h1 = reinterpret_cast<const __nv_bfloat162 *>(&r1);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                float2 f0 = __bfloat1622float2(h0[i]), f1 = __bfloat1622float2(h1[i]);
-                v[2 * i] += f0.x; v[2 * i + 1] += f0.y; v[8 + 2 * i] += f1.x; v[8 + 2 * i + 1] += f1.y;
-              }
-            } else {
-              for (int i = 0; i < nvalid; ++i) v[i] += __bfloat162float(rp[i]);
-            }
-          }
-          if (p.out_f32) {
-            float *op = reinterpret_cast<float *>(p.out) + pix * p.out_pitch + c0;
-            if (nvalid == 16) {
-#pragma unroll
-              for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4 *>(op + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-            } else {
-              for (int i = 0; i < nvalid; ++i) op[i] = v[i];
-            }
-          } else {
-            __nv_bfloat16 *op = reinterpret_cast<__nv_bfloat16 *>(p.out) + pix * p.out_pitch + c0;
-            if (nvalid == 16) {
-              uint4 o0, o1;
-              uint32_t *w0 = reinterpret_cast<uint32_t *>(&o0), *w1 = reinterpret_cast<uint32_t *>(&o1);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                __nv_bfloat162 a = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-                __nv_bfloat162 b = __floats2bfloat162_rn(v[8 + 2 * i], v[8 + 2 * i + 1]);
-                w0[i] = *reinterpret_cast<uint32_t *>(&a);
-                w1[i] = *reinterpret_cast<uint32_t *>(&b);
-              }
-              *reinterpret_cast<uint4 *>(op) = o0;
-              *reinterpret_cast<uint4 *>(op + 8) = o1;
-            } else {
-              for (int i = 0; i < nvalid; ++i) op[i] = __float2bfloat16_rn(v[i]);
-            }
-          }
+          for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
         }
       }
-      tc_fence_before();
-      mbar_arrive(tempty0 + 8u * acc);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
+      if (++acc == nacc) { acc = 0; acc_phase ^= 1u; }
     }
   }
   tc_fence_before();
@@ -467,7 +485,7 @@ int tc_prepare(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int i
   }
   // blocks must keep 1024-byte alignment so every swizzle mode stays atom-aligned
   p.blk_bytes = (p.blk_bytes + 1023u) & ~1023u;
-  const size_t budget = 227 * 1024 - 1024 - 256;
+  const size_t budget = 227 * 1024 - 1024 - 1024;
   const size_t wres = (p.w_bytes + 1023u) & ~1023u;
   UYD_REQUIRE(wres + 2 * (size_t)p.blk_bytes <= budget, UYD_E_UNSUPPORTED, "conv_tc: weights (%u B) leave no room for 2 stages",
               p.w_bytes);
@@ -476,7 +494,8 @@ int tc_prepare(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int i
   if (stages > want) stages = want;
   if (stages_override > 0 && stages_override < stages) stages = stages_override;
   p.stages = stages;
-  tc->smem = 1024 + wres + (size_t)stages * p.blk_bytes + 256;
+  p.nacc = 4 * p.N <= 512 ? 4 : 2;
+  tc->smem = 1024 + wres + (size_t)stages * p.blk_bytes + 512 + 512;  // + barriers + bias
   p.out = out_base;
   p.out_pitch = out_pitch;
   p.out_f32 = out_f32;

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(kThreads) decode_dfl_kernel(const float *__res
 __global__ void __launch_bounds__(kThreads) decode_tlbr_kernel(const float *__restrict__ cls, const float *__restrict__ reg,
                                                                uyd_detection *dets, int *cell_idx, int *d_count, int cap,
                                                                int gw, int gh, int stride, int nc, float thr, float q,
-                                                               int strict) {
+                                                               int strict, int cell_base) {
   const int g = blockIdx.x * kThreads + threadIdx.x;
   const int hw = gw * gh;
   bool has = false;
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(kThreads) decode_tlbr_kernel(const float *__re
   uyd_detection d;
   d.x1 = x1; d.y1 = y1; d.x2 = x2; d.y2 = y2; d.confidence = mc; d.class_id = best; d.valid = 1; d._pad = 0;
   dets[slot] = d;
-  if (cell_idx) cell_idx[slot] = g;
+  if (cell_idx) cell_idx[slot] = cell_base + g;
 }
 
 }  // namespace
@@ -133,12 +133,12 @@ extern "C" int uyd_decode_dfl(uyd_ctx *ctx, const float *head, int batch, int h,
 
 extern "C" int uyd_decode_tlbr(uyd_ctx *ctx, const float *d_cls, const float *d_reg, uyd_detection *dets, int *cell_idx,
                                int *d_count, int cap, int grid_w, int grid_h, int stride, int num_classes,
-                               float conf_thr, float conformal_q, int strict, uyd_stream stream) {
+                               float conf_thr, float conformal_q, int strict, int cell_base, uyd_stream stream) {
   (void)ctx;
   UYD_REQUIRE(d_cls && d_reg && dets && d_count && cap > 0 && grid_w > 0 && grid_h > 0, UYD_E_ARG,
               "uyd_decode_tlbr: bad arguments");
   const int hw = grid_w * grid_h;
   uyd::decode_tlbr_kernel<<<uyd::ceil_div(hw, uyd::kThreads), uyd::kThreads, 0, (cudaStream_t)stream>>>(
-      d_cls, d_reg, dets, cell_idx, d_count, cap, grid_w, grid_h, stride, num_classes, conf_thr, conformal_q, strict);
+      d_cls, d_reg, dets, cell_idx, d_count, cap, grid_w, grid_h, stride, num_classes, conf_thr, conformal_q, strict, cell_base);
   return (int)cudaGetLastError();
 }

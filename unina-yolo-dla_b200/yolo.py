@@ -388,18 +388,9 @@ class UninaYoloB200(nn.Module):
         is not amplified with depth.  gain = 2 (He) amplifies it ~4x, and BN statistics
         calibrated on random data make the net chaotic (>50 % deviation even in fp16) --
         DESIGN.md "Numerics" has the measurements."""
-        g = torch.Generator().manual_seed(seed)
-        for m in self.modules():
-            if isinstance(m, nn.Conv2d) and m.weight.requires_grad:
-                fan_in = m.weight.shape[1] * m.weight.shape[2] * m.weight.shape[3]
-                m.weight.copy_(torch.randn(m.weight.shape, generator=g) * (gain / fan_in) ** 0.5)
-                if m.bias is not None:
-                    m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
-            elif isinstance(m, nn.BatchNorm2d):
-                m.weight.copy_(0.8 + 0.4 * torch.rand(m.weight.shape, generator=g))
-                m.bias.copy_(0.2 * (torch.rand(m.bias.shape, generator=g) - 0.5))
-                m.running_mean.copy_(0.2 * torch.randn(m.running_mean.shape, generator=g))
-                m.running_var.copy_(0.8 + 0.4 * torch.rand(m.running_var.shape, generator=g))
+        from .synth import synthetic_init_
+
+        synthetic_init_(self, seed, gain)
         det = self.model[-1]
         for box, cls in zip(det.cv2, det.cv3):
             box[-1].bias.fill_(1.0)
