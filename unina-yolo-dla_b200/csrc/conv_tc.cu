@@ -42,6 +42,7 @@ struct TcParams {
   long long total_tiles;
   int stages;
   int nacc;              // TMEM accumulator stages (nacc * N columns)
+  int stage_pitch;       // bytes per row of the epilogue staging tile (0 = direct stores)
   uint32_t blk_bytes;    // one A block in shared memory
   uint32_t tx_bytes;     // bytes TMA delivers per A block
   uint32_t w_bytes;      // resident weights
@@ -202,6 +203,48 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&raw)[16], const 
   }
 }
 
+// Same arithmetic, but the 16 results go to this thread's row of the per-warp staging tile in
+// shared memory; the warp then copies whole rows out with 16-byte lanes laid along the row, so
+// one store instruction touches 32*16/row_bytes rows instead of 32 different 128-byte lines.
+__device__ __forceinline__ void epilogue_chunk_staged(const uint32_t (&raw)[16], const float *bias_s, int c0, long long pix,
+                                                      const TcParams &p, unsigned char *srow) {
+  float v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float x = __uint_as_float(raw[i]) + bias_s[c0 + i];
+    v[i] = p.relu ? fmaxf(x, 0.f) : x;
+  }
+  if (p.res && pix >= 0) {  // residual convs have Cout % 16 == 0 (checked on the host)
+    const __nv_bfloat16 *rp = p.res + pix * p.res_pitch + c0;
+    const uint4 r0 = *reinterpret_cast<const uint4 *>(rp), r1 = *reinterpret_cast<const uint4 *>(rp + 8);
+    const __nv_bfloat162 *h0 = reinterpret_cast<const __nv_bfloat162 *>(&r0);
+    const __nv_bfloat162 *h1 = reinterpret_cast<const __nv_bfloat162 *>(&r1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f0 = __bfloat1622float2(h0[i]), f1 = __bfloat1622float2(h1[i]);
+      v[2 * i] += f0.x; v[2 * i + 1] += f0.y; v[8 + 2 * i] += f1.x; v[8 + 2 * i + 1] += f1.y;
+    }
+  }
+  if (p.out_f32) {
+    float4 *sp = reinterpret_cast<float4 *>(srow + c0 * 4);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sp[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else {
+    uint4 o0, o1;
+    uint32_t *w0 = reinterpret_cast<uint32_t *>(&o0), *w1 = reinterpret_cast<uint32_t *>(&o1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      __nv_bfloat162 b = __floats2bfloat162_rn(v[8 + 2 * i], v[8 + 2 * i + 1]);
+      w0[i] = *reinterpret_cast<uint32_t *>(&a);
+      w1[i] = *reinterpret_cast<uint32_t *>(&b);
+    }
+    uint4 *sp = reinterpret_cast<uint4 *>(srow + c0 * 2);
+    sp[0] = o0;
+    sp[1] = o1;
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in,
                                                               const __grid_constant__ CUtensorMap tm_w, const TcParams p) {
   extern __shared__ unsigned char smem_dyn[];
@@ -335,6 +378,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int q = warp & 3;  // TMEM lane quarter this warp may touch
     const int m = q * 32 + lane;
     const int nchunks = p.N >> 4;
+    const bool staged = p.stage_pitch != 0;
+    const int esize = p.out_f32 ? 4 : 2;
+    const int lpr = staged ? (p.cout * esize) / 16 : 1;  // 16-byte lanes per output row
+    const int rows_per_it = 32 / lpr;
+    const long long out_row_pitch = (long long)p.out_pitch * esize;
+    long long *spix = reinterpret_cast<long long *>(smem_dyn + (bar0 + 1024u - raw)) + (warp - 2) * 32;
+    unsigned char *swarp = smem_dyn + (bar0 + 2048u - raw) + (size_t)(warp - 2) * 32 * p.stage_pitch;
+    unsigned char *srow = swarp + (size_t)lane * p.stage_pitch;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -354,20 +405,38 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       uint32_t cur[16], nxt[16];
       tmem_ld16_issue(taddr, cur);
       tmem_ld_wait();
+      if (staged) spix[lane] = pix;
       for (int c = 0; c < nchunks; ++c) {
         const bool more = c + 1 < nchunks;
         if (more) {
-          tmem_ld16_issue(taddr + 16u * (c + 1), nxt);  // in flight while this chunk is stored
+          tmem_ld16_issue(taddr + 16u * (c + 1), nxt);  // in flight while this chunk is processed
         } else {
           tc_fence_before();
           mbar_arrive(tempty0 + 8u * acc);  // every TMEM read of this accumulator has completed
         }
-        if (pix >= 0 && c * 16 < p.cout) epilogue_chunk(cur, bias_s, c * 16, pix, p);
+        if (staged) {
+          if (c * 16 < p.cout) epilogue_chunk_staged(cur, bias_s, c * 16, pix, p, srow);
+        } else if (pix >= 0 && c * 16 < p.cout) {
+          epilogue_chunk(cur, bias_s, c * 16, pix, p);
+        }
         if (more) {
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
         }
+      }
+      if (staged) {  // coalesced copy-out of this warp's 32 rows
+        __syncwarp();
+        const int sub = lane / lpr, chunk = lane % lpr;
+        unsigned char *gout = reinterpret_cast<unsigned char *>(p.out);
+        for (int r0 = 0; r0 < 32; r0 += rows_per_it) {
+          const int r = r0 + sub;
+          const long long pr = spix[r];
+          if (pr >= 0)
+            *reinterpret_cast<uint4 *>(gout + pr * out_row_pitch + chunk * 16) =
+                *reinterpret_cast<const uint4 *>(swarp + r * p.stage_pitch + chunk * 16);
+        }
+        __syncwarp();
       }
       if (++acc == nacc) { acc = 0; acc_phase ^= 1u; }
     }
@@ -485,8 +554,23 @@ int tc_prepare(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int i
   }
   // blocks must keep 1024-byte alignment so every swizzle mode stays atom-aligned
   p.blk_bytes = (p.blk_bytes + 1023u) & ~1023u;
-  const size_t budget = 227 * 1024 - 1024 - 1024;
+  // epilogue staging: rows of N * esize bytes (+16 B pad against bank conflicts); usable when a
+  // row of real output is a power-of-two number of 16-byte lanes
+  const int esize = out_f32 ? 4 : 2;
+  const int row_bytes = d.cout * esize;
+  const bool can_stage = row_bytes >= 16 && row_bytes <= 512 && (row_bytes & (row_bytes - 1)) == 0 &&
+                         (out_pitch * esize) % 16 == 0 && (reinterpret_cast<uintptr_t>(out_base) & 15) == 0;
+  p.stage_pitch = can_stage ? p.N * esize + 16 : 0;
+  const size_t tail = 2048 + (size_t)128 * p.stage_pitch;  // barriers + bias + row->pixel map + staging
   const size_t wres = (p.w_bytes + 1023u) & ~1023u;
+  const size_t budget = 227 * 1024 - 1024 - tail;
+  if (p.mode == TC_HALO && wres + 2 * (size_t)p.blk_bytes > budget) {  // halo blocks too big: one box per tap
+    p.mode = TC_PERTAP;
+    p.blk_bytes = 128u * p.cb_bytes;
+    p.tx_bytes = p.blk_bytes;
+    p.sbo_a = 8u * p.cb_bytes;
+    p.blk_bytes = (p.blk_bytes + 1023u) & ~1023u;
+  }
   UYD_REQUIRE(wres + 2 * (size_t)p.blk_bytes <= budget, UYD_E_UNSUPPORTED, "conv_tc: weights (%u B) leave no room for 2 stages",
               p.w_bytes);
   int stages = (int)((budget - wres) / p.blk_bytes);
@@ -495,7 +579,7 @@ int tc_prepare(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int i
   if (stages_override > 0 && stages_override < stages) stages = stages_override;
   p.stages = stages;
   p.nacc = 4 * p.N <= 512 ? 4 : 2;
-  tc->smem = 1024 + wres + (size_t)stages * p.blk_bytes + 512 + 512;  // + barriers + bias
+  tc->smem = 1024 + wres + (size_t)stages * p.blk_bytes + tail;
   p.out = out_base;
   p.out_pitch = out_pitch;
   p.out_f32 = out_f32;
