@@ -83,6 +83,21 @@ typedef struct uyd_conv {
  * bias: host fp32 [cout].  Packed to the kernel's layout and uploaded here. */
 int uyd_plan_add_conv(uyd_plan *plan, const uyd_conv *desc, const float *weight, const float *bias);
 
+/* INT8 convolution (QAT fake-quant semantics of qat.py:109-124 as an integer computation,
+ * oracle/quant.py): input slice int8 (UYD_S8 buffer), weight int8 [cout][cin][k][k] already
+ * quantised, exact int32 accumulation, y = float(acc) * mult[c] + bias[c] (fp32, separate
+ * round-to-nearest multiply and add), optional ReLU.  The output buffer's dtype selects the
+ * epilogue: UYD_S8 -> q = clamp(rne(y * out_scale), -127, 127) (the consumer's input quantiser),
+ * UYD_F32 / UYD_BF16 -> y.  Bit-exact w.r.t. the integer reference. */
+typedef struct uyd_conv_s8 {
+  int in_buf, in_coff, out_buf, out_coff;
+  int cin, cout, k, stride, relu;
+  float out_scale;
+  int impl, reserved;
+} uyd_conv_s8;
+int uyd_plan_add_conv_s8(uyd_plan *plan, const uyd_conv_s8 *desc, const int8_t *weight_q, const float *mult,
+                         const float *bias);
+
 /* SPPF cascade: reads slice [coff, coff+c) of buf and writes pool5, pool5^2, pool5^3 to
  * slices [coff+c, coff+2c), [coff+2c, ..), [coff+3c, ..) of the same buffer
  * (trainer.py:119-124; -inf padding). */

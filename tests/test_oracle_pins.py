@@ -141,3 +141,29 @@ def test_non_max_suppression_pipeline_matches_torchvision_composition():
         assert len(outs[b]) == 300
     empty = pp.non_max_suppression(np.zeros((1, 8, 100), np.float32), 0.25, 0.7)
     assert empty[0].shape == (0, 6)
+
+
+def test_int8_reference_is_the_fake_quant_graph():
+    """oracle/quant.py: the integer statement equals conv(fake_quant(x), fake_quant(w)) -> BN -> ReLU
+    (pytorch-quantization semantics as configured at qat.py:109-124) up to fp32 rounding."""
+    import torch.nn.functional as F
+    from oracle import quant as oq
+
+    rng = np.random.default_rng(0)
+    x = rng.normal(0, 1, (2, 16, 12, 12)).astype(np.float32)
+    w = rng.normal(0, 0.1, (8, 16, 3, 3)).astype(np.float32)
+    ax, aw = float(np.abs(x).max()), float(np.abs(w).max())
+    qx, qw = oq.quantize(x, ax), oq.quantize(w, aw)
+    assert qx.min() >= -127 and qx.max() == 127 or qx.min() == -127
+    g, b, mu, var = rng.uniform(0.8, 1.2, 8), rng.uniform(-0.1, 0.1, 8), rng.normal(0, 0.2, 8), rng.uniform(0.8, 1.2, 8)
+    m, bb = oq.fold_multiplier(ax, aw, g, b, mu, var, eps=1e-3)
+    acc, y, qy = oq.conv_int8(qx, qw, m, bb, 1, True, out_scale=float(oq.scale_of(2.0)))
+    fx = torch.from_numpy(qx.astype(np.float64) * ax / 127)
+    fw = torch.from_numpy(qw.astype(np.float64) * aw / 127)
+    ref = F.conv2d(fx, fw, padding=1).numpy()
+    ref = (ref - mu[None, :, None, None]) * (g / np.sqrt(var + 1e-3))[None, :, None, None] + b[None, :, None, None]
+    ref = np.maximum(ref, 0)
+    np.testing.assert_allclose(y, ref, rtol=2e-5, atol=2e-6)
+    assert np.abs(qy.astype(np.int32) - np.clip(np.rint(ref * 127 / 2.0), -127, 127)).max() <= 1
+    # half-to-even rounding and the narrow range
+    assert list(oq.quantize(np.array([0.5, 1.5, 2.5, -300.0, 300.0], np.float32), 127.0)) == [0, 2, 2, -127, 127]

@@ -22,6 +22,12 @@ class ConvDesc(C.Structure):
         "k", "stride", "depthwise", "relu", "impl", "reserved")]
 
 
+class ConvS8Desc(C.Structure):
+    _fields_ = [("in_buf", C.c_int), ("in_coff", C.c_int), ("out_buf", C.c_int), ("out_coff", C.c_int), ("cin", C.c_int),
+                ("cout", C.c_int), ("k", C.c_int), ("stride", C.c_int), ("relu", C.c_int), ("out_scale", C.c_float),
+                ("impl", C.c_int), ("reserved", C.c_int)]
+
+
 class Detection(C.Structure):
     """Layout-identical to the reference GpuDetection (gpu_postprocess.h:27-33)."""
     _fields_ = [("x1", C.c_float), ("y1", C.c_float), ("x2", C.c_float), ("y2", C.c_float),
@@ -39,6 +45,7 @@ SIGNATURES = {
     "uyd_plan_destroy": (C.c_int, [C.c_void_p]),
     "uyd_plan_add_buffer": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "uyd_plan_add_conv": (C.c_int, [C.c_void_p, C.POINTER(ConvDesc), C.c_void_p, C.c_void_p]),
+    "uyd_plan_add_conv_s8": (C.c_int, [C.c_void_p, C.POINTER(ConvS8Desc), C.c_void_p, C.c_void_p, C.c_void_p]),
     "uyd_plan_add_sppf_pool": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "uyd_plan_add_upsample2x": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "uyd_plan_set_heads": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int]),

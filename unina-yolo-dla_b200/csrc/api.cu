@@ -23,7 +23,11 @@ size_t tc_weight_bytes(const uyd_conv &d);
 void tc_pack_weights(const uyd_conv &d, const float *w, void *dst_host);
 int tc_prepare(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int ih, int iw, int max_batch, void *out_base,
                int out_pitch, int out_f32, const void *res_base, int res_pitch, void *w_dev, const float *bias_dev,
-               int mode_override, int base_offset_mode, int stages_override);
+               int mode_override, int base_offset_mode, int stages_override, int i8 = 0, const float *mult_dev = nullptr,
+               float out_scale = 0.f, int out_kind = 0);
+bool tc_supported_s8(int cin, int cout, int k, int stride, int in_pitch, int in_coff, int out_pitch, int out_coff, int out_esize);
+size_t tc_weight_bytes_s8(int cin, int cout, int k);
+void tc_pack_weights_s8(int cin, int cout, int k, const int8_t *w, void *dst_host);
 int tc_launch(const TcConv *tc, int n0, int nb, int sm_count, cudaStream_t s);
 TcConv *tc_new();
 void tc_delete(TcConv *);
@@ -43,7 +47,7 @@ struct uyd_ctx {
   int sm_count = 0;
 };
 
-enum OpKind { OP_CONV = 0, OP_SPPF = 1, OP_UPSAMPLE = 2 };
+enum OpKind { OP_CONV = 0, OP_SPPF = 1, OP_UPSAMPLE = 2, OP_CONV_S8 = 3 };
 
 struct Op {
   OpKind kind;
@@ -54,6 +58,11 @@ struct Op {
   void *w_dev = nullptr;
   float *b_dev = nullptr;
   TcConv *tc = nullptr;
+  // int8 conv
+  std::vector<float> m_host;
+  float *m_dev = nullptr;
+  float out_scale = 0.f;
+  int out_kind = 0;
   // sppf / upsample
   int buf = -1, coff = 0, c = 0, out_buf = -1, out_coff = 0;
 };
@@ -116,6 +125,7 @@ extern "C" int uyd_plan_destroy(uyd_plan *plan) {
   for (Op &o : plan->ops) {
     if (o.w_dev) cudaFree(o.w_dev);
     if (o.b_dev) cudaFree(o.b_dev);
+    if (o.m_dev) cudaFree(o.m_dev);
     if (o.tc) tc_delete(o.tc);
   }
   if (plan->arena) cudaFree(plan->arena);
@@ -198,6 +208,48 @@ extern "C" int uyd_plan_add_conv(uyd_plan *plan, const uyd_conv *d, const float 
   return UYD_OK;
 }
 
+extern "C" int uyd_plan_add_conv_s8(uyd_plan *plan, const uyd_conv_s8 *d, const int8_t *weight_q, const float *mult,
+                                    const float *bias) {
+  UYD_REQUIRE(plan && d && weight_q && mult && bias, UYD_E_ARG, "uyd_plan_add_conv_s8: NULL argument");
+  UYD_REQUIRE(!plan->finalized, UYD_E_STATE, "plan already finalized");
+  UYD_REQUIRE((d->k == 1 || d->k == 3) && (d->stride == 1 || d->stride == 2), UYD_E_UNSUPPORTED, "conv k=%d s=%d unsupported",
+              d->k, d->stride);
+  int e;
+  if ((e = check_slice(plan, d->in_buf, d->in_coff, d->cin, "conv_s8 input"))) return e;
+  if ((e = check_slice(plan, d->out_buf, d->out_coff, d->cout, "conv_s8 output"))) return e;
+  const Buffer &ib = plan->bufs[d->in_buf], &ob = plan->bufs[d->out_buf];
+  UYD_REQUIRE(ib.dtype == UYD_S8, UYD_E_ARG, "conv_s8 input buffer must be UYD_S8");
+  const int pad = d->k / 2;
+  UYD_REQUIRE(ob.h == (ib.h + 2 * pad - d->k) / d->stride + 1 && ob.w == (ib.w + 2 * pad - d->k) / d->stride + 1, UYD_E_ARG,
+              "conv_s8 output extent mismatch");
+  UYD_REQUIRE(ob.dtype != UYD_S8 || d->out_scale > 0.f, UYD_E_ARG, "conv_s8: int8 output needs out_scale > 0");
+  Op op;
+  op.kind = OP_CONV_S8;
+  op.conv.in_buf = d->in_buf; op.conv.in_coff = d->in_coff; op.conv.out_buf = d->out_buf; op.conv.out_coff = d->out_coff;
+  op.conv.res_buf = -1; op.conv.cin = d->cin; op.conv.cout = d->cout; op.conv.k = d->k; op.conv.stride = d->stride;
+  op.conv.relu = d->relu;
+  op.out_scale = d->out_scale;
+  op.out_kind = ob.dtype == UYD_S8 ? 2 : (ob.dtype == UYD_F32 ? 1 : 0);
+  const bool tc_ok = tc_supported_s8(d->cin, d->cout, d->k, d->stride, ib.c, d->in_coff, ob.c, d->out_coff, (int)ob.elem_bytes());
+  if (d->impl == UYD_IMPL_TC) {
+    UYD_REQUIRE(tc_ok, UYD_E_UNSUPPORTED, "conv_s8 %d->%d k%d s%d cannot run on the tensor-core path", d->cin, d->cout, d->k, d->stride);
+    op.use_tc = true;
+  } else if (d->impl == UYD_IMPL_AUTO) {
+    op.use_tc = tc_ok;
+  }
+  if (op.use_tc) {
+    op.w_host.resize(tc_weight_bytes_s8(d->cin, d->cout, d->k));
+    tc_pack_weights_s8(d->cin, d->cout, d->k, weight_q, op.w_host.data());
+  } else {
+    op.w_host.resize(direct_weight_bytes_s8(d->cin, d->cout, d->k));
+    direct_pack_weights_s8(d->cin, d->cout, d->k, weight_q, op.w_host.data());
+  }
+  op.b_host.assign(bias, bias + d->cout);
+  op.m_host.assign(mult, mult + d->cout);
+  plan->ops.push_back(std::move(op));
+  return UYD_OK;
+}
+
 extern "C" int uyd_plan_add_sppf_pool(uyd_plan *plan, int buf, int coff, int c) {
   UYD_REQUIRE(plan && !plan->finalized, UYD_E_STATE, "plan missing or finalized");
   int e;
@@ -265,7 +317,7 @@ extern "C" int uyd_plan_finalize(uyd_plan *plan) {
   const int bo_mode = env_int("UYD_TC_BASE_OFFSET", 0);
   const int stages = env_int("UYD_TC_STAGES", 0);
   for (Op &o : plan->ops) {
-    if (o.kind != OP_CONV) continue;
+    if (o.kind != OP_CONV && o.kind != OP_CONV_S8) continue;
     UYD_CUDA(cudaMalloc(&o.w_dev, o.w_host.size()));
     UYD_CUDA(cudaMemcpy(o.w_dev, o.w_host.data(), o.w_host.size(), cudaMemcpyHostToDevice));
     UYD_CUDA(cudaMalloc((void **)&o.b_dev, o.b_host.size() * 4));
@@ -273,6 +325,20 @@ extern "C" int uyd_plan_finalize(uyd_plan *plan) {
     plan->bytes += o.w_host.size() + o.b_host.size() * 4;
     o.w_host.clear();
     o.w_host.shrink_to_fit();
+    if (o.kind == OP_CONV_S8) {
+      UYD_CUDA(cudaMalloc((void **)&o.m_dev, o.m_host.size() * 4));
+      UYD_CUDA(cudaMemcpy(o.m_dev, o.m_host.data(), o.m_host.size() * 4, cudaMemcpyHostToDevice));
+      if (o.use_tc) {
+        const uyd_conv &d = o.conv;
+        const Buffer &ib = plan->bufs[d.in_buf], &ob = plan->bufs[d.out_buf];
+        o.tc = tc_new();
+        int e = tc_prepare(o.tc, d, slice_ptr(plan, d.in_buf, d.in_coff), ib.c, ib.h, ib.w, plan->max_batch,
+                           slice_ptr(plan, d.out_buf, d.out_coff), ob.c, 0, nullptr, 0, o.w_dev, o.b_dev, halo_fallback ? 2 : -1,
+                           bo_mode, stages, 1, o.m_dev, o.out_scale, o.out_kind);
+        if (e) return e;
+      }
+      continue;
+    }
     if (o.use_tc) {
       const uyd_conv &d = o.conv;
       const Buffer &ib = plan->bufs[d.in_buf], &ob = plan->bufs[d.out_buf];
@@ -322,6 +388,18 @@ static int launch_op(uyd_plan *plan, const Op &o, const void *x, int x_kind, int
         if (d.res_buf >= 0) { a.res = slice_ptr(plan, d.res_buf, d.res_coff); a.res_pitch = plan->bufs[d.res_buf].c; }
         a.w = o.w_dev; a.bias = o.b_dev; a.cin = d.cin; a.cout = d.cout; a.k = d.k; a.stride = d.stride; a.relu = d.relu;
         e = direct_conv_launch(a, d.depthwise != 0, s);
+      }
+    } else if (o.kind == OP_CONV_S8) {
+      const uyd_conv &d = o.conv;
+      if (o.use_tc) {
+        e = tc_launch(o.tc, 0, batch, plan->ctx->sm_count, s);
+      } else {
+        const Buffer &ib = plan->bufs[d.in_buf], &ob = plan->bufs[d.out_buf];
+        ConvArgs a{};
+        a.n = batch; a.in = slice_ptr(plan, d.in_buf, d.in_coff); a.ih = ib.h; a.iw = ib.w; a.in_pitch = ib.c;
+        a.out = slice_ptr(plan, d.out_buf, d.out_coff); a.oh = ob.h; a.ow = ob.w; a.out_pitch = ob.c;
+        a.w = o.w_dev; a.bias = o.b_dev; a.cin = d.cin; a.cout = d.cout; a.k = d.k; a.stride = d.stride; a.relu = d.relu;
+        e = direct_conv_s8_launch(a, o.m_dev, o.out_scale, o.out_kind, s);
       }
     } else if (o.kind == OP_SPPF) {
       const Buffer &b = plan->bufs[o.buf];
@@ -416,7 +494,7 @@ extern "C" int uyd_plan_op_info(uyd_plan *plan, int op, char *text, size_t text_
   UYD_REQUIRE(plan && op >= 0 && op < (int)plan->ops.size() && text && text_len > 0, UYD_E_ARG, "uyd_plan_op_info: bad arguments");
   const Op &o = plan->ops[op];
   double fl = 0, by = 0;
-  if (o.kind == OP_CONV) {
+  if (o.kind == OP_CONV || o.kind == OP_CONV_S8) {
     const uyd_conv &d = o.conv;
     const Buffer &ob = plan->bufs[d.out_buf];
     const int ih = d.in_buf < 0 ? plan->in_h : plan->bufs[d.in_buf].h, iw = d.in_buf < 0 ? plan->in_w : plan->bufs[d.in_buf].w;

@@ -67,6 +67,10 @@ size_t direct_weight_bytes(const uyd_conv &d);
 void direct_pack_weights(const uyd_conv &d, const float *w, void *dst_host);
 int direct_conv_launch(const ConvArgs &a, bool depthwise, cudaStream_t s);
 
+size_t direct_weight_bytes_s8(int cin, int cout, int k);
+void direct_pack_weights_s8(int cin, int cout, int k, const int8_t *w, void *dst_host);
+int direct_conv_s8_launch(const ConvArgs &a, const float *mult, float out_scale, int out_kind, cudaStream_t s);
+
 // pool_upsample.cu
 int sppf_pool_launch(__nv_bfloat16 *base, int n, int h, int w, int pitch, int c, cudaStream_t s);
 int upsample2x_launch(const __nv_bfloat16 *in, int in_pitch, __nv_bfloat16 *out, int out_pitch, int n,

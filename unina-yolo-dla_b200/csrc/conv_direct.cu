@@ -433,3 +433,73 @@ int direct_conv_launch(const ConvArgs &a, bool depthwise, cudaStream_t s) {
 }
 
 }  // namespace uyd
+
+// ---- INT8 (dp4a) reference path ---------------------------------------------------------------
+// Same requant epilogue as the tensor-core int8 kernel (oracle/quant.py): exact int32
+// accumulation, y = float(acc) * m_c + b_c (separate RN multiply / add), ReLU, then bf16 / fp32 /
+// int8 re-quantised with out_scale.  weights: int8 [tap][co][ci].
+namespace uyd {
+namespace {
+__global__ void __launch_bounds__(128) conv_s8_direct_kernel(ConvArgs a, const float *mult, float out_scale, int out_kind) {
+  const long long npix = (long long)a.n * a.oh * a.ow;
+  const long long p = (long long)blockIdx.x * 128 + threadIdx.x;
+  if (p >= npix) return;
+  const int co0 = blockIdx.y * 4;
+  const int ox = (int)(p % a.ow), oy = (int)((p / a.ow) % a.oh), n = (int)(p / ((long long)a.ow * a.oh));
+  const int pad = a.k / 2;
+  const int8_t *in = reinterpret_cast<const int8_t *>(a.in);
+  const int8_t *w = reinterpret_cast<const int8_t *>(a.w);
+  int acc[4] = {0, 0, 0, 0};
+  for (int ky = 0; ky < a.k; ++ky) {
+    const int iy = oy * a.stride + ky - pad;
+    if (iy < 0 || iy >= a.ih) continue;
+    for (int kx = 0; kx < a.k; ++kx) {
+      const int ix = ox * a.stride + kx - pad;
+      if (ix < 0 || ix >= a.iw) continue;
+      const int *px = reinterpret_cast<const int *>(in + (((long long)n * a.ih + iy) * a.iw + ix) * a.in_pitch);
+      const int8_t *wt = w + ((size_t)(ky * a.k + kx) * a.cout + co0) * a.cin;
+      for (int c4 = 0; c4 < a.cin / 4; ++c4) {
+        const int x = px[c4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = __dp4a(x, reinterpret_cast<const int *>(wt + (size_t)j * a.cin)[c4], acc[j]);
+      }
+    }
+  }
+  const long long opix = ((long long)n * a.oh + oy) * a.ow + ox;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (co0 + j >= a.cout) break;
+    float y = __fadd_rn(__fmul_rn(__int2float_rn(acc[j]), mult[co0 + j]), a.bias[co0 + j]);
+    if (a.relu) y = fmaxf(y, 0.f);
+    const long long o = opix * a.out_pitch + co0 + j;
+    if (out_kind == 2) {
+      const int q = max(-127, min(127, __float2int_rn(__fmul_rn(y, out_scale))));
+      reinterpret_cast<int8_t *>(a.out)[o] = (int8_t)q;
+    } else if (out_kind == 1) {
+      reinterpret_cast<float *>(a.out)[o] = y;
+    } else {
+      reinterpret_cast<__nv_bfloat16 *>(a.out)[o] = __float2bfloat16_rn(y);
+    }
+  }
+}
+}  // namespace
+
+size_t direct_weight_bytes_s8(int cin, int cout, int k) { return (size_t)cin * cout * k * k; }
+
+void direct_pack_weights_s8(int cin, int cout, int k, const int8_t *w, void *dst_host) {
+  int8_t *o = reinterpret_cast<int8_t *>(dst_host);
+  const int taps = k * k;
+  for (int t = 0; t < taps; ++t)
+    for (int co = 0; co < cout; ++co)
+      for (int ci = 0; ci < cin; ++ci) o[((size_t)t * cout + co) * cin + ci] = w[((size_t)co * cin + ci) * taps + t];
+}
+
+int direct_conv_s8_launch(const ConvArgs &a, const float *mult, float out_scale, int out_kind, cudaStream_t s) {
+  UYD_REQUIRE(a.cin % 4 == 0 && a.in_pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(a.in) & 3) == 0, UYD_E_UNSUPPORTED,
+              "int8 direct conv needs cin %% 4 == 0 and 4-byte aligned input slices");
+  const long long npix = (long long)a.n * a.oh * a.ow;
+  dim3 grid((unsigned)((npix + 127) / 128), (unsigned)ceil_div(a.cout, 4));
+  conv_s8_direct_kernel<<<grid, 128, 0, s>>>(a, mult, out_scale, out_kind);
+  return (int)cudaGetLastError();
+}
+}  // namespace uyd

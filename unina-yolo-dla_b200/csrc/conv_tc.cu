@@ -43,6 +43,10 @@ struct TcParams {
   int stages;
   int nacc;              // TMEM accumulator stages (nacc * N columns)
   int stage_pitch;       // bytes per row of the epilogue staging tile (0 = direct stores)
+  int i8;                // 1: int8 operands, int32 accumulate (kind::i8), requant epilogue
+  int out_kind;          // i8 path: 0 = bf16, 1 = fp32, 2 = int8 (re-quantised with out_scale)
+  float out_scale;
+  const float *mult;     // i8 path: per-channel fp32 multiplier m_c
   uint32_t blk_bytes;    // one A block in shared memory
   uint32_t tx_bytes;     // bytes TMA delivers per A block
   uint32_t w_bytes;      // resident weights
@@ -123,6 +127,13 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -245,6 +256,50 @@ __device__ __forceinline__ void epilogue_chunk_staged(const uint32_t (&raw)[16],
   }
 }
 
+// INT8 path: y = float(acc) * m_c + b_c with separate round-to-nearest multiply and add (the
+// oracle's integer reference, oracle/quant.py), ReLU, then bf16 / fp32 / re-quantised int8.
+__device__ __forceinline__ void epilogue_chunk_i8_staged(const uint32_t (&raw)[16], const float *bias_s, const float *mult_s,
+                                                         int c0, const TcParams &p, unsigned char *srow) {
+  float v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float x = __fadd_rn(__fmul_rn(__int2float_rn((int)raw[i]), mult_s[c0 + i]), bias_s[c0 + i]);
+    v[i] = p.relu ? fmaxf(x, 0.f) : x;
+  }
+  if (p.out_kind == 2) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint32_t pk = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int q = __float2int_rn(__fmul_rn(v[4 * i + j], p.out_scale));
+        q = max(-127, min(127, q));
+        pk |= (uint32_t)(q & 0xFF) << (8 * j);
+      }
+      w[i] = pk;
+    }
+    *reinterpret_cast<uint4 *>(srow + c0) = make_uint4(w[0], w[1], w[2], w[3]);
+  } else if (p.out_kind == 1) {
+    float4 *sp = reinterpret_cast<float4 *>(srow + c0 * 4);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sp[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else {
+    uint4 o0, o1;
+    uint32_t *w0 = reinterpret_cast<uint32_t *>(&o0), *w1 = reinterpret_cast<uint32_t *>(&o1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      __nv_bfloat162 b = __floats2bfloat162_rn(v[8 + 2 * i], v[8 + 2 * i + 1]);
+      w0[i] = *reinterpret_cast<uint32_t *>(&a);
+      w1[i] = *reinterpret_cast<uint32_t *>(&b);
+    }
+    uint4 *sp = reinterpret_cast<uint4 *>(srow + c0 * 2);
+    sp[0] = o0;
+    sp[1] = o1;
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in,
                                                               const __grid_constant__ CUtensorMap tm_w, const TcParams p) {
   extern __shared__ unsigned char smem_dyn[];
@@ -259,6 +314,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t tfull0 = wfull + 8, tempty0 = tfull0 + 8u * kMaxAcc, slot = tempty0 + 8u * kMaxAcc;
   uint32_t *slot_ptr = reinterpret_cast<uint32_t *>(smem_dyn + (slot - raw));
   float *bias_s = reinterpret_cast<float *>(smem_dyn + (bar0 + 512u - raw));
+  float *mult_s = reinterpret_cast<float *>(smem_dyn + (bar0 + 1024u - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nacc = p.nacc;
@@ -277,7 +333,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
     fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < p.N; i += kThreads) bias_s[i] = i < p.cout ? p.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < p.N; i += kThreads) {
+    bias_s[i] = i < p.cout ? p.bias[i] : 0.f;
+    mult_s[i] = (p.i8 && i < p.cout) ? p.mult[i] : 0.f;
+  }
   if (warp == 1) tmem_alloc(slot, tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -287,7 +346,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const int blocks_per_tile = p.mode == TC_PERTAP ? p.ncb * p.taps : p.ncb;
   const int taps_in_block = p.mode == TC_HALO ? p.taps : 1;
   const int ksteps = p.cb_bytes / 32;
-  const int cb_elems = p.cb_bytes / 2;
+  const int cb_elems = p.i8 ? p.cb_bytes : p.cb_bytes / 2;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const int stages = p.stages;
   const uint32_t blk_bytes = p.blk_bytes, cb_bytes = p.cb_bytes;
@@ -360,7 +419,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             for (int k = 0; k < ksteps; ++k) {
               const uint64_t ad = adesc0 + (uint64_t)(((a_tap + 32u * k) & 0x3FFFFu) >> 4);
               const uint64_t bd = bdesc0 + (uint64_t)(((wblk + 32u * k) & 0x3FFFFu) >> 4);
-              umma_bf16(d_tmem, ad, bd, idesc, accum);
+              if (p.i8) umma_i8(d_tmem, ad, bd, idesc, accum);
+              else umma_bf16(d_tmem, ad, bd, idesc, accum);
               accum = 1;
             }
             wblk += wblk_bytes;
@@ -379,12 +439,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int m = q * 32 + lane;
     const int nchunks = p.N >> 4;
     const bool staged = p.stage_pitch != 0;
-    const int esize = p.out_f32 ? 4 : 2;
+    const int esize = p.i8 ? (p.out_kind == 2 ? 1 : (p.out_kind == 1 ? 4 : 2)) : (p.out_f32 ? 4 : 2);
     const int lpr = staged ? (p.cout * esize) / 16 : 1;  // 16-byte lanes per output row
     const int rows_per_it = 32 / lpr;
     const long long out_row_pitch = (long long)p.out_pitch * esize;
-    long long *spix = reinterpret_cast<long long *>(smem_dyn + (bar0 + 1024u - raw)) + (warp - 2) * 32;
-    unsigned char *swarp = smem_dyn + (bar0 + 2048u - raw) + (size_t)(warp - 2) * 32 * p.stage_pitch;
+    long long *spix = reinterpret_cast<long long *>(smem_dyn + (bar0 + 1536u - raw)) + (warp - 2) * 32;
+    unsigned char *swarp = smem_dyn + (bar0 + 2560u - raw) + (size_t)(warp - 2) * 32 * p.stage_pitch;
     unsigned char *srow = swarp + (size_t)lane * p.stage_pitch;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -415,7 +475,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           mbar_arrive(tempty0 + 8u * acc);  // every TMEM read of this accumulator has completed
         }
         if (staged) {
-          if (c * 16 < p.cout) epilogue_chunk_staged(cur, bias_s, c * 16, pix, p, srow);
+          if (c * 16 < p.cout) {
+            if (p.i8) epilogue_chunk_i8_staged(cur, bias_s, mult_s, c * 16, p, srow);
+            else epilogue_chunk_staged(cur, bias_s, c * 16, pix, p, srow);
+          }
         } else if (pix >= 0 && c * 16 < p.cout) {
           epilogue_chunk(cur, bias_s, c * 16, pix, p);
         }
@@ -470,10 +533,10 @@ static CUtensorMapSwizzle swizzle_of(int cb_bytes) {
 }
 
 static int encode(CUtensorMap *tm, void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides_bytes,
-                  const cuuint32_t *box, const cuuint32_t *estr, int cb_bytes) {
+                  const cuuint32_t *box, const cuuint32_t *estr, int cb_bytes, bool u8 = false) {
   EncodeTiledFn fn = get_encode();
   UYD_REQUIRE(fn, UYD_E_NOGPU, "cuTensorMapEncodeTiled is not available (no CUDA driver)");
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, dims, strides_bytes, box, estr,
+  CUresult r = fn(tm, u8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, dims, strides_bytes, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_of(cb_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   UYD_REQUIRE(r == CUDA_SUCCESS, UYD_E_ARG, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank);
@@ -488,6 +551,8 @@ struct TcConv {  // everything a launch needs, prepared once at plan finalize
 };
 
 static int pick_cb(int cin) { return cin % 64 == 0 ? 64 : (cin % 32 == 0 ? 32 : (cin % 16 == 0 ? 16 : 0)); }
+// int8: channels (= bytes) per block
+static int pick_cb_s8(int cin) { return cin % 128 == 0 ? 128 : (cin % 64 == 0 ? 64 : (cin % 32 == 0 ? 32 : 0)); }
 
 bool tc_supported(const uyd_conv &d, int in_pitch, int in_coff, int out_pitch, int out_coff, bool in_is_network_input) {
   if (in_is_network_input || d.depthwise) return false;
@@ -518,15 +583,48 @@ void tc_pack_weights(const uyd_conv &d, const float *w, void *dst_host) {
         }
 }
 
+bool tc_supported_s8(int cin, int cout, int k, int stride, int in_pitch, int in_coff, int out_pitch, int out_coff, int out_esize) {
+  if (!(k == 1 || k == 3) || !(stride == 1 || stride == 2) || (k == 1 && stride != 1)) return false;
+  if (pick_cb_s8(cin) == 0 || cout > 128 || cout < 4) return false;
+  if (in_pitch % 16 || in_coff % 16) return false;
+  const int rb = cout * out_esize;
+  if (rb < 16 || rb > 512 || (rb & (rb - 1)) || (out_pitch * out_esize) % 16 || (out_coff * out_esize) % 16) return false;
+  const int N = (cout + 15) / 16 * 16;
+  return (size_t)cin * k * k * N <= 150 * 1024;
+}
+
+size_t tc_weight_bytes_s8(int cin, int cout, int k) { return (size_t)cin * k * k * ((cout + 15) / 16 * 16); }
+
+// [cout][cin][k][k] int8 -> int8 [cb][tap][n (padded to N)][CB]
+void tc_pack_weights_s8(int cin, int cout, int k, const int8_t *w, void *dst_host) {
+  const int CB = pick_cb_s8(cin), ncb = cin / CB, taps = k * k, N = (cout + 15) / 16 * 16;
+  int8_t *o = reinterpret_cast<int8_t *>(dst_host);
+  for (int cb = 0; cb < ncb; ++cb)
+    for (int t = 0; t < taps; ++t)
+      for (int n = 0; n < N; ++n)
+        for (int c = 0; c < CB; ++c)
+          o[(((size_t)cb * taps + t) * N + n) * CB + c] = n < cout ? w[((size_t)n * cin + cb * CB + c) * taps + t] : (int8_t)0;
+}
+
 // mode_override: -1 auto, else TC_*.  in_base/out_base/res_base: slice bases of image 0.
+// i8 != 0: int8 operands (weights already quantised), per-channel multiplier mult_dev,
+// out_kind 0/1/2 = bf16 / fp32 / int8 re-quantised with out_scale.
 int tc_prepare(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int ih, int iw, int max_batch, void *out_base,
                int out_pitch, int out_f32, const void *res_base, int res_pitch, void *w_dev, const float *bias_dev,
-               int mode_override, int base_offset_mode, int stages_override) {
+               int mode_override, int base_offset_mode, int stages_override, int i8 = 0, const float *mult_dev = nullptr,
+               float out_scale = 0.f, int out_kind = 0) {
   TcParams &p = tc->p;
   memset(&p, 0, sizeof(p));
-  const int CB = pick_cb(d.cin);
-  UYD_REQUIRE(CB, UYD_E_UNSUPPORTED, "conv_tc: cin %d is not a multiple of 16", d.cin);
-  p.cb_bytes = CB * 2;
+  const int es = i8 ? 1 : 2;
+  const int CB = i8 ? pick_cb_s8(d.cin) : pick_cb(d.cin);
+  UYD_REQUIRE(CB, UYD_E_UNSUPPORTED, "conv_tc: cin %d is not a multiple of %d", d.cin, i8 ? 32 : 16);
+  UYD_REQUIRE(!i8 || !res_base, UYD_E_UNSUPPORTED, "conv_tc: the int8 path has no residual input");
+  p.i8 = i8;
+  p.mult = mult_dev;
+  p.out_scale = out_scale;
+  p.out_kind = out_kind;
+  if (i8) out_f32 = out_kind == 1;
+  p.cb_bytes = CB * es;
   p.ncb = d.cin / CB;
   p.taps = d.k * d.k;
   p.stride = d.stride;
@@ -539,8 +637,9 @@ int tc_prepare(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int i
   UYD_REQUIRE(!(p.mode == TC_HALO && d.stride != 1), UYD_E_UNSUPPORTED, "conv_tc: HALO mode needs stride 1");
   p.base_offset_mode = base_offset_mode;
   p.layout_type = p.cb_bytes == 128 ? 2u : (p.cb_bytes == 64 ? 4u : 6u);
-  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  p.w_bytes = (uint32_t)tc_weight_bytes(d);
+  // c_format F32 (1) / S32 (2); a,b format 1 = BF16 resp. signed int8; K-major; N >> 3; M >> 4
+  p.idesc = ((i8 ? 2u : 1u) << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  p.w_bytes = (uint32_t)((size_t)d.cin * d.k * d.k * p.N * es);
   p.tiles_x = ceil_div(p.W, kTileW);
   p.tiles_y = ceil_div(p.H, kTileH);
   if (p.mode == TC_HALO) {
@@ -556,12 +655,13 @@ int tc_prepare(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int i
   p.blk_bytes = (p.blk_bytes + 1023u) & ~1023u;
   // epilogue staging: rows of N * esize bytes (+16 B pad against bank conflicts); usable when a
   // row of real output is a power-of-two number of 16-byte lanes
-  const int esize = out_f32 ? 4 : 2;
+  const int esize = i8 ? (out_kind == 2 ? 1 : (out_kind == 1 ? 4 : 2)) : (out_f32 ? 4 : 2);
   const int row_bytes = d.cout * esize;
   const bool can_stage = row_bytes >= 16 && row_bytes <= 512 && (row_bytes & (row_bytes - 1)) == 0 &&
                          (out_pitch * esize) % 16 == 0 && (reinterpret_cast<uintptr_t>(out_base) & 15) == 0;
   p.stage_pitch = can_stage ? p.N * esize + 16 : 0;
-  const size_t tail = 2048 + (size_t)128 * p.stage_pitch;  // barriers + bias + row->pixel map + staging
+  UYD_REQUIRE(!i8 || can_stage, UYD_E_UNSUPPORTED, "conv_tc int8: output rows must be a power-of-two number of 16-byte lanes");
+  const size_t tail = 2560 + (size_t)128 * p.stage_pitch;  // barriers + bias + row->pixel map + staging
   const size_t wres = (p.w_bytes + 1023u) & ~1023u;
   const size_t budget = 227 * 1024 - 1024 - tail;
   if (p.mode == TC_HALO && wres + 2 * (size_t)p.blk_bytes > budget) {  // halo blocks too big: one box per tap
@@ -594,27 +694,27 @@ int tc_prepare(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int i
     const cuuint64_t dims[2] = {(cuuint64_t)CB, (cuuint64_t)p.ncb * p.taps * p.N};
     const cuuint64_t str[1] = {(cuuint64_t)p.cb_bytes};
     const cuuint32_t box[2] = {(cuuint32_t)CB, (cuuint32_t)p.N};
-    int e = encode(&tc->tm_w, w_dev, 2, dims, str, box, one4, p.cb_bytes);
+    int e = encode(&tc->tm_w, w_dev, 2, dims, str, box, one4, p.cb_bytes, i8);
     if (e) return e;
   }
   if (p.mode == TC_FLAT) {
     const cuuint64_t dims[2] = {(cuuint64_t)d.cin, (cuuint64_t)max_batch * ih * iw};
-    const cuuint64_t str[1] = {(cuuint64_t)in_pitch * 2};
+    const cuuint64_t str[1] = {(cuuint64_t)in_pitch * es};
     const cuuint32_t box[2] = {(cuuint32_t)CB, 128};
-    int e = encode(&tc->tm_in, in_base, 2, dims, str, box, one4, p.cb_bytes);
+    int e = encode(&tc->tm_in, in_base, 2, dims, str, box, one4, p.cb_bytes, i8);
     if (e) return e;
   } else {
     const cuuint64_t dims[4] = {(cuuint64_t)d.cin, (cuuint64_t)iw, (cuuint64_t)ih, (cuuint64_t)max_batch};
-    const cuuint64_t str[3] = {(cuuint64_t)in_pitch * 2, (cuuint64_t)iw * in_pitch * 2, (cuuint64_t)ih * iw * in_pitch * 2};
+    const cuuint64_t str[3] = {(cuuint64_t)in_pitch * es, (cuuint64_t)iw * in_pitch * es, (cuuint64_t)ih * iw * in_pitch * es};
     if (p.mode == TC_HALO) {
       const cuuint32_t box[4] = {(cuuint32_t)CB, (cuuint32_t)(kTileW + 2), 1, 1};
-      int e = encode(&tc->tm_in, in_base, 4, dims, str, box, one4, p.cb_bytes);
+      int e = encode(&tc->tm_in, in_base, 4, dims, str, box, one4, p.cb_bytes, i8);
       if (e) return e;
     } else {
       const cuuint32_t s = (cuuint32_t)d.stride;
       const cuuint32_t box[4] = {(cuuint32_t)CB, (cuuint32_t)kTileW * s, (cuuint32_t)kTileH * s, 1};
       const cuuint32_t estr[4] = {1, s, s, 1};
-      int e = encode(&tc->tm_in, in_base, 4, dims, str, box, estr, p.cb_bytes);
+      int e = encode(&tc->tm_in, in_base, 4, dims, str, box, estr, p.cb_bytes, i8);
       if (e) return e;
     }
   }

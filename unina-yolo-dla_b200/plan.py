@@ -8,7 +8,9 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import IMPL_AUTO, UYD_BF16, UYD_F32, ConvDesc, check
+from ._lib import IMPL_AUTO, UYD_BF16, UYD_F32, UYD_S8, ConvDesc, ConvS8Desc, check
+
+_TORCH_DTYPE = {UYD_BF16: torch.bfloat16, UYD_F32: torch.float32, UYD_S8: torch.int8}
 
 
 @dataclass(frozen=True)
@@ -78,6 +80,21 @@ class Plan:
                                            bias.ctypes.data_as(C.c_void_p)), "uyd_plan_add_conv")
         return dst
 
+    def conv_s8(self, src: Slice, dst: Slice, weight_q: np.ndarray, mult: np.ndarray, bias: np.ndarray, k: int,
+                stride: int = 1, relu: bool = True, out_scale: float = 0.0, impl: int = IMPL_AUTO) -> Slice:
+        """INT8 conv: src in a UYD_S8 buffer, weight_q int8 [cout][cin][k][k]; the dtype of dst's buffer
+        selects the epilogue (int8 re-quantised with out_scale, or fp32 / bf16)."""
+        weight_q = np.ascontiguousarray(weight_q, dtype=np.int8)
+        mult = np.ascontiguousarray(mult, dtype=np.float32)
+        bias = np.ascontiguousarray(bias, dtype=np.float32)
+        cout, cin = weight_q.shape[0], weight_q.shape[1]
+        assert dst.c == cout and src.c == cin and mult.shape == (cout,) and bias.shape == (cout,)
+        d = ConvS8Desc(src.buf, src.coff, dst.buf, dst.coff, cin, cout, k, stride, int(relu), float(out_scale), impl, 0)
+        check(_lib.lib().uyd_plan_add_conv_s8(self.handle, C.byref(d), weight_q.ctypes.data_as(C.c_void_p),
+                                              mult.ctypes.data_as(C.c_void_p), bias.ctypes.data_as(C.c_void_p)),
+              "uyd_plan_add_conv_s8")
+        return dst
+
     def sppf_pool(self, s: Slice, c: int) -> None:
         check(_lib.lib().uyd_plan_add_sppf_pool(self.handle, s.buf, s.coff, c), "uyd_plan_add_sppf_pool")
 
@@ -137,14 +154,14 @@ class Plan:
     def write(self, s: Slice, nchw: torch.Tensor) -> None:
         """Stores an NCHW tensor into a slice of a bf16 buffer (layer-level tests)."""
         h, w, ctot, dtype = self.shapes[s.buf]
-        assert dtype == UYD_BF16
+        tdt = _TORCH_DTYPE[dtype]
         batch = nchw.shape[0]
         ptr = C.c_void_p()
         check(_lib.lib().uyd_plan_buffer_ptr(self.handle, s.buf, C.byref(ptr)), "uyd_plan_buffer_ptr")
-        full = torch.empty(batch, h, w, ctot, dtype=torch.bfloat16, device=f"cuda:{self.device}")
-        nbytes = full.numel() * 2
+        full = torch.empty(batch, h, w, ctot, dtype=tdt, device=f"cuda:{self.device}")
+        nbytes = full.numel() * full.element_size()
         check(_lib.lib().uyd_memcpy_d2d(C.c_void_p(full.data_ptr()), ptr, nbytes, self._stream()), "uyd_memcpy_d2d")
-        full[..., s.coff:s.coff + s.c] = nchw.to(full.device).permute(0, 2, 3, 1).to(torch.bfloat16)
+        full[..., s.coff:s.coff + s.c] = nchw.to(full.device).permute(0, 2, 3, 1).to(tdt)
         check(_lib.lib().uyd_memcpy_d2d(ptr, C.c_void_p(full.data_ptr()), nbytes, self._stream()), "uyd_memcpy_d2d")
         torch.cuda.current_stream().synchronize()
 
@@ -159,13 +176,14 @@ class Plan:
     def read(self, s: Slice, batch: int) -> torch.Tensor:
         """Copies a slice out as an NCHW fp32 tensor (layer-level parity checks)."""
         h, w, ctot, dtype = self.shapes[s.buf]
-        tdt = torch.float32 if dtype == UYD_F32 else torch.bfloat16
+        tdt = _TORCH_DTYPE[dtype]
         full = torch.empty(batch, h, w, ctot, dtype=tdt, device=f"cuda:{self.device}")
         ptr = C.c_void_p()
         check(_lib.lib().uyd_plan_buffer_ptr(self.handle, s.buf, C.byref(ptr)), "uyd_plan_buffer_ptr")
         check(_lib.lib().uyd_memcpy_d2d(C.c_void_p(full.data_ptr()), ptr, full.numel() * full.element_size(), self._stream()),
               "uyd_memcpy_d2d")
-        return full[..., s.coff:s.coff + s.c].permute(0, 3, 1, 2).float().contiguous()
+        out = full[..., s.coff:s.coff + s.c].permute(0, 3, 1, 2).contiguous()
+        return out if dtype == UYD_S8 else out.float()
 
     @property
     def bytes(self) -> int:
