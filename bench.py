@@ -203,10 +203,9 @@ def main():
         x_u8.copy_(x_host, non_blocking=True)
         det, cnt = model.predict_batched(x_u8, CONF, IOU, MAX_DET)
         if world > 1:  # batched-eval gather of the detections (the only collective of the path)
-            gd = torch.empty(world * B, MAX_DET, 6, device=dev)
-            gc = torch.empty(world * B, dtype=torch.int32, device=dev)
-            dist.all_gather_into_tensor(gd, det)
-            dist.all_gather_into_tensor(gc, cnt)
+            from unina_yolo_dla_b200.dp import gather_detections
+
+            gather_detections(det, cnt)
         det_host.copy_(det, non_blocking=True)
         cnt_host.copy_(cnt, non_blocking=True)
 
