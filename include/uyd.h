@@ -98,6 +98,16 @@ typedef struct uyd_conv_s8 {
 int uyd_plan_add_conv_s8(uyd_plan *plan, const uyd_conv_s8 *desc, const int8_t *weight_q, const float *mult,
                          const float *bias);
 
+/* Fused C3k block (Ultralytics C3k with two 3x3 bottlenecks; the interior of every C3k2 of the
+ * YAML graph): y = cv3(cat(m1(m0(cv1 x)), cv2 x)), all seven Conv+BN+ReLU layers and both
+ * residual adds in one launch, intermediates in shared memory.  weights/biases, BN folded,
+ * PyTorch layout: [0] cv1 [c/2][c][1][1], [1] cv2 [c/2][c][1][1], [2..5] m0.cv1, m0.cv2, m1.cv1, m1.cv2
+ * [c/2][c/2][3][3], [6] cv3 [c][c][1][1].  c in {8, 16, 32}; W % 40 == 0; H % 32, 20 or 16 == 0. */
+typedef struct uyd_c3k {
+  int in_buf, in_coff, out_buf, out_coff, c, reserved;
+} uyd_c3k;
+int uyd_plan_add_c3k(uyd_plan *plan, const uyd_c3k *desc, const float *const weights[7], const float *const biases[7]);
+
 /* SPPF cascade: reads slice [coff, coff+c) of buf and writes pool5, pool5^2, pool5^3 to
  * slices [coff+c, coff+2c), [coff+2c, ..), [coff+3c, ..) of the same buffer
  * (trainer.py:119-124; -inf padding). */

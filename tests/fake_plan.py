@@ -13,16 +13,26 @@ class FakePlan:
     def __init__(self, device=0, max_batch=1):
         self.max_batch = max_batch
         self.specs = []       # (h, w, c)
+        self.shapes = {}
         self.ops = []
         self.heads = []
         self.in_hw = None
 
     def buffer(self, h, w, c, dtype=0):
         self.specs.append((h, w, c))
+        self.shapes[len(self.specs) - 1] = (h, w, c, dtype)
         return Slice(len(self.specs) - 1, 0, c, h, w)
 
     def conv(self, src, dst, weight, bias, k, stride=1, relu=True, depthwise=False, res=None, impl=0):
         self.ops.append(("conv", src, dst, torch.from_numpy(weight), torch.from_numpy(bias), k, stride, relu, depthwise, res))
+        return dst
+
+    @staticmethod
+    def c3k_supported(src, dst):
+        return src.c in (8, 16, 32) and src.w % 40 == 0 and (src.h % 32 == 0 or src.h % 20 == 0 or src.h % 16 == 0)
+
+    def c3k(self, src, dst, weights, biases):
+        self.ops.append(("c3k", src, dst, [torch.from_numpy(w) for w in weights], [torch.from_numpy(b) for b in biases]))
         return dst
 
     def sppf_pool(self, s, c):
@@ -54,6 +64,14 @@ class FakePlan:
                 if res is not None:
                     y = y + get(res)
                 bufs[dst.buf][:, dst.coff:dst.coff + dst.c] = y
+            elif op[0] == "c3k":
+                _, src, dst, w, b = op
+                cb = lambda t, i, k: F.conv2d(t, w[i], b[i], padding=k // 2).relu()
+                xin = get(src)
+                a_, b_ = cb(xin, 0, 1), cb(xin, 1, 1)
+                u = a_ + cb(cb(a_, 2, 3), 3, 3)
+                v = u + cb(cb(u, 4, 3), 5, 3)
+                bufs[dst.buf][:, dst.coff:dst.coff + dst.c] = cb(torch.cat((v, b_), 1), 6, 1)
             elif op[0] == "sppf":
                 _, s, c = op
                 t = get(s.sub(0, c))

@@ -217,3 +217,36 @@ def test_predict_returns_reference_rows(T):
     for r, w in zip(res, want):
         assert r.shape[1] == 6 and r.cpu().numpy().tobytes() == w.tobytes()
         assert 0 < len(w) <= 300
+
+
+@pytest.mark.parametrize("c,H,W", [(8, 64, 80), (16, 40, 80), (32, 40, 40), (16, 80, 80), (8, 160, 160)])
+def test_fused_c3k_matches_torch(T, c, H, W):
+    """Fused C3k block vs the seven torch convs with bf16 rounding at the same points."""
+    import torch.nn.functional as F
+    import unina_yolo_dla_b200 as uyd
+
+    g = torch.Generator().manual_seed(c + H)
+    B, h = 3, c // 2
+    shapes = [(h, c, 1), (h, c, 1), (h, h, 3), (h, h, 3), (h, h, 3), (h, h, 3), (c, c, 1)]
+    ws = [torch.randn(co, ci, k, k, generator=g) / (ci * k * k) ** 0.5 for co, ci, k in shapes]
+    bs = [torch.randn(co, generator=g) * 0.1 for co, _, _ in shapes]
+    x = torch.randn(B, c, H, W, generator=g)
+    p = uyd.Plan(0, B)
+    src = p.buffer(H, W, 3 * c)          # input and output live in channel slices of wider buffers
+    dst = p.buffer(H, W, 2 * c)
+    s_in, s_out = src.sub(c, c), dst.sub(c, c)
+    p.c3k(s_in, s_out, [w.numpy() for w in ws], [b.numpy() for b in bs])
+    p.finalize()
+    p.write(s_in, x)
+    p.run_no_input(B)
+    torch.cuda.synchronize()
+    got = p.read(s_out, B).cpu()
+    r = T.bf16_round
+    cb = lambda t, i: r(F.conv2d(t, r(ws[i]), bs[i], padding=ws[i].shape[2] // 2).relu())
+    xin = r(x)
+    a_, b_ = cb(xin, 0), cb(xin, 1)
+    u = r(a_ + F.conv2d(cb(a_, 2), r(ws[3]), bs[3], padding=1).relu())
+    v = r(u + F.conv2d(cb(u, 4), r(ws[5]), bs[5], padding=1).relu())
+    want = cb(torch.cat((v, b_), 1), 6)
+    assert T.rel_err(got, want) < 1e-2
+    assert float(p.read(dst.sub(0, c), B).abs().max()) == 0.0   # nothing written outside the slice

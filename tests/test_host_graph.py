@@ -86,3 +86,21 @@ def test_library_exports_every_declared_symbol():
 def test_product_does_not_import_the_oracle():
     for f in (ROOT / "unina-yolo-dla_b200").glob("*.py"):
         assert "oracle" not in f.read_text(), f"{f.name} mentions the oracle"
+
+
+def test_emitted_plan_uses_fused_c3k_at_full_resolution(monkeypatch):
+    """At 640x640 every C3k interior (16 blocks x 7 convs) is emitted as one fused op and the plan
+    still computes the oracle's network."""
+    m = uyd.UninaYoloB200.from_yaml().init_synthetic(seed=4)
+    ref = yg.DetectionModel(yg.default_yaml_path())
+    ref.load_state_dict(m.state_dict(), strict=True)
+    ref.eval()
+    x = oi.seeded_frames(1, 640, seed=6)
+    with torch.no_grad():
+        y_ref, raw_ref = ref(x)
+    p = _emit_fake(m, 1, 640, 640, monkeypatch)
+    kinds = [o[0] for o in p.ops]
+    assert kinds.count("c3k") == 16 and kinds.count("conv") == 158 - 16 * 7
+    bufs = p.execute(x)
+    for h, r in zip(p.heads, raw_ref):
+        assert torch.allclose(bufs[h.buf], r, rtol=1e-4, atol=1e-4)

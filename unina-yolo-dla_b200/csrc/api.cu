@@ -33,6 +33,18 @@ TcConv *tc_new();
 void tc_delete(TcConv *);
 const char *tc_mode_name(const TcConv *);
 
+// c3k_fused.cu
+struct C3kArgs {
+  const __nv_bfloat16 *in;
+  __nv_bfloat16 *out;
+  const uint32_t *wfrag;
+  const float *bias;
+  int n, h, w, in_pitch, out_pitch, th, tiles_x, tiles_y;
+};
+bool c3k_supported(int c, int h, int w, int in_pitch, int in_coff, int out_pitch, int out_coff);
+void c3k_pack(int c, const float *const w[7], const float *const b[7], std::vector<uint32_t> &frags, std::vector<float> &bias);
+int c3k_launch(int c, const C3kArgs &a, cudaStream_t s);
+
 static int env_int(const char *name, int dflt) {
   const char *v = getenv(name);
   return v && *v ? atoi(v) : dflt;
@@ -47,7 +59,7 @@ struct uyd_ctx {
   int sm_count = 0;
 };
 
-enum OpKind { OP_CONV = 0, OP_SPPF = 1, OP_UPSAMPLE = 2, OP_CONV_S8 = 3 };
+enum OpKind { OP_CONV = 0, OP_SPPF = 1, OP_UPSAMPLE = 2, OP_CONV_S8 = 3, OP_C3K = 4 };
 
 struct Op {
   OpKind kind;
@@ -250,6 +262,30 @@ extern "C" int uyd_plan_add_conv_s8(uyd_plan *plan, const uyd_conv_s8 *d, const 
   return UYD_OK;
 }
 
+extern "C" int uyd_plan_add_c3k(uyd_plan *plan, const uyd_c3k *d, const float *const weights[7], const float *const biases[7]) {
+  UYD_REQUIRE(plan && d && weights && biases, UYD_E_ARG, "uyd_plan_add_c3k: NULL argument");
+  UYD_REQUIRE(!plan->finalized, UYD_E_STATE, "plan already finalized");
+  int e;
+  if ((e = check_slice(plan, d->in_buf, d->in_coff, d->c, "c3k input"))) return e;
+  if ((e = check_slice(plan, d->out_buf, d->out_coff, d->c, "c3k output"))) return e;
+  const Buffer &ib = plan->bufs[d->in_buf], &ob = plan->bufs[d->out_buf];
+  UYD_REQUIRE(ib.dtype == UYD_BF16 && ob.dtype == UYD_BF16 && ib.h == ob.h && ib.w == ob.w, UYD_E_ARG,
+              "c3k needs bf16 buffers of equal extent");
+  UYD_REQUIRE(c3k_supported(d->c, ib.h, ib.w, ib.c, d->in_coff, ob.c, d->out_coff), UYD_E_UNSUPPORTED,
+              "fused c3k: c=%d %dx%d is not supported (c in {8,16,32}, W %% 40 == 0, H %% 32|20|16 == 0, 16-byte slices)",
+              d->c, ib.h, ib.w);
+  for (int i = 0; i < 7; ++i) UYD_REQUIRE(weights[i] && biases[i], UYD_E_ARG, "uyd_plan_add_c3k: weight %d is NULL", i);
+  Op op;
+  op.kind = OP_C3K;
+  op.buf = d->in_buf; op.coff = d->in_coff; op.out_buf = d->out_buf; op.out_coff = d->out_coff; op.c = d->c;
+  std::vector<uint32_t> frags;
+  c3k_pack(d->c, weights, biases, frags, op.b_host);
+  op.w_host.resize(frags.size() * 4);
+  memcpy(op.w_host.data(), frags.data(), op.w_host.size());
+  plan->ops.push_back(std::move(op));
+  return UYD_OK;
+}
+
 extern "C" int uyd_plan_add_sppf_pool(uyd_plan *plan, int buf, int coff, int c) {
   UYD_REQUIRE(plan && !plan->finalized, UYD_E_STATE, "plan missing or finalized");
   int e;
@@ -317,7 +353,7 @@ extern "C" int uyd_plan_finalize(uyd_plan *plan) {
   const int bo_mode = env_int("UYD_TC_BASE_OFFSET", 0);
   const int stages = env_int("UYD_TC_STAGES", 0);
   for (Op &o : plan->ops) {
-    if (o.kind != OP_CONV && o.kind != OP_CONV_S8) continue;
+    if (o.kind != OP_CONV && o.kind != OP_CONV_S8 && o.kind != OP_C3K) continue;
     UYD_CUDA(cudaMalloc(&o.w_dev, o.w_host.size()));
     UYD_CUDA(cudaMemcpy(o.w_dev, o.w_host.data(), o.w_host.size(), cudaMemcpyHostToDevice));
     UYD_CUDA(cudaMalloc((void **)&o.b_dev, o.b_host.size() * 4));
@@ -325,6 +361,7 @@ extern "C" int uyd_plan_finalize(uyd_plan *plan) {
     plan->bytes += o.w_host.size() + o.b_host.size() * 4;
     o.w_host.clear();
     o.w_host.shrink_to_fit();
+    if (o.kind == OP_C3K) continue;
     if (o.kind == OP_CONV_S8) {
       UYD_CUDA(cudaMalloc((void **)&o.m_dev, o.m_host.size() * 4));
       UYD_CUDA(cudaMemcpy(o.m_dev, o.m_host.data(), o.m_host.size() * 4, cudaMemcpyHostToDevice));
@@ -389,6 +426,14 @@ static int launch_op(uyd_plan *plan, const Op &o, const void *x, int x_kind, int
         a.w = o.w_dev; a.bias = o.b_dev; a.cin = d.cin; a.cout = d.cout; a.k = d.k; a.stride = d.stride; a.relu = d.relu;
         e = direct_conv_launch(a, d.depthwise != 0, s);
       }
+    } else if (o.kind == OP_C3K) {
+      const Buffer &ib = plan->bufs[o.buf], &ob = plan->bufs[o.out_buf];
+      C3kArgs a{};
+      a.in = (const __nv_bfloat16 *)slice_ptr(plan, o.buf, o.coff);
+      a.out = (__nv_bfloat16 *)slice_ptr(plan, o.out_buf, o.out_coff);
+      a.wfrag = (const uint32_t *)o.w_dev; a.bias = o.b_dev;
+      a.n = batch; a.h = ib.h; a.w = ib.w; a.in_pitch = ib.c; a.out_pitch = ob.c;
+      e = c3k_launch(o.c, a, s);
     } else if (o.kind == OP_CONV_S8) {
       const uyd_conv &d = o.conv;
       if (o.use_tc) {
@@ -504,6 +549,12 @@ extern "C" int uyd_plan_op_info(uyd_plan *plan, int op, char *text, size_t text_
          (d.res_buf >= 0 ? (double)ob.h * ob.w * d.cout * 2 : 0);
     snprintf(text, text_len, "conv %d->%d k%d s%d%s %dx%d %s%s%s", d.cin, d.cout, d.k, d.stride, d.depthwise ? " dw" : "", ob.h,
              ob.w, o.use_tc ? "tc:" : "direct", o.use_tc ? tc_mode_name(o.tc) : "", d.res_buf >= 0 ? " +res" : "");
+  } else if (o.kind == OP_C3K) {
+    const Buffer &b = plan->bufs[o.buf];
+    const double c = o.c, h = c / 2;
+    fl = 2.0 * b.h * b.w * (2 * c * h + 4 * 9 * h * h + c * c);
+    by = (double)b.h * b.w * c * 2 * 2;
+    snprintf(text, text_len, "c3k_fused c%d %dx%d (7 convs)", o.c, b.h, b.w);
   } else if (o.kind == OP_SPPF) {
     const Buffer &b = plan->bufs[o.buf];
     by = (double)b.h * b.w * o.c * 2 * 4;

@@ -1,0 +1,373 @@
+// Fused C3k block (Ultralytics C3k with two 3x3 bottlenecks, the interior of every C3k2 of the
+// YAML graph):
+//
+//     a  = relu(cv1 x)            1x1  c  -> c_          (c_ = c / 2 = 4, 8 or 16)
+//     b  = relu(cv2 x)            1x1  c  -> c_
+//     t1 = relu(m0.cv1 a)         3x3  c_ -> c_
+//     u  = a + relu(m0.cv2 t1)    3x3  c_ -> c_
+//     t2 = relu(m1.cv1 u)         3x3  c_ -> c_
+//     v  = u + relu(m1.cv2 t2)    3x3  c_ -> c_
+//     y  = relu(cv3 [v | b])      1x1  2c_ -> c
+//
+// Unfused this is 7 launches and 12 HBM round trips of 4..32-channel tensors that are latency-
+// bound (12-70 us each at batch 64).  Here one CTA owns a TH x 40 output tile: the input tile with
+// a 4-pixel halo is staged once in shared memory, the six intermediates never leave it, and the
+// math runs on tensor cores through mma.sync.m16n8k16 (bf16, fp32 accumulate) -- tcgen05 cannot be
+// fed by K = 9*c_ = 36..144 and N = 4..16.  M = 16 consecutive pixels of a tile row; a 3x3 conv is
+// ceil(9*c_/16) k-steps whose A fragments are plain 32-bit loads at tap-shifted pixel addresses.
+// Every intermediate is rounded to bf16 exactly where the unfused path rounds it, and positions
+// outside the image are forced to zero (each conv zero-pads ITS input), so results equal the
+// unfused plan up to fp32 summation order.
+#include "common.cuh"
+
+namespace uyd {
+
+struct C3kArgs {
+  const __nv_bfloat16 *in;
+  __nv_bfloat16 *out;
+  const uint32_t *wfrag;  // packed B fragments of the 7 convs
+  const float *bias;      // [7][32]
+  int n, h, w, in_pitch, out_pitch, th, tiles_x, tiles_y;
+};
+
+namespace {
+
+constexpr int kTW = 40;         // output tile width
+constexpr int kPW = kTW + 8;    // region row pitch in pixels (4-pixel halo each side) = 3 x 16
+constexpr int kWarps = 8;
+constexpr int kThreadsC3k = kWarps * 32;
+
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t *>(&h);
+}
+__device__ __forceinline__ float2 unpack_bf16(uint32_t v) {
+  return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162 *>(&v));
+}
+
+// K-index layout of a 3x3 conv with C channels per tap: k-step s holds taps [s*TPK, (s+1)*TPK),
+// TPK = 16 / C; column kk of the step is (tap s*TPK + kk / C, channel kk % C).
+template <int C>
+struct K3 {
+  static constexpr int TPK = 16 / C;
+  static constexpr int STEPS = (9 + TPK - 1) / TPK;
+};
+
+// Geometry of one stage: output region rows [r0, r1) x cols [c0, c1) in the halo frame.
+struct Region { int r0, r1, c0, c1; };
+
+// 3x3 conv  src[frame][C] -> dst[frame][C]  (+ residual from res[frame][C]) over `reg`.
+// gy0/gx0: image coordinates of frame pixel (0,0).
+template <int C>
+__device__ __forceinline__ void stage_conv3(const __nv_bfloat16 *src, __nv_bfloat16 *dst, const __nv_bfloat16 *res,
+                                            const uint32_t *wf, const float *bias, Region reg, int gy0, int gx0, int H,
+                                            int W, int warp, int lane) {
+  constexpr int NT = (C + 7) / 8;
+  constexpr int STEPS = K3<C>::STEPS, TPK = K3<C>::TPK;
+  const int g = lane >> 2, t = lane & 3;
+  uint32_t bf[STEPS][NT][2];
+#pragma unroll
+  for (int s = 0; s < STEPS; ++s)
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const uint2 v = reinterpret_cast<const uint2 *>(wf)[(s * NT + j) * 32 + lane];
+      bf[s][j][0] = v.x;
+      bf[s][j][1] = v.y;
+    }
+  // this thread's two k-columns inside a step: 2t (a0/a1) and 2t+8 (a2/a3)
+  const int j0 = (2 * t) / C, ch0 = (2 * t) % C, j2 = (2 * t + 8) / C, ch2 = (2 * t + 8) % C;
+  const int segs_per_row = (reg.c1 - reg.c0 + 15) / 16;
+  const int nseg = (reg.r1 - reg.r0) * segs_per_row;
+  for (int seg = warp; seg < nseg; seg += kWarps) {
+    const int ry = reg.r0 + seg / segs_per_row;
+    const int rx = reg.c0 + (seg % segs_per_row) * 16;
+    float acc[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+#pragma unroll
+    for (int s = 0; s < STEPS; ++s) {
+      uint32_t a[4];
+      const int tap0 = s * TPK + j0, tap2 = s * TPK + j2;
+      if (tap0 < 9) {
+        const __nv_bfloat16 *p = src + ((ry + tap0 / 3 - 1) * kPW + rx + g + tap0 % 3 - 1) * C + ch0;
+        a[0] = *reinterpret_cast<const uint32_t *>(p);
+        a[1] = *reinterpret_cast<const uint32_t *>(p + 8 * C);
+      } else {
+        a[0] = a[1] = 0u;
+      }
+      if (tap2 < 9) {
+        const __nv_bfloat16 *p = src + ((ry + tap2 / 3 - 1) * kPW + rx + g + tap2 % 3 - 1) * C + ch2;
+        a[2] = *reinterpret_cast<const uint32_t *>(p);
+        a[3] = *reinterpret_cast<const uint32_t *>(p + 8 * C);
+      } else {
+        a[2] = a[3] = 0u;
+      }
+#pragma unroll
+      for (int j = 0; j < NT; ++j) mma16816(acc[j], a, bf[s][j][0], bf[s][j][1]);
+    }
+    // epilogue: rows g and g+8 of the segment, channels 8j + 2t, 8j + 2t + 1
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int px = rx + g + 8 * half;
+      if (px >= reg.c1) continue;
+      const bool inside = (unsigned)(gy0 + ry) < (unsigned)H && (unsigned)(gx0 + px) < (unsigned)W;
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const int n = 8 * j + 2 * t;
+        if (n >= C) continue;
+        float v0 = fmaxf(acc[j][2 * half] + bias[n], 0.f), v1 = fmaxf(acc[j][2 * half + 1] + bias[n + 1], 0.f);
+        const int o = (ry * kPW + px) * C + n;
+        if (res) {
+          const float2 r = unpack_bf16(*reinterpret_cast<const uint32_t *>(res + o));
+          v0 += r.x;
+          v1 += r.y;
+        }
+        *reinterpret_cast<uint32_t *>(dst + o) = inside ? pack_bf16(v0, v1) : 0u;
+      }
+    }
+  }
+}
+
+// 1x1 conv over one or two channel sources: K = [srcA (CA ch, frame-indexed) | srcB (CB ch)].
+// srcB (if CB > 0) and dst may use a compact frame (pitch dpw, origin at region (r0, c0)).
+template <int CA, int CB, int COUT>
+__device__ __forceinline__ void stage_conv1(const __nv_bfloat16 *srcA, const __nv_bfloat16 *srcB, __nv_bfloat16 *dst,
+                                            bool dst_compact, const uint32_t *wf, const float *bias, Region reg, int gy0,
+                                            int gx0, int H, int W, int warp, int lane) {
+  constexpr int K = CA + CB, STEPS = (K + 15) / 16, NT = (COUT + 7) / 8;
+  const int g = lane >> 2, t = lane & 3;
+  uint32_t bf[STEPS][NT][2];
+#pragma unroll
+  for (int s = 0; s < STEPS; ++s)
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const uint2 v = reinterpret_cast<const uint2 *>(wf)[(s * NT + j) * 32 + lane];
+      bf[s][j][0] = v.x;
+      bf[s][j][1] = v.y;
+    }
+  const int cw = reg.c1 - reg.c0;  // compact pitch
+  const int segs_per_row = (cw + 15) / 16;
+  const int nseg = (reg.r1 - reg.r0) * segs_per_row;
+  for (int seg = warp; seg < nseg; seg += kWarps) {
+    const int ry = reg.r0 + seg / segs_per_row;
+    const int rx = reg.c0 + (seg % segs_per_row) * 16;
+    float acc[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+#pragma unroll
+    for (int s = 0; s < STEPS; ++s) {
+      uint32_t a[4];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {  // q = 0: k = 16s + 2t ; q = 1: k = 16s + 2t + 8
+        const int k = 16 * s + 2 * t + 8 * q;
+        uint32_t lo = 0u, hi = 0u;
+        if (k < CA) {
+          const __nv_bfloat16 *p = srcA + (ry * kPW + rx + g) * CA + k;
+          lo = *reinterpret_cast<const uint32_t *>(p);
+          hi = *reinterpret_cast<const uint32_t *>(p + 8 * CA);
+        } else if (k < K) {
+          const __nv_bfloat16 *p = srcB + ((ry - reg.r0) * cw + rx - reg.c0 + g) * CB + (k - CA);
+          lo = *reinterpret_cast<const uint32_t *>(p);
+          hi = *reinterpret_cast<const uint32_t *>(p + 8 * CB);
+        }
+        a[2 * q] = lo;
+        a[2 * q + 1] = hi;
+      }
+#pragma unroll
+      for (int j = 0; j < NT; ++j) mma16816(acc[j], a, bf[s][j][0], bf[s][j][1]);
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int px = rx + g + 8 * half;
+      if (px >= reg.c1) continue;
+      const bool inside = (unsigned)(gy0 + ry) < (unsigned)H && (unsigned)(gx0 + px) < (unsigned)W;
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const int n = 8 * j + 2 * t;
+        if (n >= COUT) continue;
+        const float v0 = fmaxf(acc[j][2 * half] + bias[n], 0.f), v1 = fmaxf(acc[j][2 * half + 1] + bias[n + 1], 0.f);
+        const int o = dst_compact ? ((ry - reg.r0) * cw + px - reg.c0) * COUT + n : (ry * kPW + px) * COUT + n;
+        *reinterpret_cast<uint32_t *>(dst + o) = inside ? pack_bf16(v0, v1) : 0u;
+      }
+    }
+  }
+}
+
+// words of packed B fragments per conv
+template <int C> constexpr int frag_words_3() { return K3<C>::STEPS * ((C + 7) / 8) * 64; }
+constexpr int frag_words_1(int k, int cout) { return ((k + 15) / 16) * ((cout + 7) / 8) * 64; }
+
+template <int C>  // C = c_ (hidden width); block width c = 2C
+__global__ void __launch_bounds__(kThreadsC3k) c3k_fused_kernel(C3kArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  constexpr int CC = 2 * C;
+  const int TH = a.th;
+  const int frame_px = (TH + 8 + 1) * kPW;  // +1 slack row: over-reads of partial segments stay in bounds
+  __nv_bfloat16 *X = reinterpret_cast<__nv_bfloat16 *>(smem);  // [frame][2C]   (later: output tile [TH*40][2C])
+  __nv_bfloat16 *A = X + (size_t)frame_px * CC;                // [frame][C]    a -> u -> v
+  __nv_bfloat16 *T = A + (size_t)frame_px * C;                 // [frame][C]    t1 -> t2
+  __nv_bfloat16 *Bv = T + (size_t)frame_px * C;                // [TH*40][C]    b
+  __shared__ float sbias[7][32];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.x;
+  const int n = tile / (a.tiles_x * a.tiles_y);
+  const int tr = tile % (a.tiles_x * a.tiles_y);
+  const int ty0 = (tr / a.tiles_x) * TH, tx0 = (tr % a.tiles_x) * kTW;
+  const int gy0 = ty0 - 4, gx0 = tx0 - 4;  // image coordinates of frame pixel (0,0)
+  const int H = a.h, W = a.w;
+
+  for (int i = tid; i < 7 * 32; i += kThreadsC3k) sbias[i / 32][i % 32] = a.bias[i];
+  // ---- stage 0: input tile + halo -> X (zero outside the image, zero slack row) ----------------
+  {
+    constexpr int CH16 = CC / 8;  // 16-byte chunks per pixel
+    const __nv_bfloat16 *img = a.in + (long long)n * H * W * a.in_pitch;
+    const int total = frame_px * CH16;
+    for (int i = tid; i < total; i += kThreadsC3k) {
+      const int px = i / CH16, ch = i % CH16;
+      const int ry = px / kPW, rx = px % kPW;
+      const int gy = gy0 + ry, gx = gx0 + rx;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (ry < TH + 8 && (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W)
+        v = *reinterpret_cast<const uint4 *>(img + ((long long)gy * W + gx) * a.in_pitch + ch * 8);
+      reinterpret_cast<uint4 *>(X)[i] = v;
+    }
+    // slack rows of A and T are read (never stored) by partial segments: keep them finite
+    for (int i = tid; i < kPW * C / 2; i += kThreadsC3k) {
+      reinterpret_cast<uint32_t *>(A + (size_t)(TH + 8) * kPW * C)[i] = 0u;
+      reinterpret_cast<uint32_t *>(T + (size_t)(TH + 8) * kPW * C)[i] = 0u;
+    }
+  }
+  __syncthreads();
+
+  const uint32_t *wf = a.wfrag;
+  constexpr int W1 = frag_words_1(CC, C), W3 = frag_words_3<C>();
+  const Region R4{0, TH + 8, 0, kPW}, R3{1, TH + 7, 1, kPW - 1}, R2{2, TH + 6, 2, kPW - 2}, R1{3, TH + 5, 3, kPW - 3},
+      R0{4, TH + 4, 4, kPW - 4};
+  // ---- stage 1: a = cv1(x) on R4, b = cv2(x) on R0 ---------------------------------------------
+  stage_conv1<CC, 0, C>(X, nullptr, A, false, wf, sbias[0], R4, gy0, gx0, H, W, warp, lane);
+  stage_conv1<CC, 0, C>(X, nullptr, Bv, true, wf + W1, sbias[1], R0, gy0, gx0, H, W, warp, lane);
+  __syncthreads();
+  // ---- stages 2..5: the two bottlenecks ---------------------------------------------------------
+  stage_conv3<C>(A, T, nullptr, wf + 2 * W1, sbias[2], R3, gy0, gx0, H, W, warp, lane);
+  __syncthreads();
+  stage_conv3<C>(T, A, A, wf + 2 * W1 + W3, sbias[3], R2, gy0, gx0, H, W, warp, lane);
+  __syncthreads();
+  stage_conv3<C>(A, T, nullptr, wf + 2 * W1 + 2 * W3, sbias[4], R1, gy0, gx0, H, W, warp, lane);
+  __syncthreads();
+  stage_conv3<C>(T, A, A, wf + 2 * W1 + 3 * W3, sbias[5], R0, gy0, gx0, H, W, warp, lane);
+  __syncthreads();
+  // ---- stage 6: y = cv3([v | b]) on R0 -> output tile staged in X (compact), then coalesced copy
+  stage_conv1<C, C, CC>(A, Bv, X, true, wf + 2 * W1 + 4 * W3, sbias[6], R0, gy0, gx0, H, W, warp, lane);
+  __syncthreads();
+  {
+    constexpr int CH16 = CC / 8;
+    __nv_bfloat16 *img = a.out + (long long)n * H * W * a.out_pitch;
+    const int total = TH * kTW * CH16;
+    for (int i = tid; i < total; i += kThreadsC3k) {
+      const int px = i / CH16, ch = i % CH16;
+      const int gy = ty0 + px / kTW, gx = tx0 + px % kTW;
+      if (gy < H && gx < W)
+        *reinterpret_cast<uint4 *>(img + ((long long)gy * W + gx) * a.out_pitch + ch * 8) = reinterpret_cast<const uint4 *>(X)[i];
+    }
+  }
+}
+
+// ---- host-side weight packing ------------------------------------------------------------------
+inline uint32_t pack2(float lo, float hi) {
+  __nv_bfloat16 a = __float2bfloat16_rn(lo), b = __float2bfloat16_rn(hi);
+  uint16_t ua, ub;
+  memcpy(&ua, &a, 2);
+  memcpy(&ub, &b, 2);
+  return (uint32_t)ua | ((uint32_t)ub << 16);
+}
+
+// kfun(k) -> weight of K-index k for output channel n (0 when padded)
+template <class F>
+void pack_frags(std::vector<uint32_t> &out, int ksteps, int ntiles, int cout, F wfun) {
+  for (int s = 0; s < ksteps; ++s)
+    for (int j = 0; j < ntiles; ++j)
+      for (int lane = 0; lane < 32; ++lane) {
+        const int g = lane >> 2, t = lane & 3, n = 8 * j + g;
+        auto w = [&](int kk) { return n < cout ? wfun(s, kk, n) : 0.f; };
+        out.push_back(pack2(w(2 * t), w(2 * t + 1)));
+        out.push_back(pack2(w(2 * t + 8), w(2 * t + 9)));
+      }
+}
+
+}  // namespace
+
+size_t c3k_smem_bytes(int c_, int th) {
+  const size_t frame_px = (size_t)(th + 8 + 1) * kPW;
+  return frame_px * (2 * c_ + c_ + c_) * 2 + (size_t)th * kTW * c_ * 2;
+}
+
+int c3k_pick_th(int h) { return h % 32 == 0 ? 32 : (h % 20 == 0 ? 20 : (h % 16 == 0 ? 16 : 0)); }
+
+bool c3k_supported(int c, int h, int w, int in_pitch, int in_coff, int out_pitch, int out_coff) {
+  if (!(c == 8 || c == 16 || c == 32)) return false;
+  if (w % kTW || c3k_pick_th(h) == 0) return false;
+  if (in_pitch % 8 || in_coff % 8 || out_pitch % 8 || out_coff % 8) return false;
+  return c3k_smem_bytes(c / 2, c3k_pick_th(h)) <= 220 * 1024;
+}
+
+// weights (PyTorch layout, BN folded): w[0]=cv1 [c_][c], w[1]=cv2 [c_][c], w[2..5] = m0.cv1, m0.cv2, m1.cv1,
+// m1.cv2 [c_][c_][3][3], w[6] = cv3 [c][2c_].  Returns packed fragments + [7][32] biases.
+void c3k_pack(int c, const float *const w[7], const float *const b[7], std::vector<uint32_t> &frags, std::vector<float> &bias) {
+  const int C = c / 2;
+  frags.clear();
+  bias.assign(7 * 32, 0.f);
+  const int couts[7] = {C, C, C, C, C, C, c};
+  for (int i = 0; i < 7; ++i)
+    for (int n = 0; n < couts[i]; ++n) bias[i * 32 + n] = b[i][n];
+  for (int i = 0; i < 2; ++i) {
+    const float *wi = w[i];
+    pack_frags(frags, (c + 15) / 16, (C + 7) / 8, C, [&](int s, int kk, int n) {
+      const int k = 16 * s + kk;
+      return k < c ? wi[(size_t)n * c + k] : 0.f;
+    });
+  }
+  const int tpk = 16 / C, steps3 = (9 + tpk - 1) / tpk;
+  for (int i = 2; i < 6; ++i) {
+    const float *wi = w[i];
+    pack_frags(frags, steps3, (C + 7) / 8, C, [&](int s, int kk, int n) {
+      const int tap = s * tpk + kk / C, ch = kk % C;
+      return tap < 9 ? wi[((size_t)n * C + ch) * 9 + tap] : 0.f;
+    });
+  }
+  const float *w6 = w[6];
+  pack_frags(frags, (c + 15) / 16, (c + 7) / 8, c, [&](int s, int kk, int n) {
+    const int k = 16 * s + kk;
+    return k < c ? w6[(size_t)n * c + k] : 0.f;
+  });
+}
+
+int c3k_launch(int c, const C3kArgs &a0, cudaStream_t s) {
+  C3kArgs a = a0;
+  a.th = c3k_pick_th(a.h);
+  a.tiles_x = a.w / kTW;
+  a.tiles_y = a.h / a.th;
+  const size_t smem = c3k_smem_bytes(c / 2, a.th);
+  const unsigned grid = (unsigned)(a.n * a.tiles_x * a.tiles_y);
+  static bool attr[3] = {false, false, false};
+  auto setup = [&](auto kern, int idx) -> int {
+    if (!attr[idx]) {
+      UYD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      attr[idx] = true;
+    }
+    kern<<<grid, kThreadsC3k, smem, s>>>(a);
+    return (int)cudaGetLastError();
+  };
+  if (c == 8) return setup(c3k_fused_kernel<4>, 0);
+  if (c == 16) return setup(c3k_fused_kernel<8>, 1);
+  return setup(c3k_fused_kernel<16>, 2);
+}
+
+}  // namespace uyd

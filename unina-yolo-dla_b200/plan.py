@@ -8,7 +8,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import IMPL_AUTO, UYD_BF16, UYD_F32, UYD_S8, ConvDesc, ConvS8Desc, check
+from ._lib import IMPL_AUTO, UYD_BF16, UYD_F32, UYD_S8, C3kDesc, ConvDesc, ConvS8Desc, check
 
 _TORCH_DTYPE = {UYD_BF16: torch.bfloat16, UYD_F32: torch.float32, UYD_S8: torch.int8}
 
@@ -93,6 +93,25 @@ class Plan:
         check(_lib.lib().uyd_plan_add_conv_s8(self.handle, C.byref(d), weight_q.ctypes.data_as(C.c_void_p),
                                               mult.ctypes.data_as(C.c_void_p), bias.ctypes.data_as(C.c_void_p)),
               "uyd_plan_add_conv_s8")
+        return dst
+
+    C3K_WIDTHS = (8, 16, 32)
+
+    @staticmethod
+    def c3k_supported(src: Slice, dst: Slice, src_pitch_ok: bool = True) -> bool:
+        """Shape rule of the fused C3k kernel (mirrors c3k_supported in csrc/c3k_fused.cu)."""
+        th_ok = src.h % 32 == 0 or src.h % 20 == 0 or src.h % 16 == 0
+        return src.c in Plan.C3K_WIDTHS and src.w % 40 == 0 and th_ok and src.coff % 8 == 0 and dst.coff % 8 == 0
+
+    def c3k(self, src: Slice, dst: Slice, weights: list, biases: list) -> Slice:
+        """Fused C3k block: weights/biases = [cv1, cv2, m0.cv1, m0.cv2, m1.cv1, m1.cv2, cv3], BN folded."""
+        ws = [np.ascontiguousarray(w, dtype=np.float32) for w in weights]
+        bs = [np.ascontiguousarray(b, dtype=np.float32) for b in biases]
+        assert len(ws) == 7 and len(bs) == 7
+        wp = (C.c_void_p * 7)(*[w.ctypes.data_as(C.c_void_p) for w in ws])
+        bp = (C.c_void_p * 7)(*[b.ctypes.data_as(C.c_void_p) for b in bs])
+        d = C3kDesc(src.buf, src.coff, dst.buf, dst.coff, src.c, 0)
+        check(_lib.lib().uyd_plan_add_c3k(self.handle, C.byref(d), wp, bp), "uyd_plan_add_c3k")
         return dst
 
     def sppf_pool(self, s: Slice, c: int) -> None:

@@ -13,6 +13,7 @@ from __future__ import annotations
 import ast
 import ctypes as C
 import math
+import os
 from math import gcd
 from pathlib import Path
 
@@ -89,6 +90,14 @@ class C3k(nn.Module):
         self.m = nn.Sequential(*(Bottleneck(c_, c_, shortcut, g, k=(k, k), e=1.0) for _ in range(n)))
 
     def emit(self, p, src, dst=None):
+        fusable = (len(self.m) == 2 and all(b.add and b.cv1.k == 3 and b.cv2.k == 3 for b in self.m)
+                   and self.cv3.c2 == src.c and 2 * self.c_ == src.c and os.environ.get("UYD_NO_C3K_FUSION", "0") != "1")
+        if fusable:
+            dst = dst or p.buffer(src.h, src.w, self.cv3.c2)
+            if p.c3k_supported(src, dst) and p.shapes[src.buf][2] % 8 == 0 and p.shapes[dst.buf][2] % 8 == 0:
+                folded = [fold_bn(m.conv, m.bn) for m in (self.cv1, self.cv2, self.m[0].cv1, self.m[0].cv2,
+                                                          self.m[1].cv1, self.m[1].cv2, self.cv3)]
+                return p.c3k(src, dst, [w for w, _ in folded], [b for _, b in folded])
         cat = p.buffer(src.h, src.w, 2 * self.c_)
         t = self.cv1.emit(p, src)
         for i, b in enumerate(self.m):
