@@ -306,7 +306,8 @@ void pack_frags(std::vector<uint32_t> &out, int ksteps, int ntiles, int cout, F 
 
 size_t c3k_smem_bytes(int c_, int th) {
   const size_t frame_px = (size_t)(th + 8 + 1) * kPW;
-  return frame_px * (2 * c_ + c_ + c_) * 2 + (size_t)th * kTW * c_ * 2;
+  // + 16 pixels of slack behind the compact b tile: partial segments of the last row read past it
+  return frame_px * (2 * c_ + c_ + c_) * 2 + ((size_t)th * kTW + 16) * c_ * 2;
 }
 
 int c3k_pick_th(int h) { return h % 32 == 0 ? 32 : (h % 20 == 0 ? 20 : (h % 16 == 0 ? 16 : 0)); }
