@@ -224,20 +224,22 @@ __global__ void __launch_bounds__(kThreads) conv_dw_kernel(ConvArgs a) {
 }
 
 // Tiled stem for the shape the network actually has (3 -> 16, 3x3, stride 2): a CTA stages the
-// 17 x 65 x 3 input patch of an 8 x 32 output tile in shared memory with coalesced row reads
-// (the frame is read once from HBM instead of 9x through L1), weights as fp32 in shared memory.
-constexpr int kStemTH = 8, kStemTW = 32;
+// 33 x 65 x 3 input patch of a 16 x 32 output tile in shared memory with coalesced row reads
+// (the frame is read once from HBM instead of 9x through L1); each thread computes two
+// horizontally adjacent output pixels x 16 channels so that every weight vector read from
+// shared memory feeds two FMAs (the kernel is FMA-bound, not LSU-bound).
+constexpr int kStemTH = 16, kStemTW = 32, kStemThreads = 256;
 template <typename TIn>
-__global__ void __launch_bounds__(kStemTH *kStemTW) conv_stem_tiled_kernel(ConvArgs a) {
-  constexpr int IH = 2 * kStemTH + 1, IW = 2 * kStemTW + 1;
-  __shared__ float sx[3][IH][IW + 1];
+__global__ void __launch_bounds__(kStemThreads) conv_stem_tiled_kernel(ConvArgs a) {
+  constexpr int IH = 2 * kStemTH + 1, IW = 2 * kStemTW + 1, IP = 68;  // row pitch: 16-byte aligned rows
+  __shared__ __align__(16) float sx[3][IH][IP];
   __shared__ __align__(16) float sw[27][16];
   const int tid = threadIdx.x;
   const int ox0 = blockIdx.x * kStemTW, oy0 = blockIdx.y * kStemTH, n = blockIdx.z;
-  for (int i = tid; i < 27 * 16; i += kStemTH * kStemTW)
+  for (int i = tid; i < 27 * 16; i += kStemThreads)
     sw[i / 16][i % 16] = __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(a.w)[i]);
   const TIn *in = reinterpret_cast<const TIn *>(a.in) + (long long)n * 3 * a.ih * a.iw;
-  for (int i = tid; i < 3 * IH * IW; i += kStemTH * kStemTW) {
+  for (int i = tid; i < 3 * IH * IW; i += kStemThreads) {
     const int c = i / (IH * IW), r = (i / IW) % IH, col = i % IW;
     const int iy = oy0 * 2 - 1 + r, ix = ox0 * 2 - 1 + col;
     float v = 0.f;
@@ -248,41 +250,52 @@ __global__ void __launch_bounds__(kStemTH *kStemTW) conv_stem_tiled_kernel(ConvA
     sx[c][r][col] = v;
   }
   __syncthreads();
-  const int tx = tid % kStemTW, ty = tid / kStemTW;
-  const int ox = ox0 + tx, oy = oy0 + ty;
+  const int tx = tid % (kStemTW / 2), ty = tid / (kStemTW / 2);
+  const int ox = ox0 + 2 * tx, oy = oy0 + ty;
   if (ox >= a.ow || oy >= a.oh) return;
-  float acc[16];
+  float acc[2][16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  for (int i = 0; i < 16; ++i) acc[0][i] = acc[1][i] = 0.f;
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx)
+    for (int ci = 0; ci < 3; ++ci) {
+      const float *row = &sx[ci][2 * ty + ky][4 * tx];
+      const float4 x4 = *reinterpret_cast<const float4 *>(row);
+      const float x[5] = {x4.x, x4.y, x4.z, x4.w, row[4]};
 #pragma unroll
-      for (int ci = 0; ci < 3; ++ci) {
-        const float x = sx[ci][2 * ty + ky][2 * tx + kx];
+      for (int kx = 0; kx < 3; ++kx) {
         const float4 *wr = reinterpret_cast<const float4 *>(sw[(ky * 3 + kx) * 3 + ci]);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float4 w4 = wr[q];
-          acc[4 * q] = fmaf(x, w4.x, acc[4 * q]);
-          acc[4 * q + 1] = fmaf(x, w4.y, acc[4 * q + 1]);
-          acc[4 * q + 2] = fmaf(x, w4.z, acc[4 * q + 2]);
-          acc[4 * q + 3] = fmaf(x, w4.w, acc[4 * q + 3]);
+          acc[0][4 * q] = fmaf(x[kx], w4.x, acc[0][4 * q]);
+          acc[0][4 * q + 1] = fmaf(x[kx], w4.y, acc[0][4 * q + 1]);
+          acc[0][4 * q + 2] = fmaf(x[kx], w4.z, acc[0][4 * q + 2]);
+          acc[0][4 * q + 3] = fmaf(x[kx], w4.w, acc[0][4 * q + 3]);
+          acc[1][4 * q] = fmaf(x[kx + 2], w4.x, acc[1][4 * q]);
+          acc[1][4 * q + 1] = fmaf(x[kx + 2], w4.y, acc[1][4 * q + 1]);
+          acc[1][4 * q + 2] = fmaf(x[kx + 2], w4.z, acc[1][4 * q + 2]);
+          acc[1][4 * q + 3] = fmaf(x[kx + 2], w4.w, acc[1][4 * q + 3]);
         }
       }
-  __nv_bfloat16 *op = reinterpret_cast<__nv_bfloat16 *>(a.out) + (((long long)n * a.oh + oy) * a.ow + ox) * a.out_pitch;
-  uint4 o[2];
-  uint32_t *pw = reinterpret_cast<uint32_t *>(o);
+    }
 #pragma unroll
-  for (int i = 0; i < 16; i += 2) {
-    float v0 = acc[i] + a.bias[i], v1 = acc[i + 1] + a.bias[i + 1];
-    if (a.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-    __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
-    pw[i / 2] = *reinterpret_cast<uint32_t *>(&h);
+  for (int px = 0; px < 2; ++px) {
+    if (ox + px >= a.ow) break;
+    __nv_bfloat16 *op = reinterpret_cast<__nv_bfloat16 *>(a.out) + (((long long)n * a.oh + oy) * a.ow + ox + px) * a.out_pitch;
+    uint4 o[2];
+    uint32_t *pw = reinterpret_cast<uint32_t *>(o);
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+      float v0 = acc[px][i] + a.bias[i], v1 = acc[px][i + 1] + a.bias[i + 1];
+      if (a.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+      __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+      pw[i / 2] = *reinterpret_cast<uint32_t *>(&h);
+    }
+    reinterpret_cast<uint4 *>(op)[0] = o[0];
+    reinterpret_cast<uint4 *>(op)[1] = o[1];
   }
-  reinterpret_cast<uint4 *>(op)[0] = o[0];
-  reinterpret_cast<uint4 *>(op)[1] = o[1];
 }
 
 // Depth-wise 3x3 stride 1, four horizontally adjacent pixels x 8 channels per thread: the 3 x 6
@@ -406,8 +419,8 @@ int direct_conv_launch(const ConvArgs &a, bool depthwise, cudaStream_t s) {
     if (a.cin == 3 && a.cout == 16 && a.k == 3 && a.stride == 2 && a.out_pitch % 8 == 0 &&
         (reinterpret_cast<uintptr_t>(a.out) & 15) == 0) {
       dim3 grid(ceil_div(a.ow, kStemTW), ceil_div(a.oh, kStemTH), a.n);
-      if (u8) conv_stem_tiled_kernel<uint8_t><<<grid, kStemTH * kStemTW, 0, s>>>(a);
-      else conv_stem_tiled_kernel<float><<<grid, kStemTH * kStemTW, 0, s>>>(a);
+      if (u8) conv_stem_tiled_kernel<uint8_t><<<grid, kStemThreads, 0, s>>>(a);
+      else conv_stem_tiled_kernel<float><<<grid, kStemThreads, 0, s>>>(a);
       return (int)cudaGetLastError();
     }
     if (a.cout % 16 == 0) {

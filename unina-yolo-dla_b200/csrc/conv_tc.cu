@@ -64,7 +64,7 @@ struct TcParams {
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;  // TMA warp + MMA warp + 2 x 4 epilogue warps
 constexpr int kHaloRows = 18, kHaloPitch = 16, kTileH = 16, kTileW = 8;
 constexpr int kMaxAcc = 4;  // TMEM accumulator stages
 
@@ -300,6 +300,7 @@ __device__ __forceinline__ void epilogue_chunk_i8_staged(const uint32_t (&raw)[1
   }
 }
 
+template <bool I8>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in,
                                                               const __grid_constant__ CUtensorMap tm_w, const TcParams p) {
   extern __shared__ unsigned char smem_dyn[];
@@ -335,7 +336,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   }
   for (int i = threadIdx.x; i < p.N; i += kThreads) {
     bias_s[i] = i < p.cout ? p.bias[i] : 0.f;
-    mult_s[i] = (p.i8 && i < p.cout) ? p.mult[i] : 0.f;
+    mult_s[i] = (I8 && i < p.cout) ? p.mult[i] : 0.f;
   }
   if (warp == 1) tmem_alloc(slot, tmem_cols);
   tc_fence_before();
@@ -346,7 +347,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const int blocks_per_tile = p.mode == TC_PERTAP ? p.ncb * p.taps : p.ncb;
   const int taps_in_block = p.mode == TC_HALO ? p.taps : 1;
   const int ksteps = p.cb_bytes / 32;
-  const int cb_elems = p.i8 ? p.cb_bytes : p.cb_bytes / 2;
+  const int cb_elems = I8 ? p.cb_bytes : p.cb_bytes / 2;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const int stages = p.stages;
   const uint32_t blk_bytes = p.blk_bytes, cb_bytes = p.cb_bytes;
@@ -419,7 +420,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             for (int k = 0; k < ksteps; ++k) {
               const uint64_t ad = adesc0 + (uint64_t)(((a_tap + 32u * k) & 0x3FFFFu) >> 4);
               const uint64_t bd = bdesc0 + (uint64_t)(((wblk + 32u * k) & 0x3FFFFu) >> 4);
-              if (p.i8) umma_i8(d_tmem, ad, bd, idesc, accum);
+              if (I8) umma_i8(d_tmem, ad, bd, idesc, accum);
               else umma_bf16(d_tmem, ad, bd, idesc, accum);
               accum = 1;
             }
@@ -439,16 +440,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int m = q * 32 + lane;
     const int nchunks = p.N >> 4;
     const bool staged = p.stage_pitch != 0;
-    const int esize = p.i8 ? (p.out_kind == 2 ? 1 : (p.out_kind == 1 ? 4 : 2)) : (p.out_f32 ? 4 : 2);
+    const int esize = I8 ? (p.out_kind == 2 ? 1 : (p.out_kind == 1 ? 4 : 2)) : (p.out_f32 ? 4 : 2);
     const int lpr = staged ? (p.cout * esize) / 16 : 1;  // 16-byte lanes per output row
     const int rows_per_it = 32 / lpr;
     const long long out_row_pitch = (long long)p.out_pitch * esize;
     long long *spix = reinterpret_cast<long long *>(smem_dyn + (bar0 + 1536u - raw)) + (warp - 2) * 32;
-    unsigned char *swarp = smem_dyn + (bar0 + 2560u - raw) + (size_t)(warp - 2) * 32 * p.stage_pitch;
+    unsigned char *swarp = smem_dyn + (bar0 + 3584u - raw) + (size_t)(warp - 2) * 32 * p.stage_pitch;
+    const int group = (warp - 2) >> 2;  // two epilogue warpgroups take alternate tiles
     unsigned char *srow = swarp + (size_t)lane * p.stage_pitch;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      if ((it & 1) != group) continue;
+      const int acc = it % nacc;  // nacc is even, so accumulator parity == group
+      const uint32_t acc_phase = (uint32_t)(it / nacc) & 1u;
       long long pix;  // flattened output pixel (n, oy, ox) or -1
       if (p.mode == TC_FLAT) {
         const long long row = tile * 128 + m;
@@ -476,7 +480,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
         if (staged) {
           if (c * 16 < p.cout) {
-            if (p.i8) epilogue_chunk_i8_staged(cur, bias_s, mult_s, c * 16, p, srow);
+            if (I8) epilogue_chunk_i8_staged(cur, bias_s, mult_s, c * 16, p, srow);
             else epilogue_chunk_staged(cur, bias_s, c * 16, pix, p, srow);
           }
         } else if (pix >= 0 && c * 16 < p.cout) {
@@ -501,7 +505,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
         __syncwarp();
       }
-      if (++acc == nacc) { acc = 0; acc_phase ^= 1u; }
     }
   }
   tc_fence_before();
@@ -661,7 +664,7 @@ int tc_prepare(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int i
                          (out_pitch * esize) % 16 == 0 && (reinterpret_cast<uintptr_t>(out_base) & 15) == 0;
   p.stage_pitch = can_stage ? p.N * esize + 16 : 0;
   UYD_REQUIRE(!i8 || can_stage, UYD_E_UNSUPPORTED, "conv_tc int8: output rows must be a power-of-two number of 16-byte lanes");
-  const size_t tail = 2560 + (size_t)128 * p.stage_pitch;  // barriers + bias + row->pixel map + staging
+  const size_t tail = 3584 + (size_t)256 * p.stage_pitch;  // barriers + bias + row->pixel map + staging
   const size_t wres = (p.w_bytes + 1023u) & ~1023u;
   const size_t budget = 227 * 1024 - 1024 - tail;
   if (p.mode == TC_HALO && wres + 2 * (size_t)p.blk_bytes > budget) {  // halo blocks too big: one box per tap
@@ -720,7 +723,8 @@ int tc_prepare(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int i
   }
   static bool attr = false;
   if (!attr) {
-    UYD_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    UYD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    UYD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
   return UYD_OK;
@@ -733,7 +737,8 @@ int tc_launch(const TcConv *tc, int n0, int nb, int sm_count, cudaStream_t s) {
   p.total_tiles = p.mode == TC_FLAT ? ((long long)nb * p.H * p.W + 127) / 128 : (long long)nb * p.tiles_x * p.tiles_y;
   if (p.total_tiles == 0) return UYD_OK;
   const unsigned grid = (unsigned)(p.total_tiles < sm_count ? p.total_tiles : sm_count);
-  conv_tc_kernel<<<grid, kThreads, tc->smem, s>>>(tc->tm_in, tc->tm_w, p);
+  if (p.i8) conv_tc_kernel<true><<<grid, kThreads, tc->smem, s>>>(tc->tm_in, tc->tm_w, p);
+  else conv_tc_kernel<false><<<grid, kThreads, tc->smem, s>>>(tc->tm_in, tc->tm_w, p);
   return (int)cudaGetLastError();
 }
 
