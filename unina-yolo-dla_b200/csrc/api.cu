@@ -24,7 +24,7 @@ void tc_pack_weights(const uyd_conv &d, const float *w, void *dst_host);
 int tc_prepare(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int ih, int iw, int max_batch, void *out_base,
                int out_pitch, int out_f32, const void *res_base, int res_pitch, void *w_dev, const float *bias_dev,
                int mode_override, int base_offset_mode, int stages_override, int i8 = 0, const float *mult_dev = nullptr,
-               float out_scale = 0.f, int out_kind = 0);
+               float out_scale = 0.f, int out_kind = 0, int halo_pitch = 10);
 bool tc_supported_s8(int cin, int cout, int k, int stride, int in_pitch, int in_coff, int out_pitch, int out_coff, int out_esize);
 size_t tc_weight_bytes_s8(int cin, int cout, int k);
 void tc_pack_weights_s8(int cin, int cout, int k, const int8_t *w, void *dst_host);
@@ -352,6 +352,7 @@ extern "C" int uyd_plan_finalize(uyd_plan *plan) {
   // "(addr >> 7) & 7" reading of the PTX text, produces wrong results and is kept as a probe).
   const int bo_mode = env_int("UYD_TC_BASE_OFFSET", 0);
   const int stages = env_int("UYD_TC_STAGES", 0);
+  const int halo_pitch = env_int("UYD_TC_HALO_PITCH", 10);
   for (Op &o : plan->ops) {
     if (o.kind != OP_CONV && o.kind != OP_CONV_S8 && o.kind != OP_C3K) continue;
     UYD_CUDA(cudaMalloc(&o.w_dev, o.w_host.size()));
@@ -371,7 +372,7 @@ extern "C" int uyd_plan_finalize(uyd_plan *plan) {
         o.tc = tc_new();
         int e = tc_prepare(o.tc, d, slice_ptr(plan, d.in_buf, d.in_coff), ib.c, ib.h, ib.w, plan->max_batch,
                            slice_ptr(plan, d.out_buf, d.out_coff), ob.c, 0, nullptr, 0, o.w_dev, o.b_dev, halo_fallback ? 2 : -1,
-                           bo_mode, stages, 1, o.m_dev, o.out_scale, o.out_kind);
+                           bo_mode, stages, 1, o.m_dev, o.out_scale, o.out_kind, halo_pitch);
         if (e) return e;
       }
       continue;
@@ -383,7 +384,8 @@ extern "C" int uyd_plan_finalize(uyd_plan *plan) {
       const void *res = d.res_buf >= 0 ? slice_ptr(plan, d.res_buf, d.res_coff) : nullptr;
       int e = tc_prepare(o.tc, d, slice_ptr(plan, d.in_buf, d.in_coff), ib.c, ib.h, ib.w, plan->max_batch,
                          slice_ptr(plan, d.out_buf, d.out_coff), ob.c, ob.dtype == UYD_F32, res,
-                         d.res_buf >= 0 ? plan->bufs[d.res_buf].c : 0, o.w_dev, o.b_dev, halo_fallback ? 2 : -1, bo_mode, stages);
+                         d.res_buf >= 0 ? plan->bufs[d.res_buf].c : 0, o.w_dev, o.b_dev, halo_fallback ? 2 : -1, bo_mode, stages, 0,
+                         nullptr, 0.f, 0, halo_pitch);
       if (e) return e;
     }
   }

@@ -231,7 +231,9 @@ __global__ void __launch_bounds__(kThreads) conv_dw_kernel(ConvArgs a) {
 constexpr int kStemTH = 16, kStemTW = 32, kStemThreads = 256;
 template <typename TIn>
 __global__ void __launch_bounds__(kStemThreads) conv_stem_tiled_kernel(ConvArgs a) {
-  constexpr int IH = 2 * kStemTH + 1, IW = 2 * kStemTW + 1, IP = 68;  // row pitch: 16-byte aligned rows
+  // shared tile column j holds image column ox0*2 - 4 + j (4-element aligned so that rows are fetched
+  // as 16-byte / 4-byte vectors); the conv reads columns 3 .. 67
+  constexpr int IH = 2 * kStemTH + 1, NV = (2 * kStemTW) / 4 + 2, IP = NV * 4;
   __shared__ __align__(16) float sx[3][IH][IP];
   __shared__ __align__(16) float sw[27][16];
   const int tid = threadIdx.x;
@@ -239,15 +241,36 @@ __global__ void __launch_bounds__(kStemThreads) conv_stem_tiled_kernel(ConvArgs 
   for (int i = tid; i < 27 * 16; i += kStemThreads)
     sw[i / 16][i % 16] = __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(a.w)[i]);
   const TIn *in = reinterpret_cast<const TIn *>(a.in) + (long long)n * 3 * a.ih * a.iw;
-  for (int i = tid; i < 3 * IH * IW; i += kStemThreads) {
-    const int c = i / (IH * IW), r = (i / IW) % IH, col = i % IW;
-    const int iy = oy0 * 2 - 1 + r, ix = ox0 * 2 - 1 + col;
-    float v = 0.f;
-    if (iy >= 0 && iy < a.ih && ix >= 0 && ix < a.iw) {
-      v = (float)in[((long long)c * a.ih + iy) * a.iw + ix];
-      if (sizeof(TIn) == 1) v = __fdiv_rn(v, 255.0f);
+  const bool vec_ok = a.iw % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+#pragma unroll 4
+  for (int i = tid; i < 3 * IH * NV; i += kStemThreads) {
+    const int c = i / (IH * NV), r = (i / NV) % IH, j = i % NV;
+    const int iy = oy0 * 2 - 1 + r, ix = ox0 * 2 - 4 + 4 * j;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (iy >= 0 && iy < a.ih) {
+      const TIn *src = in + ((long long)c * a.ih + iy) * a.iw + ix;
+      if (vec_ok && ix >= 0 && ix + 3 < a.iw) {
+        if (sizeof(TIn) == 4) {
+          v = *reinterpret_cast<const float4 *>(src);
+        } else {
+          const uchar4 u = *reinterpret_cast<const uchar4 *>(src);
+          v = make_float4(__fdiv_rn((float)u.x, 255.f), __fdiv_rn((float)u.y, 255.f), __fdiv_rn((float)u.z, 255.f),
+                          __fdiv_rn((float)u.w, 255.f));
+        }
+      } else {
+        float t[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          t[e] = 0.f;
+          if (ix + e >= 0 && ix + e < a.iw) {
+            t[e] = (float)src[e];
+            if (sizeof(TIn) == 1) t[e] = __fdiv_rn(t[e], 255.0f);
+          }
+        }
+        v = make_float4(t[0], t[1], t[2], t[3]);
+      }
     }
-    sx[c][r][col] = v;
+    *reinterpret_cast<float4 *>(&sx[c][r][4 * j]) = v;
   }
   __syncthreads();
   const int tx = tid % (kStemTW / 2), ty = tid / (kStemTW / 2);
@@ -260,9 +283,8 @@ __global__ void __launch_bounds__(kStemThreads) conv_stem_tiled_kernel(ConvArgs 
   for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
     for (int ci = 0; ci < 3; ++ci) {
-      const float *row = &sx[ci][2 * ty + ky][4 * tx];
-      const float4 x4 = *reinterpret_cast<const float4 *>(row);
-      const float x[5] = {x4.x, x4.y, x4.z, x4.w, row[4]};
+      const float *row = &sx[ci][2 * ty + ky][4 * tx + 3];  // image column 2*ox - 1
+      const float x[5] = {row[0], row[1], row[2], row[3], row[4]};
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
         const float4 *wr = reinterpret_cast<const float4 *>(sw[(ky * 3 + kx) * 3 + ci]);

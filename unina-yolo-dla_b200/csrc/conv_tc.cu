@@ -42,6 +42,7 @@ struct TcParams {
   long long total_tiles;
   int stages;
   int nacc;              // TMEM accumulator stages (nacc * N columns)
+  int halo_pitch;        // HALO: pixels per halo row in shared memory (10 = dense single TMA box, 16 = padded rows)
   int stage_pitch;       // bytes per row of the epilogue staging tile (0 = direct stores)
   int i8;                // 1: int8 operands, int32 accumulate (kind::i8), requant epilogue
   int out_kind;          // i8 path: 0 = bf16, 1 = fp32, 2 = int8 (re-quantised with out_scale)
@@ -65,7 +66,7 @@ struct TcParams {
 namespace {
 
 constexpr int kThreads = 320;  // TMA warp + MMA warp + 2 x 4 epilogue warps
-constexpr int kHaloRows = 18, kHaloPitch = 16, kTileH = 16, kTileW = 8;
+constexpr int kHaloRows = 18, kTileH = 16, kTileW = 8;
 constexpr int kMaxAcc = 4;  // TMEM accumulator stages
 
 // ---- PTX wrappers ------------------------------------------------------------------------
@@ -381,8 +382,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             tma_load_2d(dst, &tm_in, fb, j * cb_elems, (int)row0);
           }
         } else if (p.mode == TC_HALO) {
-          if (lane < kHaloRows)
-            tma_load_4d(dst + (uint32_t)lane * kHaloPitch * cb_bytes, &tm_in, fb, j * cb_elems, x0 - 1, y0 - 1 + lane, n);
+          if (p.halo_pitch == kTileW + 2) {  // one dense [18][10][CB] box: the 8-row groups are not 1024-byte
+            if (lane == 0)                   // aligned, which is fine because the swizzle is a function of the address
+              tma_load_4d(dst, &tm_in, fb, j * cb_elems, x0 - 1, y0 - 1, n);
+          } else if (lane < kHaloRows) {
+            tma_load_4d(dst + (uint32_t)lane * p.halo_pitch * cb_bytes, &tm_in, fb, j * cb_elems, x0 - 1, y0 - 1 + lane, n);
+          }
         } else {
           if (lane == 0) {
             const int cb = j / p.taps, tap = j % p.taps;
@@ -416,7 +421,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           uint32_t accum = j != 0;
           for (int t = 0; t < taps_in_block; ++t) {
             // HALO: tap (r, s) starts (r * pitch + s) pixels into the halo block
-            const uint32_t a_tap = halo ? ablk + (uint32_t)((t / 3) * kHaloPitch + (t % 3)) * cb_bytes : ablk;
+            const uint32_t a_tap = halo ? ablk + (uint32_t)((t / 3) * p.halo_pitch + (t % 3)) * cb_bytes : ablk;
             for (int k = 0; k < ksteps; ++k) {
               const uint64_t ad = adesc0 + (uint64_t)(((a_tap + 32u * k) & 0x3FFFFu) >> 4);
               const uint64_t bd = bdesc0 + (uint64_t)(((wblk + 32u * k) & 0x3FFFFu) >> 4);
@@ -593,7 +598,10 @@ bool tc_supported_s8(int cin, int cout, int k, int stride, int in_pitch, int in_
   const int rb = cout * out_esize;
   if (rb < 16 || rb > 512 || (rb & (rb - 1)) || (out_pitch * out_esize) % 16 || (out_coff * out_esize) % 16) return false;
   const int N = (cout + 15) / 16 * 16;
-  return (size_t)cin * k * k * N <= 150 * 1024;
+  // resident weights + two 128-row stages + staging tile must fit
+  const size_t need = (((size_t)cin * k * k * N + 1023) & ~(size_t)1023) + 2 * (size_t)128 * pick_cb_s8(cin) + 3584 +
+                      (size_t)256 * (N * out_esize + 16) + 1024;
+  return need <= 227 * 1024;
 }
 
 size_t tc_weight_bytes_s8(int cin, int cout, int k) { return (size_t)cin * k * k * ((cout + 15) / 16 * 16); }
@@ -615,7 +623,7 @@ void tc_pack_weights_s8(int cin, int cout, int k, const int8_t *w, void *dst_hos
 int tc_prepare(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int ih, int iw, int max_batch, void *out_base,
                int out_pitch, int out_f32, const void *res_base, int res_pitch, void *w_dev, const float *bias_dev,
                int mode_override, int base_offset_mode, int stages_override, int i8 = 0, const float *mult_dev = nullptr,
-               float out_scale = 0.f, int out_kind = 0) {
+               float out_scale = 0.f, int out_kind = 0, int halo_pitch = 10) {
   TcParams &p = tc->p;
   memset(&p, 0, sizeof(p));
   const int es = i8 ? 1 : 2;
@@ -646,9 +654,10 @@ int tc_prepare(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int i
   p.tiles_x = ceil_div(p.W, kTileW);
   p.tiles_y = ceil_div(p.H, kTileH);
   if (p.mode == TC_HALO) {
-    p.blk_bytes = (uint32_t)kHaloRows * kHaloPitch * p.cb_bytes;
+    p.halo_pitch = halo_pitch == 16 ? 16 : kTileW + 2;
+    p.blk_bytes = (uint32_t)kHaloRows * p.halo_pitch * p.cb_bytes;
     p.tx_bytes = (uint32_t)kHaloRows * (kTileW + 2) * p.cb_bytes;
-    p.sbo_a = (uint32_t)kHaloPitch * p.cb_bytes;
+    p.sbo_a = (uint32_t)p.halo_pitch * p.cb_bytes;
   } else {
     p.blk_bytes = 128u * p.cb_bytes;
     p.tx_bytes = p.blk_bytes;
@@ -664,8 +673,12 @@ int tc_prepare(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int i
                          (out_pitch * esize) % 16 == 0 && (reinterpret_cast<uintptr_t>(out_base) & 15) == 0;
   p.stage_pitch = can_stage ? p.N * esize + 16 : 0;
   UYD_REQUIRE(!i8 || can_stage, UYD_E_UNSUPPORTED, "conv_tc int8: output rows must be a power-of-two number of 16-byte lanes");
-  const size_t tail = 3584 + (size_t)256 * p.stage_pitch;  // barriers + bias + row->pixel map + staging
   const size_t wres = (p.w_bytes + 1023u) & ~1023u;
+  size_t tail = 3584 + (size_t)256 * p.stage_pitch;  // barriers + bias + row->pixel map + staging
+  if (!i8 && wres + 2 * (size_t)(128u * p.cb_bytes) > 227 * 1024 - 1024 - tail) {
+    p.stage_pitch = 0;  // weights leave no room for the staging tile: per-thread row stores
+    tail = 3584;
+  }
   const size_t budget = 227 * 1024 - 1024 - tail;
   if (p.mode == TC_HALO && wres + 2 * (size_t)p.blk_bytes > budget) {  // halo blocks too big: one box per tap
     p.mode = TC_PERTAP;
@@ -710,7 +723,7 @@ int tc_prepare(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int i
     const cuuint64_t dims[4] = {(cuuint64_t)d.cin, (cuuint64_t)iw, (cuuint64_t)ih, (cuuint64_t)max_batch};
     const cuuint64_t str[3] = {(cuuint64_t)in_pitch * es, (cuuint64_t)iw * in_pitch * es, (cuuint64_t)ih * iw * in_pitch * es};
     if (p.mode == TC_HALO) {
-      const cuuint32_t box[4] = {(cuuint32_t)CB, (cuuint32_t)(kTileW + 2), 1, 1};
+      const cuuint32_t box[4] = {(cuuint32_t)CB, (cuuint32_t)(kTileW + 2), p.halo_pitch == 16 ? 1u : (cuuint32_t)kHaloRows, 1};
       int e = encode(&tc->tm_in, in_base, 4, dims, str, box, one4, p.cb_bytes, i8);
       if (e) return e;
     } else {
