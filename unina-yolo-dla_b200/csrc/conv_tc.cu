@@ -301,7 +301,7 @@ __device__ __forceinline__ void epilogue_chunk_i8_staged(const uint32_t (&raw)[1
   }
 }
 
-template <bool I8>
+template <bool I8, int KSTEPS>  // KSTEPS = 32-byte k-steps per channel block (cb_bytes / 32)
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in,
                                                               const __grid_constant__ CUtensorMap tm_w, const TcParams p) {
   extern __shared__ unsigned char smem_dyn[];
@@ -346,8 +346,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t tmem_base = *slot_ptr;
 
   const int blocks_per_tile = p.mode == TC_PERTAP ? p.ncb * p.taps : p.ncb;
-  const int taps_in_block = p.mode == TC_HALO ? p.taps : 1;
-  const int ksteps = p.cb_bytes / 32;
   const int cb_elems = I8 ? p.cb_bytes : p.cb_bytes / 2;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const int stages = p.stages;
@@ -408,6 +406,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const uint32_t wblk_bytes = (uint32_t)p.N * cb_bytes;
     const uint32_t idesc = p.idesc;
     const bool halo = p.mode == TC_HALO;
+    const uint32_t px_units = cb_bytes >> 4, row_units = (uint32_t)p.halo_pitch * px_units, wblk_units = wblk_bytes >> 4;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       mbar_wait(tempty0 + 8u * acc, acc_phase ^ 1u);
       tc_fence_after();
@@ -416,20 +415,31 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         mbar_wait(full0 + 8u * stage, phase);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t ablk = a_s + (uint32_t)stage * blk_bytes;
-          uint32_t wblk = w_s + (uint32_t)(halo ? j * p.taps : j) * wblk_bytes;
+          // The issue loop runs in ONE thread: every instruction here sits on the critical path of the
+          // tensor pipe, so descriptors are advanced by precomputed 16-byte-unit increments and both
+          // loops are fully unrolled (KSTEPS is a template parameter).
+          const uint64_t ablk_d = adesc0 + (uint64_t)(((a_s + (uint32_t)stage * blk_bytes) & 0x3FFFFu) >> 4);
+          uint64_t wd = bdesc0 + (uint64_t)(((w_s + (uint32_t)(halo ? j * 9 : j) * wblk_bytes) & 0x3FFFFu) >> 4);
           uint32_t accum = j != 0;
-          for (int t = 0; t < taps_in_block; ++t) {
-            // HALO: tap (r, s) starts (r * pitch + s) pixels into the halo block
-            const uint32_t a_tap = halo ? ablk + (uint32_t)((t / 3) * p.halo_pitch + (t % 3)) * cb_bytes : ablk;
-            for (int k = 0; k < ksteps; ++k) {
-              const uint64_t ad = adesc0 + (uint64_t)(((a_tap + 32u * k) & 0x3FFFFu) >> 4);
-              const uint64_t bd = bdesc0 + (uint64_t)(((wblk + 32u * k) & 0x3FFFFu) >> 4);
-              if (I8) umma_i8(d_tmem, ad, bd, idesc, accum);
-              else umma_bf16(d_tmem, ad, bd, idesc, accum);
+          if (halo) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              const uint64_t ad = ablk_d + (uint64_t)((t / 3) * row_units + (t % 3) * px_units);
+#pragma unroll
+              for (int k = 0; k < KSTEPS; ++k) {
+                if (I8) umma_i8(d_tmem, ad + 2 * k, wd + 2 * k, idesc, accum);
+                else umma_bf16(d_tmem, ad + 2 * k, wd + 2 * k, idesc, accum);
+                accum = 1;
+              }
+              wd += wblk_units;
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < KSTEPS; ++k) {
+              if (I8) umma_i8(d_tmem, ablk_d + 2 * k, wd + 2 * k, idesc, accum);
+              else umma_bf16(d_tmem, ablk_d + 2 * k, wd + 2 * k, idesc, accum);
               accum = 1;
             }
-            wblk += wblk_bytes;
           }
           umma_commit(empty0 + 8u * stage);  // smem slot is free once these MMAs retire
           if (j == blocks_per_tile - 1) umma_commit(tfull0 + 8u * acc);
@@ -736,8 +746,12 @@ int tc_prepare(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int i
   }
   static bool attr = false;
   if (!attr) {
-    UYD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    UYD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    UYD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    UYD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    UYD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    UYD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    UYD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    UYD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
   return UYD_OK;
@@ -750,8 +764,14 @@ int tc_launch(const TcConv *tc, int n0, int nb, int sm_count, cudaStream_t s) {
   p.total_tiles = p.mode == TC_FLAT ? ((long long)nb * p.H * p.W + 127) / 128 : (long long)nb * p.tiles_x * p.tiles_y;
   if (p.total_tiles == 0) return UYD_OK;
   const unsigned grid = (unsigned)(p.total_tiles < sm_count ? p.total_tiles : sm_count);
-  if (p.i8) conv_tc_kernel<true><<<grid, kThreads, tc->smem, s>>>(tc->tm_in, tc->tm_w, p);
-  else conv_tc_kernel<false><<<grid, kThreads, tc->smem, s>>>(tc->tm_in, tc->tm_w, p);
+  const int ks = p.cb_bytes / 32;
+#define UYD_TC_LAUNCH(I8V, KS) conv_tc_kernel<I8V, KS><<<grid, kThreads, tc->smem, s>>>(tc->tm_in, tc->tm_w, p)
+  if (p.i8) {
+    if (ks == 1) UYD_TC_LAUNCH(true, 1); else if (ks == 2) UYD_TC_LAUNCH(true, 2); else UYD_TC_LAUNCH(true, 4);
+  } else {
+    if (ks == 1) UYD_TC_LAUNCH(false, 1); else if (ks == 2) UYD_TC_LAUNCH(false, 2); else UYD_TC_LAUNCH(false, 4);
+  }
+#undef UYD_TC_LAUNCH
   return (int)cudaGetLastError();
 }
 
