@@ -248,6 +248,33 @@ def main():
     ms_e2e = timed(step_e2e, a.steps)
     n_det = int(cnt_host.sum().item())
 
+    # stage split of one resident step and batch-1 latency (p50 over 50 synchronised calls)
+    def span(fn, reps=5):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    y_keep = model.forward(x_dev, raw_heads=False)
+    ms_fwd_decode = span(lambda: model.forward(x_dev, raw_heads=False))
+    ms_stack = span(lambda: plan.run(x_dev))
+    ms_nms = span(lambda: model.nms(y_keep, CONF, IOU, MAX_DET))
+    x1 = x_dev[:1].contiguous()
+    for _ in range(5):
+        model.predict_batched(x1, CONF, IOU, MAX_DET)
+    lat = []
+    for _ in range(50):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        model.predict_batched(x1, CONF, IOU, MAX_DET)
+        torch.cuda.synchronize()
+        lat.append((time.perf_counter() - t0) * 1e3)
+    lat.sort()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -285,6 +312,9 @@ def main():
                      "share_of_conv_stack": ms[top] / sum(ms)},
         "conv_stack": {"ms_per_step_profiled": sum(ms), "tflops": conv_flops * B / (sum(ms) * 1e-3) / 1e12,
                        "frac_of_tensor_peak": conv_flops * B / (sum(ms) * 1e-3) / 1e12 / pk["tflops"]},
+        "stages_ms": {"conv_stack": ms_stack, "dfl_decode": ms_fwd_decode - ms_stack, "nms": ms_nms},
+        "latency_bs1_ms": {"p50": lat[len(lat) // 2], "min": lat[0], "p90": lat[int(len(lat) * 0.9)], "calls": len(lat),
+                           "note": "predict_batched on one resident frame, host-synchronised wall clock"},
         "clocks": sampler.summary(),
     }
     if world == 1:

@@ -250,3 +250,38 @@ def test_fused_c3k_matches_torch(T, c, H, W):
     want = cb(torch.cat((v, b_), 1), 6)
     assert T.rel_err(got, want) < 1e-2
     assert float(p.read(dst.sub(0, c), B).abs().max()) == 0.0   # nothing written outside the slice
+
+
+def test_dense_scene_1280_nms_stress_is_bit_exact(T):
+    """BASELINE config 5: 1280x1280 (134 400 anchors), ~100k candidates per image: exercises the
+    top-30000 truncation and the early exit at 300 kept boxes."""
+    import unina_yolo_dla_b200 as uyd
+    from oracle import postproc as pp
+
+    A = 102400 + 25600 + 6400
+    y = T.synth_predictions(3, 4, A, seed=9, frac_conf=0.75, img=1280.0, cluster=True)
+    want, widx = pp.non_max_suppression(y, 0.25, 0.7, 300, 30000, return_index=True)
+    m = uyd.UninaYoloB200.from_yaml()
+    det, cnt, idx = m.nms(torch.from_numpy(y).cuda(), 0.25, 0.7, 300, 30000, return_index=True)
+    det, cnt, idx = det.cpu().numpy(), cnt.cpu().numpy(), idx.cpu().numpy()
+    assert (y[:, 4:].max(1) > 0.25).sum(1).min() > 90000
+    for b in range(3):
+        n = len(want[b])
+        assert cnt[b] == n
+        np.testing.assert_array_equal(idx[b, :n], widx[b])
+        assert det[b, :n].tobytes() == want[b].tobytes()
+
+
+def test_full_forward_1280_matches_oracle(T):
+    from oracle import init as oi
+
+    m, ref = _paired_models(seed=1)
+    x = oi.seeded_frames(1, 1280, seed=6)
+    with torch.no_grad():
+        y_ref, raw_ref = ref(x)
+    y, raws = m(x.cuda())
+    torch.cuda.synchronize()
+    assert y.shape == (1, 8, 134400)
+    for a, b in zip(raws, raw_ref):
+        assert T.rel_err(a.cpu()[:, :64], b[:, :64]) <= 1e-2 and T.rel_err(a.cpu()[:, 64:], b[:, 64:]) <= 1e-2
+    assert T.rel_err(y.cpu()[:, :4], y_ref[:, :4]) <= 1e-2
