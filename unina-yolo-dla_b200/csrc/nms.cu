@@ -246,18 +246,32 @@ __global__ void __launch_bounds__(kGreedyThreads) nms_greedy_kernel(const float4
       mask[r][cw] = bits;
     }
     __syncthreads();
-    // (d) serial resolution by warp 0: lane l owns suppression word l
+    // (d) resolution by warp 0: lane l owns suppression word l.  Instead of walking every survivor the
+    // warp jumps straight to the next unsuppressed one (ballot over the lanes' words + ffs), so the
+    // serial chain has one link per KEPT box, not per candidate.
     if (wid == 0) {
       unsigned remv = 0;
       int k = kept;
-      for (int r = 0; r < m && k < max_det; ++r) {
-        const unsigned wbits = __shfl_sync(0xffffffffu, remv, r >> 5);
-        if ((wbits >> (r & 31)) & 1u) continue;
+      int r = 0;
+      while (k < max_det) {
+        // candidates >= r that are still alive, restricted to valid indices < m
+        const int base_bit = lane * 32;
+        unsigned alive_bits = ~remv;
+        if (base_bit + 32 <= r) alive_bits = 0u;
+        else if (base_bit < r) alive_bits &= ~0u << (r - base_bit);
+        if (base_bit >= m) alive_bits = 0u;
+        else if (base_bit + 32 > m) alive_bits &= (m - base_bit) == 32 ? ~0u : ((1u << (m - base_bit)) - 1u);
+        const unsigned lanes = __ballot_sync(0xffffffffu, alive_bits != 0u);
+        if (!lanes) break;
+        const int src_lane = __ffs(lanes) - 1;
+        const int bit = __ffs(__shfl_sync(0xffffffffu, alive_bits, src_lane)) - 1;
+        r = src_lane * 32 + bit;
         if (lane == 0) {
           kbox[k] = abox[r]; karea[k] = aarea[r]; kcls[k] = acls[r]; ksrc[k] = asrc[r];
         }
         ++k;
         if (lane < words) remv |= mask[r][lane];
+        ++r;
       }
       if (lane == 0) s_kept = k;
     }
