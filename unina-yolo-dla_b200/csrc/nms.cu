@@ -31,7 +31,7 @@
 namespace uyd {
 namespace {
 
-constexpr int kChunk = 512;
+constexpr int kChunk = 128;
 constexpr int kGreedyThreads = 512;
 constexpr int kMaxDetCap = 1024;
 constexpr int kAnchorBits = 22;
@@ -166,11 +166,17 @@ __device__ __forceinline__ bool suppresses(const float4 &a, float aa, int ca, co
   const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y), xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
   const float w = fmaxf(0.f, __fsub_rn(xx2, xx1)), h = fmaxf(0.f, __fsub_rn(yy2, yy1));
   const float inter = __fmul_rn(w, h);
+  // inter == 0 gives 0/x = 0 or 0/0 = NaN: never > thr for thr >= 0, so the division is skipped
+  if (inter == 0.f && thr >= 0.f) return false;
   return __fdiv_rn(inter, __fsub_rn(__fadd_rn(aa, ab), inter)) > thr;
 }
 
 // boxes/cls: candidates of image b at [b * cand_stride, ...), in processing order.
 // n_ptr[b] candidates (clamped to n_cap).  Writes kept ranks (<= max_det) and their number.
+//
+// The kernel is instruction-bound (ncu: IPC ~4 on the 64 SMs that hold a CTA), so the work per
+// candidate is kept minimal: chunks of 128 candidates (the within-chunk bitmask costs chunk^2/2
+// IoUs, so small chunks are cheap), 4 threads per candidate splitting the kept list in phase (a).
 template <bool HPP>
 __global__ void __launch_bounds__(kGreedyThreads) nms_greedy_kernel(const float4 *__restrict__ boxes,
                                                                     const int *__restrict__ cls, long long cand_stride,
@@ -198,22 +204,27 @@ __global__ void __launch_bounds__(kGreedyThreads) nms_greedy_kernel(const float4
   if (tid == 0) s_kept = 0;
   __syncthreads();
 
+  constexpr int kSplit = kGreedyThreads / kChunk;  // threads per candidate in phase (a)
   for (int c0 = 0; c0 < n; c0 += kChunk) {
     const int kept = s_kept;
     if (kept >= max_det) break;
-    // (a) test against the kept list
-    const int i = c0 + tid;
-    bool alive = i < n;
+    // (a) test against the kept list: kSplit consecutive lanes share a candidate
+    const int i = c0 + tid / kSplit, slice = tid % kSplit;
+    const bool valid = i < n;
     float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
     float ar = 0.f;
     int cl = 0;
-    if (alive) {
+    bool sup = false;
+    if (valid) {
       bx = cbox[i];
       cl = ccls[i];
       ar = box_area(bx);
-      for (int k = 0; k < kept; ++k)
-        if (suppresses<HPP>(kbox[k], karea[k], kcls[k], bx, ar, cl, thr)) { alive = false; break; }
+      for (int k = slice; k < kept; k += kSplit)
+        if (suppresses<HPP>(kbox[k], karea[k], kcls[k], bx, ar, cl, thr)) { sup = true; break; }
     }
+#pragma unroll
+    for (int o = 1; o < kSplit; o <<= 1) sup |= __shfl_xor_sync(0xffffffffu, sup ? 1 : 0, o) != 0;
+    const bool alive = valid && !sup && slice == 0;  // one representative lane per candidate
     // (b) ordered compaction of survivors
     const unsigned bal = __ballot_sync(0xffffffffu, alive);
     if (lane == 0) warp_cnt[wid] = __popc(bal);
@@ -246,21 +257,19 @@ __global__ void __launch_bounds__(kGreedyThreads) nms_greedy_kernel(const float4
       mask[r][cw] = bits;
     }
     __syncthreads();
-    // (d) resolution by warp 0: lane l owns suppression word l.  Instead of walking every survivor the
-    // warp jumps straight to the next unsuppressed one (ballot over the lanes' words + ffs), so the
-    // serial chain has one link per KEPT box, not per candidate.
+    // (d) resolution by warp 0: lane l owns suppression word l.  The warp jumps straight to the next
+    // unsuppressed survivor (ballot over the lanes' words + ffs): one serial link per KEPT box.
     if (wid == 0) {
       unsigned remv = 0;
       int k = kept;
       int r = 0;
       while (k < max_det) {
-        // candidates >= r that are still alive, restricted to valid indices < m
         const int base_bit = lane * 32;
         unsigned alive_bits = ~remv;
         if (base_bit + 32 <= r) alive_bits = 0u;
         else if (base_bit < r) alive_bits &= ~0u << (r - base_bit);
         if (base_bit >= m) alive_bits = 0u;
-        else if (base_bit + 32 > m) alive_bits &= (m - base_bit) == 32 ? ~0u : ((1u << (m - base_bit)) - 1u);
+        else if (base_bit + 32 > m) alive_bits &= (1u << (m - base_bit)) - 1u;
         const unsigned lanes = __ballot_sync(0xffffffffu, alive_bits != 0u);
         if (!lanes) break;
         const int src_lane = __ffs(lanes) - 1;
