@@ -108,6 +108,17 @@ typedef struct uyd_c3k {
 } uyd_c3k;
 int uyd_plan_add_c3k(uyd_plan *plan, const uyd_c3k *desc, const float *const weights[7], const float *const biases[7]);
 
+/* Fused class branch of the Detect head (Detect.cv3[l], non-legacy): DWConv(cin,cin,3) -> Conv(cin,mid,1)
+ * -> DWConv(mid,mid,3) -> Conv(mid,mid,1) -> Conv2d(mid,nc,1) in one launch; the nc logits are
+ * written as fp32 into a slice of the head buffer.  weights/biases (BN folded): [0] dw1 [cin][1][3][3],
+ * [1] pw1 [mid][cin][1][1], [2] dw2 [mid][1][3][3], [3] pw2 [mid][mid][1][1], [4] pw3 [nc][mid][1][1] (+ its bias).
+ * cin in {32, 64}, mid == 32, nc <= 8, W % 40 == 0, H % 8 == 0. */
+typedef struct uyd_cls_branch {
+  int in_buf, in_coff, out_buf, out_coff, cin, mid, nc, reserved;
+} uyd_cls_branch;
+int uyd_plan_add_cls_branch(uyd_plan *plan, const uyd_cls_branch *desc, const float *const weights[5],
+                            const float *const biases[5]);
+
 /* SPPF cascade: reads slice [coff, coff+c) of buf and writes pool5, pool5^2, pool5^3 to
  * slices [coff+c, coff+2c), [coff+2c, ..), [coff+3c, ..) of the same buffer
  * (trainer.py:119-124; -inf padding). */

@@ -35,6 +35,14 @@ class FakePlan:
         self.ops.append(("c3k", src, dst, [torch.from_numpy(w) for w in weights], [torch.from_numpy(b) for b in biases]))
         return dst
 
+    @staticmethod
+    def cls_branch_supported(src, mid, nc):
+        return src.c in (32, 64) and mid == 32 and nc <= 8 and src.w % 40 == 0 and src.h % 8 == 0
+
+    def cls_branch(self, src, dst, mid, weights, biases):
+        self.ops.append(("cls", src, dst, [torch.from_numpy(w) for w in weights], [torch.from_numpy(b) for b in biases]))
+        return dst
+
     def sppf_pool(self, s, c):
         self.ops.append(("sppf", s, c))
 
@@ -64,6 +72,14 @@ class FakePlan:
                 if res is not None:
                     y = y + get(res)
                 bufs[dst.buf][:, dst.coff:dst.coff + dst.c] = y
+            elif op[0] == "cls":
+                _, src, dst, w, b = op
+                t = get(src)
+                t = F.conv2d(t, w[0], b[0], padding=1, groups=w[0].shape[0]).relu()
+                t = F.conv2d(t, w[1], b[1]).relu()
+                t = F.conv2d(t, w[2], b[2], padding=1, groups=w[2].shape[0]).relu()
+                t = F.conv2d(t, w[3], b[3]).relu()
+                bufs[dst.buf][:, dst.coff:dst.coff + dst.c] = F.conv2d(t, w[4], b[4])
             elif op[0] == "c3k":
                 _, src, dst, w, b = op
                 cb = lambda t, i, k: F.conv2d(t, w[i], b[i], padding=k // 2).relu()

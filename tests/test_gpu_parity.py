@@ -285,3 +285,36 @@ def test_full_forward_1280_matches_oracle(T):
     for a, b in zip(raws, raw_ref):
         assert T.rel_err(a.cpu()[:, :64], b[:, :64]) <= 1e-2 and T.rel_err(a.cpu()[:, 64:], b[:, 64:]) <= 1e-2
     assert T.rel_err(y.cpu()[:, :4], y_ref[:, :4]) <= 1e-2
+
+
+@pytest.mark.parametrize("cin,H,W", [(32, 40, 80), (64, 16, 40), (32, 160, 160)])
+def test_fused_cls_branch_matches_torch(T, cin, H, W):
+    import torch.nn.functional as F
+    import unina_yolo_dla_b200 as uyd
+    from unina_yolo_dla_b200._lib import UYD_F32
+
+    g = torch.Generator().manual_seed(cin + W)
+    B, mid, nc = 2, 32, 4
+    ws = [torch.randn(cin, 1, 3, 3, generator=g) / 3, torch.randn(mid, cin, 1, 1, generator=g) / cin ** 0.5,
+          torch.randn(mid, 1, 3, 3, generator=g) / 3, torch.randn(mid, mid, 1, 1, generator=g) / mid ** 0.5,
+          torch.randn(nc, mid, 1, 1, generator=g) / mid ** 0.5]
+    bs = [torch.randn(w.shape[0], generator=g) * 0.1 for w in ws]
+    x = torch.randn(B, cin, H, W, generator=g)
+    p = uyd.Plan(0, B)
+    src = p.buffer(H, W, cin)
+    head = p.buffer(H, W, 68, UYD_F32)
+    dst = head.sub(64, nc)
+    p.cls_branch(src, dst, mid, [w.numpy() for w in ws], [b.numpy() for b in bs])
+    p.finalize()
+    p.write(src, x)
+    p.run_no_input(B)
+    torch.cuda.synchronize()
+    got = p.read(dst, B).cpu()
+    r = T.bf16_round
+    t = r(F.conv2d(r(x), r(ws[0]), bs[0], padding=1, groups=cin).relu())
+    t = r(F.conv2d(t, r(ws[1]), bs[1]).relu())
+    t = r(F.conv2d(t, r(ws[2]), bs[2], padding=1, groups=mid).relu())
+    t = r(F.conv2d(t, r(ws[3]), bs[3]).relu())
+    want = F.conv2d(t, r(ws[4]), bs[4])
+    assert T.rel_err(got, want) < 1e-2
+    assert float(p.read(head.sub(0, 64), B).abs().max()) == 0.0

@@ -100,7 +100,8 @@ def test_emitted_plan_uses_fused_c3k_at_full_resolution(monkeypatch):
         y_ref, raw_ref = ref(x)
     p = _emit_fake(m, 1, 640, 640, monkeypatch)
     kinds = [o[0] for o in p.ops]
-    assert kinds.count("c3k") == 16 and kinds.count("conv") == 158 - 16 * 7
+    # 16 fused C3k blocks (7 convs each) and the class branches of the P2/P3 levels (5 convs each)
+    assert kinds.count("c3k") == 16 and kinds.count("cls") == 2 and kinds.count("conv") == 158 - 16 * 7 - 2 * 5
     bufs = p.execute(x)
     for h, r in zip(p.heads, raw_ref):
         assert torch.allclose(bufs[h.buf], r, rtol=1e-4, atol=1e-4)

@@ -32,6 +32,10 @@ class C3kDesc(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("in_buf", "in_coff", "out_buf", "out_coff", "c", "reserved")]
 
 
+class ClsBranchDesc(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("in_buf", "in_coff", "out_buf", "out_coff", "cin", "mid", "nc", "reserved")]
+
+
 class Detection(C.Structure):
     """Layout-identical to the reference GpuDetection (gpu_postprocess.h:27-33)."""
     _fields_ = [("x1", C.c_float), ("y1", C.c_float), ("x2", C.c_float), ("y2", C.c_float),
@@ -51,6 +55,7 @@ SIGNATURES = {
     "uyd_plan_add_conv": (C.c_int, [C.c_void_p, C.POINTER(ConvDesc), C.c_void_p, C.c_void_p]),
     "uyd_plan_add_conv_s8": (C.c_int, [C.c_void_p, C.POINTER(ConvS8Desc), C.c_void_p, C.c_void_p, C.c_void_p]),
     "uyd_plan_add_c3k": (C.c_int, [C.c_void_p, C.POINTER(C3kDesc), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "uyd_plan_add_cls_branch": (C.c_int, [C.c_void_p, C.POINTER(ClsBranchDesc), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "uyd_plan_add_sppf_pool": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "uyd_plan_add_upsample2x": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "uyd_plan_set_heads": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int]),

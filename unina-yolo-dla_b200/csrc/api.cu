@@ -45,6 +45,19 @@ bool c3k_supported(int c, int h, int w, int in_pitch, int in_coff, int out_pitch
 void c3k_pack(int c, const float *const w[7], const float *const b[7], std::vector<uint32_t> &frags, std::vector<float> &bias);
 int c3k_launch(int c, const C3kArgs &a, cudaStream_t s);
 
+struct ClsArgs {
+  const __nv_bfloat16 *in;
+  float *out;
+  const __nv_bfloat16 *wdw;
+  const uint32_t *wfrag;
+  const float *bias;
+  int n, h, w, in_pitch, out_pitch, nc, tiles_x, tiles_y;
+};
+bool cls_branch_supported(int cin, int mid, int nc, int h, int w, int in_pitch, int in_coff, int out_pitch, int out_coff);
+void cls_branch_pack(int cin, int nc, const float *const w[5], const float *const b[5], std::vector<__nv_bfloat16> &wdw,
+                     std::vector<uint32_t> &frags, std::vector<float> &bias);
+int cls_branch_launch(int cin, const ClsArgs &a, cudaStream_t s);
+
 static int env_int(const char *name, int dflt) {
   const char *v = getenv(name);
   return v && *v ? atoi(v) : dflt;
@@ -59,7 +72,7 @@ struct uyd_ctx {
   int sm_count = 0;
 };
 
-enum OpKind { OP_CONV = 0, OP_SPPF = 1, OP_UPSAMPLE = 2, OP_CONV_S8 = 3, OP_C3K = 4 };
+enum OpKind { OP_CONV = 0, OP_SPPF = 1, OP_UPSAMPLE = 2, OP_CONV_S8 = 3, OP_C3K = 4, OP_CLS = 5 };
 
 struct Op {
   OpKind kind;
@@ -75,6 +88,9 @@ struct Op {
   float *m_dev = nullptr;
   float out_scale = 0.f;
   int out_kind = 0;
+  std::vector<unsigned char> w2_host;  // cls branch: depth-wise weights
+  void *w2_dev = nullptr;
+  int nc = 0;
   // sppf / upsample
   int buf = -1, coff = 0, c = 0, out_buf = -1, out_coff = 0;
 };
@@ -138,6 +154,7 @@ extern "C" int uyd_plan_destroy(uyd_plan *plan) {
     if (o.w_dev) cudaFree(o.w_dev);
     if (o.b_dev) cudaFree(o.b_dev);
     if (o.m_dev) cudaFree(o.m_dev);
+    if (o.w2_dev) cudaFree(o.w2_dev);
     if (o.tc) tc_delete(o.tc);
   }
   if (plan->arena) cudaFree(plan->arena);
@@ -286,6 +303,34 @@ extern "C" int uyd_plan_add_c3k(uyd_plan *plan, const uyd_c3k *d, const float *c
   return UYD_OK;
 }
 
+extern "C" int uyd_plan_add_cls_branch(uyd_plan *plan, const uyd_cls_branch *d, const float *const weights[5],
+                                       const float *const biases[5]) {
+  UYD_REQUIRE(plan && d && weights && biases, UYD_E_ARG, "uyd_plan_add_cls_branch: NULL argument");
+  UYD_REQUIRE(!plan->finalized, UYD_E_STATE, "plan already finalized");
+  int e;
+  if ((e = check_slice(plan, d->in_buf, d->in_coff, d->cin, "cls branch input"))) return e;
+  if ((e = check_slice(plan, d->out_buf, d->out_coff, d->nc, "cls branch output"))) return e;
+  const Buffer &ib = plan->bufs[d->in_buf], &ob = plan->bufs[d->out_buf];
+  UYD_REQUIRE(ib.dtype == UYD_BF16 && ob.dtype == UYD_F32 && ib.h == ob.h && ib.w == ob.w, UYD_E_ARG,
+              "cls branch: bf16 input and fp32 output of equal extent");
+  UYD_REQUIRE(cls_branch_supported(d->cin, d->mid, d->nc, ib.h, ib.w, ib.c, d->in_coff, ob.c, d->out_coff), UYD_E_UNSUPPORTED,
+              "fused cls branch: cin=%d mid=%d nc=%d %dx%d unsupported (cin in {32,64}, mid 32, nc <= 8, W %% 40, H %% 8)",
+              d->cin, d->mid, d->nc, ib.h, ib.w);
+  for (int i = 0; i < 5; ++i) UYD_REQUIRE(weights[i] && biases[i], UYD_E_ARG, "uyd_plan_add_cls_branch: weight %d is NULL", i);
+  Op op;
+  op.kind = OP_CLS;
+  op.buf = d->in_buf; op.coff = d->in_coff; op.out_buf = d->out_buf; op.out_coff = d->out_coff; op.c = d->cin; op.nc = d->nc;
+  std::vector<__nv_bfloat16> wdw;
+  std::vector<uint32_t> frags;
+  cls_branch_pack(d->cin, d->nc, weights, biases, wdw, frags, op.b_host);
+  op.w_host.resize(frags.size() * 4);
+  memcpy(op.w_host.data(), frags.data(), op.w_host.size());
+  op.w2_host.resize(wdw.size() * 2);
+  memcpy(op.w2_host.data(), wdw.data(), op.w2_host.size());
+  plan->ops.push_back(std::move(op));
+  return UYD_OK;
+}
+
 extern "C" int uyd_plan_add_sppf_pool(uyd_plan *plan, int buf, int coff, int c) {
   UYD_REQUIRE(plan && !plan->finalized, UYD_E_STATE, "plan missing or finalized");
   int e;
@@ -354,7 +399,7 @@ extern "C" int uyd_plan_finalize(uyd_plan *plan) {
   const int stages = env_int("UYD_TC_STAGES", 0);
   const int halo_pitch = env_int("UYD_TC_HALO_PITCH", 10);
   for (Op &o : plan->ops) {
-    if (o.kind != OP_CONV && o.kind != OP_CONV_S8 && o.kind != OP_C3K) continue;
+    if (o.kind != OP_CONV && o.kind != OP_CONV_S8 && o.kind != OP_C3K && o.kind != OP_CLS) continue;
     UYD_CUDA(cudaMalloc(&o.w_dev, o.w_host.size()));
     UYD_CUDA(cudaMemcpy(o.w_dev, o.w_host.data(), o.w_host.size(), cudaMemcpyHostToDevice));
     UYD_CUDA(cudaMalloc((void **)&o.b_dev, o.b_host.size() * 4));
@@ -362,6 +407,11 @@ extern "C" int uyd_plan_finalize(uyd_plan *plan) {
     plan->bytes += o.w_host.size() + o.b_host.size() * 4;
     o.w_host.clear();
     o.w_host.shrink_to_fit();
+    if (o.kind == OP_CLS) {
+      UYD_CUDA(cudaMalloc(&o.w2_dev, o.w2_host.size()));
+      UYD_CUDA(cudaMemcpy(o.w2_dev, o.w2_host.data(), o.w2_host.size(), cudaMemcpyHostToDevice));
+      continue;
+    }
     if (o.kind == OP_C3K) continue;
     if (o.kind == OP_CONV_S8) {
       UYD_CUDA(cudaMalloc((void **)&o.m_dev, o.m_host.size() * 4));
@@ -436,6 +486,14 @@ static int launch_op(uyd_plan *plan, const Op &o, const void *x, int x_kind, int
       a.wfrag = (const uint32_t *)o.w_dev; a.bias = o.b_dev;
       a.n = batch; a.h = ib.h; a.w = ib.w; a.in_pitch = ib.c; a.out_pitch = ob.c;
       e = c3k_launch(o.c, a, s);
+    } else if (o.kind == OP_CLS) {
+      const Buffer &ib = plan->bufs[o.buf], &ob = plan->bufs[o.out_buf];
+      ClsArgs a{};
+      a.in = (const __nv_bfloat16 *)slice_ptr(plan, o.buf, o.coff);
+      a.out = (float *)slice_ptr(plan, o.out_buf, o.out_coff);
+      a.wdw = (const __nv_bfloat16 *)o.w2_dev; a.wfrag = (const uint32_t *)o.w_dev; a.bias = o.b_dev;
+      a.n = batch; a.h = ib.h; a.w = ib.w; a.in_pitch = ib.c; a.out_pitch = ob.c; a.nc = o.nc;
+      e = cls_branch_launch(o.c, a, s);
     } else if (o.kind == OP_CONV_S8) {
       const uyd_conv &d = o.conv;
       if (o.use_tc) {
@@ -551,6 +609,12 @@ extern "C" int uyd_plan_op_info(uyd_plan *plan, int op, char *text, size_t text_
          (d.res_buf >= 0 ? (double)ob.h * ob.w * d.cout * 2 : 0);
     snprintf(text, text_len, "conv %d->%d k%d s%d%s %dx%d %s%s%s", d.cin, d.cout, d.k, d.stride, d.depthwise ? " dw" : "", ob.h,
              ob.w, o.use_tc ? "tc:" : "direct", o.use_tc ? tc_mode_name(o.tc) : "", d.res_buf >= 0 ? " +res" : "");
+  } else if (o.kind == OP_CLS) {
+    const Buffer &b = plan->bufs[o.buf];
+    const double c = o.c;
+    fl = 2.0 * b.h * b.w * (9 * c + c * 32 + 9 * 32 + 32 * 32 + 32 * o.nc);
+    by = (double)b.h * b.w * (c * 2 + o.nc * 4);
+    snprintf(text, text_len, "cls_branch_fused c%d %dx%d (5 convs)", o.c, b.h, b.w);
   } else if (o.kind == OP_C3K) {
     const Buffer &b = plan->bufs[o.buf];
     const double c = o.c, h = c / 2;

@@ -30,6 +30,15 @@ struct C3kArgs {
   int n, h, w, in_pitch, out_pitch, th, tiles_x, tiles_y;
 };
 
+struct ClsArgs {
+  const __nv_bfloat16 *in;
+  float *out;               // head buffer slice base (fp32), pitch in floats
+  const __nv_bfloat16 *wdw; // [9][cin] then [9][32]  (bf16, tap-major)
+  const uint32_t *wfrag;    // pw1, pw2, pw3 fragments
+  const float *bias;        // [5][128]: dw1, pw1, dw2, pw2, pw3
+  int n, h, w, in_pitch, out_pitch, nc, tiles_x, tiles_y;
+};
+
 namespace {
 
 constexpr int kTW = 40;         // output tile width
@@ -280,6 +289,132 @@ __global__ void __launch_bounds__(kThreadsC3k) c3k_fused_kernel(C3kArgs a) {
   }
 }
 
+// =================================================================================================
+// Fused class branch of the Detect head (Ultralytics Detect.cv3[l], non-legacy):
+//     y1 = relu(dw3x3(x))   z1 = relu(pw(y1))   y2 = relu(dw3x3(z1))   z2 = relu(pw(z2))   out = pw(z2) + b
+// (DWConv(c,c,3) -> Conv(c,32,1) -> DWConv(32,32,3) -> Conv(32,32,1) -> Conv2d(32,nc,1)).
+// Unfused: five launches and ~10 HBM passes over 160x160x32 tensors per image.  Here a CTA owns an
+// 8 x 40 tile (+2 halo): depth-wise taps on CUDA cores out of shared memory, point-wise convs on
+// mma.sync, the nc logits go straight to the fp32 head buffer.
+// =================================================================================================
+constexpr int kClsTH = 8;
+
+// depth-wise 3x3 + bias + ReLU over `reg`:  src[frame][C] -> dst[frame][C]; thread = (pixel, 8 channels)
+template <int C>
+__device__ __forceinline__ void stage_dw(const __nv_bfloat16 *src, __nv_bfloat16 *dst, const __nv_bfloat16 *w,
+                                         const float *bias, Region reg, int tid) {
+  constexpr int CG = C / 8;
+  const int rw = reg.c1 - reg.c0;
+  const int total = (reg.r1 - reg.r0) * rw * CG;
+  for (int i = tid; i < total; i += kThreadsC3k) {
+    const int cg = i % CG, px = (i / CG) % rw + reg.c0, ry = i / (CG * rw) + reg.r0;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = bias[cg * 8 + j];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const uint4 xv = *reinterpret_cast<const uint4 *>(src + ((ry + t / 3 - 1) * kPW + px + t % 3 - 1) * C + cg * 8);
+      const uint4 wv = *reinterpret_cast<const uint4 *>(w + t * C + cg * 8);
+      const uint32_t *xp = reinterpret_cast<const uint32_t *>(&xv), *wp = reinterpret_cast<const uint32_t *>(&wv);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 xf = unpack_bf16(xp[j]), wf2 = unpack_bf16(wp[j]);
+        acc[2 * j] = fmaf(xf.x, wf2.x, acc[2 * j]);
+        acc[2 * j + 1] = fmaf(xf.y, wf2.y, acc[2 * j + 1]);
+      }
+    }
+    uint4 o;
+    uint32_t *op = reinterpret_cast<uint32_t *>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) op[j] = pack_bf16(fmaxf(acc[2 * j], 0.f), fmaxf(acc[2 * j + 1], 0.f));
+    *reinterpret_cast<uint4 *>(dst + (ry * kPW + px) * C + cg * 8) = o;
+  }
+}
+
+template <int CIN>
+__global__ void __launch_bounds__(kThreadsC3k) cls_branch_fused_kernel(ClsArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  constexpr int MID = 32, CW = CIN > MID ? CIN : MID;
+  constexpr int TH = kClsTH;
+  constexpr int frame_px = (TH + 4 + 1) * kPW;  // halo 2 + one slack row
+  __nv_bfloat16 *XZ = reinterpret_cast<__nv_bfloat16 *>(smem);  // x [frame][CIN], later z1 / z2 [frame][32]
+  __nv_bfloat16 *Y = XZ + (size_t)frame_px * CW;                // y1 [frame][CIN], later y2 [frame][32]
+  __shared__ float sbias[5][128];
+  __shared__ __align__(16) __nv_bfloat16 swdw[9 * (CIN + MID)];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.x;
+  const int n = tile / (a.tiles_x * a.tiles_y);
+  const int tr = tile % (a.tiles_x * a.tiles_y);
+  const int ty0 = (tr / a.tiles_x) * TH, tx0 = (tr % a.tiles_x) * kTW;
+  const int gy0 = ty0 - 2, gx0 = tx0 - 2;
+  const int H = a.h, W = a.w;
+  for (int i = tid; i < 5 * 128; i += kThreadsC3k) sbias[i / 128][i % 128] = a.bias[i];
+  for (int i = tid; i < 9 * (CIN + MID); i += kThreadsC3k) swdw[i] = a.wdw[i];
+  {  // x tile + halo (zero outside the image / in the slack columns and row)
+    constexpr int CH16 = CIN / 8;
+    const __nv_bfloat16 *img = a.in + (long long)n * H * W * a.in_pitch;
+    for (int i = tid; i < frame_px * CH16; i += kThreadsC3k) {
+      const int px = i / CH16, ch = i % CH16;
+      const int ry = px / kPW, rx = px % kPW;
+      const int gy = gy0 + ry, gx = gx0 + rx;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (ry < TH + 4 && rx < kTW + 4 && (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W)
+        v = *reinterpret_cast<const uint4 *>(img + ((long long)gy * W + gx) * a.in_pitch + ch * 8);
+      *reinterpret_cast<uint4 *>(XZ + (size_t)px * CIN + ch * 8) = v;
+    }
+    // y is read by partial mma segments beyond the region: keep the whole buffer finite
+    for (int i = tid; i < frame_px * CW / 8; i += kThreadsC3k) reinterpret_cast<uint4 *>(Y)[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  __syncthreads();
+  const Region R1{1, TH + 3, 1, kTW + 3}, R0{2, TH + 2, 2, kTW + 2};
+  constexpr int W1 = frag_words_1(CIN, MID), W2 = frag_words_1(MID, MID);
+  stage_dw<CIN>(XZ, Y, swdw, sbias[0], R1, tid);                                                           // y1
+  __syncthreads();
+  stage_conv1<CIN, 0, MID>(Y, nullptr, XZ, false, a.wfrag, sbias[1], R1, gy0, gx0, H, W, warp, lane);      // z1 (0 outside)
+  __syncthreads();
+  stage_dw<MID>(XZ, Y, swdw + 9 * CIN, sbias[2], R0, tid);                                                 // y2
+  __syncthreads();
+  stage_conv1<MID, 0, MID>(Y, nullptr, XZ, false, a.wfrag + W1, sbias[3], R0, gy0, gx0, H, W, warp, lane); // z2
+  __syncthreads();
+  {  // logits = pw3(z2) + bias  ->  fp32 head slice (N padded to 8, K = 32 = 2 k-steps)
+    const uint32_t *wf = a.wfrag + W1 + W2;
+    const int g = lane >> 2, t = lane & 3;
+    uint32_t bf[2][2];
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2) {
+      const uint2 v = reinterpret_cast<const uint2 *>(wf)[s2 * 32 + lane];
+      bf[s2][0] = v.x; bf[s2][1] = v.y;
+    }
+    float *img = a.out + (long long)n * H * W * a.out_pitch;
+    const int nseg = TH * 3;
+    for (int seg = warp; seg < nseg; seg += kWarps) {
+      const int ry = R0.r0 + seg / 3, rx = R0.c0 + (seg % 3) * 16;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2) {
+        uint32_t af[4];
+        const __nv_bfloat16 *p = XZ + (ry * kPW + rx + g) * MID + 16 * s2 + 2 * t;
+        af[0] = *reinterpret_cast<const uint32_t *>(p);
+        af[1] = *reinterpret_cast<const uint32_t *>(p + 8 * MID);
+        af[2] = *reinterpret_cast<const uint32_t *>(p + 8);
+        af[3] = *reinterpret_cast<const uint32_t *>(p + 8 * MID + 8);
+        mma16816(acc, af, bf[s2][0], bf[s2][1]);
+      }
+      const int nch = 2 * t;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int px = rx + g + 8 * half;
+        const int gy = gy0 + ry, gx = gx0 + px;
+        if (px >= R0.c1 || gy >= H || gx >= W) continue;
+        float *o = img + ((long long)gy * W + gx) * a.out_pitch + nch;
+        if (nch < a.nc) o[0] = acc[2 * half] + sbias[4][nch];
+        if (nch + 1 < a.nc) o[1] = acc[2 * half + 1] + sbias[4][nch + 1];
+      }
+    }
+  }
+}
+
 // ---- host-side weight packing ------------------------------------------------------------------
 inline uint32_t pack2(float lo, float hi) {
   __nv_bfloat16 a = __float2bfloat16_rn(lo), b = __float2bfloat16_rn(hi);
@@ -348,6 +483,50 @@ void c3k_pack(int c, const float *const w[7], const float *const b[7], std::vect
     const int k = 16 * s + kk;
     return k < c ? w6[(size_t)n * c + k] : 0.f;
   });
+}
+
+bool cls_branch_supported(int cin, int mid, int nc, int h, int w, int in_pitch, int in_coff, int out_pitch, int out_coff) {
+  if (!(cin == 32 || cin == 64) || mid != 32 || nc < 1 || nc > 8) return false;
+  if (w % kTW || h % kClsTH) return false;
+  return in_pitch % 8 == 0 && in_coff % 8 == 0;
+}
+
+// w[0] dw1 [cin][1][3][3], w[1] pw1 [32][cin], w[2] dw2 [32][1][3][3], w[3] pw2 [32][32], w[4] pw3 [nc][32]
+void cls_branch_pack(int cin, int nc, const float *const w[5], const float *const b[5], std::vector<__nv_bfloat16> &wdw,
+                     std::vector<uint32_t> &frags, std::vector<float> &bias) {
+  const int mid = 32;
+  wdw.assign((size_t)9 * (cin + mid), __float2bfloat16_rn(0.f));
+  for (int t = 0; t < 9; ++t) {
+    for (int c = 0; c < cin; ++c) wdw[(size_t)t * cin + c] = __float2bfloat16_rn(w[0][(size_t)c * 9 + t]);
+    for (int c = 0; c < mid; ++c) wdw[(size_t)9 * cin + (size_t)t * mid + c] = __float2bfloat16_rn(w[2][(size_t)c * 9 + t]);
+  }
+  bias.assign(5 * 128, 0.f);
+  const int widths[5] = {cin, mid, mid, mid, nc};
+  for (int i = 0; i < 5; ++i)
+    for (int c = 0; c < widths[i]; ++c) bias[i * 128 + c] = b[i][c];
+  frags.clear();
+  const float *w1 = w[1], *w3 = w[3], *w4 = w[4];
+  pack_frags(frags, (cin + 15) / 16, mid / 8, mid, [&](int s, int kk, int n) { return w1[(size_t)n * cin + 16 * s + kk]; });
+  pack_frags(frags, mid / 16, mid / 8, mid, [&](int s, int kk, int n) { return w3[(size_t)n * mid + 16 * s + kk]; });
+  pack_frags(frags, mid / 16, 1, nc, [&](int s, int kk, int n) { return w4[(size_t)n * mid + 16 * s + kk]; });
+}
+
+int cls_branch_launch(int cin, const ClsArgs &a0, cudaStream_t s) {
+  ClsArgs a = a0;
+  a.tiles_x = a.w / kTW;
+  a.tiles_y = a.h / kClsTH;
+  const int cw = cin > 32 ? cin : 32;
+  const size_t smem = (size_t)(kClsTH + 5) * kPW * cw * 2 * 2;
+  const unsigned grid = (unsigned)(a.n * a.tiles_x * a.tiles_y);
+  static bool attr[2] = {false, false};
+  if (cin == 32) {
+    if (!attr[0]) { UYD_CUDA(cudaFuncSetAttribute(cls_branch_fused_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr[0] = true; }
+    cls_branch_fused_kernel<32><<<grid, kThreadsC3k, smem, s>>>(a);
+  } else {
+    if (!attr[1]) { UYD_CUDA(cudaFuncSetAttribute(cls_branch_fused_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr[1] = true; }
+    cls_branch_fused_kernel<64><<<grid, kThreadsC3k, smem, s>>>(a);
+  }
+  return (int)cudaGetLastError();
 }
 
 int c3k_launch(int c, const C3kArgs &a0, cudaStream_t s) {

@@ -8,7 +8,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import IMPL_AUTO, UYD_BF16, UYD_F32, UYD_S8, C3kDesc, ConvDesc, ConvS8Desc, check
+from ._lib import IMPL_AUTO, UYD_BF16, UYD_F32, UYD_S8, C3kDesc, ClsBranchDesc, ConvDesc, ConvS8Desc, check
 
 _TORCH_DTYPE = {UYD_BF16: torch.bfloat16, UYD_F32: torch.float32, UYD_S8: torch.int8}
 
@@ -112,6 +112,21 @@ class Plan:
         bp = (C.c_void_p * 7)(*[b.ctypes.data_as(C.c_void_p) for b in bs])
         d = C3kDesc(src.buf, src.coff, dst.buf, dst.coff, src.c, 0)
         check(_lib.lib().uyd_plan_add_c3k(self.handle, C.byref(d), wp, bp), "uyd_plan_add_c3k")
+        return dst
+
+    @staticmethod
+    def cls_branch_supported(src: Slice, mid: int, nc: int) -> bool:
+        return src.c in (32, 64) and mid == 32 and nc <= 8 and src.w % 40 == 0 and src.h % 8 == 0 and src.coff % 8 == 0
+
+    def cls_branch(self, src: Slice, dst: Slice, mid: int, weights: list, biases: list) -> Slice:
+        """Fused Detect class branch: weights/biases = [dw1, pw1, dw2, pw2, pw3] (BN folded); dst = fp32 head slice."""
+        ws = [np.ascontiguousarray(w, dtype=np.float32) for w in weights]
+        bs = [np.ascontiguousarray(b, dtype=np.float32) for b in biases]
+        assert len(ws) == 5 and len(bs) == 5
+        wp = (C.c_void_p * 5)(*[w.ctypes.data_as(C.c_void_p) for w in ws])
+        bp = (C.c_void_p * 5)(*[b.ctypes.data_as(C.c_void_p) for b in bs])
+        d = ClsBranchDesc(src.buf, src.coff, dst.buf, dst.coff, src.c, mid, dst.c, 0)
+        check(_lib.lib().uyd_plan_add_cls_branch(self.handle, C.byref(d), wp, bp), "uyd_plan_add_cls_branch")
         return dst
 
     def sppf_pool(self, s: Slice, c: int) -> None:

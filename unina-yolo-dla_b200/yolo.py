@@ -194,10 +194,19 @@ class Detect(nn.Module):
             t = self.cv2[i][0].emit(p, f)
             t = self.cv2[i][1].emit(p, t)
             emit_plain_conv(p, self.cv2[i][2], t, head.sub(0, 4 * self.reg_max))
-            t = f
-            for blk in (self.cv3[i][0], self.cv3[i][1]):
-                t = blk[1].emit(p, blk[0].emit(p, t))
-            emit_plain_conv(p, self.cv3[i][2], t, head.sub(4 * self.reg_max, self.nc))
+            cls_dst = head.sub(4 * self.reg_max, self.nc)
+            b0, b1, last = self.cv3[i][0], self.cv3[i][1], self.cv3[i][2]
+            mid = b0[1].c2
+            if (os.environ.get("UYD_NO_CLS_FUSION", "0") != "1" and b0[0].g == f.c and b1[0].g == mid and b1[1].c2 == mid
+                    and p.cls_branch_supported(f, mid, self.nc) and p.shapes[f.buf][2] % 8 == 0):
+                folded = [fold_bn(m.conv, m.bn) for m in (b0[0], b0[1], b1[0], b1[1])]
+                folded.append((last.weight.detach().float().cpu().numpy(), last.bias.detach().float().cpu().numpy()))
+                p.cls_branch(f, cls_dst, mid, [w for w, _ in folded], [b for _, b in folded])
+            else:
+                t = f
+                for blk in (b0, b1):
+                    t = blk[1].emit(p, blk[0].emit(p, t))
+                emit_plain_conv(p, last, t, cls_dst)
             heads.append(head)
         return heads
 
