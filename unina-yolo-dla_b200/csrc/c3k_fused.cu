@@ -146,7 +146,7 @@ __device__ __forceinline__ void stage_conv3(const __nv_bfloat16 *src, __nv_bfloa
 
 // 1x1 conv over one or two channel sources: K = [srcA (CA ch, frame-indexed) | srcB (CB ch)].
 // srcB (if CB > 0) and dst may use a compact frame (pitch dpw, origin at region (r0, c0)).
-template <int CA, int CB, int COUT>
+template <int CA, int CB, int COUT, int NW = kWarps>
 __device__ __forceinline__ void stage_conv1(const __nv_bfloat16 *srcA, const __nv_bfloat16 *srcB, __nv_bfloat16 *dst,
                                             bool dst_compact, const uint32_t *wf, const float *bias, Region reg, int gy0,
                                             int gx0, int H, int W, int warp, int lane) {
@@ -164,7 +164,7 @@ __device__ __forceinline__ void stage_conv1(const __nv_bfloat16 *srcA, const __n
   const int cw = reg.c1 - reg.c0;  // compact pitch
   const int segs_per_row = (cw + 15) / 16;
   const int nseg = (reg.r1 - reg.r0) * segs_per_row;
-  for (int seg = warp; seg < nseg; seg += kWarps) {
+  for (int seg = warp; seg < nseg; seg += NW) {
     const int ry = reg.r0 + seg / segs_per_row;
     const int rx = reg.c0 + (seg % segs_per_row) * 16;
     float acc[NT][4];
@@ -298,15 +298,16 @@ __global__ void __launch_bounds__(kThreadsC3k) c3k_fused_kernel(C3kArgs a) {
 // mma.sync, the nc logits go straight to the fp32 head buffer.
 // =================================================================================================
 constexpr int kClsTH = 8;
+constexpr int kClsWarps = 16, kClsThreads = kClsWarps * 32;
 
 // depth-wise 3x3 + bias + ReLU over `reg`:  src[frame][C] -> dst[frame][C]; thread = (pixel, 8 channels)
-template <int C>
+template <int C, int NTHREADS>
 __device__ __forceinline__ void stage_dw(const __nv_bfloat16 *src, __nv_bfloat16 *dst, const __nv_bfloat16 *w,
                                          const float *bias, Region reg, int tid) {
   constexpr int CG = C / 8;
   const int rw = reg.c1 - reg.c0;
   const int total = (reg.r1 - reg.r0) * rw * CG;
-  for (int i = tid; i < total; i += kThreadsC3k) {
+  for (int i = tid; i < total; i += NTHREADS) {
     const int cg = i % CG, px = (i / CG) % rw + reg.c0, ry = i / (CG * rw) + reg.r0;
     float acc[8];
 #pragma unroll
@@ -332,7 +333,7 @@ __device__ __forceinline__ void stage_dw(const __nv_bfloat16 *src, __nv_bfloat16
 }
 
 template <int CIN>
-__global__ void __launch_bounds__(kThreadsC3k) cls_branch_fused_kernel(ClsArgs a) {
+__global__ void __launch_bounds__(kClsThreads) cls_branch_fused_kernel(ClsArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int MID = 32, CW = CIN > MID ? CIN : MID;
   constexpr int TH = kClsTH;
@@ -349,12 +350,13 @@ __global__ void __launch_bounds__(kThreadsC3k) cls_branch_fused_kernel(ClsArgs a
   const int ty0 = (tr / a.tiles_x) * TH, tx0 = (tr % a.tiles_x) * kTW;
   const int gy0 = ty0 - 2, gx0 = tx0 - 2;
   const int H = a.h, W = a.w;
-  for (int i = tid; i < 5 * 128; i += kThreadsC3k) sbias[i / 128][i % 128] = a.bias[i];
-  for (int i = tid; i < 9 * (CIN + MID); i += kThreadsC3k) swdw[i] = a.wdw[i];
+  for (int i = tid; i < 5 * 128; i += kClsThreads) sbias[i / 128][i % 128] = a.bias[i];
+  for (int i = tid; i < 9 * (CIN + MID); i += kClsThreads) swdw[i] = a.wdw[i];
   {  // x tile + halo (zero outside the image / in the slack columns and row)
     constexpr int CH16 = CIN / 8;
     const __nv_bfloat16 *img = a.in + (long long)n * H * W * a.in_pitch;
-    for (int i = tid; i < frame_px * CH16; i += kThreadsC3k) {
+#pragma unroll 4
+    for (int i = tid; i < frame_px * CH16; i += kClsThreads) {
       const int px = i / CH16, ch = i % CH16;
       const int ry = px / kPW, rx = px % kPW;
       const int gy = gy0 + ry, gx = gx0 + rx;
@@ -363,19 +365,18 @@ __global__ void __launch_bounds__(kThreadsC3k) cls_branch_fused_kernel(ClsArgs a
         v = *reinterpret_cast<const uint4 *>(img + ((long long)gy * W + gx) * a.in_pitch + ch * 8);
       *reinterpret_cast<uint4 *>(XZ + (size_t)px * CIN + ch * 8) = v;
     }
-    // y is read by partial mma segments beyond the region: keep the whole buffer finite
-    for (int i = tid; i < frame_px * CW / 8; i += kThreadsC3k) reinterpret_cast<uint4 *>(Y)[i] = make_uint4(0u, 0u, 0u, 0u);
+    // (Y is read beyond the region only by mma rows that are never stored: rows are independent, no init needed)
   }
   __syncthreads();
   const Region R1{1, TH + 3, 1, kTW + 3}, R0{2, TH + 2, 2, kTW + 2};
   constexpr int W1 = frag_words_1(CIN, MID), W2 = frag_words_1(MID, MID);
-  stage_dw<CIN>(XZ, Y, swdw, sbias[0], R1, tid);                                                           // y1
+  stage_dw<CIN, kClsThreads>(XZ, Y, swdw, sbias[0], R1, tid);                                                           // y1
   __syncthreads();
-  stage_conv1<CIN, 0, MID>(Y, nullptr, XZ, false, a.wfrag, sbias[1], R1, gy0, gx0, H, W, warp, lane);      // z1 (0 outside)
+  stage_conv1<CIN, 0, MID, kClsWarps>(Y, nullptr, XZ, false, a.wfrag, sbias[1], R1, gy0, gx0, H, W, warp, lane);      // z1 (0 outside)
   __syncthreads();
-  stage_dw<MID>(XZ, Y, swdw + 9 * CIN, sbias[2], R0, tid);                                                 // y2
+  stage_dw<MID, kClsThreads>(XZ, Y, swdw + 9 * CIN, sbias[2], R0, tid);                                                 // y2
   __syncthreads();
-  stage_conv1<MID, 0, MID>(Y, nullptr, XZ, false, a.wfrag + W1, sbias[3], R0, gy0, gx0, H, W, warp, lane); // z2
+  stage_conv1<MID, 0, MID, kClsWarps>(Y, nullptr, XZ, false, a.wfrag + W1, sbias[3], R0, gy0, gx0, H, W, warp, lane); // z2
   __syncthreads();
   {  // logits = pw3(z2) + bias  ->  fp32 head slice (N padded to 8, K = 32 = 2 k-steps)
     const uint32_t *wf = a.wfrag + W1 + W2;
@@ -388,7 +389,7 @@ __global__ void __launch_bounds__(kThreadsC3k) cls_branch_fused_kernel(ClsArgs a
     }
     float *img = a.out + (long long)n * H * W * a.out_pitch;
     const int nseg = TH * 3;
-    for (int seg = warp; seg < nseg; seg += kWarps) {
+    for (int seg = warp; seg < nseg; seg += kClsWarps) {
       const int ry = R0.r0 + seg / 3, rx = R0.c0 + (seg % 3) * 16;
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -521,10 +522,10 @@ int cls_branch_launch(int cin, const ClsArgs &a0, cudaStream_t s) {
   static bool attr[2] = {false, false};
   if (cin == 32) {
     if (!attr[0]) { UYD_CUDA(cudaFuncSetAttribute(cls_branch_fused_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr[0] = true; }
-    cls_branch_fused_kernel<32><<<grid, kThreadsC3k, smem, s>>>(a);
+    cls_branch_fused_kernel<32><<<grid, kClsThreads, smem, s>>>(a);
   } else {
     if (!attr[1]) { UYD_CUDA(cudaFuncSetAttribute(cls_branch_fused_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr[1] = true; }
-    cls_branch_fused_kernel<64><<<grid, kThreadsC3k, smem, s>>>(a);
+    cls_branch_fused_kernel<64><<<grid, kClsThreads, smem, s>>>(a);
   }
   return (int)cudaGetLastError();
 }
