@@ -92,27 +92,36 @@ __device__ __forceinline__ void stage_conv3(const __nv_bfloat16 *src, __nv_bfloa
     }
   // this thread's two k-columns inside a step: 2t (a0/a1) and 2t+8 (a2/a3)
   const int j0 = (2 * t) / C, ch0 = (2 * t) % C, j2 = (2 * t + 8) / C, ch2 = (2 * t + 8) % C;
+  // element offsets of this thread's two A columns relative to the segment's first pixel, per k-step
+  // (hoisted: the tap -> (row, col) arithmetic would otherwise run for every segment)
+  int off0[STEPS], off2[STEPS];
+#pragma unroll
+  for (int s = 0; s < STEPS; ++s) {
+    const int tap0 = s * TPK + j0, tap2 = s * TPK + j2;
+    off0[s] = tap0 < 9 ? ((tap0 / 3 - 1) * kPW + tap0 % 3 - 1) * C + ch0 : -(1 << 30);
+    off2[s] = tap2 < 9 ? ((tap2 / 3 - 1) * kPW + tap2 % 3 - 1) * C + ch2 : -(1 << 30);
+  }
   const int segs_per_row = (reg.c1 - reg.c0 + 15) / 16;
   const int nseg = (reg.r1 - reg.r0) * segs_per_row;
   for (int seg = warp; seg < nseg; seg += kWarps) {
     const int ry = reg.r0 + seg / segs_per_row;
     const int rx = reg.c0 + (seg % segs_per_row) * 16;
+    const __nv_bfloat16 *seg_base = src + (ry * kPW + rx + g) * C;
     float acc[NT][4];
 #pragma unroll
     for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
 #pragma unroll
     for (int s = 0; s < STEPS; ++s) {
       uint32_t a[4];
-      const int tap0 = s * TPK + j0, tap2 = s * TPK + j2;
-      if (tap0 < 9) {
-        const __nv_bfloat16 *p = src + ((ry + tap0 / 3 - 1) * kPW + rx + g + tap0 % 3 - 1) * C + ch0;
+      if (off0[s] > -(1 << 29)) {
+        const __nv_bfloat16 *p = seg_base + off0[s];
         a[0] = *reinterpret_cast<const uint32_t *>(p);
         a[1] = *reinterpret_cast<const uint32_t *>(p + 8 * C);
       } else {
         a[0] = a[1] = 0u;
       }
-      if (tap2 < 9) {
-        const __nv_bfloat16 *p = src + ((ry + tap2 / 3 - 1) * kPW + rx + g + tap2 % 3 - 1) * C + ch2;
+      if (off2[s] > -(1 << 29)) {
+        const __nv_bfloat16 *p = seg_base + off2[s];
         a[2] = *reinterpret_cast<const uint32_t *>(p);
         a[3] = *reinterpret_cast<const uint32_t *>(p + 8 * C);
       } else {
@@ -300,35 +309,64 @@ __global__ void __launch_bounds__(kThreadsC3k) c3k_fused_kernel(C3kArgs a) {
 constexpr int kClsTH = 8;
 constexpr int kClsWarps = 16, kClsThreads = kClsWarps * 32;
 
-// depth-wise 3x3 + bias + ReLU over `reg`:  src[frame][C] -> dst[frame][C]; thread = (pixel, 8 channels)
+// depth-wise 3x3 + bias + ReLU over `reg`:  src[frame][C] -> dst[frame][C]; thread = (2 adjacent pixels, 8 channels):
+// the 3 x 4 input window and the converted weights are shared by both outputs.
 template <int C, int NTHREADS>
 __device__ __forceinline__ void stage_dw(const __nv_bfloat16 *src, __nv_bfloat16 *dst, const __nv_bfloat16 *w,
                                          const float *bias, Region reg, int tid) {
   constexpr int CG = C / 8;
-  const int rw = reg.c1 - reg.c0;
-  const int total = (reg.r1 - reg.r0) * rw * CG;
+  const int rw = reg.c1 - reg.c0, rw2 = (rw + 1) / 2;
+  const int total = (reg.r1 - reg.r0) * rw2 * CG;
   for (int i = tid; i < total; i += NTHREADS) {
-    const int cg = i % CG, px = (i / CG) % rw + reg.c0, ry = i / (CG * rw) + reg.r0;
-    float acc[8];
+    const int cg = i % CG, px = ((i / CG) % rw2) * 2 + reg.c0, ry = i / (CG * rw2) + reg.r0;
+    float acc[2][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = bias[cg * 8 + j];
+    for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = bias[cg * 8 + j];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const uint4 xv = *reinterpret_cast<const uint4 *>(src + ((ry + t / 3 - 1) * kPW + px + t % 3 - 1) * C + cg * 8);
-      const uint4 wv = *reinterpret_cast<const uint4 *>(w + t * C + cg * 8);
-      const uint32_t *xp = reinterpret_cast<const uint32_t *>(&xv), *wp = reinterpret_cast<const uint32_t *>(&wv);
+    for (int ky = 0; ky < 3; ++ky) {
+      float wv[3][8];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 xf = unpack_bf16(xp[j]), wf2 = unpack_bf16(wp[j]);
-        acc[2 * j] = fmaf(xf.x, wf2.x, acc[2 * j]);
-        acc[2 * j + 1] = fmaf(xf.y, wf2.y, acc[2 * j + 1]);
+      for (int kx = 0; kx < 3; ++kx) {
+        const uint4 wr = *reinterpret_cast<const uint4 *>(w + (ky * 3 + kx) * C + cg * 8);
+        const uint32_t *wp = reinterpret_cast<const uint32_t *>(&wr);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16(wp[j]);
+          wv[kx][2 * j] = f.x;
+          wv[kx][2 * j + 1] = f.y;
+        }
+      }
+      const __nv_bfloat16 *row = src + ((ry + ky - 1) * kPW + px - 1) * C + cg * 8;
+#pragma unroll
+      for (int col = 0; col < 4; ++col) {
+        const uint4 xr = *reinterpret_cast<const uint4 *>(row + col * C);
+        const uint32_t *xp = reinterpret_cast<const uint32_t *>(&xr);
+        float xv[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16(xp[j]);
+          xv[2 * j] = f.x;
+          xv[2 * j + 1] = f.y;
+        }
+        if (col < 3) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[0][j] = fmaf(xv[j], wv[col][j], acc[0][j]);
+        }
+        if (col > 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[1][j] = fmaf(xv[j], wv[col - 1][j], acc[1][j]);
+        }
       }
     }
-    uint4 o;
-    uint32_t *op = reinterpret_cast<uint32_t *>(&o);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) op[j] = pack_bf16(fmaxf(acc[2 * j], 0.f), fmaxf(acc[2 * j + 1], 0.f));
-    *reinterpret_cast<uint4 *>(dst + (ry * kPW + px) * C + cg * 8) = o;
+    for (int q = 0; q < 2; ++q) {
+      if (px + q >= reg.c1) break;
+      uint4 o;
+      uint32_t *op = reinterpret_cast<uint32_t *>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) op[j] = pack_bf16(fmaxf(acc[q][2 * j], 0.f), fmaxf(acc[q][2 * j + 1], 0.f));
+      *reinterpret_cast<uint4 *>(dst + (ry * kPW + px + q) * C + cg * 8) = o;
+    }
   }
 }
 
