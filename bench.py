@@ -8,9 +8,12 @@ Workload (BASELINE.json configs[1]): unina-yolo-dla-m, bf16 forward + DFL decode
 640x640, batch 64 per GPU, seeded synthetic weights (UninaYoloB200.init_synthetic) and frames.
 A step = one pass of the hot path over one batch.
   value : images/s, frames already resident in HBM as NCHW fp32 (the reference forward signature)
-  e2e   : images/s through the public predict call with HOST frames: pinned uint8 NCHW frames
-          -> H2D -> forward(+/255 fused in the stem) -> decode -> NMS -> D2H of [B,300,6]+counts
-          (+ NCCL all_gather of the detections when N > 1: the batched-eval gather)
+  e2e   : images/s through the public streaming predict call with HOST frames: K pinned uint8
+          NCHW batches fed to UninaYoloB200.predict_stream -> per step H2D (on a copy stream,
+          overlapping the previous step's compute) -> forward(+/255 fused in the stem) -> decode
+          -> NMS -> D2H of [B,300,6]+counts (+ NCCL all_gather of the detections when N > 1: the
+          batched-eval gather).  e2e.single_call_ms is the same step as ONE blocking
+          predict_batched call (copy and compute serialised).
   roofline    : the dominant kernel, timed live with CUDA events inside the timed steps
   cpu_baseline: the oracle (restated reference path) on the host cores, bounded sample
 Multi-GPU: frames shard data-parallel, no collective on the forward path ("weak" scaling).
@@ -201,15 +204,30 @@ def main():
     def step_resident():
         return model.predict_batched(x_dev, CONF, IOU, MAX_DET)
 
-    def step_e2e():
+    def step_e2e():  # one blocking call: H2D, compute, D2H serialised
         x_u8.copy_(x_host, non_blocking=True)
         det, cnt = model.predict_batched(x_u8, CONF, IOU, MAX_DET)
         if world > 1:  # batched-eval gather of the detections (the only collective of the path)
             from unina_yolo_dla_b200.dp import gather_detections
 
-            gather_detections(det, cnt)
+            det, cnt = gather_detections(det, cnt)
+            det, cnt = det[rank * B:(rank + 1) * B], cnt[rank * B:(rank + 1) * B]
         det_host.copy_(det, non_blocking=True)
         cnt_host.copy_(cnt, non_blocking=True)
+
+    def run_stream(steps):  # the streaming API: H2D of step i+1 overlaps the compute of step i
+        if world == 1:
+            for det_h, cnt_h in model.predict_stream((x_host for _ in range(steps)), CONF, IOU, MAX_DET, to_host=True):
+                pass
+            det_host.copy_(det_h)
+            cnt_host.copy_(cnt_h)
+        else:
+            from unina_yolo_dla_b200.dp import gather_detections
+
+            for det, cnt in model.predict_stream((x_host for _ in range(steps)), CONF, IOU, MAX_DET, to_host=False):
+                gd, gc = gather_detections(det, cnt)
+                det_host.copy_(gd[rank * B:(rank + 1) * B], non_blocking=True)
+                cnt_host.copy_(gc[rank * B:(rank + 1) * B], non_blocking=True)
 
     warm = max(3, a.warmup)
     for _ in range(warm):
@@ -247,11 +265,14 @@ def main():
     plan.set_timed_op(-1, 0)
     for _ in range(2):
         step_e2e()
-    ms_e2e = timed(step_e2e, a.steps)
+    ms_e2e_single = timed(step_e2e, a.steps)
+    run_stream(2)
+    ms_e2e = timed(lambda: run_stream(a.steps), 1)
     n_det = int(cnt_host.sum().item())
 
     # stage split of one resident step and batch-1 latency (p50 over 50 synchronised calls)
     def span(fn, reps=5):
+        fn()  # warm-up: the first call may grow the caching allocator
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -306,7 +327,9 @@ def main():
                    "conv_gflop_per_image": conv_flops / 1e9},
         "e2e": {"value": world * B * a.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": x_host.numel(),
                 "d2h_bytes_per_step": det_host.numel() * 4 + cnt_host.numel() * 4, "ms_per_step": ms_e2e / a.steps,
-                "api": "UninaYoloB200.predict_batched(uint8 NCHW frames from pinned host memory)"},
+                "single_call_ms": ms_e2e_single / a.steps,
+                "api": "UninaYoloB200.predict_stream(pinned uint8 NCHW host batches): H2D of step i+1 overlaps step i; "
+                       "single_call_ms = one blocking predict_batched(host frames) per step"},
         "gpu_launches": kernels_per_step * a.steps,
         "roofline": {"kernel": top_text, "bound": "tensor" if tensor_bound else "hbm", "achieved": achieved, "peak": peak,
                      "unit": unit, "frac": achieved / peak, "traffic": traffic, "peak_source": pk["src"],

@@ -318,3 +318,38 @@ def test_fused_cls_branch_matches_torch(T, cin, H, W):
     want = F.conv2d(t, r(ws[4]), bs[4])
     assert T.rel_err(got, want) < 1e-2
     assert float(p.read(head.sub(0, 64), B).abs().max()) == 0.0
+
+
+def test_graph_replay_equals_direct_launch(T):
+    """Small batches replay a captured CUDA graph of the whole step: same bytes as the direct path."""
+    from oracle import init as oi
+
+    m, _ = _paired_models(seed=0)
+    x = oi.seeded_frames(2, 320, seed=8).cuda()
+    m.calibrate_cls_bias(x, 400, 0.25)
+    d0, c0 = m.predict_batched(x, graph=False)
+    for _ in range(3):                       # capture, then two replays with fresh input copies
+        d1, c1 = m.predict_batched(x, graph=True)
+    torch.cuda.synchronize()
+    assert int(c0.sum()) > 0 and torch.equal(c0, c1) and torch.equal(d0, d1)
+    x2 = oi.seeded_frames(2, 320, seed=9).cuda()
+    d2, c2 = m.predict_batched(x2, graph=True)
+    d3, c3 = m.predict_batched(x2, graph=False)
+    assert torch.equal(c2, c3) and torch.equal(d2, d3) and not torch.equal(d2, d0)
+
+
+def test_predict_stream_equals_predict_batched(T):
+    """The double-buffered streaming API returns, in order, what predict_batched returns per batch
+    (incl. a ragged last batch), as pinned host tensors."""
+    m, _ = _paired_models(seed=0)
+    g = torch.Generator().manual_seed(12)
+    batches = [(torch.rand(n, 3, 320, 320, generator=g) * 255).to(torch.uint8).pin_memory() for n in (12, 12, 12, 5)]
+    m.calibrate_cls_bias(batches[0].cuda(), 400, 0.25)
+    want = [tuple(t.cpu() for t in m.predict_batched(b.cuda())) for b in batches]
+    got = [(d.clone(), c.clone()) for d, c in m.predict_stream(iter(batches))]
+    assert len(got) == len(want)
+    for (d, c), (wd, wc) in zip(got, want):
+        assert int(wc.sum()) > 0 and torch.equal(c, wc) and torch.equal(d, wd)
+    dev = [(d.cpu(), c.cpu()) for d, c in m.predict_stream(iter(batches[:1]), to_host=False)]
+    assert torch.equal(dev[0][0], want[0][0]) and torch.equal(dev[0][1], want[0][1])
+    assert list(m.predict_stream(iter([]))) == []

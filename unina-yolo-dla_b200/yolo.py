@@ -281,6 +281,7 @@ class UninaYoloB200(nn.Module):
         det.bias_init()
         self._plans = {}
         self._nms_ws = {}
+        self._graphs = {}
         self.eval()
 
     @classmethod
@@ -306,6 +307,7 @@ class UninaYoloB200(nn.Module):
 
     def refresh(self) -> None:
         """Drop compiled plans (call after mutating parameters in place)."""
+        self._graphs.clear()
         self._plans.clear()
 
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
@@ -314,6 +316,7 @@ class UninaYoloB200(nn.Module):
         return out
 
     def _apply(self, fn, recurse=True):
+        self._graphs.clear()
         self._plans.clear()
         return super()._apply(fn, recurse)
 
@@ -451,6 +454,23 @@ class UninaYoloB200(nn.Module):
             xs.append(t)
         return y, xs
 
+    def _nms_workspace(self, dev: int, B: int, A: int, device) -> torch.Tensor:
+        need = int(_lib.lib().uyd_nms_workspace_bytes(B, A))
+        ws = self._nms_ws.get(dev)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(need, dtype=torch.uint8, device=device)
+            self._nms_ws[dev] = ws
+        return ws
+
+    def _nms_into(self, y, det, idx, cnt, ws, conf, iou, max_det, max_nms, max_wh) -> None:
+        """C call only (no allocation): safe inside CUDA-graph capture."""
+        B, no, A = y.shape
+        dev = y.device.index if y.device.index is not None else torch.cuda.current_device()
+        check(_lib.lib().uyd_nms(_lib.context(dev), C.c_void_p(y.data_ptr()), B, no - 4, A, conf, iou, max_nms, max_det,
+                                 max_wh, C.c_void_p(ws.data_ptr()), ws.numel(), C.c_void_p(det.data_ptr()),
+                                 C.c_void_p(idx.data_ptr()) if idx is not None else None, C.c_void_p(cnt.data_ptr()),
+                                 C.c_void_p(torch.cuda.current_stream().cuda_stream)), "uyd_nms")
+
     @torch.no_grad()
     def nms(self, y: torch.Tensor, conf: float = 0.25, iou: float = 0.7, max_det: int = 300, max_nms: int = 30000,
             max_wh: float = 7680.0, return_index: bool = False):
@@ -458,24 +478,65 @@ class UninaYoloB200(nn.Module):
         assert y.is_cuda and y.dtype == torch.float32 and y.is_contiguous()
         B, no, A = y.shape
         dev = y.device.index if y.device.index is not None else torch.cuda.current_device()
-        need = int(_lib.lib().uyd_nms_workspace_bytes(B, A))
-        ws = self._nms_ws.get(dev)
-        if ws is None or ws.numel() < need:
-            ws = torch.empty(need, dtype=torch.uint8, device=y.device)
-            self._nms_ws[dev] = ws
+        ws = self._nms_workspace(dev, B, A, y.device)
         det = torch.zeros(B, max_det, 6, dtype=torch.float32, device=y.device)
         idx = torch.full((B, max_det), -1, dtype=torch.int32, device=y.device)
         cnt = torch.zeros(B, dtype=torch.int32, device=y.device)
-        check(_lib.lib().uyd_nms(_lib.context(dev), C.c_void_p(y.data_ptr()), B, no - 4, A, conf, iou, max_nms, max_det,
-                                 max_wh, C.c_void_p(ws.data_ptr()), ws.numel(), C.c_void_p(det.data_ptr()),
-                                 C.c_void_p(idx.data_ptr()), C.c_void_p(cnt.data_ptr()),
-                                 C.c_void_p(torch.cuda.current_stream().cuda_stream)), "uyd_nms")
+        self._nms_into(y, det, idx, cnt, ws, conf, iou, max_det, max_nms, max_wh)
         return (det, cnt, idx) if return_index else (det, cnt)
+
+    # batches up to this size replay a captured CUDA graph (the ~70 launches of a step are
+    # launch-latency-bound below it); larger batches are launched directly.
+    GRAPH_MAX_BATCH = 8
+
+    def _graph_for(self, x: torch.Tensor, conf, iou, max_det, max_nms):
+        B, _, H, W = x.shape
+        dev = x.device.index if x.device.index is not None else torch.cuda.current_device()
+        key = (dev, B, H, W, x.dtype, float(conf), float(iou), int(max_det), int(max_nms))
+        g = self._graphs.get(key)
+        if g is not None:
+            return g
+        p = self.plan_for(x)
+        A = sum(h.h * h.w for h in p.heads)
+        xs = torch.empty_like(x)
+        y = torch.empty(B, 4 + self.nc, A, dtype=torch.float32, device=x.device)
+        det = torch.zeros(B, max_det, 6, dtype=torch.float32, device=x.device)
+        cnt = torch.zeros(B, dtype=torch.int32, device=x.device)
+        ws = torch.empty(int(_lib.lib().uyd_nms_workspace_bytes(B, A)), dtype=torch.uint8, device=x.device)
+
+        def body():
+            det.zero_()
+            p.run(xs)
+            p.decode(y, B)
+            self._nms_into(y, det, None, cnt, ws, conf, iou, max_det, max_nms, 7680.0)
+
+        xs.copy_(x)
+        side = torch.cuda.Stream(device=x.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # warm-up outside capture: one-time kernel attribute calls happen here
+            body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(x.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            body()
+        g = (graph, xs, det, cnt, (p, y, ws))  # the graph writes y / ws on every replay: keep them alive
+        self._graphs[key] = g
+        return g
 
     @torch.no_grad()
     def predict_batched(self, x: torch.Tensor, conf: float = 0.25, iou: float = 0.7, max_det: int = 300,
-                        max_nms: int = 30000):
-        """Forward + decode + NMS, everything left on the device: (det[B,max_det,6], count[B])."""
+                        max_nms: int = 30000, graph: bool | None = None):
+        """Forward + decode + NMS, everything left on the device: (det[B,max_det,6], count[B]).
+        ``graph`` (default: batch <= GRAPH_MAX_BATCH) replays the whole step as one CUDA graph."""
+        x = self._prep(x)
+        if graph is None:
+            graph = x.shape[0] <= self.GRAPH_MAX_BATCH and os.environ.get("UYD_NO_GRAPH", "0") != "1"
+        if graph:
+            g, xs, det, cnt, _ = self._graph_for(x, conf, iou, max_det, max_nms)
+            xs.copy_(x)
+            g.replay()
+            return det.clone(), cnt.clone()
         y = self.forward(x, raw_heads=False)
         return self.nms(y, conf, iou, max_det, max_nms)
 
@@ -485,3 +546,83 @@ class UninaYoloB200(nn.Module):
         det, cnt = self.predict_batched(x, conf, iou, max_det, max_nms)
         counts = cnt.tolist()
         return [det[b, :n] for b, n in enumerate(counts)]
+
+    @torch.no_grad()
+    def predict_stream(self, batches, conf: float = 0.25, iou: float = 0.7, max_det: int = 300, max_nms: int = 30000,
+                       to_host: bool = True):
+        """Generator form of ``predict`` (the reference consumes ``YOLO.predict(..., stream=True)``,
+        train.py:396-423): ``batches`` yields host frame batches ``[B,3,H,W]`` (uint8 or float, ideally
+        pinned).  Batch i+1 is copied host->device on a copy stream while batch i computes, so a
+        steady-state step costs max(copy, compute) instead of their sum.  Yields, in order,
+        ``(det[B,max_det,6], count[B])`` -- pinned host tensors (``to_host``) or device tensors;
+        either is valid until the generator is advanced twice more (two slots are recycled)."""
+        if not torch.cuda.is_available():
+            raise _lib.UydError("no CUDA device: the B200 path has no CPU fallback")
+        prm = next(self.parameters())
+        device = prm.device if prm.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        it = iter(batches)
+        try:
+            first = next(it)
+        except StopIteration:
+            return
+        Bmax = first.shape[0]
+        copy_s = torch.cuda.Stream(device=device)
+        main_s = torch.cuda.current_stream(device)
+
+        class Slot:
+            pass
+
+        slots = []
+        for _ in range(2):
+            s = Slot()
+            s.x = torch.empty(first.shape, dtype=first.dtype if first.dtype == torch.uint8 else torch.float32, device=device)
+            s.ready, s.free, s.out = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+            s.det = s.cnt = s.det_h = s.cnt_h = None
+            s.n = s.n_in = 0
+            slots.append(s)
+        if to_host:
+            for s in slots:
+                s.det_h = torch.empty(Bmax, max_det, 6, dtype=torch.float32).pin_memory()
+                s.cnt_h = torch.empty(Bmax, dtype=torch.int32).pin_memory()
+
+        def stage(s, xb):
+            if xb.shape[0] > Bmax or xb.shape[1:] != first.shape[1:]:
+                raise ValueError("predict_stream: later batches must not exceed the first batch's shape")
+            s.n_in = xb.shape[0]  # (s.n belongs to the result still pending in this slot)
+            with torch.cuda.stream(copy_s):
+                copy_s.wait_event(s.free)  # the step that last read this slot has finished
+                s.x[: s.n_in].copy_(xb, non_blocking=True)
+                s.ready.record(copy_s)
+
+        stage(slots[0], first)
+        i, pending = 0, None
+        while True:
+            s = slots[i % 2]
+            try:
+                nxt = next(it)
+            except StopIteration:
+                nxt = None
+            if nxt is not None:
+                stage(slots[(i + 1) % 2], nxt)
+            main_s.wait_event(s.ready)
+            s.n = s.n_in
+            s.det, s.cnt = self.predict_batched(s.x[: s.n], conf, iou, max_det, max_nms)
+            s.free.record(main_s)
+            if to_host:
+                s.det_h[: s.n].copy_(s.det, non_blocking=True)
+                s.cnt_h[: s.n].copy_(s.cnt, non_blocking=True)
+            s.out.record(main_s)
+            if pending is not None:
+                yield self._stream_result(pending, to_host)
+            pending = s
+            i += 1
+            if nxt is None:
+                break
+        yield self._stream_result(pending, to_host)
+
+    @staticmethod
+    def _stream_result(s, to_host):
+        if to_host:
+            s.out.synchronize()
+            return s.det_h[: s.n], s.cnt_h[: s.n]
+        return s.det, s.cnt
