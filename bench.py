@@ -197,7 +197,8 @@ def main():
     x_host = (torch.rand(B, 3, S, S, generator=torch.Generator().manual_seed(200 + rank)) * 255).to(torch.uint8).pin_memory()
     x_u8 = torch.empty_like(x_host, device=dev)
     model.calibrate_cls_bias(x_dev[: min(B, 8)], CANDIDATES_PER_IMAGE, CONF)
-    plan = model.plan_for(x_dev)
+    plan = model.plan_for(x_dev, fused=True)   # the plan predict runs: head kernels decode in their epilogue
+    y_prof = torch.empty(B, 4 + model.nc, model.num_anchors(S, S), device=dev)
     det_host = torch.empty(B, MAX_DET, 6).pin_memory()
     cnt_host = torch.empty(B, dtype=torch.int32).pin_memory()
 
@@ -234,7 +235,7 @@ def main():
         step_resident()
     torch.cuda.synchronize()
     # per-op profile (outside the timed region) -> dominant kernel
-    ms = plan.profile(x_dev)
+    ms = plan.profile(x_dev, y_prof)
     top = max(range(len(ms)), key=lambda i: ms[i])
     top_text, top_flops, top_bytes = plan.op_info(top)
     plan.set_timed_op(top, a.steps)
@@ -284,7 +285,7 @@ def main():
 
     y_keep = model.forward(x_dev, raw_heads=False)
     ms_fwd_decode = span(lambda: model.forward(x_dev, raw_heads=False))
-    ms_stack = span(lambda: plan.run(x_dev))
+    ms_stack = span(lambda: plan.run(x_dev, y_prof if plan.fused else None))
     ms_nms = span(lambda: model.nms(y_keep, CONF, IOU, MAX_DET))
     x1 = x_dev[:1].contiguous()
     for _ in range(5):
@@ -313,7 +314,8 @@ def main():
     tj = ROOT / "profiles" / "roofline_traffic.json"
     if tj.exists():
         traffic = json.loads(tj.read_text()).get(top_text)
-    kernels_per_step = plan.launches + len(plan.heads) + 5  # conv stack + DFL decode per level + 5 NMS kernels (cub sort excluded)
+    # conv stack (+ DFL decode per level when the plan does not decode in its head kernels) + 5 NMS kernels (cub sort excluded)
+    kernels_per_step = plan.launches + (0 if plan.fused else len(plan.heads)) + 5
     conv_flops = sum(plan.op_info(i)[1] for i in range(plan.launches))
     out = {
         "metric": METRIC, "value": world * B * a.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
@@ -337,9 +339,10 @@ def main():
                      "share_of_conv_stack": ms[top] / sum(ms)},
         "conv_stack": {"ms_per_step_profiled": sum(ms), "tflops": conv_flops * B / (sum(ms) * 1e-3) / 1e12,
                        "frac_of_tensor_peak": conv_flops * B / (sum(ms) * 1e-3) / 1e12 / pk["tflops"]},
-        "stages_ms": {"conv_stack": ms_stack, "dfl_decode": ms_fwd_decode - ms_stack, "nms": ms_nms},
+        "stages_ms": {"conv_stack": ms_stack, "dfl_decode": ms_fwd_decode - ms_stack, "nms": ms_nms,
+                      "note": "fused plan: the DFL decode runs inside the head kernels (conv_stack includes it)" if plan.fused else ""},
         "latency_bs1_ms": {"p50": lat[len(lat) // 2], "min": lat[0], "p90": lat[int(len(lat) * 0.9)], "calls": len(lat),
-                           "note": "predict_batched on one resident frame, host-synchronised wall clock"},
+                           "note": "predict_batched on one resident frame (CUDA-graph replay), host-synchronised wall clock"},
         "clocks": sampler.summary(),
     }
     if world == 1:

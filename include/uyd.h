@@ -119,6 +119,27 @@ typedef struct uyd_cls_branch {
 int uyd_plan_add_cls_branch(uyd_plan *plan, const uyd_cls_branch *desc, const float *const weights[5],
                             const float *const biases[5]);
 
+/* Chained head kernel (csrc/conv_chain.cu): 3x3 stride-1 Conv+BN+ReLU (cin -> n1; dw1 = 1: the
+ * depth-wise DWConv(cin,cin,3), cin == n1) followed in the same launch by a 1x1 conv (n1 -> n2) and a
+ * fused final stage, all on tcgen05 with the intermediate tile kept in shared memory:
+ *   UYD_CHAIN_STORE : bias2 (+ReLU when relu2) -> out slice (bf16 or fp32 buffer)
+ *   UYD_CHAIN_PW3   : ReLU -> Conv2d(n2, nc, 1) (w3, b3; Detect.cv3[l][2]) -> raw logits into the out slice
+ *                     (when out_buf >= 0) and sigmoid scores into y channels [y_ch0, y_ch0 + nc)
+ *   UYD_CHAIN_DFL   : n2 == 64 box logits -> raw fp32 into the out slice (when out_buf >= 0) and the DFL
+ *                     softmax-integral decode (cx, cy, w, h) * stride_px into y channels [y_ch0, y_ch0 + 4)
+ * y is the decoded output [batch, no, a_total] handed to uyd_plan_run_decoded; this op writes anchors
+ * [a_off, a_off + H*W).  cin, n1 in {32, 64}; n2 <= 64; nc <= 8.
+ * w1: [n1][cin][3][3] (dw1: [n1][1][3][3]), w2: [n2][n1], w3: [nc][n2]; BN folded, PyTorch layout. */
+enum { UYD_CHAIN_STORE = 0, UYD_CHAIN_PW3 = 2, UYD_CHAIN_DFL = 3 };
+typedef struct uyd_chain {
+  int in_buf, in_coff, cin, n1, n2, dw1, relu2, final_kind;
+  int out_buf, out_coff, nc;
+  int a_total, a_off, y_ch0, no;
+  float stride_px;
+} uyd_chain;
+int uyd_plan_add_chain(uyd_plan *plan, const uyd_chain *desc, const float *w1, const float *b1, const float *w2,
+                       const float *b2, const float *w3, const float *b3);
+
 /* SPPF cascade: reads slice [coff, coff+c) of buf and writes pool5, pool5^2, pool5^3 to
  * slices [coff+c, coff+2c), [coff+2c, ..), [coff+3c, ..) of the same buffer
  * (trainer.py:119-124; -inf padding). */
@@ -146,11 +167,19 @@ int uyd_plan_run(uyd_plan *plan, const float *x, int batch, uyd_stream stream);
  * reference predictor's pre-process (im.float() / 255) fused into the first conv. */
 int uyd_plan_run_u8(uyd_plan *plan, const uint8_t *x, int batch, uyd_stream stream);
 
+/* Same as uyd_plan_run / _run_u8 (x_dtype = UYD_F32 | UYD_U8) for plans whose head ops decode in their
+ * epilogue (uyd_plan_add_chain with PW3 / DFL finals): y [batch, no, a_total] fp32 receives the decoded
+ * prediction directly, no raw head tensor is materialised. */
+enum { UYD_U8 = 3 };
+int uyd_plan_run_decoded(uyd_plan *plan, const void *x, int x_dtype, int batch, float *y, uyd_stream stream);
+
 /* Measurement hooks (CUDA events on `stream`, no effect on results):
  *  - uyd_plan_profile: one pass with every op bracketed; ms[uyd_plan_num_launches]; syncs.
  *  - uyd_plan_set_timed_op / _read: bracket ONE op inside normal uyd_plan_run calls.
  *  - uyd_plan_op_info: description + algorithmic flops / compulsory bytes per image. */
 int uyd_plan_profile(uyd_plan *plan, const float *x, int batch, uyd_stream stream, float *ms);
+/* decoded-output buffer the profiling pass hands to head ops that decode in their epilogue */
+int uyd_plan_set_profile_output(uyd_plan *plan, float *y);
 int uyd_plan_set_timed_op(uyd_plan *plan, int op, int max_samples);
 int uyd_plan_timed_op_read(uyd_plan *plan, float *total_ms, int *samples);
 int uyd_plan_op_info(uyd_plan *plan, int op, char *text, size_t text_len, double *flops_per_image,

@@ -43,6 +43,17 @@ class FakePlan:
         self.ops.append(("cls", src, dst, [torch.from_numpy(w) for w in weights], [torch.from_numpy(b) for b in biases]))
         return dst
 
+    @staticmethod
+    def chain_supported(src, n1, n2):
+        return src.c in (32, 64) and n1 in (32, 64) and 1 <= n2 <= 64 and src.coff % 8 == 0
+
+    def chain(self, src, w1, b1, w2, b2, *, dw1=False, relu2=False, final=0, out=None, w3=None, b3=None, a_total=0, a_off=0,
+              y_ch0=0, no=0, stride=1.0):
+        t = lambda a: None if a is None else torch.as_tensor(a, dtype=torch.float32)
+        self.ops.append(("chain", src, out, t(w1), t(b1), t(w2), t(b2), dw1, relu2, final, t(w3), t(b3),
+                         (a_total, a_off, y_ch0, no, stride)))
+        return out
+
     def sppf_pool(self, s, c):
         self.ops.append(("sppf", s, c))
 
@@ -63,8 +74,34 @@ class FakePlan:
         def get(s):
             return x if s.buf < 0 else bufs[s.buf][:, s.coff:s.coff + s.c]
 
+        self.y = None
         for op in self.ops:
-            if op[0] == "conv":
+            if op[0] == "chain":
+                _, src, out, w1, b1, w2, b2, dw1, relu2, final, w3, b3, (a_total, a_off, y_ch0, no, stride) = op
+                xin = get(src)
+                t = F.conv2d(xin, w1, b1, padding=1, groups=xin.shape[1] if dw1 else 1).relu()
+                u = F.conv2d(t, w2.reshape(w2.shape[0], -1, 1, 1), b2)
+                hw = src.h * src.w
+                if self.y is None and a_total and final != 0 and out is None:
+                    self.y = torch.zeros(B, no, a_total)
+                if final == 0:  # STORE
+                    bufs[out.buf][:, out.coff:out.coff + out.c] = u.relu() if relu2 else u
+                elif final == 2:  # PW3
+                    lg = F.conv2d(u.relu(), w3.reshape(w3.shape[0], -1, 1, 1), b3)
+                    if out is not None:
+                        bufs[out.buf][:, out.coff:out.coff + out.c] = lg
+                    else:
+                        self.y[:, y_ch0:y_ch0 + lg.shape[1], a_off:a_off + hw] = lg.sigmoid().flatten(2)
+                else:  # DFL
+                    if out is not None:
+                        bufs[out.buf][:, out.coff:out.coff + out.c] = u
+                    else:
+                        d = (u.view(B, 4, 16, hw).softmax(2) * torch.arange(16.0).view(1, 1, 16, 1)).sum(2)  # l, t, r, b
+                        ax = (torch.arange(hw) % src.w).float() + 0.5
+                        ay = (torch.arange(hw) // src.w).float() + 0.5
+                        x1, y1, x2, y2 = ax - d[:, 0], ay - d[:, 1], ax + d[:, 2], ay + d[:, 3]
+                        self.y[:, y_ch0:y_ch0 + 4, a_off:a_off + hw] = torch.stack(((x1 + x2) / 2, (y1 + y2) / 2, x2 - x1, y2 - y1), 1) * stride
+            elif op[0] == "conv":
                 _, src, dst, w, b, k, stride, relu, dw, res = op
                 y = F.conv2d(get(src), w, b, stride=stride, padding=k // 2, groups=w.shape[0] if dw else 1)
                 if relu:

@@ -353,3 +353,115 @@ def test_predict_stream_equals_predict_batched(T):
     dev = [(d.cpu(), c.cpu()) for d, c in m.predict_stream(iter(batches[:1]), to_host=False)]
     assert torch.equal(dev[0][0], want[0][0]) and torch.equal(dev[0][1], want[0][1])
     assert list(m.predict_stream(iter([]))) == []
+
+
+CHAIN_CASES = [
+    # cin, n1, n2, dw1, final, H, W
+    (64, 64, 64, False, "store_f32", 32, 24),
+    (64, 64, 64, False, "dfl", 40, 40),
+    (64, 64, 64, False, "dfl", 160, 160),     # more tiles than SMs: persistent loop, both epilogue groups, stage wrap
+    (32, 32, 32, True, "store_bf16", 40, 40),
+    (64, 64, 32, True, "store_bf16", 24, 40),
+    (32, 32, 32, True, "pw3", 40, 40),
+    (32, 32, 32, True, "pw3", 160, 160),
+    (32, 64, 64, False, "store_bf16", 20, 20),
+    (64, 32, 32, False, "store_bf16", 20, 20),
+]
+
+
+@pytest.mark.parametrize("case", CHAIN_CASES, ids=lambda c: f"{c[0]}-{c[1]}-{c[2]}-{'dw' if c[3] else 'dense'}-{c[4]}-{c[5]}x{c[6]}")
+def test_chained_head_kernel_matches_torch(T, case):
+    """3x3 conv -> 1x1 conv -> final stage in one tcgen05 launch vs torch with bf16 rounding at the same points;
+    raw outputs and decoded outputs (DFL boxes, sigmoid scores) of the same launch configuration."""
+    import torch.nn.functional as F
+    import unina_yolo_dla_b200 as uyd
+    from unina_yolo_dla_b200._lib import CHAIN_DFL, CHAIN_PW3, CHAIN_STORE, UYD_BF16, UYD_F32
+
+    cin, n1, n2, dw1, final, H, W = case
+    g = torch.Generator().manual_seed(cin + n1 + H)
+    B, nc = 2, 4
+    r = T.bf16_round
+    x = torch.randn(B, cin, H, W, generator=g)
+    w1 = torch.randn(n1, 1 if dw1 else cin, 3, 3, generator=g) / (9 * (1 if dw1 else cin)) ** 0.5
+    w2 = torch.randn(n2, n1, generator=g) / n1 ** 0.5
+    w3 = torch.randn(nc, n2, generator=g) / n2 ** 0.5
+    b1, b2, b3 = (torch.randn(n, generator=g) * 0.1 for n in (n1, n2, nc))
+    if final == "dfl":
+        w2, b2 = w2 * 3, b2 + 1.0
+    t = r(F.conv2d(r(x), r(w1), b1, padding=1, groups=cin if dw1 else 1).relu())
+    u = F.conv2d(t, r(w2).view(n2, n1, 1, 1), b2)
+
+    def run(decoded):
+        p = uyd.Plan(0, B)
+        src = p.buffer(H, W, cin + 8).sub(8, cin)          # the input lives in a channel slice
+        A, a_off = H * W + 7, 3
+        geo = dict(a_total=A, a_off=a_off, no=4 + nc, stride=8.0)
+        out = None
+        if final == "store_f32":
+            out = p.buffer(H, W, 68, UYD_F32).sub(0, n2)
+            p.chain(src, w1.numpy(), b1.numpy(), w2.numpy(), b2.numpy(), dw1=dw1, final=CHAIN_STORE, out=out)
+        elif final == "store_bf16":
+            out = p.buffer(H, W, n2 + 16).sub(16, n2)
+            p.chain(src, w1.numpy(), b1.numpy(), w2.numpy(), b2.numpy(), dw1=dw1, relu2=True, final=CHAIN_STORE, out=out)
+        elif final == "dfl":
+            out = None if decoded else p.buffer(H, W, 68, UYD_F32).sub(0, 64)
+            p.chain(src, w1.numpy(), b1.numpy(), w2.numpy(), b2.numpy(), dw1=dw1, final=CHAIN_DFL, out=out, y_ch0=0, **geo)
+        else:
+            out = None if decoded else p.buffer(H, W, 68, UYD_F32).sub(64, nc)
+            p.chain(src, w1.numpy(), b1.numpy(), w2.numpy(), b2.numpy(), dw1=dw1, relu2=True, final=CHAIN_PW3, w3=w3.numpy(),
+                    b3=b3.numpy(), out=out, y_ch0=4, **geo)
+        p.finalize()
+        p.write(src, x)
+        y = torch.full((B, 4 + nc, A), -7.0, device="cuda")
+        if decoded:
+            p.run_no_input(B, y)
+        else:
+            p.run_no_input(B)
+        torch.cuda.synchronize()
+        return (p.read(out, B).cpu() if out is not None else None), y.cpu(), a_off
+
+    if final == "store_f32":
+        got, _, _ = run(False)
+        assert T.rel_err(got, u) < 6e-3
+    elif final == "store_bf16":
+        got, _, _ = run(False)
+        assert T.rel_err(got, r(u.relu())) < 1e-2
+    elif final == "dfl":
+        raw, _, _ = run(False)
+        assert T.rel_err(raw, u) < 6e-3
+        _, y, a_off = run(True)
+        d = (raw.view(B, 4, 16, H * W).softmax(2) * torch.arange(16.0).view(1, 1, 16, 1)).sum(2)
+        ax = (torch.arange(H * W) % W).float() + 0.5
+        ay = (torch.arange(H * W) // W).float() + 0.5
+        x1, y1, x2, y2 = ax - d[:, 0], ay - d[:, 1], ax + d[:, 2], ay + d[:, 3]
+        want = torch.stack(((x1 + x2) / 2, (y1 + y2) / 2, x2 - x1, y2 - y1), 1) * 8.0
+        assert float((y[:, :4, a_off:a_off + H * W] - want).abs().max()) < 2e-3      # same logits: only exp differs
+        assert float((y[:, 4:] + 7.0).abs().max()) == 0.0 and float((y[:, :, :a_off] + 7.0).abs().max()) == 0.0
+        assert float((y[:, :, a_off + H * W:] + 7.0).abs().max()) == 0.0            # nothing outside its anchors / channels
+    else:
+        z = r(u.relu())
+        lg = F.conv2d(z, r(w3).view(nc, n2, 1, 1), b3)
+        raw, _, _ = run(False)
+        assert T.rel_err(raw, lg) < 1e-2
+        _, y, a_off = run(True)
+        assert float((y[:, 4:, a_off:a_off + H * W] - raw.sigmoid().flatten(2)).abs().max()) < 1e-5
+        assert float((y[:, :4] + 7.0).abs().max()) == 0.0
+
+
+def test_fused_decode_plan_equals_raw_head_plan(T):
+    """forward(raw_heads=False) runs the plan whose head kernels decode in their epilogue; it must
+    reproduce the decode of the raw-head plan (same logits, same arithmetic)."""
+    from oracle import init as oi
+
+    m, ref = _paired_models(seed=0)
+    x = oi.seeded_frames(2, 640, seed=5)
+    y_raw, _ = m(x.cuda())
+    y_fused = m(x.cuda(), raw_heads=False)
+    torch.cuda.synchronize()
+    assert m.plan_for(x.cuda(), fused=True).fused
+    assert float((y_raw[:, :4] - y_fused[:, :4]).abs().max()) < 2e-3
+    assert float((y_raw[:, 4:] - y_fused[:, 4:]).abs().max()) < 1e-5
+    with torch.no_grad():
+        y_ref, _ = ref(x)
+    assert T.rel_err(y_fused.cpu()[:, :4], y_ref[:, :4]) <= 1e-2
+    assert float((y_fused.cpu()[:, 4:] - y_ref[:, 4:]).abs().max()) <= 1e-2

@@ -15,11 +15,11 @@ from oracle import yolo_graph as yg
 ROOT = Path(__file__).resolve().parents[1]
 
 
-def _emit_fake(model, B, H, W, monkeypatch):
+def _emit_fake(model, B, H, W, monkeypatch, fused=False):
     import unina_yolo_dla_b200.yolo as ymod
 
     monkeypatch.setattr(ymod, "Plan", FakePlan)
-    return model._build_plan(0, B, H, W)
+    return model._build_plan(0, B, H, W, fused)
 
 
 def test_emitted_plan_equals_oracle_network(monkeypatch):
@@ -39,9 +39,36 @@ def test_emitted_plan_equals_oracle_network(monkeypatch):
         assert torch.allclose(got, feats[i], rtol=1e-4, atol=1e-4), f"layer {i} differs"
     for h, r in zip(p.heads, raw_ref):
         assert torch.allclose(bufs[h.buf], r, rtol=1e-4, atol=1e-4)
-    # census: 158 convs + 1 pool cascade + 2 upsamples, no concat / chunk op at all
+    # census: 158 convs (19 of them inside the 8 chained head launches) + 1 pool cascade + 2 upsamples,
+    # no concat / chunk op at all
     kinds = [o[0] for o in p.ops]
-    assert kinds.count("conv") == 158 and kinds.count("sppf") == 1 and kinds.count("up") == 2
+    assert kinds.count("chain") == 8 and kinds.count("conv") == 158 - 19 and kinds.count("sppf") == 1 and kinds.count("up") == 2
+
+
+def test_unchained_plan_is_the_plain_conv_list(monkeypatch):
+    monkeypatch.setenv("UYD_NO_CHAIN", "1")
+    m = uyd.UninaYoloB200.from_yaml().init_synthetic(seed=3)
+    p = _emit_fake(m, 1, 128, 128, monkeypatch)
+    kinds = [o[0] for o in p.ops]
+    assert kinds.count("conv") == 158 and kinds.count("chain") == 0
+
+
+def test_fused_decode_plan_writes_the_oracle_prediction(monkeypatch):
+    """The plan variant whose head kernels decode in their epilogue has no head buffers and its
+    emitted ops compute the oracle's y[B, 4+nc, A] (DFL decode + sigmoid)."""
+    m = uyd.UninaYoloB200.from_yaml().init_synthetic(seed=5)
+    ref = yg.DetectionModel(yg.default_yaml_path())
+    ref.load_state_dict(m.state_dict(), strict=True)
+    ref.eval()
+    x = oi.seeded_frames(2, 128, seed=7)
+    with torch.no_grad():
+        y_ref, _ = ref(x)
+    p = _emit_fake(m, 2, 128, 128, monkeypatch, fused=True)
+    assert p.fused and all(h.buf < 0 for h in p.heads)
+    p.execute(x)
+    assert p.y.shape == y_ref.shape
+    assert torch.allclose(p.y[:, :4], y_ref[:, :4], rtol=1e-4, atol=1e-3)
+    assert torch.allclose(p.y[:, 4:], y_ref[:, 4:], rtol=1e-4, atol=1e-5)
 
 
 def test_state_dict_schema_matches_oracle_and_roundtrips():
@@ -100,8 +127,8 @@ def test_emitted_plan_uses_fused_c3k_at_full_resolution(monkeypatch):
         y_ref, raw_ref = ref(x)
     p = _emit_fake(m, 1, 640, 640, monkeypatch)
     kinds = [o[0] for o in p.ops]
-    # 16 fused C3k blocks (7 convs each) and the class branches of the P2/P3 levels (5 convs each)
-    assert kinds.count("c3k") == 16 and kinds.count("cls") == 2 and kinds.count("conv") == 158 - 16 * 7 - 2 * 5
+    # 16 fused C3k blocks (7 convs each) and 8 chained head launches (19 convs)
+    assert kinds.count("c3k") == 16 and kinds.count("chain") == 8 and kinds.count("conv") == 158 - 16 * 7 - 19
     bufs = p.execute(x)
     for h, r in zip(p.heads, raw_ref):
         assert torch.allclose(bufs[h.buf], r, rtol=1e-4, atol=1e-4)

@@ -8,7 +8,8 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 LIB_PATH = HERE / "libuyd.so"
 
-UYD_BF16, UYD_F32, UYD_S8 = 0, 1, 2
+UYD_BF16, UYD_F32, UYD_S8, UYD_U8 = 0, 1, 2, 3
+CHAIN_STORE, CHAIN_PW3, CHAIN_DFL = 0, 2, 3
 IMPL_AUTO, IMPL_DIRECT, IMPL_TC = 0, 1, 2
 
 
@@ -36,6 +37,11 @@ class ClsBranchDesc(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("in_buf", "in_coff", "out_buf", "out_coff", "cin", "mid", "nc", "reserved")]
 
 
+class ChainDesc(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("in_buf", "in_coff", "cin", "n1", "n2", "dw1", "relu2", "final_kind", "out_buf",
+                                       "out_coff", "nc", "a_total", "a_off", "y_ch0", "no")] + [("stride_px", C.c_float)]
+
+
 class Detection(C.Structure):
     """Layout-identical to the reference GpuDetection (gpu_postprocess.h:27-33)."""
     _fields_ = [("x1", C.c_float), ("y1", C.c_float), ("x2", C.c_float), ("y2", C.c_float),
@@ -56,6 +62,10 @@ SIGNATURES = {
     "uyd_plan_add_conv_s8": (C.c_int, [C.c_void_p, C.POINTER(ConvS8Desc), C.c_void_p, C.c_void_p, C.c_void_p]),
     "uyd_plan_add_c3k": (C.c_int, [C.c_void_p, C.POINTER(C3kDesc), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "uyd_plan_add_cls_branch": (C.c_int, [C.c_void_p, C.POINTER(ClsBranchDesc), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "uyd_plan_add_chain": (C.c_int, [C.c_void_p, C.POINTER(ChainDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]),
+    "uyd_plan_run_decoded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "uyd_plan_set_profile_output": (C.c_int, [C.c_void_p, C.c_void_p]),
     "uyd_plan_add_sppf_pool": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "uyd_plan_add_upsample2x": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "uyd_plan_set_heads": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int]),

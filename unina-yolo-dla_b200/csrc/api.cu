@@ -58,6 +58,21 @@ void cls_branch_pack(int cin, int nc, const float *const w[5], const float *cons
                      std::vector<uint32_t> &frags, std::vector<float> &bias);
 int cls_branch_launch(int cin, const ClsArgs &a, cudaStream_t s);
 
+// conv_chain.cu
+struct ChainConv;
+ChainConv *chain_new();
+void chain_delete(ChainConv *);
+bool chain_supported(int cin, int n1, int n2, int in_pitch, int in_coff);
+size_t chain_w1_bytes(int cin, int n1);
+size_t chain_w2_bytes(int n1, int n2);
+void chain_pack_w1(int cin, int n1, bool depthwise, const float *w, void *dst_host);
+void chain_pack_w2(int n1, int n2, const float *w, void *dst_host);
+int chain_prepare(ChainConv *cc, int cin, int n1, int n2, void *in_base, int in_pitch, int h, int w, int max_batch,
+                  void *w1_dev, void *w2_dev, const float *bias1, const float *bias2, int relu2, int final_kind, int nc,
+                  const float *w3_dev, const float *bias3_dev, void *out_base, int out_pitch, int out_f32, int a_total,
+                  int a_off, int y_ch0, int no, float stride_px);
+int chain_launch(const ChainConv *cc, int nb, float *y, int sm_count, cudaStream_t s);
+
 static int env_int(const char *name, int dflt) {
   const char *v = getenv(name);
   return v && *v ? atoi(v) : dflt;
@@ -72,7 +87,7 @@ struct uyd_ctx {
   int sm_count = 0;
 };
 
-enum OpKind { OP_CONV = 0, OP_SPPF = 1, OP_UPSAMPLE = 2, OP_CONV_S8 = 3, OP_C3K = 4, OP_CLS = 5 };
+enum OpKind { OP_CONV = 0, OP_SPPF = 1, OP_UPSAMPLE = 2, OP_CONV_S8 = 3, OP_C3K = 4, OP_CLS = 5, OP_CHAIN = 6 };
 
 struct Op {
   OpKind kind;
@@ -91,6 +106,11 @@ struct Op {
   std::vector<unsigned char> w2_host;  // cls branch: depth-wise weights
   void *w2_dev = nullptr;
   int nc = 0;
+  // chained head kernel
+  uyd_chain chain{};
+  ChainConv *cc = nullptr;
+  std::vector<float> b2_host, w3_host, b3_host;
+  float *b2_dev = nullptr, *w3_dev = nullptr, *b3_dev = nullptr;
   // sppf / upsample
   int buf = -1, coff = 0, c = 0, out_buf = -1, out_coff = 0;
 };
@@ -106,6 +126,7 @@ struct uyd_plan {
   int in_c = 0, in_h = 0, in_w = 0;  // network input extent (derived from the first conv)
   size_t bytes = 0;
   void *arena = nullptr;
+  float *profile_y = nullptr;          // decoded output used by uyd_plan_profile (uyd_plan_set_profile_output)
   int timed_op = -1, timed_used = 0;  // uyd_plan_set_timed_op
   std::vector<cudaEvent_t> timed_ev;
 };
@@ -156,6 +177,10 @@ extern "C" int uyd_plan_destroy(uyd_plan *plan) {
     if (o.m_dev) cudaFree(o.m_dev);
     if (o.w2_dev) cudaFree(o.w2_dev);
     if (o.tc) tc_delete(o.tc);
+    if (o.cc) chain_delete(o.cc);
+    if (o.b2_dev) cudaFree(o.b2_dev);
+    if (o.w3_dev) cudaFree(o.w3_dev);
+    if (o.b3_dev) cudaFree(o.b3_dev);
   }
   if (plan->arena) cudaFree(plan->arena);
   for (cudaEvent_t e : plan->timed_ev) cudaEventDestroy(e);
@@ -331,6 +356,56 @@ extern "C" int uyd_plan_add_cls_branch(uyd_plan *plan, const uyd_cls_branch *d, 
   return UYD_OK;
 }
 
+extern "C" int uyd_plan_add_chain(uyd_plan *plan, const uyd_chain *d, const float *w1, const float *b1, const float *w2,
+                                  const float *b2, const float *w3, const float *b3) {
+  UYD_REQUIRE(plan && d && w1 && b1 && w2 && b2, UYD_E_ARG, "uyd_plan_add_chain: NULL argument");
+  UYD_REQUIRE(!plan->finalized, UYD_E_STATE, "plan already finalized");
+  int e;
+  if ((e = check_slice(plan, d->in_buf, d->in_coff, d->cin, "chain input"))) return e;
+  const Buffer &ib = plan->bufs[d->in_buf];
+  UYD_REQUIRE(ib.dtype == UYD_BF16, UYD_E_ARG, "chain input must be bf16");
+  UYD_REQUIRE(chain_supported(d->cin, d->n1, d->n2, ib.c, d->in_coff), UYD_E_UNSUPPORTED,
+              "chain %d -> %d -> %d unsupported (cin, n1 in {32, 64}; n2 <= 64; 16-byte aligned input slice)", d->cin, d->n1, d->n2);
+  UYD_REQUIRE(!d->dw1 || d->cin == d->n1, UYD_E_ARG, "chain: a depth-wise first conv needs cin == n1");
+  UYD_REQUIRE(d->final_kind == UYD_CHAIN_STORE || d->final_kind == UYD_CHAIN_PW3 || d->final_kind == UYD_CHAIN_DFL, UYD_E_ARG,
+              "chain: unknown final stage %d", d->final_kind);
+  if (d->out_buf >= 0) {
+    const int oc = d->final_kind == UYD_CHAIN_PW3 ? d->nc : d->n2;
+    if ((e = check_slice(plan, d->out_buf, d->out_coff, oc, "chain output"))) return e;
+    const Buffer &ob = plan->bufs[d->out_buf];
+    UYD_REQUIRE(ob.h == ib.h && ob.w == ib.w, UYD_E_ARG, "chain output extent differs from the input");
+    if (d->final_kind == UYD_CHAIN_STORE)
+      UYD_REQUIRE(d->n2 % 16 == 0 && (ob.c * ob.elem_bytes()) % 16 == 0 && (d->out_coff * ob.elem_bytes()) % 16 == 0 &&
+                      (ob.dtype == UYD_BF16 || ob.dtype == UYD_F32), UYD_E_UNSUPPORTED, "chain STORE needs n2 %% 16 == 0 and 16-byte rows");
+    else
+      UYD_REQUIRE(ob.dtype == UYD_F32 && (d->final_kind == UYD_CHAIN_PW3 || ((ob.c % 4) == 0 && (d->out_coff % 4) == 0)),
+                  UYD_E_UNSUPPORTED, "chain PW3 / DFL raw output goes to an fp32 head buffer");
+  } else {
+    UYD_REQUIRE(d->final_kind != UYD_CHAIN_STORE, UYD_E_ARG, "chain STORE needs an output slice");
+  }
+  if (d->final_kind == UYD_CHAIN_PW3) UYD_REQUIRE(w3 && b3 && d->nc >= 1 && d->nc <= 8 && d->n2 <= 64, UYD_E_ARG, "chain PW3: w3/b3, nc <= 8");
+  if (d->final_kind == UYD_CHAIN_DFL) UYD_REQUIRE(d->n2 == 64, UYD_E_ARG, "chain DFL: n2 must be 4 x 16");
+  Op op;
+  op.kind = OP_CHAIN;
+  op.chain = *d;
+  op.w_host.resize(chain_w1_bytes(d->cin, d->n1));
+  chain_pack_w1(d->cin, d->n1, d->dw1 != 0, w1, op.w_host.data());
+  op.w2_host.resize(chain_w2_bytes(d->n1, d->n2));
+  chain_pack_w2(d->n1, d->n2, w2, op.w2_host.data());
+  const int N2 = (d->n2 + 15) / 16 * 16;
+  op.b_host.assign(b1, b1 + d->n1);
+  op.b2_host.assign(N2, 0.f);
+  for (int i = 0; i < d->n2; ++i) op.b2_host[i] = b2[i];
+  if (d->final_kind == UYD_CHAIN_PW3) {
+    op.w3_host.assign((size_t)d->nc * N2, 0.f);
+    for (int c = 0; c < d->nc; ++c)
+      for (int k = 0; k < d->n2; ++k) op.w3_host[(size_t)c * N2 + k] = __bfloat162float(__float2bfloat16_rn(w3[(size_t)c * d->n2 + k]));
+    op.b3_host.assign(b3, b3 + d->nc);
+  }
+  plan->ops.push_back(std::move(op));
+  return UYD_OK;
+}
+
 extern "C" int uyd_plan_add_sppf_pool(uyd_plan *plan, int buf, int coff, int c) {
   UYD_REQUIRE(plan && !plan->finalized, UYD_E_STATE, "plan missing or finalized");
   int e;
@@ -399,7 +474,7 @@ extern "C" int uyd_plan_finalize(uyd_plan *plan) {
   const int stages = env_int("UYD_TC_STAGES", 0);
   const int halo_pitch = env_int("UYD_TC_HALO_PITCH", 10);
   for (Op &o : plan->ops) {
-    if (o.kind != OP_CONV && o.kind != OP_CONV_S8 && o.kind != OP_C3K && o.kind != OP_CLS) continue;
+    if (o.kind != OP_CONV && o.kind != OP_CONV_S8 && o.kind != OP_C3K && o.kind != OP_CLS && o.kind != OP_CHAIN) continue;
     UYD_CUDA(cudaMalloc(&o.w_dev, o.w_host.size()));
     UYD_CUDA(cudaMemcpy(o.w_dev, o.w_host.data(), o.w_host.size(), cudaMemcpyHostToDevice));
     UYD_CUDA(cudaMalloc((void **)&o.b_dev, o.b_host.size() * 4));
@@ -410,6 +485,33 @@ extern "C" int uyd_plan_finalize(uyd_plan *plan) {
     if (o.kind == OP_CLS) {
       UYD_CUDA(cudaMalloc(&o.w2_dev, o.w2_host.size()));
       UYD_CUDA(cudaMemcpy(o.w2_dev, o.w2_host.data(), o.w2_host.size(), cudaMemcpyHostToDevice));
+      continue;
+    }
+    if (o.kind == OP_CHAIN) {
+      const uyd_chain &d = o.chain;
+      UYD_CUDA(cudaMalloc(&o.w2_dev, o.w2_host.size()));
+      UYD_CUDA(cudaMemcpy(o.w2_dev, o.w2_host.data(), o.w2_host.size(), cudaMemcpyHostToDevice));
+      UYD_CUDA(cudaMalloc((void **)&o.b2_dev, o.b2_host.size() * 4));
+      UYD_CUDA(cudaMemcpy(o.b2_dev, o.b2_host.data(), o.b2_host.size() * 4, cudaMemcpyHostToDevice));
+      if (!o.w3_host.empty()) {
+        UYD_CUDA(cudaMalloc((void **)&o.w3_dev, o.w3_host.size() * 4));
+        UYD_CUDA(cudaMemcpy(o.w3_dev, o.w3_host.data(), o.w3_host.size() * 4, cudaMemcpyHostToDevice));
+        UYD_CUDA(cudaMalloc((void **)&o.b3_dev, o.b3_host.size() * 4));
+        UYD_CUDA(cudaMemcpy(o.b3_dev, o.b3_host.data(), o.b3_host.size() * 4, cudaMemcpyHostToDevice));
+      }
+      const Buffer &ib = plan->bufs[d.in_buf];
+      void *out = nullptr;
+      int out_pitch = 0, out_f32 = 0;
+      if (d.out_buf >= 0) {
+        out = slice_ptr(plan, d.out_buf, d.out_coff);
+        out_pitch = plan->bufs[d.out_buf].c;
+        out_f32 = plan->bufs[d.out_buf].dtype == UYD_F32;
+      }
+      o.cc = chain_new();
+      int e = chain_prepare(o.cc, d.cin, d.n1, d.n2, slice_ptr(plan, d.in_buf, d.in_coff), ib.c, ib.h, ib.w, plan->max_batch, o.w_dev,
+                            o.w2_dev, o.b_dev, o.b2_dev, d.relu2, d.final_kind, d.nc, o.w3_dev, o.b3_dev, out, out_pitch, out_f32,
+                            d.a_total, d.a_off, d.y_ch0, d.no, d.stride_px);
+      if (e) return e;
       continue;
     }
     if (o.kind == OP_C3K) continue;
@@ -454,7 +556,7 @@ extern "C" int uyd_plan_buffer_ptr(uyd_plan *plan, int id, void **ptr) {
 }
 
 // x_kind: 1 = NCHW fp32 frames, 2 = NCHW uint8 frames (divided by 255 on load)
-static int launch_op(uyd_plan *plan, const Op &o, const void *x, int x_kind, int batch, cudaStream_t s) {
+static int launch_op(uyd_plan *plan, const Op &o, const void *x, int x_kind, int batch, cudaStream_t s, float *y = nullptr) {
   {
     int e = UYD_OK;
     if (o.kind == OP_CONV) {
@@ -486,6 +588,9 @@ static int launch_op(uyd_plan *plan, const Op &o, const void *x, int x_kind, int
       a.wfrag = (const uint32_t *)o.w_dev; a.bias = o.b_dev;
       a.n = batch; a.h = ib.h; a.w = ib.w; a.in_pitch = ib.c; a.out_pitch = ob.c;
       e = c3k_launch(o.c, a, s);
+    } else if (o.kind == OP_CHAIN) {
+      UYD_REQUIRE(y || o.chain.out_buf >= 0, UYD_E_ARG, "this plan decodes in its head kernels: run it with uyd_plan_run_decoded");
+      e = chain_launch(o.cc, batch, y, plan->ctx->sm_count, s);
     } else if (o.kind == OP_CLS) {
       const Buffer &ib = plan->bufs[o.buf], &ob = plan->bufs[o.out_buf];
       ClsArgs a{};
@@ -518,14 +623,14 @@ static int launch_op(uyd_plan *plan, const Op &o, const void *x, int x_kind, int
   }
 }
 
-static int run_ops(uyd_plan *plan, const void *x, int x_kind, int batch, uyd_stream stream) {
+static int run_ops(uyd_plan *plan, const void *x, int x_kind, int batch, uyd_stream stream, float *y = nullptr) {
   UYD_REQUIRE(plan && plan->finalized, UYD_E_STATE, "plan not finalized");
   UYD_REQUIRE(batch > 0 && batch <= plan->max_batch, UYD_E_ARG, "batch %d outside (0, %d]", batch, plan->max_batch);
   cudaStream_t s = (cudaStream_t)stream;
   for (size_t i = 0; i < plan->ops.size(); ++i) {
     const bool timed = (int)i == plan->timed_op && plan->timed_used < (int)plan->timed_ev.size() / 2;
     if (timed) UYD_CUDA(cudaEventRecord(plan->timed_ev[2 * plan->timed_used], s));
-    int e = launch_op(plan, plan->ops[i], x, x_kind, batch, s);
+    int e = launch_op(plan, plan->ops[i], x, x_kind, batch, s, y);
     if (e) return e;
     if (timed) UYD_CUDA(cudaEventRecord(plan->timed_ev[2 * plan->timed_used++ + 1], s));
   }
@@ -540,6 +645,12 @@ extern "C" int uyd_plan_run_u8(uyd_plan *plan, const uint8_t *x, int batch, uyd_
   return run_ops(plan, x, 2, batch, stream);
 }
 
+extern "C" int uyd_plan_run_decoded(uyd_plan *plan, const void *x, int x_dtype, int batch, float *y, uyd_stream stream) {
+  UYD_REQUIRE(x_dtype == UYD_F32 || x_dtype == UYD_U8, UYD_E_ARG, "uyd_plan_run_decoded: x_dtype must be UYD_F32 or UYD_U8");
+  UYD_REQUIRE(y, UYD_E_ARG, "uyd_plan_run_decoded: y is NULL");
+  return run_ops(plan, x, x_dtype == UYD_F32 ? 1 : 2, batch, stream, y);
+}
+
 // Times every op separately with CUDA events on `stream` (one pass, ops serialised as in a
 // normal run).  ms: [uyd_plan_num_launches].  Synchronises the stream.
 extern "C" int uyd_plan_profile(uyd_plan *plan, const float *x, int batch, uyd_stream stream, float *ms) {
@@ -551,13 +662,19 @@ extern "C" int uyd_plan_profile(uyd_plan *plan, const float *x, int batch, uyd_s
   for (auto &e : ev) UYD_CUDA(cudaEventCreate(&e));
   UYD_CUDA(cudaEventRecord(ev[0], s));
   for (size_t i = 0; i < n; ++i) {
-    int e = launch_op(plan, plan->ops[i], x, 1, batch, s);
+    int e = launch_op(plan, plan->ops[i], x, 1, batch, s, plan->profile_y);
     if (e) return e;
     UYD_CUDA(cudaEventRecord(ev[i + 1], s));
   }
   UYD_CUDA(cudaStreamSynchronize(s));
   for (size_t i = 0; i < n; ++i) UYD_CUDA(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
   for (auto &e : ev) cudaEventDestroy(e);
+  return UYD_OK;
+}
+
+extern "C" int uyd_plan_set_profile_output(uyd_plan *plan, float *y) {
+  UYD_REQUIRE(plan, UYD_E_ARG, "uyd_plan_set_profile_output: plan is NULL");
+  plan->profile_y = y;
   return UYD_OK;
 }
 
@@ -609,6 +726,16 @@ extern "C" int uyd_plan_op_info(uyd_plan *plan, int op, char *text, size_t text_
          (d.res_buf >= 0 ? (double)ob.h * ob.w * d.cout * 2 : 0);
     snprintf(text, text_len, "conv %d->%d k%d s%d%s %dx%d %s%s%s", d.cin, d.cout, d.k, d.stride, d.depthwise ? " dw" : "", ob.h,
              ob.w, o.use_tc ? "tc:" : "direct", o.use_tc ? tc_mode_name(o.tc) : "", d.res_buf >= 0 ? " +res" : "");
+  } else if (o.kind == OP_CHAIN) {
+    const uyd_chain &d = o.chain;
+    const Buffer &b = plan->bufs[d.in_buf];
+    const double px = (double)b.h * b.w;
+    fl = 2.0 * px * ((d.dw1 ? 9.0 * d.cin : 9.0 * d.cin * d.n1) + (double)d.n1 * d.n2 + (d.final_kind == UYD_CHAIN_PW3 ? (double)d.n2 * d.nc : 0.0));
+    const double dec = d.final_kind == UYD_CHAIN_DFL ? 16 : (d.final_kind == UYD_CHAIN_PW3 ? 4.0 * d.nc : 0);
+    const double rawb = d.out_buf >= 0 ? (d.final_kind == UYD_CHAIN_PW3 ? 4.0 * d.nc : d.n2 * (double)plan->bufs[d.out_buf].elem_bytes()) : 0;
+    by = px * (d.cin * 2.0 + rawb + (d.out_buf >= 0 && d.final_kind != UYD_CHAIN_STORE ? 0 : dec));
+    snprintf(text, text_len, "chain %s%d->%d k3 + %d->%d k1 + %s %dx%d tc", d.dw1 ? "dw" : "", d.cin, d.n1, d.n1, d.n2,
+             d.final_kind == UYD_CHAIN_DFL ? "dfl" : (d.final_kind == UYD_CHAIN_PW3 ? "pw3" : "store"), b.h, b.w);
   } else if (o.kind == OP_CLS) {
     const Buffer &b = plan->bufs[o.buf];
     const double c = o.c;

@@ -1,0 +1,547 @@
+// Chained tcgen05 kernel for the Detect head (Ultralytics Detect.cv2 / cv3):
+//
+//     GEMM1 : 3x3 stride-1 conv  Cin -> N1   (HALO mode of conv_tc.cu: one TMA halo box per channel
+//             block, nine tap-shifted UMMA descriptors)            + bias + ReLU -> bf16
+//     GEMM2 : 1x1 conv           N1  -> N2   A operand = the bf16 tile the epilogue warps wrote to
+//             shared memory in the canonical K-major swizzled UMMA layout (never leaves the SM)
+//     FINAL : one of
+//               STORE  bias (+ReLU) -> bf16 / fp32 NHWC slice               (cls stage 1, raw box logits)
+//               PW3    ReLU -> bf16 -> nc <= 8 dot products on CUDA cores   (Detect.cv3[l][2])
+//                      -> raw logits into the head slice and / or sigmoid scores into y
+//               DFL    softmax-integral over 4 x 16 bins -> (cx, cy, w, h) * stride into y
+//                      (Detect._inference + DFL + dist2bbox, same arithmetic as decode.cu)
+//
+// Box branch  : Conv(64,64,3) -> Conv2d(64,64,1) -> DFL                    = one launch, the 64 logits
+//               of an anchor stay in TMEM / registers.
+// Class branch: DWConv(c,c,3) runs as a dense 3x3 GEMM with diagonal weights (the tensor pipe is
+//               otherwise idle and the tap-shifted descriptors make the window free), followed by
+//               its 1x1 conv: [dw1, pw1] -> z1 (bf16) and [dw2, pw2, pw3] -> logits / scores.
+//
+// Warp roles (320 threads, persistent CTA per SM): warp 0 TMA producer, warp 1 TMEM allocator +
+// single-thread MMA issuer, warps 2-5 / 6-9 two epilogue groups taking alternate tiles.  The
+// issuer is software-pipelined: GEMM1 of tile t+1 is issued before GEMM2 of tile t, so the
+// tensor pipe never waits for the epilogue's shared-memory tile.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace uyd {
+
+enum { CH_STORE = 0, CH_PW3 = 2, CH_DFL = 3 };
+
+struct ChainParams {
+  int H, W, n0, nb;
+  int tiles_x, tiles_y;
+  long long total_tiles;
+  int ncb, cb_bytes;  // GEMM1: input channel blocks, bytes per block row (64 / 128)
+  int N1, N2;         // UMMA N of the two GEMMs
+  int c2;             // real output channels of GEMM2 (STORE)
+  int stages;
+  uint32_t blk_bytes, tx_bytes, w1_bytes, w2_bytes, a2_bytes;
+  uint32_t idesc1, idesc2, layout1, layout2;
+  int relu2, final_kind, nc;
+  const float *bias1, *bias2, *bias3, *w3;  // w3: fp32 [nc][N2] holding bf16-rounded values
+  void *out;                                // raw store target (slice base of image 0) or null
+  int out_pitch, out_f32;
+  float *y;                                 // decoded output [B, no, a_total] or null
+  int a_total, a_off, y_ch0, no;
+  float stride_px;
+};
+
+namespace {
+
+constexpr int kChainThreads = 320;
+constexpr int kHaloRows = 18, kTileH = 16, kTileW = 8, kHaloPitch = kTileW + 2;
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// KS1 / KS2 = 32-byte k-steps per channel-block row of GEMM1 / GEMM2 (cb_bytes / 32, N1 * 2 / 32)
+template <int KS1, int KS2>
+__global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __grid_constant__ CUtensorMap tm_in,
+                                                                      const __grid_constant__ CUtensorMap tm_w1,
+                                                                      const __grid_constant__ CUtensorMap tm_w2,
+                                                                      const ChainParams p) {
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t raw = smem_u32(smem_dyn);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t w1_s = base;
+  const uint32_t w2_s = w1_s + ((p.w1_bytes + 1023u) & ~1023u);
+  const uint32_t a2_s = w2_s + ((p.w2_bytes + 1023u) & ~1023u);
+  const uint32_t a_s = a2_s + 2u * p.a2_bytes;
+  const uint32_t bar0 = a_s + (uint32_t)p.stages * p.blk_bytes;
+  // barriers: full[8] empty[8] wfull tfull1[2] tempty1[2] a2full[2] tfull2[2] tempty2[2] | slot | floats
+  const uint32_t full0 = bar0, empty0 = bar0 + 64, wfull = bar0 + 128;
+  const uint32_t tfull1 = bar0 + 136, tempty1 = bar0 + 152, a2full = bar0 + 168, tfull2 = bar0 + 184, tempty2 = bar0 + 200;
+  const uint32_t slot = bar0 + 216;
+  uint32_t *slot_ptr = reinterpret_cast<uint32_t *>(smem_dyn + (slot - raw));
+  float *fs = reinterpret_cast<float *>(smem_dyn + (bar0 + 256u - raw));
+  float *bias1_s = fs, *bias2_s = fs + 128, *bias3_s = fs + 256, *w3_s = fs + 264;  // w3_s: [8][64]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < 2u * (uint32_t)(p.N1 + p.N2)) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full0 + 8u * s, 1);
+      mbar_init(empty0 + 8u * s, 1);
+    }
+    mbar_init(wfull, 1);
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(tfull1 + 8u * g, 1);
+      mbar_init(tempty1 + 8u * g, 128);
+      mbar_init(a2full + 8u * g, 128);
+      mbar_init(tfull2 + 8u * g, 1);
+      mbar_init(tempty2 + 8u * g, 128);
+    }
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < 128; i += kChainThreads) {
+    bias1_s[i] = i < p.N1 ? p.bias1[i] : 0.f;
+    bias2_s[i] = i < p.N2 ? p.bias2[i] : 0.f;
+  }
+  if (p.final_kind == CH_PW3) {
+    for (int i = threadIdx.x; i < 8 * 64; i += kChainThreads) {
+      const int c = i >> 6, k = i & 63;
+      w3_s[i] = (c < p.nc && k < p.N2) ? p.w3[c * p.N2 + k] : 0.f;
+    }
+    if (threadIdx.x < 8) bias3_s[threadIdx.x] = threadIdx.x < p.nc ? p.bias3[threadIdx.x] : 0.f;
+  }
+  if (warp == 1) tmem_alloc(slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *slot_ptr;
+
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int stages = p.stages;
+  const uint32_t blk_bytes = p.blk_bytes, cb_bytes = p.cb_bytes;
+  const uint32_t cb2_bytes = (uint32_t)p.N1 * 2u;  // one row of the GEMM2 A / B operands
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      mbar_expect_tx(wfull, p.w1_bytes + p.w2_bytes);
+      const int nblk = p.ncb * 9;
+      for (int i = 0; i < nblk; ++i) tma_load_2d(w1_s + (uint32_t)i * p.N1 * cb_bytes, &tm_w1, wfull, 0, i * p.N1);
+      tma_load_2d(w2_s, &tm_w2, wfull, 0, 0);
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    const int cb_elems = (int)cb_bytes / 2;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int n = p.n0 + (int)(tile / tiles_per_img);
+      const int t = (int)(tile % tiles_per_img);
+      const int y0 = (t / p.tiles_x) * kTileH, x0 = (t % p.tiles_x) * kTileW;
+      for (int j = 0; j < p.ncb; ++j) {
+        mbar_wait(empty0 + 8u * stage, phase ^ 1u);
+        if (lane == 0) {
+          const uint32_t fb = full0 + 8u * stage;
+          mbar_expect_tx(fb, p.tx_bytes);
+          tma_load_4d(a_s + (uint32_t)stage * blk_bytes, &tm_in, fb, j * cb_elems, x0 - 1, y0 - 1, n);
+        }
+        __syncwarp();
+        if (++stage == stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    mbar_wait(wfull, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint64_t adesc0 = make_desc_base((uint32_t)kHaloPitch * cb_bytes, p.layout1);
+    const uint64_t bdesc0 = make_desc_base(8u * cb_bytes, p.layout1);
+    const uint64_t a2desc0 = make_desc_base(8u * cb2_bytes, p.layout2);
+    const uint32_t wblk_units = ((uint32_t)p.N1 * cb_bytes) >> 4;
+    const uint32_t px_units = cb_bytes >> 4, row_units = (uint32_t)kHaloPitch * px_units;
+    const uint64_t w2d = a2desc0 + (uint64_t)((w2_s & 0x3FFFFu) >> 4);
+    auto issue_gemm2 = [&](int it) {  // tile index `it` of this CTA (group = it & 1)
+      const int g = it & 1;
+      const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(a2full + 8u * g, ph);          // the epilogue group has written its bf16 tile
+      mbar_wait(tempty2 + 8u * g, ph ^ 1u);    // and has drained the previous result of this accumulator
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t d2 = tmem_base + 2u * (uint32_t)p.N1 + (uint32_t)g * p.N2;
+        const uint64_t ad = a2desc0 + (uint64_t)(((a2_s + (uint32_t)g * p.a2_bytes) & 0x3FFFFu) >> 4);
+#pragma unroll
+        for (int k = 0; k < KS2; ++k) umma_bf16(d2, ad + 2 * k, w2d + 2 * k, p.idesc2, k != 0);
+        umma_commit(tfull2 + 8u * g);
+      }
+      __syncwarp();
+    };
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int g = it & 1;
+      mbar_wait(tempty1 + 8u * g, ((uint32_t)(it >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d1 = tmem_base + (uint32_t)g * p.N1;
+      for (int j = 0; j < p.ncb; ++j) {
+        mbar_wait(full0 + 8u * stage, phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t ablk_d = adesc0 + (uint64_t)(((a_s + (uint32_t)stage * blk_bytes) & 0x3FFFFu) >> 4);
+          uint64_t wd = bdesc0 + (uint64_t)(((w1_s + (uint32_t)(j * 9) * p.N1 * cb_bytes) & 0x3FFFFu) >> 4);
+          uint32_t accum = j != 0;
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            const uint64_t ad = ablk_d + (uint64_t)((t / 3) * row_units + (t % 3) * px_units);
+#pragma unroll
+            for (int k = 0; k < KS1; ++k) {
+              umma_bf16(d1, ad + 2 * k, wd + 2 * k, p.idesc1, accum);
+              accum = 1;
+            }
+            wd += wblk_units;
+          }
+          umma_commit(empty0 + 8u * stage);
+          if (j == p.ncb - 1) umma_commit(tfull1 + 8u * g);
+        }
+        __syncwarp();
+        if (++stage == stages) { stage = 0; phase ^= 1u; }
+      }
+      if (it > 0) issue_gemm2(it - 1);
+    }
+    if (it > 0) issue_gemm2(it - 1);
+  } else {
+    // ================= epilogue (two groups of four warps, alternate tiles) =================
+    const int q = warp & 3;
+    const int m = q * 32 + lane;         // accumulator row = pixel of the 16 x 8 tile
+    const int g = (warp - 2) >> 2;
+    const int nch1 = p.N1 >> 4;
+    unsigned char *a2_row = smem_dyn + (a2_s + (uint32_t)g * p.a2_bytes - raw) + (size_t)m * cb2_bytes;
+    // 16-byte chunk c of row m lives at chunk (c ^ swz) (TMA / UMMA swizzle: address bits [4,7) ^= bits [7,10),
+    // restricted to the row width)
+    const uint32_t swz = cb2_bytes == 128 ? (uint32_t)(m & 7) : (cb2_bytes == 64 ? (uint32_t)((m >> 1) & 3) : (uint32_t)((m >> 2) & 1));
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      if ((it & 1) != g) continue;
+      const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+      const int n = p.n0 + (int)(tile / tiles_per_img);
+      const int t = (int)(tile % tiles_per_img);
+      const int oy = (t / p.tiles_x) * kTileH + (m >> 3), ox = (t % p.tiles_x) * kTileW + (m & 7);
+      const bool inside = oy < p.H && ox < p.W;
+      // ---- stage 1: acc1 -> bias, ReLU -> bf16 -> swizzled shared-memory tile (A of GEMM2) ----
+      mbar_wait(tfull1 + 8u * g, ph);
+      tc_fence_after();
+      {
+        const uint32_t t1 = lane_base + (uint32_t)g * p.N1;
+        uint32_t cur[16], nxt[16];
+        tmem_ld16_issue(t1, cur);
+        tmem_ld_wait();
+        for (int c = 0; c < nch1; ++c) {
+          const bool more = c + 1 < nch1;
+          if (more) {
+            tmem_ld16_issue(t1 + 16u * (c + 1), nxt);
+          } else {
+            tc_fence_before();
+            mbar_arrive(tempty1 + 8u * g);
+          }
+          uint4 o0, o1;
+          uint32_t *w0 = reinterpret_cast<uint32_t *>(&o0), *w1 = reinterpret_cast<uint32_t *>(&o1);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float a0 = fmaxf(__uint_as_float(cur[2 * i]) + bias1_s[c * 16 + 2 * i], 0.f);
+            const float a1 = fmaxf(__uint_as_float(cur[2 * i + 1]) + bias1_s[c * 16 + 2 * i + 1], 0.f);
+            const float b0 = fmaxf(__uint_as_float(cur[8 + 2 * i]) + bias1_s[c * 16 + 8 + 2 * i], 0.f);
+            const float b1 = fmaxf(__uint_as_float(cur[8 + 2 * i + 1]) + bias1_s[c * 16 + 8 + 2 * i + 1], 0.f);
+            __nv_bfloat162 ha = __floats2bfloat162_rn(a0, a1), hb = __floats2bfloat162_rn(b0, b1);
+            w0[i] = *reinterpret_cast<uint32_t *>(&ha);
+            w1[i] = *reinterpret_cast<uint32_t *>(&hb);
+          }
+          *reinterpret_cast<uint4 *>(a2_row + (((uint32_t)(2 * c) ^ swz) << 4)) = o0;
+          *reinterpret_cast<uint4 *>(a2_row + (((uint32_t)(2 * c + 1) ^ swz) << 4)) = o1;
+          if (more) {
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
+          }
+        }
+      }
+      fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+      mbar_arrive(a2full + 8u * g);
+      // ---- stage 2: acc2 -> final ----
+      mbar_wait(tfull2 + 8u * g, ph);
+      tc_fence_after();
+      const uint32_t t2 = lane_base + 2u * (uint32_t)p.N1 + (uint32_t)g * p.N2;
+      const long long pix = ((long long)n * p.H + oy) * p.W + ox;
+      const int nch2 = p.N2 >> 4;
+      if (p.final_kind == CH_DFL) {
+        float d[4];
+        float raw_keep[16];
+#pragma unroll
+        for (int side = 0; side < 4; ++side) {
+          uint32_t r[16];
+          tmem_ld16_issue(t2 + 16u * side, r);
+          tmem_ld_wait();
+          if (side == 3) {
+            tc_fence_before();
+            mbar_arrive(tempty2 + 8u * g);
+          }
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + bias2_s[side * 16 + i];
+          if (p.out && inside) {
+            float *op = reinterpret_cast<float *>(p.out) + pix * p.out_pitch + side * 16;
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4 *>(op + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          }
+          float mx = v[0];
+#pragma unroll
+          for (int i = 1; i < 16; ++i) mx = fmaxf(mx, v[i]);
+          float s = 0.f, ws = 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float e = expf(v[i] - mx);
+            s += e;
+            ws = fmaf((float)i, e, ws);
+          }
+          d[side] = ws / s;
+          (void)raw_keep;
+        }
+        if (p.y && inside) {
+          const float ax = (float)ox + 0.5f, ay = (float)oy + 0.5f;
+          const float x1 = ax - d[0], y1 = ay - d[1], x2 = ax + d[2], y2 = ay + d[3];
+          float *yo = p.y + ((long long)n * p.no + p.y_ch0) * p.a_total + p.a_off + oy * p.W + ox;
+          yo[0] = (x1 + x2) * 0.5f * p.stride_px;
+          yo[(long long)p.a_total] = (y1 + y2) * 0.5f * p.stride_px;
+          yo[2ll * p.a_total] = (x2 - x1) * p.stride_px;
+          yo[3ll * p.a_total] = (y2 - y1) * p.stride_px;
+        }
+      } else if (p.final_kind == CH_PW3) {
+        float lg[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) lg[c] = bias3_s[c];
+        for (int ch = 0; ch < nch2; ++ch) {
+          uint32_t r[16];
+          tmem_ld16_issue(t2 + 16u * ch, r);
+          tmem_ld_wait();
+          if (ch == nch2 - 1) {
+            tc_fence_before();
+            mbar_arrive(tempty2 + 8u * g);
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            // z2 is a bf16 activation in the unfused graph: round it the same way before the last conv
+            const float z = __bfloat162float(__float2bfloat16_rn(fmaxf(__uint_as_float(r[i]) + bias2_s[ch * 16 + i], 0.f)));
+#pragma unroll
+            for (int c = 0; c < 8; ++c) lg[c] = fmaf(z, w3_s[c * 64 + ch * 16 + i], lg[c]);
+          }
+        }
+        if (inside) {
+          if (p.out) {
+            float *op = reinterpret_cast<float *>(p.out) + pix * p.out_pitch;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              if (c < p.nc) op[c] = lg[c];
+          }
+          if (p.y) {
+            float *yo = p.y + ((long long)n * p.no + p.y_ch0) * p.a_total + p.a_off + oy * p.W + ox;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              if (c < p.nc) yo[(long long)c * p.a_total] = sigmoidf_(lg[c]);
+          }
+        }
+      } else {  // CH_STORE: bias (+ReLU) -> bf16 / fp32 row of the NHWC slice
+        for (int ch = 0; ch < nch2; ++ch) {
+          uint32_t r[16];
+          tmem_ld16_issue(t2 + 16u * ch, r);
+          tmem_ld_wait();
+          if (ch == nch2 - 1) {
+            tc_fence_before();
+            mbar_arrive(tempty2 + 8u * g);
+          }
+          if (!inside || ch * 16 >= p.c2) continue;
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float x = __uint_as_float(r[i]) + bias2_s[ch * 16 + i];
+            v[i] = p.relu2 ? fmaxf(x, 0.f) : x;
+          }
+          if (p.out_f32) {
+            float *op = reinterpret_cast<float *>(p.out) + pix * p.out_pitch + ch * 16;
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4 *>(op + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          } else {
+            __nv_bfloat16 *op = reinterpret_cast<__nv_bfloat16 *>(p.out) + pix * p.out_pitch + ch * 16;
+            uint4 o0, o1;
+            uint32_t *w0 = reinterpret_cast<uint32_t *>(&o0), *w1 = reinterpret_cast<uint32_t *>(&o1);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              __nv_bfloat162 ha = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+              __nv_bfloat162 hb = __floats2bfloat162_rn(v[8 + 2 * i], v[8 + 2 * i + 1]);
+              w0[i] = *reinterpret_cast<uint32_t *>(&ha);
+              w1[i] = *reinterpret_cast<uint32_t *>(&hb);
+            }
+            *reinterpret_cast<uint4 *>(op) = o0;
+            *reinterpret_cast<uint4 *>(op + 8) = o1;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn chain_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int chain_encode(CUtensorMap *tm, void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides_bytes,
+                 const cuuint32_t *box, int row_bytes) {
+  EncodeTiledFn fn = chain_encode_fn();
+  UYD_REQUIRE(fn, UYD_E_NOGPU, "cuTensorMapEncodeTiled is not available (no CUDA driver)");
+  const cuuint32_t one4[4] = {1, 1, 1, 1};
+  const CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                                 : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, dims, strides_bytes, box, one4,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  UYD_REQUIRE(r == CUDA_SUCCESS, UYD_E_ARG, "conv_chain: cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank);
+  return UYD_OK;
+}
+
+uint32_t layout_code(int row_bytes) { return row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u); }
+
+}  // namespace
+
+struct ChainConv {
+  CUtensorMap tm_in, tm_w1, tm_w2;
+  ChainParams p;
+  size_t smem;
+};
+
+ChainConv *chain_new() { return new ChainConv(); }
+void chain_delete(ChainConv *c) { delete c; }
+
+// Shape rule: cin in {32, 64} (one channel block), n1 in {32, 64}, n2 <= 64.
+bool chain_supported(int cin, int n1, int n2, int in_pitch, int in_coff) {
+  if (!(cin == 32 || cin == 64) || !(n1 == 32 || n1 == 64) || n2 < 1 || n2 > 64) return false;
+  return in_pitch % 8 == 0 && in_coff % 8 == 0;
+}
+
+size_t chain_w1_bytes(int cin, int n1) { return (size_t)9 * cin * n1 * 2; }
+size_t chain_w2_bytes(int n1, int n2) { return (size_t)n1 * ((n2 + 15) / 16 * 16) * 2; }
+
+// w1: [n1][cin][3][3] fp32 (dense) or, when depthwise, [n1][1][3][3] expanded to a diagonal dense matrix.
+// Layout: bf16 [tap][n (N1)][cin]   (one channel block)
+void chain_pack_w1(int cin, int n1, bool depthwise, const float *w, void *dst_host) {
+  __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(dst_host);
+  for (int t = 0; t < 9; ++t)
+    for (int n = 0; n < n1; ++n)
+      for (int c = 0; c < cin; ++c) {
+        float v;
+        if (depthwise) v = (n == c) ? w[(size_t)n * 9 + t] : 0.f;
+        else v = w[((size_t)n * cin + c) * 9 + t];
+        o[((size_t)t * n1 + n) * cin + c] = __float2bfloat16_rn(v);
+      }
+}
+
+// w2: [n2][n1] fp32 -> bf16 [N2 padded][n1]
+void chain_pack_w2(int n1, int n2, const float *w, void *dst_host) {
+  __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(dst_host);
+  const int N2 = (n2 + 15) / 16 * 16;
+  for (int n = 0; n < N2; ++n)
+    for (int k = 0; k < n1; ++k) o[(size_t)n * n1 + k] = __float2bfloat16_rn(n < n2 ? w[(size_t)n * n1 + k] : 0.f);
+}
+
+int chain_prepare(ChainConv *cc, int cin, int n1, int n2, void *in_base, int in_pitch, int h, int w, int max_batch,
+                  void *w1_dev, void *w2_dev, const float *bias1, const float *bias2, int relu2, int final_kind, int nc,
+                  const float *w3_dev, const float *bias3_dev, void *out_base, int out_pitch, int out_f32, int a_total,
+                  int a_off, int y_ch0, int no, float stride_px) {
+  ChainParams &p = cc->p;
+  memset(&p, 0, sizeof(p));
+  p.H = h; p.W = w;
+  p.ncb = 1;
+  p.cb_bytes = cin * 2;
+  p.N1 = n1;
+  p.N2 = (n2 + 15) / 16 * 16;
+  p.c2 = n2;
+  UYD_REQUIRE(final_kind != CH_DFL || p.N2 == 64, UYD_E_UNSUPPORTED, "conv_chain: the DFL final needs 4 x 16 logits");
+  UYD_REQUIRE(final_kind != CH_PW3 || (nc >= 1 && nc <= 8 && w3_dev && bias3_dev), UYD_E_UNSUPPORTED, "conv_chain: PW3 needs nc <= 8");
+  p.tiles_x = ceil_div(w, kTileW);
+  p.tiles_y = ceil_div(h, kTileH);
+  p.blk_bytes = ((uint32_t)kHaloRows * kHaloPitch * p.cb_bytes + 1023u) & ~1023u;
+  p.tx_bytes = (uint32_t)kHaloRows * kHaloPitch * p.cb_bytes;
+  p.w1_bytes = (uint32_t)chain_w1_bytes(cin, n1);
+  p.w2_bytes = (uint32_t)chain_w2_bytes(n1, n2);
+  p.a2_bytes = 128u * (uint32_t)n1 * 2u;
+  p.layout1 = layout_code(p.cb_bytes);
+  p.layout2 = layout_code(n1 * 2);
+  p.idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N1 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  p.idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N2 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  p.relu2 = relu2;
+  p.final_kind = final_kind;
+  p.nc = nc;
+  p.bias1 = bias1; p.bias2 = bias2; p.bias3 = bias3_dev; p.w3 = w3_dev;
+  p.out = out_base; p.out_pitch = out_pitch; p.out_f32 = out_f32;
+  p.a_total = a_total; p.a_off = a_off; p.y_ch0 = y_ch0; p.no = no; p.stride_px = stride_px;
+  const size_t fixed = 1024 + ((p.w1_bytes + 1023u) & ~1023u) + ((p.w2_bytes + 1023u) & ~1023u) + 2 * (size_t)p.a2_bytes + 256 + 4096;
+  int stages = (int)((227 * 1024 - fixed) / p.blk_bytes);
+  UYD_REQUIRE(stages >= 2, UYD_E_UNSUPPORTED, "conv_chain: %d -> %d -> %d leaves no room for two halo stages", cin, n1, n2);
+  if (stages > 6) stages = 6;
+  p.stages = stages;
+  cc->smem = fixed + (size_t)stages * p.blk_bytes;
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)cin, (cuuint64_t)9 * n1};
+    const cuuint64_t str[1] = {(cuuint64_t)p.cb_bytes};
+    const cuuint32_t box[2] = {(cuuint32_t)cin, (cuuint32_t)n1};
+    int e = chain_encode(&cc->tm_w1, w1_dev, 2, dims, str, box, p.cb_bytes);
+    if (e) return e;
+  }
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)n1, (cuuint64_t)p.N2};
+    const cuuint64_t str[1] = {(cuuint64_t)n1 * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)n1, (cuuint32_t)p.N2};
+    int e = chain_encode(&cc->tm_w2, w2_dev, 2, dims, str, box, n1 * 2);
+    if (e) return e;
+  }
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)max_batch};
+    const cuuint64_t str[3] = {(cuuint64_t)in_pitch * 2, (cuuint64_t)w * in_pitch * 2, (cuuint64_t)h * w * in_pitch * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)cin, (cuuint32_t)kHaloPitch, (cuuint32_t)kHaloRows, 1};
+    int e = chain_encode(&cc->tm_in, in_base, 4, dims, str, box, p.cb_bytes);
+    if (e) return e;
+  }
+  static bool attr = false;
+  if (!attr) {
+    UYD_CUDA(cudaFuncSetAttribute(conv_chain_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    UYD_CUDA(cudaFuncSetAttribute(conv_chain_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    UYD_CUDA(cudaFuncSetAttribute(conv_chain_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    UYD_CUDA(cudaFuncSetAttribute(conv_chain_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  return UYD_OK;
+}
+
+int chain_launch(const ChainConv *cc, int nb, float *y, int sm_count, cudaStream_t s) {
+  ChainParams p = cc->p;
+  p.n0 = 0;
+  p.nb = nb;
+  p.y = y;
+  p.total_tiles = (long long)nb * p.tiles_x * p.tiles_y;
+  if (p.total_tiles == 0) return UYD_OK;
+  const unsigned grid = (unsigned)(p.total_tiles < sm_count ? p.total_tiles : sm_count);
+  const int ks1 = p.cb_bytes / 32, ks2 = p.N1 * 2 / 32;
+#define UYD_CHAIN_LAUNCH(A, B) conv_chain_kernel<A, B><<<grid, kChainThreads, cc->smem, s>>>(cc->tm_in, cc->tm_w1, cc->tm_w2, p)
+  if (ks1 == 2 && ks2 == 2) UYD_CHAIN_LAUNCH(2, 2);
+  else if (ks1 == 2 && ks2 == 4) UYD_CHAIN_LAUNCH(2, 4);
+  else if (ks1 == 4 && ks2 == 2) UYD_CHAIN_LAUNCH(4, 2);
+  else UYD_CHAIN_LAUNCH(4, 4);
+#undef UYD_CHAIN_LAUNCH
+  return (int)cudaGetLastError();
+}
+
+}  // namespace uyd

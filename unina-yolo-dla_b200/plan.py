@@ -8,7 +8,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import IMPL_AUTO, UYD_BF16, UYD_F32, UYD_S8, C3kDesc, ClsBranchDesc, ConvDesc, ConvS8Desc, check
+from ._lib import (CHAIN_DFL, CHAIN_PW3, CHAIN_STORE, IMPL_AUTO, UYD_BF16, UYD_F32, UYD_S8, UYD_U8, C3kDesc, ChainDesc,
+                   ClsBranchDesc, ConvDesc, ConvS8Desc, check)
 
 _TORCH_DTYPE = {UYD_BF16: torch.bfloat16, UYD_F32: torch.float32, UYD_S8: torch.int8}
 
@@ -129,6 +130,34 @@ class Plan:
         check(_lib.lib().uyd_plan_add_cls_branch(self.handle, C.byref(d), wp, bp), "uyd_plan_add_cls_branch")
         return dst
 
+    @staticmethod
+    def chain_supported(src: Slice, n1: int, n2: int) -> bool:
+        """Shape rule of the chained head kernel (chain_supported in csrc/conv_chain.cu)."""
+        return src.c in (32, 64) and n1 in (32, 64) and 1 <= n2 <= 64 and src.coff % 8 == 0
+
+    def chain(self, src: Slice, w1, b1, w2, b2, *, dw1: bool = False, relu2: bool = False, final: int = CHAIN_STORE,
+              out: Slice | None = None, w3=None, b3=None, a_total: int = 0, a_off: int = 0, y_ch0: int = 0, no: int = 0,
+              stride: float = 1.0) -> Slice | None:
+        """3x3 Conv+BN+ReLU (dense or depth-wise) -> 1x1 conv -> fused final stage, one launch
+        (uyd_plan_add_chain).  Weights BN-folded, PyTorch layout."""
+        f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+        w1, b1, w2, b2 = f32(w1), f32(b1), f32(w2).reshape(np.shape(w2)[0], -1), f32(b2)
+        n1, n2 = w1.shape[0], w2.shape[0]
+        assert w2.shape[1] == n1 and b1.shape == (n1,) and b2.shape == (n2,)
+        assert w1.shape[1] == (1 if dw1 else src.c) and w1.shape[2:] == (3, 3)
+        nc = 0
+        if final == CHAIN_PW3:
+            w3, b3 = f32(w3).reshape(np.shape(w3)[0], -1), f32(b3)
+            nc = w3.shape[0]
+            assert w3.shape[1] == n2 and b3.shape == (nc,)
+        d = ChainDesc(src.buf, src.coff, src.c, n1, n2, int(dw1), int(relu2), final, out.buf if out else -1,
+                      out.coff if out else 0, nc, a_total, a_off, y_ch0, no, float(stride))
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+        check(_lib.lib().uyd_plan_add_chain(self.handle, C.byref(d), ptr(w1), ptr(b1), ptr(w2), ptr(b2),
+                                            ptr(w3) if final == CHAIN_PW3 else None, ptr(b3) if final == CHAIN_PW3 else None),
+              "uyd_plan_add_chain")
+        return out
+
     def sppf_pool(self, s: Slice, c: int) -> None:
         check(_lib.lib().uyd_plan_add_sppf_pool(self.handle, s.buf, s.coff, c), "uyd_plan_add_sppf_pool")
 
@@ -154,14 +183,24 @@ class Plan:
     def _stream() -> C.c_void_p:
         return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
-    def run(self, x: torch.Tensor) -> None:
+    def run(self, x: torch.Tensor, y: torch.Tensor | None = None) -> None:
+        """Runs every op; ``y`` ([B, no, A] fp32) receives the decoded prediction of plans whose head
+        kernels decode in their epilogue."""
         assert x.is_cuda and x.is_contiguous() and x.dtype in (torch.float32, torch.uint8)
+        if y is not None:
+            assert y.is_cuda and y.is_contiguous() and y.dtype == torch.float32 and y.shape[0] >= x.shape[0]
+            check(_lib.lib().uyd_plan_run_decoded(self.handle, C.c_void_p(x.data_ptr()),
+                                                  UYD_F32 if x.dtype == torch.float32 else UYD_U8, x.shape[0],
+                                                  C.c_void_p(y.data_ptr()), self._stream()), "uyd_plan_run_decoded")
+            return
         fn = _lib.lib().uyd_plan_run if x.dtype == torch.float32 else _lib.lib().uyd_plan_run_u8
         check(fn(self.handle, C.c_void_p(x.data_ptr()), x.shape[0], self._stream()), "uyd_plan_run")
 
-    def profile(self, x: torch.Tensor) -> list[float]:
+    def profile(self, x: torch.Tensor, y: torch.Tensor | None = None) -> list[float]:
         """Per-op milliseconds of one pass (CUDA events around every op)."""
         assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+        check(_lib.lib().uyd_plan_set_profile_output(self.handle, C.c_void_p(y.data_ptr()) if y is not None else None),
+              "uyd_plan_set_profile_output")
         ms = (C.c_float * self.launches)()
         check(_lib.lib().uyd_plan_profile(self.handle, C.c_void_p(x.data_ptr()), x.shape[0], self._stream(), ms),
               "uyd_plan_profile")
@@ -181,8 +220,13 @@ class Plan:
         check(_lib.lib().uyd_plan_timed_op_read(self.handle, C.byref(tot), C.byref(n)), "uyd_plan_timed_op_read")
         return tot.value, n.value
 
-    def run_no_input(self, batch: int) -> None:
+    def run_no_input(self, batch: int, y: torch.Tensor | None = None) -> None:
         """Runs a plan whose first op does not read the network input (layer-level tests)."""
+        if y is not None:
+            dummy = torch.empty(16, dtype=torch.float32, device=y.device)
+            check(_lib.lib().uyd_plan_run_decoded(self.handle, C.c_void_p(dummy.data_ptr()), UYD_F32, batch,
+                                                  C.c_void_p(y.data_ptr()), self._stream()), "uyd_plan_run_decoded")
+            return
         check(_lib.lib().uyd_plan_run(self.handle, None, batch, self._stream()), "uyd_plan_run")
 
     def write(self, s: Slice, nchw: torch.Tensor) -> None:

@@ -22,10 +22,14 @@ import torch.nn as nn
 import yaml
 
 from . import _lib
-from ._lib import UYD_BF16, UYD_F32, check
+from ._lib import CHAIN_DFL, CHAIN_PW3, CHAIN_STORE, UYD_BF16, UYD_F32, check
 from .plan import NETWORK_INPUT, Plan, Slice, fold_bn
 
 DEFAULT_YAML = Path(__file__).resolve().parent / "unina-yolo-dla-m.yaml"
+
+
+class _NoFuse(Exception):
+    """The decode cannot be folded into the head kernels for this graph / shape."""
 
 
 def _make_divisible(x, d):
@@ -187,27 +191,53 @@ class Detect(nn.Module):
             a[-1].bias.data[:] = 1.0
             b[-1].bias.data[: self.nc] = math.log(5 / self.nc / (640 / float(s)) ** 2)
 
-    def emit(self, p, feats):
-        heads = []
+    def emit(self, p, feats, fused: bool = False):
+        """Box branch: Conv3x3 -> [Conv3x3 -> Conv2d 1x1 -> DFL] (one chained tcgen05 launch).
+        Class branch: [DWConv3x3 -> Conv1x1] -> [DWConv3x3 -> Conv1x1 -> Conv2d 1x1 (-> sigmoid)].
+        ``fused``: the chained kernels write the decoded prediction y directly and no raw head
+        tensor exists; otherwise they write the raw logits into fp32 head buffers."""
+        use_chain = os.environ.get("UYD_NO_CHAIN", "0") != "1"
+        a_total = sum(f.h * f.w for f in feats)
+        heads, a_off = [], 0
+        wb = lambda conv: (conv.weight.detach().float().cpu().numpy(), conv.bias.detach().float().cpu().numpy())
         for i, f in enumerate(feats):
-            head = p.buffer(f.h, f.w, self.no, UYD_F32)
+            geo = dict(a_total=a_total, a_off=a_off, no=4 + self.nc, stride=float(self.stride[i]))
+            head = None if fused else p.buffer(f.h, f.w, self.no, UYD_F32)
+            # ---- box branch ----
             t = self.cv2[i][0].emit(p, f)
-            t = self.cv2[i][1].emit(p, t)
-            emit_plain_conv(p, self.cv2[i][2], t, head.sub(0, 4 * self.reg_max))
-            cls_dst = head.sub(4 * self.reg_max, self.nc)
-            b0, b1, last = self.cv3[i][0], self.cv3[i][1], self.cv3[i][2]
-            mid = b0[1].c2
-            if (os.environ.get("UYD_NO_CLS_FUSION", "0") != "1" and b0[0].g == f.c and b1[0].g == mid and b1[1].c2 == mid
-                    and p.cls_branch_supported(f, mid, self.nc) and p.shapes[f.buf][2] % 8 == 0):
-                folded = [fold_bn(m.conv, m.bn) for m in (b0[0], b0[1], b1[0], b1[1])]
-                folded.append((last.weight.detach().float().cpu().numpy(), last.bias.detach().float().cpu().numpy()))
-                p.cls_branch(f, cls_dst, mid, [w for w, _ in folded], [b for _, b in folded])
+            mid_conv, last = self.cv2[i][1], self.cv2[i][2]
+            if (use_chain and mid_conv.k == 3 and mid_conv.s == 1 and mid_conv.g == 1 and 4 * self.reg_max == 64
+                    and p.chain_supported(t, mid_conv.c2, 64) and p.shapes[t.buf][2] % 8 == 0):
+                w1, b1 = fold_bn(mid_conv.conv, mid_conv.bn)
+                w2, b2 = wb(last)
+                p.chain(t, w1, b1, w2, b2, final=CHAIN_DFL if fused else CHAIN_STORE,
+                        out=None if fused else head.sub(0, 4 * self.reg_max), y_ch0=0, **geo)
+            elif fused:
+                raise _NoFuse
             else:
-                t = f
-                for blk in (b0, b1):
-                    t = blk[1].emit(p, blk[0].emit(p, t))
-                emit_plain_conv(p, last, t, cls_dst)
-            heads.append(head)
+                emit_plain_conv(p, last, mid_conv.emit(p, t), head.sub(0, 4 * self.reg_max))
+            # ---- class branch ----
+            b0, b1_, last = self.cv3[i][0], self.cv3[i][1], self.cv3[i][2]
+            mid = b0[1].c2
+            dw_ok = lambda blk, c: blk[0].g == c and blk[0].k == 3 and blk[0].s == 1 and blk[1].k == 1
+            if use_chain and dw_ok(b0, f.c) and p.chain_supported(f, f.c, mid) and mid % 16 == 0 and p.shapes[f.buf][2] % 8 == 0:
+                w1, b1 = fold_bn(b0[0].conv, b0[0].bn)
+                w2, b2 = fold_bn(b0[1].conv, b0[1].bn)
+                z1 = p.chain(f, w1, b1, w2, b2, dw1=True, relu2=True, final=CHAIN_STORE, out=p.buffer(f.h, f.w, mid))
+            else:
+                z1 = b0[1].emit(p, b0[0].emit(p, f))
+            if use_chain and dw_ok(b1_, mid) and b1_[1].c2 == mid and p.chain_supported(z1, mid, mid) and self.nc <= 8:
+                w1, b1 = fold_bn(b1_[0].conv, b1_[0].bn)
+                w2, b2 = fold_bn(b1_[1].conv, b1_[1].bn)
+                w3, b3 = wb(last)
+                p.chain(z1, w1, b1, w2, b2, dw1=True, relu2=True, final=CHAIN_PW3, w3=w3, b3=b3,
+                        out=None if fused else head.sub(4 * self.reg_max, self.nc), y_ch0=4, **geo)
+            elif fused:
+                raise _NoFuse
+            else:
+                emit_plain_conv(p, last, b1_[1].emit(p, b1_[0].emit(p, z1)), head.sub(4 * self.reg_max, self.nc))
+            heads.append(head if head is not None else Slice(-1, 0, self.no, f.h, f.w))
+            a_off += f.h * f.w
         return heads
 
 
@@ -305,6 +335,9 @@ class UninaYoloB200(nn.Module):
                 st.append(s_in)
         raise ValueError("graph has no Detect layer")
 
+    def num_anchors(self, H: int, W: int) -> int:
+        return sum((H // int(s)) * (W // int(s)) for s in self.stride.tolist())
+
     def refresh(self) -> None:
         """Drop compiled plans (call after mutating parameters in place)."""
         self._graphs.clear()
@@ -321,9 +354,10 @@ class UninaYoloB200(nn.Module):
         return super()._apply(fn, recurse)
 
     # ---- plan construction -------------------------------------------------------------
-    def _build_plan(self, device: int, max_batch: int, H: int, W: int) -> Plan:
+    def _build_plan(self, device: int, max_batch: int, H: int, W: int, fused: bool = False) -> Plan:
         p = Plan(device, max_batch)
         p.in_hw = (H, W)
+        p.fused = fused
         layers = list(self.model)
         # pass 1: extents of every layer output
         shape = []
@@ -370,22 +404,44 @@ class UninaYoloB200(nn.Module):
                 outs.append(home[m.i])
             elif isinstance(m, Detect):
                 feats = [src_of(j) for j in m.f]
-                heads = m.emit(p, feats)
-                p.set_heads(heads, [int(s) for s in m.stride.tolist()], m.reg_max, m.nc)
+                heads = m.emit(p, feats, fused)
+                if fused:
+                    p.heads = heads  # extents only: the decoded output is written by the head kernels
+                else:
+                    p.set_heads(heads, [int(s) for s in m.stride.tolist()], m.reg_max, m.nc)
                 outs.append(None)
         p.layer_outputs = outs
         return p.finalize()
 
-    def plan_for(self, x: torch.Tensor) -> Plan:
+    def plan_for(self, x: torch.Tensor, fused: bool = False) -> Plan:
+        """The compiled plan for frames shaped like ``x``.  ``fused``: the variant whose head kernels
+        write the decoded prediction directly (no raw head tensors); falls back to the raw-head
+        variant when the graph / shape does not allow it."""
         B, _, H, W = x.shape
         dev = x.device.index if x.device.index is not None else torch.cuda.current_device()
-        key = (dev, H, W)
+        key = (dev, H, W, bool(fused))
         p = self._plans.get(key)
         if p is None or p.max_batch < B:
             if H % 32 or W % 32:
                 raise ValueError("frame height/width must be multiples of 32")
-            p = self._build_plan(dev, B, H, W)
+            if fused:
+                try:
+                    p = self._build_plan(dev, B, H, W, True)
+                except _NoFuse:
+                    p = self.plan_for(x, False)
+            else:
+                p = self._build_plan(dev, B, H, W, False)
             self._plans[key] = p
+        return p
+
+    def _decoded_into(self, x: torch.Tensor, y: torch.Tensor) -> Plan:
+        """x -> y[B,4+nc,A] through the fused plan (C calls only: usable under graph capture)."""
+        p = self.plan_for(x, fused=os.environ.get("UYD_NO_FUSED_DECODE", "0") != "1")
+        if p.fused:
+            p.run(x, y)
+        else:
+            p.run(x)
+            p.decode(y, x.shape[0])
         return p
 
     # ---- execution ---------------------------------------------------------------------
@@ -439,14 +495,15 @@ class UninaYoloB200(nn.Module):
     def forward(self, x: torch.Tensor, raw_heads: bool = True):
         """Eval forward of DetectionModel: ``(y[B,4+nc,A], [x_l[B,no,H_l,W_l]])``."""
         x = self._prep(x)
-        p = self.plan_for(x)
         B = x.shape[0]
-        p.run(x)
-        A = sum(h.h * h.w for h in p.heads)
+        A = self.num_anchors(x.shape[2], x.shape[3])
         y = torch.empty(B, 4 + self.nc, A, dtype=torch.float32, device=x.device)
-        p.decode(y, B)
         if not raw_heads:
+            self._decoded_into(x, y)
             return y
+        p = self.plan_for(x)
+        p.run(x)
+        p.decode(y, B)
         xs = []
         for lvl, h in enumerate(p.heads):
             t = torch.empty(B, h.c, h.h, h.w, dtype=torch.float32, device=x.device)
@@ -496,8 +553,7 @@ class UninaYoloB200(nn.Module):
         g = self._graphs.get(key)
         if g is not None:
             return g
-        p = self.plan_for(x)
-        A = sum(h.h * h.w for h in p.heads)
+        A = self.num_anchors(H, W)
         xs = torch.empty_like(x)
         y = torch.empty(B, 4 + self.nc, A, dtype=torch.float32, device=x.device)
         det = torch.zeros(B, max_det, 6, dtype=torch.float32, device=x.device)
@@ -506,8 +562,7 @@ class UninaYoloB200(nn.Module):
 
         def body():
             det.zero_()
-            p.run(xs)
-            p.decode(y, B)
+            self._decoded_into(xs, y)
             self._nms_into(y, det, None, cnt, ws, conf, iou, max_det, max_nms, 7680.0)
 
         xs.copy_(x)
@@ -520,7 +575,7 @@ class UninaYoloB200(nn.Module):
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             body()
-        g = (graph, xs, det, cnt, (p, y, ws))  # the graph writes y / ws on every replay: keep them alive
+        g = (graph, xs, det, cnt, (self.plan_for(xs, True), y, ws))  # the graph writes y / ws on every replay: keep them alive
         self._graphs[key] = g
         return g
 
