@@ -17,6 +17,7 @@ def main():
     ap.add_argument("--size", type=int, default=640)
     ap.add_argument("--top", type=int, default=40)
     ap.add_argument("--cand", type=int, default=1500)
+    ap.add_argument("--ncu", action="store_true", help="bracket ONE step with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     a = ap.parse_args()
     m = uyd.UninaYoloB200.from_yaml().init_synthetic(0).cuda()
     x = torch.rand(a.batch, 3, a.size, a.size, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
@@ -24,6 +25,12 @@ def main():
     for _ in range(3):
         m.predict_batched(x)
     torch.cuda.synchronize()
+    if a.ncu:
+        torch.cuda.profiler.start()
+        m.predict_batched(x)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         for _ in range(3):
             m.predict_batched(x)

@@ -52,7 +52,16 @@ namespace {
 constexpr int kChainThreads = 320;
 constexpr int kHaloRows = 18, kTileH = 16, kTileW = 8, kHaloPitch = kTileW + 2;
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+// 16 consecutive floats of a shared-memory vector as four 16-byte broadcast loads
+__device__ __forceinline__ void load_bias16(const float *s, float (&v)[16]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 q = reinterpret_cast<const float4 *>(s)[i];
+    v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+  }
+}
 
 // KS1 / KS2 = 32-byte k-steps per channel-block row of GEMM1 / GEMM2 (cb_bytes / 32, N1 * 2 / 32)
 template <int KS1, int KS2>
@@ -100,8 +109,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     bias2_s[i] = i < p.N2 ? p.bias2[i] : 0.f;
   }
   if (p.final_kind == CH_PW3) {
-    for (int i = threadIdx.x; i < 8 * 64; i += kChainThreads) {
-      const int c = i >> 6, k = i & 63;
+    for (int i = threadIdx.x; i < 8 * 64; i += kChainThreads) {  // shared layout [k][8 classes]: one 16-byte load per 4 classes
+      const int k = i >> 3, c = i & 7;
       w3_s[i] = (c < p.nc && k < p.N2) ? p.w3[c * p.N2 + k] : 0.f;
     }
     if (threadIdx.x < 8) bias3_s[threadIdx.x] = threadIdx.x < p.nc ? p.bias3[threadIdx.x] : 0.f;
@@ -238,12 +247,14 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
           }
           uint4 o0, o1;
           uint32_t *w0 = reinterpret_cast<uint32_t *>(&o0), *w1 = reinterpret_cast<uint32_t *>(&o1);
+          float bv[16];
+          load_bias16(bias1_s + c * 16, bv);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float a0 = fmaxf(__uint_as_float(cur[2 * i]) + bias1_s[c * 16 + 2 * i], 0.f);
-            const float a1 = fmaxf(__uint_as_float(cur[2 * i + 1]) + bias1_s[c * 16 + 2 * i + 1], 0.f);
-            const float b0 = fmaxf(__uint_as_float(cur[8 + 2 * i]) + bias1_s[c * 16 + 8 + 2 * i], 0.f);
-            const float b1 = fmaxf(__uint_as_float(cur[8 + 2 * i + 1]) + bias1_s[c * 16 + 8 + 2 * i + 1], 0.f);
+            const float a0 = fmaxf(__uint_as_float(cur[2 * i]) + bv[2 * i], 0.f);
+            const float a1 = fmaxf(__uint_as_float(cur[2 * i + 1]) + bv[2 * i + 1], 0.f);
+            const float b0 = fmaxf(__uint_as_float(cur[8 + 2 * i]) + bv[8 + 2 * i], 0.f);
+            const float b1 = fmaxf(__uint_as_float(cur[8 + 2 * i + 1]) + bv[8 + 2 * i + 1], 0.f);
             __nv_bfloat162 ha = __floats2bfloat162_rn(a0, a1), hb = __floats2bfloat162_rn(b0, b1);
             w0[i] = *reinterpret_cast<uint32_t *>(&ha);
             w1[i] = *reinterpret_cast<uint32_t *>(&hb);
@@ -267,7 +278,6 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
       const int nch2 = p.N2 >> 4;
       if (p.final_kind == CH_DFL) {
         float d[4];
-        float raw_keep[16];
 #pragma unroll
         for (int side = 0; side < 4; ++side) {
           uint32_t r[16];
@@ -278,8 +288,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
             mbar_arrive(tempty2 + 8u * g);
           }
           float v[16];
+          load_bias16(bias2_s + side * 16, v);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + bias2_s[side * 16 + i];
+          for (int i = 0; i < 16; ++i) v[i] += __uint_as_float(r[i]);
           if (p.out && inside) {
             float *op = reinterpret_cast<float *>(p.out) + pix * p.out_pitch + side * 16;
 #pragma unroll
@@ -291,12 +302,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
           float s = 0.f, ws = 0.f;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float e = expf(v[i] - mx);
+            const float e = __expf(v[i] - mx);  // ex2.approx: the 16 softmax weights need no more (same in decode.cu)
             s += e;
             ws = fmaf((float)i, e, ws);
           }
           d[side] = ws / s;
-          (void)raw_keep;
         }
         if (p.y && inside) {
           const float ax = (float)ox + 0.5f, ay = (float)oy + 0.5f;
@@ -319,12 +329,18 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
             tc_fence_before();
             mbar_arrive(tempty2 + 8u * g);
           }
+          float bv[16];
+          load_bias16(bias2_s + ch * 16, bv);
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             // z2 is a bf16 activation in the unfused graph: round it the same way before the last conv
-            const float z = __bfloat162float(__float2bfloat16_rn(fmaxf(__uint_as_float(r[i]) + bias2_s[ch * 16 + i], 0.f)));
-#pragma unroll
-            for (int c = 0; c < 8; ++c) lg[c] = fmaf(z, w3_s[c * 64 + ch * 16 + i], lg[c]);
+            const float z = __bfloat162float(__float2bfloat16_rn(fmaxf(__uint_as_float(r[i]) + bv[i], 0.f)));
+            const float4 wa = *reinterpret_cast<const float4 *>(w3_s + (ch * 16 + i) * 8);
+            lg[0] = fmaf(z, wa.x, lg[0]); lg[1] = fmaf(z, wa.y, lg[1]); lg[2] = fmaf(z, wa.z, lg[2]); lg[3] = fmaf(z, wa.w, lg[3]);
+            if (p.nc > 4) {
+              const float4 wb = *reinterpret_cast<const float4 *>(w3_s + (ch * 16 + i) * 8 + 4);
+              lg[4] = fmaf(z, wb.x, lg[4]); lg[5] = fmaf(z, wb.y, lg[5]); lg[6] = fmaf(z, wb.z, lg[6]); lg[7] = fmaf(z, wb.w, lg[7]);
+            }
           }
         }
         if (inside) {
@@ -352,9 +368,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
           }
           if (!inside || ch * 16 >= p.c2) continue;
           float v[16];
+          load_bias16(bias2_s + ch * 16, v);
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float x = __uint_as_float(r[i]) + bias2_s[ch * 16 + i];
+            const float x = __uint_as_float(r[i]) + v[i];
             v[i] = p.relu2 ? fmaxf(x, 0.f) : x;
           }
           if (p.out_f32) {

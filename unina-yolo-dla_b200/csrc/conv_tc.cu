@@ -75,8 +75,13 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&raw)[16], const 
                                                const TcParams &p) {
   float v[16];
 #pragma unroll
+  for (int i = 0; i < 4; ++i) {  // 16-byte broadcast loads of the bias vector
+    const float4 q = reinterpret_cast<const float4 *>(bias_s + c0)[i];
+    v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+  }
+#pragma unroll
   for (int i = 0; i < 16; ++i) {
-    float x = __uint_as_float(raw[i]) + bias_s[c0 + i];
+    const float x = __uint_as_float(raw[i]) + v[i];
     v[i] = p.relu ? fmaxf(x, 0.f) : x;
   }
   const int nvalid = p.cout - c0;
@@ -130,8 +135,13 @@ __device__ __forceinline__ void epilogue_chunk_staged(const uint32_t (&raw)[16],
                                                       const TcParams &p, unsigned char *srow) {
   float v[16];
 #pragma unroll
+  for (int i = 0; i < 4; ++i) {  // 16-byte broadcast loads of the bias vector
+    const float4 q = reinterpret_cast<const float4 *>(bias_s + c0)[i];
+    v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+  }
+#pragma unroll
   for (int i = 0; i < 16; ++i) {
-    float x = __uint_as_float(raw[i]) + bias_s[c0 + i];
+    const float x = __uint_as_float(raw[i]) + v[i];
     v[i] = p.relu ? fmaxf(x, 0.f) : x;
   }
   if (p.res && pix >= 0) {  // residual convs have Cout % 16 == 0 (checked on the host)

@@ -10,7 +10,7 @@ namespace {
 
 constexpr int kThreads = 256;
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
 // head: [batch, H, W, 4*16 + nc] fp32.  y: [batch, 4+nc, a_total].
 template <int REG_MAX>
@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(kThreads) decode_dfl_kernel(const float *__res
   float s = 0.f, ws = 0.f;
 #pragma unroll
   for (int i = 0; i < REG_MAX; ++i) {
-    const float e = expf(v[i] - m);
+    const float e = __expf(v[i] - m);  // ex2.approx (identical in conv_chain.cu's fused decode)
     s += e;
     ws = fmaf((float)i, e, ws);
   }
