@@ -1,0 +1,109 @@
+// Probe: issue rate / execution time of back-to-back tcgen05.mma (kind::f16, M = 128, K = 16) for several N,
+// operands in shared memory (SWIZZLE_128B K-major, contents irrelevant), one CTA per SM.
+// Variants: issue under `if (lane == 0)` (divergent: ptxas wraps every UTCHMMA in an ELECT loop) vs
+// under elect.sync on a converged warp; same accumulator vs alternating accumulators.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o mma_rate mma_rate.cu ; run on a B200.
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
+               "l"(a), "l"(b), "r"(idesc), "r"(acc)
+               : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+template <int MODE>  // 0: if (lane == 0), 1: elect.sync, 2: elect + alternate accumulators every 4 MMAs
+__global__ void __launch_bounds__(128, 1) probe(int N, int iters, long long *out) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint32_t slot;
+  __shared__ __align__(8) unsigned long long bar;
+  const uint32_t base = (smem_u32(smem) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 48 * 1024 / 4; i += 128) reinterpret_cast<uint32_t *>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = slot;
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint64_t ad = make_desc(base, 1024), bd = make_desc(base + 16384, 1024);
+  long long t0 = 0, t1 = 0, t2 = 0;
+  if (warp == 1) {
+    t0 = clock64();
+    if (MODE == 0) {
+      if (lane == 0) {
+#pragma unroll 1
+        for (int i = 0; i < iters; i += 4) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma(tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);
+        }
+      }
+      __syncwarp();
+    } else {
+#pragma unroll 1
+      for (int i = 0; i < iters; i += 4) {
+        const uint32_t d = (MODE == 2 && (i & 4)) ? tmem + 256 : tmem;
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma(d, ad + 2 * k, bd + 2 * k, idesc, 1u);
+        }
+        __syncwarp();
+      }
+    }
+    t1 = clock64();
+    if (elect_one()) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    __syncwarp();
+    uint32_t ok = 0;
+    while (!ok) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(&bar)) : "memory");
+    }
+    t2 = clock64();
+    if (lane == 0 && blockIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+int main() {
+  long long *d, h[2];
+  cudaMalloc(&d, 16);
+  const int iters = 4000;
+  auto run = [&](int mode, int N) {
+    const size_t smem = 49 * 1024;
+    void (*k)(int, int, long long *) = mode == 0 ? probe<0> : (mode == 1 ? probe<1> : probe<2>);
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    for (int rep = 0; rep < 2; ++rep) k<<<148, 128, smem>>>(N, iters, d);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+    printf("mode %d N %3d: issue %.1f cyc/mma, issue+drain %.1f cyc/mma  (%s)\n", mode, N, (double)h[0] / iters, (double)h[1] / iters,
+           cudaGetErrorString(e));
+  };
+  for (int mode = 0; mode < 3; ++mode)
+    for (int N : {16, 32, 64, 128, 256}) run(mode, N);
+  return 0;
+}

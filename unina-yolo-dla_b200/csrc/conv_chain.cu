@@ -17,10 +17,12 @@
 //               otherwise idle and the tap-shifted descriptors make the window free), followed by
 //               its 1x1 conv: [dw1, pw1] -> z1 (bf16) and [dw2, pw2, pw3] -> logits / scores.
 //
-// Warp roles (320 threads, persistent CTA per SM): warp 0 TMA producer, warp 1 TMEM allocator +
-// single-thread MMA issuer, warps 2-5 / 6-9 two epilogue groups taking alternate tiles.  The
-// issuer is software-pipelined: GEMM1 of tile t+1 is issued before GEMM2 of tile t, so the
-// tensor pipe never waits for the epilogue's shared-memory tile.
+// Warp roles (512 threads, persistent CTA per SM): warp 0 TMA producer, warp 1 TMEM allocator + GEMM1
+// issuer, warp 2 GEMM2 issuer, warps 4-15 three epilogue groups taking tiles round-robin.  GEMM1 of the
+// following tiles is issued while a tile's bf16 operand is being written, so the tensor pipe never
+// waits for the epilogue.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -45,11 +47,13 @@ struct ChainParams {
   float *y;                                 // decoded output [B, no, a_total] or null
   int a_total, a_off, y_ch0, no;
   float stride_px;
+  long long *dbg;  // UYD_CHAIN_TIMELINE: clock64 stamps of CTA 0, [tile][8]
 };
 
 namespace {
 
-constexpr int kChainThreads = 320;
+constexpr int kNG = 3;                              // epilogue groups (4 warps each) taking tiles round-robin
+constexpr int kChainThreads = 128 + 128 * kNG;       // TMA, GEMM1 issuer, GEMM2 issuer, (idle), epilogue groups
 constexpr int kHaloRows = 18, kTileH = 16, kTileW = 8, kHaloPitch = kTileW + 2;
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
@@ -61,6 +65,10 @@ __device__ __forceinline__ void load_bias16(const float *s, float (&v)[16]) {
     const float4 q = reinterpret_cast<const float4 *>(s)[i];
     v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
   }
+}
+
+__device__ __forceinline__ void stamp(const ChainParams &p, int it, int slot, int lane) {
+  if (p.dbg && blockIdx.x == 0 && lane == 0 && it < 64) p.dbg[(slot >> 3) * 512 + it * 8 + (slot & 7)] = clock64();
 }
 
 // KS1 / KS2 = 32-byte k-steps per channel-block row of GEMM1 / GEMM2 (cb_bytes / 32, N1 * 2 / 32)
@@ -75,19 +83,19 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
   const uint32_t w1_s = base;
   const uint32_t w2_s = w1_s + ((p.w1_bytes + 1023u) & ~1023u);
   const uint32_t a2_s = w2_s + ((p.w2_bytes + 1023u) & ~1023u);
-  const uint32_t a_s = a2_s + 2u * p.a2_bytes;
+  const uint32_t a_s = a2_s + (uint32_t)kNG * p.a2_bytes;
   const uint32_t bar0 = a_s + (uint32_t)p.stages * p.blk_bytes;
-  // barriers: full[8] empty[8] wfull tfull1[2] tempty1[2] a2full[2] tfull2[2] tempty2[2] | slot | floats
+  // barriers: full[8] empty[8] wfull tfull1[4] tempty1[4] a2full[4] tfull2[4] tempty2[4] | slot | floats
   const uint32_t full0 = bar0, empty0 = bar0 + 64, wfull = bar0 + 128;
-  const uint32_t tfull1 = bar0 + 136, tempty1 = bar0 + 152, a2full = bar0 + 168, tfull2 = bar0 + 184, tempty2 = bar0 + 200;
-  const uint32_t slot = bar0 + 216;
+  const uint32_t tfull1 = bar0 + 136, tempty1 = bar0 + 168, a2full = bar0 + 200, tfull2 = bar0 + 232, tempty2 = bar0 + 264;
+  const uint32_t slot = bar0 + 296;
   uint32_t *slot_ptr = reinterpret_cast<uint32_t *>(smem_dyn + (slot - raw));
-  float *fs = reinterpret_cast<float *>(smem_dyn + (bar0 + 256u - raw));
+  float *fs = reinterpret_cast<float *>(smem_dyn + (bar0 + 320u - raw));
   float *bias1_s = fs, *bias2_s = fs + 128, *bias3_s = fs + 256, *w3_s = fs + 264;  // w3_s: [8][64]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t tmem_cols = 32;
-  while (tmem_cols < 2u * (uint32_t)(p.N1 + p.N2)) tmem_cols <<= 1;
+  while (tmem_cols < (uint32_t)kNG * (uint32_t)(p.N1 + p.N2)) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -95,7 +103,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
       mbar_init(empty0 + 8u * s, 1);
     }
     mbar_init(wfull, 1);
-    for (int g = 0; g < 2; ++g) {
+    for (int g = 0; g < kNG; ++g) {
       mbar_init(tfull1 + 8u * g, 1);
       mbar_init(tempty1 + 8u * g, 128);
       mbar_init(a2full + 8u * g, 128);
@@ -147,59 +155,42 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
           const uint32_t fb = full0 + 8u * stage;
           mbar_expect_tx(fb, p.tx_bytes);
           tma_load_4d(a_s + (uint32_t)stage * blk_bytes, &tm_in, fb, j * cb_elems, x0 - 1, y0 - 1, n);
+          if (p.dbg && blockIdx.x == 0) { const int itp = (int)((tile - blockIdx.x) / gridDim.x); if (itp < 64) p.dbg[itp * 8 + 0] = clock64(); }
         }
         __syncwarp();
         if (++stage == stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
+    // ================= GEMM1 issuer =================
+    // tcgen05.mma issue is nearly synchronous with execution (the queue is a few instructions deep), so
+    // every cycle this thread spends polling barriers is a tensor-pipe bubble: GEMM2 has its own issuing
+    // warp, whose waits overlap GEMM1's execution.
     mbar_wait(wfull, 0);
     int stage = 0;
     uint32_t phase = 0;
     const uint64_t adesc0 = make_desc_base((uint32_t)kHaloPitch * cb_bytes, p.layout1);
     const uint64_t bdesc0 = make_desc_base(8u * cb_bytes, p.layout1);
-    const uint64_t a2desc0 = make_desc_base(8u * cb2_bytes, p.layout2);
     const uint32_t wblk_units = ((uint32_t)p.N1 * cb_bytes) >> 4;
     const uint32_t px_units = cb_bytes >> 4, row_units = (uint32_t)kHaloPitch * px_units;
-    const uint64_t w2d = a2desc0 + (uint64_t)((w2_s & 0x3FFFFu) >> 4);
-    auto issue_gemm2 = [&](int it) {  // tile index `it` of this CTA (group = it & 1)
-      const int g = it & 1;
-      const uint32_t ph = (uint32_t)(it >> 1) & 1u;
-      mbar_wait(a2full + 8u * g, ph);          // the epilogue group has written its bf16 tile
-      mbar_wait(tempty2 + 8u * g, ph ^ 1u);    // and has drained the previous result of this accumulator
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t d2 = tmem_base + 2u * (uint32_t)p.N1 + (uint32_t)g * p.N2;
-        const uint64_t ad = a2desc0 + (uint64_t)(((a2_s + (uint32_t)g * p.a2_bytes) & 0x3FFFFu) >> 4);
-#pragma unroll
-        for (int k = 0; k < KS2; ++k) umma_bf16(d2, ad + 2 * k, w2d + 2 * k, p.idesc2, k != 0);
-        umma_commit(tfull2 + 8u * g);
-      }
-      __syncwarp();
-    };
-    int it = 0;
+    int it = 0, g = 0;
+    uint32_t gph = 0;  // phase of this group's barriers
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      const int g = it & 1;
-      mbar_wait(tempty1 + 8u * g, ((uint32_t)(it >> 1) & 1u) ^ 1u);
-      tc_fence_after();
+      mbar_wait(tempty1 + 8u * g, gph ^ 1u);
       const uint32_t d1 = tmem_base + (uint32_t)g * p.N1;
       for (int j = 0; j < p.ncb; ++j) {
         mbar_wait(full0 + 8u * stage, phase);
         tc_fence_after();
-        if (lane == 0) {
-          const uint64_t ablk_d = adesc0 + (uint64_t)(((a_s + (uint32_t)stage * blk_bytes) & 0x3FFFFu) >> 4);
-          uint64_t wd = bdesc0 + (uint64_t)(((w1_s + (uint32_t)(j * 9) * p.N1 * cb_bytes) & 0x3FFFFu) >> 4);
-          uint32_t accum = j != 0;
+        stamp(p, it, 1, lane);  // GEMM1 operands landed, issue starts
+        const uint64_t ablk_d = adesc0 + (uint64_t)(((a_s + (uint32_t)stage * blk_bytes) & 0x3FFFFu) >> 4);
+        const uint64_t wd0 = bdesc0 + (uint64_t)(((w1_s + (uint32_t)(j * 9) * p.N1 * cb_bytes) & 0x3FFFFu) >> 4);
+        if (elect_one()) {
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
             const uint64_t ad = ablk_d + (uint64_t)((t / 3) * row_units + (t % 3) * px_units);
+            const uint64_t wd = wd0 + (uint64_t)t * wblk_units;
 #pragma unroll
-            for (int k = 0; k < KS1; ++k) {
-              umma_bf16(d1, ad + 2 * k, wd + 2 * k, p.idesc1, accum);
-              accum = 1;
-            }
-            wd += wblk_units;
+            for (int k = 0; k < KS1; ++k) umma_bf16(d1, ad + 2 * k, wd + 2 * k, p.idesc1, (j != 0 || t != 0 || k != 0) ? 1u : 0u);
           }
           umma_commit(empty0 + 8u * stage);
           if (j == p.ncb - 1) umma_commit(tfull1 + 8u * g);
@@ -207,14 +198,35 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
         __syncwarp();
         if (++stage == stages) { stage = 0; phase ^= 1u; }
       }
-      if (it > 0) issue_gemm2(it - 1);
+      if (++g == kNG) { g = 0; gph ^= 1u; }
     }
-    if (it > 0) issue_gemm2(it - 1);
-  } else {
+  } else if (warp == 2) {
+    // ================= GEMM2 issuer =================
+    mbar_wait(wfull, 0);
+    const uint64_t a2desc0 = make_desc_base(8u * cb2_bytes, p.layout2);
+    const uint64_t w2d = a2desc0 + (uint64_t)((w2_s & 0x3FFFFu) >> 4);
+    int it = 0, g = 0;
+    uint32_t gph = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      mbar_wait(tempty2 + 8u * g, gph ^ 1u);   // the previous result of this accumulator has been drained
+      mbar_wait(a2full + 8u * g, gph);         // the epilogue group has written its bf16 tile
+      tc_fence_after();
+      stamp(p, it, 2, lane);  // GEMM2 issue
+      if (elect_one()) {
+        const uint32_t d2 = tmem_base + (uint32_t)kNG * (uint32_t)p.N1 + (uint32_t)g * p.N2;
+        const uint64_t ad = a2desc0 + (uint64_t)(((a2_s + (uint32_t)g * p.a2_bytes) & 0x3FFFFu) >> 4);
+#pragma unroll
+        for (int k = 0; k < KS2; ++k) umma_bf16(d2, ad + 2 * k, w2d + 2 * k, p.idesc2, k != 0);
+        umma_commit(tfull2 + 8u * g);
+      }
+      __syncwarp();
+      if (++g == kNG) { g = 0; gph ^= 1u; }
+    }
+  } else if (warp >= 4) {
     // ================= epilogue (two groups of four warps, alternate tiles) =================
     const int q = warp & 3;
     const int m = q * 32 + lane;         // accumulator row = pixel of the 16 x 8 tile
-    const int g = (warp - 2) >> 2;
+    const int g = (warp - 4) >> 2;
     const int nch1 = p.N1 >> 4;
     unsigned char *a2_row = smem_dyn + (a2_s + (uint32_t)g * p.a2_bytes - raw) + (size_t)m * cb2_bytes;
     // 16-byte chunk c of row m lives at chunk (c ^ swz) (TMA / UMMA swizzle: address bits [4,7) ^= bits [7,10),
@@ -223,8 +235,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     int it = 0;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      if ((it & 1) != g) continue;
-      const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+      if (it % kNG != g) continue;
+      const uint32_t ph = (uint32_t)(it / kNG) & 1u;
       const int n = p.n0 + (int)(tile / tiles_per_img);
       const int t = (int)(tile % tiles_per_img);
       const int oy = (t / p.tiles_x) * kTileH + (m >> 3), ox = (t % p.tiles_x) * kTileW + (m & 7);
@@ -232,6 +244,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
       // ---- stage 1: acc1 -> bias, ReLU -> bf16 -> swizzled shared-memory tile (A of GEMM2) ----
       mbar_wait(tfull1 + 8u * g, ph);
       tc_fence_after();
+      if (q == 0) stamp(p, it, 3, lane);  // accumulator 1 complete
       {
         const uint32_t t1 = lane_base + (uint32_t)g * p.N1;
         uint32_t cur[16], nxt[16];
@@ -270,27 +283,31 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
       }
       fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
       mbar_arrive(a2full + 8u * g);
+      if (q == 0) stamp(p, it, 4, lane);  // bf16 tile written
       // ---- stage 2: acc2 -> final ----
       mbar_wait(tfull2 + 8u * g, ph);
       tc_fence_after();
-      const uint32_t t2 = lane_base + 2u * (uint32_t)p.N1 + (uint32_t)g * p.N2;
+      if (q == 0) stamp(p, it, 5, lane);  // accumulator 2 complete
+      const uint32_t t2 = lane_base + (uint32_t)kNG * (uint32_t)p.N1 + (uint32_t)g * p.N2;
       const long long pix = ((long long)n * p.H + oy) * p.W + ox;
       const int nch2 = p.N2 >> 4;
       if (p.final_kind == CH_DFL) {
         float d[4];
+        uint32_t cur[16], nxt[16];
+        tmem_ld16_issue(t2, cur);
+        tmem_ld_wait();
 #pragma unroll
         for (int side = 0; side < 4; ++side) {
-          uint32_t r[16];
-          tmem_ld16_issue(t2 + 16u * side, r);
-          tmem_ld_wait();
-          if (side == 3) {
+          if (side < 3) {
+            tmem_ld16_issue(t2 + 16u * (side + 1), nxt);  // in flight while this side is reduced
+          } else {
             tc_fence_before();
             mbar_arrive(tempty2 + 8u * g);
           }
           float v[16];
           load_bias16(bias2_s + side * 16, v);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += __uint_as_float(r[i]);
+          for (int i = 0; i < 16; ++i) v[i] += __uint_as_float(cur[i]);
           if (p.out && inside) {
             float *op = reinterpret_cast<float *>(p.out) + pix * p.out_pitch + side * 16;
 #pragma unroll
@@ -307,6 +324,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
             ws = fmaf((float)i, e, ws);
           }
           d[side] = ws / s;
+          if (side < 3) {
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
+          }
         }
         if (p.y && inside) {
           const float ax = (float)ox + 0.5f, ay = (float)oy + 0.5f;
@@ -321,11 +343,14 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
         float lg[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) lg[c] = bias3_s[c];
+        uint32_t cur[16], nxt[16];
+        tmem_ld16_issue(t2, cur);
+        tmem_ld_wait();
         for (int ch = 0; ch < nch2; ++ch) {
-          uint32_t r[16];
-          tmem_ld16_issue(t2 + 16u * ch, r);
-          tmem_ld_wait();
-          if (ch == nch2 - 1) {
+          const bool more = ch + 1 < nch2;
+          if (more) {
+            tmem_ld16_issue(t2 + 16u * (ch + 1), nxt);
+          } else {
             tc_fence_before();
             mbar_arrive(tempty2 + 8u * g);
           }
@@ -334,13 +359,18 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             // z2 is a bf16 activation in the unfused graph: round it the same way before the last conv
-            const float z = __bfloat162float(__float2bfloat16_rn(fmaxf(__uint_as_float(r[i]) + bv[i], 0.f)));
+            const float z = __bfloat162float(__float2bfloat16_rn(fmaxf(__uint_as_float(cur[i]) + bv[i], 0.f)));
             const float4 wa = *reinterpret_cast<const float4 *>(w3_s + (ch * 16 + i) * 8);
             lg[0] = fmaf(z, wa.x, lg[0]); lg[1] = fmaf(z, wa.y, lg[1]); lg[2] = fmaf(z, wa.z, lg[2]); lg[3] = fmaf(z, wa.w, lg[3]);
             if (p.nc > 4) {
               const float4 wb = *reinterpret_cast<const float4 *>(w3_s + (ch * 16 + i) * 8 + 4);
               lg[4] = fmaf(z, wb.x, lg[4]); lg[5] = fmaf(z, wb.y, lg[5]); lg[6] = fmaf(z, wb.z, lg[6]); lg[7] = fmaf(z, wb.w, lg[7]);
             }
+          }
+          if (more) {
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
           }
         }
         if (inside) {
@@ -394,6 +424,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
           }
         }
       }
+      if (q == 0) stamp(p, it, 6, lane);  // final stage done
     }
   }
   tc_fence_before();
@@ -505,7 +536,7 @@ int chain_prepare(ChainConv *cc, int cin, int n1, int n2, void *in_base, int in_
   p.bias1 = bias1; p.bias2 = bias2; p.bias3 = bias3_dev; p.w3 = w3_dev;
   p.out = out_base; p.out_pitch = out_pitch; p.out_f32 = out_f32;
   p.a_total = a_total; p.a_off = a_off; p.y_ch0 = y_ch0; p.no = no; p.stride_px = stride_px;
-  const size_t fixed = 1024 + ((p.w1_bytes + 1023u) & ~1023u) + ((p.w2_bytes + 1023u) & ~1023u) + 2 * (size_t)p.a2_bytes + 256 + 4096;
+  const size_t fixed = 1024 + ((p.w1_bytes + 1023u) & ~1023u) + ((p.w2_bytes + 1023u) & ~1023u) + (size_t)kNG * p.a2_bytes + 320 + 4096;
   int stages = (int)((227 * 1024 - fixed) / p.blk_bytes);
   UYD_REQUIRE(stages >= 2, UYD_E_UNSUPPORTED, "conv_chain: %d -> %d -> %d leaves no room for two halo stages", cin, n1, n2);
   if (stages > 6) stages = 6;
@@ -552,12 +583,32 @@ int chain_launch(const ChainConv *cc, int nb, float *y, int sm_count, cudaStream
   if (p.total_tiles == 0) return UYD_OK;
   const unsigned grid = (unsigned)(p.total_tiles < sm_count ? p.total_tiles : sm_count);
   const int ks1 = p.cb_bytes / 32, ks2 = p.N1 * 2 / 32;
+  static long long *dbg_dev = nullptr;
+  const bool timeline = getenv("UYD_CHAIN_TIMELINE") && p.total_tiles >= 64ll * grid;
+  if (timeline) {
+    if (!dbg_dev) cudaMalloc(&dbg_dev, 2 * 64 * 8 * sizeof(long long));
+    cudaMemsetAsync(dbg_dev, 0, 2 * 64 * 8 * sizeof(long long), s);
+    p.dbg = dbg_dev;
+  }
 #define UYD_CHAIN_LAUNCH(A, B) conv_chain_kernel<A, B><<<grid, kChainThreads, cc->smem, s>>>(cc->tm_in, cc->tm_w1, cc->tm_w2, p)
   if (ks1 == 2 && ks2 == 2) UYD_CHAIN_LAUNCH(2, 2);
   else if (ks1 == 2 && ks2 == 4) UYD_CHAIN_LAUNCH(2, 4);
   else if (ks1 == 4 && ks2 == 2) UYD_CHAIN_LAUNCH(4, 2);
   else UYD_CHAIN_LAUNCH(4, 4);
 #undef UYD_CHAIN_LAUNCH
+  if (timeline) {  // debug only: dump the stamps of CTA 0 (cycles relative to its first TMA issue)
+    long long h[2 * 64 * 8];
+    cudaStreamSynchronize(s);
+    cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "chain timeline cin=%d N1=%d N2=%d final=%d (tma g1issue g2issue acc1 a2 acc2 done)\n", p.cb_bytes / 2, p.N1, p.N2, p.final_kind);
+    for (int t = 0; t < 40; ++t) {
+      fprintf(stderr, "  tile %2d:", t);
+      for (int k = 0; k < 7; ++k) fprintf(stderr, " %7lld", h[t * 8 + k] ? h[t * 8 + k] - h[0] : -1);
+      fprintf(stderr, "  | mma:");
+      for (int k = 0; k < 6; ++k) fprintf(stderr, " %7lld", h[512 + t * 8 + k] ? h[512 + t * 8 + k] - h[0] : -1);
+      fprintf(stderr, "\n");
+    }
+  }
   return (int)cudaGetLastError();
 }
 

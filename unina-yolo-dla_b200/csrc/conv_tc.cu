@@ -332,8 +332,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       for (int j = 0; j < blocks_per_tile; ++j) {
         mbar_wait(full0 + 8u * stage, phase);
         tc_fence_after();
-        if (lane == 0) {
-          // The issue loop runs in ONE thread: every instruction here sits on the critical path of the
+        if (elect_one()) {
+          // The issue loop runs in ONE thread (elect.sync on the converged warp, see tc_ptx.cuh): every instruction here sits on the critical path of the
           // tensor pipe, so descriptors are advanced by precomputed 16-byte-unit increments and both
           // loops are fully unrolled (KSTEPS is a template parameter).
           const uint64_t ablk_d = adesc0 + (uint64_t)(((a_s + (uint32_t)stage * blk_bytes) & 0x3FFFFu) >> 4);

@@ -99,6 +99,16 @@ __device__ __forceinline__ uint64_t make_desc_base(uint32_t sbo, uint32_t layout
   return d;
 }
 
+// One lane of a converged warp (elect.sync).  Single-thread tcgen05 / TMA issue must sit under this,
+// not under `lane == 0`: ptxas then emits the uniform-datapath instruction directly, whereas a divergent
+// lane test wraps every UTCHMMA in an ELECT/BRA loop (measured, tools/probes/mma_rate.cu: 51 vs 40-48
+// cycles per MMA at N <= 64).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 }  // namespace
