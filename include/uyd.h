@@ -83,6 +83,13 @@ typedef struct uyd_conv {
  * bias: host fp32 [cout].  Packed to the kernel's layout and uploaded here. */
 int uyd_plan_add_conv(uyd_plan *plan, const uyd_conv *desc, const float *weight, const float *bias);
 
+/* Fused stem (csrc/stem_fused.cu): the first two layers of the YAML graph, Conv(3,16,3,2) -> Conv(16,32,3,2)
+ * (both Conv+BN+ReLU, BN folded), in one launch reading the network input; the 16-channel tensor between
+ * them stays in shared memory.  Must be the first op.  w0 [16][3][3][3], w1 [32][16][3][3] (PyTorch layout).
+ * The output buffer has a quarter of the frame extent. */
+int uyd_plan_add_stem2(uyd_plan *plan, int out_buf, int out_coff, const float *w0, const float *b0, const float *w1,
+                       const float *b1);
+
 /* INT8 convolution (QAT fake-quant semantics of qat.py:109-124 as an integer computation,
  * oracle/quant.py): input slice int8 (UYD_S8 buffer), weight int8 [cout][cin][k][k] already
  * quantised, exact int32 accumulation, y = float(acc) * mult[c] + bias[c] (fp32, separate

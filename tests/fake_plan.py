@@ -43,6 +43,11 @@ class FakePlan:
         self.ops.append(("cls", src, dst, [torch.from_numpy(w) for w in weights], [torch.from_numpy(b) for b in biases]))
         return dst
 
+    def stem2(self, dst, w0, b0, w1, b1):
+        t = lambda a: torch.as_tensor(a, dtype=torch.float32)
+        self.ops.append(("stem2", dst, t(w0), t(b0), t(w1), t(b1)))
+        return dst
+
     @staticmethod
     def chain_supported(src, n1, n2):
         return src.c in (32, 64) and n1 in (32, 64) and 1 <= n2 <= 64 and src.coff % 8 == 0
@@ -76,7 +81,11 @@ class FakePlan:
 
         self.y = None
         for op in self.ops:
-            if op[0] == "chain":
+            if op[0] == "stem2":
+                _, dst, w0, b0, w1, b1 = op
+                t = F.conv2d(x, w0, b0, stride=2, padding=1).relu()
+                bufs[dst.buf][:, dst.coff:dst.coff + dst.c] = F.conv2d(t, w1, b1, stride=2, padding=1).relu()
+            elif op[0] == "chain":
                 _, src, out, w1, b1, w2, b2, dw1, relu2, final, w3, b3, (a_total, a_off, y_ch0, no, stride) = op
                 xin = get(src)
                 t = F.conv2d(xin, w1, b1, padding=1, groups=xin.shape[1] if dw1 else 1).relu()

@@ -62,6 +62,7 @@ SIGNATURES = {
     "uyd_plan_add_conv_s8": (C.c_int, [C.c_void_p, C.POINTER(ConvS8Desc), C.c_void_p, C.c_void_p, C.c_void_p]),
     "uyd_plan_add_c3k": (C.c_int, [C.c_void_p, C.POINTER(C3kDesc), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "uyd_plan_add_cls_branch": (C.c_int, [C.c_void_p, C.POINTER(ClsBranchDesc), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "uyd_plan_add_stem2": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "uyd_plan_add_chain": (C.c_int, [C.c_void_p, C.POINTER(ChainDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),
     "uyd_plan_run_decoded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

@@ -73,6 +73,19 @@ int chain_prepare(ChainConv *cc, int cin, int n1, int n2, void *in_base, int in_
                   int a_off, int y_ch0, int no, float stride_px);
 int chain_launch(const ChainConv *cc, int nb, float *y, int sm_count, cudaStream_t s);
 
+// stem_fused.cu
+struct StemArgs {
+  const void *in;
+  __nv_bfloat16 *out;
+  const uint32_t *wfrag;
+  const float *bias;
+  int n, ih, iw, oh, ow, out_pitch, u8;
+};
+bool stem_fused_supported(int c0, int c1, int ih, int iw, int out_pitch, int out_coff);
+void stem_fused_pack(const float *w0, const float *b0, const float *w1, const float *b1, std::vector<uint32_t> &frags,
+                     std::vector<float> &bias);
+int stem_fused_launch(const StemArgs &a, cudaStream_t s);
+
 static int env_int(const char *name, int dflt) {
   const char *v = getenv(name);
   return v && *v ? atoi(v) : dflt;
@@ -87,7 +100,7 @@ struct uyd_ctx {
   int sm_count = 0;
 };
 
-enum OpKind { OP_CONV = 0, OP_SPPF = 1, OP_UPSAMPLE = 2, OP_CONV_S8 = 3, OP_C3K = 4, OP_CLS = 5, OP_CHAIN = 6 };
+enum OpKind { OP_CONV = 0, OP_SPPF = 1, OP_UPSAMPLE = 2, OP_CONV_S8 = 3, OP_C3K = 4, OP_CLS = 5, OP_CHAIN = 6, OP_STEM2 = 7 };
 
 struct Op {
   OpKind kind;
@@ -406,6 +419,28 @@ extern "C" int uyd_plan_add_chain(uyd_plan *plan, const uyd_chain *d, const floa
   return UYD_OK;
 }
 
+extern "C" int uyd_plan_add_stem2(uyd_plan *plan, int out_buf, int out_coff, const float *w0, const float *b0, const float *w1,
+                                  const float *b1) {
+  UYD_REQUIRE(plan && w0 && b0 && w1 && b1, UYD_E_ARG, "uyd_plan_add_stem2: NULL argument");
+  UYD_REQUIRE(!plan->finalized, UYD_E_STATE, "plan already finalized");
+  UYD_REQUIRE(plan->ops.empty(), UYD_E_ARG, "only the first op may read the network input");
+  int e;
+  if ((e = check_slice(plan, out_buf, out_coff, 32, "stem2 output"))) return e;
+  const Buffer &ob = plan->bufs[out_buf];
+  UYD_REQUIRE(ob.dtype == UYD_BF16 && stem_fused_supported(16, 32, ob.h * 4, ob.w * 4, ob.c, out_coff), UYD_E_UNSUPPORTED,
+              "stem2: bf16 output slice with 16-byte alignment");
+  plan->in_c = 3; plan->in_h = ob.h * 4; plan->in_w = ob.w * 4;
+  Op op;
+  op.kind = OP_STEM2;
+  op.out_buf = out_buf; op.out_coff = out_coff;
+  std::vector<uint32_t> frags;
+  stem_fused_pack(w0, b0, w1, b1, frags, op.b_host);
+  op.w_host.resize(frags.size() * 4);
+  memcpy(op.w_host.data(), frags.data(), op.w_host.size());
+  plan->ops.push_back(std::move(op));
+  return UYD_OK;
+}
+
 extern "C" int uyd_plan_add_sppf_pool(uyd_plan *plan, int buf, int coff, int c) {
   UYD_REQUIRE(plan && !plan->finalized, UYD_E_STATE, "plan missing or finalized");
   int e;
@@ -474,7 +509,7 @@ extern "C" int uyd_plan_finalize(uyd_plan *plan) {
   const int stages = env_int("UYD_TC_STAGES", 0);
   const int halo_pitch = env_int("UYD_TC_HALO_PITCH", 10);
   for (Op &o : plan->ops) {
-    if (o.kind != OP_CONV && o.kind != OP_CONV_S8 && o.kind != OP_C3K && o.kind != OP_CLS && o.kind != OP_CHAIN) continue;
+    if (o.kind != OP_CONV && o.kind != OP_CONV_S8 && o.kind != OP_C3K && o.kind != OP_CLS && o.kind != OP_CHAIN && o.kind != OP_STEM2) continue;
     UYD_CUDA(cudaMalloc(&o.w_dev, o.w_host.size()));
     UYD_CUDA(cudaMemcpy(o.w_dev, o.w_host.data(), o.w_host.size(), cudaMemcpyHostToDevice));
     UYD_CUDA(cudaMalloc((void **)&o.b_dev, o.b_host.size() * 4));
@@ -514,7 +549,7 @@ extern "C" int uyd_plan_finalize(uyd_plan *plan) {
       if (e) return e;
       continue;
     }
-    if (o.kind == OP_C3K) continue;
+    if (o.kind == OP_C3K || o.kind == OP_STEM2) continue;
     if (o.kind == OP_CONV_S8) {
       UYD_CUDA(cudaMalloc((void **)&o.m_dev, o.m_host.size() * 4));
       UYD_CUDA(cudaMemcpy(o.m_dev, o.m_host.data(), o.m_host.size() * 4, cudaMemcpyHostToDevice));
@@ -588,6 +623,14 @@ static int launch_op(uyd_plan *plan, const Op &o, const void *x, int x_kind, int
       a.wfrag = (const uint32_t *)o.w_dev; a.bias = o.b_dev;
       a.n = batch; a.h = ib.h; a.w = ib.w; a.in_pitch = ib.c; a.out_pitch = ob.c;
       e = c3k_launch(o.c, a, s);
+    } else if (o.kind == OP_STEM2) {
+      UYD_REQUIRE(x, UYD_E_ARG, "uyd_plan_run: x is NULL");
+      const Buffer &ob = plan->bufs[o.out_buf];
+      StemArgs a{};
+      a.in = x; a.out = (__nv_bfloat16 *)slice_ptr(plan, o.out_buf, o.out_coff);
+      a.wfrag = (const uint32_t *)o.w_dev; a.bias = o.b_dev;
+      a.n = batch; a.ih = plan->in_h; a.iw = plan->in_w; a.oh = ob.h; a.ow = ob.w; a.out_pitch = ob.c; a.u8 = x_kind == 2;
+      e = stem_fused_launch(a, s);
     } else if (o.kind == OP_CHAIN) {
       UYD_REQUIRE(y || o.chain.out_buf >= 0, UYD_E_ARG, "this plan decodes in its head kernels: run it with uyd_plan_run_decoded");
       e = chain_launch(o.cc, batch, y, plan->ctx->sm_count, s);
@@ -726,6 +769,11 @@ extern "C" int uyd_plan_op_info(uyd_plan *plan, int op, char *text, size_t text_
          (d.res_buf >= 0 ? (double)ob.h * ob.w * d.cout * 2 : 0);
     snprintf(text, text_len, "conv %d->%d k%d s%d%s %dx%d %s%s%s", d.cin, d.cout, d.k, d.stride, d.depthwise ? " dw" : "", ob.h,
              ob.w, o.use_tc ? "tc:" : "direct", o.use_tc ? tc_mode_name(o.tc) : "", d.res_buf >= 0 ? " +res" : "");
+  } else if (o.kind == OP_STEM2) {
+    const Buffer &b = plan->bufs[o.out_buf];
+    fl = 2.0 * (4.0 * b.h * b.w * 16 * 27 + (double)b.h * b.w * 32 * 144);
+    by = 16.0 * b.h * b.w * 3 * 4 + (double)b.h * b.w * 32 * 2;
+    snprintf(text, text_len, "stem2 3->16 k3 s2 + 16->32 k3 s2 fused -> %dx%d", b.h, b.w);
   } else if (o.kind == OP_CHAIN) {
     const uyd_chain &d = o.chain;
     const Buffer &b = plan->bufs[d.in_buf];

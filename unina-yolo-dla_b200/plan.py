@@ -67,6 +67,11 @@ class Plan:
         self.shapes[bid.value] = (h, w, c, dtype)
         return Slice(bid.value, 0, c, h, w)
 
+    def buffer_slice(self, buf: int, coff: int, c: int) -> Slice:
+        h, w, ctot, _ = self.shapes[buf]
+        assert coff + c <= ctot
+        return Slice(buf, coff, c, h, w)
+
     def conv(self, src: Slice, dst: Slice, weight: np.ndarray, bias: np.ndarray, k: int, stride: int = 1,
              relu: bool = True, depthwise: bool = False, res: Slice | None = None, impl: int = IMPL_AUTO) -> Slice:
         weight = np.ascontiguousarray(weight, dtype=np.float32)
@@ -128,6 +133,15 @@ class Plan:
         bp = (C.c_void_p * 5)(*[b.ctypes.data_as(C.c_void_p) for b in bs])
         d = ClsBranchDesc(src.buf, src.coff, dst.buf, dst.coff, src.c, mid, dst.c, 0)
         check(_lib.lib().uyd_plan_add_cls_branch(self.handle, C.byref(d), wp, bp), "uyd_plan_add_cls_branch")
+        return dst
+
+    def stem2(self, dst: Slice, w0, b0, w1, b1) -> Slice:
+        """Fused Conv(3,16,3,2) -> Conv(16,32,3,2) reading the network input (uyd_plan_add_stem2)."""
+        f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+        w0, b0, w1, b1 = f32(w0), f32(b0), f32(w1), f32(b1)
+        assert w0.shape == (16, 3, 3, 3) and w1.shape == (32, 16, 3, 3) and dst.c == 32
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+        check(_lib.lib().uyd_plan_add_stem2(self.handle, dst.buf, dst.coff, ptr(w0), ptr(b0), ptr(w1), ptr(b1)), "uyd_plan_add_stem2")
         return dst
 
     @staticmethod

@@ -387,11 +387,23 @@ class UninaYoloB200(nn.Module):
                     off += shape[j][0]
         # pass 3: emit
         outs = []
+        l0, l1 = layers[0], layers[1]
+        stem2 = (os.environ.get("UYD_NO_STEM_FUSION", "0") != "1" and isinstance(l0, Conv) and isinstance(l1, Conv)
+                 and (l0.c1, l0.c2, l0.k, l0.s, l0.g) == (3, 16, 3, 2, 1) and (l1.c1, l1.c2, l1.k, l1.s, l1.g) == (16, 32, 3, 2, 1)
+                 and l1.f == -1 and 0 not in self.save and 0 not in home and H % 4 == 0 and W % 4 == 0)
         for m in layers:
             def src_of(j):
                 return outs[m.i - 1] if j == -1 else outs[j]
             dst = home.get(m.i)
-            if m.i == 0:
+            if stem2 and m.i == 0:
+                outs.append(None)      # lives only in shared memory of the fused stem kernel
+            elif stem2 and m.i == 1:
+                dst = dst or p.buffer(H // 4, W // 4, l1.c2)
+                if p.shapes[dst.buf][2] % 8 or dst.coff % 8:
+                    raise ValueError("fused stem needs a 16-byte aligned output slice")
+                (w0, b0), (w1, b1) = fold_bn(l0.conv, l0.bn), fold_bn(l1.conv, l1.bn)
+                outs.append(p.stem2(dst, w0, b0, w1, b1))
+            elif m.i == 0:
                 assert isinstance(m, Conv), "the first layer must be a Conv reading the frame"
                 outs.append(m.emit(p, NETWORK_INPUT, dst))
             elif isinstance(m, (Conv, C3k2, SPPF_DLA)):
