@@ -3,11 +3,12 @@
 // HBM traffic per frame and the 16-channel layer cannot feed tcgen05 efficiently (32-byte TMA rows).
 //
 // One CTA = 8 x 16 outputs of layer 1:
-//   * the 35 x 67 x 3 frame patch is staged in shared memory as fp32 (uint8 frames: x / 255 on load,
-//     the reference predictor's pre-process);
+//   * the 35 x 68 x 3 frame patch is staged in shared memory as two bf16 planes hi + lo (hi + lo == the
+//     fp32 value up to 2^-17, split once per element; uint8 frames: x / 255 first, the reference
+//     predictor's pre-process), so the frame itself is not rounded (weights are bf16 as everywhere);
 //   * layer 0 over the 17 x 33 region runs on tensor cores (mma.sync m16n8k16, bf16 x bf16 -> fp32):
-//     K = (ci, ky) x 4 column slots (the 4th slot has zero weights), and every frame value enters as
-//     hi + lo bf16 parts, so the frame itself is not rounded (weights are bf16 as everywhere);
+//     K = (ci, ky) x 4 column slots kx = -1..2 (slot -1 has zero weights and makes every slot pair a
+//     4-byte aligned shared-memory word);
 //   * its bf16 result (zero outside the image = layer 1's padding) never leaves shared memory;
 //   * layer 1 is nine k-steps of mma.sync (one filter tap = 16 channels per step).
 #include "common.cuh"
@@ -26,7 +27,7 @@ namespace {
 
 constexpr int kTH = 8, kTW = 16;            // layer-1 output tile
 constexpr int kL0H = 2 * kTH + 1, kL0W = 2 * kTW + 1;   // 17 x 33 layer-0 region
-constexpr int kInH = 2 * kL0H + 1, kInW = 2 * kL0W + 2;  // 35 rows x 68 columns (column 67 is padding for the 4th slot)
+constexpr int kInH = 2 * kL0H + 1, kInW = 2 * kL0W + 2;  // 35 rows x 68 columns (frame columns 4*ox0 - 4 ...; column 0 only feeds the zero slot)
 constexpr int kL0Pitch = 20;                // bf16 per layer-0 pixel in shared memory (16 + 4: conflict-free stride-2 reads)
 constexpr int kL0Px = kL0H * kL0W;          // 561
 constexpr int kThreads = 256;
@@ -52,47 +53,73 @@ __device__ __forceinline__ void split_bf16(float2 v, uint32_t &hi, uint32_t &lo)
 template <typename TIn>
 __global__ void __launch_bounds__(kThreads) stem_fused_kernel(StemArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
-  float *in_s = reinterpret_cast<float *>(smem);                                   // [3][35][68]
-  __nv_bfloat16 *l0_s = reinterpret_cast<__nv_bfloat16 *>(in_s + 3 * kInH * kInW);  // [561 + 16][20]
-  uint32_t *w_s = reinterpret_cast<uint32_t *>(l0_s + (kL0Px + 16) * kL0Pitch);     // fragments
+  __nv_bfloat16 *hi_s = reinterpret_cast<__nv_bfloat16 *>(smem);                   // [3][35][68] high parts
+  __nv_bfloat16 *lo_s = hi_s + 3 * kInH * kInW;                                     // [3][35][68] residuals
+  __nv_bfloat16 *l0_s = lo_s + 3 * kInH * kInW;                                     // [561 + 19][20]
+  uint32_t *w_s = reinterpret_cast<uint32_t *>(l0_s + (kL0Px + 19) * kL0Pitch);     // fragments (16-byte aligned)
   float *b_s = reinterpret_cast<float *>(w_s + (6 + 36) * 64);                      // [48]
-  __nv_bfloat16 *stage_s = reinterpret_cast<__nv_bfloat16 *>(in_s);                 // output staging aliases the frame patch
+  __nv_bfloat16 *stage_s = hi_s;                                                    // output staging aliases the frame patch
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int ox0 = blockIdx.x * kTW, oy0 = blockIdx.y * kTH, n = blockIdx.z;
-  const int ix0 = 4 * ox0 - 4, iy0 = 4 * oy0 - 3;  // frame coordinates of the aligned patch origin (shared column c <-> frame column ix0 + 1 + c)
+  const int ix0 = 4 * ox0 - 4, iy0 = 4 * oy0 - 3;  // frame coordinates of the patch origin (16-byte aligned columns)
 
-  for (int i = tid; i < (6 + 36) * 64; i += kThreads) w_s[i] = a.wfrag[i];
-  if (tid < 48) b_s[tid] = a.bias[tid];
+  // All global loads of a thread are issued before the first dependent store (the patch is 7 16-byte loads per
+  // thread: issued one by one they serialise 7 DRAM latencies, measured 28 % of all stall samples).
+  constexpr int kWVec = (6 + 36) * 64 / 4, kWIters = (kWVec + kThreads - 1) / kThreads;
+  uint4 wv[kWIters];
+#pragma unroll
+  for (int it = 0; it < kWIters; ++it) {
+    const int i = tid + it * kThreads;
+    wv[it] = i < kWVec ? reinterpret_cast<const uint4 *>(a.wfrag)[i] : make_uint4(0u, 0u, 0u, 0u);
+  }
   // ---- frame patch -> shared fp32 (zero outside the frame) ----
   const TIn *img = reinterpret_cast<const TIn *>(a.in) + (long long)n * 3 * a.ih * a.iw;
-  for (int i = tid; i < 3 * kInH * (kInW / 4); i += kThreads) {
-    const int c = i / (kInH * (kInW / 4)), r = (i / (kInW / 4)) % kInH, j = i % (kInW / 4);
+  constexpr int kVecPerRow = kInW / 4, kPatchVec = 3 * kInH * kVecPerRow, kPIters = (kPatchVec + kThreads - 1) / kThreads;
+  float pv[kPIters][4];
+  const bool vec_ok = (a.iw & 3) == 0;
+#pragma unroll
+  for (int it = 0; it < kPIters; ++it) {
+    const int i = tid + it * kThreads;
+    const int c = i / (kInH * kVecPerRow), r = (i / kVecPerRow) % kInH, j = i % kVecPerRow;
     const int iy = iy0 + r, ix = ix0 + 4 * j;
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (iy >= 0 && iy < a.ih) {
+    pv[it][0] = pv[it][1] = pv[it][2] = pv[it][3] = 0.f;
+    if (i < kPatchVec && iy >= 0 && iy < a.ih) {
       const TIn *src = img + ((long long)c * a.ih + iy) * a.iw + ix;
-      if (ix >= 0 && ix + 3 < a.iw && (a.iw & 3) == 0) {
+      if (vec_ok && ix >= 0 && ix + 3 < a.iw) {
         if (sizeof(TIn) == 4) {
           const float4 q = *reinterpret_cast<const float4 *>(src);
-          v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+          pv[it][0] = q.x; pv[it][1] = q.y; pv[it][2] = q.z; pv[it][3] = q.w;
         } else {
           const uchar4 q = *reinterpret_cast<const uchar4 *>(src);
-          v[0] = __fdiv_rn((float)q.x, 255.f); v[1] = __fdiv_rn((float)q.y, 255.f);
-          v[2] = __fdiv_rn((float)q.z, 255.f); v[3] = __fdiv_rn((float)q.w, 255.f);
+          pv[it][0] = (float)q.x; pv[it][1] = (float)q.y; pv[it][2] = (float)q.z; pv[it][3] = (float)q.w;
         }
       } else {
 #pragma unroll
         for (int e = 0; e < 4; ++e)
-          if (ix + e >= 0 && ix + e < a.iw) v[e] = sizeof(TIn) == 4 ? (float)src[e] : __fdiv_rn((float)src[e], 255.f);
+          if (ix + e >= 0 && ix + e < a.iw) pv[it][e] = (float)src[e];
       }
     }
-    float *dst = in_s + (c * kInH + r) * kInW;
+  }
+  if (tid < 48) b_s[tid] = a.bias[tid];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {  // shared column = loaded column - 1 (so that tap pairs are 8-byte aligned); the
-      const int cs = 4 * j + e - 1;  // wrapped element lands in the padding column 67
-      dst[cs < 0 ? kInW - 1 : cs] = v[e];
+  for (int it = 0; it < kWIters; ++it) {
+    const int i = tid + it * kThreads;
+    if (i < kWVec) reinterpret_cast<uint4 *>(w_s)[i] = wv[it];
+  }
+#pragma unroll
+  for (int it = 0; it < kPIters; ++it) {
+    const int i = tid + it * kThreads;
+    if (i >= kPatchVec) continue;
+    uint32_t h[2], l[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      float2 v = make_float2(pv[it][2 * e], pv[it][2 * e + 1]);
+      if (sizeof(TIn) == 1) v = make_float2(__fdiv_rn(v.x, 255.f), __fdiv_rn(v.y, 255.f));
+      split_bf16(v, h[e], l[e]);
     }
+    reinterpret_cast<uint2 *>(hi_s)[i] = make_uint2(h[0], h[1]);  // i enumerates (c, r, 4-column group) = the plane layout
+    reinterpret_cast<uint2 *>(lo_s)[i] = make_uint2(l[0], l[1]);
   }
   __syncthreads();
 
@@ -108,7 +135,7 @@ __global__ void __launch_bounds__(kThreads) stem_fused_kernel(StemArgs a) {
       }
     // this thread's two (ci, ky) combinations per k-step and its column slot
     int off0[3], off2[3];
-    const int kx = 2 * (t & 1);
+    const int kx = 2 * (t & 1);  // slot pair (-1, 0) or (1, 2) = patch columns 2x + kx, 2x + kx + 1
 #pragma unroll
     for (int s = 0; s < 3; ++s) {
       const int c0 = min(4 * s + (t >> 1), 8), c2 = min(4 * s + 2 + (t >> 1), 8);  // combos >= 9 carry zero weights
@@ -120,17 +147,17 @@ __global__ void __launch_bounds__(kThreads) stem_fused_kernel(StemArgs a) {
     for (int seg = warp; seg < kSegs; seg += kThreads / 32) {
       const int p0 = min(seg * 16 + g, kL0Px - 1), p1 = min(seg * 16 + g + 8, kL0Px - 1);
       const int y0 = p0 / kL0W, x0 = p0 % kL0W, y1 = p1 / kL0W, x1 = p1 % kL0W;
-      const float *r0 = in_s + 2 * y0 * kInW + 2 * x0, *r1 = in_s + 2 * y1 * kInW + 2 * x1;
+      const int r0 = 2 * y0 * kInW + 2 * x0, r1 = 2 * y1 * kInW + 2 * x1;
       float acc[2][4];
 #pragma unroll
       for (int j = 0; j < 2; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
 #pragma unroll
       for (int s = 0; s < 3; ++s) {
         uint32_t hi[4], lo[4];
-        split_bf16(*reinterpret_cast<const float2 *>(r0 + off0[s]), hi[0], lo[0]);
-        split_bf16(*reinterpret_cast<const float2 *>(r1 + off0[s]), hi[1], lo[1]);
-        split_bf16(*reinterpret_cast<const float2 *>(r0 + off2[s]), hi[2], lo[2]);
-        split_bf16(*reinterpret_cast<const float2 *>(r1 + off2[s]), hi[3], lo[3]);
+        hi[0] = *reinterpret_cast<const uint32_t *>(hi_s + r0 + off0[s]); lo[0] = *reinterpret_cast<const uint32_t *>(lo_s + r0 + off0[s]);
+        hi[1] = *reinterpret_cast<const uint32_t *>(hi_s + r1 + off0[s]); lo[1] = *reinterpret_cast<const uint32_t *>(lo_s + r1 + off0[s]);
+        hi[2] = *reinterpret_cast<const uint32_t *>(hi_s + r0 + off2[s]); lo[2] = *reinterpret_cast<const uint32_t *>(lo_s + r0 + off2[s]);
+        hi[3] = *reinterpret_cast<const uint32_t *>(hi_s + r1 + off2[s]); lo[3] = *reinterpret_cast<const uint32_t *>(lo_s + r1 + off2[s]);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           mma16816(acc[j], hi, bf[s][j][0], bf[s][j][1]);
@@ -229,9 +256,9 @@ bool stem_fused_supported(int c0, int c1, int ih, int iw, int out_pitch, int out
 void stem_fused_pack(const float *w0, const float *b0, const float *w1, const float *b1, std::vector<uint32_t> &frags,
                      std::vector<float> &bias) {
   frags.clear();
-  pack_frags(frags, 3, 2, [&](int k, int n) {  // k = (ci * 3 + ky) * 4 + slot
-    const int combo = k / 4, kx = k % 4;
-    return (combo < 9 && kx < 3) ? w0[((size_t)n * 3 + combo / 3) * 9 + (combo % 3) * 3 + kx] : 0.f;
+  pack_frags(frags, 3, 2, [&](int k, int n) {  // k = (ci * 3 + ky) * 4 + slot, slot <-> kx = slot - 1
+    const int combo = k / 4, kx = k % 4 - 1;
+    return (combo < 9 && kx >= 0) ? w0[((size_t)n * 3 + combo / 3) * 9 + (combo % 3) * 3 + kx] : 0.f;
   });
   pack_frags(frags, 9, 4, [&](int k, int n) {  // k = tap * 16 + ci
     return w1[((size_t)n * 16 + k % 16) * 9 + k / 16];
@@ -242,7 +269,7 @@ void stem_fused_pack(const float *w0, const float *b0, const float *w1, const fl
 }
 
 int stem_fused_launch(const StemArgs &a, cudaStream_t s) {
-  const size_t smem = (size_t)3 * kInH * kInW * 4 + (size_t)(kL0Px + 16) * kL0Pitch * 2 + (6 + 36) * 64 * 4 + 48 * 4;
+  const size_t smem = (size_t)2 * 3 * kInH * kInW * 2 + (size_t)(kL0Px + 19) * kL0Pitch * 2 + (6 + 36) * 64 * 4 + 48 * 4;
   static bool attr = false;
   if (!attr) {
     UYD_CUDA(cudaFuncSetAttribute(stem_fused_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
