@@ -3,9 +3,11 @@
 // Pipeline (Ultralytics non_max_suppression + torchvision.ops.nms, SURVEY.md A.3/A.4;
 // reference call sites train.py:396-405, eval.py:32):
 //   1. nms_key_kernel     : per anchor best class / score, conf filter, 64-bit sort key
-//                           (image | ~score bits | anchor) -> ties resolve to the lower anchor
+//                           (image | descending-score code | anchor) -> ties resolve to the lower anchor
 //   2. cub radix sort     : one sort over the whole batch; image segments come out contiguous,
-//                           each in stable score-descending order
+//                           each in stable score-descending order.  Keys are produced in anchor order
+//                           and the LSD radix sort is stable, so only the (image, score) bits are sorted:
+//                           5 passes instead of 8 when conf_thr >= 0 (31-bit code of a positive score)
 //   3. nms_gather_kernel  : top max_nms candidates per image -> xyxy, class-offset boxes
 //   4. nms_greedy_kernel  : one CTA per image.  Candidates are consumed in chunks of 512:
 //                           (a) every candidate is tested against the boxes kept so far,
@@ -86,6 +88,9 @@ Layout carve(void *ws, int batch, int anchors) {
 }
 
 // y: [batch, 4+nc, A].  One thread per (image, anchor).
+// POS: every candidate score is a positive float (conf_thr >= 0): code = 0x7FFFFFFF - bits (31 bits, image at
+// bit 53); otherwise code = order-preserving map of the signed float, complemented (32 bits, image at bit 54).
+template <bool POS>
 __global__ void __launch_bounds__(256) nms_key_kernel(const float *__restrict__ y, int batch, int nc, int A, float thr,
                                                       uint64_t *__restrict__ keys, int *__restrict__ count) {
   const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
@@ -102,8 +107,17 @@ __global__ void __launch_bounds__(256) nms_key_kernel(const float *__restrict__ 
       if (v > best) best = v;  // first maximum wins
     }
     ok = best > thr;
-    keys[t] = ok ? (((uint64_t)b << kImageShift) | ((uint64_t)(~__float_as_uint(best)) << kScoreShift) | (uint64_t)a)
-                 : kInvalidKey;
+    uint64_t key = kInvalidKey;
+    if (ok) {
+      const uint32_t bits = __float_as_uint(best);
+      if (POS) {
+        key = ((uint64_t)b << (kImageShift - 1)) | ((uint64_t)(0x7FFFFFFFu - bits) << kScoreShift) | (uint64_t)a;
+      } else {  // ascending-order code of a signed float, complemented for descending order
+        const uint32_t asc = (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);
+        key = ((uint64_t)b << kImageShift) | ((uint64_t)(~asc) << kScoreShift) | (uint64_t)a;
+      }
+    }
+    keys[t] = key;
   }
   const unsigned m = __ballot_sync(0xffffffffu, ok);
   if (m) {  // per-image counts: one atomic per warp (plus stragglers across an image boundary)
@@ -403,11 +417,17 @@ extern "C" int uyd_nms(uyd_ctx *ctx, const float *y, int batch, int nc, int anch
   if ((double)thr_f > iou_thr) thr_f = nextafterf(thr_f, -INFINITY);
 
   UYD_CUDA(cudaMemsetAsync(L.count, 0, (size_t)batch * 4, s));
-  nms_key_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(y, batch, nc, anchors, conf_thr, L.keys_in, L.count);
+  const bool pos = conf_thr >= 0.f;  // NaN-safe: a NaN threshold selects nothing either way
+  if (pos) nms_key_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(y, batch, nc, anchors, conf_thr, L.keys_in, L.count);
+  else nms_key_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(y, batch, nc, anchors, conf_thr, L.keys_in, L.count);
   UYD_CUDA(cudaGetLastError());
   nms_scan_kernel<<<1, 32, 0, s>>>(L.count, L.offset, batch);
   size_t tmp = L.cub_bytes;
-  UYD_CUDA(cub::DeviceRadixSort::SortKeys(L.cub_tmp, tmp, L.keys_in, L.keys_out, (int)total, 0, 64, s));
+  // keys arrive in anchor order and the sort is stable: the anchor bits need no pass
+  int image_bits = 1;
+  while ((1 << image_bits) < batch) ++image_bits;
+  const int end_bit = (pos ? kImageShift - 1 : kImageShift) + image_bits;
+  UYD_CUDA(cub::DeviceRadixSort::SortKeys(L.cub_tmp, tmp, L.keys_in, L.keys_out, (int)total, kScoreShift, end_bit, s));
   dim3 ggrid((unsigned)ceil_div(max_nms, 256), (unsigned)batch);
   nms_gather_kernel<<<ggrid, 256, 0, s>>>(y, nc, anchors, max_nms, max_wh, L.keys_out, L);
   UYD_CUDA(cudaGetLastError());
