@@ -100,10 +100,16 @@ typedef struct uyd_conv_s8 {
   int in_buf, in_coff, out_buf, out_coff;
   int cin, cout, k, stride, relu;
   float out_scale;
-  int impl, reserved;
+  int impl;
+  int depthwise;           /* 1: groups == cin == cout (weight [c][1][k][k])                              */
+  int res_buf, res_coff;   /* bf16 residual slice added (fp32) AFTER the activation, res_buf = -1: none */
 } uyd_conv_s8;
 int uyd_plan_add_conv_s8(uyd_plan *plan, const uyd_conv_s8 *desc, const int8_t *weight_q, const float *mult,
                          const float *bias);
+
+/* Input quantiser of a QuantConv2d (qat.py:109-124): q = clamp(rne(x * scale), -127, 127), scale = 127 / amax,
+ * from a bf16 slice into a slice of a UYD_S8 buffer of the same extent (C % 4 == 0). */
+int uyd_plan_add_quantize(uyd_plan *plan, int in_buf, int in_coff, int out_buf, int out_coff, int c, float scale);
 
 /* Fused C3k block (Ultralytics C3k with two 3x3 bottlenecks; the interior of every C3k2 of the
  * YAML graph): y = cv3(cat(m1(m0(cv1 x)), cv2 x)), all seven Conv+BN+ReLU layers and both
@@ -196,6 +202,11 @@ int uyd_plan_op_info(uyd_plan *plan, int op, char *text, size_t text_len, double
  * class scores), A = sum of H_l*W_l, levels concatenated in head order. */
 int uyd_plan_run_decode(uyd_plan *plan, float *y, int batch, uyd_stream stream);
 
+/* INT8 graphs: the DFL projection conv (frozen arange(16) weights) is a QuantConv2d like every other conv
+ * (train.py:725): amax_in > 0 makes uyd_plan_run_decode quantise the softmax probabilities with 127 / amax_in
+ * and the weights with 127 / 15; 0 switches it off. */
+int uyd_plan_set_dfl_quant(uyd_plan *plan, float amax_in);
+
 /* Optional: raw heads as the reference returns them, NCHW fp32 [batch, no, H_l, W_l]. */
 int uyd_plan_export_head_nchw(uyd_plan *plan, int level, float *out, int batch, uyd_stream stream);
 
@@ -253,6 +264,10 @@ int uyd_nms_detections(uyd_ctx *ctx, const uyd_detection *dets, const int *cell_
                        const int *d_count, int cap, float iou_thr, void *workspace,
                        size_t workspace_bytes, uyd_detection *out, int *d_out_count,
                        uyd_stream stream);
+
+/* max |x| over the first `batch` images of a bf16 slice, as the bit pattern of a non-negative float OR-ed into
+ * *d_bits with atomicMax (caller zeroes it): max calibration of the static input scales (qat.py:129-220). */
+int uyd_plan_slice_absmax(uyd_plan *plan, int buf, int coff, int c, int batch, unsigned int *d_bits, uyd_stream stream);
 
 /* Plain device-to-device copy on `stream` (lets a host binding without a CUDA runtime of
  * its own read plan buffers into memory it owns). */

@@ -49,11 +49,11 @@ def fold_multiplier(amax_x: float, amax_w: float, gamma=None, beta=None, mean=No
 
 
 def conv_int8(qx: np.ndarray, qw: np.ndarray, mult: np.ndarray, bias: np.ndarray, stride: int = 1, relu: bool = True,
-              out_scale: float | None = None):
-    """qx [N,C,H,W] int8, qw [Co,Ci,k,k] int8 -> (acc int32 [N,Co,OH,OW], y fp32, q_y int8 or None)."""
+              out_scale: float | None = None, groups: int = 1):
+    """qx [N,C,H,W] int8, qw [Co,Ci/g,k,k] int8 -> (acc int32 [N,Co,OH,OW], y fp32, q_y int8 or None)."""
     k = qw.shape[2]
     acc = F.conv2d(torch.from_numpy(qx.astype(np.float64)), torch.from_numpy(qw.astype(np.float64)), stride=stride,
-                   padding=k // 2).numpy()
+                   padding=k // 2, groups=groups).numpy()
     acc = np.rint(acc).astype(np.int64)
     assert np.abs(acc).max() < 2 ** 31
     acc32 = acc.astype(np.int32)

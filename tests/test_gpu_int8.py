@@ -90,3 +90,90 @@ def test_int8_accumulator_beyond_2_pow_24_rounds_like_numpy():
     p.run_no_input(B)
     torch.cuda.synchronize()
     assert p.read(dst, B).cpu().numpy().tobytes() == y.tobytes()
+
+
+def test_quantize_op_and_residual_and_depthwise_are_bit_exact():
+    """The pieces the INT8 network adds to the single conv: the input quantiser (bf16 -> int8), the
+    residual add after the activation (tensor-core and dp4a kernels) and the depth-wise int8 conv."""
+    import unina_yolo_dla_b200 as uyd
+    from unina_yolo_dla_b200._lib import IMPL_DIRECT, IMPL_TC, UYD_BF16, UYD_S8
+    from oracle import quant as oq
+    from oracle.quant_graph import bf16
+
+    rng = np.random.default_rng(3)
+    B, H, W = 2, 24, 40
+    for cin, cout, k, impl, dw in ((64, 64, 3, IMPL_TC, False), (32, 32, 1, IMPL_TC, False), (8, 8, 3, IMPL_DIRECT, False),
+                                   (4, 4, 3, IMPL_DIRECT, False), (32, 32, 3, IMPL_DIRECT, True), (128, 128, 3, IMPL_DIRECT, True)):
+        x = bf16(torch.from_numpy(rng.normal(0, 1, (B, cin, H, W)).astype(np.float32)))
+        res = bf16(torch.from_numpy(rng.normal(0, 1, (B, cout, H, W)).astype(np.float32)))
+        w = (rng.normal(0, 1, (cout, 1 if dw else cin, k, k)) / np.sqrt((1 if dw else cin) * k * k)).astype(np.float32)
+        ax, aw = float(x.abs().max()), float(np.abs(w).max())
+        qx, qw = oq.quantize(x.numpy(), ax), oq.quantize(w, aw)
+        mult, bias = oq.fold_multiplier(ax, aw, rng.uniform(0.8, 1.2, cout), rng.uniform(-0.1, 0.1, cout),
+                                        rng.normal(0, 0.2, cout), rng.uniform(0.8, 1.2, cout), eps=1e-3)
+        _, y, _ = oq.conv_int8(qx, qw, mult, bias, 1, relu=True, groups=cin if dw else 1)
+        use_res = not dw
+        want = bf16(torch.from_numpy(y) + res) if use_res else bf16(torch.from_numpy(y))
+        p = uyd.Plan(0, B)
+        src = p.buffer(H, W, cin + 8).sub(8, cin)            # bf16 activation in a channel slice
+        q = p.buffer(H, W, cin, UYD_S8)
+        dst = p.buffer(H, W, cout)
+        rs = p.buffer(H, W, cout + 16).sub(16, cout)
+        p.quantize(src, q, float(oq.scale_of(ax)))
+        p.conv_s8(q, dst, qw, mult, bias, k, 1, relu=True, impl=impl, depthwise=dw, res=rs if use_res else None)
+        p.finalize()
+        p.write(src, x)
+        p.write(rs, res)
+        p.run_no_input(B)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(p.read(q, B).cpu().numpy(), qx)
+        assert torch.equal(p.read(dst, B).cpu(), want), (cin, cout, k, dw)
+
+
+def test_int8_network_is_bit_exact_from_the_last_float_layer():
+    """BASELINE config 3: the whole INT8 graph (static max-calibrated scales, model.0-2 float) reproduces the
+    integer reference byte for byte on the raw head outputs, given the tensor the float layers produce; the
+    decoded prediction (DFL projection quantised too) agrees within the exp() tolerance and NMS on it is exact."""
+    import unina_yolo_dla_b200 as uyd
+    from oracle import init as oi
+    from oracle import postproc as pp
+    from oracle import yolo_graph as yg
+    from oracle.quant_graph import Int8Graph
+
+    m = uyd.UninaYoloB200.from_yaml().init_synthetic(seed=0).cuda()
+    x = oi.seeded_frames(2, 320, seed=11).cuda()
+    m.calibrate_cls_bias(x, 500, 0.25)
+    amax = m.calibrate_int8(x)
+    # 157 convs (the stem reads the frame and stays float) + the DFL projection
+    assert len(amax) == 158 and "model.0.conv" not in amax and "model.20.dfl.conv" in amax and m.quant is not None
+    y, raws = m(x)
+    torch.cuda.synchronize()
+    p = m.plan_for(x)
+    n_s8 = sum(1 for i in range(p.launches) if p.op_info(i)[0].startswith("conv_s8"))
+    assert n_s8 == 158 - 2 - 16                               # every conv outside model.0, model.1 and model.2 (16 convs)
+    l2 = p.read(p.layer_outputs[2], 2).cpu()
+    ref = yg.DetectionModel(yg.default_yaml_path())
+    ref.load_state_dict({k: v.cpu() for k, v in m.state_dict().items()}, strict=True)
+    ref.eval()
+    g = Int8Graph(ref, amax)
+    want = g.forward_from({2: l2})
+    for a, b in zip(raws, want):
+        assert a.shape == b.shape and a.cpu().numpy().tobytes() == b.numpy().tobytes()
+    y_ref = g.decode(ref.model[-1], want, "model.20.dfl.conv")
+    assert float((y.cpu()[:, :4] - y_ref[:, :4]).abs().max()) < 0.6     # one quantisation step of a probability ~ 0.5 px at stride 16
+    assert float((y.cpu()[:, 4:] - y_ref[:, 4:]).abs().max()) < 2e-6
+    det, cnt, idx = m.nms(y, 0.25, 0.7, 300, return_index=True)
+    wdet, widx = pp.non_max_suppression(y.cpu().numpy(), 0.25, 0.7, 300, return_index=True)
+    for b in range(2):
+        n = int(cnt[b])
+        assert n == len(wdet[b]) > 0 and np.array_equal(idx[b, :n].cpu().numpy(), widx[b])
+    # the INT8 prediction stays close to the bf16 one (sanity of the scales, not a parity claim)
+    m.set_quantization(None)
+    y_f = m(x, raw_heads=False)
+    assert float((y.cpu()[:, 4:] - y_f.cpu()[:, 4:]).abs().max()) < 0.25
+    # a QAT checkpoint (reference schema + _amax buffers) switches the INT8 path on again
+    sd = dict(m.state_dict())
+    sd.update({k: v for k, v in uyd.UninaYoloB200.from_yaml().set_quantization(amax).quant_state_dict().items()})
+    m2 = uyd.UninaYoloB200.from_yaml()
+    m2.load_state_dict(sd)
+    assert m2.quant is not None and m2.quant.amax.keys() == amax.keys()

@@ -26,7 +26,7 @@ class ConvDesc(C.Structure):
 class ConvS8Desc(C.Structure):
     _fields_ = [("in_buf", C.c_int), ("in_coff", C.c_int), ("out_buf", C.c_int), ("out_coff", C.c_int), ("cin", C.c_int),
                 ("cout", C.c_int), ("k", C.c_int), ("stride", C.c_int), ("relu", C.c_int), ("out_scale", C.c_float),
-                ("impl", C.c_int), ("reserved", C.c_int)]
+                ("impl", C.c_int), ("depthwise", C.c_int), ("res_buf", C.c_int), ("res_coff", C.c_int)]
 
 
 class C3kDesc(C.Structure):
@@ -62,6 +62,8 @@ SIGNATURES = {
     "uyd_plan_add_conv_s8": (C.c_int, [C.c_void_p, C.POINTER(ConvS8Desc), C.c_void_p, C.c_void_p, C.c_void_p]),
     "uyd_plan_add_c3k": (C.c_int, [C.c_void_p, C.POINTER(C3kDesc), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "uyd_plan_add_cls_branch": (C.c_int, [C.c_void_p, C.POINTER(ClsBranchDesc), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "uyd_plan_add_quantize": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]),
+    "uyd_plan_slice_absmax": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "uyd_plan_add_stem2": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "uyd_plan_add_chain": (C.c_int, [C.c_void_p, C.POINTER(ChainDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),
@@ -82,6 +84,7 @@ SIGNATURES = {
     "uyd_plan_op_info": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_double),
                                    C.POINTER(C.c_double)]),
     "uyd_plan_run_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "uyd_plan_set_dfl_quant": (C.c_int, [C.c_void_p, C.c_float]),
     "uyd_plan_export_head_nchw": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "uyd_decode_dfl": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                  C.c_void_p, C.c_int, C.c_int, C.c_void_p]),

@@ -100,7 +100,7 @@ struct uyd_ctx {
   int sm_count = 0;
 };
 
-enum OpKind { OP_CONV = 0, OP_SPPF = 1, OP_UPSAMPLE = 2, OP_CONV_S8 = 3, OP_C3K = 4, OP_CLS = 5, OP_CHAIN = 6, OP_STEM2 = 7 };
+enum OpKind { OP_CONV = 0, OP_SPPF = 1, OP_UPSAMPLE = 2, OP_CONV_S8 = 3, OP_C3K = 4, OP_CLS = 5, OP_CHAIN = 6, OP_STEM2 = 7, OP_QUANT = 8 };
 
 struct Op {
   OpKind kind;
@@ -136,6 +136,7 @@ struct uyd_plan {
   std::vector<Op> ops;
   std::vector<int> heads, head_strides;
   int reg_max = 16, nc = 0;
+  float dfl_amax = 0.f;                // > 0: the DFL projection runs as a QuantConv2d (uyd_plan_set_dfl_quant)
   int in_c = 0, in_h = 0, in_w = 0;  // network input extent (derived from the first conv)
   size_t bytes = 0;
   void *arena = nullptr;
@@ -293,11 +294,19 @@ extern "C" int uyd_plan_add_conv_s8(uyd_plan *plan, const uyd_conv_s8 *d, const 
   Op op;
   op.kind = OP_CONV_S8;
   op.conv.in_buf = d->in_buf; op.conv.in_coff = d->in_coff; op.conv.out_buf = d->out_buf; op.conv.out_coff = d->out_coff;
-  op.conv.res_buf = -1; op.conv.cin = d->cin; op.conv.cout = d->cout; op.conv.k = d->k; op.conv.stride = d->stride;
+  op.conv.res_buf = d->res_buf; op.conv.res_coff = d->res_coff; op.conv.depthwise = d->depthwise;
+  op.conv.cin = d->cin; op.conv.cout = d->cout; op.conv.k = d->k; op.conv.stride = d->stride;
   op.conv.relu = d->relu;
+  UYD_REQUIRE(!d->depthwise || (d->cin == d->cout && d->res_buf < 0), UYD_E_ARG, "conv_s8: depth-wise needs cin == cout, no residual");
+  if (d->res_buf >= 0) {
+    if ((e = check_slice(plan, d->res_buf, d->res_coff, d->cout, "conv_s8 residual"))) return e;
+    const Buffer &rb = plan->bufs[d->res_buf];
+    UYD_REQUIRE(rb.h == ob.h && rb.w == ob.w && rb.dtype == UYD_BF16, UYD_E_ARG, "conv_s8 residual must match the output extent (bf16)");
+  }
   op.out_scale = d->out_scale;
   op.out_kind = ob.dtype == UYD_S8 ? 2 : (ob.dtype == UYD_F32 ? 1 : 0);
-  const bool tc_ok = tc_supported_s8(d->cin, d->cout, d->k, d->stride, ib.c, d->in_coff, ob.c, d->out_coff, (int)ob.elem_bytes());
+  bool tc_ok = !d->depthwise && tc_supported_s8(d->cin, d->cout, d->k, d->stride, ib.c, d->in_coff, ob.c, d->out_coff, (int)ob.elem_bytes());
+  if (tc_ok && d->res_buf >= 0 && (d->cout % 16 || plan->bufs[d->res_buf].c % 8 || d->res_coff % 8)) tc_ok = false;
   if (d->impl == UYD_IMPL_TC) {
     UYD_REQUIRE(tc_ok, UYD_E_UNSUPPORTED, "conv_s8 %d->%d k%d s%d cannot run on the tensor-core path", d->cin, d->cout, d->k, d->stride);
     op.use_tc = true;
@@ -307,6 +316,9 @@ extern "C" int uyd_plan_add_conv_s8(uyd_plan *plan, const uyd_conv_s8 *d, const 
   if (op.use_tc) {
     op.w_host.resize(tc_weight_bytes_s8(d->cin, d->cout, d->k));
     tc_pack_weights_s8(d->cin, d->cout, d->k, weight_q, op.w_host.data());
+  } else if (d->depthwise) {
+    op.w_host.resize((size_t)d->cin * d->k * d->k);
+    direct_pack_weights_s8_dw(d->cin, d->k, weight_q, op.w_host.data());
   } else {
     op.w_host.resize(direct_weight_bytes_s8(d->cin, d->cout, d->k));
     direct_pack_weights_s8(d->cin, d->cout, d->k, weight_q, op.w_host.data());
@@ -441,6 +453,32 @@ extern "C" int uyd_plan_add_stem2(uyd_plan *plan, int out_buf, int out_coff, con
   return UYD_OK;
 }
 
+extern "C" int uyd_plan_add_quantize(uyd_plan *plan, int in_buf, int in_coff, int out_buf, int out_coff, int c, float scale) {
+  UYD_REQUIRE(plan && !plan->finalized, UYD_E_STATE, "plan missing or finalized");
+  int e;
+  if ((e = check_slice(plan, in_buf, in_coff, c, "quantize input"))) return e;
+  if ((e = check_slice(plan, out_buf, out_coff, c, "quantize output"))) return e;
+  const Buffer &a = plan->bufs[in_buf], &b = plan->bufs[out_buf];
+  UYD_REQUIRE(a.dtype == UYD_BF16 && b.dtype == UYD_S8 && a.h == b.h && a.w == b.w, UYD_E_ARG, "quantize: bf16 -> int8 buffers of equal extent");
+  UYD_REQUIRE(c % 4 == 0 && a.c % 4 == 0 && in_coff % 4 == 0 && b.c % 4 == 0 && out_coff % 4 == 0 && scale > 0.f, UYD_E_UNSUPPORTED,
+              "quantize: channel counts / offsets must be multiples of 4 and scale positive");
+  Op op;
+  op.kind = OP_QUANT;
+  op.buf = in_buf; op.coff = in_coff; op.c = c; op.out_buf = out_buf; op.out_coff = out_coff; op.out_scale = scale;
+  plan->ops.push_back(std::move(op));
+  return UYD_OK;
+}
+
+extern "C" int uyd_plan_slice_absmax(uyd_plan *plan, int buf, int coff, int c, int batch, unsigned int *d_bits, uyd_stream stream) {
+  UYD_REQUIRE(plan && plan->finalized && d_bits, UYD_E_STATE, "uyd_plan_slice_absmax: plan not finalized / NULL output");
+  int e;
+  if ((e = check_slice(plan, buf, coff, c, "absmax"))) return e;
+  const Buffer &b = plan->bufs[buf];
+  UYD_REQUIRE(b.dtype == UYD_BF16 && batch > 0 && batch <= plan->max_batch, UYD_E_ARG, "absmax: bf16 slice, batch within the plan");
+  return absmax_launch((const __nv_bfloat16 *)((char *)b.ptr + (size_t)coff * 2), b.c, (long long)batch * b.h * b.w, c, d_bits,
+                       (cudaStream_t)stream);
+}
+
 extern "C" int uyd_plan_add_sppf_pool(uyd_plan *plan, int buf, int coff, int c) {
   UYD_REQUIRE(plan && !plan->finalized, UYD_E_STATE, "plan missing or finalized");
   int e;
@@ -557,9 +595,10 @@ extern "C" int uyd_plan_finalize(uyd_plan *plan) {
         const uyd_conv &d = o.conv;
         const Buffer &ib = plan->bufs[d.in_buf], &ob = plan->bufs[d.out_buf];
         o.tc = tc_new();
+        const void *res = d.res_buf >= 0 ? slice_ptr(plan, d.res_buf, d.res_coff) : nullptr;
         int e = tc_prepare(o.tc, d, slice_ptr(plan, d.in_buf, d.in_coff), ib.c, ib.h, ib.w, plan->max_batch,
-                           slice_ptr(plan, d.out_buf, d.out_coff), ob.c, 0, nullptr, 0, o.w_dev, o.b_dev, halo_fallback ? 2 : -1,
-                           bo_mode, stages, 1, o.m_dev, o.out_scale, o.out_kind, halo_pitch);
+                           slice_ptr(plan, d.out_buf, d.out_coff), ob.c, 0, res, d.res_buf >= 0 ? plan->bufs[d.res_buf].c : 0, o.w_dev,
+                           o.b_dev, halo_fallback ? 2 : -1, bo_mode, stages, 1, o.m_dev, o.out_scale, o.out_kind, halo_pitch);
         if (e) return e;
       }
       continue;
@@ -652,8 +691,14 @@ static int launch_op(uyd_plan *plan, const Op &o, const void *x, int x_kind, int
         a.n = batch; a.in = slice_ptr(plan, d.in_buf, d.in_coff); a.ih = ib.h; a.iw = ib.w; a.in_pitch = ib.c;
         a.out = slice_ptr(plan, d.out_buf, d.out_coff); a.oh = ob.h; a.ow = ob.w; a.out_pitch = ob.c;
         a.w = o.w_dev; a.bias = o.b_dev; a.cin = d.cin; a.cout = d.cout; a.k = d.k; a.stride = d.stride; a.relu = d.relu;
-        e = direct_conv_s8_launch(a, o.m_dev, o.out_scale, o.out_kind, s);
+        if (d.res_buf >= 0) { a.res = slice_ptr(plan, d.res_buf, d.res_coff); a.res_pitch = plan->bufs[d.res_buf].c; }
+        e = d.depthwise ? direct_conv_s8_dw_launch(a, o.m_dev, o.out_scale, o.out_kind, s)
+                        : direct_conv_s8_launch(a, o.m_dev, o.out_scale, o.out_kind, s);
       }
+    } else if (o.kind == OP_QUANT) {
+      const Buffer &ib = plan->bufs[o.buf], &ob = plan->bufs[o.out_buf];
+      e = quantize_s8_launch((const __nv_bfloat16 *)slice_ptr(plan, o.buf, o.coff), ib.c, (int8_t *)slice_ptr(plan, o.out_buf, o.out_coff),
+                             ob.c, (long long)batch * ib.h * ib.w, o.c, o.out_scale, s);
     } else if (o.kind == OP_SPPF) {
       const Buffer &b = plan->bufs[o.buf];
       e = sppf_pool_launch((__nv_bfloat16 *)slice_ptr(plan, o.buf, o.coff), batch, b.h, b.w, b.c, o.c, s);
@@ -765,10 +810,14 @@ extern "C" int uyd_plan_op_info(uyd_plan *plan, int op, char *text, size_t text_
     const int ih = d.in_buf < 0 ? plan->in_h : plan->bufs[d.in_buf].h, iw = d.in_buf < 0 ? plan->in_w : plan->bufs[d.in_buf].w;
     const double macs = (double)ob.h * ob.w * d.cout * d.k * d.k * (d.depthwise ? 1 : d.cin);
     fl = 2 * macs;
-    by = (double)ih * iw * d.cin * (d.in_buf < 0 ? 4 : 2) + (double)ob.h * ob.w * d.cout * ob.elem_bytes() +
+    by = (double)ih * iw * d.cin * (d.in_buf < 0 ? 4 : (o.kind == OP_CONV_S8 ? 1 : 2)) + (double)ob.h * ob.w * d.cout * ob.elem_bytes() +
          (d.res_buf >= 0 ? (double)ob.h * ob.w * d.cout * 2 : 0);
-    snprintf(text, text_len, "conv %d->%d k%d s%d%s %dx%d %s%s%s", d.cin, d.cout, d.k, d.stride, d.depthwise ? " dw" : "", ob.h,
-             ob.w, o.use_tc ? "tc:" : "direct", o.use_tc ? tc_mode_name(o.tc) : "", d.res_buf >= 0 ? " +res" : "");
+    snprintf(text, text_len, "conv%s %d->%d k%d s%d%s %dx%d %s%s%s", o.kind == OP_CONV_S8 ? "_s8" : "", d.cin, d.cout, d.k, d.stride,
+             d.depthwise ? " dw" : "", ob.h, ob.w, o.use_tc ? "tc:" : "direct", o.use_tc ? tc_mode_name(o.tc) : "", d.res_buf >= 0 ? " +res" : "");
+  } else if (o.kind == OP_QUANT) {
+    const Buffer &b = plan->bufs[o.buf];
+    by = (double)b.h * b.w * o.c * 3;
+    snprintf(text, text_len, "quantize c%d %dx%d bf16->s8", o.c, b.h, b.w);
   } else if (o.kind == OP_STEM2) {
     const Buffer &b = plan->bufs[o.out_buf];
     fl = 2.0 * (4.0 * b.h * b.w * 16 * 27 + (double)b.h * b.w * 32 * 144);
@@ -819,10 +868,16 @@ extern "C" int uyd_plan_run_decode(uyd_plan *plan, float *y, int batch, uyd_stre
   for (size_t i = 0; i < plan->heads.size(); ++i) {
     const Buffer &b = plan->bufs[plan->heads[i]];
     int e = decode_dfl_launch((const float *)b.ptr, batch, b.h, b.w, plan->reg_max, plan->nc, (float)plan->head_strides[i], y,
-                              a_total, a_off, (cudaStream_t)stream);
+                              a_total, a_off, (cudaStream_t)stream, plan->dfl_amax);
     if (e) return e;
     a_off += b.h * b.w;
   }
+  return UYD_OK;
+}
+
+extern "C" int uyd_plan_set_dfl_quant(uyd_plan *plan, float amax_in) {
+  UYD_REQUIRE(plan && amax_in >= 0.f, UYD_E_ARG, "uyd_plan_set_dfl_quant: bad arguments");
+  plan->dfl_amax = amax_in;
   return UYD_OK;
 }
 

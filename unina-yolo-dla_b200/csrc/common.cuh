@@ -70,6 +70,11 @@ int direct_conv_launch(const ConvArgs &a, bool depthwise, cudaStream_t s);
 size_t direct_weight_bytes_s8(int cin, int cout, int k);
 void direct_pack_weights_s8(int cin, int cout, int k, const int8_t *w, void *dst_host);
 int direct_conv_s8_launch(const ConvArgs &a, const float *mult, float out_scale, int out_kind, cudaStream_t s);
+void direct_pack_weights_s8_dw(int c, int k, const int8_t *w, void *dst_host);
+int direct_conv_s8_dw_launch(const ConvArgs &a, const float *mult, float out_scale, int out_kind, cudaStream_t s);
+int quantize_s8_launch(const __nv_bfloat16 *in, int in_pitch, int8_t *out, int out_pitch, long long npix, int c, float scale,
+                       cudaStream_t s);
+int absmax_launch(const __nv_bfloat16 *in, int in_pitch, long long npix, int c, unsigned int *out_bits, cudaStream_t s);
 
 // pool_upsample.cu
 int sppf_pool_launch(__nv_bfloat16 *base, int n, int h, int w, int pitch, int c, cudaStream_t s);
@@ -79,6 +84,6 @@ int nhwc_to_nchw_f32_launch(const float *in, float *out, int n, int h, int w, in
 
 // decode.cu
 int decode_dfl_launch(const float *head, int batch, int h, int w, int reg_max, int nc, float stride,
-                      float *y, int a_total, int a_off, cudaStream_t s);
+                      float *y, int a_total, int a_off, cudaStream_t s, float dfl_amax = 0.f);
 
 }  // namespace uyd

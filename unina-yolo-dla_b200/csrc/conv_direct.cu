@@ -469,12 +469,25 @@ int direct_conv_launch(const ConvArgs &a, bool depthwise, cudaStream_t s) {
 
 }  // namespace uyd
 
-// ---- INT8 (dp4a) reference path ---------------------------------------------------------------
+// ---- INT8 (dp4a) path ----------------------------------------------------------------------------
 // Same requant epilogue as the tensor-core int8 kernel (oracle/quant.py): exact int32
-// accumulation, y = float(acc) * m_c + b_c (separate RN multiply / add), ReLU, then bf16 / fp32 /
-// int8 re-quantised with out_scale.  weights: int8 [tap][co][ci].
+// accumulation, y = float(acc) * m_c + b_c (separate RN multiply / add), ReLU, + residual (bf16,
+// added in fp32 after the activation), then bf16 / fp32 / int8 re-quantised with out_scale.
+// weights: int8 [tap][co][ci]  (depth-wise: [tap][c]).
 namespace uyd {
 namespace {
+
+__device__ __forceinline__ void store_s8_result(const ConvArgs &a, long long o, float y, float out_scale, int out_kind) {
+  if (out_kind == 2) {
+    const int q = max(-127, min(127, __float2int_rn(__fmul_rn(y, out_scale))));
+    reinterpret_cast<int8_t *>(a.out)[o] = (int8_t)q;
+  } else if (out_kind == 1) {
+    reinterpret_cast<float *>(a.out)[o] = y;
+  } else {
+    reinterpret_cast<__nv_bfloat16 *>(a.out)[o] = __float2bfloat16_rn(y);
+  }
+}
+
 __global__ void __launch_bounds__(128) conv_s8_direct_kernel(ConvArgs a, const float *mult, float out_scale, int out_kind) {
   const long long npix = (long long)a.n * a.oh * a.ow;
   const long long p = (long long)blockIdx.x * 128 + threadIdx.x;
@@ -496,7 +509,8 @@ __global__ void __launch_bounds__(128) conv_s8_direct_kernel(ConvArgs a, const f
       for (int c4 = 0; c4 < a.cin / 4; ++c4) {
         const int x = px[c4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[j] = __dp4a(x, reinterpret_cast<const int *>(wt + (size_t)j * a.cin)[c4], acc[j]);
+        for (int j = 0; j < 4; ++j)
+          if (co0 + j < a.cout) acc[j] = __dp4a(x, reinterpret_cast<const int *>(wt + (size_t)j * a.cin)[c4], acc[j]);
       }
     }
   }
@@ -506,16 +520,82 @@ __global__ void __launch_bounds__(128) conv_s8_direct_kernel(ConvArgs a, const f
     if (co0 + j >= a.cout) break;
     float y = __fadd_rn(__fmul_rn(__int2float_rn(acc[j]), mult[co0 + j]), a.bias[co0 + j]);
     if (a.relu) y = fmaxf(y, 0.f);
-    const long long o = opix * a.out_pitch + co0 + j;
-    if (out_kind == 2) {
-      const int q = max(-127, min(127, __float2int_rn(__fmul_rn(y, out_scale))));
-      reinterpret_cast<int8_t *>(a.out)[o] = (int8_t)q;
-    } else if (out_kind == 1) {
-      reinterpret_cast<float *>(a.out)[o] = y;
-    } else {
-      reinterpret_cast<__nv_bfloat16 *>(a.out)[o] = __float2bfloat16_rn(y);
+    if (a.res) y = __fadd_rn(y, __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(a.res)[opix * a.res_pitch + co0 + j]));
+    store_s8_result(a, opix * a.out_pitch + co0 + j, y, out_scale, out_kind);
+  }
+}
+
+// depth-wise 3x3 (any stride), thread = pixel x 4 channels
+__global__ void __launch_bounds__(128) conv_s8_dw_kernel(ConvArgs a, const float *mult, float out_scale, int out_kind) {
+  const int cg = a.cin / 4;
+  const long long total = (long long)a.n * a.oh * a.ow * cg;
+  const long long t = (long long)blockIdx.x * 128 + threadIdx.x;
+  if (t >= total) return;
+  const int c0 = (int)(t % cg) * 4;
+  const long long p = t / cg;
+  const int ox = (int)(p % a.ow), oy = (int)((p / a.ow) % a.oh), n = (int)(p / ((long long)a.ow * a.oh));
+  const int pad = a.k / 2;
+  const int8_t *in = reinterpret_cast<const int8_t *>(a.in);
+  const int8_t *w = reinterpret_cast<const int8_t *>(a.w);
+  int acc[4] = {0, 0, 0, 0};
+  for (int ky = 0; ky < a.k; ++ky) {
+    const int iy = oy * a.stride + ky - pad;
+    if (iy < 0 || iy >= a.ih) continue;
+    for (int kx = 0; kx < a.k; ++kx) {
+      const int ix = ox * a.stride + kx - pad;
+      if (ix < 0 || ix >= a.iw) continue;
+      const char4 x = *reinterpret_cast<const char4 *>(in + (((long long)n * a.ih + iy) * a.iw + ix) * a.in_pitch + c0);
+      const char4 wv = *reinterpret_cast<const char4 *>(w + (size_t)(ky * a.k + kx) * a.cin + c0);
+      acc[0] += (int)x.x * wv.x; acc[1] += (int)x.y * wv.y; acc[2] += (int)x.z * wv.z; acc[3] += (int)x.w * wv.w;
     }
   }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float y = __fadd_rn(__fmul_rn(__int2float_rn(acc[j]), mult[c0 + j]), a.bias[c0 + j]);
+    if (a.relu) y = fmaxf(y, 0.f);
+    store_s8_result(a, p * a.out_pitch + c0 + j, y, out_scale, out_kind);
+  }
+}
+
+// q = clamp(rne(x * scale), -127, 127): the input quantiser of a QuantConv2d (qat.py:109-124), one
+// thread = 4 channels of one pixel (the narrowest slices of the graph are 4 channels wide).
+__global__ void __launch_bounds__(256) quantize_s8_kernel(const __nv_bfloat16 *__restrict__ in, int in_pitch,
+                                                          int8_t *__restrict__ out, int out_pitch, long long npix, int c,
+                                                          float scale) {
+  const int cg = c / 4;
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (t >= npix * cg) return;
+  const int c0 = (int)(t % cg) * 4;
+  const long long p = t / cg;
+  const uint2 raw = *reinterpret_cast<const uint2 *>(in + p * in_pitch + c0);
+  const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&raw);
+  uint32_t w = 0u;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    const int q0 = max(-127, min(127, __float2int_rn(__fmul_rn(f.x, scale))));
+    const int q1 = max(-127, min(127, __float2int_rn(__fmul_rn(f.y, scale))));
+    w |= ((uint32_t)(q0 & 0xFF) << (16 * i)) | ((uint32_t)(q1 & 0xFF) << (16 * i + 8));
+  }
+  *reinterpret_cast<uint32_t *>(out + p * out_pitch + c0) = w;
+}
+
+// |x| maximum of a bf16 slice (max calibration of the input quantisers, qat.py:129-220): the bit pattern of a
+// non-negative float orders like an unsigned integer, so one atomicMax per block suffices.
+__global__ void __launch_bounds__(256) absmax_kernel(const __nv_bfloat16 *__restrict__ in, int in_pitch, long long npix, int c,
+                                                     unsigned int *__restrict__ out_bits) {
+  const int cg = c / 4;
+  float m = 0.f;
+  for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < npix * cg; t += (long long)gridDim.x * 256) {
+    const int c0 = (int)(t % cg) * 4;
+    const uint2 raw = *reinterpret_cast<const uint2 *>(in + (t / cg) * in_pitch + c0);
+    const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&raw);
+    const float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]);
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(f0.x), fabsf(f0.y)), fmaxf(fabsf(f1.x), fabsf(f1.y))));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out_bits, __float_as_uint(m));
 }
 }  // namespace
 
@@ -529,12 +609,46 @@ void direct_pack_weights_s8(int cin, int cout, int k, const int8_t *w, void *dst
       for (int ci = 0; ci < cin; ++ci) o[((size_t)t * cout + co) * cin + ci] = w[((size_t)co * cin + ci) * taps + t];
 }
 
+// depth-wise: [c][1][k][k] -> [tap][c]
+void direct_pack_weights_s8_dw(int c, int k, const int8_t *w, void *dst_host) {
+  int8_t *o = reinterpret_cast<int8_t *>(dst_host);
+  const int taps = k * k;
+  for (int t = 0; t < taps; ++t)
+    for (int ch = 0; ch < c; ++ch) o[(size_t)t * c + ch] = w[(size_t)ch * taps + t];
+}
+
 int direct_conv_s8_launch(const ConvArgs &a, const float *mult, float out_scale, int out_kind, cudaStream_t s) {
   UYD_REQUIRE(a.cin % 4 == 0 && a.in_pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(a.in) & 3) == 0, UYD_E_UNSUPPORTED,
               "int8 direct conv needs cin %% 4 == 0 and 4-byte aligned input slices");
   const long long npix = (long long)a.n * a.oh * a.ow;
   dim3 grid((unsigned)((npix + 127) / 128), (unsigned)ceil_div(a.cout, 4));
   conv_s8_direct_kernel<<<grid, 128, 0, s>>>(a, mult, out_scale, out_kind);
+  return (int)cudaGetLastError();
+}
+
+int direct_conv_s8_dw_launch(const ConvArgs &a, const float *mult, float out_scale, int out_kind, cudaStream_t s) {
+  UYD_REQUIRE(a.cin == a.cout && a.cin % 4 == 0 && a.in_pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(a.in) & 3) == 0 && !a.res,
+              UYD_E_UNSUPPORTED, "int8 depth-wise conv needs C %% 4 == 0, 4-byte aligned slices and no residual");
+  const long long total = (long long)a.n * a.oh * a.ow * (a.cin / 4);
+  conv_s8_dw_kernel<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(a, mult, out_scale, out_kind);
+  return (int)cudaGetLastError();
+}
+
+int quantize_s8_launch(const __nv_bfloat16 *in, int in_pitch, int8_t *out, int out_pitch, long long npix, int c, float scale,
+                       cudaStream_t s) {
+  UYD_REQUIRE(c % 4 == 0 && in_pitch % 4 == 0 && out_pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 7) == 0 &&
+                  (reinterpret_cast<uintptr_t>(out) & 3) == 0, UYD_E_UNSUPPORTED, "quantize: C %% 4 == 0 and aligned slices");
+  const long long total = npix * (c / 4);
+  quantize_s8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, in_pitch, out, out_pitch, npix, c, scale);
+  return (int)cudaGetLastError();
+}
+
+int absmax_launch(const __nv_bfloat16 *in, int in_pitch, long long npix, int c, unsigned int *out_bits, cudaStream_t s) {
+  UYD_REQUIRE(c % 4 == 0 && in_pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 7) == 0, UYD_E_UNSUPPORTED,
+              "absmax: C %% 4 == 0 and 8-byte aligned slices");
+  long long blocks = (npix * (c / 4) + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  absmax_kernel<<<(unsigned)blocks, 256, 0, s>>>(in, in_pitch, npix, c, out_bits);
   return (int)cudaGetLastError();
 }
 }  // namespace uyd

@@ -178,12 +178,24 @@ __device__ __forceinline__ void epilogue_chunk_staged(const uint32_t (&raw)[16],
 // INT8 path: y = float(acc) * m_c + b_c with separate round-to-nearest multiply and add (the
 // oracle's integer reference, oracle/quant.py), ReLU, then bf16 / fp32 / re-quantised int8.
 __device__ __forceinline__ void epilogue_chunk_i8_staged(const uint32_t (&raw)[16], const float *bias_s, const float *mult_s,
-                                                         int c0, const TcParams &p, unsigned char *srow) {
+                                                         int c0, long long pix, const TcParams &p, unsigned char *srow) {
   float v[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const float x = __fadd_rn(__fmul_rn(__int2float_rn((int)raw[i]), mult_s[c0 + i]), bias_s[c0 + i]);
     v[i] = p.relu ? fmaxf(x, 0.f) : x;
+  }
+  if (p.res && pix >= 0) {  // residual (bf16) added in fp32 after the activation; Cout % 16 == 0 (checked on the host)
+    const __nv_bfloat16 *rp = p.res + pix * p.res_pitch + c0;
+    const uint4 r0 = *reinterpret_cast<const uint4 *>(rp), r1 = *reinterpret_cast<const uint4 *>(rp + 8);
+    const __nv_bfloat162 *h0 = reinterpret_cast<const __nv_bfloat162 *>(&r0);
+    const __nv_bfloat162 *h1 = reinterpret_cast<const __nv_bfloat162 *>(&r1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f0 = __bfloat1622float2(h0[i]), f1 = __bfloat1622float2(h1[i]);
+      v[2 * i] = __fadd_rn(v[2 * i], f0.x); v[2 * i + 1] = __fadd_rn(v[2 * i + 1], f0.y);
+      v[8 + 2 * i] = __fadd_rn(v[8 + 2 * i], f1.x); v[8 + 2 * i + 1] = __fadd_rn(v[8 + 2 * i + 1], f1.y);
+    }
   }
   if (p.out_kind == 2) {
     uint32_t w[4];
@@ -413,7 +425,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
         if (staged) {
           if (c * 16 < p.cout) {
-            if (I8) epilogue_chunk_i8_staged(cur, bias_s, mult_s, c * 16, p, srow);
+            if (I8) epilogue_chunk_i8_staged(cur, bias_s, mult_s, c * 16, pix, p, srow);
             else epilogue_chunk_staged(cur, bias_s, c * 16, pix, p, srow);
           }
         } else if (pix >= 0 && c * 16 < p.cout) {
@@ -557,7 +569,7 @@ int tc_prepare(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int i
   const int es = i8 ? 1 : 2;
   const int CB = i8 ? pick_cb_s8(d.cin) : pick_cb(d.cin);
   UYD_REQUIRE(CB, UYD_E_UNSUPPORTED, "conv_tc: cin %d is not a multiple of %d", d.cin, i8 ? 32 : 16);
-  UYD_REQUIRE(!i8 || !res_base, UYD_E_UNSUPPORTED, "conv_tc: the int8 path has no residual input");
+  UYD_REQUIRE(!i8 || !res_base || d.cout % 16 == 0, UYD_E_UNSUPPORTED, "conv_tc int8: a residual input needs Cout %% 16 == 0");
   p.i8 = i8;
   p.mult = mult_dev;
   p.out_scale = out_scale;

@@ -14,9 +14,13 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __ex
 
 // head: [batch, H, W, 4*16 + nc] fp32.  y: [batch, 4+nc, a_total].
 template <int REG_MAX>
+// q_scale > 0: the DFL projection conv is a QuantConv2d as well (every nn.Conv2d is wrapped, train.py:725):
+// probabilities are quantised with scale q_scale = 127 / amax_p, the arange(16) weights with 127 / 15, and the
+// expectation is the integer dot product times dq = (amax_p / 127) * (15 / 127).
 __global__ void __launch_bounds__(kThreads) decode_dfl_kernel(const float *__restrict__ head, long long n_anchor_total,
                                                               int hw, int w, int nc, float stride,
-                                                              float *__restrict__ y, int a_total, int a_off) {
+                                                              float *__restrict__ y, int a_total, int a_off, float q_scale,
+                                                              float dq) {
   const int no = 4 * REG_MAX + nc;
   const int lane = threadIdx.x & 31;
   const int side = lane & 3;
@@ -41,7 +45,17 @@ __global__ void __launch_bounds__(kThreads) decode_dfl_kernel(const float *__res
     s += e;
     ws = fmaf((float)i, e, ws);
   }
-  const float d = ws / s;  // expected distance of this side, in cells
+  float d = ws / s;  // expected distance of this side, in cells
+  if (q_scale > 0.f) {
+    int acc = 0;
+#pragma unroll
+    for (int i = 0; i < REG_MAX; ++i) {
+      const int qp = max(-127, min(127, __float2int_rn(__fmul_rn(__fdiv_rn(__expf(v[i] - m), s), q_scale))));
+      const int qw = __float2int_rn(__fmul_rn((float)i, __fdiv_rn(127.f, (float)(REG_MAX - 1))));
+      acc += qp * qw;
+    }
+    d = __fmul_rn((float)acc, dq);
+  }
   const unsigned full = 0xffffffffu;
   const int base = lane & ~3;
   const float dl = __shfl_sync(full, d, base + 0);
@@ -111,14 +125,19 @@ __global__ void __launch_bounds__(kThreads) decode_tlbr_kernel(const float *__re
 }  // namespace
 
 int decode_dfl_launch(const float *head, int batch, int h, int w, int reg_max, int nc, float stride, float *y,
-                      int a_total, int a_off, cudaStream_t s) {
+                      int a_total, int a_off, cudaStream_t s, float dfl_amax) {
   UYD_REQUIRE(reg_max == 16, UYD_E_UNSUPPORTED, "DFL decode is built for reg_max == 16 (got %d)", reg_max);
   UYD_REQUIRE(((4 * reg_max + nc) % 4) == 0 && (reinterpret_cast<uintptr_t>(head) & 15) == 0, UYD_E_UNSUPPORTED,
               "head rows must be 16-byte aligned (4*reg_max+nc multiple of 4)");
   const long long n = (long long)batch * h * w;
   const long long warps = (n + 7) / 8;
   const long long blocks = (warps * 32 + kThreads - 1) / kThreads;
-  decode_dfl_kernel<16><<<(unsigned)blocks, kThreads, 0, s>>>(head, n, h * w, w, nc, stride, y, a_total, a_off);
+  float q_scale = 0.f, dq = 0.f;
+  if (dfl_amax > 0.f) {
+    q_scale = 127.f / dfl_amax;
+    dq = (dfl_amax / 127.f) * (15.f / 127.f);
+  }
+  decode_dfl_kernel<16><<<(unsigned)blocks, kThreads, 0, s>>>(head, n, h * w, w, nc, stride, y, a_total, a_off, q_scale, dq);
   return (int)cudaGetLastError();
 }
 
@@ -128,7 +147,7 @@ extern "C" int uyd_decode_dfl(uyd_ctx *ctx, const float *head, int batch, int h,
                               float stride, float *y, int a_total, int a_off, uyd_stream stream) {
   (void)ctx;
   UYD_REQUIRE(head && y && batch > 0 && h > 0 && w > 0, UYD_E_ARG, "uyd_decode_dfl: bad arguments");
-  return uyd::decode_dfl_launch(head, batch, h, w, reg_max, nc, stride, y, a_total, a_off, (cudaStream_t)stream);
+  return uyd::decode_dfl_launch(head, batch, h, w, reg_max, nc, stride, y, a_total, a_off, (cudaStream_t)stream, 0.f);
 }
 
 extern "C" int uyd_decode_tlbr(uyd_ctx *ctx, const float *d_cls, const float *d_reg, uyd_detection *dets, int *cell_idx,

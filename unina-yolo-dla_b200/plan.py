@@ -87,19 +87,35 @@ class Plan:
         return dst
 
     def conv_s8(self, src: Slice, dst: Slice, weight_q: np.ndarray, mult: np.ndarray, bias: np.ndarray, k: int,
-                stride: int = 1, relu: bool = True, out_scale: float = 0.0, impl: int = IMPL_AUTO) -> Slice:
-        """INT8 conv: src in a UYD_S8 buffer, weight_q int8 [cout][cin][k][k]; the dtype of dst's buffer
-        selects the epilogue (int8 re-quantised with out_scale, or fp32 / bf16)."""
+                stride: int = 1, relu: bool = True, out_scale: float = 0.0, impl: int = IMPL_AUTO, depthwise: bool = False,
+                res: Slice | None = None) -> Slice:
+        """INT8 conv: src in a UYD_S8 buffer, weight_q int8 [cout][cin][k][k] (depth-wise: [c][1][k][k]); the dtype
+        of dst's buffer selects the epilogue (int8 re-quantised with out_scale, or fp32 / bf16); ``res`` is a bf16
+        slice added after the activation."""
         weight_q = np.ascontiguousarray(weight_q, dtype=np.int8)
         mult = np.ascontiguousarray(mult, dtype=np.float32)
         bias = np.ascontiguousarray(bias, dtype=np.float32)
-        cout, cin = weight_q.shape[0], weight_q.shape[1]
+        cout = weight_q.shape[0]
+        cin = cout if depthwise else weight_q.shape[1]
         assert dst.c == cout and src.c == cin and mult.shape == (cout,) and bias.shape == (cout,)
-        d = ConvS8Desc(src.buf, src.coff, dst.buf, dst.coff, cin, cout, k, stride, int(relu), float(out_scale), impl, 0)
+        d = ConvS8Desc(src.buf, src.coff, dst.buf, dst.coff, cin, cout, k, stride, int(relu), float(out_scale), impl,
+                       int(depthwise), res.buf if res else -1, res.coff if res else 0)
         check(_lib.lib().uyd_plan_add_conv_s8(self.handle, C.byref(d), weight_q.ctypes.data_as(C.c_void_p),
                                               mult.ctypes.data_as(C.c_void_p), bias.ctypes.data_as(C.c_void_p)),
               "uyd_plan_add_conv_s8")
         return dst
+
+    def quantize(self, src: Slice, dst: Slice, scale: float) -> Slice:
+        """bf16 slice -> int8 slice, q = clamp(rne(x * scale), -127, 127) (uyd_plan_add_quantize)."""
+        assert src.c == dst.c
+        check(_lib.lib().uyd_plan_add_quantize(self.handle, src.buf, src.coff, dst.buf, dst.coff, src.c, float(scale)),
+              "uyd_plan_add_quantize")
+        return dst
+
+    def slice_absmax(self, s: Slice, batch: int, out_bits: torch.Tensor) -> None:
+        """atomicMax of the float bits of max|x| over a bf16 slice into ``out_bits`` (uint32/int32 device scalar)."""
+        check(_lib.lib().uyd_plan_slice_absmax(self.handle, s.buf, s.coff, s.c, batch, C.c_void_p(out_bits.data_ptr()),
+                                               self._stream()), "uyd_plan_slice_absmax")
 
     C3K_WIDTHS = (8, 16, 32)
 

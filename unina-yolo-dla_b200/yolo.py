@@ -22,7 +22,8 @@ import torch.nn as nn
 import yaml
 
 from . import _lib
-from ._lib import CHAIN_DFL, CHAIN_PW3, CHAIN_STORE, UYD_BF16, UYD_F32, check
+from ._lib import CHAIN_DFL, CHAIN_PW3, CHAIN_STORE, UYD_BF16, UYD_F32, UYD_S8, check
+from . import quant as Q
 from .plan import NETWORK_INPUT, Plan, Slice, fold_bn
 
 DEFAULT_YAML = Path(__file__).resolve().parent / "unina-yolo-dla-m.yaml"
@@ -51,9 +52,13 @@ class Conv(nn.Module):
             (src.h + 2 * (self.k // 2) - self.k) // self.s + 1, (src.w + 2 * (self.k // 2) - self.k) // self.s + 1)
         if dst is None:
             dst = p.buffer(oh, ow, self.c2)
-        w, b = fold_bn(self.conv, self.bn)
         dw = self.g > 1
         assert not dw or self.g == self.c1 == self.c2, "only depth-wise grouped convs occur in this graph"
+        name = getattr(self.conv, "_uyd_name", "")
+        _record_input(p, name, src)
+        if _quantized(p, name) and src.buf >= 0:
+            return emit_quant_conv(p, name, self.conv, self.bn, src, dst, relu=True, res=res)
+        w, b = fold_bn(self.conv, self.bn)
         return p.conv(src, dst, w, b, self.k, self.s, relu=True, depthwise=dw, res=res)
 
 
@@ -61,8 +66,39 @@ def DWConv(c1, c2, k=1, s=1):
     return Conv(c1, c2, k, s, g=gcd(c1, c2))
 
 
+def _quantized(p, name: str) -> bool:
+    q = getattr(p, "quant", None)
+    return q is not None and q.covers(name)
+
+
+def _record_input(p, name: str, src: Slice) -> None:
+    rec = getattr(p, "conv_inputs", None)
+    if rec is not None and name:
+        rec[name] = src
+
+
+def emit_quant_conv(p: Plan, name: str, conv: nn.Conv2d, bn, src: Slice, dst: Slice, relu: bool, res: Slice | None = None) -> Slice:
+    """QuantConv2d as an integer convolution (quant.py): input quantiser -> int8 conv -> requant epilogue."""
+    ax, aw = p.quant.amax[name]
+    scale = float(Q.scale_of(ax))
+    cache = p.__dict__.setdefault("_qcache", {})
+    key = (src.buf, src.coff, src.c, scale)
+    qsrc = cache.get(key)
+    if qsrc is None:  # one int8 copy per (activation slice, scale): convs sharing both share the copy
+        qsrc = p.quantize(src, p.buffer(src.h, src.w, src.c, UYD_S8), scale)
+        cache[key] = qsrc
+    qw = Q.quantize_weights(conv.weight, aw)
+    mult, bias = Q.requant_params(ax, aw, bn, conv.bias)
+    dw = conv.groups > 1
+    return p.conv_s8(qsrc, dst, qw, mult, bias, conv.kernel_size[0], conv.stride[0], relu=relu, depthwise=dw, res=res)
+
+
 def emit_plain_conv(p: Plan, conv: nn.Conv2d, src: Slice, dst: Slice) -> Slice:
     """Final biased 1x1 convs of the heads (no BN, no activation)."""
+    name = getattr(conv, "_uyd_name", "")
+    _record_input(p, name, src)
+    if _quantized(p, name):
+        return emit_quant_conv(p, name, conv, None, src, dst, relu=False)
     w = conv.weight.detach().float().cpu().numpy()
     b = conv.bias.detach().float().cpu().numpy()
     return p.conv(src, dst, w, b, conv.kernel_size[0], conv.stride[0], relu=False)
@@ -95,7 +131,8 @@ class C3k(nn.Module):
 
     def emit(self, p, src, dst=None):
         fusable = (len(self.m) == 2 and all(b.add and b.cv1.k == 3 and b.cv2.k == 3 for b in self.m)
-                   and self.cv3.c2 == src.c and 2 * self.c_ == src.c and os.environ.get("UYD_NO_C3K_FUSION", "0") != "1")
+                   and self.cv3.c2 == src.c and 2 * self.c_ == src.c and os.environ.get("UYD_NO_C3K_FUSION", "0") != "1"
+                   and getattr(p, "fusion", True) and not _quantized(p, getattr(self.cv1.conv, "_uyd_name", "")))
         if fusable:
             dst = dst or p.buffer(src.h, src.w, self.cv3.c2)
             if p.c3k_supported(src, dst) and p.shapes[src.buf][2] % 8 == 0 and p.shapes[dst.buf][2] % 8 == 0:
@@ -196,7 +233,8 @@ class Detect(nn.Module):
         Class branch: [DWConv3x3 -> Conv1x1] -> [DWConv3x3 -> Conv1x1 -> Conv2d 1x1 (-> sigmoid)].
         ``fused``: the chained kernels write the decoded prediction y directly and no raw head
         tensor exists; otherwise they write the raw logits into fp32 head buffers."""
-        use_chain = os.environ.get("UYD_NO_CHAIN", "0") != "1"
+        use_chain = (os.environ.get("UYD_NO_CHAIN", "0") != "1" and getattr(p, "fusion", True)
+                     and not _quantized(p, getattr(self.cv2[0][0].conv, "_uyd_name", "")))
         a_total = sum(f.h * f.w for f in feats)
         heads, a_off = [], 0
         wb = lambda conv: (conv.weight.detach().float().cpu().numpy(), conv.bias.detach().float().cpu().numpy())
@@ -309,9 +347,13 @@ class UninaYoloB200(nn.Module):
         det.stride = torch.tensor([float(s) for s in self._level_strides()])
         self.stride = det.stride
         det.bias_init()
+        for name, mod in self.named_modules():
+            if isinstance(mod, nn.Conv2d):
+                mod._uyd_name = name            # the key of the pytorch-quantization ``_amax`` buffers
         self._plans = {}
         self._nms_ws = {}
         self._graphs = {}
+        self.quant = None                       # quant.QuantSpec when the INT8 path is active
         self.eval()
 
     @classmethod
@@ -344,8 +386,30 @@ class UninaYoloB200(nn.Module):
         self._plans.clear()
 
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
-        out = super().load_state_dict(state_dict, strict=strict, assign=assign)
+        """Accepts the reference schema (925 entries) plus, for QAT checkpoints, the pytorch-quantization
+        ``<conv>._input_quantizer._amax`` / ``<conv>._weight_quantizer._amax`` buffers, which switch the
+        INT8 path on (qat.py:109-124)."""
+        plain, amax = Q.split_state_dict(state_dict)
+        out = super().load_state_dict(plain, strict=strict, assign=assign)
+        if amax:
+            self.set_quantization(amax)
         self.refresh()
+        return out
+
+    def set_quantization(self, amax: dict | None, float_layers=(0, 1, 2)) -> "UninaYoloB200":
+        """Switches the INT8 path on (``amax``: conv module name -> (input amax, weight amax)) or off (None).
+        Convs of ``model.{i}`` for i in ``float_layers`` stay bf16 (the reference's precision carve-out,
+        qat.py:700-753); convs without an entry stay bf16 too."""
+        self.quant = Q.QuantSpec(dict(amax), tuple(float_layers)) if amax else None
+        self.refresh()
+        return self
+
+    def quant_state_dict(self) -> dict:
+        """The ``_amax`` buffers of the active quantisation in pytorch-quantization's naming."""
+        out = {}
+        for n, (ai, aw) in (self.quant.amax if self.quant else {}).items():
+            out[n + Q.IN_SUFFIX] = torch.tensor(ai)
+            out[n + Q.W_SUFFIX] = torch.tensor(aw)
         return out
 
     def _apply(self, fn, recurse=True):
@@ -354,10 +418,17 @@ class UninaYoloB200(nn.Module):
         return super()._apply(fn, recurse)
 
     # ---- plan construction -------------------------------------------------------------
-    def _build_plan(self, device: int, max_batch: int, H: int, W: int, fused: bool = False) -> Plan:
+    def _build_plan(self, device: int, max_batch: int, H: int, W: int, fused: bool = False, fusion: bool = True,
+                    record_inputs: bool = False) -> Plan:
+        """``fusion=False`` emits one op per conv (calibration needs every conv input in HBM);
+        ``record_inputs`` keeps the input slice of every conv in ``plan.conv_inputs``."""
         p = Plan(device, max_batch)
         p.in_hw = (H, W)
         p.fused = fused
+        p.fusion = fusion
+        p.quant = self.quant
+        if record_inputs:
+            p.conv_inputs = {}
         layers = list(self.model)
         # pass 1: extents of every layer output
         shape = []
@@ -388,7 +459,7 @@ class UninaYoloB200(nn.Module):
         # pass 3: emit
         outs = []
         l0, l1 = layers[0], layers[1]
-        stem2 = (os.environ.get("UYD_NO_STEM_FUSION", "0") != "1" and isinstance(l0, Conv) and isinstance(l1, Conv)
+        stem2 = (os.environ.get("UYD_NO_STEM_FUSION", "0") != "1" and fusion and not _quantized(p, "model.1.conv") and isinstance(l0, Conv) and isinstance(l1, Conv)
                  and (l0.c1, l0.c2, l0.k, l0.s, l0.g) == (3, 16, 3, 2, 1) and (l1.c1, l1.c2, l1.k, l1.s, l1.g) == (16, 32, 3, 2, 1)
                  and l1.f == -1 and 0 not in self.save and 0 not in home and H % 4 == 0 and W % 4 == 0)
         for m in layers:
@@ -421,6 +492,10 @@ class UninaYoloB200(nn.Module):
                     p.heads = heads  # extents only: the decoded output is written by the head kernels
                 else:
                     p.set_heads(heads, [int(s) for s in m.stride.tolist()], m.reg_max, m.nc)
+                    dfl_name = getattr(m.dfl.conv, "_uyd_name", "")
+                    _record_input(p, dfl_name, Slice(-2, 0, m.reg_max, 0, 0))
+                    if _quantized(p, dfl_name):
+                        check(_lib.lib().uyd_plan_set_dfl_quant(p.handle, float(self.quant.amax[dfl_name][0])), "uyd_plan_set_dfl_quant")
                 outs.append(None)
         p.layer_outputs = outs
         return p.finalize()
@@ -502,6 +577,41 @@ class UninaYoloB200(nn.Module):
             cls[-1].bias.add_(shift)
         self.refresh()
         return shift
+
+    @torch.no_grad()
+    def calibrate_int8(self, frames: torch.Tensor, float_layers=(0, 1, 2), enable: bool = True) -> dict:
+        """Max calibration of the static INT8 scales (the reference's calibration pass, qat.py:129-220, never
+        materialises them): input amax of every conv = max |x| of its input over ``frames`` in the bf16
+        forward (one GPU reduction per conv input, uyd_plan_slice_absmax), weight amax = max |w|.  Returns
+        ``{conv name: (amax_in, amax_w)}`` and, with ``enable``, switches the INT8 path on."""
+        saved, self.quant = self.quant, None
+        try:
+            x = self._prep(frames)
+            B, _, H, W = x.shape
+            dev = x.device.index if x.device.index is not None else torch.cuda.current_device()
+            p = self._build_plan(dev, B, H, W, fused=False, fusion=False, record_inputs=True)
+            p.run(x)
+            names = [n for n, s in p.conv_inputs.items() if s.buf >= 0]
+            bits = torch.zeros(len(names), dtype=torch.int32, device=x.device)
+            for i, n in enumerate(names):
+                p.slice_absmax(p.conv_inputs[n], B, bits[i:i + 1])
+            vals = bits.view(torch.float32).cpu().tolist()
+            convs = {n: m for n, m in self.named_modules() if isinstance(m, nn.Conv2d)}
+            amax = {n: (max(v, 1e-6), float(convs[n].weight.detach().abs().max())) for n, v in zip(names, vals)}
+            det = self.model[-1]
+            dfl_name = getattr(det.dfl.conv, "_uyd_name", "")
+            if dfl_name in p.conv_inputs:  # input of the DFL projection: the softmax probabilities of the box logits
+                pm = 0.0
+                for lvl, h in enumerate(p.heads):
+                    t = torch.empty(B, h.c, h.h, h.w, dtype=torch.float32, device=x.device)
+                    p.export_head(lvl, t, B)
+                    pm = max(pm, float(t[:, :4 * det.reg_max].reshape(B, 4, det.reg_max, -1).softmax(2).max()))
+                amax[dfl_name] = (pm, float(det.reg_max - 1))
+        finally:
+            self.quant = saved
+        if enable:
+            self.set_quantization(amax, float_layers)
+        return amax
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor, raw_heads: bool = True):
