@@ -269,6 +269,29 @@ int uyd_nms_detections(uyd_ctx *ctx, const uyd_detection *dets, const int *cell_
  * *d_bits with atomicMax (caller zeroes it): max calibration of the static input scales (qat.py:129-220). */
 int uyd_plan_slice_absmax(uyd_plan *plan, int buf, int coff, int c, int batch, unsigned int *d_bits, uyd_stream stream);
 
+/* ------------------------------------------------------------------------------------
+ * Camera-frame pre-processing in front of the plan (drop-in for cuda_preprocess.h:62-84; kernels
+ * cuda_preprocess.cu:99-253): BGRA / NV12 bytes -> RGB, (x / 255 - mean) / std, planar CHW fp32.
+ * uyd_norm_params is layout-identical to NormParams (cuda_preprocess.h:38-45).  The *_batch variants
+ * process `batch` frames `frame_stride` bytes apart into [batch, 3, H, W].
+ * ---------------------------------------------------------------------------------- */
+typedef struct uyd_norm_params {
+  float mean_r, mean_g, mean_b, std_r, std_g, std_b;
+} uyd_norm_params;
+uyd_norm_params uyd_norm_params_imagenet(void); /* create_norm_params_imagenet */
+uyd_norm_params uyd_norm_params_unit(void);     /* mean 0, std 1: plain x / 255 (the Ultralytics predictor's pre-process) */
+int uyd_preprocess_bgra_resize(const uint8_t *d_input, float *d_output, int src_width, int src_height, int src_pitch,
+                               int dst_width, int dst_height, uyd_norm_params params, uyd_stream stream);
+int uyd_preprocess_bgra(const uint8_t *d_input, float *d_output, int width, int height, int pitch, uyd_norm_params params,
+                        uyd_stream stream);
+int uyd_preprocess_nv12(const uint8_t *d_y_plane, const uint8_t *d_uv_plane, float *d_output, int width, int height,
+                        int y_pitch, int uv_pitch, uyd_norm_params params, uyd_stream stream);
+int uyd_preprocess_bgra_batch(const uint8_t *d_input, float *d_output, int batch, long long frame_stride, int width,
+                              int height, int pitch, uyd_norm_params params, uyd_stream stream);
+int uyd_preprocess_bgra_resize_batch(const uint8_t *d_input, float *d_output, int batch, long long frame_stride,
+                                     int src_width, int src_height, int src_pitch, int dst_width, int dst_height,
+                                     uyd_norm_params params, uyd_stream stream);
+
 /* Plain device-to-device copy on `stream` (lets a host binding without a CUDA runtime of
  * its own read plan buffers into memory it owns). */
 int uyd_memcpy_d2d(void *dst, const void *src, size_t bytes, uyd_stream stream);

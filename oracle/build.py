@@ -4,6 +4,9 @@
 * ``oracle/_ref/libref_postprocess.so`` <- the reference's own postprocess.hpp compiled
   *where it lies* under /root/reference (only when that mount exists; the GPU box uses
   the prebuilt file that travels with the snapshot).
+* ``oracle/_ref/libref_preprocess.so``  <- the reference's own cuda_preprocess.cu compiled with nvcc for
+  sm_100a where it lies (its kernels are the parity oracle of the pre-processing row; they run on the GPU
+  box only, from the prebuilt file).
 """
 from __future__ import annotations
 
@@ -41,6 +44,22 @@ def build_ref(force: bool = False):
     return REF_SO if REF_SO.exists() else None
 
 
+REF_PRE_SRC = Path("/root/reference/unina_yolo_dla/ros2_ws/src/perception/src/cuda_preprocess.cu")
+REF_PRE_SO = HERE / "_ref" / "libref_preprocess.so"
+
+
+def build_ref_preprocess(force: bool = False):
+    """The reference's CUDA pre-processing kernels as a shared library (nvcc, sm_100a), or None."""
+    if REF_PRE_SRC.exists() and (force or _stale(REF_PRE_SO, [REF_PRE_SRC])):
+        REF_PRE_SO.parent.mkdir(exist_ok=True)
+        subprocess.check_call(
+            ["/usr/local/cuda/bin/nvcc", "-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a", "-O2",
+             f"-I{REF_INC}", str(REF_PRE_SRC), "-o", str(REF_PRE_SO), "-cudart", "static"],
+            stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return REF_PRE_SO if REF_PRE_SO.exists() else None
+
+
 if __name__ == "__main__":
+    print(build_ref_preprocess(True))
     print(build_oracle(True))
     print(build_ref(True))

@@ -1,0 +1,98 @@
+"""Pre-processing row: our kernels vs the reference's own CUDA kernels (compiled from
+/root/reference by oracle/build.py into oracle/_ref/, run here on the GPU) and vs the numpy restatement."""
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+REF_SO = Path(__file__).resolve().parents[1] / "oracle" / "_ref" / "libref_preprocess.so"
+
+
+class RefNorm(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("mean_r", "mean_g", "mean_b", "std_r", "std_g", "std_b")]
+
+
+@pytest.fixture(scope="module")
+def ref():
+    if not REF_SO.exists():
+        pytest.skip("oracle/_ref/libref_preprocess.so was not built (no /root/reference at build time)")
+    L = C.CDLL(str(REF_SO))
+    L.preprocess_bgra_resize.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, RefNorm, C.c_void_p]
+    L.preprocess_bgra.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, RefNorm, C.c_void_p]
+    L.preprocess_nv12.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, RefNorm, C.c_void_p]
+    return L
+
+
+IMAGENET = (0.485, 0.456, 0.406, 0.229, 0.224, 0.225)
+
+
+def _frames(B, H, W, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(0, 256, (B, H, W, 4), generator=g, dtype=torch.uint8)
+
+
+@pytest.mark.parametrize("H,W", [(640, 640), (96, 132), (37, 50)])
+def test_bgra_matches_reference_kernel_and_numpy(ref, H, W):
+    from unina_yolo_dla_b200 import preprocess as pre
+    from oracle import preproc as op
+
+    x = _frames(2, H, W, 1).cuda()
+    got = pre.bgra(x, pre.norm_params())
+    want = torch.empty_like(got)
+    for b in range(2):
+        assert ref.preprocess_bgra(x[b].data_ptr(), want[b].data_ptr(), W, H, W * 4, RefNorm(*IMAGENET), None) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)                                   # same expression, same compiler: bit-exact
+    assert np.allclose(op.bgra(x[1].cpu().numpy()), want[1].cpu().numpy(), rtol=0, atol=1e-6)
+    unit = pre.bgra(x)                                              # plain x / 255 feeds the YAML model
+    rgb = x[..., [2, 1, 0]].permute(0, 3, 1, 2).cpu().numpy().astype(np.float32)
+    assert np.array_equal(unit.cpu().numpy(), rgb / np.float32(255))    # IEEE division, exactly the stem's uint8 path
+
+
+@pytest.mark.parametrize("src,dst", [((720, 1280), (640, 640)), ((480, 640), (640, 640)), ((100, 75), (64, 96))])
+def test_bgra_resize_matches_reference_kernel_and_numpy(ref, src, dst):
+    from unina_yolo_dla_b200 import preprocess as pre
+    from oracle import preproc as op
+
+    (H, W), (oh, ow) = src, dst
+    x = _frames(2, H, W, 2).cuda()
+    got = pre.bgra(x, pre.norm_params(), size=(oh, ow))
+    want = torch.empty_like(got)
+    for b in range(2):
+        assert ref.preprocess_bgra_resize(x[b].data_ptr(), want[b].data_ptr(), W, H, W * 4, ow, oh, RefNorm(*IMAGENET), None) == 0
+    torch.cuda.synchronize()
+    assert float((got - want).abs().max()) <= 1e-6                  # normalised units; fma contraction only
+    assert np.allclose(op.bgra_resize(x[0].cpu().numpy(), oh, ow), want[0].cpu().numpy(), rtol=0, atol=2e-5)
+
+
+@pytest.mark.parametrize("H,W", [(64, 96), (50, 38)])
+def test_nv12_matches_reference_kernel_and_numpy(ref, H, W):
+    from unina_yolo_dla_b200 import preprocess as pre
+    from oracle import preproc as op
+
+    g = torch.Generator().manual_seed(3)
+    yp = torch.randint(0, 256, (H, W), generator=g, dtype=torch.uint8).cuda()
+    uv = torch.randint(0, 256, ((H + 1) // 2, W + (W % 2)), generator=g, dtype=torch.uint8).cuda()
+    got = pre.nv12(yp, uv, pre.norm_params())
+    want = torch.empty_like(got)
+    assert ref.preprocess_nv12(yp.data_ptr(), uv.data_ptr(), want.data_ptr(), W, H, yp.stride(0), uv.stride(0), RefNorm(*IMAGENET), None) == 0
+    torch.cuda.synchronize()
+    assert float((got - want).abs().max()) <= 1e-6
+    assert np.allclose(op.nv12(yp.cpu().numpy(), uv.cpu().numpy()), want[0].cpu().numpy(), rtol=0, atol=2e-5)
+
+
+def test_preprocessed_camera_frame_feeds_the_model():
+    """BGRA camera bytes -> preprocess (x / 255) -> predict equals predict on the equivalent uint8 NCHW frames."""
+    import unina_yolo_dla_b200 as uyd
+    from unina_yolo_dla_b200 import preprocess as pre
+
+    m = uyd.UninaYoloB200.from_yaml().init_synthetic(seed=0).cuda()
+    cam = _frames(2, 320, 320, 4).cuda()
+    rgb = cam[..., [2, 1, 0]].permute(0, 3, 1, 2).contiguous()
+    m.calibrate_cls_bias(rgb, 300, 0.25)
+    d0, c0 = m.predict_batched(pre.bgra(cam), graph=False)
+    d1, c1 = m.predict_batched(rgb, graph=False)
+    assert int(c0.sum()) > 0 and torch.equal(c0, c1) and torch.equal(d0, d1)

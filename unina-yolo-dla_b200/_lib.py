@@ -42,6 +42,11 @@ class ChainDesc(C.Structure):
                                        "out_coff", "nc", "a_total", "a_off", "y_ch0", "no")] + [("stride_px", C.c_float)]
 
 
+class NormParams(C.Structure):
+    """Layout-identical to the reference NormParams (cuda_preprocess.h:38-45)."""
+    _fields_ = [(n, C.c_float) for n in ("mean_r", "mean_g", "mean_b", "std_r", "std_g", "std_b")]
+
+
 class Detection(C.Structure):
     """Layout-identical to the reference GpuDetection (gpu_postprocess.h:27-33)."""
     _fields_ = [("x1", C.c_float), ("y1", C.c_float), ("x2", C.c_float), ("y2", C.c_float),
@@ -96,6 +101,15 @@ SIGNATURES = {
     "uyd_nms_detections_workspace_bytes": (C.c_size_t, [C.c_int]),
     "uyd_nms_detections": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p,
                                      C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "uyd_norm_params_imagenet": (NormParams, []),
+    "uyd_norm_params_unit": (NormParams, []),
+    "uyd_preprocess_bgra_resize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, NormParams, C.c_void_p]),
+    "uyd_preprocess_bgra": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, NormParams, C.c_void_p]),
+    "uyd_preprocess_nv12": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, NormParams, C.c_void_p]),
+    "uyd_preprocess_bgra_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int, NormParams,
+                                            C.c_void_p]),
+    "uyd_preprocess_bgra_resize_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                   C.c_int, NormParams, C.c_void_p]),
     "uyd_memcpy_d2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
 }
 
