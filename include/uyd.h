@@ -269,6 +269,19 @@ int uyd_nms_detections(uyd_ctx *ctx, const uyd_detection *dets, const int *cell_
  * *d_bits with atomicMax (caller zeroes it): max calibration of the static input scales (qat.py:129-220). */
 int uyd_plan_slice_absmax(uyd_plan *plan, int buf, int coff, int c, int batch, unsigned int *d_bits, uyd_stream stream);
 
+/* Batched evaluation of the detections (the consumer of the gathered [N, 6] rows):
+ *   counters[0..2] += small-object TP, FP, FN with the semantics of UninaValidator.update_metrics
+ *     (trainer.py:210-265): boxes in pixels, "small" = width and height < size_thr, a match = same class
+ *     and Ultralytics box_iou > small_iou_thr; images without a small ground truth are skipped;
+ *   scores [batch, max_det] (may be NULL) = 1 - IoU of every prediction greedily matched, in confidence
+ *     order, to the best unmatched same-class ground truth with IoU >= match_iou_thr, else -1: the
+ *     nonconformity scores of calibrate_conformal_prediction (train.py:335-470).
+ * det [batch, max_det, 6] rows (x1,y1,x2,y2,conf,cls) in confidence order with count [batch] valid rows
+ * (uyd_nms output); gt [batch, gt_max, 5] rows (cls, x1, y1, x2, y2) in pixels with gt_count [batch]. */
+int uyd_eval_update(uyd_ctx *ctx, const float *det, const int *count, int batch, int max_det, const float *gt,
+                    const int *gt_count, int gt_max, float size_thr, float small_iou_thr, float match_iou_thr,
+                    unsigned long long *counters, float *scores, uyd_stream stream);
+
 /* ------------------------------------------------------------------------------------
  * Camera-frame pre-processing in front of the plan (drop-in for cuda_preprocess.h:62-84; kernels
  * cuda_preprocess.cu:99-253): BGRA / NV12 bytes -> RGB, (x / 255 - mean) / std, planar CHW fp32.

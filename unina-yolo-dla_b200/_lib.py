@@ -110,6 +110,8 @@ SIGNATURES = {
                                             C.c_void_p]),
     "uyd_preprocess_bgra_resize_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int,
                                                    C.c_int, NormParams, C.c_void_p]),
+    "uyd_eval_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_float,
+                                  C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "uyd_memcpy_d2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
 }
 

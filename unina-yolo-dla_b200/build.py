@@ -8,7 +8,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libuyd.so"
-SOURCES = ["api.cu", "conv_direct.cu", "stem_fused.cu", "conv_tc.cu", "conv_chain.cu", "c3k_fused.cu", "pool_upsample.cu", "decode.cu", "nms.cu", "preprocess.cu"]
+SOURCES = ["api.cu", "conv_direct.cu", "stem_fused.cu", "conv_tc.cu", "conv_chain.cu", "c3k_fused.cu", "pool_upsample.cu", "decode.cu", "nms.cu", "preprocess.cu", "evalmatch.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
