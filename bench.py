@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--size", type=int, default=640)
     ap.add_argument("--cpu-sample", type=int, default=32, help="frames of the bounded CPU sample")
     ap.add_argument("--profile-out", default="", help="write the per-op table (markdown) here")
+    ap.add_argument("--int8", type=int, default=0, metavar="BATCH",
+                    help="also time the INT8 graph (static max-calibrated scales, BASELINE config 3) at this batch, e.g. 256")
     return ap.parse_args()
 
 
@@ -131,6 +133,31 @@ def cpu_baseline(model, size: int, sample: int, chunk: int = 8):
     dt = time.perf_counter() - t0
     return {"value": done / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
             "sample": f"{done} frames of the same workload in chunks of {chunk} (oracle fp32 forward + DFL decode + NMS)"}
+
+
+def bench_int8(model, batch: int, size: int, dev, steps: int):
+    """BASELINE config 3: the INT8 graph (model.0-2 float, every other conv int8 with static scales calibrated on
+    8 frames, DFL projection quantised) at `batch` frames, forward + decode + NMS, frames resident in HBM."""
+    g = torch.Generator(device=dev).manual_seed(300)
+    x = torch.rand(batch, 3, size, size, device=dev, generator=g)
+    model.calibrate_int8(x[:8])
+    plan = model.plan_for(x)
+    for _ in range(2):
+        model.predict_batched(x, CONF, IOU, MAX_DET)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        model.predict_batched(x, CONF, IOU, MAX_DET)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    n_s8 = sum(1 for i in range(plan.launches) if plan.op_info(i)[0].startswith("conv_s8"))
+    out = {"value": batch / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "batch": batch, "steps": steps, "dtype": "s8 x s8 -> s32",
+           "plan_launches": plan.launches, "int8_convs": n_s8, "activation_bytes": plan.bytes,
+           "note": "quantize ops are separate launches in this round (one int8 copy per activation slice and scale)"}
+    model.set_quantization(None)
+    return out
 
 
 def run_reference(a):
@@ -345,6 +372,8 @@ def main():
                            "note": "predict_batched on one resident frame (CUDA-graph replay), host-synchronised wall clock"},
         "clocks": sampler.summary(),
     }
+    if a.int8 > 0:
+        out["int8"] = bench_int8(model, a.int8, S, dev, max(3, a.steps // 2))
     if world == 1:
         out["cpu_baseline"] = cpu_baseline(model, S, a.cpu_sample)
     if a.profile_out:

@@ -65,3 +65,26 @@ def test_two_rank_gloo_gather_equals_single_process(tmp_path):
     det, cnt = _pack(pp.non_max_suppression(y, 0.25, 0.7, 300))
     assert torch.equal(gc, cnt) and torch.equal(gd, det)
     assert int(cnt.sum()) > 0
+
+
+def _eval_worker(rank, world, port, out_path):
+    from unina_yolo_dla_b200.evaluate import DetectionEvaluator
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ev = DetectionEvaluator(device="cpu")
+    ev.counters += torch.tensor([3 + rank, 1, 2 * rank])                      # what two shards would have counted
+    ev._scores = [torch.tensor([[0.1 * (rank + 1), -1.0, 0.3], [-1.0, 0.2, -1.0]][: 2 - rank])]
+    ev.reduce()
+    if rank == 0:
+        torch.save((ev.counters, ev.nonconformity_scores().sort().values), out_path)
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_evaluator_reduce(tmp_path):
+    """Per-rank evaluation + reduction: counters add up, the nonconformity scores of all ranks are pooled."""
+    out = tmp_path / "eval.pt"
+    mp.spawn(_eval_worker, args=(2, _free_port(), str(out)), nprocs=2, join=True)
+    counters, scores = torch.load(out)
+    assert counters.tolist() == [7, 2, 2]
+    assert torch.allclose(scores, torch.tensor([0.1, 0.2, 0.2, 0.3, 0.3]))
