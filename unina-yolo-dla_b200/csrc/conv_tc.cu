@@ -19,10 +19,11 @@
 //                         traversal stride.  Always swizzle-atom aligned; also the fallback
 //                         for HALO.
 //
-// Warp roles (192 threads, one persistent CTA per SM): warp 0 = TMA producer, warp 1 = TMEM
-// allocator + single-thread tcgen05.mma issuer, warps 2..5 = epilogue (tcgen05.ld -> bias ->
-// ReLU -> residual -> bf16/fp32 -> global).  Three mbarrier pipelines: smem full/empty,
-// TMEM full/empty (two accumulators), weights-resident.
+// Warp roles (576 threads, one persistent CTA per SM): warp 0 = TMA producer, warp 1 = TMEM
+// allocator + single-thread tcgen05.mma issuer (elect.sync), warps 2..17 = four epilogue warpgroups
+// taking tiles round-robin (tcgen05.ld -> bias -> ReLU -> residual -> bf16/fp32 -> staged, row-coalesced
+// global stores).  Three mbarrier pipelines: smem full/empty, TMEM full/empty (four accumulators),
+// weights-resident.
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -43,6 +44,7 @@ struct TcParams {
   long long total_tiles;
   int stages;
   int nacc;              // TMEM accumulator stages (nacc * N columns)
+  int ngroups;           // active epilogue warpgroups (1, 2 or 4: as many as the staging tiles leave room for)
   int halo_pitch;        // HALO: pixels per halo row in shared memory (10 = dense single TMA box, 16 = padded rows)
   int stage_pitch;       // bytes per row of the epilogue staging tile (0 = direct stores)
   int i8;                // 1: int8 operands, int32 accumulate (kind::i8), requant epilogue
@@ -66,7 +68,10 @@ struct TcParams {
 
 namespace {
 
-constexpr int kThreads = 320;  // TMA warp + MMA warp + 2 x 4 epilogue warps
+constexpr int kEpiGroups = 4;                   // epilogue warpgroups taking tiles round-robin (latency hiding: the epilogue
+                                                // of a tile is a long dependent chain: TMEM load -> math -> staging -> stores)
+constexpr int kThreads = 64 + 128 * kEpiGroups;  // TMA warp + MMA warp + kEpiGroups x 4 epilogue warps
+constexpr uint32_t kTailFixed = 1536 + 8 * 128 * kEpiGroups;  // barriers + bias + mult | row -> pixel map
 constexpr int kHaloRows = 18, kTileH = 16, kTileW = 8;
 constexpr int kMaxAcc = 4;  // TMEM accumulator stages
 
@@ -390,13 +395,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int rows_per_it = 32 / lpr;
     const long long out_row_pitch = (long long)p.out_pitch * esize;
     long long *spix = reinterpret_cast<long long *>(smem_dyn + (bar0 + 1536u - raw)) + (warp - 2) * 32;
-    unsigned char *swarp = smem_dyn + (bar0 + 3584u - raw) + (size_t)(warp - 2) * 32 * p.stage_pitch;
-    const int group = (warp - 2) >> 2;  // two epilogue warpgroups take alternate tiles
+    unsigned char *swarp = smem_dyn + (bar0 + kTailFixed - raw) + (size_t)(warp - 2) * 32 * p.stage_pitch;
+    const int group = (warp - 2) >> 2;  // the epilogue warpgroups take tiles round-robin
     unsigned char *srow = swarp + (size_t)lane * p.stage_pitch;
     int it = 0;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      if ((it & 1) != group) continue;
-      const int acc = it % nacc;  // nacc is even, so accumulator parity == group
+      if (it % p.ngroups != group) continue;  // (groups >= ngroups never match: they idle)
+      const int acc = it % nacc;  // nacc is a multiple of ngroups: an accumulator always belongs to the same group
       const uint32_t acc_phase = (uint32_t)(it / nacc) & 1u;
       long long pix;  // flattened output pixel (n, oy, ox) or -1
       if (p.mode == TC_FLAT) {
@@ -539,8 +544,8 @@ bool tc_supported_s8(int cin, int cout, int k, int stride, int in_pitch, int in_
   if (rb < 16 || rb > 512 || (rb & (rb - 1)) || (out_pitch * out_esize) % 16 || (out_coff * out_esize) % 16) return false;
   const int N = (cout + 15) / 16 * 16;
   // resident weights + two 128-row stages + staging tile must fit
-  const size_t need = (((size_t)cin * k * k * N + 1023) & ~(size_t)1023) + 2 * (size_t)128 * pick_cb_s8(cin) + 3584 +
-                      (size_t)256 * (N * out_esize + 16) + 1024;
+  const size_t need = (((size_t)cin * k * k * N + 1023) & ~(size_t)1023) + 2 * (size_t)128 * pick_cb_s8(cin) + kTailFixed +
+                      (size_t)128 * 1 * (N * out_esize + 16) + 1024;  // at least one staging group
   return need <= 227 * 1024;
 }
 
@@ -614,10 +619,16 @@ int tc_prepare(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int i
   p.stage_pitch = can_stage ? p.N * esize + 16 : 0;
   UYD_REQUIRE(!i8 || can_stage, UYD_E_UNSUPPORTED, "conv_tc int8: output rows must be a power-of-two number of 16-byte lanes");
   const size_t wres = (p.w_bytes + 1023u) & ~1023u;
-  size_t tail = 3584 + (size_t)256 * p.stage_pitch;  // barriers + bias + row->pixel map + staging
+  // as many epilogue groups as the staging tiles leave room for next to the resident weights and two stages
+  const size_t two_stages = 2 * (((size_t)(p.mode == TC_HALO ? (uint32_t)kHaloRows * p.halo_pitch * p.cb_bytes : 128u * p.cb_bytes) + 1023u) & ~(size_t)1023);
+  p.ngroups = kEpiGroups;
+  while (p.ngroups > 1 && p.stage_pitch && wres + two_stages + kTailFixed + (size_t)128 * p.ngroups * p.stage_pitch > 227 * 1024 - 1024)
+    p.ngroups >>= 1;
+  size_t tail = kTailFixed + (size_t)128 * p.ngroups * p.stage_pitch;  // barriers + bias + row->pixel map + staging
   if (!i8 && wres + 2 * (size_t)(128u * p.cb_bytes) > 227 * 1024 - 1024 - tail) {
     p.stage_pitch = 0;  // weights leave no room for the staging tile: per-thread row stores
-    tail = 3584;
+    p.ngroups = kEpiGroups;
+    tail = kTailFixed;
   }
   const size_t budget = 227 * 1024 - 1024 - tail;
   if (p.mode == TC_HALO && wres + 2 * (size_t)p.blk_bytes > budget) {  // halo blocks too big: one box per tap
