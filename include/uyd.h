@@ -76,7 +76,10 @@ typedef struct uyd_conv {
   int depthwise;           /* 1: groups == cin == cout                                     */
   int relu;                /* 1: ReLU after (folded BN) bias                               */
   int impl;                /* UYD_IMPL_*                                                   */
-  int reserved;
+  int pre_buf_p1;          /* 0: none; else 1 + id of an fp32 buffer [h/2, w/2, cout] that is added,
+                              nearest-x2 upsampled, BEFORE the activation: Upsample + Concat + 1x1 Conv is
+                              computed as up(W_a * x_low) + W_b * x_skip, the upsampled tensor and the
+                              concatenation are never written (tensor-core path only)              */
 } uyd_conv;
 
 /* weight: host fp32 [cout][cin/groups][k][k] (PyTorch layout, BN already folded);

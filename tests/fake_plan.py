@@ -23,8 +23,8 @@ class FakePlan:
         self.shapes[len(self.specs) - 1] = (h, w, c, dtype)
         return Slice(len(self.specs) - 1, 0, c, h, w)
 
-    def conv(self, src, dst, weight, bias, k, stride=1, relu=True, depthwise=False, res=None, impl=0):
-        self.ops.append(("conv", src, dst, torch.from_numpy(weight), torch.from_numpy(bias), k, stride, relu, depthwise, res))
+    def conv(self, src, dst, weight, bias, k, stride=1, relu=True, depthwise=False, res=None, impl=0, pre=None):
+        self.ops.append(("conv", src, dst, torch.as_tensor(weight).float(), torch.as_tensor(bias).float(), k, stride, relu, depthwise, res, pre))
         return dst
 
     @staticmethod
@@ -111,8 +111,10 @@ class FakePlan:
                         x1, y1, x2, y2 = ax - d[:, 0], ay - d[:, 1], ax + d[:, 2], ay + d[:, 3]
                         self.y[:, y_ch0:y_ch0 + 4, a_off:a_off + hw] = torch.stack(((x1 + x2) / 2, (y1 + y2) / 2, x2 - x1, y2 - y1), 1) * stride
             elif op[0] == "conv":
-                _, src, dst, w, b, k, stride, relu, dw, res = op
+                _, src, dst, w, b, k, stride, relu, dw, res, pre = op
                 y = F.conv2d(get(src), w, b, stride=stride, padding=k // 2, groups=w.shape[0] if dw else 1)
+                if pre is not None:
+                    y = y + F.interpolate(get(pre), scale_factor=2, mode="nearest")
                 if relu:
                     y = y.relu()
                 if res is not None:

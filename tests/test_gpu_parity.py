@@ -495,3 +495,32 @@ def test_fused_stem_matches_torch(T, H, W, u8):
     want = r(F.conv2d(t, r(w1), b1, stride=2, padding=1).relu())
     assert T.rel_err(got, want) < 6e-3
     assert float(p.read(p.buffer_slice(dst.buf, 0, 16), B).abs().max()) == 0.0   # nothing outside the slice
+
+
+@pytest.mark.parametrize("ca,cb,cout,h,w", [(64, 32, 16, 40, 40), (128, 64, 32, 24, 40), (64, 32, 16, 160, 160)])
+def test_upsample_concat_conv_fold_matches_torch(T, ca, cb, cout, h, w):
+    """Upsample(x2) + Concat + 1x1 Conv computed as relu(up(W_a a) + W_b b + bias): the half-resolution partial
+    sums stay fp32 and are added inside the tensor-core conv's epilogue."""
+    import torch.nn.functional as F
+    import unina_yolo_dla_b200 as uyd
+    from unina_yolo_dla_b200._lib import UYD_F32
+
+    g = torch.Generator().manual_seed(ca + w)
+    B = 2
+    r = T.bf16_round
+    lo, sk = torch.randn(B, ca, h // 2, w // 2, generator=g), torch.randn(B, cb, h, w, generator=g)
+    wt = torch.randn(cout, ca + cb, 1, 1, generator=g) / (ca + cb) ** 0.5
+    bias = torch.randn(cout, generator=g) * 0.1
+    p = uyd.Plan(0, B)
+    s_lo, s_sk = p.buffer(h // 2, w // 2, ca), p.buffer(h, w, cb + 16).sub(16, cb)
+    part = p.buffer(h // 2, w // 2, cout, UYD_F32)
+    dst = p.buffer(h, w, 2 * cout).sub(cout, cout)
+    p.conv(s_lo, part, wt[:, :ca].numpy(), bias.numpy() * 0, 1, 1, relu=False)
+    p.conv(s_sk, dst, wt[:, ca:].numpy(), bias.numpy(), 1, 1, relu=True, pre=part)
+    p.finalize()
+    p.write(s_lo, lo)
+    p.write(s_sk, sk)
+    p.run_no_input(B)
+    torch.cuda.synchronize()
+    want = r(F.conv2d(torch.cat((F.interpolate(r(lo), scale_factor=2, mode="nearest"), r(sk)), 1), r(wt), bias).relu())
+    assert T.rel_err(p.read(dst, B).cpu(), want) < 6e-3

@@ -42,17 +42,19 @@ def test_emitted_plan_equals_oracle_network(monkeypatch):
     # census: 158 convs (2 inside the fused stem, 19 inside the 8 chained head launches) + 1 pool cascade +
     # 2 upsamples, no concat / chunk op at all
     kinds = [o[0] for o in p.ops]
-    assert kinds.count("stem2") == 1 and kinds.count("chain") == 8 and kinds.count("conv") == 158 - 2 - 19
-    assert kinds.count("sppf") == 1 and kinds.count("up") == 2
+    assert kinds.count("stem2") == 1 and kinds.count("chain") == 8 and kinds.count("conv") == 158 - 2 - 19 + 2
+    # + 2 half-resolution partial-sum convs: both Upsample + Concat pairs are folded into the next C3k2's first conv
+    assert kinds.count("sppf") == 1 and kinds.count("up") == 0
 
 
 def test_unchained_plan_is_the_plain_conv_list(monkeypatch):
     monkeypatch.setenv("UYD_NO_CHAIN", "1")
     monkeypatch.setenv("UYD_NO_STEM_FUSION", "1")
+    monkeypatch.setenv("UYD_NO_UPSAMPLE_FOLD", "1")
     m = uyd.UninaYoloB200.from_yaml().init_synthetic(seed=3)
     p = _emit_fake(m, 1, 128, 128, monkeypatch)
     kinds = [o[0] for o in p.ops]
-    assert kinds.count("conv") == 158 and kinds.count("chain") == 0
+    assert kinds.count("conv") == 158 and kinds.count("chain") == 0 and kinds.count("up") == 2
 
 
 def test_fused_decode_plan_writes_the_oracle_prediction(monkeypatch):
@@ -131,7 +133,7 @@ def test_emitted_plan_uses_fused_c3k_at_full_resolution(monkeypatch):
     kinds = [o[0] for o in p.ops]
     # the fused stem (2 convs), 16 fused C3k blocks (7 convs each) and 8 chained head launches (19 convs)
     assert kinds.count("stem2") == 1 and kinds.count("c3k") == 16 and kinds.count("chain") == 8
-    assert kinds.count("conv") == 158 - 2 - 16 * 7 - 19
+    assert kinds.count("conv") == 158 - 2 - 16 * 7 - 19 + 2 and kinds.count("up") == 0
     bufs = p.execute(x)
     for h, r in zip(p.heads, raw_ref):
         assert torch.allclose(bufs[h.buf], r, rtol=1e-4, atol=1e-4)

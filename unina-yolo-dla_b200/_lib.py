@@ -20,7 +20,7 @@ class UydError(RuntimeError):
 class ConvDesc(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "in_buf", "in_coff", "out_buf", "out_coff", "res_buf", "res_coff", "cin", "cout",
-        "k", "stride", "depthwise", "relu", "impl", "reserved")]
+        "k", "stride", "depthwise", "relu", "impl", "pre_buf_p1")]
 
 
 class ConvS8Desc(C.Structure):

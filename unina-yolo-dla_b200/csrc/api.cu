@@ -31,6 +31,7 @@ void tc_pack_weights_s8(int cin, int cout, int k, const int8_t *w, void *dst_hos
 int tc_launch(const TcConv *tc, int n0, int nb, int sm_count, cudaStream_t s);
 TcConv *tc_new();
 void tc_delete(TcConv *);
+void tc_set_pre(TcConv *tc, const float *pre);
 const char *tc_mode_name(const TcConv *);
 
 // c3k_fused.cu
@@ -250,6 +251,13 @@ extern "C" int uyd_plan_add_conv(uyd_plan *plan, const uyd_conv *d, const float 
     UYD_REQUIRE(plan->bufs[d->res_buf].h == ob.h && plan->bufs[d->res_buf].w == ob.w && plan->bufs[d->res_buf].dtype == UYD_BF16,
                 UYD_E_ARG, "residual slice must match the output extent (bf16)");
   }
+  if (d->pre_buf_p1) {
+    const int pb = d->pre_buf_p1 - 1;
+    UYD_REQUIRE(pb >= 0 && pb < (int)plan->bufs.size(), UYD_E_ARG, "conv: partial-sum buffer id out of range");
+    const Buffer &b = plan->bufs[pb];
+    UYD_REQUIRE(b.dtype == UYD_F32 && b.c == d->cout && b.h * 2 == ob.h && b.w * 2 == ob.w && d->cout % 16 == 0, UYD_E_ARG,
+                "conv: the partial-sum buffer must be fp32 [h/2, w/2, cout]");
+  }
   Op op;
   op.kind = OP_CONV;
   op.conv = *d;
@@ -264,6 +272,7 @@ extern "C" int uyd_plan_add_conv(uyd_plan *plan, const uyd_conv *d, const float 
   } else if (d->impl == UYD_IMPL_AUTO) {
     op.use_tc = tc_ok && d->cin >= min_c && env_int("UYD_DISABLE_TC", 0) == 0;
   }
+  UYD_REQUIRE(!d->pre_buf_p1 || op.use_tc, UYD_E_UNSUPPORTED, "conv: partial sums are only added on the tensor-core path");
   if (op.use_tc) {
     op.w_host.resize(tc_weight_bytes(*d));
     tc_pack_weights(*d, weight, op.w_host.data());
@@ -613,6 +622,7 @@ extern "C" int uyd_plan_finalize(uyd_plan *plan) {
                          d.res_buf >= 0 ? plan->bufs[d.res_buf].c : 0, o.w_dev, o.b_dev, halo_fallback ? 2 : -1, bo_mode, stages, 0,
                          nullptr, 0.f, 0, halo_pitch);
       if (e) return e;
+      if (d.pre_buf_p1) tc_set_pre(o.tc, (const float *)plan->bufs[d.pre_buf_p1 - 1].ptr);
     }
   }
   plan->finalized = true;
@@ -813,7 +823,8 @@ extern "C" int uyd_plan_op_info(uyd_plan *plan, int op, char *text, size_t text_
     by = (double)ih * iw * d.cin * (d.in_buf < 0 ? 4 : (o.kind == OP_CONV_S8 ? 1 : 2)) + (double)ob.h * ob.w * d.cout * ob.elem_bytes() +
          (d.res_buf >= 0 ? (double)ob.h * ob.w * d.cout * 2 : 0);
     snprintf(text, text_len, "conv%s %d->%d k%d s%d%s %dx%d %s%s%s", o.kind == OP_CONV_S8 ? "_s8" : "", d.cin, d.cout, d.k, d.stride,
-             d.depthwise ? " dw" : "", ob.h, ob.w, o.use_tc ? "tc:" : "direct", o.use_tc ? tc_mode_name(o.tc) : "", d.res_buf >= 0 ? " +res" : "");
+             d.depthwise ? " dw" : "", ob.h, ob.w, o.use_tc ? "tc:" : "direct", o.use_tc ? tc_mode_name(o.tc) : "",
+             d.res_buf >= 0 ? " +res" : (o.kind == OP_CONV && d.pre_buf_p1 ? " +up(partial)" : ""));
   } else if (o.kind == OP_QUANT) {
     const Buffer &b = plan->bufs[o.buf];
     by = (double)b.h * b.w * o.c * 3;

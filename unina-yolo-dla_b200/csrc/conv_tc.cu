@@ -64,6 +64,7 @@ struct TcParams {
   int res_pitch;
   const float *bias;
   int relu;
+  const float *pre;      // fp32 [n, H/2, W/2, cout] partial sums added (nearest x2 upsampled) before the activation, or null
 };
 
 namespace {
@@ -77,12 +78,20 @@ constexpr int kMaxAcc = 4;  // TMEM accumulator stages
 
 // One 16-column chunk of one accumulator row: bias -> ReLU -> residual -> store.
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&raw)[16], const float *bias_s, int c0, long long pix,
-                                               const TcParams &p) {
+                                               const TcParams &p, long long ppix) {
   float v[16];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {  // 16-byte broadcast loads of the bias vector
     const float4 q = reinterpret_cast<const float4 *>(bias_s + c0)[i];
     v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+  }
+  if (ppix >= 0) {  // partial sums of the low-resolution half (cout % 16 == 0, checked on the host)
+    const float4 *pp = reinterpret_cast<const float4 *>(p.pre + ppix * p.cout + c0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 q = pp[i];
+      v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
+    }
   }
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
@@ -137,12 +146,20 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&raw)[16], const 
 // shared memory; the warp then copies whole rows out with 16-byte lanes laid along the row, so
 // one store instruction touches 32*16/row_bytes rows instead of 32 different 128-byte lines.
 __device__ __forceinline__ void epilogue_chunk_staged(const uint32_t (&raw)[16], const float *bias_s, int c0, long long pix,
-                                                      const TcParams &p, unsigned char *srow) {
+                                                      const TcParams &p, unsigned char *srow, long long ppix) {
   float v[16];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {  // 16-byte broadcast loads of the bias vector
     const float4 q = reinterpret_cast<const float4 *>(bias_s + c0)[i];
     v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+  }
+  if (ppix >= 0) {  // partial sums of the low-resolution half of an upsample + concat + 1x1 conv (staged rows: cout % 16 == 0)
+    const float4 *pp = reinterpret_cast<const float4 *>(p.pre + ppix * p.cout + c0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 q = pp[i];
+      v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
+    }
   }
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
@@ -403,15 +420,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       if (it % p.ngroups != group) continue;  // (groups >= ngroups never match: they idle)
       const int acc = it % nacc;  // nacc is a multiple of ngroups: an accumulator always belongs to the same group
       const uint32_t acc_phase = (uint32_t)(it / nacc) & 1u;
-      long long pix;  // flattened output pixel (n, oy, ox) or -1
+      long long pix;        // flattened output pixel (n, oy, ox) or -1
+      long long ppix = -1;  // pixel of the half-resolution partial-sum tensor this output pixel adds, or -1
       if (p.mode == TC_FLAT) {
         const long long row = tile * 128 + m;
         pix = row < (long long)p.nb * p.H * p.W ? (long long)p.n0 * p.H * p.W + row : -1;
+        if (p.pre && pix >= 0) {
+          const int ox = (int)(pix % p.W);
+          const long long t = pix / p.W;
+          const int oy = (int)(t % p.H);
+          ppix = ((t / p.H) * (p.H >> 1) + (oy >> 1)) * (p.W >> 1) + (ox >> 1);
+        }
       } else {
         const int n = p.n0 + (int)(tile / tiles_per_img);
         const int t = (int)(tile % tiles_per_img);
         const int oy = (t / p.tiles_x) * kTileH + (m >> 3), ox = (t % p.tiles_x) * kTileW + (m & 7);
         pix = (oy < p.H && ox < p.W) ? ((long long)n * p.H + oy) * p.W + ox : -1;
+        if (p.pre && pix >= 0) ppix = ((long long)n * (p.H >> 1) + (oy >> 1)) * (p.W >> 1) + (ox >> 1);
       }
       mbar_wait(tfull0 + 8u * acc, acc_phase);
       tc_fence_after();
@@ -431,10 +456,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         if (staged) {
           if (c * 16 < p.cout) {
             if (I8) epilogue_chunk_i8_staged(cur, bias_s, mult_s, c * 16, pix, p, srow);
-            else epilogue_chunk_staged(cur, bias_s, c * 16, pix, p, srow);
+            else epilogue_chunk_staged(cur, bias_s, c * 16, pix, p, srow, ppix);
           }
         } else if (pix >= 0 && c * 16 < p.cout) {
-          epilogue_chunk(cur, bias_s, c * 16, pix, p);
+          epilogue_chunk(cur, bias_s, c * 16, pix, p, ppix);
         }
         if (more) {
           tmem_ld_wait();
@@ -716,6 +741,7 @@ int tc_launch(const TcConv *tc, int n0, int nb, int sm_count, cudaStream_t s) {
   return (int)cudaGetLastError();
 }
 
+void tc_set_pre(TcConv *tc, const float *pre) { tc->p.pre = pre; }
 TcConv *tc_new() { return new TcConv(); }
 void tc_delete(TcConv *t) { delete t; }
 const char *tc_mode_name(const TcConv *t) { return t->p.mode == TC_FLAT ? "flat" : (t->p.mode == TC_HALO ? "halo" : "pertap"); }

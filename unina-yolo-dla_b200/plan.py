@@ -73,7 +73,10 @@ class Plan:
         return Slice(buf, coff, c, h, w)
 
     def conv(self, src: Slice, dst: Slice, weight: np.ndarray, bias: np.ndarray, k: int, stride: int = 1,
-             relu: bool = True, depthwise: bool = False, res: Slice | None = None, impl: int = IMPL_AUTO) -> Slice:
+             relu: bool = True, depthwise: bool = False, res: Slice | None = None, impl: int = IMPL_AUTO,
+             pre: Slice | None = None) -> Slice:
+        """``pre``: an fp32 buffer [h/2, w/2, cout] of partial sums that is added, nearest-x2 upsampled, before the
+        activation (Upsample + Concat + 1x1 conv without materialising the upsampled tensor)."""
         weight = np.ascontiguousarray(weight, dtype=np.float32)
         bias = np.ascontiguousarray(bias, dtype=np.float32)
         cout = weight.shape[0]
@@ -81,7 +84,7 @@ class Plan:
         assert weight.shape[2] == k and weight.shape[3] == k and bias.shape == (cout,)
         assert dst.c == cout and (src.buf < 0 or src.c == cin), (src, dst, weight.shape)
         d = ConvDesc(src.buf, src.coff, dst.buf, dst.coff, res.buf if res else -1, res.coff if res else 0,
-                     cin, cout, k, stride, int(depthwise), int(relu), impl, 0)
+                     cin, cout, k, stride, int(depthwise), int(relu), impl, (pre.buf + 1) if pre is not None else 0)
         check(_lib.lib().uyd_plan_add_conv(self.handle, C.byref(d), weight.ctypes.data_as(C.c_void_p),
                                            bias.ctypes.data_as(C.c_void_p)), "uyd_plan_add_conv")
         return dst

@@ -147,6 +147,15 @@ class C3k(nn.Module):
         return self.cv3.emit(p, cat, dst)
 
 
+class UpCat:
+    """Upsample(x2, nearest) + Concat that is never materialised: ``low`` (half extent) is the tensor the graph
+    upsamples, ``skip`` (full extent) the one it is concatenated with, in that channel order."""
+
+    def __init__(self, low: Slice, skip: Slice):
+        self.low, self.skip = low, skip
+        self.h, self.w, self.c = skip.h, skip.w, low.c + skip.c
+
+
 class C3k2(nn.Module):
     """C2f: cv1 -> chunk(2) -> n blocks chained on the last chunk -> cat -> cv2.  cv1 writes
     straight into the first 2c channels of the cat buffer; each block appends its c channels."""
@@ -162,7 +171,18 @@ class C3k2(nn.Module):
     def emit(self, p, src, dst=None):
         c, n = self.c, len(self.m)
         cat = p.buffer(src.h, src.w, (2 + n) * c)
-        self.cv1.emit(p, src, cat.sub(0, 2 * c))
+        if isinstance(src, UpCat):
+            # cv1 is linear and 1x1, nearest upsampling commutes with it:
+            #   cv1(cat(up(a), b)) = relu(up(W_a a) + W_b b + bias)
+            # W_a a is computed at HALF resolution into an fp32 buffer and added inside cv1's epilogue, so
+            # neither the upsampled tensor nor the concatenation is ever written.
+            w, b = fold_bn(self.cv1.conv, self.cv1.bn)
+            ca = src.low.c
+            part = p.buffer(src.low.h, src.low.w, 2 * c, UYD_F32)
+            p.conv(src.low, part, w[:, :ca], b * 0, 1, 1, relu=False)
+            p.conv(src.skip, cat.sub(0, 2 * c), w[:, ca:], b, 1, 1, relu=True, pre=part)
+        else:
+            self.cv1.emit(p, src, cat.sub(0, 2 * c))
         for i, m in enumerate(self.m):
             m.emit(p, cat.sub((1 + i) * c, c), cat.sub((2 + i) * c, c))
         return self.cv2.emit(p, cat, dst)
@@ -443,10 +463,19 @@ class UninaYoloB200(nn.Module):
                 shape.append(None)
             else:
                 shape.append((m.c_out, ih, iw))
+        # pass 2a: Upsample -> Concat([-1, j]) -> C3k2 with no other consumer: folded into the C3k2's first conv
+        folded = {}   # concat layer index -> (upsample layer index, skip layer index)
+        if fusion and os.environ.get("UYD_NO_UPSAMPLE_FOLD", "0") != "1":
+            for u, c, k in zip(layers, layers[1:], layers[2:]):
+                if (isinstance(u, nn.Upsample) and isinstance(c, Concat) and isinstance(k, C3k2) and isinstance(c.f, list)
+                        and len(c.f) == 2 and c.f[0] == -1 and c.f[1] != -1 and k.f == -1 and u.i not in self.save
+                        and c.i not in self.save and (2 * k.c) % 16 == 0 and shape[u.i][0] % 16 == 0
+                        and shape[c.f[1] % c.i][0] % 16 == 0 and not _quantized(p, getattr(k.cv1.conv, "_uyd_name", ""))):
+                    folded[c.i] = (u.i, c.f[1] % c.i)
         # pass 2: every tensor consumed by a Concat lives inside that Concat's buffer
         home = {}
         for m in layers:
-            if isinstance(m, Concat):
+            if isinstance(m, Concat) and m.i not in folded:
                 c, h, w = shape[m.i]
                 cat = p.buffer(h, w, c)
                 home[m.i] = cat
@@ -481,9 +510,16 @@ class UninaYoloB200(nn.Module):
                 outs.append(m.emit(p, src_of(m.f), dst))
             elif isinstance(m, nn.Upsample):
                 s = src_of(m.f)
+                if any(u == m.i for u, _ in folded.values()):
+                    outs.append(s)      # stays at half resolution: its consumer is a folded Concat
+                    continue
                 dst = dst or p.buffer(s.h * 2, s.w * 2, s.c)
                 outs.append(p.upsample2x(s, dst))
             elif isinstance(m, Concat):
+                if m.i in folded:
+                    u, j = folded[m.i]
+                    outs.append(UpCat(outs[u], outs[j]))
+                    continue
                 outs.append(home[m.i])
             elif isinstance(m, Detect):
                 feats = [src_of(j) for j in m.f]
@@ -497,7 +533,8 @@ class UninaYoloB200(nn.Module):
                     if _quantized(p, dfl_name):
                         check(_lib.lib().uyd_plan_set_dfl_quant(p.handle, float(self.quant.amax[dfl_name][0])), "uyd_plan_set_dfl_quant")
                 outs.append(None)
-        p.layer_outputs = outs
+        hidden = set(folded) | {u for u, _ in folded.values()}   # layers whose output tensor is never written
+        p.layer_outputs = [None if (i in hidden or not isinstance(o, Slice)) else o for i, o in enumerate(outs)]
         return p.finalize()
 
     def plan_for(self, x: torch.Tensor, fused: bool = False) -> Plan:
