@@ -315,7 +315,6 @@ extern "C" int uyd_plan_add_conv_s8(uyd_plan *plan, const uyd_conv_s8 *d, const 
   op.out_scale = d->out_scale;
   op.out_kind = ob.dtype == UYD_S8 ? 2 : (ob.dtype == UYD_F32 ? 1 : 0);
   bool tc_ok = !d->depthwise && tc_supported_s8(d->cin, d->cout, d->k, d->stride, ib.c, d->in_coff, ob.c, d->out_coff, (int)ob.elem_bytes());
-  if (tc_ok && d->res_buf >= 0 && (d->cout % 16 || plan->bufs[d->res_buf].c % 8 || d->res_coff % 8)) tc_ok = false;
   if (d->impl == UYD_IMPL_TC) {
     UYD_REQUIRE(tc_ok, UYD_E_UNSUPPORTED, "conv_s8 %d->%d k%d s%d cannot run on the tensor-core path", d->cin, d->cout, d->k, d->stride);
     op.use_tc = true;

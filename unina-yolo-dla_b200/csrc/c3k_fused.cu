@@ -568,9 +568,24 @@ int cls_branch_launch(int cin, const ClsArgs &a0, cudaStream_t s) {
   return (int)cudaGetLastError();
 }
 
+// Tile height for a launch: the tallest tile (least halo recompute) that still gives every SM a CTA; small
+// batches (latency runs) get short tiles so that one frame spreads over many SMs instead of 2-20 CTAs.
+int c3k_launch_th(int n, int h, int w) {
+  const int tallest = c3k_pick_th(h);
+  const int cands[5] = {32, 20, 16, 8, 4};
+  int best = tallest;
+  for (int i = 0; i < 5; ++i) {
+    const int th = cands[i];
+    if (th > tallest || h % th) continue;
+    best = th;
+    if ((long long)n * (w / kTW) * (h / th) >= 148) break;
+  }
+  return best;
+}
+
 int c3k_launch(int c, const C3kArgs &a0, cudaStream_t s) {
   C3kArgs a = a0;
-  a.th = c3k_pick_th(a.h);
+  a.th = c3k_launch_th(a.n, a.h, a.w);
   a.tiles_x = a.w / kTW;
   a.tiles_y = a.h / a.th;
   const size_t smem = c3k_smem_bytes(c / 2, a.th);

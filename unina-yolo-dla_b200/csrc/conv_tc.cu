@@ -207,16 +207,22 @@ __device__ __forceinline__ void epilogue_chunk_i8_staged(const uint32_t (&raw)[1
     const float x = __fadd_rn(__fmul_rn(__int2float_rn((int)raw[i]), mult_s[c0 + i]), bias_s[c0 + i]);
     v[i] = p.relu ? fmaxf(x, 0.f) : x;
   }
-  if (p.res && pix >= 0) {  // residual (bf16) added in fp32 after the activation; Cout % 16 == 0 (checked on the host)
+  if (p.res && pix >= 0) {  // residual (bf16) added in fp32 after the activation
     const __nv_bfloat16 *rp = p.res + pix * p.res_pitch + c0;
-    const uint4 r0 = *reinterpret_cast<const uint4 *>(rp), r1 = *reinterpret_cast<const uint4 *>(rp + 8);
-    const __nv_bfloat162 *h0 = reinterpret_cast<const __nv_bfloat162 *>(&r0);
-    const __nv_bfloat162 *h1 = reinterpret_cast<const __nv_bfloat162 *>(&r1);
+    if (p.cout - c0 >= 16 && ((p.res_pitch | (int)(reinterpret_cast<uintptr_t>(p.res) >> 1)) & 7) == 0) {
+      const uint4 r0 = *reinterpret_cast<const uint4 *>(rp), r1 = *reinterpret_cast<const uint4 *>(rp + 8);
+      const __nv_bfloat162 *h0 = reinterpret_cast<const __nv_bfloat162 *>(&r0);
+      const __nv_bfloat162 *h1 = reinterpret_cast<const __nv_bfloat162 *>(&r1);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 f0 = __bfloat1622float2(h0[i]), f1 = __bfloat1622float2(h1[i]);
-      v[2 * i] = __fadd_rn(v[2 * i], f0.x); v[2 * i + 1] = __fadd_rn(v[2 * i + 1], f0.y);
-      v[8 + 2 * i] = __fadd_rn(v[8 + 2 * i], f1.x); v[8 + 2 * i + 1] = __fadd_rn(v[8 + 2 * i + 1], f1.y);
+      for (int i = 0; i < 4; ++i) {
+        const float2 f0 = __bfloat1622float2(h0[i]), f1 = __bfloat1622float2(h1[i]);
+        v[2 * i] = __fadd_rn(v[2 * i], f0.x); v[2 * i + 1] = __fadd_rn(v[2 * i + 1], f0.y);
+        v[8 + 2 * i] = __fadd_rn(v[8 + 2 * i], f1.x); v[8 + 2 * i + 1] = __fadd_rn(v[8 + 2 * i + 1], f1.y);
+      }
+    } else {  // narrow or unaligned slices (Cout = 8 bottlenecks): guarded scalar loads
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (c0 + i < p.cout) v[i] = __fadd_rn(v[i], __bfloat162float(rp[i]));
     }
   }
   if (p.out_kind == 2) {
@@ -599,7 +605,6 @@ int tc_prepare(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int i
   const int es = i8 ? 1 : 2;
   const int CB = i8 ? pick_cb_s8(d.cin) : pick_cb(d.cin);
   UYD_REQUIRE(CB, UYD_E_UNSUPPORTED, "conv_tc: cin %d is not a multiple of %d", d.cin, i8 ? 32 : 16);
-  UYD_REQUIRE(!i8 || !res_base || d.cout % 16 == 0, UYD_E_UNSUPPORTED, "conv_tc int8: a residual input needs Cout %% 16 == 0");
   p.i8 = i8;
   p.mult = mult_dev;
   p.out_scale = out_scale;

@@ -17,6 +17,7 @@ import os
 from math import gcd
 from pathlib import Path
 
+import numpy as np
 import torch
 import torch.nn as nn
 import yaml
@@ -81,15 +82,29 @@ def emit_quant_conv(p: Plan, name: str, conv: nn.Conv2d, bn, src: Slice, dst: Sl
     """QuantConv2d as an integer convolution (quant.py): input quantiser -> int8 conv -> requant epilogue."""
     ax, aw = p.quant.amax[name]
     scale = float(Q.scale_of(ax))
-    cache = p.__dict__.setdefault("_qcache", {})
-    key = (src.buf, src.coff, src.c, scale)
-    qsrc = cache.get(key)
-    if qsrc is None:  # one int8 copy per (activation slice, scale): convs sharing both share the copy
-        qsrc = p.quantize(src, p.buffer(src.h, src.w, src.c, UYD_S8), scale)
-        cache[key] = qsrc
     qw = Q.quantize_weights(conv.weight, aw)
     mult, bias = Q.requant_params(ax, aw, bn, conv.bias)
-    dw = conv.groups > 1
+    cout, dw = qw.shape[0], conv.groups > 1
+    # tensor-core (tcgen05 kind::i8) eligibility is a matter of layout, not of arithmetic (the int32 sums are
+    # exact either way): the int8 copy of the input is ours, so it is padded with zero channels to a multiple
+    # of 32, and a depth-wise conv runs as a dense conv with diagonal weights.
+    tc_rows = cout >= 8 and cout & (cout - 1) == 0 or (cout == 4 and p.shapes[dst.buf][3] == UYD_F32)
+    cpad = src.c
+    if tc_rows and os.environ.get("UYD_INT8_NO_PAD", "0") != "1":
+        cpad = (src.c + 31) // 32 * 32
+        if dw:
+            dense = np.zeros((cout, cpad, qw.shape[2], qw.shape[3]), np.int8)
+            dense[np.arange(cout), np.arange(cout)] = qw[:, 0]
+            qw, dw = dense, False
+        elif cpad != src.c:
+            qw = np.concatenate((qw, np.zeros((cout, cpad - src.c, qw.shape[2], qw.shape[3]), np.int8)), 1)
+    cache = p.__dict__.setdefault("_qcache", {})
+    key = (src.buf, src.coff, src.c, scale, cpad)
+    qsrc = cache.get(key)
+    if qsrc is None:  # one int8 copy per (activation slice, scale, padded width): convs sharing them share the copy
+        qbuf = p.buffer(src.h, src.w, cpad, UYD_S8)          # zero-filled at finalize: the pad channels stay zero
+        p.quantize(src, qbuf.sub(0, src.c), scale)
+        qsrc = cache[key] = qbuf
     return p.conv_s8(qsrc, dst, qw, mult, bias, conv.kernel_size[0], conv.stride[0], relu=relu, depthwise=dw, res=res)
 
 
