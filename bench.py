@@ -289,6 +289,7 @@ def main():
     ms_total = timed(step_resident, a.steps)
     if rank == 0:
         sampler.stop_flag = True
+        sampler.join(timeout=10)   # an nvidia-smi query still in flight stalls work submission for tens of ms
     top_ms_total, top_n = plan.timed_op_read()
     plan.set_timed_op(-1, 0)
     for _ in range(2):

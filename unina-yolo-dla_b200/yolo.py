@@ -795,24 +795,32 @@ class UninaYoloB200(nn.Module):
         except StopIteration:
             return
         Bmax = first.shape[0]
-        copy_s = torch.cuda.Stream(device=device)
         main_s = torch.cuda.current_stream(device)
+        # staging slots, pinned result buffers, copy stream and events are allocated once per
+        # (frame shape, dtype, max_det) and reused by later calls: cudaHostAlloc alone costs milliseconds
+        skey = (device, tuple(first.shape), first.dtype, max_det, to_host)
+        state = self.__dict__.setdefault("_stream_state", {}).get(skey)
+        if state is None:
 
-        class Slot:
-            pass
+            class Slot:
+                pass
 
-        slots = []
-        for _ in range(2):
-            s = Slot()
-            s.x = torch.empty(first.shape, dtype=first.dtype if first.dtype == torch.uint8 else torch.float32, device=device)
-            s.ready, s.free, s.out = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
-            s.det = s.cnt = s.det_h = s.cnt_h = None
-            s.n = s.n_in = 0
-            slots.append(s)
-        if to_host:
-            for s in slots:
-                s.det_h = torch.empty(Bmax, max_det, 6, dtype=torch.float32).pin_memory()
-                s.cnt_h = torch.empty(Bmax, dtype=torch.int32).pin_memory()
+            slots = []
+            for _ in range(2):
+                s = Slot()
+                s.x = torch.empty(first.shape, dtype=first.dtype if first.dtype == torch.uint8 else torch.float32, device=device)
+                s.ready, s.free, s.out = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+                s.det = s.cnt = s.det_h = s.cnt_h = None
+                s.n = s.n_in = 0
+                if to_host:
+                    s.det_h = torch.empty(Bmax, max_det, 6, dtype=torch.float32).pin_memory()
+                    s.cnt_h = torch.empty(Bmax, dtype=torch.int32).pin_memory()
+                slots.append(s)
+            state = self._stream_state[skey] = (torch.cuda.Stream(device=device), slots)
+        copy_s, slots = state
+        copy_s.wait_stream(main_s)   # a previous generator's last step may still read the slots
+        for s in slots:
+            s.free.record(main_s)
 
         def stage(s, xb):
             if xb.shape[0] > Bmax or xb.shape[1:] != first.shape[1:]:
