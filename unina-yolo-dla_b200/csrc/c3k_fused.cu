@@ -224,6 +224,7 @@ constexpr int frag_words_1(int k, int cout) { return ((k + 15) / 16) * ((cout + 
 
 template <int C>  // C = c_ (hidden width); block width c = 2C
 __global__ void __launch_bounds__(kThreadsC3k) c3k_fused_kernel(C3kArgs a) {
+  pdl_trigger();
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int CC = 2 * C;
   const int TH = a.th;

@@ -35,6 +35,13 @@ void set_error(const char *fmt, ...);
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+#ifdef __CUDACC__
+// Lets a successor launched with programmatic stream serialization (the tcgen05 kernels, tc_ptx.cuh) start its
+// prologue while this kernel is still running; the successor still waits for this kernel's completion before
+// it reads any activation.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 // ---------------------------------------------------------------------------------------
 // Plan-level data structures shared by the kernel translation units.
 // ---------------------------------------------------------------------------------------

@@ -111,7 +111,13 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
       mbar_init(tempty2 + 8u * g, 128);
     }
     fence_barrier_init();
+    // weights: part of the prologue that overlaps the previous kernel's tail
+    mbar_expect_tx(wfull, p.w1_bytes + p.w2_bytes);
+    const int nblk = p.ncb * 9;
+    for (int i = 0; i < nblk; ++i) tma_load_2d(w1_s + (uint32_t)i * p.N1 * p.cb_bytes, &tm_w1, wfull, 0, i * p.N1);
+    tma_load_2d(w2_s, &tm_w2, wfull, 0, 0);
   }
+  griddep_trigger();
   for (int i = threadIdx.x; i < 128; i += kChainThreads) {
     bias1_s[i] = i < p.N1 ? p.bias1[i] : 0.f;
     bias2_s[i] = i < p.N2 ? p.bias2[i] : 0.f;
@@ -128,6 +134,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *slot_ptr;
+  griddep_wait();  // from here on the activations written by the previous kernel are read
 
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const int stages = p.stages;
@@ -136,12 +143,6 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
 
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
-      mbar_expect_tx(wfull, p.w1_bytes + p.w2_bytes);
-      const int nblk = p.ncb * 9;
-      for (int i = 0; i < nblk; ++i) tma_load_2d(w1_s + (uint32_t)i * p.N1 * cb_bytes, &tm_w1, wfull, 0, i * p.N1);
-      tma_load_2d(w2_s, &tm_w2, wfull, 0, 0);
-    }
     int stage = 0;
     uint32_t phase = 0;
     const int cb_elems = (int)cb_bytes / 2;
@@ -590,7 +591,7 @@ int chain_launch(const ChainConv *cc, int nb, float *y, int sm_count, cudaStream
     cudaMemsetAsync(dbg_dev, 0, 2 * 64 * 8 * sizeof(long long), s);
     p.dbg = dbg_dev;
   }
-#define UYD_CHAIN_LAUNCH(A, B) conv_chain_kernel<A, B><<<grid, kChainThreads, cc->smem, s>>>(cc->tm_in, cc->tm_w1, cc->tm_w2, p)
+#define UYD_CHAIN_LAUNCH(A, B) UYD_CUDA(launch_pdl(conv_chain_kernel<A, B>, dim3(grid), dim3(kChainThreads), cc->smem, s, cc->tm_in, cc->tm_w1, cc->tm_w2, p))
   if (ks1 == 2 && ks2 == 2) UYD_CHAIN_LAUNCH(2, 2);
   else if (ks1 == 2 && ks2 == 4) UYD_CHAIN_LAUNCH(2, 4);
   else if (ks1 == 4 && ks2 == 2) UYD_CHAIN_LAUNCH(4, 2);

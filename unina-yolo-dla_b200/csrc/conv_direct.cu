@@ -323,6 +323,7 @@ __global__ void __launch_bounds__(kStemThreads) conv_stem_tiled_kernel(ConvArgs 
 // Depth-wise 3x3 stride 1, four horizontally adjacent pixels x 8 channels per thread: the 3 x 6
 // input window is loaded once (18 x 16 B) for 4 outputs instead of 36 loads.
 __global__ void __launch_bounds__(kThreads) conv_dw4_kernel(ConvArgs a) {
+  pdl_trigger();
   const int cg = a.cin / 8, wq = a.ow / 4;
   const long long total = (long long)a.n * a.oh * wq * cg;
   const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;

@@ -292,7 +292,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       mbar_init(tempty0 + 8u * a, 128);
     }
     fence_barrier_init();
+    // the weights do not depend on the previous kernel: their TMA is part of the prologue that overlaps its tail
+    mbar_expect_tx(wfull, p.w_bytes);
+    const int nblk = p.ncb * p.taps;
+    for (int i = 0; i < nblk; ++i) tma_load_2d(w_s + (uint32_t)i * p.N * p.cb_bytes, &tm_w, wfull, 0, i * p.N);
   }
+  griddep_trigger();
   for (int i = threadIdx.x; i < p.N; i += kThreads) {
     bias_s[i] = i < p.cout ? p.bias[i] : 0.f;
     mult_s[i] = (I8 && i < p.cout) ? p.mult[i] : 0.f;
@@ -302,6 +307,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *slot_ptr;
+  griddep_wait();  // from here on the activations written by the previous kernel are read
 
   const int blocks_per_tile = p.mode == TC_PERTAP ? p.ncb * p.taps : p.ncb;
   const int cb_elems = I8 ? p.cb_bytes : p.cb_bytes / 2;
@@ -311,11 +317,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
-      mbar_expect_tx(wfull, p.w_bytes);
-      const int nblk = p.ncb * p.taps;
-      for (int i = 0; i < nblk; ++i) tma_load_2d(w_s + (uint32_t)i * p.N * cb_bytes, &tm_w, wfull, 0, i * p.N);
-    }
     int stage = 0;
     uint32_t phase = 0;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -736,7 +737,7 @@ int tc_launch(const TcConv *tc, int n0, int nb, int sm_count, cudaStream_t s) {
   if (p.total_tiles == 0) return UYD_OK;
   const unsigned grid = (unsigned)(p.total_tiles < sm_count ? p.total_tiles : sm_count);
   const int ks = p.cb_bytes / 32;
-#define UYD_TC_LAUNCH(I8V, KS) conv_tc_kernel<I8V, KS><<<grid, kThreads, tc->smem, s>>>(tc->tm_in, tc->tm_w, p)
+#define UYD_TC_LAUNCH(I8V, KS) UYD_CUDA(launch_pdl(conv_tc_kernel<I8V, KS>, dim3(grid), dim3(kThreads), tc->smem, s, tc->tm_in, tc->tm_w, p))
   if (p.i8) {
     if (ks == 1) UYD_TC_LAUNCH(true, 1); else if (ks == 2) UYD_TC_LAUNCH(true, 2); else UYD_TC_LAUNCH(true, 4);
   } else {

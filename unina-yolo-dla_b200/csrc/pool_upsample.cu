@@ -23,6 +23,7 @@ __device__ __forceinline__ uint4 max8(uint4 a, uint4 b) {
 // image row x 8-channel group: the 13 input rows are reduced column-wise into shared memory
 // (vertical maxima for radius 2/4/6), then each thread reduces horizontally.
 __global__ void __launch_bounds__(kThreads) sppf_pool_kernel(__nv_bfloat16 *base, int h, int w, int pitch, int c) {
+  pdl_trigger();
   extern __shared__ uint4 col[];  // [3][w][cg] vertical maxima
   const int cg = c / 8;
   const int y = blockIdx.x % h;

@@ -52,6 +52,7 @@ __device__ __forceinline__ void split_bf16(float2 v, uint32_t &hi, uint32_t &lo)
 
 template <typename TIn>
 __global__ void __launch_bounds__(kThreads) stem_fused_kernel(StemArgs a) {
+  pdl_trigger();
   extern __shared__ __align__(16) unsigned char smem[];
   __nv_bfloat16 *hi_s = reinterpret_cast<__nv_bfloat16 *>(smem);                   // [3][35][68] high parts
   __nv_bfloat16 *lo_s = hi_s + 3 * kInH * kInW;                                     // [3][35][68] residuals

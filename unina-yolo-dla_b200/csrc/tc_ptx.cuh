@@ -1,6 +1,8 @@
 // PTX wrappers shared by the tcgen05 kernels (conv_tc.cu, conv_chain.cu): mbarrier, TMA, TMEM,
 // UMMA issue/commit and the K-major shared-memory matrix descriptor.  sm_100a only.
 #pragma once
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace uyd {
@@ -109,7 +111,31 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start while its predecessor in the stream is still running; griddep_wait() blocks until that predecessor has
+// completed and its writes are visible.  Everything before it (barrier init, TMEM allocation, weight TMA,
+// bias loads) overlaps the predecessor's tail.  griddep_trigger() lets the successor start early.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 }  // namespace
+
+// Launch with the programmatic-stream-serialization attribute (UYD_NO_PDL=1 launches plainly).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  static const bool off = [] { const char *v = getenv("UYD_NO_PDL"); return v && *v == '1'; }();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = off ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 }  // namespace uyd
