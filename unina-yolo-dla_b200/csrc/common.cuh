@@ -6,6 +6,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -40,6 +41,25 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 // prologue while this kernel is still running; the successor still waits for this kernel's completion before
 // it reads any activation.
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// Blocks until the predecessor kernel has completed and its writes are visible (no-op for plain launches).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// Launch with the programmatic-stream-serialization attribute (UYD_NO_PDL=1 launches plainly).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  static const bool off = [] { const char *v = getenv("UYD_NO_PDL"); return v && *v == '1'; }();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = off ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 #endif
 
 // ---------------------------------------------------------------------------------------

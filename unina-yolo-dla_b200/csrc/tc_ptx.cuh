@@ -122,20 +122,4 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 
 }  // namespace
 
-// Launch with the programmatic-stream-serialization attribute (UYD_NO_PDL=1 launches plainly).
-template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
-  static const bool off = [] { const char *v = getenv("UYD_NO_PDL"); return v && *v == '1'; }();
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = off ? 0 : 1;
-  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
-}
 }  // namespace uyd
