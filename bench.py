@@ -50,6 +50,9 @@ def parse():
     ap.add_argument("--size", type=int, default=640)
     ap.add_argument("--cpu-sample", type=int, default=32, help="frames of the bounded CPU sample")
     ap.add_argument("--profile-out", default="", help="write the per-op table (markdown) here")
+    ap.add_argument("--stress", type=int, default=0, metavar="BATCH",
+                    help="also time decode-free NMS on a synthetic dense 1280x1280 scene (134 400 anchors, ~100k candidates per "
+                         "image, BASELINE config 5) at this batch, e.g. 32")
     ap.add_argument("--int8", type=int, default=0, metavar="BATCH",
                     help="also time the INT8 graph (static max-calibrated scales, BASELINE config 3) at this batch, e.g. 256")
     return ap.parse_args()
@@ -158,6 +161,34 @@ def bench_int8(model, batch: int, size: int, dev, steps: int):
            "note": "quantize ops are separate launches in this round (one int8 copy per activation slice and scale)"}
     model.set_quantization(None)
     return out
+
+
+def bench_nms_stress(model, batch: int, dev, steps: int):
+    """BASELINE config 5: class-aware NMS on a dense 1280x1280 scene: 134 400 anchors per image, ~75 % of them
+    above conf (top-30000 truncation active), boxes clustered around 64 centres per image."""
+    A = 102400 + 25600 + 6400
+    g = torch.Generator(device=dev).manual_seed(500)
+    centres = torch.rand(batch, 2, 64, device=dev, generator=g) * 1200 + 40
+    pick = torch.randint(0, 64, (batch, 1, A), device=dev, generator=g).expand(batch, 2, A)
+    y = torch.empty(batch, 8, A, device=dev)
+    y[:, 0:2] = torch.gather(centres, 2, pick) + torch.randn(batch, 2, A, device=dev, generator=g) * 6
+    y[:, 2:4] = torch.rand(batch, 2, A, device=dev, generator=g) * 88 + 8
+    sc = torch.rand(batch, 4, A, device=dev, generator=g)
+    lift = torch.rand(batch, 1, A, device=dev, generator=g) < 0.75
+    y[:, 4:] = torch.where(lift, 0.25 + 0.75 * sc, 0.2 * sc)
+    cand = int((y[:, 4:].amax(1) > CONF).sum(1).float().mean())
+    for _ in range(2):
+        det, cnt = model.nms(y, CONF, IOU, MAX_DET)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        det, cnt = model.nms(y, CONF, IOU, MAX_DET)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"ms_per_step": ms, "images_per_s": batch / (ms * 1e-3), "batch": batch, "anchors": A, "candidates_per_image": cand,
+            "kept_per_image": float(cnt.float().mean()), "steps": steps}
 
 
 def run_reference(a):
@@ -375,6 +406,8 @@ def main():
     }
     if a.int8 > 0:
         out["int8"] = bench_int8(model, a.int8, S, dev, max(3, a.steps // 2))
+    if a.stress > 0:
+        out["nms_stress_1280"] = bench_nms_stress(model, a.stress, dev, max(3, a.steps // 2))
     if world == 1:
         out["cpu_baseline"] = cpu_baseline(model, S, a.cpu_sample)
     if a.profile_out:
