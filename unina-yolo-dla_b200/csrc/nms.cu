@@ -27,6 +27,7 @@
 #include <cub/cub.cuh>
 
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -332,6 +333,263 @@ __global__ void nms_emit_rows_kernel(Layout L, int A, int max_det, const int *__
   }
 }
 
+// =================================================================================================
+// Fused per-image NMS (the default path of uyd_nms): ONE launch, one 1024-thread CTA per image.
+//   1. scan   : best class / score per anchor, conf filter, 64-bit key (score code | anchor | class); the keys
+//               of the current slab are captured in shared memory.  A slab is a key range holding at most
+//               kFCap candidates: normally the whole image (<= kFCap candidates: one pass over the scores);
+//               dense scenes are cut into consecutive ranges with a 2048-bin histogram of the key space
+//               (three passes per slab; the ranges are processed best-first, so the loop usually ends after
+//               the first slab because max_det boxes are kept).
+//   2. sort   : bitonic sort of the slab in shared memory (keys are unique: ties in score resolve to the lower
+//               anchor, exactly the stable descending sort of the reference).
+//   3. greedy : as nms_greedy_kernel (chunks of 128, kept-list test by 8 threads per candidate, ballot
+//               compaction, IoU bitmask among survivors, one warp resolves), boxes formed on the fly from y.
+//   4. emit   : rows / anchor indices / count written by the same CTA.
+// Replaces key kernel + 5 radix passes over batch x anchors + gather + greedy + emit (365 -> ~150 us at
+// batch 64 x 33 600 anchors) and is what batch-1 latency needs (one dependent launch instead of eleven).
+// =================================================================================================
+constexpr int kFThreads = 1024, kFCap = 4096, kFChunk = 128, kFSplit = kFThreads / kFChunk, kFBins = 2048;
+constexpr int kKeyAnchorShift = 8, kKeyCodeShift = 30;  // key = code << 30 | anchor << 8 | class
+
+__device__ __forceinline__ uint64_t fused_key(float best, int j, int a, bool pos) {
+  const uint32_t bits = __float_as_uint(best);
+  uint32_t code;
+  if (pos) code = 0x7FFFFFFFu - bits;
+  else code = ~((bits & 0x80000000u) ? ~bits : (bits | 0x80000000u));
+  return ((uint64_t)code << kKeyCodeShift) | ((uint64_t)a << kKeyAnchorShift) | (uint64_t)j;
+}
+__device__ __forceinline__ float fused_key_score(uint64_t key, bool pos) {
+  const uint32_t code = (uint32_t)(key >> kKeyCodeShift);
+  if (pos) return __uint_as_float(0x7FFFFFFFu - code);
+  const uint32_t asc = ~code;
+  return __uint_as_float((asc & 0x80000000u) ? (asc & 0x7FFFFFFFu) : ~asc);
+}
+
+struct FusedSmem {
+  unsigned long long keys[kFCap];
+  unsigned int hist[kFBins];
+  float4 kbox[kMaxDetCap], kraw[kMaxDetCap];
+  float karea[kMaxDetCap], kconf[kMaxDetCap];
+  int kcls[kMaxDetCap], kanchor[kMaxDetCap];
+  float4 abox[kFChunk], araw[kFChunk];
+  float aarea[kFChunk], aconf[kFChunk];
+  int acls[kFChunk], aanchor[kFChunk];
+  unsigned mask[kFChunk][kFChunk / 32];
+  int warp_cnt[kFThreads / 32];
+  unsigned long long kmin, kmax, cut;
+  int count, kept, alive;
+};
+
+__global__ void __launch_bounds__(kFThreads, 1) nms_image_kernel(const float *__restrict__ y, int nc, int A, float conf_thr,
+                                                                 float iou_thr, int max_nms, int max_det, float max_wh, int pos,
+                                                                 float *__restrict__ out_det, int *__restrict__ out_idx,
+                                                                 int *__restrict__ out_count) {
+  extern __shared__ __align__(16) unsigned char fused_raw[];
+  FusedSmem &S = *reinterpret_cast<FusedSmem *>(fused_raw);
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const float *yb = y + (long long)b * (4 + nc) * A;
+  if (tid == 0) S.kept = 0;
+  unsigned long long lo = 0ull;   // keys below lo have been consumed
+  int processed = 0;
+  __syncthreads();
+
+  // mode 0: count keys in [lo, hi), track min / max, capture the first kFCap;  mode 1: histogram over (key - kmin) >> shift
+  auto scan = [&](unsigned long long hi, int mode, int shift) {
+    for (int a0 = 0; a0 < A; a0 += kFThreads) {
+      const int a = a0 + tid;
+      bool in = false;
+      unsigned long long key = 0ull;
+      if (a < A) {
+        const float *p = yb + 4ll * A + a;
+        float best = p[0];
+        int j = 0;
+        for (int c = 1; c < nc; ++c) {
+          const float v = p[(long long)c * A];
+          if (v > best) { best = v; j = c; }   // first maximum wins
+        }
+        if (best > conf_thr) {
+          key = fused_key(best, j, a, pos != 0);
+          in = key >= lo && key < hi;
+        }
+      }
+      if (mode == 0) {
+        const unsigned bal = __ballot_sync(0xffffffffu, in);
+        if (bal) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(&S.count, __popc(bal));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (in) {
+            const int slot = base + __popc(bal & ((1u << lane) - 1));
+            if (slot < kFCap) S.keys[slot] = key;
+          }
+          unsigned long long mn = in ? key : ~0ull, mx = in ? key : 0ull;  // one pair of atomics per warp
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long omn = __shfl_xor_sync(0xffffffffu, mn, o), omx = __shfl_xor_sync(0xffffffffu, mx, o);
+            mn = omn < mn ? omn : mn;
+            mx = omx > mx ? omx : mx;
+          }
+          if (lane == 0) { atomicMin(&S.kmin, mn); atomicMax(&S.kmax, mx); }
+        }
+      } else if (in) {
+        atomicAdd(&S.hist[(unsigned)((key - S.kmin) >> shift)], 1u);
+      }
+    }
+  };
+
+  while (true) {
+    // ---- 1. the next slab: keys in [lo, hi) with at most kFCap members ----
+    unsigned long long hi = ~0ull;
+    int n_slab = 0;
+    while (true) {
+      if (tid == 0) { S.count = 0; S.kmin = ~0ull; S.kmax = 0ull; }
+      __syncthreads();
+      scan(hi, 0, 0);
+      __syncthreads();
+      n_slab = S.count;
+      if (n_slab <= kFCap) break;
+      // too many: histogram the occupied key range and cut it where the cumulative count would exceed the capacity
+      const unsigned long long kmin = S.kmin, span = S.kmax - S.kmin;
+      int shift = 0;
+      while ((span >> shift) >= (unsigned long long)kFBins) ++shift;
+      for (int i = tid; i < kFBins; i += kFThreads) S.hist[i] = 0u;
+      __syncthreads();
+      scan(hi, 1, shift);
+      __syncthreads();
+      if (tid == 0) {
+        unsigned cum = 0;
+        int nb = 0;
+        while (nb < kFBins && cum + S.hist[nb] <= (unsigned)kFCap) cum += S.hist[nb++];
+        if (nb == 0) nb = 1;  // a single bin overflows: narrow the range to it (keys are unique, so this terminates)
+        S.cut = kmin + ((unsigned long long)nb << shift);
+      }
+      __syncthreads();
+      hi = S.cut;
+      __syncthreads();
+    }
+    if (n_slab == 0) break;
+    // ---- 2. bitonic sort of the slab (ascending key = descending score, ties -> lower anchor) ----
+    int P = 32;
+    while (P < n_slab) P <<= 1;
+    for (int i = n_slab + tid; i < P; i += kFThreads) S.keys[i] = ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= P; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < P; i += kFThreads) {
+          const int q = i ^ j;
+          if (q > i) {
+            const unsigned long long x = S.keys[i], z = S.keys[q];
+            const bool up = (i & k) == 0;
+            if ((x > z) == up) { S.keys[i] = z; S.keys[q] = x; }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    // ---- 3. greedy NMS over the slab, in order, at most max_nms candidates per image in total ----
+    const int take = min(n_slab, max_nms - processed);
+    for (int c0 = 0; c0 < take; c0 += kFChunk) {
+      const int kept = S.kept;
+      if (kept >= max_det) break;
+      const int i = c0 + tid / kFSplit, slice = tid % kFSplit;
+      const bool valid = i < take;
+      float4 bo = make_float4(0.f, 0.f, 0.f, 0.f), bx = bo;
+      float ar = 0.f, sc = 0.f;
+      int cl = 0, an = 0;
+      bool sup = false;
+      if (valid) {
+        const unsigned long long key = S.keys[i];
+        an = (int)((key >> kKeyAnchorShift) & ((1u << kAnchorBits) - 1));
+        cl = (int)(key & 0xFF);
+        sc = fused_key_score(key, pos != 0);
+        const float *p = yb + an;
+        const float cx = p[0], cy = p[A], w = p[2ll * A], h = p[3ll * A];
+        const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);
+        bx.x = __fsub_rn(cx, hw); bx.y = __fsub_rn(cy, hh); bx.z = __fadd_rn(cx, hw); bx.w = __fadd_rn(cy, hh);
+        const float off = __fmul_rn((float)cl, max_wh);
+        bo.x = __fadd_rn(bx.x, off); bo.y = __fadd_rn(bx.y, off); bo.z = __fadd_rn(bx.z, off); bo.w = __fadd_rn(bx.w, off);
+        ar = box_area(bo);
+        for (int k = slice; k < kept; k += kFSplit)
+          if (suppresses<false>(S.kbox[k], S.karea[k], S.kcls[k], bo, ar, cl, iou_thr)) { sup = true; break; }
+      }
+#pragma unroll
+      for (int o = 1; o < kFSplit; o <<= 1) sup |= __shfl_xor_sync(0xffffffffu, sup ? 1 : 0, o) != 0;
+      const bool alive = valid && !sup && slice == 0;
+      const unsigned bal = __ballot_sync(0xffffffffu, alive);
+      if (lane == 0) S.warp_cnt[wid] = __popc(bal);
+      __syncthreads();
+      int base = 0;
+      for (int w2 = 0; w2 < wid; ++w2) base += S.warp_cnt[w2];
+      if (tid == kFThreads - 1) S.alive = base + __popc(bal);
+      if (alive) {
+        const int slot = base + __popc(bal & ((1u << lane) - 1));
+        S.abox[slot] = bo; S.araw[slot] = bx; S.aarea[slot] = ar; S.acls[slot] = cl; S.aconf[slot] = sc; S.aanchor[slot] = an;
+      }
+      __syncthreads();
+      const int m = S.alive;
+      const int words = (m + 31) >> 5;
+      for (int item = tid; item < m * words; item += kFThreads) {
+        const int r = item / words, cw = item % words;
+        unsigned bits = 0;
+        if (cw * 32 + 31 > r) {
+          const float4 rb = S.abox[r];
+          const float ra = S.aarea[r];
+          const int rc = S.acls[r];
+          const int j0 = cw * 32;
+#pragma unroll 4
+          for (int jj = 0; jj < 32; ++jj) {
+            const int j = j0 + jj;
+            if (j > r && j < m && suppresses<false>(rb, ra, rc, S.abox[j], S.aarea[j], S.acls[j], iou_thr)) bits |= 1u << jj;
+          }
+        }
+        S.mask[r][cw] = bits;
+      }
+      __syncthreads();
+      if (wid == 0) {
+        unsigned remv = 0;
+        int k = kept, r = 0;
+        while (k < max_det) {
+          const int base_bit = lane * 32;
+          unsigned alive_bits = ~remv;
+          if (base_bit + 32 <= r) alive_bits = 0u;
+          else if (base_bit < r) alive_bits &= ~0u << (r - base_bit);
+          if (base_bit >= m) alive_bits = 0u;
+          else if (base_bit + 32 > m) alive_bits &= (1u << (m - base_bit)) - 1u;
+          const unsigned lanes = __ballot_sync(0xffffffffu, alive_bits != 0u);
+          if (!lanes) break;
+          const int src_lane = __ffs(lanes) - 1;
+          const int bit = __ffs(__shfl_sync(0xffffffffu, alive_bits, src_lane)) - 1;
+          r = src_lane * 32 + bit;
+          if (lane == 0) {
+            S.kbox[k] = S.abox[r]; S.kraw[k] = S.araw[r]; S.karea[k] = S.aarea[r]; S.kcls[k] = S.acls[r];
+            S.kconf[k] = S.aconf[r]; S.kanchor[k] = S.aanchor[r];
+          }
+          ++k;
+          if (lane < words) remv |= S.mask[r][lane];
+          ++r;
+        }
+        if (lane == 0) S.kept = k;
+      }
+      __syncthreads();
+    }
+    processed += take;
+    if (hi == ~0ull || S.kept >= max_det || processed >= max_nms) break;
+    lo = hi;
+    __syncthreads();
+  }
+  // ---- 4. emit ----
+  __syncthreads();
+  const int kept = S.kept;
+  for (int k = tid; k < kept; k += kFThreads) {
+    float *o = out_det + ((long long)b * max_det + k) * 6;
+    const float4 r = S.kraw[k];
+    o[0] = r.x; o[1] = r.y; o[2] = r.z; o[3] = r.w; o[4] = S.kconf[k]; o[5] = (float)S.kcls[k];
+    if (out_idx) out_idx[(long long)b * max_det + k] = S.kanchor[k];
+  }
+  if (tid == 0) out_count[b] = kept;
+}
+
 // ---- detection-record variant (custom head, postprocess.hpp semantics) ----------------------
 struct DetLayout {
   uint64_t *keys_in, *keys_out;
@@ -409,12 +667,24 @@ extern "C" int uyd_nms(uyd_ctx *ctx, const float *y, int batch, int nc, int anch
   UYD_REQUIRE(max_det > 0 && max_det <= kMaxDetCap, UYD_E_UNSUPPORTED, "uyd_nms: max_det <= %d", kMaxDetCap);
   if (max_nms > anchors) max_nms = anchors;
   UYD_REQUIRE(max_nms > 0, UYD_E_ARG, "uyd_nms: max_nms must be positive");
-  Layout L = carve(workspace, batch, anchors);
-  UYD_REQUIRE(L.total <= workspace_bytes, UYD_E_ARG, "uyd_nms: workspace too small (%zu < %zu)", workspace_bytes, L.total);
   cudaStream_t s = (cudaStream_t)stream;
   const long long total = (long long)batch * anchors;
   float thr_f = (float)iou_thr;  // largest float <= the double threshold
   if ((double)thr_f > iou_thr) thr_f = nextafterf(thr_f, -INFINITY);
+  static const bool legacy = [] { const char *v = getenv("UYD_NMS_LEGACY"); return v && *v == '1'; }();
+  if (!legacy && nc <= 256) {  // fused per-image kernel (needs no workspace)
+    static bool attr_set = false;
+    if (!attr_set) {
+      UYD_CUDA(cudaFuncSetAttribute(nms_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem)));
+      attr_set = true;
+    }
+    nms_image_kernel<<<batch, kFThreads, sizeof(FusedSmem), s>>>(y, nc, anchors, conf_thr, thr_f, max_nms, max_det, max_wh,
+                                                                 conf_thr >= 0.f ? 1 : 0, out_det, out_idx, out_count);
+    UYD_CUDA(cudaGetLastError());
+    return UYD_OK;
+  }
+  Layout L = carve(workspace, batch, anchors);
+  UYD_REQUIRE(L.total <= workspace_bytes, UYD_E_ARG, "uyd_nms: workspace too small (%zu < %zu)", workspace_bytes, L.total);
 
   UYD_CUDA(cudaMemsetAsync(L.count, 0, (size_t)batch * 4, s));
   const bool pos = conf_thr >= 0.f;  // NaN-safe: a NaN threshold selects nothing either way
