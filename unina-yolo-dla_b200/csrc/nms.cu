@@ -375,7 +375,8 @@ struct FusedSmem {
   float4 abox[kFChunk], araw[kFChunk];
   float aarea[kFChunk], aconf[kFChunk];
   int acls[kFChunk], aanchor[kFChunk];
-  unsigned mask[kFChunk][kFChunk / 32];
+  __align__(16) unsigned mask[kFChunk][kFChunk / 32];
+  int klist[kFChunk];
   int warp_cnt[kFThreads / 32];
   unsigned long long kmin, kmax, cut;
   int count, kept, alive;
@@ -529,47 +530,51 @@ __global__ void __launch_bounds__(kFThreads, 1) nms_image_kernel(const float *__
       __syncthreads();
       const int m = S.alive;
       const int words = (m + 31) >> 5;
-      for (int item = tid; item < m * words; item += kFThreads) {
-        const int r = item / words, cw = item % words;
+      // (c) suppression bitmask among survivors (upper triangle), one item = 16 pairs so that all 1024 threads work
+      for (int item = tid; item < m * words * 2; item += kFThreads) {
+        const int r = item / (words * 2), cw = (item >> 1) % words, half = item & 1;
         unsigned bits = 0;
-        if (cw * 32 + 31 > r) {
+        const int j0 = cw * 32 + half * 16;
+        if (j0 + 15 > r) {
           const float4 rb = S.abox[r];
           const float ra = S.aarea[r];
           const int rc = S.acls[r];
-          const int j0 = cw * 32;
 #pragma unroll 4
-          for (int jj = 0; jj < 32; ++jj) {
+          for (int jj = 0; jj < 16; ++jj) {
             const int j = j0 + jj;
             if (j > r && j < m && suppresses<false>(rb, ra, rc, S.abox[j], S.aarea[j], S.acls[j], iou_thr)) bits |= 1u << jj;
           }
         }
-        S.mask[r][cw] = bits;
+        reinterpret_cast<unsigned short *>(&S.mask[r][cw])[half] = (unsigned short)bits;
       }
       __syncthreads();
-      if (wid == 0) {
-        unsigned remv = 0;
-        int k = kept, r = 0;
-        while (k < max_det) {
-          const int base_bit = lane * 32;
-          unsigned alive_bits = ~remv;
-          if (base_bit + 32 <= r) alive_bits = 0u;
-          else if (base_bit < r) alive_bits &= ~0u << (r - base_bit);
-          if (base_bit >= m) alive_bits = 0u;
-          else if (base_bit + 32 > m) alive_bits &= (1u << (m - base_bit)) - 1u;
-          const unsigned lanes = __ballot_sync(0xffffffffu, alive_bits != 0u);
-          if (!lanes) break;
-          const int src_lane = __ffs(lanes) - 1;
-          const int bit = __ffs(__shfl_sync(0xffffffffu, alive_bits, src_lane)) - 1;
-          r = src_lane * 32 + bit;
-          if (lane == 0) {
-            S.kbox[k] = S.abox[r]; S.kraw[k] = S.araw[r]; S.karea[k] = S.aarea[r]; S.kcls[k] = S.acls[r];
-            S.kconf[k] = S.aconf[r]; S.kanchor[k] = S.aanchor[r];
+      // (d) serial resolution by ONE thread with the removal mask in registers (the chain per kept box is
+      // ffs -> one 16-byte row load -> or); the kept-list entries are copied by all threads afterwards
+      if (tid == 0) {
+        unsigned rem[kFChunk / 32] = {0u, 0u, 0u, 0u};
+        int k = kept;
+#pragma unroll
+        for (int w = 0; w < kFChunk / 32; ++w) {
+          if (w >= words) break;
+          const unsigned in_range = (w * 32 + 32 <= m) ? ~0u : ((1u << (m - w * 32)) - 1u);
+          unsigned alive_bits = ~rem[w] & in_range;
+          while (alive_bits && k < max_det) {
+            const int bit = __ffs(alive_bits) - 1, r = w * 32 + bit;
+            S.klist[k - kept] = r;
+            ++k;
+            const uint4 row = *reinterpret_cast<const uint4 *>(S.mask[r]);
+            rem[0] |= row.x; rem[1] |= row.y; rem[2] |= row.z; rem[3] |= row.w;
+            alive_bits = ~rem[w] & in_range & ~((2u << bit) - 1u);
           }
-          ++k;
-          if (lane < words) remv |= S.mask[r][lane];
-          ++r;
         }
-        if (lane == 0) S.kept = k;
+        S.kept = k;
+      }
+      __syncthreads();
+      const int k_new = S.kept - kept;
+      if (tid < k_new) {
+        const int r = S.klist[tid], k = kept + tid;
+        S.kbox[k] = S.abox[r]; S.kraw[k] = S.araw[r]; S.karea[k] = S.aarea[r]; S.kcls[k] = S.acls[r];
+        S.kconf[k] = S.aconf[r]; S.kanchor[k] = S.aanchor[r];
       }
       __syncthreads();
     }
