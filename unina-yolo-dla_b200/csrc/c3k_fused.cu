@@ -18,6 +18,8 @@
 // Every intermediate is rounded to bf16 exactly where the unfused path rounds it, and positions
 // outside the image are forced to zero (each conv zero-pads ITS input), so results equal the
 // unfused plan up to fp32 summation order.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace uyd {
@@ -575,6 +577,10 @@ int cls_branch_launch(int cin, const ClsArgs &a0, cudaStream_t s) {
 // 128 CTAs and 51 us with TH = 8 on 320.)
 int c3k_launch_th(int n, int h, int w) {
   const int tallest = c3k_pick_th(h);
+  if (const char *v = getenv("UYD_C3K_TH")) {  // experiment hook
+    const int th = atoi(v);
+    if (th > 0 && th <= tallest && h % th == 0) return th;
+  }
   const int cands[5] = {32, 20, 16, 8, 4};
   int best = tallest;
   for (int i = 0; i < 5; ++i) {
