@@ -373,8 +373,8 @@ def main():
     tj = ROOT / "profiles" / "roofline_traffic.json"
     if tj.exists():
         traffic = json.loads(tj.read_text()).get(top_text)
-    # conv stack (+ DFL decode per level when the plan does not decode in its head kernels) + 5 NMS kernels (cub sort excluded)
-    kernels_per_step = plan.launches + (0 if plan.fused else len(plan.heads)) + 5
+    # conv stack (+ DFL decode per level when the plan does not decode in its head kernels) + the fused NMS kernel
+    kernels_per_step = plan.launches + (0 if plan.fused else len(plan.heads)) + 1
     conv_flops = sum(plan.op_info(i)[1] for i in range(plan.launches))
     out = {
         "metric": METRIC, "value": world * B * a.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,

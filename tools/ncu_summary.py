@@ -2,7 +2,7 @@
 into the committed summaries under profiles/:
    profiles/<name>_launches.md   per-kernel totals of ONE predict step (ncu gpu__time_duration, cold, serialised)
    profiles/<name>_kernels.md    per-launch metrics of the captured kernels (time, DRAM bytes, throughputs, stalls)
-Usage: python tools/ncu_summary.py <tag> <name>"""
+Usage: python tools/ncu_summary.py <tag> <name> [rep-suffix ...]   (default rep: <tag>_step.ncu-rep)"""
 import csv
 import subprocess
 import sys
@@ -45,9 +45,13 @@ M = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", 
      "lts__throughput.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_tensor.sum", "smsp__inst_executed.sum",
      "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
      "smsp__cycles_active.avg", "sm__pipe_tensor_op_hmma_cycles_active.avg.pct_of_peak_sustained_active"]
-rep = ROOT / "gpurun_out" / f"{tag}_step.ncu-rep"
-raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv", "--metrics", ",".join(M)], capture_output=True, text=True).stdout
-rr = list(csv.reader(raw.splitlines()))
+suffixes = sys.argv[3:] or ["step"]
+rr = []
+for sfx in suffixes:
+    rep = ROOT / "gpurun_out" / f"{tag}_{sfx}.ncu-rep"
+    raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv", "--metrics", ",".join(M)], capture_output=True, text=True).stdout
+    part = list(csv.reader(raw.splitlines()))
+    rr = part if not rr else rr + part[2:]
 hh, units = rr[0], rr[1]
 jx = {n: i for i, n in enumerate(hh)}
 cols = [m for m in M if m in jx]
