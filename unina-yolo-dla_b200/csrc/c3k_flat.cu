@@ -1,0 +1,242 @@
+// Fused C3k block kernel, flat-frame formulation: see c3k_flat.cuh for the design and the per-lane maps.
+#include "c3k_flat.cuh"
+
+#include "common.cuh"
+
+namespace uyd {
+
+struct C3kArgs {  // same struct as in c3k_fused.cu / api.cu
+  const __nv_bfloat16 *in;
+  __nv_bfloat16 *out;
+  const uint32_t *wfrag;
+  const float *bias;
+  int n, h, w, in_pitch, out_pitch, th, tiles_x, tiles_y;
+};
+
+namespace {
+using namespace c3kf;
+
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int KS, int NT>
+__device__ __forceinline__ void load_b(const uint32_t *wf, int lane, uint32_t (&bf)[KS][NT][2]) {
+#pragma unroll
+  for (int s = 0; s < KS; ++s)
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const uint2 v = __ldg(reinterpret_cast<const uint2 *>(wf) + (s * NT + j) * 32 + lane);
+      bf[s][j][0] = v.x;
+      bf[s][j][1] = v.y;
+    }
+}
+
+template <int NT>
+__device__ __forceinline__ void init_acc(float (&acc)[NT][4], const float (&bz)[NT][2]) {
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    acc[j][0] = acc[j][2] = bz[j][0];
+    acc[j][1] = acc[j][3] = bz[j][1];
+  }
+}
+
+template <int C, bool RES>
+__device__ __forceinline__ void run_conv3(const unsigned char *S, unsigned char *D, const uint32_t *wf, const float *bias,
+                                          const uint32_t *maskw, int blk_lo, int blk_hi, int warp, int lane, int nwarps) {
+  using G = Geo<C>;
+  using St = Stage3<C>;
+  uint32_t bf[St::KS][St::NT][2];
+  load_b<St::KS, St::NT>(wf, lane, bf);
+  float bz[St::NT][2];
+  St::bias_regs(bias, lane, bz);
+  for (int blk = blk_lo + warp; blk < blk_hi; blk += nwarps) {
+    const int f = blk * 32;
+    const uint32_t mw = maskw[blk];
+#pragma unroll
+    for (int mt = 0; mt < G::MT; ++mt) {
+      float acc[St::NT][4];
+      init_acc<St::NT>(acc, bz);
+#pragma unroll
+      for (int s = 0; s < St::KS; ++s) {
+        uint32_t a[4];
+        St::load_a(S, f, lane, s, mt, a);
+#pragma unroll
+        for (int j = 0; j < St::NT; ++j) mma16816(acc[j], a, bf[s][j][0], bf[s][j][1]);
+      }
+      St::template store<RES>(D, f, lane, mt, acc, mw);
+    }
+  }
+}
+
+template <int C, int NW>
+__global__ void __launch_bounds__(NW * 32) c3k_flat_kernel(C3kArgs a) {
+  pdl_trigger();
+  using G = Geo<C>;
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int TH = a.th;
+  const Layout L = make_layout<C>(TH);
+  unsigned char *X = smem + L.x_off;   // x frame [FR][2C]; later t frame [FR][C] and the staged y tile [TH*48][2C]
+  unsigned char *A = smem + L.a_off;   // a -> u -> v  [FR][C]
+  unsigned char *Bv = smem + L.b_off;  // b            [TH*48][C], origin = frame row 4
+  uint32_t *maskw = reinterpret_cast<uint32_t *>(smem + L.mask_off);
+  float *sbias = reinterpret_cast<float *>(smem + L.bias_off);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.x;
+  const int n = tile / (a.tiles_x * a.tiles_y);
+  const int tr = tile % (a.tiles_x * a.tiles_y);
+  const int ty0 = (tr / a.tiles_x) * TH, tx0 = (tr % a.tiles_x) * kTW;
+  const int gy0 = ty0 - 4, gx0 = tx0 - 4;  // image coordinates of frame pixel 0
+  const int H = a.h, W = a.w;
+  constexpr int NT = NW * 32;
+
+  for (int i = tid; i < 7 * 32; i += NT) sbias[i] = a.bias[i];
+  // inside-image bit per frame pixel (rows and columns outside the image are every conv's zero padding)
+  for (int i = tid; i < L.FR / 32; i += NT) {
+    uint32_t m = 0u;
+    int ry = (i * 32) / kPW, rx = (i * 32) % kPW;
+    for (int b = 0; b < 32; ++b) {
+      if ((unsigned)(gy0 + ry) < (unsigned)H && (unsigned)(gx0 + rx) < (unsigned)W) m |= 1u << b;
+      if (++rx == kPW) { rx = 0; ++ry; }
+    }
+    maskw[i] = m;
+  }
+  // ---- stage 0: input tile + halo -> X (zero outside the image) ----
+  {
+    constexpr int CH16 = G::CC / 8;  // 16-byte chunks per pixel
+    const __nv_bfloat16 *img = a.in + (long long)n * H * W * a.in_pitch;
+    const int total = L.FR * CH16;
+#pragma unroll 4
+    for (int i = tid; i < total; i += NT) {
+      const int px = i / CH16, ch = i % CH16;
+      const int ry = px / kPW, rx = px - ry * kPW;
+      const int gy = gy0 + ry, gx = gx0 + rx;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if ((unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W)
+        v = __ldg(reinterpret_cast<const uint4 *>(img + ((long long)gy * W + gx) * a.in_pitch + ch * 8));
+      reinterpret_cast<uint4 *>(X)[i] = v;
+    }
+  }
+  __syncthreads();
+
+  const uint32_t *wf = a.wfrag;
+  // ---- stage 1: a on the whole frame, b on the output rows ----
+  {
+    using St = Stage1<C>;
+    uint32_t bf[St::KS][St::NT][2];
+    load_b<St::KS, St::NT>(wf, lane, bf);
+    float bz[St::NT][2];
+    St::bias_regs(sbias, lane, bz);
+    const int b_lo = kB0 / 32, b_hi = (TH + 4) * kPW / 32;
+    for (int blk = warp; blk < L.FR / 32; blk += NW) {
+      const int f = blk * 32;
+      const uint32_t mw = maskw[blk];
+      const bool do_b = blk >= b_lo && blk < b_hi;
+#pragma unroll
+      for (int mt = 0; mt < G::MT; ++mt) {
+        float acc[St::NT][4];
+        init_acc<St::NT>(acc, bz);
+#pragma unroll
+        for (int s = 0; s < St::KS; ++s) {
+          uint32_t af[4];
+          St::load_a(X, f, lane, s, mt, af);
+#pragma unroll
+          for (int j = 0; j < St::NT; ++j) mma16816(acc[j], af, bf[s][j][0], bf[s][j][1]);
+        }
+        St::store(A, Bv, f, lane, mt, acc, mw, do_b);
+      }
+    }
+  }
+  __syncthreads();
+  // ---- stages 2..5: t1 = m0.cv1(a); u = a + m0.cv2(t1); t2 = m1.cv1(u); v = u + m1.cv2(t2)  (t aliases x) ----
+  unsigned char *T = X;
+  int lo, hi;
+  conv3_blocks(0, TH, lo, hi);
+  run_conv3<C, false>(A, T, wf + G::W1, sbias + 2 * 32, maskw, lo, hi, warp, lane, NW);
+  __syncthreads();
+  conv3_blocks(1, TH, lo, hi);
+  run_conv3<C, true>(T, A, wf + G::W1 + G::W3, sbias + 3 * 32, maskw, lo, hi, warp, lane, NW);
+  __syncthreads();
+  conv3_blocks(2, TH, lo, hi);
+  run_conv3<C, false>(A, T, wf + G::W1 + 2 * G::W3, sbias + 4 * 32, maskw, lo, hi, warp, lane, NW);
+  __syncthreads();
+  conv3_blocks(3, TH, lo, hi);
+  run_conv3<C, true>(T, A, wf + G::W1 + 3 * G::W3, sbias + 5 * 32, maskw, lo, hi, warp, lane, NW);
+  __syncthreads();
+  // ---- stage 6: y = cv3([v | b]) on the output rows -> staged in X (t is dead) ----
+  {
+    using St = Stage6<C>;
+    uint32_t bf[St::KS][St::NT][2];
+    load_b<St::KS, St::NT>(wf + G::W1 + 4 * G::W3, lane, bf);
+    float bz[St::NT][2];
+    St::bias_regs(sbias + 6 * 32, lane, bz);
+    const int b_lo = kB0 / 32, b_hi = (TH + 4) * kPW / 32;
+    for (int blk = b_lo + warp; blk < b_hi; blk += NW) {
+      const int f = blk * 32;
+#pragma unroll
+      for (int mt = 0; mt < G::MT; ++mt) {
+        float acc[St::NT][4];
+        init_acc<St::NT>(acc, bz);
+#pragma unroll
+        for (int s = 0; s < St::KS; ++s) {
+          uint32_t af[4];
+          St::load_a(A, Bv, f, lane, s, mt, af);
+#pragma unroll
+          for (int j = 0; j < St::NT; ++j) mma16816(acc[j], af, bf[s][j][0], bf[s][j][1]);
+        }
+        St::store(X, f, lane, mt, acc);
+      }
+    }
+  }
+  __syncthreads();
+  {
+    constexpr int CH16 = G::CC / 8;
+    __nv_bfloat16 *img = a.out + (long long)n * H * W * a.out_pitch;
+    const int total = TH * kTW * CH16;
+#pragma unroll 4
+    for (int i = tid; i < total; i += NT) {
+      const int px = i / CH16, ch = i % CH16;
+      const int ry = px / kTW, rx = px - ry * kTW;
+      *reinterpret_cast<uint4 *>(img + ((long long)(ty0 + ry) * W + tx0 + rx) * a.out_pitch + ch * 8) =
+          *reinterpret_cast<const uint4 *>(X + ((ry * kPW + rx + 4) * CH16 + ch) * 16);
+    }
+  }
+}
+
+}  // namespace
+
+size_t c3k_flat_smem_bytes(int c_, int th) {
+  return c_ == 4 ? make_layout<4>(th).total : (c_ == 8 ? make_layout<8>(th).total : make_layout<16>(th).total);
+}
+
+int c3k_flat_words(int c) { return c == 8 ? Geo<4>::WORDS : (c == 16 ? Geo<8>::WORDS : Geo<16>::WORDS); }
+
+void c3k_flat_pack(int c, const float *const w[7], std::vector<uint32_t> &frags) {
+  if (c == 8) pack_all<4>(w, frags);
+  else if (c == 16) pack_all<8>(w, frags);
+  else pack_all<16>(w, frags);
+}
+
+// a.th / tiles_x / tiles_y are set by the caller (c3k_launch); a.wfrag points at the flat-layout fragments.
+int c3k_flat_launch(int c, const C3kArgs &a, cudaStream_t s) {
+  const size_t smem = c3k_flat_smem_bytes(c / 2, a.th);
+  const unsigned grid = (unsigned)(a.n * a.tiles_x * a.tiles_y);
+  static bool attr[3] = {false, false, false};
+  auto go = [&](auto kern, int idx, int threads) -> int {
+    if (!attr[idx]) {
+      UYD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr[idx] = true;
+    }
+    kern<<<grid, threads, smem, s>>>(a);
+    return (int)cudaGetLastError();
+  };
+  if (c == 8) return go(c3k_flat_kernel<4, 8>, 0, 256);
+  if (c == 16) return go(c3k_flat_kernel<8, 8>, 1, 256);
+  return go(c3k_flat_kernel<16, 16>, 2, 512);
+}
+
+}  // namespace uyd

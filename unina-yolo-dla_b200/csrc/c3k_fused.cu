@@ -24,6 +24,12 @@
 
 namespace uyd {
 
+// c3k_flat.cu: the second-generation kernel (default); this file's c3k_fused_kernel stays behind UYD_C3K_LEGACY=1
+size_t c3k_flat_smem_bytes(int c_, int th);
+void c3k_flat_pack(int c, const float *const w[7], std::vector<uint32_t> &frags);
+struct C3kArgs;
+int c3k_flat_launch(int c, const C3kArgs &a, cudaStream_t s);
+
 struct C3kArgs {
   const __nv_bfloat16 *in;
   __nv_bfloat16 *out;
@@ -525,6 +531,13 @@ void c3k_pack(int c, const float *const w[7], const float *const b[7], std::vect
     const int k = 16 * s + kk;
     return k < c ? w6[(size_t)n * c + k] : 0.f;
   });
+  c3k_flat_pack(c, w, frags);  // the flat-frame kernel's fragments follow the legacy ones (c3k_legacy_words)
+}
+
+// words of legacy fragments in front of the flat-frame ones
+static int c3k_legacy_words(int c) {
+  const int C = c / 2, tpk = 16 / C, steps3 = (9 + tpk - 1) / tpk;
+  return 2 * frag_words_1(c, C) + 4 * steps3 * ((C + 7) / 8) * 64 + frag_words_1(c, c);
 }
 
 bool cls_branch_supported(int cin, int mid, int nc, int h, int w, int in_pitch, int in_coff, int out_pitch, int out_coff) {
@@ -597,6 +610,11 @@ int c3k_launch(int c, const C3kArgs &a0, cudaStream_t s) {
   a.th = c3k_launch_th(a.n, a.h, a.w);
   a.tiles_x = a.w / kTW;
   a.tiles_y = a.h / a.th;
+  static const bool legacy = [] { const char *v = getenv("UYD_C3K_LEGACY"); return v && *v == '1'; }();
+  if (!legacy) {
+    a.wfrag += c3k_legacy_words(c);
+    return c3k_flat_launch(c, a, s);
+  }
   const size_t smem = c3k_smem_bytes(c / 2, a.th);
   const unsigned grid = (unsigned)(a.n * a.tiles_x * a.tiles_y);
   static bool attr[3] = {false, false, false};
