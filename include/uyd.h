@@ -92,6 +92,11 @@ int uyd_plan_add_conv(uyd_plan *plan, const uyd_conv *desc, const float *weight,
  * The output buffer has a quarter of the frame extent. */
 int uyd_plan_add_stem2(uyd_plan *plan, int out_buf, int out_coff, const float *w0, const float *b0, const float *w1,
                        const float *b1);
+/* The same launch with the 1x1 Conv(32,16)+BN+ReLU that consumes the stem folded in (model.2.cv1 of
+ * unina-yolo-dla-m.yaml, ultralytics C3k2.cv1): w2 [16][32], b2 [16].  The stem's 32-channel output is rounded to
+ * bf16 in registers and never written; the 16-channel output slice needs 8-byte alignment. */
+int uyd_plan_add_stem2_pw(uyd_plan *plan, int out_buf, int out_coff, const float *w0, const float *b0, const float *w1,
+                          const float *b1, const float *w2, const float *b2);
 
 /* INT8 convolution (QAT fake-quant semantics of qat.py:109-124 as an integer computation,
  * oracle/quant.py): input slice int8 (UYD_S8 buffer), weight int8 [cout][cin][k][k] already

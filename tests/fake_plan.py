@@ -43,9 +43,9 @@ class FakePlan:
         self.ops.append(("cls", src, dst, [torch.from_numpy(w) for w in weights], [torch.from_numpy(b) for b in biases]))
         return dst
 
-    def stem2(self, dst, w0, b0, w1, b1):
-        t = lambda a: torch.as_tensor(a, dtype=torch.float32)
-        self.ops.append(("stem2", dst, t(w0), t(b0), t(w1), t(b1)))
+    def stem2(self, dst, w0, b0, w1, b1, w2=None, b2=None):
+        t = lambda a: None if a is None else torch.as_tensor(a, dtype=torch.float32)
+        self.ops.append(("stem2", dst, t(w0), t(b0), t(w1), t(b1), t(w2), t(b2)))
         return dst
 
     @staticmethod
@@ -82,9 +82,12 @@ class FakePlan:
         self.y = None
         for op in self.ops:
             if op[0] == "stem2":
-                _, dst, w0, b0, w1, b1 = op
+                _, dst, w0, b0, w1, b1, w2, b2 = op
                 t = F.conv2d(x, w0, b0, stride=2, padding=1).relu()
-                bufs[dst.buf][:, dst.coff:dst.coff + dst.c] = F.conv2d(t, w1, b1, stride=2, padding=1).relu()
+                t = F.conv2d(t, w1, b1, stride=2, padding=1).relu()
+                if w2 is not None:
+                    t = F.conv2d(t, w2.reshape(16, 32, 1, 1), b2).relu()
+                bufs[dst.buf][:, dst.coff:dst.coff + dst.c] = t
             elif op[0] == "chain":
                 _, src, out, w1, b1, w2, b2, dw1, relu2, final, w3, b3, (a_total, a_off, y_ch0, no, stride) = op
                 xin = get(src)

@@ -467,10 +467,11 @@ def test_fused_decode_plan_equals_raw_head_plan(T):
     assert float((y_fused.cpu()[:, 4:] - y_ref[:, 4:]).abs().max()) <= 1e-2
 
 
-@pytest.mark.parametrize("H,W,u8", [(64, 96, False), (160, 128, True), (640, 640, False)])
-def test_fused_stem_matches_torch(T, H, W, u8):
-    """Conv(3,16,3,2) -> Conv(16,32,3,2) in one launch: the frame is not rounded (hi + lo bf16 parts),
-    the 16-channel intermediate is rounded to bf16 exactly where the unfused plan rounds it."""
+@pytest.mark.parametrize("H,W,u8,pw", [(64, 96, False, False), (160, 128, True, False), (640, 640, False, False),
+                                        (64, 96, True, True), (100, 136, False, True), (640, 640, True, True)])
+def test_fused_stem_matches_torch(T, H, W, u8, pw):
+    """Conv(3,16,3,2) -> Conv(16,32,3,2) (-> 1x1 Conv(32,16), model.2.cv1) in one launch: the frame is rounded to
+    tf32 (2^-11), the 16- and 32-channel intermediates are rounded to bf16 exactly where the unfused plan rounds them."""
     import torch.nn.functional as F
     import unina_yolo_dla_b200 as uyd
 
@@ -478,23 +479,31 @@ def test_fused_stem_matches_torch(T, H, W, u8):
     B = 2
     r = T.bf16_round
     w0, w1 = torch.randn(16, 3, 3, 3, generator=g) / 27 ** 0.5, torch.randn(32, 16, 3, 3, generator=g) / 144 ** 0.5
-    b0, b1 = torch.randn(16, generator=g) * 0.1, torch.randn(32, generator=g) * 0.1
+    w2 = torch.randn(16, 32, 1, 1, generator=g) / 32 ** 0.5
+    b0, b1, b2 = (torch.randn(n, generator=g) * 0.1 for n in (16, 32, 16))
     if u8:
         xin = (torch.rand(B, 3, H, W, generator=g) * 255).to(torch.uint8)
         xf = xin.float() / 255
     else:
         xin = xf = torch.rand(B, 3, H, W, generator=g)
     p = uyd.Plan(0, B)
-    dst = p.buffer(H // 4, W // 4, 48).sub(16, 32)
-    p.stem2(dst, w0.numpy(), b0.numpy(), w1.numpy(), b1.numpy())
+    if pw:
+        dst = p.buffer(H // 4, W // 4, 36).sub(4, 16)
+        p.stem2(dst, w0.numpy(), b0.numpy(), w1.numpy(), b1.numpy(), w2.numpy(), b2.numpy())
+    else:
+        dst = p.buffer(H // 4, W // 4, 48).sub(16, 32)
+        p.stem2(dst, w0.numpy(), b0.numpy(), w1.numpy(), b1.numpy())
     p.finalize()
     p.run(xin.cuda())
     torch.cuda.synchronize()
     got = p.read(dst, B).cpu()
     t = r(F.conv2d(xf, r(w0), b0, stride=2, padding=1).relu())
     want = r(F.conv2d(t, r(w1), b1, stride=2, padding=1).relu())
+    if pw:
+        want = r(F.conv2d(want, r(w2), b2).relu())
     assert T.rel_err(got, want) < 6e-3
-    assert float(p.read(p.buffer_slice(dst.buf, 0, 16), B).abs().max()) == 0.0   # nothing outside the slice
+    assert float(p.read(p.buffer_slice(dst.buf, 0, dst.coff), B).abs().max()) == 0.0   # nothing outside the slice
+    assert float(p.read(p.buffer_slice(dst.buf, dst.coff + dst.c, p.shapes[dst.buf][2] - dst.coff - dst.c), B).abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("ca,cb,cout,h,w", [(64, 32, 16, 40, 40), (128, 64, 32, 24, 40), (64, 32, 16, 160, 160)])

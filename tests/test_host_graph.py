@@ -39,10 +39,10 @@ def test_emitted_plan_equals_oracle_network(monkeypatch):
         assert torch.allclose(got, feats[i], rtol=1e-4, atol=1e-4), f"layer {i} differs"
     for h, r in zip(p.heads, raw_ref):
         assert torch.allclose(bufs[h.buf], r, rtol=1e-4, atol=1e-4)
-    # census: 158 convs (2 inside the fused stem, 19 inside the 8 chained head launches) + 1 pool cascade +
-    # 2 upsamples, no concat / chunk op at all
+    # census: 158 convs (3 inside the fused stem: layers 0, 1 and model.2.cv1; 19 inside the 8 chained head launches)
+    # + 1 pool cascade + 2 upsamples, no concat / chunk op at all
     kinds = [o[0] for o in p.ops]
-    assert kinds.count("stem2") == 1 and kinds.count("chain") == 8 and kinds.count("conv") == 158 - 2 - 19 + 2
+    assert kinds.count("stem2") == 1 and kinds.count("chain") == 8 and kinds.count("conv") == 158 - 3 - 19 + 2
     # + 2 half-resolution partial-sum convs: both Upsample + Concat pairs are folded into the next C3k2's first conv
     assert kinds.count("sppf") == 1 and kinds.count("up") == 0
 
@@ -131,9 +131,9 @@ def test_emitted_plan_uses_fused_c3k_at_full_resolution(monkeypatch):
         y_ref, raw_ref = ref(x)
     p = _emit_fake(m, 1, 640, 640, monkeypatch)
     kinds = [o[0] for o in p.ops]
-    # the fused stem (2 convs), 16 fused C3k blocks (7 convs each) and 8 chained head launches (19 convs)
+    # the fused stem (3 convs), 16 fused C3k blocks (7 convs each) and 8 chained head launches (19 convs)
     assert kinds.count("stem2") == 1 and kinds.count("c3k") == 16 and kinds.count("chain") == 8
-    assert kinds.count("conv") == 158 - 2 - 16 * 7 - 19 + 2 and kinds.count("up") == 0
+    assert kinds.count("conv") == 158 - 3 - 16 * 7 - 19 + 2 and kinds.count("up") == 0
     bufs = p.execute(x)
     for h, r in zip(p.heads, raw_ref):
         assert torch.allclose(bufs[h.buf], r, rtol=1e-4, atol=1e-4)

@@ -24,7 +24,7 @@ def _nvcc() -> str:
 
 def build(force: bool = False, verbose: bool = False) -> Path:
     srcs = [CSRC / s for s in SOURCES]
-    deps = srcs + [CSRC / "c3k_flat.cuh", CSRC / "tc_ptx.cuh", CSRC / "common.cuh", HERE.parent / "include" / "uyd.h"]
+    deps = srcs + [CSRC / "stem_v2.cuh", CSRC / "c3k_flat.cuh", CSRC / "tc_ptx.cuh", CSRC / "common.cuh", HERE.parent / "include" / "uyd.h"]
     if not force and LIB.exists() and all(d.stat().st_mtime <= LIB.stat().st_mtime for d in deps):
         return LIB
     objs = []
@@ -32,7 +32,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     logs = []
     for s in srcs:
         o = HERE / "build" / (s.stem + ".o")
-        if force or not o.exists() or any(d.stat().st_mtime > o.stat().st_mtime for d in (s, deps[-4], deps[-3], deps[-2], deps[-1])):
+        if force or not o.exists() or any(d.stat().st_mtime > o.stat().st_mtime for d in (s, *deps[len(srcs):])):
             r = subprocess.run([_nvcc(), *NVCC_FLAGS, "-c", str(s), "-o", str(o)], capture_output=True, text=True)
             logs.append(r.stderr)
             if r.returncode != 0:

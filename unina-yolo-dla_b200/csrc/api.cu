@@ -80,11 +80,11 @@ struct StemArgs {
   __nv_bfloat16 *out;
   const uint32_t *wfrag;
   const float *bias;
-  int n, ih, iw, oh, ow, out_pitch, u8;
+  int n, ih, iw, oh, ow, out_pitch, u8, pw;
 };
 bool stem_fused_supported(int c0, int c1, int ih, int iw, int out_pitch, int out_coff);
-void stem_fused_pack(const float *w0, const float *b0, const float *w1, const float *b1, std::vector<uint32_t> &frags,
-                     std::vector<float> &bias);
+void stem_fused_pack(const float *w0, const float *b0, const float *w1, const float *b1, const float *w2, const float *b2,
+                     std::vector<uint32_t> &frags, std::vector<float> &bias);
 int stem_fused_launch(const StemArgs &a, cudaStream_t s);
 
 static int env_int(const char *name, int dflt) {
@@ -439,26 +439,38 @@ extern "C" int uyd_plan_add_chain(uyd_plan *plan, const uyd_chain *d, const floa
   return UYD_OK;
 }
 
-extern "C" int uyd_plan_add_stem2(uyd_plan *plan, int out_buf, int out_coff, const float *w0, const float *b0, const float *w1,
-                                  const float *b1) {
+static int add_stem(uyd_plan *plan, int out_buf, int out_coff, const float *w0, const float *b0, const float *w1, const float *b1,
+                    const float *w2, const float *b2) {
   UYD_REQUIRE(plan && w0 && b0 && w1 && b1, UYD_E_ARG, "uyd_plan_add_stem2: NULL argument");
   UYD_REQUIRE(!plan->finalized, UYD_E_STATE, "plan already finalized");
   UYD_REQUIRE(plan->ops.empty(), UYD_E_ARG, "only the first op may read the network input");
+  const int cout = w2 ? 16 : 32;
   int e;
-  if ((e = check_slice(plan, out_buf, out_coff, 32, "stem2 output"))) return e;
+  if ((e = check_slice(plan, out_buf, out_coff, cout, "stem2 output"))) return e;
   const Buffer &ob = plan->bufs[out_buf];
-  UYD_REQUIRE(ob.dtype == UYD_BF16 && stem_fused_supported(16, 32, ob.h * 4, ob.w * 4, ob.c, out_coff), UYD_E_UNSUPPORTED,
-              "stem2: bf16 output slice with 16-byte alignment");
+  UYD_REQUIRE(ob.dtype == UYD_BF16 && stem_fused_supported(16, 32, ob.h * 4, ob.w * 4, w2 ? 2 * ob.c : ob.c, w2 ? 2 * out_coff : out_coff),
+              UYD_E_UNSUPPORTED, "stem2: bf16 output slice, 16-byte aligned (8-byte with the 1x1 folded in)");
   plan->in_c = 3; plan->in_h = ob.h * 4; plan->in_w = ob.w * 4;
   Op op;
   op.kind = OP_STEM2;
-  op.out_buf = out_buf; op.out_coff = out_coff;
+  op.out_buf = out_buf; op.out_coff = out_coff; op.c = w2 ? 1 : 0;
   std::vector<uint32_t> frags;
-  stem_fused_pack(w0, b0, w1, b1, frags, op.b_host);
+  stem_fused_pack(w0, b0, w1, b1, w2, b2, frags, op.b_host);
   op.w_host.resize(frags.size() * 4);
   memcpy(op.w_host.data(), frags.data(), op.w_host.size());
   plan->ops.push_back(std::move(op));
   return UYD_OK;
+}
+
+extern "C" int uyd_plan_add_stem2(uyd_plan *plan, int out_buf, int out_coff, const float *w0, const float *b0, const float *w1,
+                                  const float *b1) {
+  return add_stem(plan, out_buf, out_coff, w0, b0, w1, b1, nullptr, nullptr);
+}
+
+extern "C" int uyd_plan_add_stem2_pw(uyd_plan *plan, int out_buf, int out_coff, const float *w0, const float *b0, const float *w1,
+                                     const float *b1, const float *w2, const float *b2) {
+  UYD_REQUIRE(w2 && b2, UYD_E_ARG, "uyd_plan_add_stem2_pw: NULL argument");
+  return add_stem(plan, out_buf, out_coff, w0, b0, w1, b1, w2, b2);
 }
 
 extern "C" int uyd_plan_add_quantize(uyd_plan *plan, int in_buf, int in_coff, int out_buf, int out_coff, int c, float scale) {
@@ -677,7 +689,7 @@ static int launch_op(uyd_plan *plan, const Op &o, const void *x, int x_kind, int
       StemArgs a{};
       a.in = x; a.out = (__nv_bfloat16 *)slice_ptr(plan, o.out_buf, o.out_coff);
       a.wfrag = (const uint32_t *)o.w_dev; a.bias = o.b_dev;
-      a.n = batch; a.ih = plan->in_h; a.iw = plan->in_w; a.oh = ob.h; a.ow = ob.w; a.out_pitch = ob.c; a.u8 = x_kind == 2;
+      a.n = batch; a.ih = plan->in_h; a.iw = plan->in_w; a.oh = ob.h; a.ow = ob.w; a.out_pitch = ob.c; a.u8 = x_kind == 2; a.pw = o.c;
       e = stem_fused_launch(a, s);
     } else if (o.kind == OP_CHAIN) {
       UYD_REQUIRE(y || o.chain.out_buf >= 0, UYD_E_ARG, "this plan decodes in its head kernels: run it with uyd_plan_run_decoded");
@@ -830,9 +842,9 @@ extern "C" int uyd_plan_op_info(uyd_plan *plan, int op, char *text, size_t text_
     snprintf(text, text_len, "quantize c%d %dx%d bf16->s8", o.c, b.h, b.w);
   } else if (o.kind == OP_STEM2) {
     const Buffer &b = plan->bufs[o.out_buf];
-    fl = 2.0 * (4.0 * b.h * b.w * 16 * 27 + (double)b.h * b.w * 32 * 144);
-    by = 16.0 * b.h * b.w * 3 * 4 + (double)b.h * b.w * 32 * 2;
-    snprintf(text, text_len, "stem2 3->16 k3 s2 + 16->32 k3 s2 fused -> %dx%d", b.h, b.w);
+    fl = 2.0 * (4.0 * b.h * b.w * 16 * 27 + (double)b.h * b.w * 32 * 144 + (o.c ? (double)b.h * b.w * 16 * 32 : 0.0));
+    by = 16.0 * b.h * b.w * 3 * 4 + (double)b.h * b.w * (o.c ? 16 : 32) * 2;
+    snprintf(text, text_len, "stem2 3->16 k3 s2 + 16->32 k3 s2%s fused -> %dx%d", o.c ? " + 32->16 k1" : "", b.h, b.w);
   } else if (o.kind == OP_CHAIN) {
     const uyd_chain &d = o.chain;
     const Buffer &b = plan->bufs[d.in_buf];

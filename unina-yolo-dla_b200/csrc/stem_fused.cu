@@ -11,6 +11,8 @@
 //     4-byte aligned shared-memory word);
 //   * its bf16 result (zero outside the image = layer 1's padding) never leaves shared memory;
 //   * layer 1 is nine k-steps of mma.sync (one filter tap = 16 channels per step).
+#include "stem_v2.cuh"
+
 #include "common.cuh"
 
 namespace uyd {
@@ -21,6 +23,7 @@ struct StemArgs {
   const uint32_t *wfrag;  // [L0: 3 k-steps x 2 n-tiles | L1: 9 k-steps x 4 n-tiles] x 32 lanes x 2 words
   const float *bias;      // [16 | 32]
   int n, ih, iw, oh, ow, out_pitch, u8;
+  int pw;  // 1: the 1x1 Conv(32,16) follows in the same launch (second-generation kernel only); out has 16 channels
 };
 
 namespace {
@@ -227,6 +230,201 @@ __global__ void __launch_bounds__(kThreads) stem_fused_kernel(StemArgs a) {
   }
 }
 
+// =================================================================================================
+// Second generation (design and lane maps: stem_v2.cuh)
+// =================================================================================================
+__device__ __forceinline__ void mma1688_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+
+template <typename TIn, bool PW>
+__global__ void __launch_bounds__(stemv2::kThreads) stem_v2_kernel(StemArgs a) {
+  using namespace stemv2;
+  pdl_trigger();
+  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned char *patch = smem;                                               // [3][35][68] fp32, tf32-rounded
+  unsigned char *l0s = smem + kPatchBytes;                                   // [576][48 B]: 16 bf16 channels + pad
+  uint32_t *w1s = reinterpret_cast<uint32_t *>(smem + kPatchBytes + kL0Bytes);  // layer-1 fragments
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int ox0 = blockIdx.x * kTW, oy0 = blockIdx.y * kTH, n = blockIdx.z;
+  const int ix0 = 4 * ox0 - 4, iy0 = 4 * oy0 - 3;  // frame coordinates of the patch origin (16-byte aligned columns)
+
+  // ---- all global loads first: layer-1 fragments and this thread's 7 patch vectors (column j, rows rl + 15 i) ----
+  constexpr int kW1Vec = kW1Words / 4, kWIters = (kW1Vec + kThreads - 1) / kThreads;
+  const uint4 *w1g = reinterpret_cast<const uint4 *>(a.wfrag + kW0Words);
+  uint4 wv[kWIters];
+#pragma unroll
+  for (int it = 0; it < kWIters; ++it) {
+    const int i = tid + it * kThreads;
+    wv[it] = i < kW1Vec ? __ldg(w1g + i) : make_uint4(0u, 0u, 0u, 0u);
+  }
+  constexpr int kVecPerRow = kInW / 4;                  // 17
+  constexpr int kRowLanes = 15, kPIters = 3 * kInH / kRowLanes;  // 105 (channel, row) lines = 15 x 7
+  static_assert(kRowLanes * kPIters == 3 * kInH && kRowLanes * kVecPerRow <= kThreads, "patch load map");
+  const TIn *img = reinterpret_cast<const TIn *>(a.in) + (long long)n * 3 * a.ih * a.iw;
+  const int pj = tid % kVecPerRow, prl = tid / kVecPerRow;
+  const int ix = ix0 + 4 * pj;
+  const bool col_ok = prl < kRowLanes && ix >= 0 && ix + 3 < a.iw;
+  float pv[kPIters][4];
+  {
+    int c = 0, r = prl;
+#pragma unroll
+    for (int it = 0; it < kPIters; ++it) {
+      const int iy = iy0 + r;
+      pv[it][0] = pv[it][1] = pv[it][2] = pv[it][3] = 0.f;
+      if (col_ok && (unsigned)iy < (unsigned)a.ih) {
+        const TIn *src = img + ((long long)c * a.ih + iy) * a.iw + ix;
+        if (sizeof(TIn) == 4) {
+          const float4 q = __ldg(reinterpret_cast<const float4 *>(src));
+          pv[it][0] = q.x; pv[it][1] = q.y; pv[it][2] = q.z; pv[it][3] = q.w;
+        } else {
+          const uchar4 q = __ldg(reinterpret_cast<const uchar4 *>(src));
+          pv[it][0] = (float)q.x; pv[it][1] = (float)q.y; pv[it][2] = (float)q.z; pv[it][3] = (float)q.w;
+        }
+      }
+      r += kRowLanes;
+      if (r >= kInH) { r -= kInH; ++c; }
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < kWIters; ++it) {
+    const int i = tid + it * kThreads;
+    if (i < kW1Vec) reinterpret_cast<uint4 *>(w1s)[i] = wv[it];
+  }
+  if (prl < kRowLanes) {
+#pragma unroll
+    for (int it = 0; it < kPIters; ++it) {
+      uint4 o;
+      uint32_t *op = reinterpret_cast<uint32_t *>(&o);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) op[e] = to_tf32(sizeof(TIn) == 1 ? div255(pv[it][e]) : pv[it][e]);
+      // line (c, r) = prl + 15 it of the [3][35] plane stack: the stack is contiguous, so the line index is enough
+      *reinterpret_cast<uint4 *>(patch + ((prl + kRowLanes * it) * kInW + 4 * pj) * 4) = o;
+    }
+  }
+  __syncthreads();
+
+  // ---- layer 0: 17 x 33 region, 16 channels, mma.m16n8k8.tf32 ----
+  {
+    uint32_t bf[5][2][2];
+#pragma unroll
+    for (int s = 0; s < 5; ++s)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const uint2 v = __ldg(reinterpret_cast<const uint2 *>(a.wfrag) + (s * 2 + j) * 32 + lane);
+        bf[s][j][0] = v.x; bf[s][j][1] = v.y;
+      }
+    float bz[2][2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { bz[j][0] = __ldg(a.bias + 8 * j + 2 * t); bz[j][1] = __ldg(a.bias + 8 * j + 2 * t + 1); }
+    int koff[5];
+#pragma unroll
+    for (int s = 0; s < 5; ++s) koff[s] = l0_k_off(s, t);
+    const int ly0 = 2 * oy0 - 1, lx0 = 2 * ox0 - 1;  // layer-0 coordinates of the region origin
+    const int LH = a.ih >> 1, LW = a.iw >> 1;
+    int p0 = warp * 16 + g, y0 = p0 / kL0W, x0 = p0 - y0 * kL0W, y1 = (p0 + 8) / kL0W, x1 = p0 + 8 - y1 * kL0W;
+    for (int seg = warp; seg < kL0Segs; seg += kThreads / 32) {
+      const int r0 = 2 * min(y0, kL0H - 1) * kInW + 2 * x0, r1 = 2 * min(y1, kL0H - 1) * kInW + 2 * x1;
+      float acc[2][4];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) { acc[j][0] = acc[j][2] = bz[j][0]; acc[j][1] = acc[j][3] = bz[j][1]; }
+#pragma unroll
+      for (int s = 0; s < 5; ++s) {
+        uint32_t af[4];
+        l0_load_a(patch, r0, r1, koff[s], af);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) mma1688_tf32(acc[j], af, bf[s][j][0], bf[s][j][1]);
+      }
+      const int p = seg * 16 + g;
+      if (p < kL0Px) {
+        const bool in = (unsigned)(ly0 + y0) < (unsigned)LH && (unsigned)(lx0 + x0) < (unsigned)LW;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) l0_store(l0s, p, t, j, acc[j][0], acc[j][1], in);
+      }
+      if (p + 8 < kL0Px) {
+        const bool in = (unsigned)(ly0 + y1) < (unsigned)LH && (unsigned)(lx0 + x1) < (unsigned)LW;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) l0_store(l0s, p + 8, t, j, acc[j][2], acc[j][3], in);
+      }
+      // next segment of this warp: p += 128 = 3 * 33 + 29
+      x0 += 128 - 3 * kL0W; y0 += 3; if (x0 >= kL0W) { x0 -= kL0W; ++y0; }
+      x1 += 128 - 3 * kL0W; y1 += 3; if (x1 >= kL0W) { x1 -= kL0W; ++y1; }
+    }
+  }
+  __syncthreads();
+
+  // ---- layer 1: warp = output row oy0 + warp, 16 pixels x 32 channels, one tap per k-step ----
+  {
+    float acc[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      acc[j][0] = acc[j][2] = __ldg(a.bias + 16 + l1_chan(j, t, 0));
+      acc[j][1] = acc[j][3] = __ldg(a.bias + 16 + l1_chan(j, t, 1));
+    }
+    const uint2 *wf = reinterpret_cast<const uint2 *>(w1s);
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      uint32_t af[4];
+      l1_load_a(l0s, warp, lane, tap, af);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint2 b = wf[(tap * 4 + j) * 32 + lane];
+        mma16816(acc[j], af, b.x, b.y);
+      }
+    }
+    const int oy = oy0 + warp;
+    __nv_bfloat16 *orow = a.out + ((long long)n * a.oh + oy) * a.ow * a.out_pitch;
+    if (!PW) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int px = ox0 + g + 8 * h;
+        if (oy < a.oh && px < a.ow)
+          *reinterpret_cast<uint4 *>(orow + (long long)px * a.out_pitch + 8 * t) =
+              make_uint4(relu_pack_bf16(acc[0][2 * h], acc[0][2 * h + 1]), relu_pack_bf16(acc[1][2 * h], acc[1][2 * h + 1]),
+                         relu_pack_bf16(acc[2][2 * h], acc[2][2 * h + 1]), relu_pack_bf16(acc[3][2 * h], acc[3][2 * h + 1]));
+      }
+    } else {
+      // 1x1 conv on the bf16-rounded layer-1 output: the accumulators re-packed as A fragments
+      const uint2 *w2 = reinterpret_cast<const uint2 *>(a.wfrag + kW0Words + kW1Words);
+      float acc2[2][4];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        acc2[j][0] = acc2[j][2] = __ldg(a.bias + 48 + pw_chan(j, t, 0));
+        acc2[j][1] = acc2[j][3] = __ldg(a.bias + 48 + pw_chan(j, t, 1));
+      }
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        uint32_t af[4];
+        af[0] = relu_pack_bf16(acc[2 * ks][0], acc[2 * ks][1]);
+        af[1] = relu_pack_bf16(acc[2 * ks][2], acc[2 * ks][3]);
+        af[2] = relu_pack_bf16(acc[2 * ks + 1][0], acc[2 * ks + 1][1]);
+        af[3] = relu_pack_bf16(acc[2 * ks + 1][2], acc[2 * ks + 1][3]);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const uint2 b = __ldg(w2 + (ks * 2 + j) * 32 + lane);
+          mma16816(acc2[j], af, b.x, b.y);
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int px = ox0 + g + 8 * h;
+        if (oy < a.oh && px < a.ow)
+          *reinterpret_cast<uint2 *>(orow + (long long)px * a.out_pitch + 4 * t) =
+              make_uint2(relu_pack_bf16(acc2[0][2 * h], acc2[0][2 * h + 1]), relu_pack_bf16(acc2[1][2 * h], acc2[1][2 * h + 1]));
+      }
+    }
+  }
+}
+
 uint32_t pack2(float lo, float hi) {
   __nv_bfloat16 x = __float2bfloat16_rn(lo), y = __float2bfloat16_rn(hi);
   uint16_t ux, uy;
@@ -254,8 +452,9 @@ bool stem_fused_supported(int c0, int c1, int ih, int iw, int out_pitch, int out
 }
 
 // w0 [16][3][3][3], w1 [32][16][3][3] (BN folded, PyTorch layout)
-void stem_fused_pack(const float *w0, const float *b0, const float *w1, const float *b1, std::vector<uint32_t> &frags,
-                     std::vector<float> &bias) {
+// frags = [legacy | second generation (stem_v2.cuh)], bias = [16 | 32 | 16 (1x1, zero without w2)]
+void stem_fused_pack(const float *w0, const float *b0, const float *w1, const float *b1, const float *w2, const float *b2,
+                     std::vector<uint32_t> &frags, std::vector<float> &bias) {
   frags.clear();
   pack_frags(frags, 3, 2, [&](int k, int n) {  // k = (ci * 3 + ky) * 4 + slot, slot <-> kx = slot - 1
     const int combo = k / 4, kx = k % 4 - 1;
@@ -264,12 +463,39 @@ void stem_fused_pack(const float *w0, const float *b0, const float *w1, const fl
   pack_frags(frags, 9, 4, [&](int k, int n) {  // k = tap * 16 + ci
     return w1[((size_t)n * 16 + k % 16) * 9 + k / 16];
   });
-  bias.assign(48, 0.f);
+  bias.assign(64, 0.f);
   for (int i = 0; i < 16; ++i) bias[i] = b0[i];
   for (int i = 0; i < 32; ++i) bias[16 + i] = b1[i];
+  for (int i = 0; i < 16 && b2; ++i) bias[48 + i] = b2[i];
+  stemv2::pack(w0, w1, w2, frags);
+}
+
+static int stem_v2_launch(const StemArgs &a0, cudaStream_t s) {
+  StemArgs a = a0;
+  a.wfrag += (6 + 36) * 64;  // skip the legacy fragments
+  static bool attr = false;
+  if (!attr) {
+    UYD_CUDA(cudaFuncSetAttribute(stem_v2_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, stemv2::kSmemBytes));
+    UYD_CUDA(cudaFuncSetAttribute(stem_v2_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, stemv2::kSmemBytes));
+    UYD_CUDA(cudaFuncSetAttribute(stem_v2_kernel<uint8_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, stemv2::kSmemBytes));
+    UYD_CUDA(cudaFuncSetAttribute(stem_v2_kernel<uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, stemv2::kSmemBytes));
+    attr = true;
+  }
+  dim3 grid(ceil_div(a.ow, stemv2::kTW), ceil_div(a.oh, stemv2::kTH), a.n);
+  const size_t smem = stemv2::kSmemBytes;
+  if (a.u8) {
+    if (a.pw) stem_v2_kernel<uint8_t, true><<<grid, stemv2::kThreads, smem, s>>>(a);
+    else stem_v2_kernel<uint8_t, false><<<grid, stemv2::kThreads, smem, s>>>(a);
+  } else {
+    if (a.pw) stem_v2_kernel<float, true><<<grid, stemv2::kThreads, smem, s>>>(a);
+    else stem_v2_kernel<float, false><<<grid, stemv2::kThreads, smem, s>>>(a);
+  }
+  return (int)cudaGetLastError();
 }
 
 int stem_fused_launch(const StemArgs &a, cudaStream_t s) {
+  static const bool legacy = [] { const char *v = getenv("UYD_STEM_LEGACY"); return v && *v == '1'; }();
+  if (!legacy || a.pw) return stem_v2_launch(a, s);
   const size_t smem = (size_t)2 * 3 * kInH * kInW * 2 + (size_t)(kL0Px + 19) * kL0Pitch * 2 + (6 + 36) * 64 * 4 + 48 * 4;
   static bool attr = false;
   if (!attr) {

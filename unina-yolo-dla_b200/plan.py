@@ -154,13 +154,21 @@ class Plan:
         check(_lib.lib().uyd_plan_add_cls_branch(self.handle, C.byref(d), wp, bp), "uyd_plan_add_cls_branch")
         return dst
 
-    def stem2(self, dst: Slice, w0, b0, w1, b1) -> Slice:
-        """Fused Conv(3,16,3,2) -> Conv(16,32,3,2) reading the network input (uyd_plan_add_stem2)."""
+    def stem2(self, dst: Slice, w0, b0, w1, b1, w2=None, b2=None) -> Slice:
+        """Fused Conv(3,16,3,2) -> Conv(16,32,3,2) reading the network input (uyd_plan_add_stem2); with
+        ``w2, b2`` the 1x1 Conv(32,16) consuming it runs in the same launch (uyd_plan_add_stem2_pw)."""
         f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
         w0, b0, w1, b1 = f32(w0), f32(b0), f32(w1), f32(b1)
-        assert w0.shape == (16, 3, 3, 3) and w1.shape == (32, 16, 3, 3) and dst.c == 32
+        assert w0.shape == (16, 3, 3, 3) and w1.shape == (32, 16, 3, 3)
         ptr = lambda a: a.ctypes.data_as(C.c_void_p)
-        check(_lib.lib().uyd_plan_add_stem2(self.handle, dst.buf, dst.coff, ptr(w0), ptr(b0), ptr(w1), ptr(b1)), "uyd_plan_add_stem2")
+        if w2 is None:
+            assert dst.c == 32
+            check(_lib.lib().uyd_plan_add_stem2(self.handle, dst.buf, dst.coff, ptr(w0), ptr(b0), ptr(w1), ptr(b1)), "uyd_plan_add_stem2")
+        else:
+            w2, b2 = f32(w2).reshape(16, 32), f32(b2)
+            assert dst.c == 16 and b2.shape == (16,)
+            check(_lib.lib().uyd_plan_add_stem2_pw(self.handle, dst.buf, dst.coff, ptr(w0), ptr(b0), ptr(w1), ptr(b1), ptr(w2), ptr(b2)),
+                  "uyd_plan_add_stem2_pw")
         return dst
 
     @staticmethod

@@ -171,6 +171,14 @@ class UpCat:
         self.h, self.w, self.c = skip.h, skip.w, low.c + skip.c
 
 
+class StemOut:
+    """Output of the fused stem when its only consumer is a C3k2 whose 1x1 cv1 joins the stem's launch
+    (uyd_plan_add_stem2_pw): the 32-channel tensor is never written."""
+
+    def __init__(self, h, w, c, folded):
+        self.h, self.w, self.c, self.folded = h, w, c, folded
+
+
 class C3k2(nn.Module):
     """C2f: cv1 -> chunk(2) -> n blocks chained on the last chunk -> cat -> cv2.  cv1 writes
     straight into the first 2c channels of the cat buffer; each block appends its c channels."""
@@ -196,6 +204,9 @@ class C3k2(nn.Module):
             part = p.buffer(src.low.h, src.low.w, 2 * c, UYD_F32)
             p.conv(src.low, part, w[:, :ca], b * 0, 1, 1, relu=False)
             p.conv(src.skip, cat.sub(0, 2 * c), w[:, ca:], b, 1, 1, relu=True, pre=part)
+        elif isinstance(src, StemOut):
+            w, b = fold_bn(self.cv1.conv, self.cv1.bn)
+            p.stem2(cat.sub(0, 2 * c), *src.folded, w, b)
         else:
             self.cv1.emit(p, src, cat.sub(0, 2 * c))
         for i, m in enumerate(self.m):
@@ -506,12 +517,19 @@ class UninaYoloB200(nn.Module):
         stem2 = (os.environ.get("UYD_NO_STEM_FUSION", "0") != "1" and fusion and not _quantized(p, "model.1.conv") and isinstance(l0, Conv) and isinstance(l1, Conv)
                  and (l0.c1, l0.c2, l0.k, l0.s, l0.g) == (3, 16, 3, 2, 1) and (l1.c1, l1.c2, l1.k, l1.s, l1.g) == (16, 32, 3, 2, 1)
                  and l1.f == -1 and 0 not in self.save and 0 not in home and H % 4 == 0 and W % 4 == 0)
+        l2 = layers[2] if len(layers) > 2 else None
+        # model.1 feeds only model.2 (a C3k2 with a 32 -> 16 cv1): that 1x1 joins the stem's launch
+        stem_pw = (stem2 and os.environ.get("UYD_NO_STEM_PW", "0") != "1" and isinstance(l2, C3k2) and l2.f == -1 and l2.c == 8
+                   and 1 not in self.save and 1 not in home and getattr(p, "conv_inputs", None) is None
+                   and not _quantized(p, getattr(l2.cv1.conv, "_uyd_name", "")))
         for m in layers:
             def src_of(j):
                 return outs[m.i - 1] if j == -1 else outs[j]
             dst = home.get(m.i)
             if stem2 and m.i == 0:
                 outs.append(None)      # lives only in shared memory of the fused stem kernel
+            elif stem_pw and m.i == 1:
+                outs.append(StemOut(H // 4, W // 4, l1.c2, fold_bn(l0.conv, l0.bn) + fold_bn(l1.conv, l1.bn)))
             elif stem2 and m.i == 1:
                 dst = dst or p.buffer(H // 4, W // 4, l1.c2)
                 if p.shapes[dst.buf][2] % 8 or dst.coff % 8:
