@@ -491,7 +491,7 @@ def test_fused_stem_matches_torch(T, H, W, u8, pw):
         dst = p.buffer(H // 4, W // 4, 36).sub(4, 16)
         p.stem2(dst, w0.numpy(), b0.numpy(), w1.numpy(), b1.numpy(), w2.numpy(), b2.numpy())
     else:
-        dst = p.buffer(H // 4, W // 4, 48).sub(16, 32)
+        dst = p.buffer(H // 4, W // 4, 56).sub(16, 32)
         p.stem2(dst, w0.numpy(), b0.numpy(), w1.numpy(), b1.numpy())
     p.finalize()
     p.run(xin.cuda())

@@ -11,6 +11,8 @@
 //     4-byte aligned shared-memory word);
 //   * its bf16 result (zero outside the image = layer 1's padding) never leaves shared memory;
 //   * layer 1 is nine k-steps of mma.sync (one filter tap = 16 channels per step).
+#include <type_traits>
+
 #include "stem_v2.cuh"
 
 #include "common.cuh"
@@ -233,193 +235,202 @@ __global__ void __launch_bounds__(kThreads) stem_fused_kernel(StemArgs a) {
 // =================================================================================================
 // Second generation (design and lane maps: stem_v2.cuh)
 // =================================================================================================
-__device__ __forceinline__ void mma1688_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+__device__ __forceinline__ void mma1688_tf32(float (&d)[4], const uint4 &a, uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+      : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ uint32_t to_tf32(float v) {
+__device__ __forceinline__ void mma16816v(float (&d)[4], const uint4 &a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t v) {
   uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(r) : "r"(v));
   return r;
 }
 
 template <typename TIn, bool PW>
-__global__ void __launch_bounds__(stemv2::kThreads) stem_v2_kernel(StemArgs a) {
+__global__ void __launch_bounds__(stemv2::kThreads, 3) stem_v2_kernel(StemArgs a) {
   using namespace stemv2;
   pdl_trigger();
   extern __shared__ __align__(16) unsigned char smem[];
-  unsigned char *patch = smem;                                               // [3][35][68] fp32, tf32-rounded
-  unsigned char *l0s = smem + kPatchBytes;                                   // [576][48 B]: 16 bf16 channels + pad
-  uint32_t *w1s = reinterpret_cast<uint32_t *>(smem + kPatchBytes + kL0Bytes);  // layer-1 fragments
+  unsigned char *patch = smem;                             // [3][18 even | 17 odd rows][68] fp32 (tf32)
+  unsigned char *l0s = smem + kPatchBytes;                 // [584 pixels q = 34 y + x][48 B]: word w = channels (w, w+8)
+  unsigned char *w1s = smem + kPatchBytes + kL0Bytes;      // layer-1 A fragments [tap][m-tile][lane] x 16 B
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int ox0 = blockIdx.x * kTW, oy0 = blockIdx.y * kTH, n = blockIdx.z;
   const int ix0 = 4 * ox0 - 4, iy0 = 4 * oy0 - 3;  // frame coordinates of the patch origin (16-byte aligned columns)
 
-  // ---- all global loads first: layer-1 fragments and this thread's 7 patch vectors (column j, rows rl + 15 i) ----
+  // ---- all global loads first: layer-1 fragments and this thread's 7 patch vectors (column j, lines rl + 15 i) ----
   constexpr int kW1Vec = kW1Words / 4, kWIters = (kW1Vec + kThreads - 1) / kThreads;
-  const uint4 *w1g = reinterpret_cast<const uint4 *>(a.wfrag + kW0Words);
+  const uint4 *w1g = reinterpret_cast<const uint4 *>(a.wfrag + 2 * kW0Words);
   uint4 wv[kWIters];
 #pragma unroll
   for (int it = 0; it < kWIters; ++it) {
     const int i = tid + it * kThreads;
     wv[it] = i < kW1Vec ? __ldg(w1g + i) : make_uint4(0u, 0u, 0u, 0u);
   }
-  constexpr int kVecPerRow = kInW / 4;                  // 17
-  constexpr int kRowLanes = 15, kPIters = 3 * kInH / kRowLanes;  // 105 (channel, row) lines = 15 x 7
-  static_assert(kRowLanes * kPIters == 3 * kInH && kRowLanes * kVecPerRow <= kThreads, "patch load map");
+  // thread (pj, prl): column vector pj of patch rows prl, prl + 15 and (prl < 5) prl + 30 of each channel
+  constexpr int kVecPerRow = kInW / 4, kRowLanes = 15;  // 17 vectors per row, 255 loading threads
+  static_assert(2 * kRowLanes <= kInH && 3 * kRowLanes >= kInH && kRowLanes * kVecPerRow <= kThreads, "patch load map");
   const TIn *img = reinterpret_cast<const TIn *>(a.in) + (long long)n * 3 * a.ih * a.iw;
+  asm volatile("" : "+l"(img));  // keep the per-load address arithmetic 32-bit: one IMAD.WIDE.U32 on this base
   const int pj = tid % kVecPerRow, prl = tid / kVecPerRow;
   const int ix = ix0 + 4 * pj;
   const bool col_ok = prl < kRowLanes && ix >= 0 && ix + 3 < a.iw;
-  float pv[kPIters][4];
-  {
-    int c = 0, r = prl;
+  const unsigned plane = (unsigned)(a.ih * a.iw);
+  bool ok[3];
+  unsigned off[3];
 #pragma unroll
-    for (int it = 0; it < kPIters; ++it) {
-      const int iy = iy0 + r;
-      pv[it][0] = pv[it][1] = pv[it][2] = pv[it][3] = 0.f;
-      if (col_ok && (unsigned)iy < (unsigned)a.ih) {
-        const TIn *src = img + ((long long)c * a.ih + iy) * a.iw + ix;
-        if (sizeof(TIn) == 4) {
-          const float4 q = __ldg(reinterpret_cast<const float4 *>(src));
-          pv[it][0] = q.x; pv[it][1] = q.y; pv[it][2] = q.z; pv[it][3] = q.w;
-        } else {
-          const uchar4 q = __ldg(reinterpret_cast<const uchar4 *>(src));
-          pv[it][0] = (float)q.x; pv[it][1] = (float)q.y; pv[it][2] = (float)q.z; pv[it][3] = (float)q.w;
-        }
-      }
-      r += kRowLanes;
-      if (r >= kInH) { r -= kInH; ++c; }
-    }
+  for (int k = 0; k < 3; ++k) {
+    const int r = prl + kRowLanes * k, iy = iy0 + r;
+    ok[k] = col_ok && r < kInH && (unsigned)iy < (unsigned)a.ih;
+    off[k] = (unsigned)(iy * a.iw + ix);  // meaningful only when ok[k]
   }
+  uint4 pv[3][3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      pv[c][k] = make_uint4(0u, 0u, 0u, 0u);
+      if (ok[k]) {
+        const TIn *src = img + (off[k] + c * plane);
+        if (sizeof(TIn) == 4) pv[c][k] = __ldg(reinterpret_cast<const uint4 *>(src));
+        else pv[c][k].x = __ldg(reinterpret_cast<const unsigned int *>(src));
+      }
+    }
 #pragma unroll
   for (int it = 0; it < kWIters; ++it) {
     const int i = tid + it * kThreads;
     if (i < kW1Vec) reinterpret_cast<uint4 *>(w1s)[i] = wv[it];
   }
-  if (prl < kRowLanes) {
 #pragma unroll
-    for (int it = 0; it < kPIters; ++it) {
-      uint4 o;
-      uint32_t *op = reinterpret_cast<uint32_t *>(&o);
+  for (int k = 0; k < 3; ++k) {
+    const int r = prl + kRowLanes * k;
+    if (prl < kRowLanes && r < kInH) {
+      unsigned char *dst = patch + (patch_line(0, r) * kInW + 4 * pj) * 4;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) op[e] = to_tf32(sizeof(TIn) == 1 ? div255(pv[it][e]) : pv[it][e]);
-      // line (c, r) = prl + 15 it of the [3][35] plane stack: the stack is contiguous, so the line index is enough
-      *reinterpret_cast<uint4 *>(patch + ((prl + kRowLanes * it) * kInW + 4 * pj) * 4) = o;
+      for (int c = 0; c < 3; ++c) {
+        const uint4 v = pv[c][k];
+        uint4 o;
+        if (sizeof(TIn) == 4) {  // round to nearest tf32: the mma reads the upper 19 bits
+          o = ok[k] ? make_uint4(v.x + 0x1000u, v.y + 0x1000u, v.z + 0x1000u, v.w + 0x1000u) : v;
+        } else {                 // integers 0..255 are exact; 1/255 lives in the weights
+          o = make_uint4(__float_as_uint((float)(v.x & 0xffu)), __float_as_uint((float)((v.x >> 8) & 0xffu)),
+                         __float_as_uint((float)((v.x >> 16) & 0xffu)), __float_as_uint((float)(v.x >> 24)));
+        }
+        *reinterpret_cast<uint4 *>(dst + c * kInH * kInW * 4) = o;
+      }
     }
   }
   __syncthreads();
 
-  // ---- layer 0: 17 x 33 region, 16 channels, mma.m16n8k8.tf32 ----
+  // ---- layer 0: 73 groups of 8 flat pixels, 16 channels = the 16 mma rows, mma.m16n8k8.tf32 ----
   {
-    uint32_t bf[5][2][2];
+    const uint4 *w0g = reinterpret_cast<const uint4 *>(a.wfrag + (a.u8 ? kW0Words : 0));
+    uint4 af[5];
 #pragma unroll
-    for (int s = 0; s < 5; ++s)
+    for (int s = 0; s < 5; ++s) af[s] = __ldg(w0g + s * 32 + lane);
+    const float b_lo = __ldg(a.bias + g), b_hi = __ldg(a.bias + g + 8);
+    const unsigned char *pb[5];
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const uint2 v = __ldg(reinterpret_cast<const uint2 *>(a.wfrag) + (s * 2 + j) * 32 + lane);
-        bf[s][j][0] = v.x; bf[s][j][1] = v.y;
-      }
-    float bz[2][2];
+    for (int s = 0; s < 5; ++s)  // l0_k_off(s, t) from two compile-time constants
+      pb[s] = patch + 64 * warp + 8 * g + 8 * (t & 1) + 4 * ((t >> 1) ? l0_k_off(s, 2) : l0_k_off(s, 0));
+    unsigned char *sb = l0s + (8 * warp + 2 * t) * kL0Pitch + 4 * g;
+    // groups warp + 8 i: pixels q = 8 (warp + 8 i) + (B: g | D: 2t, 2t+1); three independent mma chains at a time
+    auto groups = [&](int i0, auto cnt) {
+      constexpr int NG = decltype(cnt)::value;
+      float acc[NG][4];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) { bz[j][0] = __ldg(a.bias + 8 * j + 2 * t); bz[j][1] = __ldg(a.bias + 8 * j + 2 * t + 1); }
-    int koff[5];
-#pragma unroll
-    for (int s = 0; s < 5; ++s) koff[s] = l0_k_off(s, t);
-    const int ly0 = 2 * oy0 - 1, lx0 = 2 * ox0 - 1;  // layer-0 coordinates of the region origin
-    const int LH = a.ih >> 1, LW = a.iw >> 1;
-    int p0 = warp * 16 + g, y0 = p0 / kL0W, x0 = p0 - y0 * kL0W, y1 = (p0 + 8) / kL0W, x1 = p0 + 8 - y1 * kL0W;
-    for (int seg = warp; seg < kL0Segs; seg += kThreads / 32) {
-      const int r0 = 2 * min(y0, kL0H - 1) * kInW + 2 * x0, r1 = 2 * min(y1, kL0H - 1) * kInW + 2 * x1;
-      float acc[2][4];
-#pragma unroll
-      for (int j = 0; j < 2; ++j) { acc[j][0] = acc[j][2] = bz[j][0]; acc[j][1] = acc[j][3] = bz[j][1]; }
+      for (int j = 0; j < NG; ++j) { acc[j][0] = acc[j][1] = b_lo; acc[j][2] = acc[j][3] = b_hi; }
 #pragma unroll
       for (int s = 0; s < 5; ++s) {
-        uint32_t af[4];
-        l0_load_a(patch, r0, r1, koff[s], af);
+        uint2 v[NG];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) mma1688_tf32(acc[j], af, bf[s][j][0], bf[s][j][1]);
-      }
-      const int p = seg * 16 + g;
-      if (p < kL0Px) {
-        const bool in = (unsigned)(ly0 + y0) < (unsigned)LH && (unsigned)(lx0 + x0) < (unsigned)LW;
+        for (int j = 0; j < NG; ++j) v[j] = ld64(pb[s] + 512 * (i0 + j));
 #pragma unroll
-        for (int j = 0; j < 2; ++j) l0_store(l0s, p, t, j, acc[j][0], acc[j][1], in);
+        for (int j = 0; j < NG; ++j) mma1688_tf32(acc[j], af[s], v[j].x, v[j].y);
       }
-      if (p + 8 < kL0Px) {
-        const bool in = (unsigned)(ly0 + y1) < (unsigned)LH && (unsigned)(lx0 + x1) < (unsigned)LW;
 #pragma unroll
-        for (int j = 0; j < 2; ++j) l0_store(l0s, p + 8, t, j, acc[j][2], acc[j][3], in);
+      for (int j = 0; j < NG; ++j) {
+        st32(sb + 64 * kL0Pitch * (i0 + j), relu_pack_bf16(acc[j][0], acc[j][2]));
+        st32(sb + 64 * kL0Pitch * (i0 + j) + kL0Pitch, relu_pack_bf16(acc[j][1], acc[j][3]));
       }
-      // next segment of this warp: p += 128 = 3 * 33 + 29
-      x0 += 128 - 3 * kL0W; y0 += 3; if (x0 >= kL0W) { x0 -= kL0W; ++y0; }
-      x1 += 128 - 3 * kL0W; y1 += 3; if (x1 >= kL0W) { x1 -= kL0W; ++y1; }
-    }
+    };
+    static_assert(kGroups == 73, "nine groups per warp and one more for warp 0");
+    groups(0, std::integral_constant<int, 3>{});
+    groups(3, std::integral_constant<int, 3>{});
+    groups(6, std::integral_constant<int, 3>{});
+    if (warp == 0) groups(9, std::integral_constant<int, 1>{});
   }
   __syncthreads();
+  // layer 1's zero padding: layer-0 row -1 / column -1 exist only in the tiles on the top / left image border
+  if (oy0 == 0 || ox0 == 0) {
+    if (oy0 == 0)
+      for (int i = tid; i < kL0P * 8; i += kThreads) st32(l0s + (i >> 3) * kL0Pitch + 4 * (i & 7), 0u);
+    if (ox0 == 0 && tid < kL0H * 8) st32(l0s + (tid >> 3) * kL0P * kL0Pitch + 4 * (tid & 7), 0u);
+    __syncthreads();
+  }
 
-  // ---- layer 1: warp = output row oy0 + warp, 16 pixels x 32 channels, one tap per k-step ----
+  // ---- layer 1: warp = output row oy0 + warp, two groups of 8 pixels x two 16-channel m-tiles, one tap per k-step ----
   {
-    float acc[4][4];
+    float acc[2][2][4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      acc[j][0] = acc[j][2] = __ldg(a.bias + 16 + l1_chan(j, t, 0));
-      acc[j][1] = acc[j][3] = __ldg(a.bias + 16 + l1_chan(j, t, 1));
+    for (int mt = 0; mt < 2; ++mt) {
+      const float2 bz = __ldg(reinterpret_cast<const float2 *>(a.bias + 16 + 4 * g + 2 * mt));
+#pragma unroll
+      for (int xg = 0; xg < 2; ++xg) { acc[xg][mt][0] = acc[xg][mt][1] = bz.x; acc[xg][mt][2] = acc[xg][mt][3] = bz.y; }
     }
-    const uint2 *wf = reinterpret_cast<const uint2 *>(w1s);
+    const unsigned char *bb = l0s + l1_b_off(warp, 0, g, t, 0);
+    const uint4 *wf = reinterpret_cast<const uint4 *>(w1s) + lane;
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
-      uint32_t af[4];
-      l1_load_a(l0s, warp, lane, tap, af);
+      const uint4 a0 = wf[(tap * 2 + 0) * 32], a1 = wf[(tap * 2 + 1) * 32];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint2 b = wf[(tap * 4 + j) * 32 + lane];
-        mma16816(acc[j], af, b.x, b.y);
+      for (int xg = 0; xg < 2; ++xg) {
+        const uint2 b = ld64(bb + ((tap / 3) * kL0P + 16 * xg + tap % 3) * kL0Pitch);
+        mma16816v(acc[xg][0], a0, b.x, b.y);
+        mma16816v(acc[xg][1], a1, b.x, b.y);
       }
     }
     const int oy = oy0 + warp;
     __nv_bfloat16 *orow = a.out + ((long long)n * a.oh + oy) * a.ow * a.out_pitch;
     if (!PW) {
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int px = ox0 + g + 8 * h;
-        if (oy < a.oh && px < a.ow)
-          *reinterpret_cast<uint4 *>(orow + (long long)px * a.out_pitch + 8 * t) =
-              make_uint4(relu_pack_bf16(acc[0][2 * h], acc[0][2 * h + 1]), relu_pack_bf16(acc[1][2 * h], acc[1][2 * h + 1]),
-                         relu_pack_bf16(acc[2][2 * h], acc[2][2 * h + 1]), relu_pack_bf16(acc[3][2 * h], acc[3][2 * h + 1]));
-      }
-    } else {
-      // 1x1 conv on the bf16-rounded layer-1 output: the accumulators re-packed as A fragments
-      const uint2 *w2 = reinterpret_cast<const uint2 *>(a.wfrag + kW0Words + kW1Words);
-      float acc2[2][4];
+      for (int xg = 0; xg < 2; ++xg)
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        acc2[j][0] = acc2[j][2] = __ldg(a.bias + 48 + pw_chan(j, t, 0));
-        acc2[j][1] = acc2[j][3] = __ldg(a.bias + 48 + pw_chan(j, t, 1));
-      }
-#pragma unroll
-      for (int ks = 0; ks < 2; ++ks) {
-        uint32_t af[4];
-        af[0] = relu_pack_bf16(acc[2 * ks][0], acc[2 * ks][1]);
-        af[1] = relu_pack_bf16(acc[2 * ks][2], acc[2 * ks][3]);
-        af[2] = relu_pack_bf16(acc[2 * ks + 1][0], acc[2 * ks + 1][1]);
-        af[3] = relu_pack_bf16(acc[2 * ks + 1][2], acc[2 * ks + 1][3]);
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const uint2 b = __ldg(w2 + (ks * 2 + j) * 32 + lane);
-          mma16816(acc2[j], af, b.x, b.y);
+        for (int h = 0; h < 2; ++h) {
+          const int px = ox0 + 8 * xg + 2 * t + h;
+          if (oy < a.oh && px < a.ow)
+            *reinterpret_cast<uint2 *>(orow + (long long)px * a.out_pitch + 4 * g) =
+                make_uint2(relu_pack_bf16(acc[xg][0][h], acc[xg][0][2 + h]), relu_pack_bf16(acc[xg][1][h], acc[xg][1][2 + h]));
         }
-      }
+    } else {
+      // 1x1 conv on the bf16-rounded layer-1 output: (channel x pixel) accumulator tiles -> movmatrix -> B fragments
+      const uint4 *w2 = reinterpret_cast<const uint4 *>(a.wfrag + 2 * kW0Words + kW1Words) + lane;
+      const uint4 p0 = __ldg(w2), p1 = __ldg(w2 + 32);
+      const float2 bz = __ldg(reinterpret_cast<const float2 *>(a.bias + 48 + 2 * g));
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int px = ox0 + g + 8 * h;
-        if (oy < a.oh && px < a.ow)
-          *reinterpret_cast<uint2 *>(orow + (long long)px * a.out_pitch + 4 * t) =
-              make_uint2(relu_pack_bf16(acc2[0][2 * h], acc2[0][2 * h + 1]), relu_pack_bf16(acc2[1][2 * h], acc2[1][2 * h + 1]));
+      for (int xg = 0; xg < 2; ++xg) {
+        float acc2[4] = {bz.x, bz.x, bz.y, bz.y};
+        uint32_t bq[2][2];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) bq[mt][hh] = movmatrix_trans(relu_pack_bf16(acc[xg][mt][2 * hh], acc[xg][mt][2 * hh + 1]));
+        mma16816v(acc2, p0, bq[0][0], bq[0][1]);
+        mma16816v(acc2, p1, bq[1][0], bq[1][1]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int px = ox0 + 8 * xg + 2 * t + h;
+          if (oy < a.oh && px < a.ow)
+            *reinterpret_cast<uint32_t *>(orow + (long long)px * a.out_pitch + 2 * g) = relu_pack_bf16(acc2[h], acc2[2 + h]);
+        }
       }
     }
   }
