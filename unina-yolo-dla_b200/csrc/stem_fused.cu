@@ -233,8 +233,11 @@ __global__ void __launch_bounds__(kThreads) stem_fused_kernel(StemArgs a) {
 }
 
 // =================================================================================================
-// Second generation (design and lane maps: stem_v2.cuh)
+// Second generation (design and lane maps: stem_v2.cuh).  Lives in uyd::stemv2 so that the header's constants win
+// over the first generation's equally named ones above.
 // =================================================================================================
+}  // namespace
+namespace stemv2 {
 __device__ __forceinline__ void mma1688_tf32(float (&d)[4], const uint4 &a, uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -255,7 +258,6 @@ __device__ __forceinline__ uint32_t movmatrix_trans(uint32_t v) {
 
 template <typename TIn, bool PW>
 __global__ void __launch_bounds__(stemv2::kThreads, 3) stem_v2_kernel(StemArgs a) {
-  using namespace stemv2;
   pdl_trigger();
   extern __shared__ __align__(16) unsigned char smem[];
   unsigned char *patch = smem;                             // [3][18 even | 17 odd rows][68] fp32 (tf32)
@@ -435,6 +437,8 @@ __global__ void __launch_bounds__(stemv2::kThreads, 3) stem_v2_kernel(StemArgs a
     }
   }
 }
+}  // namespace stemv2
+namespace {
 
 uint32_t pack2(float lo, float hi) {
   __nv_bfloat16 x = __float2bfloat16_rn(lo), y = __float2bfloat16_rn(hi);
@@ -486,20 +490,20 @@ static int stem_v2_launch(const StemArgs &a0, cudaStream_t s) {
   a.wfrag += (6 + 36) * 64;  // skip the legacy fragments
   static bool attr = false;
   if (!attr) {
-    UYD_CUDA(cudaFuncSetAttribute(stem_v2_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, stemv2::kSmemBytes));
-    UYD_CUDA(cudaFuncSetAttribute(stem_v2_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, stemv2::kSmemBytes));
-    UYD_CUDA(cudaFuncSetAttribute(stem_v2_kernel<uint8_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, stemv2::kSmemBytes));
-    UYD_CUDA(cudaFuncSetAttribute(stem_v2_kernel<uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, stemv2::kSmemBytes));
+    UYD_CUDA(cudaFuncSetAttribute(stemv2::stem_v2_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, stemv2::kSmemBytes));
+    UYD_CUDA(cudaFuncSetAttribute(stemv2::stem_v2_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, stemv2::kSmemBytes));
+    UYD_CUDA(cudaFuncSetAttribute(stemv2::stem_v2_kernel<uint8_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, stemv2::kSmemBytes));
+    UYD_CUDA(cudaFuncSetAttribute(stemv2::stem_v2_kernel<uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, stemv2::kSmemBytes));
     attr = true;
   }
   dim3 grid(ceil_div(a.ow, stemv2::kTW), ceil_div(a.oh, stemv2::kTH), a.n);
   const size_t smem = stemv2::kSmemBytes;
   if (a.u8) {
-    if (a.pw) stem_v2_kernel<uint8_t, true><<<grid, stemv2::kThreads, smem, s>>>(a);
-    else stem_v2_kernel<uint8_t, false><<<grid, stemv2::kThreads, smem, s>>>(a);
+    if (a.pw) stemv2::stem_v2_kernel<uint8_t, true><<<grid, stemv2::kThreads, smem, s>>>(a);
+    else stemv2::stem_v2_kernel<uint8_t, false><<<grid, stemv2::kThreads, smem, s>>>(a);
   } else {
-    if (a.pw) stem_v2_kernel<float, true><<<grid, stemv2::kThreads, smem, s>>>(a);
-    else stem_v2_kernel<float, false><<<grid, stemv2::kThreads, smem, s>>>(a);
+    if (a.pw) stemv2::stem_v2_kernel<float, true><<<grid, stemv2::kThreads, smem, s>>>(a);
+    else stemv2::stem_v2_kernel<float, false><<<grid, stemv2::kThreads, smem, s>>>(a);
   }
   return (int)cudaGetLastError();
 }
