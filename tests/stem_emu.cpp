@@ -69,7 +69,7 @@ static void warp_movmatrix_trans(const uint32_t in[32], uint32_t out[32]) {
   }
 }
 
-// frame: [3][ih][iw] fp32 (u8 = 1: integer values 0..255, the kernel's uint8 path with 1/255 in the weights);
+// frame: [3][ih][iw] fp32 (u8 = 1: integer values 0..255, divided by 255 here as the kernel's uint8 path does);
 // out: [oh][ow][pw ? 16 : 32] fp32 (bf16 values)
 extern "C" int stem_emu(int ih, int iw, int pw, int u8, const float *w0, const float *b0, const float *w1, const float *b1,
                         const float *w2, const float *b2, const float *frame, float *out) {
@@ -84,7 +84,7 @@ extern "C" int stem_emu(int ih, int iw, int pw, int u8, const float *w0, const f
   for (int i = 0; i < 16 && pw; ++i) bias[48 + i] = b2[i];
   std::vector<unsigned char> smem(kSmemBytes);
   unsigned char *patch = smem.data(), *l0s = smem.data() + kPatchBytes;
-  const uint32_t *w0f = frags.data() + (u8 ? kW0Words : 0), *w1f = frags.data() + 2 * kW0Words, *w2f = w1f + kW1Words;
+  const uint32_t *w0f = frags.data(), *w1f = frags.data() + kW0Words, *w2f = w1f + kW1Words;
 
   for (int oy0 = 0; oy0 < oh; oy0 += kTH)
     for (int ox0 = 0; ox0 < ow; ox0 += kTW) {
@@ -96,7 +96,7 @@ extern "C" int stem_emu(int ih, int iw, int pw, int u8, const float *w0, const f
             const int iy = iy0 + r, ix = ix0 + col;
             const bool in = iy >= 0 && iy < ih && ix >= 0 && ix < iw;
             const float v = in ? frame[((size_t)c * ih + iy) * iw + ix] : 0.f;
-            st32(patch + (patch_line(c, r) * kInW + col) * 4, !in ? 0u : (u8 ? f32_bits(v) : f32_bits(v) + 0x1000u));
+            st32(patch + (patch_line(c, r) * kInW + col) * 4, !in ? 0u : f32_bits(u8 ? div255(v) : v) + 0x1000u);
           }
       // layer 0
       for (int grp = 0; grp < kGroups; ++grp) {
@@ -189,4 +189,16 @@ extern "C" int stem_emu(int ih, int iw, int pw, int u8, const float *w0, const f
         }
     }
   return 0;
+}
+
+// x / 255 by the kernel's two-step correction (device branch restated with fmaf) for all 256 inputs
+extern "C" int div255_mismatches() {
+  int bad = 0;
+  const float r = 1.0f / 255.0f;
+  for (int x = 0; x < 256; ++x) {
+    const float xf = (float)x, q = xf * r;
+    const float got = fmaf(fmaf(-q, 255.0f, xf), r, q);
+    bad += got != xf / 255.0f;
+  }
+  return bad;
 }

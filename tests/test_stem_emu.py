@@ -25,6 +25,7 @@ def emu():
         subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I/usr/local/cuda/include", str(src), "-o", str(out)], check=True)
     lib = C.CDLL(str(out))
     lib.stem_emu.restype = C.c_int
+    lib.div255_mismatches.restype = C.c_int
     return lib
 
 
@@ -56,3 +57,7 @@ def test_stem_v2_lane_maps_match_torch(emu, H, W, pw, u8):
     assert np.isfinite(y).all()
     err = np.abs(y - want).max() / max(np.abs(want).max(), 1e-6)
     assert err < 6e-3, err
+
+
+def test_div255_equals_ieee_quotient(emu):
+    assert emu.div255_mismatches() == 0

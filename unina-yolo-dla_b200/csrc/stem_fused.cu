@@ -260,7 +260,7 @@ template <typename TIn, bool PW>
 __global__ void __launch_bounds__(stemv2::kThreads, 3) stem_v2_kernel(StemArgs a) {
   pdl_trigger();
   extern __shared__ __align__(16) unsigned char smem[];
-  unsigned char *patch = smem;                             // [3][18 even | 17 odd rows][68] fp32 (tf32)
+  unsigned char *patch = smem;                             // [3][38 lines: even rows at 0, odd rows at 20][68] fp32 (tf32)
   unsigned char *l0s = smem + kPatchBytes;                 // [584 pixels q = 34 y + x][48 B]: word w = channels (w, w+8)
   unsigned char *w1s = smem + kPatchBytes + kL0Bytes;      // layer-1 A fragments [tap][m-tile][lane] x 16 B
 
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(stemv2::kThreads, 3) stem_v2_kernel(StemArgs a
 
   // ---- all global loads first: layer-1 fragments and this thread's 7 patch vectors (column j, lines rl + 15 i) ----
   constexpr int kW1Vec = kW1Words / 4, kWIters = (kW1Vec + kThreads - 1) / kThreads;
-  const uint4 *w1g = reinterpret_cast<const uint4 *>(a.wfrag + 2 * kW0Words);
+  const uint4 *w1g = reinterpret_cast<const uint4 *>(a.wfrag + kW0Words);
   uint4 wv[kWIters];
 #pragma unroll
   for (int it = 0; it < kWIters; ++it) {
@@ -322,11 +322,11 @@ __global__ void __launch_bounds__(stemv2::kThreads, 3) stem_v2_kernel(StemArgs a
         uint4 o;
         if (sizeof(TIn) == 4) {  // round to nearest tf32: the mma reads the upper 19 bits
           o = ok[k] ? make_uint4(v.x + 0x1000u, v.y + 0x1000u, v.z + 0x1000u, v.w + 0x1000u) : v;
-        } else {                 // integers 0..255 are exact; 1/255 lives in the weights
-          o = make_uint4(__float_as_uint((float)(v.x & 0xffu)), __float_as_uint((float)((v.x >> 8) & 0xffu)),
-                         __float_as_uint((float)((v.x >> 16) & 0xffu)), __float_as_uint((float)(v.x >> 24)));
+        } else {                 // x / 255 exactly as the float pre-process computes it, then the same rounding
+          auto cv = [&](uint32_t b) { return ok[k] ? __float_as_uint(div255((float)b)) + 0x1000u : 0u; };
+          o = make_uint4(cv(v.x & 0xffu), cv((v.x >> 8) & 0xffu), cv((v.x >> 16) & 0xffu), cv(v.x >> 24));
         }
-        *reinterpret_cast<uint4 *>(dst + c * kInH * kInW * 4) = o;
+        *reinterpret_cast<uint4 *>(dst + c * kChanLines * kInW * 4) = o;
       }
     }
   }
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(stemv2::kThreads, 3) stem_v2_kernel(StemArgs a
 
   // ---- layer 0: 73 groups of 8 flat pixels, 16 channels = the 16 mma rows, mma.m16n8k8.tf32 ----
   {
-    const uint4 *w0g = reinterpret_cast<const uint4 *>(a.wfrag + (a.u8 ? kW0Words : 0));
+    const uint4 *w0g = reinterpret_cast<const uint4 *>(a.wfrag);
     uint4 af[5];
 #pragma unroll
     for (int s = 0; s < 5; ++s) af[s] = __ldg(w0g + s * 32 + lane);
@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(stemv2::kThreads, 3) stem_v2_kernel(StemArgs a
         }
     } else {
       // 1x1 conv on the bf16-rounded layer-1 output: (channel x pixel) accumulator tiles -> movmatrix -> B fragments
-      const uint4 *w2 = reinterpret_cast<const uint4 *>(a.wfrag + 2 * kW0Words + kW1Words) + lane;
+      const uint4 *w2 = reinterpret_cast<const uint4 *>(a.wfrag + kW0Words + kW1Words) + lane;
       const uint4 p0 = __ldg(w2), p1 = __ldg(w2 + 32);
       const float2 bz = __ldg(reinterpret_cast<const float2 *>(a.bias + 48 + 2 * g));
 #pragma unroll

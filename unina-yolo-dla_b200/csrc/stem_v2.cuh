@@ -14,8 +14,10 @@
 //     that the address of layer-0 pixel q = 34 y + x is  8 q + (per-thread constant of the k-step): layer 0 is a
 //     fully unrolled loop over 8-pixel groups of a FLAT pixel index with immediate offsets (column 33 of each row
 //     is a garbage pixel nobody reads; mma columns are independent);
-//   * uint8 frames are converted with I2F only: integers are exact in tf32 and 1/255 is folded into a second
-//     set of layer-0 weights;
+//   * uint8 frames: x / 255 as q = x*r, q += fma(-q, 255, x) * r, which equals the IEEE quotient for all 256 inputs
+//     (tests/test_stem_emu.py), so a uint8 frame gives bit-identical results to its float image / 255;
+//   * the patch lines are placed (odd rows at line 20, 38 lines per channel, 272-byte lines) so that the two
+//     (channel, row) combinations one LDS.64 of layer 0 touches fall into disjoint shared-memory banks;
 //   * the layer-0 tile keeps channels (w, w + 8) in word w of a 48-byte pixel: the transposed accumulators
 //     (channel g | g+8, pixels 2t | 2t+1) pack into it with two cvt.rn.relu.bf16x2, conflict-free; the top row /
 //     left column outside the image (layer 1's zero padding) is cleared afterwards, by border CTAs only;
@@ -40,18 +42,18 @@ constexpr int kL0H = 2 * kTH + 1, kL0P = 2 * kTW + 2;  // 17 rows x 34 pixels (p
 constexpr int kGroups = (16 * kL0P + 2 * kTW + 1 + 7) / 8;  // 8-pixel groups covering q = 0 .. 16*34 + 32: 73
 constexpr int kL0Px = kGroups * 8;                     // 584
 constexpr int kInH = 2 * kL0H + 1, kInW = 2 * kL0P;    // 35 x 68 frame patch (column 0 only feeds the zero slot)
-constexpr int kEvenRows = (kInH + 1) / 2;              // 18 even patch rows precede the 17 odd ones
+constexpr int kOddLine = 20, kChanLines = 38;          // 18 even patch rows at line 0, 17 odd ones at line 20 of a channel
 constexpr int kL0Pitch = 48;                           // bytes per layer-0 pixel (8 words + pad: conflict-free)
-constexpr int kPatchBytes = 3 * kInH * kInW * 4;       // 28560
+constexpr int kPatchBytes = 3 * kChanLines * kInW * 4;  // 31008
 constexpr int kL0Bytes = kL0Px * kL0Pitch;             // 28032
 constexpr int kW0Words = 5 * 128, kW1Words = 9 * 2 * 128, kW2Words = 2 * 128;  // A fragments: 32 lanes x 4 words each
 constexpr int kSmemBytes = kPatchBytes + kL0Bytes + kW1Words * 4;
 constexpr int kThreads = 256;
-// fragment buffer: [L0 (fp32 frames) | L0 / 255 (uint8 frames) | L1 | 1x1]
-constexpr int kFragWords = 2 * kW0Words + kW1Words + kW2Words;
+// fragment buffer: [L0 | L1 | 1x1]
+constexpr int kFragWords = kW0Words + kW1Words + kW2Words;
 
 // patch line of frame-patch row r of channel c: even rows first
-C3K_HD int patch_line(int c, int r) { return c * kInH + ((r & 1) ? kEvenRows + (r >> 1) : (r >> 1)); }
+C3K_HD int patch_line(int c, int r) { return c * kChanLines + ((r & 1) ? kOddLine + (r >> 1) : (r >> 1)); }
 
 // ---- layer 0 (tf32 m16n8k8): logical k = t -> slot 2(t&1), k = t+4 -> slot 2(t&1)+1 of combination 2s + (t>>1) ----
 // float offset of this lane's slot pair in k-step s, relative to the pixel term 2 q
@@ -87,21 +89,26 @@ C3K_HD int pw_chan(int r) { return 2 * (r & 7) + (r >> 3); }
 inline uint32_t f32_bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 inline float bits_f32(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 inline float bf16_round(float f) { return bits_f32((uint32_t)host_f2bf(f) << 16); }
-// round to nearest (ties away) to 10 mantissa bits = cvt.rna.tf32
-inline uint32_t tf32_rna(float f) { return (f32_bits(f) + 0x1000u) & 0xffffe000u; }
+
+// x / 255 for integer x in [0, 255]: equals the IEEE fp32 quotient (checked exhaustively, tests/test_stem_emu.py)
+C3K_HD float div255(float x) {
+#if defined(__CUDA_ARCH__)
+  const float r = 1.0f / 255.0f;
+  const float q = __fmul_rn(x, r);
+  return __fmaf_rn(__fmaf_rn(-q, 255.0f, x), r, q);
+#else
+  return x / 255.0f;
+#endif
+}
 
 // m16n8k8 A fragment: a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4); m16n8k16: a0 (g, 2t..) a1 (g+8, 2t..) a2 (g, 2t+8..) a3 (g+8, 2t+8..)
 inline void pack(const float *w0, const float *w1, const float *w2 /* may be null */, std::vector<uint32_t> &out) {
-  for (int u8 = 0; u8 < 2; ++u8)
-    for (int s = 0; s < 5; ++s)
-      for (int lane = 0; lane < 32; ++lane) {
-        const int g = lane >> 2, t = lane & 3;
-        auto w = [&](int row, int k) {
-          const float v = bf16_round(l0_weight(w0, s, k, row));
-          return u8 ? tf32_rna(v / 255.0f) : f32_bits(v);
-        };
-        out.push_back(w(g, t)); out.push_back(w(g + 8, t)); out.push_back(w(g, t + 4)); out.push_back(w(g + 8, t + 4));
-      }
+  for (int s = 0; s < 5; ++s)
+    for (int lane = 0; lane < 32; ++lane) {
+      const int g = lane >> 2, t = lane & 3;
+      auto w = [&](int row, int k) { return f32_bits(bf16_round(l0_weight(w0, s, k, row))); };
+      out.push_back(w(g, t)); out.push_back(w(g + 8, t)); out.push_back(w(g, t + 4)); out.push_back(w(g + 8, t + 4));
+    }
   for (int tap = 0; tap < 9; ++tap)
     for (int mt = 0; mt < 2; ++mt)
       for (int lane = 0; lane < 32; ++lane) {
