@@ -147,9 +147,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     uint32_t phase = 0;
     const int cb_elems = (int)cb_bytes / 2;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int n = p.n0 + (int)(tile / tiles_per_img);
-      const int t = (int)(tile % tiles_per_img);
-      const int y0 = (t / p.tiles_x) * kTileH, x0 = (t % p.tiles_x) * kTileW;
+      const unsigned ut = (unsigned)tile, img = ut / (unsigned)tiles_per_img, t = ut - img * (unsigned)tiles_per_img;
+      const unsigned ty = t / (unsigned)p.tiles_x;
+      const int n = p.n0 + (int)img;
+      const int y0 = (int)ty * kTileH, x0 = (int)(t - ty * (unsigned)p.tiles_x) * kTileW;
       for (int j = 0; j < p.ncb; ++j) {
         mbar_wait(empty0 + 8u * stage, phase ^ 1u);
         if (lane == 0) {
@@ -234,13 +235,14 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     // restricted to the row width)
     const uint32_t swz = cb2_bytes == 128 ? (uint32_t)(m & 7) : (cb2_bytes == 64 ? (uint32_t)((m >> 1) & 3) : (uint32_t)((m >> 2) & 1));
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    int it = 0;
-    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      if (it % kNG != g) continue;
-      const uint32_t ph = (uint32_t)(it / kNG) & 1u;
-      const int n = p.n0 + (int)(tile / tiles_per_img);
-      const int t = (int)(tile % tiles_per_img);
-      const int oy = (t / p.tiles_x) * kTileH + (m >> 3), ox = (t % p.tiles_x) * kTileW + (m & 7);
+    // group g takes tiles g, g + kNG, ... of this CTA's sequence; tile indices fit 32 bits (checked on the host)
+    int it = g;
+    uint32_t ph = 0;
+    for (long long tile = blockIdx.x + (long long)g * gridDim.x; tile < p.total_tiles; tile += (long long)kNG * gridDim.x, it += kNG, ph ^= 1u) {
+      const unsigned ut = (unsigned)tile, img = ut / (unsigned)tiles_per_img, t = ut - img * (unsigned)tiles_per_img;
+      const unsigned ty = t / (unsigned)p.tiles_x, tx = t - ty * (unsigned)p.tiles_x;
+      const int n = p.n0 + (int)img;
+      const int oy = (int)ty * kTileH + (m >> 3), ox = (int)tx * kTileW + (m & 7);
       const bool inside = oy < p.H && ox < p.W;
       // ---- stage 1: acc1 -> bias, ReLU -> bf16 -> swizzled shared-memory tile (A of GEMM2) ----
       mbar_wait(tfull1 + 8u * g, ph);
@@ -582,6 +584,7 @@ int chain_launch(const ChainConv *cc, int nb, float *y, int sm_count, cudaStream
   p.y = y;
   p.total_tiles = (long long)nb * p.tiles_x * p.tiles_y;
   if (p.total_tiles == 0) return UYD_OK;
+  UYD_REQUIRE(p.total_tiles < (1ll << 31), UYD_E_UNSUPPORTED, "conv_chain: %lld tiles exceed the kernel's 32-bit tile index", p.total_tiles);
   const unsigned grid = (unsigned)(p.total_tiles < sm_count ? p.total_tiles : sm_count);
   const int ks1 = p.cb_bytes / 32, ks2 = p.N1 * 2 / 32;
   static long long *dbg_dev = nullptr;

@@ -322,10 +322,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       int n = 0, x0 = 0, y0 = 0;
       if (p.mode != TC_FLAT) {
-        n = p.n0 + (int)(tile / tiles_per_img);
-        const int t = (int)(tile % tiles_per_img);
-        y0 = (t / p.tiles_x) * kTileH;
-        x0 = (t % p.tiles_x) * kTileW;
+        const unsigned ut = (unsigned)tile, img = ut / (unsigned)tiles_per_img, t = ut - img * (unsigned)tiles_per_img;
+        const unsigned ty = t / (unsigned)p.tiles_x;
+        n = p.n0 + (int)img;
+        y0 = (int)ty * kTileH;
+        x0 = (int)(t - ty * (unsigned)p.tiles_x) * kTileW;
       }
       for (int j = 0; j < blocks_per_tile; ++j) {
         mbar_wait(empty0 + 8u * stage, phase ^ 1u);
@@ -422,26 +423,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     unsigned char *swarp = smem_dyn + (bar0 + kTailFixed - raw) + (size_t)(warp - 2) * 32 * p.stage_pitch;
     const int group = (warp - 2) >> 2;  // the epilogue warpgroups take tiles round-robin
     unsigned char *srow = swarp + (size_t)lane * p.stage_pitch;
-    int it = 0;
-    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      if (it % p.ngroups != group) continue;  // (groups >= ngroups never match: they idle)
-      const int acc = it % nacc;  // nacc is a multiple of ngroups: an accumulator always belongs to the same group
-      const uint32_t acc_phase = (uint32_t)(it / nacc) & 1u;
+    // Group g takes tiles g, g + ngroups, ... of this CTA's sequence (groups >= ngroups idle).  ngroups and nacc are
+    // powers of two (nacc a multiple of ngroups: an accumulator always belongs to the same group) and every tile /
+    // pixel index of a launch fits 32 bits (checked on the host): no runtime division on the per-tile path except
+    // the one 32-bit tile -> (image, tile row, tile column) split.
+    const int nacc_mask = nacc - 1, nacc_shift = nacc == 4 ? 2 : 1;
+    const unsigned hw = (unsigned)p.H * (unsigned)p.W;
+    int it = group;
+    for (long long tile = blockIdx.x + (long long)group * gridDim.x; group < p.ngroups && tile < p.total_tiles;
+         tile += (long long)p.ngroups * gridDim.x, it += p.ngroups) {
+      const int acc = it & nacc_mask;
+      const uint32_t acc_phase = (uint32_t)(it >> nacc_shift) & 1u;
       long long pix;        // flattened output pixel (n, oy, ox) or -1
       long long ppix = -1;  // pixel of the half-resolution partial-sum tensor this output pixel adds, or -1
       if (p.mode == TC_FLAT) {
-        const long long row = tile * 128 + m;
-        pix = row < (long long)p.nb * p.H * p.W ? (long long)p.n0 * p.H * p.W + row : -1;
+        const unsigned row = (unsigned)tile * 128u + (unsigned)m;
+        pix = row < (unsigned)p.nb * hw ? (long long)((unsigned)p.n0 * hw + row) : -1;
         if (p.pre && pix >= 0) {
-          const int ox = (int)(pix % p.W);
-          const long long t = pix / p.W;
-          const int oy = (int)(t % p.H);
-          ppix = ((t / p.H) * (p.H >> 1) + (oy >> 1)) * (p.W >> 1) + (ox >> 1);
+          const unsigned upix = (unsigned)pix, t = upix / (unsigned)p.W, ox = upix - t * (unsigned)p.W;
+          const unsigned img = t / (unsigned)p.H, oy = t - img * (unsigned)p.H;
+          ppix = (long long)((img * (unsigned)(p.H >> 1) + (oy >> 1)) * (unsigned)(p.W >> 1) + (ox >> 1));
         }
       } else {
-        const int n = p.n0 + (int)(tile / tiles_per_img);
-        const int t = (int)(tile % tiles_per_img);
-        const int oy = (t / p.tiles_x) * kTileH + (m >> 3), ox = (t % p.tiles_x) * kTileW + (m & 7);
+        const unsigned ut = (unsigned)tile, img = ut / (unsigned)tiles_per_img, t = ut - img * (unsigned)tiles_per_img;
+        const unsigned ty = t / (unsigned)p.tiles_x, tx = t - ty * (unsigned)p.tiles_x;
+        const int n = p.n0 + (int)img;
+        const int oy = (int)ty * kTileH + (m >> 3), ox = (int)tx * kTileW + (m & 7);
         pix = (oy < p.H && ox < p.W) ? ((long long)n * p.H + oy) * p.W + ox : -1;
         if (p.pre && pix >= 0) ppix = ((long long)n * (p.H >> 1) + (oy >> 1)) * (p.W >> 1) + (ox >> 1);
       }
@@ -735,6 +742,8 @@ int tc_launch(const TcConv *tc, int n0, int nb, int sm_count, cudaStream_t s) {
   p.nb = nb;
   p.total_tiles = p.mode == TC_FLAT ? ((long long)nb * p.H * p.W + 127) / 128 : (long long)nb * p.tiles_x * p.tiles_y;
   if (p.total_tiles == 0) return UYD_OK;
+  UYD_REQUIRE((long long)(p.n0 + nb) * p.H * p.W < (1ll << 31) && p.total_tiles < (1ll << 24), UYD_E_UNSUPPORTED,
+              "conv_tc: %d images of %dx%d exceed the kernel's 32-bit pixel index", p.n0 + nb, p.H, p.W);
   const unsigned grid = (unsigned)(p.total_tiles < sm_count ? p.total_tiles : sm_count);
   const int ks = p.cb_bytes / 32;
 #define UYD_TC_LAUNCH(I8V, KS) UYD_CUDA(launch_pdl(conv_tc_kernel<I8V, KS>, dim3(grid), dim3(kThreads), tc->smem, s, tc->tm_in, tc->tm_w, p))
