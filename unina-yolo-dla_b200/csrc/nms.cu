@@ -397,45 +397,61 @@ __global__ void __launch_bounds__(kFThreads, 1) nms_image_kernel(const float *__
 
   // mode 0: count keys in [lo, hi), track min / max, capture the first kFCap;  mode 1: histogram over (key - kmin) >> shift
   auto scan = [&](unsigned long long hi, int mode, int shift) {
-    for (int a0 = 0; a0 < A; a0 += kFThreads) {
-      const int a = a0 + tid;
-      bool in = false;
-      unsigned long long key = 0ull;
-      if (a < A) {
-        const float *p = yb + 4ll * A + a;
-        float best = p[0];
-        int j = 0;
-        for (int c = 1; c < nc; ++c) {
-          const float v = p[(long long)c * A];
-          if (v > best) { best = v; j = c; }   // first maximum wins
+    constexpr int U = 4;  // anchors per thread and round: U independent loads in flight per class plane
+    unsigned long long mn = ~0ull, mx = 0ull;  // per-thread key range, reduced once after the loop
+    for (int a0 = 0; a0 < A; a0 += U * kFThreads) {
+      float best[U];
+      int bj[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int a = a0 + u * kFThreads + tid;
+        best[u] = a < A ? yb[4ll * A + a] : -INFINITY;
+        bj[u] = 0;
+      }
+      for (int c = 1; c < nc; ++c) {
+        const float *pc = yb + (4ll + c) * A;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int a = a0 + u * kFThreads + tid;
+          const float v = a < A ? pc[a] : -INFINITY;
+          if (v > best[u]) { best[u] = v; bj[u] = c; }   // first maximum wins
         }
-        if (best > conf_thr) {
-          key = fused_key(best, j, a, pos != 0);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int a = a0 + u * kFThreads + tid;
+        bool in = false;
+        unsigned long long key = 0ull;
+        if (a < A && best[u] > conf_thr) {
+          key = fused_key(best[u], bj[u], a, pos != 0);
           in = key >= lo && key < hi;
         }
-      }
-      if (mode == 0) {
-        const unsigned bal = __ballot_sync(0xffffffffu, in);
-        if (bal) {
-          int base = 0;
-          if (lane == 0) base = atomicAdd(&S.count, __popc(bal));
-          base = __shfl_sync(0xffffffffu, base, 0);
-          if (in) {
-            const int slot = base + __popc(bal & ((1u << lane) - 1));
-            if (slot < kFCap) S.keys[slot] = key;
+        if (mode == 0) {
+          const unsigned bal = __ballot_sync(0xffffffffu, in);
+          if (bal) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&S.count, __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (in) {
+              const int slot = base + __popc(bal & ((1u << lane) - 1));
+              if (slot < kFCap) S.keys[slot] = key;
+              mn = key < mn ? key : mn;
+              mx = key > mx ? key : mx;
+            }
           }
-          unsigned long long mn = in ? key : ~0ull, mx = in ? key : 0ull;  // one pair of atomics per warp
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const unsigned long long omn = __shfl_xor_sync(0xffffffffu, mn, o), omx = __shfl_xor_sync(0xffffffffu, mx, o);
-            mn = omn < mn ? omn : mn;
-            mx = omx > mx ? omx : mx;
-          }
-          if (lane == 0) { atomicMin(&S.kmin, mn); atomicMax(&S.kmax, mx); }
+        } else if (in) {
+          atomicAdd(&S.hist[(unsigned)((key - S.kmin) >> shift)], 1u);
         }
-      } else if (in) {
-        atomicAdd(&S.hist[(unsigned)((key - S.kmin) >> shift)], 1u);
       }
+    }
+    if (mode == 0) {  // one pair of atomics per warp
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long omn = __shfl_xor_sync(0xffffffffu, mn, o), omx = __shfl_xor_sync(0xffffffffu, mx, o);
+        mn = omn < mn ? omn : mn;
+        mx = omx > mx ? omx : mx;
+      }
+      if (lane == 0 && mn <= mx) { atomicMin(&S.kmin, mn); atomicMax(&S.kmax, mx); }
     }
   };
 
@@ -475,17 +491,17 @@ __global__ void __launch_bounds__(kFThreads, 1) nms_image_kernel(const float *__
     while (P < n_slab) P <<= 1;
     for (int i = n_slab + tid; i < P; i += kFThreads) S.keys[i] = ~0ull;
     __syncthreads();
+    // One compare-exchange per thread and step: pair p -> elements i = p with a zero inserted at bit log2(j), i | j.
+    // For j <= 32 the 32 pairs of a warp live in its own 64 consecutive elements: those steps only need __syncwarp.
     for (int k = 2; k <= P; k <<= 1) {
       for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int i = tid; i < P; i += kFThreads) {
-          const int q = i ^ j;
-          if (q > i) {
-            const unsigned long long x = S.keys[i], z = S.keys[q];
-            const bool up = (i & k) == 0;
-            if ((x > z) == up) { S.keys[i] = z; S.keys[q] = x; }
-          }
+        for (int pr = tid; pr < (P >> 1); pr += kFThreads) {
+          const int i = ((pr & ~(j - 1)) << 1) | (pr & (j - 1)), q = i | j;
+          const unsigned long long x = S.keys[i], z = S.keys[q];
+          if ((x > z) == ((i & k) == 0)) { S.keys[i] = z; S.keys[q] = x; }
         }
-        __syncthreads();
+        if (j > 32 || j == 1 || P > 2 * kFThreads) __syncthreads();
+        else __syncwarp();
       }
     }
     // ---- 3. greedy NMS over the slab, in order, at most max_nms candidates per image in total ----
