@@ -21,19 +21,16 @@ __device__ __forceinline__ uint4 max8(uint4 a, uint4 b) {
 // P = MaxPool2d(5, 1, 2) and -inf padding.  Cascading clipped windows composes exactly:
 // y1 = max over the clipped 5x5, y2 = 9x9, y3 = 13x13 window of x.  One CTA handles one
 // image row x 8-channel group: the 13 input rows are reduced column-wise into shared memory
-// (vertical maxima for radius 2/4/6), then each thread reduces horizontally.  A CTA walks `rows` consecutive
-// image rows: 12 of the 13 input rows of the next output row are already in its L1 (one row per CTA re-read
-// every input row 13 times through L2, which bounded the kernel).
-__global__ void __launch_bounds__(kThreads) sppf_pool_kernel(__nv_bfloat16 *base, int h, int w, int pitch, int c, int rows) {
+// (vertical maxima for radius 2/4/6), then each thread reduces horizontally.
+__global__ void __launch_bounds__(kThreads) sppf_pool_kernel(__nv_bfloat16 *base, int h, int w, int pitch, int c) {
   pdl_trigger();
   extern __shared__ uint4 col[];  // [3][w][cg] vertical maxima
   const int cg = c / 8;
-  const int bands = h / rows;
-  const int n = blockIdx.x / bands;
+  const int y = blockIdx.x % h;
+  const int n = blockIdx.x / h;
   const __nv_bfloat16 *img = base + (long long)n * h * w * pitch;
   const int items = w * cg;
   const uint4 ninf = make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u);  // bf16 -inf x8
-  for (int y = (blockIdx.x % bands) * rows, y_end = y + rows; y < y_end; ++y) {
   for (int it = threadIdx.x; it < items; it += kThreads) {
     const int x = it / cg, g = it % cg;
     uint4 m2 = ninf, m4 = ninf, m6 = ninf;
@@ -68,8 +65,6 @@ __global__ void __launch_bounds__(kThreads) sppf_pool_kernel(__nv_bfloat16 *base
     *reinterpret_cast<uint4 *>(o + c) = r2;
     *reinterpret_cast<uint4 *>(o + 2 * c) = r4;
     *reinterpret_cast<uint4 *>(o + 3 * c) = r6;
-  }
-  __syncthreads();  // col is rewritten for the next row
   }
 }
 
@@ -113,11 +108,7 @@ int sppf_pool_launch(__nv_bfloat16 *base, int n, int h, int w, int pitch, int c,
   const size_t smem = (size_t)3 * w * (c / 8) * sizeof(uint4);
   UYD_REQUIRE(smem <= 200 * 1024, UYD_E_UNSUPPORTED, "sppf row does not fit shared memory");
   if (smem > 48 * 1024) cudaFuncSetAttribute(sppf_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  // bands of 8 (or 4 / 2) rows while that still leaves about two CTAs per SM
-  int rows = 1;
-  for (int r = 8; r > 1; r >>= 1)
-    if (h % r == 0 && n * (h / r) >= 296) { rows = r; break; }
-  sppf_pool_kernel<<<n * (h / rows), kThreads, smem, s>>>(base, h, w, pitch, c, rows);
+  sppf_pool_kernel<<<n * h, kThreads, smem, s>>>(base, h, w, pitch, c);
   return (int)cudaGetLastError();
 }
 
