@@ -12,8 +12,8 @@ python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_
 python tools/kernel_table.py --top 40 > gpurun_out/${TAG}_ktable.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/${TAG}_launches.csv \
     python tools/kernel_table.py --ncu > gpurun_out/${TAG}_launches.log 2>&1; echo "launch list exit=$?"
-ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"stem_fused|nms_image|conv_chain" -c 11 \
+ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"stem_v2|stem_fused|nms_image|conv_chain" -c 11 \
     -o gpurun_out/${TAG}_a -f python tools/kernel_table.py --ncu > gpurun_out/${TAG}_full_a.log 2>&1; echo "full set a exit=$?"
-ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"c3k_fused|conv_tc" -c 14 \
+ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"c3k_flat|c3k_fused|conv_tc" -c 14 \
     -o gpurun_out/${TAG}_b -f python tools/kernel_table.py --ncu > gpurun_out/${TAG}_full_b.log 2>&1; echo "full set b exit=$?"
 du -sh gpurun_out
