@@ -417,8 +417,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const bool staged = p.stage_pitch != 0;
     const int esize = I8 ? (p.out_kind == 2 ? 1 : (p.out_kind == 1 ? 4 : 2)) : (p.out_f32 ? 4 : 2);
     const int lpr = staged ? (p.cout * esize) / 16 : 1;  // 16-byte lanes per output row
-    const int rows_per_it = 32 / lpr;
+    const int lpr_shift = 31 - __clz(lpr);  // lpr is a power of two (host check)
+    const int rows_per_it = 32 >> lpr_shift, sub = lane >> lpr_shift, chunk = lane & (lpr - 1);
     const long long out_row_pitch = (long long)p.out_pitch * esize;
+    unsigned char *gout_lane = reinterpret_cast<unsigned char *>(p.out) + (long long)sub * out_row_pitch + chunk * 16;
+    const long long gstep = (long long)rows_per_it * out_row_pitch;
+    const int sstep = rows_per_it * p.stage_pitch;
     long long *spix = reinterpret_cast<long long *>(smem_dyn + (bar0 + 1536u - raw)) + (warp - 2) * 32;
     unsigned char *swarp = smem_dyn + (bar0 + kTailFixed - raw) + (size_t)(warp - 2) * 32 * p.stage_pitch;
     const int group = (warp - 2) >> 2;  // the epilogue warpgroups take tiles round-robin
@@ -481,16 +485,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
         }
       }
-      if (staged) {  // coalesced copy-out of this warp's 32 rows
+      if (staged) {  // coalesced copy-out of this warp's 32 rows: 16-byte lanes laid along the rows
         __syncwarp();
-        const int sub = lane / lpr, chunk = lane % lpr;
-        unsigned char *gout = reinterpret_cast<unsigned char *>(p.out);
-        for (int r0 = 0; r0 < 32; r0 += rows_per_it) {
-          const int r = r0 + sub;
-          const long long pr = spix[r];
-          if (pr >= 0)
-            *reinterpret_cast<uint4 *>(gout + pr * out_row_pitch + chunk * 16) =
-                *reinterpret_cast<const uint4 *>(swarp + r * p.stage_pitch + chunk * 16);
+        const unsigned char *sp = swarp + sub * p.stage_pitch + chunk * 16;
+        if (p.mode == TC_FLAT) {  // the rows of a tile are consecutive pixels: no row -> pixel map
+          const unsigned row0 = (unsigned)tile * 128u + (unsigned)(q * 32), nrows = (unsigned)p.nb * hw;
+          unsigned char *gp = gout_lane + (long long)((unsigned)p.n0 * hw + row0) * out_row_pitch;
+          for (int r = sub; r < 32; r += rows_per_it, gp += gstep, sp += sstep)
+            if (row0 + (unsigned)r < nrows) *reinterpret_cast<uint4 *>(gp) = *reinterpret_cast<const uint4 *>(sp);
+        } else {
+          for (int r = sub; r < 32; r += rows_per_it, sp += sstep) {
+            const long long pr = spix[r];
+            if (pr >= 0) *reinterpret_cast<uint4 *>(gout_lane + pr * out_row_pitch - (long long)sub * out_row_pitch) = *reinterpret_cast<const uint4 *>(sp);
+          }
         }
         __syncwarp();
       }
