@@ -40,6 +40,12 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 // Lets a successor launched with programmatic stream serialization (the tcgen05 kernels, tc_ptx.cuh) start its
 // prologue while this kernel is still running; the successor still waits for this kernel's completion before
 // it reads any activation.
+// (lo, hi) -> max(x, 0) rounded to nearest-even bf16, packed: one F2FP.RELU
+__device__ __forceinline__ uint32_t relu_pack_bf16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // Blocks until the predecessor kernel has completed and its writes are visible (no-op for plain launches).
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

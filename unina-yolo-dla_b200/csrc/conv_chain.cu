@@ -266,14 +266,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
           float bv[16];
           load_bias16(bias1_s + c * 16, bv);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float a0 = fmaxf(__uint_as_float(cur[2 * i]) + bv[2 * i], 0.f);
-            const float a1 = fmaxf(__uint_as_float(cur[2 * i + 1]) + bv[2 * i + 1], 0.f);
-            const float b0 = fmaxf(__uint_as_float(cur[8 + 2 * i]) + bv[8 + 2 * i], 0.f);
-            const float b1 = fmaxf(__uint_as_float(cur[8 + 2 * i + 1]) + bv[8 + 2 * i + 1], 0.f);
-            __nv_bfloat162 ha = __floats2bfloat162_rn(a0, a1), hb = __floats2bfloat162_rn(b0, b1);
-            w0[i] = *reinterpret_cast<uint32_t *>(&ha);
-            w1[i] = *reinterpret_cast<uint32_t *>(&hb);
+          for (int i = 0; i < 4; ++i) {  // bias -> ReLU -> bf16 pair in one cvt.rn.relu.bf16x2
+            w0[i] = relu_pack_bf16x2(__uint_as_float(cur[2 * i]) + bv[2 * i], __uint_as_float(cur[2 * i + 1]) + bv[2 * i + 1]);
+            w1[i] = relu_pack_bf16x2(__uint_as_float(cur[8 + 2 * i]) + bv[8 + 2 * i], __uint_as_float(cur[8 + 2 * i + 1]) + bv[8 + 2 * i + 1]);
           }
           *reinterpret_cast<uint4 *>(a2_row + (((uint32_t)(2 * c) ^ swz) << 4)) = o0;
           *reinterpret_cast<uint4 *>(a2_row + (((uint32_t)(2 * c + 1) ^ swz) << 4)) = o1;
@@ -359,15 +354,28 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
           }
           float bv[16];
           load_bias16(bias2_s + ch * 16, bv);
+          // z2 is a bf16 activation in the unfused graph: ReLU + round it the same way before the last conv
+          // (one cvt.rn.relu.bf16x2 per pair, unpacked with a shift / mask); the nc > 4 half is a separate loop
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            // z2 is a bf16 activation in the unfused graph: round it the same way before the last conv
-            const float z = __bfloat162float(__float2bfloat16_rn(fmaxf(__uint_as_float(cur[i]) + bv[i], 0.f)));
-            const float4 wa = *reinterpret_cast<const float4 *>(w3_s + (ch * 16 + i) * 8);
-            lg[0] = fmaf(z, wa.x, lg[0]); lg[1] = fmaf(z, wa.y, lg[1]); lg[2] = fmaf(z, wa.z, lg[2]); lg[3] = fmaf(z, wa.w, lg[3]);
+          for (int h0 = 0; h0 < 16; h0 += 4) {
+            float z[4];
+#pragma unroll
+            for (int i = 0; i < 4; i += 2) {
+              const uint32_t pk = relu_pack_bf16x2(__uint_as_float(cur[h0 + i]) + bv[h0 + i], __uint_as_float(cur[h0 + i + 1]) + bv[h0 + i + 1]);
+              z[i] = __uint_as_float(pk << 16);
+              z[i + 1] = __uint_as_float(pk & 0xffff0000u);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 wa = *reinterpret_cast<const float4 *>(w3_s + (ch * 16 + h0 + i) * 8);
+              lg[0] = fmaf(z[i], wa.x, lg[0]); lg[1] = fmaf(z[i], wa.y, lg[1]); lg[2] = fmaf(z[i], wa.z, lg[2]); lg[3] = fmaf(z[i], wa.w, lg[3]);
+            }
             if (p.nc > 4) {
-              const float4 wb = *reinterpret_cast<const float4 *>(w3_s + (ch * 16 + i) * 8 + 4);
-              lg[4] = fmaf(z, wb.x, lg[4]); lg[5] = fmaf(z, wb.y, lg[5]); lg[6] = fmaf(z, wb.z, lg[6]); lg[7] = fmaf(z, wb.w, lg[7]);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 wb = *reinterpret_cast<const float4 *>(w3_s + (ch * 16 + h0 + i) * 8 + 4);
+                lg[4] = fmaf(z[i], wb.x, lg[4]); lg[5] = fmaf(z[i], wb.y, lg[5]); lg[6] = fmaf(z[i], wb.z, lg[6]); lg[7] = fmaf(z[i], wb.w, lg[7]);
+              }
             }
           }
           if (more) {

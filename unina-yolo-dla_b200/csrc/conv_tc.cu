@@ -161,6 +161,19 @@ __device__ __forceinline__ void epilogue_chunk_staged(const uint32_t (&raw)[16],
       v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
     }
   }
+  if (p.relu && !p.res && !p.out_f32) {  // the common case (Conv + BN + ReLU -> bf16): ReLU rides on the conversion
+    uint4 o0, o1;
+    uint32_t *w0 = reinterpret_cast<uint32_t *>(&o0), *w1 = reinterpret_cast<uint32_t *>(&o1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      w0[i] = relu_pack_bf16x2(__uint_as_float(raw[2 * i]) + v[2 * i], __uint_as_float(raw[2 * i + 1]) + v[2 * i + 1]);
+      w1[i] = relu_pack_bf16x2(__uint_as_float(raw[8 + 2 * i]) + v[8 + 2 * i], __uint_as_float(raw[8 + 2 * i + 1]) + v[8 + 2 * i + 1]);
+    }
+    uint4 *sp = reinterpret_cast<uint4 *>(srow + c0 * 2);
+    sp[0] = o0;
+    sp[1] = o1;
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const float x = __uint_as_float(raw[i]) + v[i];
