@@ -105,6 +105,26 @@ C3K_HD void st128(unsigned char *p, uint32_t x, uint32_t y, uint32_t z, uint32_t
 // {2t, 2t+1} (a0/a1, b0) and {2t+8, 2t+9} (a2/a3, b1) = physical 4t .. 4t+3 (one 8-byte load).
 C3K_HD int phys_col(int kk) { return 4 * ((kk & 7) >> 1) + 2 * (kk >> 3) + (kk & 1); }
 
+// ldmatrix.x4 A fragments (wherever the 16-byte chunks of a row are 16-byte aligned): lane L supplies the address of
+// row (L & 7) + 8 ((L >> 3) & 1), chunk L >> 4 (chunk 0 = logical k 0..7, chunk 1 = k 8..15), and the four result
+// registers ARE a0..a3 -- no LDS.64 pair to interleave with register moves.  Logical k = physical column with this path.
+// Used by the c_ = 8 stages whose rows are 16 bytes apart (80x80 blocks: 38.6 -> 36.9 us).
+C3K_HD int ldsm_row(int lane) { return (lane & 7) + 8 * ((lane >> 3) & 1); }
+C3K_HD int ldsm_chunk(int lane) { return lane >> 4; }
+// rowfn(L) = the address lane L supplies
+template <class F>
+C3K_HD void ldsm_a(F rowfn, int lane, uint32_t (&a)[4]) {
+#if defined(__CUDA_ARCH__)
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(rowfn(lane));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3])
+               : "r"(addr));
+#else
+  const int g = lane >> 2, t = lane & 3;  // host emulation: register i = word t of the row lane 8 i + g points at
+  for (int i = 0; i < 4; ++i) a[i] = ld32(rowfn(8 * i + g) + 4 * t);
+#endif
+}
+
 template <int C>
 struct Geo {
   static_assert(C == 4 || C == 8 || C == 16, "c_ in {4, 8, 16}");
@@ -151,6 +171,7 @@ template <int C>
 struct Stage1 {
   using G = Geo<C>;
   static constexpr int KS = G::K1, NT = G::N1;
+  static constexpr bool LDSM = false;  // rows are 32 / 64 bytes apart: an 8-row ldmatrix phase would hit every bank twice
   // A fragment of k-step s, row tile mt: a[0]/a[2] rows g, a[1]/a[3] rows g + 8
   C3K_HD static void load_a(const unsigned char *X, int f, int lane, int s, int mt, uint32_t (&a)[4]) {
     const int g = lane >> 2, t = lane & 3;
@@ -223,18 +244,20 @@ struct Stage3 {
   C3K_HD static int tap_px8(int s, int slot) {
     return s <= 2 ? (s - 1) * kPW - 1 + slot : (s == 3 ? -kPW + 1 + kPW * slot : kPW + 1);
   }
+  // ldmatrix where consecutive rows are 16 bytes apart (c_ = 8): the eight rows of a phase cover all banks once.
+  // c_ = 4: the window of a pixel pair starts at an odd pixel (8-byte aligned only); c_ = 16: 32-byte rows would
+  // conflict two-way (measured: 23 -> 29 us).
+  static constexpr bool LDSM = C == 8;
   C3K_HD static void load_a(const unsigned char *S, int f, int lane, int s, int mt, uint32_t (&a)[4]) {
-    const int g = lane >> 2, t = lane & 3;
-    const unsigned char *p;
-    if (C == 4) {
-      p = S + (f + 2 * g - 1 + (s - 1) * kPW) * G::PXA + 8 * t;
-    } else if (C == 8) {
-      p = S + (f + 16 * mt + g + tap_px8(s, t >> 1)) * G::PXA + 8 * (t & 1);
+    if (C == 8) {  // chunk = slot: the two pixels of the k-step
+      ldsm_a([=](int L) { return S + (f + 16 * mt + ldsm_row(L) + tap_px8(s, ldsm_chunk(L))) * G::PXA; }, lane, a);
     } else {
-      p = S + (f + 16 * mt + g + (s / 3 - 1) * kPW + s % 3 - 1) * G::PXA + 8 * t;
+      const int g = lane >> 2, t = lane & 3;
+      const unsigned char *p = C == 4 ? S + (f + 2 * g - 1 + (s - 1) * kPW) * G::PXA + 8 * t
+                                      : S + (f + 16 * mt + g + (s / 3 - 1) * kPW + s % 3 - 1) * G::PXA + 8 * t;
+      const uint2 lo = ld64(p), hi = ld64(p + 8 * G::ROWA);
+      a[0] = lo.x; a[2] = lo.y; a[1] = hi.x; a[3] = hi.y;
     }
-    const uint2 lo = ld64(p), hi = ld64(p + 8 * G::ROWA);
-    a[0] = lo.x; a[2] = lo.y; a[1] = hi.x; a[3] = hi.y;
   }
   C3K_HD static void bias_regs(const float *bias, int lane, float (&bz)[NT][2]) {  // bias = this conv's [32]
     const int t = lane & 3;
@@ -305,18 +328,18 @@ struct Stage6 {
   using G = Geo<C>;
   static constexpr int KS = G::K6, NT = G::N6;
   // V = the a frame (holds v), Bv = b tile (origin kB0)
+  static constexpr bool LDSM = C == 8;
   C3K_HD static void load_a(const unsigned char *V, const unsigned char *Bv, int f, int lane, int s, int mt, uint32_t (&a)[4]) {
-    const int g = lane >> 2, t = lane & 3;
-    const unsigned char *p;
-    if (C == 4) {
-      p = (t < 2 ? V + f * G::PXA : Bv + (f - kB0) * G::PXA) + g * G::ROWA + 8 * (t & 1);
-    } else if (C == 8) {
-      p = (t < 2 ? V + f * G::PXA : Bv + (f - kB0) * G::PXA) + (16 * mt + g) * G::PXA + 8 * (t & 1);
+    if (C == 8) {  // chunk 0 = the pixel's 16 bytes of v, chunk 1 = of b
+      ldsm_a([=](int L) { return (ldsm_chunk(L) == 0 ? V + f * G::PXA : Bv + (f - kB0) * G::PXA) + (16 * mt + ldsm_row(L)) * G::PXA; }, lane, a);
     } else {
-      p = (s == 0 ? V + f * G::PXA : Bv + (f - kB0) * G::PXA) + (16 * mt + g) * G::PXA + 8 * t;
+      const int g = lane >> 2, t = lane & 3;
+      const unsigned char *p;
+      if (C == 4) p = (t < 2 ? V + f * G::PXA : Bv + (f - kB0) * G::PXA) + g * G::ROWA + 8 * (t & 1);
+      else p = (s == 0 ? V + f * G::PXA : Bv + (f - kB0) * G::PXA) + (16 * mt + g) * G::PXA + 8 * t;
+      const uint2 lo = ld64(p), hi = ld64(p + 8 * G::ROWA);
+      a[0] = lo.x; a[2] = lo.y; a[1] = hi.x; a[3] = hi.y;
     }
-    const uint2 lo = ld64(p), hi = ld64(p + 8 * G::ROWA);
-    a[0] = lo.x; a[2] = lo.y; a[1] = hi.x; a[3] = hi.y;
   }
   C3K_HD static void bias_regs(const float *bias, int lane, float (&bz)[NT][2]) {  // bias = cv3's [32]
     const int t = lane & 3;
@@ -363,13 +386,14 @@ struct Stage6 {
 };
 
 // ---- host-side packing: B fragments of every stage (m16n8k16: lane (g, t) holds B[2t, 2t+1][g] and B[2t+8, 2t+9][g])
+// ldsm: the stage loads A with ldmatrix (logical k = physical column), otherwise with LDS.64 (phys_col permutation)
 template <class F>
-void pack_stage(std::vector<uint32_t> &out, int ksteps, int ntiles, F wfun) {
+void pack_stage(std::vector<uint32_t> &out, int ksteps, int ntiles, bool ldsm, F wfun) {
   for (int s = 0; s < ksteps; ++s)
     for (int j = 0; j < ntiles; ++j)
       for (int lane = 0; lane < 32; ++lane) {
         const int n = lane >> 2, t = lane & 3;
-        auto w = [&](int kk) { return host_f2bf(wfun(s, phys_col(kk), j, n)); };
+        auto w = [&](int kk) { return host_f2bf(wfun(s, ldsm ? kk : phys_col(kk), j, n)); };
         out.push_back((uint32_t)w(2 * t) | ((uint32_t)w(2 * t + 1) << 16));
         out.push_back((uint32_t)w(2 * t + 8) | ((uint32_t)w(2 * t + 9) << 16));
       }
@@ -379,10 +403,10 @@ void pack_stage(std::vector<uint32_t> &out, int ksteps, int ntiles, F wfun) {
 template <int C>
 void pack_all(const float *const w[7], std::vector<uint32_t> &out) {
   using G = Geo<C>;
-  pack_stage(out, G::K1, G::N1, [&](int s, int p, int j, int n) { return Stage1<C>::weight(w[0], w[1], s, p, j, n); });
+  pack_stage(out, G::K1, G::N1, Stage1<C>::LDSM, [&](int s, int p, int j, int n) { return Stage1<C>::weight(w[0], w[1], s, p, j, n); });
   for (int i = 2; i < 6; ++i)
-    pack_stage(out, G::K3, G::N3, [&](int s, int p, int j, int n) { return Stage3<C>::weight(w[i], s, p, j, n); });
-  pack_stage(out, G::K6, G::N6, [&](int s, int p, int j, int n) { return Stage6<C>::weight(w[6], s, p, j, n); });
+    pack_stage(out, G::K3, G::N3, Stage3<C>::LDSM, [&](int s, int p, int j, int n) { return Stage3<C>::weight(w[i], s, p, j, n); });
+  pack_stage(out, G::K6, G::N6, Stage6<C>::LDSM, [&](int s, int p, int j, int n) { return Stage6<C>::weight(w[6], s, p, j, n); });
 }
 
 }  // namespace c3kf
