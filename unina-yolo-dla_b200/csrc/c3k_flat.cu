@@ -94,31 +94,43 @@ __global__ void __launch_bounds__(NW * 32) c3k_flat_kernel(C3kArgs a) {
   const int H = a.h, W = a.w;
   constexpr int NT = NW * 32;
 
-  for (int i = tid; i < 7 * 32; i += NT) sbias[i] = a.bias[i];
-  // inside-image bit per frame pixel (rows and columns outside the image are every conv's zero padding)
-  for (int i = tid; i < L.FR / 32; i += NT) {
-    uint32_t m = 0u;
-    int ry = (i * 32) / kPW, rx = (i * 32) % kPW;
-    for (int b = 0; b < 32; ++b) {
-      if ((unsigned)(gy0 + ry) < (unsigned)H && (unsigned)(gx0 + rx) < (unsigned)W) m |= 1u << b;
-      if (++rx == kPW) { rx = 0; ++ry; }
-    }
-    maskw[i] = m;
-  }
-  // ---- stage 0: input tile + halo -> X (zero outside the image) ----
+  // ---- stage 0: input tile + halo -> X (zero outside the image).  Eight 16-byte loads per thread are issued
+  // before anything else; the bias copy and the inside-image bits are computed while they are in flight. ----
   {
     constexpr int CH16 = G::CC / 8;  // 16-byte chunks per pixel
+    constexpr int UN = 8;
     const __nv_bfloat16 *img = a.in + (long long)n * H * W * a.in_pitch;
     const int total = L.FR * CH16;
-#pragma unroll 4
-    for (int i = tid; i < total; i += NT) {
-      const int px = i / CH16, ch = i % CH16;
-      const int ry = px / kPW, rx = px - ry * kPW;
-      const int gy = gy0 + ry, gx = gx0 + rx;
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if ((unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W)
-        v = __ldg(reinterpret_cast<const uint4 *>(img + ((long long)gy * W + gx) * a.in_pitch + ch * 8));
-      reinterpret_cast<uint4 *>(X)[i] = v;
+    for (int base = 0; base < total; base += UN * NT) {
+      uint4 v[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int i = base + u * NT + tid;
+        const int px = i / CH16, ch = i % CH16;
+        const int ry = px / kPW, rx = px - ry * kPW;
+        const int gy = gy0 + ry, gx = gx0 + rx;
+        v[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (i < total && (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W)
+          v[u] = __ldg(reinterpret_cast<const uint4 *>(img + (unsigned)((gy * W + gx) * a.in_pitch + ch * 8)));
+      }
+      if (base == 0) {
+        for (int i = tid; i < 7 * 32; i += NT) sbias[i] = a.bias[i];
+        // inside-image bit per frame pixel (rows and columns outside the image are every conv's zero padding)
+        for (int i = tid; i < L.FR / 32; i += NT) {
+          uint32_t m = 0u;
+          int ry = (i * 32) / kPW, rx = (i * 32) % kPW;
+          for (int b = 0; b < 32; ++b) {
+            if ((unsigned)(gy0 + ry) < (unsigned)H && (unsigned)(gx0 + rx) < (unsigned)W) m |= 1u << b;
+            if (++rx == kPW) { rx = 0; ++ry; }
+          }
+          maskw[i] = m;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int i = base + u * NT + tid;
+        if (i < total) reinterpret_cast<uint4 *>(X)[i] = v[u];
+      }
     }
   }
   __syncthreads();
