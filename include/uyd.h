@@ -255,7 +255,8 @@ size_t uyd_nms_workspace_bytes(int batch, int anchors);
  *   first), top max_nms, class-offset (cls*max_wh) greedy NMS with IoU > iou_thr
  *   (fp32 IoU compared against the double threshold, like torchvision), first max_det.
  * out_det [batch, max_det, 6] fp32 rows (x1,y1,x2,y2,conf,cls); out_idx [batch, max_det]
- * anchor index of every kept row (may be NULL); out_count [batch]. */
+ * anchor index of every kept row (may be NULL); out_count [batch].  Every output element is
+ * written: rows past the count are zeros, their index -1 (no pre-initialisation needed). */
 int uyd_nms(uyd_ctx *ctx, const float *y, int batch, int nc, int anchors, float conf_thr,
             double iou_thr, int max_nms, int max_det, float max_wh, void *workspace,
             size_t workspace_bytes, float *out_det, int *out_idx, int *out_count,

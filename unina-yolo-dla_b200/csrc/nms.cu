@@ -602,11 +602,15 @@ __global__ void __launch_bounds__(kFThreads, 1) nms_image_kernel(const float *__
   // ---- 4. emit ----
   __syncthreads();
   const int kept = S.kept;
-  for (int k = tid; k < kept; k += kFThreads) {
+  for (int k = tid; k < max_det; k += kFThreads) {  // every row is defined: zeros / index -1 past the count
     float *o = out_det + ((long long)b * max_det + k) * 6;
-    const float4 r = S.kraw[k];
-    o[0] = r.x; o[1] = r.y; o[2] = r.z; o[3] = r.w; o[4] = S.kconf[k]; o[5] = (float)S.kcls[k];
-    if (out_idx) out_idx[(long long)b * max_det + k] = S.kanchor[k];
+    if (k < kept) {
+      const float4 r = S.kraw[k];
+      o[0] = r.x; o[1] = r.y; o[2] = r.z; o[3] = r.w; o[4] = S.kconf[k]; o[5] = (float)S.kcls[k];
+    } else {
+      o[0] = o[1] = o[2] = o[3] = o[4] = o[5] = 0.f;
+    }
+    if (out_idx) out_idx[(long long)b * max_det + k] = k < kept ? S.kanchor[k] : -1;
   }
   if (tid == 0) out_count[b] = kept;
 }
@@ -706,6 +710,10 @@ extern "C" int uyd_nms(uyd_ctx *ctx, const float *y, int batch, int nc, int anch
   }
   Layout L = carve(workspace, batch, anchors);
   UYD_REQUIRE(L.total <= workspace_bytes, UYD_E_ARG, "uyd_nms: workspace too small (%zu < %zu)", workspace_bytes, L.total);
+  // rows past the count: zeros / index -1 (the emit kernel only writes kept rows)
+  UYD_CUDA(cudaMemsetAsync(out_det, 0, (size_t)batch * max_det * 6 * sizeof(float), s));
+  if (out_idx) UYD_CUDA(cudaMemsetAsync(out_idx, 0xFF, (size_t)batch * max_det * sizeof(int), s));
+  UYD_CUDA(cudaMemsetAsync(out_count, 0, (size_t)batch * sizeof(int), s));
 
   UYD_CUDA(cudaMemsetAsync(L.count, 0, (size_t)batch * 4, s));
   const bool pos = conf_thr >= 0.f;  // NaN-safe: a NaN threshold selects nothing either way

@@ -728,9 +728,10 @@ class UninaYoloB200(nn.Module):
         B, no, A = y.shape
         dev = y.device.index if y.device.index is not None else torch.cuda.current_device()
         ws = self._nms_workspace(dev, B, A, y.device)
-        det = torch.zeros(B, max_det, 6, dtype=torch.float32, device=y.device)
-        idx = torch.full((B, max_det), -1, dtype=torch.int32, device=y.device)
-        cnt = torch.zeros(B, dtype=torch.int32, device=y.device)
+        # uyd_nms defines every output element (zeros / -1 past the count): no fill launches
+        det = torch.empty(B, max_det, 6, dtype=torch.float32, device=y.device)
+        idx = torch.empty((B, max_det), dtype=torch.int32, device=y.device) if return_index else None
+        cnt = torch.empty(B, dtype=torch.int32, device=y.device)
         self._nms_into(y, det, idx, cnt, ws, conf, iou, max_det, max_nms, max_wh)
         return (det, cnt, idx) if return_index else (det, cnt)
 
