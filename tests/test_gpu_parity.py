@@ -61,10 +61,13 @@ TC_CASES = [
     (128, 64, 3, 1, 24, 24, dict()),
     (32, 64, 3, 1, 32, 32, dict()),
     (16, 16, 3, 1, 40, 40, dict(residual=True)),
-    # 3x3 stride 2 (per-tap, TMA traversal stride)
+    # 3x3 stride 2: per-tap boxes with TMA traversal stride; Cin = 32 -> one contiguous pixel-pair box per tile (PAIRS)
     (16, 32, 3, 2, 64, 64, dict()),
     (32, 64, 3, 2, 32, 48, dict()),
     (64, 128, 3, 2, 32, 32, dict()),
+    (32, 32, 3, 2, 80, 80, dict(in_total=96, in_coff=32)),     # input is a channel slice (pair = 2 x 64 B at pitch 192 B)
+    (32, 64, 3, 2, 160, 160, dict(out_total=128, out_coff=64)),  # more tiles than SMs, partial tiles on neither edge
+    (32, 32, 3, 2, 36, 52, dict()),                              # partial tiles on both edges
 ]
 
 

@@ -29,7 +29,14 @@
 
 namespace uyd {
 
-enum { TC_FLAT = 0, TC_HALO = 1, TC_PERTAP = 2 };
+// PAIRS (3x3 stride 2, Cin = 32): ncu of PERTAP showed nothing saturated but the TMA unit -- nine boxes with traversal
+// stride 2 are 1152 separate 64-byte segments per tile (~6 cycles each).  Here ONE contiguous box [34 rows][9 pixel
+// pairs][2 x 32 channels] is loaded per tile (the dense NHWC input viewed as [n][h][w/2][2 c]): an A row is a PAIR of pixels =
+// 128 bytes (SWIZZLE_128B), the even / odd pixel of the pair is a 64-byte offset inside the row (like a k-step),
+// the previous pair a 128-byte row shift (like a HALO tap), and the vertical stride 2 is the descriptor's stride
+// between 8-row groups (2 box rows).  Same 18 MMAs per tile, every input byte fetched once.
+enum { TC_FLAT = 0, TC_HALO = 1, TC_PERTAP = 2, TC_PAIRS = 3 };
+constexpr int kPairRows = 34, kPairCols = 9;  // box of a 16 x 8 output tile: input rows 2 y0 - 1 .., pixel pairs x0 - 1 ..
 
 struct TcParams {
   int mode;
@@ -322,7 +329,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t tmem_base = *slot_ptr;
   griddep_wait();  // from here on the activations written by the previous kernel are read
 
-  const int blocks_per_tile = p.mode == TC_PERTAP ? p.ncb * p.taps : p.ncb;
+  const int blocks_per_tile = p.mode == TC_PERTAP ? p.ncb * p.taps : p.ncb;  // HALO / PAIRS: all taps from one block
   const int cb_elems = I8 ? p.cb_bytes : p.cb_bytes / 2;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const int stages = p.stages;
@@ -359,6 +366,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           } else if (lane < kHaloRows) {
             tma_load_4d(dst + (uint32_t)lane * p.halo_pitch * cb_bytes, &tm_in, fb, j * cb_elems, x0 - 1, y0 - 1 + lane, n);
           }
+        } else if (p.mode == TC_PAIRS) {
+          if (lane == 0) tma_load_4d(dst, &tm_in, fb, 0, x0 - 1, 2 * y0 - 1, n);
         } else {
           if (lane == 0) {
             const int cb = j / p.taps, tap = j % p.taps;
@@ -374,7 +383,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     mbar_wait(wfull, 0);
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
-    const uint64_t adesc0 = make_desc_base(p.sbo_a, p.layout_type);
+    const bool pairs = p.mode == TC_PAIRS;
+    const uint64_t adesc0 = make_desc_base(p.sbo_a, pairs ? 2u : p.layout_type);  // PAIRS: 128-byte A rows, SWIZZLE_128B
     const uint64_t bdesc0 = make_desc_base(8u * cb_bytes, p.layout_type);
     const uint32_t wblk_bytes = (uint32_t)p.N * cb_bytes;
     const uint32_t idesc = p.idesc;
@@ -392,9 +402,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           // tensor pipe, so descriptors are advanced by precomputed 16-byte-unit increments and both
           // loops are fully unrolled (KSTEPS is a template parameter).
           const uint64_t ablk_d = adesc0 + (uint64_t)(((a_s + (uint32_t)stage * blk_bytes) & 0x3FFFFu) >> 4);
-          uint64_t wd = bdesc0 + (uint64_t)(((w_s + (uint32_t)(halo ? j * 9 : j) * wblk_bytes) & 0x3FFFFu) >> 4);
+          uint64_t wd = bdesc0 + (uint64_t)(((w_s + (uint32_t)((halo || pairs) ? j * 9 : j) * wblk_bytes) & 0x3FFFFu) >> 4);
           uint32_t accum = j != 0;
-          if (halo) {
+          if (pairs) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              // box row t / 3 (+ 2 per output row through SBO); kx = 0: odd pixel of pair 0, 1: even pixel of pair 1, 2: its odd pixel
+              const uint64_t ad = ablk_d + (uint64_t)(((t / 3) * kPairCols * 128 + 64 + (t % 3) * 64) >> 4);
+#pragma unroll
+              for (int k = 0; k < KSTEPS; ++k) {
+                umma_bf16(d_tmem, ad + 2 * k, wd + 2 * k, idesc, accum);
+                accum = 1;
+              }
+              wd += wblk_units;
+            }
+          } else if (halo) {
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
               const uint64_t ad = ablk_d + (uint64_t)((t / 3) * row_units + (t % 3) * px_units);
@@ -647,6 +669,10 @@ int tc_prepare(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int i
   p.H = d.k == 1 ? ih : (ih + 2 * 1 - 3) / d.stride + 1;
   p.W = d.k == 1 ? iw : (iw + 2 * 1 - 3) / d.stride + 1;
   p.mode = d.k == 1 ? TC_FLAT : (d.stride == 1 ? TC_HALO : TC_PERTAP);
+  // PAIRS needs a dense input (pitch == Cin: the two pixels of a pair are 128 contiguous bytes) and an even width
+  if (p.mode == TC_PERTAP && d.stride == 2 && !i8 && p.cb_bytes == 64 && p.ncb == 1 && iw % 2 == 0 && in_pitch == d.cin &&
+      (reinterpret_cast<uintptr_t>(in_base) & 127) == 0 && mode_override < 0)
+    p.mode = TC_PAIRS;
   if (mode_override >= 0 && d.k == 3) p.mode = mode_override;
   UYD_REQUIRE(!(p.mode == TC_HALO && d.stride != 1), UYD_E_UNSUPPORTED, "conv_tc: HALO mode needs stride 1");
   p.base_offset_mode = base_offset_mode;
@@ -661,6 +687,11 @@ int tc_prepare(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int i
     p.blk_bytes = (uint32_t)kHaloRows * p.halo_pitch * p.cb_bytes;
     p.tx_bytes = (uint32_t)kHaloRows * (kTileW + 2) * p.cb_bytes;
     p.sbo_a = (uint32_t)p.halo_pitch * p.cb_bytes;
+  } else if (p.mode == TC_PAIRS) {
+    p.halo_pitch = kPairCols;
+    p.blk_bytes = (uint32_t)kPairRows * kPairCols * 128u;
+    p.tx_bytes = p.blk_bytes;
+    p.sbo_a = 2u * kPairCols * 128u;  // consecutive output rows are two box rows apart
   } else {
     p.blk_bytes = 128u * p.cb_bytes;
     p.tx_bytes = p.blk_bytes;
@@ -678,7 +709,7 @@ int tc_prepare(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int i
   UYD_REQUIRE(!i8 || can_stage, UYD_E_UNSUPPORTED, "conv_tc int8: output rows must be a power-of-two number of 16-byte lanes");
   const size_t wres = (p.w_bytes + 1023u) & ~1023u;
   // as many epilogue groups as the staging tiles leave room for next to the resident weights and two stages
-  const size_t two_stages = 2 * (((size_t)(p.mode == TC_HALO ? (uint32_t)kHaloRows * p.halo_pitch * p.cb_bytes : 128u * p.cb_bytes) + 1023u) & ~(size_t)1023);
+  const size_t two_stages = 2 * (((size_t)(p.mode == TC_HALO ? (uint32_t)kHaloRows * p.halo_pitch * p.cb_bytes : (p.mode == TC_PAIRS ? (uint32_t)kPairRows * kPairCols * 128u : 128u * p.cb_bytes)) + 1023u) & ~(size_t)1023);
   p.ngroups = kEpiGroups;
   while (p.ngroups > 1 && p.stage_pitch && wres + two_stages + kTailFixed + (size_t)128 * p.ngroups * p.stage_pitch > 227 * 1024 - 1024)
     p.ngroups >>= 1;
@@ -689,7 +720,7 @@ int tc_prepare(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int i
     tail = kTailFixed;
   }
   const size_t budget = 227 * 1024 - 1024 - tail;
-  if (p.mode == TC_HALO && wres + 2 * (size_t)p.blk_bytes > budget) {  // halo blocks too big: one box per tap
+  if ((p.mode == TC_HALO || p.mode == TC_PAIRS) && wres + 2 * (size_t)p.blk_bytes > budget) {  // blocks too big: one box per tap
     p.mode = TC_PERTAP;
     p.blk_bytes = 128u * p.cb_bytes;
     p.tx_bytes = p.blk_bytes;
@@ -699,7 +730,7 @@ int tc_prepare(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int i
   UYD_REQUIRE(wres + 2 * (size_t)p.blk_bytes <= budget, UYD_E_UNSUPPORTED, "conv_tc: weights (%u B) leave no room for 2 stages",
               p.w_bytes);
   int stages = (int)((budget - wres) / p.blk_bytes);
-  const int want = p.mode == TC_HALO ? 4 : 12;
+  const int want = p.mode == TC_HALO ? 4 : (p.mode == TC_PAIRS ? 3 : 12);
   if (stages > want) stages = want;
   if (stages_override > 0 && stages_override < stages) stages = stages_override;
   p.stages = stages;
@@ -727,6 +758,12 @@ int tc_prepare(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int i
     const cuuint64_t str[1] = {(cuuint64_t)in_pitch * es};
     const cuuint32_t box[2] = {(cuuint32_t)CB, 128};
     int e = encode(&tc->tm_in, in_base, 2, dims, str, box, one4, p.cb_bytes, i8);
+    if (e) return e;
+  } else if (p.mode == TC_PAIRS) {  // [n][h][w/2][2 c]: a box row = one pixel pair = 128 contiguous bytes
+    const cuuint64_t dims[4] = {(cuuint64_t)2 * d.cin, (cuuint64_t)(iw / 2), (cuuint64_t)ih, (cuuint64_t)max_batch};
+    const cuuint64_t str[3] = {(cuuint64_t)2 * in_pitch * es, (cuuint64_t)iw * in_pitch * es, (cuuint64_t)ih * iw * in_pitch * es};
+    const cuuint32_t box[4] = {(cuuint32_t)2 * CB, (cuuint32_t)kPairCols, (cuuint32_t)kPairRows, 1};
+    int e = encode(&tc->tm_in, in_base, 4, dims, str, box, one4, 128, i8);
     if (e) return e;
   } else {
     const cuuint64_t dims[4] = {(cuuint64_t)d.cin, (cuuint64_t)iw, (cuuint64_t)ih, (cuuint64_t)max_batch};
@@ -779,6 +816,8 @@ int tc_launch(const TcConv *tc, int n0, int nb, int sm_count, cudaStream_t s) {
 void tc_set_pre(TcConv *tc, const float *pre) { tc->p.pre = pre; }
 TcConv *tc_new() { return new TcConv(); }
 void tc_delete(TcConv *t) { delete t; }
-const char *tc_mode_name(const TcConv *t) { return t->p.mode == TC_FLAT ? "flat" : (t->p.mode == TC_HALO ? "halo" : "pertap"); }
+const char *tc_mode_name(const TcConv *t) {
+  return t->p.mode == TC_FLAT ? "flat" : (t->p.mode == TC_HALO ? "halo" : (t->p.mode == TC_PAIRS ? "pairs" : "pertap"));
+}
 
 }  // namespace uyd
