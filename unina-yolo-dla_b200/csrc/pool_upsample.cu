@@ -68,6 +68,53 @@ __global__ void __launch_bounds__(kThreads) sppf_pool_kernel(__nv_bfloat16 *base
   }
 }
 
+// Plane formulation of the same cascade (used when two planes of h x w x 32 bytes fit shared memory, i.e. the
+// network's 40 x 40 SPPF): one CTA owns (image, two 8-channel groups = one 32-byte sector per pixel), loads the plane
+// ONCE and runs the three cascaded 5 x 5 pools separably in shared memory (horizontal into B, vertical back into A and
+// out to the concat slice).  The row kernel above re-reads every input row 13 times through L2 (3.5 TB/s of L2
+// traffic, 49 us at batch 64); here every byte is read once.
+constexpr int kPlaneThreads = 512;
+__global__ void __launch_bounds__(kPlaneThreads) sppf_plane_kernel(__nv_bfloat16 *base, int h, int w, int pitch, int c, int gp) {
+  pdl_trigger();
+  extern __shared__ uint4 pl[];  // A [h*w*gp] | B [h*w*gp]
+  const int groups = (c / 8) / gp;
+  const int n = blockIdx.x / groups, g0 = (blockIdx.x % groups) * gp;
+  const int items = h * w * gp;
+  uint4 *A = pl, *B = pl + items;
+  __nv_bfloat16 *img = base + (long long)n * h * w * pitch + g0 * 8;
+  const uint4 ninf = make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u);  // bf16 -inf x8
+  for (int it = threadIdx.x; it < items; it += kPlaneThreads) {
+    const int px = it / gp, g = it - px * gp;
+    A[it] = *reinterpret_cast<const uint4 *>(img + (long long)px * pitch + g * 8);
+  }
+  __syncthreads();
+  const int rowi = w * gp;
+  for (int stage = 1; stage <= 3; ++stage) {
+    for (int it = threadIdx.x; it < items; it += kPlaneThreads) {  // horizontal 5-max, clipped = -inf padding
+      const int x = (it % rowi) / gp;
+      uint4 m = A[it];
+      if (x >= 1) m = max8(m, A[it - gp]);
+      if (x >= 2) m = max8(m, A[it - 2 * gp]);
+      if (x + 1 < w) m = max8(m, A[it + gp]);
+      if (x + 2 < w) m = max8(m, A[it + 2 * gp]);
+      B[it] = m;
+    }
+    __syncthreads();
+    for (int it = threadIdx.x; it < items; it += kPlaneThreads) {  // vertical 5-max -> A (input of the next pool) and out
+      const int y = it / rowi;
+      uint4 m = B[it];
+      if (y >= 1) m = max8(m, B[it - rowi]);
+      if (y >= 2) m = max8(m, B[it - 2 * rowi]);
+      if (y + 1 < h) m = max8(m, B[it + rowi]);
+      if (y + 2 < h) m = max8(m, B[it + 2 * rowi]);
+      A[it] = m;
+      const int px = it / gp, g = it - px * gp;
+      *reinterpret_cast<uint4 *>(img + (long long)px * pitch + stage * c + g * 8) = m;
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) upsample2x_kernel(const __nv_bfloat16 *in, int in_pitch, __nv_bfloat16 *out,
                                                               int out_pitch, long long total, int oh, int ow, int cg) {
   const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
@@ -105,6 +152,15 @@ __global__ void nhwc_to_nchw_kernel(const float *in, float *out, int hw, int c) 
 int sppf_pool_launch(__nv_bfloat16 *base, int n, int h, int w, int pitch, int c, cudaStream_t s) {
   UYD_REQUIRE(c % 8 == 0 && pitch % 8 == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0, UYD_E_UNSUPPORTED,
               "sppf pool needs C %% 8 == 0 and 16-byte aligned slices");
+  static const bool rows_only = [] { const char *v = getenv("UYD_SPPF_ROWS"); return v && *v == '1'; }();
+  const int gp = (c / 8) % 2 == 0 ? 2 : 1;
+  const size_t plane = (size_t)2 * h * w * gp * sizeof(uint4);
+  if (!rows_only && plane <= 110 * 1024) {  // two CTAs per SM
+    static bool attr = false;
+    if (!attr) { UYD_CUDA(cudaFuncSetAttribute(sppf_plane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); attr = true; }
+    sppf_plane_kernel<<<n * ((c / 8) / gp), kPlaneThreads, plane, s>>>(base, h, w, pitch, c, gp);
+    return (int)cudaGetLastError();
+  }
   const size_t smem = (size_t)3 * w * (c / 8) * sizeof(uint4);
   UYD_REQUIRE(smem <= 200 * 1024, UYD_E_UNSUPPORTED, "sppf row does not fit shared memory");
   if (smem > 48 * 1024) cudaFuncSetAttribute(sppf_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
