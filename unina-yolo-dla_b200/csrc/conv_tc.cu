@@ -719,7 +719,7 @@ int tc_prepare(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int i
     p.ngroups = kEpiGroups;
     tail = kTailFixed;
   }
-  const size_t budget = 227 * 1024 - 1024 - tail;
+  const size_t budget = 227 * 1024 - 1024 - tail;  // (PAIRS may trade epilogue groups for a third stage below)
   if ((p.mode == TC_HALO || p.mode == TC_PAIRS) && wres + 2 * (size_t)p.blk_bytes > budget) {  // blocks too big: one box per tap
     p.mode = TC_PERTAP;
     p.blk_bytes = 128u * p.cb_bytes;
@@ -730,6 +730,12 @@ int tc_prepare(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int i
   UYD_REQUIRE(wres + 2 * (size_t)p.blk_bytes <= budget, UYD_E_UNSUPPORTED, "conv_tc: weights (%u B) leave no room for 2 stages",
               p.w_bytes);
   int stages = (int)((budget - wres) / p.blk_bytes);
+  if (p.mode == TC_PAIRS && stages < 3 && p.ngroups > 2 && p.stage_pitch) {
+    // a PAIRS stage is a whole tile (39 KB): a third tile in flight hides more TMA latency than epilogue groups 3 and 4
+    const size_t tail2 = kTailFixed + (size_t)128 * 2 * p.stage_pitch;
+    const int stages2 = (int)((227 * 1024 - 1024 - tail2 - wres) / p.blk_bytes);
+    if (stages2 > stages) { p.ngroups = 2; tail = tail2; stages = stages2; }
+  }
   const int want = p.mode == TC_HALO ? 4 : (p.mode == TC_PAIRS ? 3 : 12);
   if (stages > want) stages = want;
   if (stages_override > 0 && stages_override < stages) stages = stages_override;
