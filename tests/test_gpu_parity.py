@@ -512,6 +512,27 @@ def test_fused_stem_matches_torch(T, H, W, u8, pw):
     assert float(p.read(p.buffer_slice(dst.buf, dst.coff + dst.c, p.shapes[dst.buf][2] - dst.coff - dst.c), B).abs().max()) == 0.0
 
 
+def test_plan_errors_are_reported_not_thrown(T):
+    """The C ABI returns an error code + message (gpu_postprocess.h convention: cudaError_t-like int, no exceptions
+    across the boundary); the Python host turns it into UydError.  Misaligned / misplaced ops are refused at build time."""
+    import unina_yolo_dla_b200 as uyd
+    from unina_yolo_dla_b200._lib import UydError
+
+    z = lambda *s: np.zeros(s, np.float32)
+    p = uyd.Plan(0, 1)
+    dst = p.buffer(16, 16, 40).sub(2, 16)                     # 4-byte aligned slice: the folded stem needs 8
+    with pytest.raises(UydError):
+        p.stem2(dst, z(16, 3, 3, 3), z(16), z(32, 16, 3, 3), z(32), z(16, 32), z(16))
+    p = uyd.Plan(0, 1)
+    a, b = p.buffer(16, 16, 32), p.buffer(16, 16, 32)
+    p.conv(a, b, z(32, 32, 1, 1), z(32), 1, 1)
+    with pytest.raises(UydError):                              # only the first op may read the network input
+        p.stem2(p.buffer(16, 16, 32), z(16, 3, 3, 3), z(16), z(32, 16, 3, 3), z(32))
+    p.finalize()
+    with pytest.raises(UydError):                              # no op may be added after finalize
+        p.conv(a, b, z(32, 32, 1, 1), z(32), 1, 1)
+
+
 @pytest.mark.parametrize("ca,cb,cout,h,w", [(64, 32, 16, 40, 40), (128, 64, 32, 24, 40), (64, 32, 16, 160, 160)])
 def test_upsample_concat_conv_fold_matches_torch(T, ca, cb, cout, h, w):
     """Upsample(x2) + Concat + 1x1 Conv computed as relu(up(W_a a) + W_b b + bias): the half-resolution partial
