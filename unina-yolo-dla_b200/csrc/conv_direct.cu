@@ -581,6 +581,43 @@ __global__ void __launch_bounds__(256) quantize_s8_kernel(const __nv_bfloat16 *_
   *reinterpret_cast<uint32_t *>(out + p * out_pitch + c0) = w;
 }
 
+// 16 channels per thread (two 16-byte loads, one 16-byte store), four items per thread in flight, 32-bit indexing:
+// the 4-channel kernel above reached 3.1 TB/s (121 quantize launches = 35 % of the INT8 step).  Same arithmetic per element.
+__device__ __forceinline__ uint32_t quant4(uint32_t lo, uint32_t hi, float scale) {
+  const float f0 = __uint_as_float(lo << 16), f1 = __uint_as_float(lo & 0xffff0000u);
+  const float f2 = __uint_as_float(hi << 16), f3 = __uint_as_float(hi & 0xffff0000u);
+  const int q0 = max(-127, min(127, __float2int_rn(__fmul_rn(f0, scale))));
+  const int q1 = max(-127, min(127, __float2int_rn(__fmul_rn(f1, scale))));
+  const int q2 = max(-127, min(127, __float2int_rn(__fmul_rn(f2, scale))));
+  const int q3 = max(-127, min(127, __float2int_rn(__fmul_rn(f3, scale))));
+  return (uint32_t)(q0 & 0xFF) | ((uint32_t)(q1 & 0xFF) << 8) | ((uint32_t)(q2 & 0xFF) << 16) | ((uint32_t)(q3 & 0xFF) << 24);
+}
+__global__ void __launch_bounds__(256) quantize_s8_x16_kernel(const __nv_bfloat16 *__restrict__ in, int in_pitch,
+                                                              int8_t *__restrict__ out, int out_pitch, unsigned total, int cg,
+                                                              float scale) {
+  constexpr int U = 4;
+  const unsigned t0 = blockIdx.x * (256u * U) + threadIdx.x;
+  uint4 a[U], b[U];
+  unsigned px[U], c0[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const unsigned t = t0 + u * 256u;
+    px[u] = t / (unsigned)cg;
+    c0[u] = (t - px[u] * (unsigned)cg) * 16u;
+    if (t < total) {
+      const uint4 *src = reinterpret_cast<const uint4 *>(in + (size_t)px[u] * in_pitch + c0[u]);
+      a[u] = src[0];
+      b[u] = src[1];
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (t0 + u * 256u < total)
+      *reinterpret_cast<uint4 *>(out + (size_t)px[u] * out_pitch + c0[u]) =
+          make_uint4(quant4(a[u].x, a[u].y, scale), quant4(a[u].z, a[u].w, scale), quant4(b[u].x, b[u].y, scale), quant4(b[u].z, b[u].w, scale));
+  }
+}
+
 // |x| maximum of a bf16 slice (max calibration of the input quantisers, qat.py:129-220): the bit pattern of a
 // non-negative float orders like an unsigned integer, so one atomicMax per block suffices.
 __global__ void __launch_bounds__(256) absmax_kernel(const __nv_bfloat16 *__restrict__ in, int in_pitch, long long npix, int c,
@@ -639,6 +676,12 @@ int quantize_s8_launch(const __nv_bfloat16 *in, int in_pitch, int8_t *out, int o
                        cudaStream_t s) {
   UYD_REQUIRE(c % 4 == 0 && in_pitch % 4 == 0 && out_pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 7) == 0 &&
                   (reinterpret_cast<uintptr_t>(out) & 3) == 0, UYD_E_UNSUPPORTED, "quantize: C %% 4 == 0 and aligned slices");
+  if (c % 16 == 0 && in_pitch % 8 == 0 && out_pitch % 16 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(out) & 15) == 0 && npix * (c / 16) < (1ll << 31)) {
+    const unsigned total16 = (unsigned)(npix * (c / 16));
+    quantize_s8_x16_kernel<<<(total16 + 1023u) / 1024u, 256, 0, s>>>(in, in_pitch, out, out_pitch, total16, c / 16, scale);
+    return (int)cudaGetLastError();
+  }
   const long long total = npix * (c / 4);
   quantize_s8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, in_pitch, out, out_pitch, npix, c, scale);
   return (int)cudaGetLastError();
