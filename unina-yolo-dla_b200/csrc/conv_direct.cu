@@ -526,6 +526,52 @@ __global__ void __launch_bounds__(128) conv_s8_direct_kernel(ConvArgs a, const f
   }
 }
 
+// 4 -> 4 channels, 3x3, stride 1, bf16 output (the bottleneck convs of the 160 x 160 C3k blocks in the INT8 graph): the
+// general kernel above spends its time on 64-bit index arithmetic, per-tap weight loads and four 2-byte stores
+// (0.27 ms per launch at batch 256 = 0.3 TB/s).  Here: 32-bit indices, the 36 weight words in registers, one 8-byte
+// store per pixel.  Identical arithmetic per element (exact int32 sums, the same fp32 epilogue ops in the same order).
+__global__ void __launch_bounds__(256) conv_s8_c4_kernel(ConvArgs a, const float *__restrict__ mult) {
+  const unsigned npix = (unsigned)a.n * a.oh * a.ow;
+  const unsigned p = blockIdx.x * 256u + threadIdx.x;
+  int wr[9][4];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) wr[t][j] = __ldg(reinterpret_cast<const int *>(a.w) + t * 4 + j);  // [tap][cout][cin = 4]
+  if (p >= npix) return;
+  const unsigned hw = (unsigned)a.oh * a.ow;
+  const unsigned n = p / hw, r = p - n * hw, oy = r / (unsigned)a.ow, ox = r - oy * (unsigned)a.ow;
+  const int8_t *in = reinterpret_cast<const int8_t *>(a.in);
+  int acc[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = (int)oy + ky - 1;
+    if (iy < 0 || iy >= a.ih) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ix = (int)ox + kx - 1;
+      if (ix < 0 || ix >= a.iw) continue;
+      const int x = *reinterpret_cast<const int *>(in + (size_t)((n * a.ih + iy) * a.iw + ix) * a.in_pitch);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] = __dp4a(x, wr[ky * 3 + kx][j], acc[j]);
+    }
+  }
+  float y[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    y[j] = __fadd_rn(__fmul_rn(__int2float_rn(acc[j]), __ldg(mult + j)), __ldg(a.bias + j));
+    if (a.relu) y[j] = fmaxf(y[j], 0.f);
+  }
+  if (a.res) {
+    const uint2 rv = *reinterpret_cast<const uint2 *>(reinterpret_cast<const __nv_bfloat16 *>(a.res) + (size_t)p * a.res_pitch);
+    y[0] = __fadd_rn(y[0], __uint_as_float(rv.x << 16)); y[1] = __fadd_rn(y[1], __uint_as_float(rv.x & 0xffff0000u));
+    y[2] = __fadd_rn(y[2], __uint_as_float(rv.y << 16)); y[3] = __fadd_rn(y[3], __uint_as_float(rv.y & 0xffff0000u));
+  }
+  const __nv_bfloat162 h0 = __floats2bfloat162_rn(y[0], y[1]), h1 = __floats2bfloat162_rn(y[2], y[3]);
+  *reinterpret_cast<uint2 *>(reinterpret_cast<__nv_bfloat16 *>(a.out) + (size_t)p * a.out_pitch) =
+      make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
+}
+
 // depth-wise 3x3 (any stride), thread = pixel x 4 channels
 __global__ void __launch_bounds__(128) conv_s8_dw_kernel(ConvArgs a, const float *mult, float out_scale, int out_kind) {
   const int cg = a.cin / 4;
@@ -659,6 +705,12 @@ int direct_conv_s8_launch(const ConvArgs &a, const float *mult, float out_scale,
   UYD_REQUIRE(a.cin % 4 == 0 && a.in_pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(a.in) & 3) == 0, UYD_E_UNSUPPORTED,
               "int8 direct conv needs cin %% 4 == 0 and 4-byte aligned input slices");
   const long long npix = (long long)a.n * a.oh * a.ow;
+  const auto al8 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 7) == 0; };
+  if (a.cin == 4 && a.cout == 4 && a.k == 3 && a.stride == 1 && out_kind == 0 && a.oh == a.ih && a.ow == a.iw && npix < (1ll << 31) &&
+      npix * a.in_pitch < (1ll << 32) && a.out_pitch % 4 == 0 && al8(a.out) && (!a.res || (a.res_pitch % 4 == 0 && al8(a.res)))) {
+    conv_s8_c4_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, s>>>(a, mult);
+    return (int)cudaGetLastError();
+  }
   dim3 grid((unsigned)((npix + 127) / 128), (unsigned)ceil_div(a.cout, 4));
   conv_s8_direct_kernel<<<grid, 128, 0, s>>>(a, mult, out_scale, out_kind);
   return (int)cudaGetLastError();
