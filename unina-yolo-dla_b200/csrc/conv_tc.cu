@@ -221,11 +221,31 @@ __device__ __forceinline__ void epilogue_chunk_staged(const uint32_t (&raw)[16],
 // oracle's integer reference, oracle/quant.py), ReLU, then bf16 / fp32 / re-quantised int8.
 __device__ __forceinline__ void epilogue_chunk_i8_staged(const uint32_t (&raw)[16], const float *bias_s, const float *mult_s,
                                                          int c0, long long pix, const TcParams &p, unsigned char *srow) {
-  float v[16];
+  float v[16], mv[16], bv[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const float x = __fadd_rn(__fmul_rn(__int2float_rn((int)raw[i]), mult_s[c0 + i]), bias_s[c0 + i]);
-    v[i] = p.relu ? fmaxf(x, 0.f) : x;
+  for (int i = 0; i < 4; ++i) {  // 16-byte broadcast loads of the multiplier / bias vectors
+    const float4 m4 = reinterpret_cast<const float4 *>(mult_s + c0)[i], b4 = reinterpret_cast<const float4 *>(bias_s + c0)[i];
+    mv[4 * i] = m4.x; mv[4 * i + 1] = m4.y; mv[4 * i + 2] = m4.z; mv[4 * i + 3] = m4.w;
+    bv[4 * i] = b4.x; bv[4 * i + 1] = b4.y; bv[4 * i + 2] = b4.z; bv[4 * i + 3] = b4.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __fadd_rn(__fmul_rn(__int2float_rn((int)raw[i]), mv[i]), bv[i]);
+  if (p.relu && !p.res && p.out_kind == 0) {  // the common case: ReLU rides on the bf16 conversion
+    uint4 o0, o1;
+    uint32_t *w0 = reinterpret_cast<uint32_t *>(&o0), *w1 = reinterpret_cast<uint32_t *>(&o1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      w0[i] = relu_pack_bf16x2(v[2 * i], v[2 * i + 1]);
+      w1[i] = relu_pack_bf16x2(v[8 + 2 * i], v[8 + 2 * i + 1]);
+    }
+    uint4 *sp = reinterpret_cast<uint4 *>(srow + c0 * 2);
+    sp[0] = o0;
+    sp[1] = o1;
+    return;
+  }
+  if (p.relu) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
   }
   if (p.res && pix >= 0) {  // residual (bf16) added in fp32 after the activation
     const __nv_bfloat16 *rp = p.res + pix * p.res_pitch + c0;
