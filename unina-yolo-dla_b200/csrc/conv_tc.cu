@@ -756,7 +756,7 @@ int tc_prepare(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int i
     const int stages2 = (int)((227 * 1024 - 1024 - tail2 - wres) / p.blk_bytes);
     if (stages2 > stages) { p.ngroups = 2; tail = tail2; stages = stages2; }
   }
-  const int want = p.mode == TC_HALO ? 4 : (p.mode == TC_PAIRS ? 3 : 12);
+  const int want = p.mode == TC_HALO ? 4 : (p.mode == TC_PAIRS ? 4 : 12);
   if (stages > want) stages = want;
   if (stages_override > 0 && stages_override < stages) stages = stages_override;
   p.stages = stages;
