@@ -475,14 +475,13 @@ def test_fused_decode_plan_equals_raw_head_plan(T):
 
 @pytest.mark.parametrize("H,W,u8,pw", [(64, 96, False, False), (160, 128, True, False), (640, 640, False, False),
                                         (64, 96, True, True), (100, 136, False, True), (640, 640, True, True)])
-def test_fused_stem_matches_torch(T, H, W, u8, pw):
+def test_fused_stem_matches_torch(T, H, W, u8, pw, B=2):
     """Conv(3,16,3,2) -> Conv(16,32,3,2) (-> 1x1 Conv(32,16), model.2.cv1) in one launch: the frame is rounded to
     tf32 (2^-11), the 16- and 32-channel intermediates are rounded to bf16 exactly where the unfused plan rounds them."""
     import torch.nn.functional as F
     import unina_yolo_dla_b200 as uyd
 
     g = torch.Generator().manual_seed(H + W)
-    B = 2
     r = T.bf16_round
     w0, w1 = torch.randn(16, 3, 3, 3, generator=g) / 27 ** 0.5, torch.randn(32, 16, 3, 3, generator=g) / 144 ** 0.5
     w2 = torch.randn(16, 32, 1, 1, generator=g) / 32 ** 0.5
@@ -510,6 +509,13 @@ def test_fused_stem_matches_torch(T, H, W, u8, pw):
     assert T.rel_err(got, want) < 6e-3
     assert float(p.read(p.buffer_slice(dst.buf, 0, dst.coff), B).abs().max()) == 0.0   # nothing outside the slice
     assert float(p.read(p.buffer_slice(dst.buf, dst.coff + dst.c, p.shapes[dst.buf][2] - dst.coff - dst.c), B).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("u8,pw", [(False, True), (True, False)])
+def test_fused_stem_persistent_ctas(T, u8, pw):
+    """Enough tiles (8 x 1600 > 8 per SM) for the persistent variant: CTAs walk the tiles with the layer-1 weight
+    fragments in registers; a tile's shared-memory planes are recycled by the next one."""
+    test_fused_stem_matches_torch(T, 640, 640, u8, pw, B=8)
 
 
 def test_plan_errors_are_reported_not_thrown(T):

@@ -256,16 +256,32 @@ __device__ __forceinline__ uint32_t movmatrix_trans(uint32_t v) {
   return r;
 }
 
-template <typename TIn, bool PW>
-__global__ void __launch_bounds__(stemv2::kThreads, 3) stem_v2_kernel(StemArgs a) {
+// PERSIST: two CTAs per SM walk the tiles and keep the 18 layer-1 A fragments in registers (the per-tile re-read of
+// those 9 KB by each of the eight warps is 576 of the ~3100 L1/shared wavefronts a tile costs, the kernel's bound).
+template <typename TIn, bool PW, bool PERSIST>
+__global__ void __launch_bounds__(stemv2::kThreads, PERSIST ? 2 : 3) stem_v2_kernel(StemArgs a) {
   pdl_trigger();
   extern __shared__ __align__(16) unsigned char smem[];
   unsigned char *patch = smem;                             // [3][38 lines: even rows at 0, odd rows at 20][68] fp32 (tf32)
   unsigned char *l0s = smem + kPatchBytes;                 // [584 pixels q = 34 y + x][48 B]: word w = channels (w, w+8)
-  unsigned char *w1s = smem + kPatchBytes + kL0Bytes;      // layer-1 A fragments [tap][m-tile][lane] x 16 B
+  unsigned char *w1s = smem + kPatchBytes + kL0Bytes;      // layer-1 A fragments [tap][m-tile][lane] x 16 B (!PERSIST)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int ox0 = blockIdx.x * kTW, oy0 = blockIdx.y * kTH, n = blockIdx.z;
+  uint4 w1r[PERSIST ? 18 : 1];
+  if (PERSIST) {
+#pragma unroll
+    for (int i = 0; i < (PERSIST ? 18 : 0); ++i) w1r[i] = __ldg(reinterpret_cast<const uint4 *>(a.wfrag + kW0Words) + i * 32 + lane);
+  }
+  const int tiles_x = (a.ow + kTW - 1) / kTW, tiles_y = (a.oh + kTH - 1) / kTH;
+  const int total_tiles = PERSIST ? tiles_x * tiles_y * a.n : 1;
+  for (int tile = PERSIST ? (int)blockIdx.x : 0; tile < total_tiles; tile += PERSIST ? (int)gridDim.x : 1) {
+  int ox0, oy0, n;
+  if (PERSIST) {
+    const int per = tiles_x * tiles_y, r = tile % per;
+    n = tile / per; oy0 = (r / tiles_x) * kTH; ox0 = (r % tiles_x) * kTW;
+  } else {
+    ox0 = blockIdx.x * kTW; oy0 = blockIdx.y * kTH; n = blockIdx.z;
+  }
   const int ix0 = 4 * ox0 - 4, iy0 = 4 * oy0 - 3;  // frame coordinates of the patch origin (16-byte aligned columns)
 
   // ---- all global loads first: layer-1 fragments and this thread's 7 patch vectors (column j, lines rl + 15 i) ----
@@ -275,7 +291,7 @@ __global__ void __launch_bounds__(stemv2::kThreads, 3) stem_v2_kernel(StemArgs a
 #pragma unroll
   for (int it = 0; it < kWIters; ++it) {
     const int i = tid + it * kThreads;
-    wv[it] = i < kW1Vec ? __ldg(w1g + i) : make_uint4(0u, 0u, 0u, 0u);
+    wv[it] = (!PERSIST && i < kW1Vec) ? __ldg(w1g + i) : make_uint4(0u, 0u, 0u, 0u);
   }
   // thread (pj, prl): column vector pj of patch rows prl, prl + 15 and (prl < 5) prl + 30 of each channel
   constexpr int kVecPerRow = kInW / 4, kRowLanes = 15;  // 17 vectors per row, 255 loading threads
@@ -309,7 +325,7 @@ __global__ void __launch_bounds__(stemv2::kThreads, 3) stem_v2_kernel(StemArgs a
 #pragma unroll
   for (int it = 0; it < kWIters; ++it) {
     const int i = tid + it * kThreads;
-    if (i < kW1Vec) reinterpret_cast<uint4 *>(w1s)[i] = wv[it];
+    if (!PERSIST && i < kW1Vec) reinterpret_cast<uint4 *>(w1s)[i] = wv[it];
   }
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
@@ -392,7 +408,7 @@ __global__ void __launch_bounds__(stemv2::kThreads, 3) stem_v2_kernel(StemArgs a
     const uint4 *wf = reinterpret_cast<const uint4 *>(w1s) + lane;
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
-      const uint4 a0 = wf[(tap * 2 + 0) * 32], a1 = wf[(tap * 2 + 1) * 32];
+      const uint4 a0 = PERSIST ? w1r[PERSIST ? tap * 2 : 0] : wf[(tap * 2 + 0) * 32], a1 = PERSIST ? w1r[PERSIST ? tap * 2 + 1 : 0] : wf[(tap * 2 + 1) * 32];
 #pragma unroll
       for (int xg = 0; xg < 2; ++xg) {
         const uint2 b = ld64(bb + ((tap / 3) * kL0P + 16 * xg + tap % 3) * kL0Pitch);
@@ -436,6 +452,7 @@ __global__ void __launch_bounds__(stemv2::kThreads, 3) stem_v2_kernel(StemArgs a
       }
     }
   }
+  }  // tile loop
 }
 }  // namespace stemv2
 namespace {
@@ -488,24 +505,30 @@ void stem_fused_pack(const float *w0, const float *b0, const float *w1, const fl
 static int stem_v2_launch(const StemArgs &a0, cudaStream_t s) {
   StemArgs a = a0;
   a.wfrag += (6 + 36) * 64;  // skip the legacy fragments
-  static bool attr = false;
-  if (!attr) {
-    UYD_CUDA(cudaFuncSetAttribute(stemv2::stem_v2_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, stemv2::kSmemBytes));
-    UYD_CUDA(cudaFuncSetAttribute(stemv2::stem_v2_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, stemv2::kSmemBytes));
-    UYD_CUDA(cudaFuncSetAttribute(stemv2::stem_v2_kernel<uint8_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, stemv2::kSmemBytes));
-    UYD_CUDA(cudaFuncSetAttribute(stemv2::stem_v2_kernel<uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, stemv2::kSmemBytes));
-    attr = true;
+  static const bool persist = [] { const char *v = getenv("UYD_STEM_PERSIST"); return !(v && *v == '0'); }();
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    UYD_CUDA(cudaGetDevice(&dev));
+    UYD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  dim3 grid(ceil_div(a.ow, stemv2::kTW), ceil_div(a.oh, stemv2::kTH), a.n);
+  const int tiles = ceil_div(a.ow, stemv2::kTW) * ceil_div(a.oh, stemv2::kTH) * a.n;
   const size_t smem = stemv2::kSmemBytes;
+  auto go = [&](auto kern, bool pers) -> int {
+    UYD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, stemv2::kSmemBytes));
+    if (pers) kern<<<tiles < 2 * sms ? tiles : 2 * sms, stemv2::kThreads, smem, s>>>(a);
+    else kern<<<dim3(ceil_div(a.ow, stemv2::kTW), ceil_div(a.oh, stemv2::kTH), a.n), stemv2::kThreads, smem, s>>>(a);
+    return (int)cudaGetLastError();
+  };
+  // persistent CTAs pay off once there are several tiles per CTA (batch-1 frames keep one tile per CTA)
+  const bool pers = persist && tiles >= 8 * sms;
+  using namespace stemv2;
   if (a.u8) {
-    if (a.pw) stemv2::stem_v2_kernel<uint8_t, true><<<grid, stemv2::kThreads, smem, s>>>(a);
-    else stemv2::stem_v2_kernel<uint8_t, false><<<grid, stemv2::kThreads, smem, s>>>(a);
-  } else {
-    if (a.pw) stemv2::stem_v2_kernel<float, true><<<grid, stemv2::kThreads, smem, s>>>(a);
-    else stemv2::stem_v2_kernel<float, false><<<grid, stemv2::kThreads, smem, s>>>(a);
+    if (a.pw) return pers ? go(stem_v2_kernel<uint8_t, true, true>, true) : go(stem_v2_kernel<uint8_t, true, false>, false);
+    return pers ? go(stem_v2_kernel<uint8_t, false, true>, true) : go(stem_v2_kernel<uint8_t, false, false>, false);
   }
-  return (int)cudaGetLastError();
+  if (a.pw) return pers ? go(stem_v2_kernel<float, true, true>, true) : go(stem_v2_kernel<float, true, false>, false);
+  return pers ? go(stem_v2_kernel<float, false, true>, true) : go(stem_v2_kernel<float, false, false>, false);
 }
 
 int stem_fused_launch(const StemArgs &a, cudaStream_t s) {
