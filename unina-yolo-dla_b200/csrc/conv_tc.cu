@@ -404,8 +404,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
     const bool pairs = p.mode == TC_PAIRS;
-    // PAIRS: an A row is a pixel pair = 2 cb_bytes (128 bytes -> SWIZZLE_128B, 64 bytes -> SWIZZLE_64B)
-    const uint64_t adesc0 = make_desc_base(p.sbo_a, pairs ? (cb_bytes == 64 ? 2u : 4u) : p.layout_type);
+    const uint64_t adesc0 = make_desc_base(p.sbo_a, pairs ? 2u : p.layout_type);  // PAIRS: 128-byte A rows, SWIZZLE_128B
     const uint64_t bdesc0 = make_desc_base(8u * cb_bytes, p.layout_type);
     const uint32_t wblk_bytes = (uint32_t)p.N * cb_bytes;
     const uint32_t idesc = p.idesc;
@@ -429,11 +428,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
               // box row t / 3 (+ 2 per output row through SBO); kx = 0: odd pixel of pair 0, 1: even pixel of pair 1, 2: its odd pixel
-              const uint64_t ad = ablk_d + (uint64_t)(((uint32_t)(t / 3) * kPairCols * 2u * cb_bytes + (1u + (uint32_t)(t % 3)) * cb_bytes) >> 4);
+              const uint64_t ad = ablk_d + (uint64_t)(((t / 3) * kPairCols * 128 + 64 + (t % 3) * 64) >> 4);
 #pragma unroll
               for (int k = 0; k < KSTEPS; ++k) {
-                if (I8) umma_i8(d_tmem, ad + 2 * k, wd + 2 * k, idesc, accum);
-                else umma_bf16(d_tmem, ad + 2 * k, wd + 2 * k, idesc, accum);
+                umma_bf16(d_tmem, ad + 2 * k, wd + 2 * k, idesc, accum);
                 accum = 1;
               }
               wd += wblk_units;
@@ -692,8 +690,7 @@ int tc_prepare(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int i
   p.W = d.k == 1 ? iw : (iw + 2 * 1 - 3) / d.stride + 1;
   p.mode = d.k == 1 ? TC_FLAT : (d.stride == 1 ? TC_HALO : TC_PERTAP);
   // PAIRS needs a dense input (pitch == Cin: the two pixels of a pair are 128 contiguous bytes) and an even width
-  // (bf16 Cin = 32: 128-byte pair rows; int8 Cin = 32: 64-byte pair rows)
-  if (p.mode == TC_PERTAP && d.stride == 2 && (p.cb_bytes == 64 || p.cb_bytes == 32) && p.ncb == 1 && iw % 2 == 0 && in_pitch == d.cin &&
+  if (p.mode == TC_PERTAP && d.stride == 2 && !i8 && p.cb_bytes == 64 && p.ncb == 1 && iw % 2 == 0 && in_pitch == d.cin &&
       (reinterpret_cast<uintptr_t>(in_base) & 127) == 0 && mode_override < 0)
     p.mode = TC_PAIRS;
   if (mode_override >= 0 && d.k == 3) p.mode = mode_override;
@@ -712,9 +709,9 @@ int tc_prepare(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int i
     p.sbo_a = (uint32_t)p.halo_pitch * p.cb_bytes;
   } else if (p.mode == TC_PAIRS) {
     p.halo_pitch = kPairCols;
-    p.blk_bytes = (uint32_t)kPairRows * kPairCols * 2u * p.cb_bytes;
+    p.blk_bytes = (uint32_t)kPairRows * kPairCols * 128u;
     p.tx_bytes = p.blk_bytes;
-    p.sbo_a = 2u * kPairCols * 2u * p.cb_bytes;  // consecutive output rows are two box rows apart
+    p.sbo_a = 2u * kPairCols * 128u;  // consecutive output rows are two box rows apart
   } else {
     p.blk_bytes = 128u * p.cb_bytes;
     p.tx_bytes = p.blk_bytes;
@@ -732,7 +729,7 @@ int tc_prepare(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int i
   UYD_REQUIRE(!i8 || can_stage, UYD_E_UNSUPPORTED, "conv_tc int8: output rows must be a power-of-two number of 16-byte lanes");
   const size_t wres = (p.w_bytes + 1023u) & ~1023u;
   // as many epilogue groups as the staging tiles leave room for next to the resident weights and two stages
-  const size_t two_stages = 2 * (((size_t)(p.mode == TC_HALO ? (uint32_t)kHaloRows * p.halo_pitch * p.cb_bytes : (p.mode == TC_PAIRS ? (uint32_t)kPairRows * kPairCols * 2u * p.cb_bytes : 128u * p.cb_bytes)) + 1023u) & ~(size_t)1023);
+  const size_t two_stages = 2 * (((size_t)(p.mode == TC_HALO ? (uint32_t)kHaloRows * p.halo_pitch * p.cb_bytes : (p.mode == TC_PAIRS ? (uint32_t)kPairRows * kPairCols * 128u : 128u * p.cb_bytes)) + 1023u) & ~(size_t)1023);
   p.ngroups = kEpiGroups;
   while (p.ngroups > 1 && p.stage_pitch && wres + two_stages + kTailFixed + (size_t)128 * p.ngroups * p.stage_pitch > 227 * 1024 - 1024)
     p.ngroups >>= 1;
@@ -792,7 +789,7 @@ int tc_prepare(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int i
     const cuuint64_t dims[4] = {(cuuint64_t)2 * d.cin, (cuuint64_t)(iw / 2), (cuuint64_t)ih, (cuuint64_t)max_batch};
     const cuuint64_t str[3] = {(cuuint64_t)2 * in_pitch * es, (cuuint64_t)iw * in_pitch * es, (cuuint64_t)ih * iw * in_pitch * es};
     const cuuint32_t box[4] = {(cuuint32_t)2 * CB, (cuuint32_t)kPairCols, (cuuint32_t)kPairRows, 1};
-    int e = encode(&tc->tm_in, in_base, 4, dims, str, box, one4, 2 * p.cb_bytes, i8);
+    int e = encode(&tc->tm_in, in_base, 4, dims, str, box, one4, 128, i8);
     if (e) return e;
   } else {
     const cuuint64_t dims[4] = {(cuuint64_t)d.cin, (cuuint64_t)iw, (cuuint64_t)ih, (cuuint64_t)max_batch};
