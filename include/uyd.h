@@ -274,6 +274,19 @@ int uyd_nms_detections(uyd_ctx *ctx, const uyd_detection *dets, const int *cell_
                        size_t workspace_bytes, uyd_detection *out, int *d_out_count,
                        uyd_stream stream);
 
+/* In-place form with the semantics run_gpu_nms leaves behind (gpu_postprocess.h:70-71, gpu_postprocess.cu:366-387):
+ * the first n (<= 1024, host-side count as in the reference signature) records of `dets` are rewritten in
+ * confidence-descending order (ties: cell_idx, or slot when NULL) with valid = 1 for survivors of the exact greedy
+ * NMS and 0 for suppressed records; records that arrive with valid == 0 neither suppress nor survive.
+ * d_out_count (device, may be NULL) receives the number of survivors. */
+int uyd_nms_detections_inplace(uyd_ctx *ctx, uyd_detection *dets, const int *cell_idx, int n, float iou_thr,
+                               int *d_out_count, uyd_stream stream);
+
+/* Ordered compaction of the valid records among the first n (<= 1024) into `out` + their number (device):
+ * the cub::DeviceSelect::If of copy_valid_detections_to_host (gpu_postprocess.cu:412-416). */
+int uyd_compact_valid(uyd_ctx *ctx, const uyd_detection *dets, int n, uyd_detection *out, int *d_out_count,
+                      uyd_stream stream);
+
 /* max |x| over the first `batch` images of a bf16 slice, as the bit pattern of a non-negative float OR-ed into
  * *d_bits with atomicMax (caller zeroes it): max calibration of the static input scales (qat.py:129-220). */
 int uyd_plan_slice_absmax(uyd_plan *plan, int buf, int coff, int c, int batch, unsigned int *d_bits, uyd_stream stream);

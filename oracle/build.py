@@ -59,7 +59,27 @@ def build_ref_preprocess(force: bool = False):
     return REF_PRE_SO if REF_PRE_SO.exists() else None
 
 
+COMPAT_TEST_SRC = HERE.parent / "tests" / "compat" / "node_sequence.cpp"
+COMPAT_TEST_BIN = HERE / "_ref" / "compat_node_test"
+
+
+def build_compat_test(force: bool = False):
+    """tests/compat/node_sequence.cpp compiled against the REFERENCE's headers (where they lie) and linked with
+    unina-yolo-dla_b200/libuyd_compat.so; a prebuilt binary on the GPU box.  None when the mount is missing and
+    no prebuilt binary exists."""
+    pkg = HERE.parent / "unina-yolo-dla_b200"
+    lib = pkg / "libuyd_compat.so"
+    if REF_INC.exists() and lib.exists() and (force or _stale(COMPAT_TEST_BIN, [COMPAT_TEST_SRC, lib, HERE.parent / "include" / "uyd_compat.h"])):
+        COMPAT_TEST_BIN.parent.mkdir(exist_ok=True)
+        subprocess.check_call(
+            ["/usr/local/cuda/bin/nvcc", "-O2", "-std=c++17", "-Xcompiler", "-ffp-contract=off", f"-I{REF_INC}", f"-I{HERE.parent / 'include'}",
+             str(COMPAT_TEST_SRC), "-o", str(COMPAT_TEST_BIN), f"-L{pkg}", "-luyd_compat", "-luyd", "-ldl",
+             "-Xlinker", "-rpath=$ORIGIN/../../unina-yolo-dla_b200", "-cudart", "static"])
+    return COMPAT_TEST_BIN if COMPAT_TEST_BIN.exists() else None
+
+
 if __name__ == "__main__":
     print(build_ref_preprocess(True))
     print(build_oracle(True))
     print(build_ref(True))
+    print(build_compat_test(True))

@@ -72,8 +72,8 @@ static float hpp_iou(const uydo_det *a, const uydo_det *b) { /* postprocess.hpp:
 /* decode_head (postprocess.hpp:94-145): CHW fp32 logits, sigmoid-argmax (strict >, first
  * max wins, max_conf starts at 0), keep iff conf > thr, TLBR * stride around the cell
  * centre, optional dilation by q*w, q*h.  Row-major cell order.  Returns count. */
-int uydo_decode_tlbr(const float *cls, const float *reg, int w, int h, int stride, int nc,
-                     float thr, float q, uydo_det *out, int cap) {
+int uydo_decode_tlbr_cells(const float *cls, const float *reg, int w, int h, int stride, int nc,
+                           float thr, float q, uydo_det *out, int *cells, int cap) {
   int n = 0, hw = w * h;
   for (int y = 0; y < h; ++y)
     for (int x = 0; x < w; ++x) {
@@ -95,11 +95,16 @@ int uydo_decode_tlbr(const float *cls, const float *reg, int w, int h, int strid
           float dw = (d.x2 - d.x1) * q, dh = (d.y2 - d.y1) * q;
           d.x1 -= dw; d.y1 -= dh; d.x2 += dw; d.y2 += dh;
         }
-        if (n < cap) out[n] = d;
+        if (n < cap) { out[n] = d; if (cells) cells[n] = g; }
         ++n;
       }
     }
   return n;
+}
+
+int uydo_decode_tlbr(const float *cls, const float *reg, int w, int h, int stride, int nc,
+                     float thr, float q, uydo_det *out, int cap) {
+  return uydo_decode_tlbr_cells(cls, reg, w, h, stride, nc, thr, q, out, 0, cap);
 }
 
 /* nms (postprocess.hpp:44-67) on detections ALREADY sorted by confidence descending

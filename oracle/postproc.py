@@ -112,12 +112,17 @@ def non_max_suppression(pred: np.ndarray, conf_thres=0.25, iou_thres=0.45, max_d
 
 
 def decode_tlbr(cls: np.ndarray, reg: np.ndarray, stride: int, conf_thr: float, q: float = 0.0,
-                use_ref: bool = False) -> np.ndarray:
+                use_ref: bool = False, return_cells: bool = False):
     """postprocess.hpp:94-145 on one level.  cls [nc,H,W], reg [4,H,W] fp32 -> DET_DTYPE[n]."""
     cls = np.ascontiguousarray(cls, np.float32)
     reg = np.ascontiguousarray(reg, np.float32)
     nc, h, w = cls.shape
     out = np.zeros(h * w, dtype=DET_DTYPE)
+    if return_cells:  # + the row-major grid cell of every detection (the restatement only)
+        cells = np.zeros(h * w, dtype=np.int32)
+        n = lib().uydo_decode_tlbr_cells(_fp(cls), _fp(reg), ctypes.c_int(w), ctypes.c_int(h), ctypes.c_int(stride), ctypes.c_int(nc),
+                                         ctypes.c_float(conf_thr), ctypes.c_float(q), _fp(out), _fp(cells), ctypes.c_int(h * w))
+        return out[:n].copy(), cells[:n].copy()
     L = ref_lib() if use_ref else lib()
     fn = L.ref_decode_head if use_ref else L.uydo_decode_tlbr
     n = fn(_fp(cls), _fp(reg), ctypes.c_int(w), ctypes.c_int(h), ctypes.c_int(stride), ctypes.c_int(nc),

@@ -359,6 +359,16 @@ def test_predict_stream_equals_predict_batched(T):
     dev = [(d.cpu(), c.cpu()) for d, c in m.predict_stream(iter(batches[:1]), to_host=False)]
     assert torch.equal(dev[0][0], want[0][0]) and torch.equal(dev[0][1], want[0][1])
     assert list(m.predict_stream(iter([]))) == []
+    # a consumer may hold result k while it handles k + 1 and k + 2 (tracking, frame differencing): no clone here
+    six = [batches[i % 3] for i in range(6)]
+    held = []
+    for k, (d, c) in enumerate(m.predict_stream(iter(six))):
+        held.append((d, c))
+        for back in (1, 2):
+            if k - back >= 0:
+                hd, hc = held[k - back]
+                wd, wc = want[(k - back) % 3]
+                assert torch.equal(hc, wc) and torch.equal(hd, wd), f"result {k - back} was overwritten by step {k}"
 
 
 CHAIN_CASES = [

@@ -102,6 +102,8 @@ SIGNATURES = {
     "uyd_nms_detections_workspace_bytes": (C.c_size_t, [C.c_int]),
     "uyd_nms_detections": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p,
                                      C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "uyd_nms_detections_inplace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
+    "uyd_compact_valid": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "uyd_norm_params_imagenet": (NormParams, []),
     "uyd_norm_params_unit": (NormParams, []),
     "uyd_preprocess_bgra_resize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, NormParams, C.c_void_p]),

@@ -2,6 +2,9 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <memory>
+#include <mutex>
+#include <set>
+#include <utility>
 
 #include "common.cuh"
 
@@ -15,6 +18,40 @@ void set_error(const char *fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+// Registry behind smem_optin (common.cuh): the attribute is per (kernel, device).
+int smem_optin_impl(const void *kernel, int bytes) {
+  static std::mutex mu;
+  static std::set<std::pair<const void *, int>> done;
+  int dev = 0;
+  UYD_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  if (done.count({kernel, dev})) return UYD_OK;
+  UYD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done.insert({kernel, dev});
+  return UYD_OK;
+}
+
+int current_sm_count() {
+  static int sms[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+  return sms[dev];
+}
+
+// Makes `device` current for the lifetime of the guard and restores the caller's device afterwards: no entry
+// point changes the caller's (or torch's) current device.
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int device) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != device) err = cudaSetDevice(device);
+    else if (err == cudaSuccess) prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 // conv_tc.cu
 struct TcConv;
@@ -159,7 +196,6 @@ extern "C" int uyd_create(int device, uyd_ctx **out) {
   UYD_CUDA(cudaGetDeviceProperties(&prop, device));
   UYD_REQUIRE(prop.major == 10, UYD_E_NOGPU, "uyd_create: device %d is sm_%d%d; this library is sm_100a only", device,
               prop.major, prop.minor);
-  UYD_CUDA(cudaSetDevice(device));
   uyd_ctx *c = new uyd_ctx();
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
@@ -185,7 +221,7 @@ extern "C" int uyd_plan_create(uyd_ctx *ctx, int max_batch, uyd_plan **out) {
 
 extern "C" int uyd_plan_destroy(uyd_plan *plan) {
   if (!plan) return UYD_OK;
-  cudaSetDevice(plan->ctx->device);
+  uyd::DeviceGuard guard(plan->ctx->device);
   for (Op &o : plan->ops) {
     if (o.w_dev) cudaFree(o.w_dev);
     if (o.b_dev) cudaFree(o.b_dev);
@@ -231,7 +267,8 @@ extern "C" int uyd_plan_add_conv(uyd_plan *plan, const uyd_conv *d, const float 
   int ih, iw, in_pitch = 0;
   if (d->in_buf < 0) {
     UYD_REQUIRE(plan->ops.empty(), UYD_E_ARG, "only the first op may read the network input");
-    const Buffer &ob = plan->bufs.at(d->out_buf);
+    if ((e = check_slice(plan, d->out_buf, d->out_coff, d->cout, "conv output"))) return e;
+    const Buffer &ob = plan->bufs[d->out_buf];
     ih = ob.h * d->stride; iw = ob.w * d->stride;
     plan->in_c = d->cin; plan->in_h = ih; plan->in_w = iw;
   } else {
@@ -548,7 +585,9 @@ static void *slice_ptr(const uyd_plan *p, int buf, int coff) {
 
 extern "C" int uyd_plan_finalize(uyd_plan *plan) {
   UYD_REQUIRE(plan && !plan->finalized, UYD_E_STATE, "plan missing or already finalized");
-  UYD_CUDA(cudaSetDevice(plan->ctx->device));
+  UYD_REQUIRE(!plan->arena, UYD_E_STATE, "uyd_plan_finalize failed before on this plan: destroy it (uyd_plan_destroy frees the partial allocations)");
+  uyd::DeviceGuard guard(plan->ctx->device);
+  UYD_CUDA(guard.err);
   size_t total = 0;
   std::vector<size_t> offs;
   for (Buffer &b : plan->bufs) {
@@ -735,6 +774,8 @@ static int launch_op(uyd_plan *plan, const Op &o, const void *x, int x_kind, int
 static int run_ops(uyd_plan *plan, const void *x, int x_kind, int batch, uyd_stream stream, float *y = nullptr) {
   UYD_REQUIRE(plan && plan->finalized, UYD_E_STATE, "plan not finalized");
   UYD_REQUIRE(batch > 0 && batch <= plan->max_batch, UYD_E_ARG, "batch %d outside (0, %d]", batch, plan->max_batch);
+  uyd::DeviceGuard guard(plan->ctx->device);  // the stream must belong to the plan's device
+  UYD_CUDA(guard.err);
   cudaStream_t s = (cudaStream_t)stream;
   for (size_t i = 0; i < plan->ops.size(); ++i) {
     const bool timed = (int)i == plan->timed_op && plan->timed_used < (int)plan->timed_ev.size() / 2;
@@ -767,7 +808,14 @@ extern "C" int uyd_plan_profile(uyd_plan *plan, const float *x, int batch, uyd_s
   UYD_REQUIRE(batch > 0 && batch <= plan->max_batch, UYD_E_ARG, "batch %d outside (0, %d]", batch, plan->max_batch);
   cudaStream_t s = (cudaStream_t)stream;
   const size_t n = plan->ops.size();
-  std::vector<cudaEvent_t> ev(n + 1);
+  uyd::DeviceGuard guard(plan->ctx->device);
+  UYD_CUDA(guard.err);
+  struct Events {  // destroyed on every return path
+    std::vector<cudaEvent_t> ev;
+    ~Events() { for (cudaEvent_t e : ev) if (e) cudaEventDestroy(e); }
+  } E;
+  E.ev.assign(n + 1, nullptr);
+  auto &ev = E.ev;
   for (auto &e : ev) UYD_CUDA(cudaEventCreate(&e));
   UYD_CUDA(cudaEventRecord(ev[0], s));
   for (size_t i = 0; i < n; ++i) {
@@ -777,7 +825,6 @@ extern "C" int uyd_plan_profile(uyd_plan *plan, const float *x, int batch, uyd_s
   }
   UYD_CUDA(cudaStreamSynchronize(s));
   for (size_t i = 0; i < n; ++i) UYD_CUDA(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
-  for (auto &e : ev) cudaEventDestroy(e);
   return UYD_OK;
 }
 

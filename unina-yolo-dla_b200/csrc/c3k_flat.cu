@@ -237,12 +237,8 @@ void c3k_flat_pack(int c, const float *const w[7], std::vector<uint32_t> &frags)
 int c3k_flat_launch(int c, const C3kArgs &a, cudaStream_t s) {
   const size_t smem = c3k_flat_smem_bytes(c / 2, a.th);
   const unsigned grid = (unsigned)(a.n * a.tiles_x * a.tiles_y);
-  static bool attr[3] = {false, false, false};
-  auto go = [&](auto kern, int idx, int threads) -> int {
-    if (!attr[idx]) {
-      UYD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      attr[idx] = true;
-    }
+  auto go = [&](auto kern, int, int threads) -> int {
+    if (int e = smem_optin(kern, 227 * 1024)) return e;
     kern<<<grid, threads, smem, s>>>(a);
     return (int)cudaGetLastError();
   };

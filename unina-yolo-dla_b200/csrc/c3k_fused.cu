@@ -573,12 +573,11 @@ int cls_branch_launch(int cin, const ClsArgs &a0, cudaStream_t s) {
   const int cw = cin > 32 ? cin : 32;
   const size_t smem = (size_t)(kClsTH + 5) * kPW * cw * 2 * 2;
   const unsigned grid = (unsigned)(a.n * a.tiles_x * a.tiles_y);
-  static bool attr[2] = {false, false};
   if (cin == 32) {
-    if (!attr[0]) { UYD_CUDA(cudaFuncSetAttribute(cls_branch_fused_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr[0] = true; }
+    if (int e = smem_optin(cls_branch_fused_kernel<32>, 200 * 1024)) return e;
     cls_branch_fused_kernel<32><<<grid, kClsThreads, smem, s>>>(a);
   } else {
-    if (!attr[1]) { UYD_CUDA(cudaFuncSetAttribute(cls_branch_fused_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr[1] = true; }
+    if (int e = smem_optin(cls_branch_fused_kernel<64>, 200 * 1024)) return e;
     cls_branch_fused_kernel<64><<<grid, kClsThreads, smem, s>>>(a);
   }
   return (int)cudaGetLastError();
@@ -617,12 +616,8 @@ int c3k_launch(int c, const C3kArgs &a0, cudaStream_t s) {
   }
   const size_t smem = c3k_smem_bytes(c / 2, a.th);
   const unsigned grid = (unsigned)(a.n * a.tiles_x * a.tiles_y);
-  static bool attr[3] = {false, false, false};
-  auto setup = [&](auto kern, int idx) -> int {
-    if (!attr[idx]) {
-      UYD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-      attr[idx] = true;
-    }
+  auto setup = [&](auto kern, int) -> int {
+    if (int e = smem_optin(kern, 220 * 1024)) return e;
     kern<<<grid, kThreadsC3k, smem, s>>>(a);   // plain launch: measured, a PDL launch of this kernel gains nothing at batch 64
     return (int)cudaGetLastError();             // and costs 20 us of batch-1 latency (early CTAs squat on the SMs)
   };

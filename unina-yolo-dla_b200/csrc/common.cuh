@@ -36,6 +36,13 @@ void set_error(const char *fmt, ...);
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Opt-in to > 48 KB of dynamic shared memory, once per (kernel, device): cudaFuncSetAttribute applies to the
+// CURRENT device only, so a process that drives several GPUs needs it on each of them (api.cu).
+int smem_optin_impl(const void *kernel, int bytes);
+template <class K>
+inline int smem_optin(K *kernel, size_t bytes) { return smem_optin_impl(reinterpret_cast<const void *>(kernel), (int)bytes); }
+int current_sm_count();  // SM count of the current device (cached per device)
+
 #ifdef __CUDACC__
 // Lets a successor launched with programmatic stream serialization (the tcgen05 kernels, tc_ptx.cuh) start its
 // prologue while this kernel is still running; the successor still waits for this kernel's completion before

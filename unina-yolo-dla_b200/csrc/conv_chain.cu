@@ -574,14 +574,10 @@ int chain_prepare(ChainConv *cc, int cin, int n1, int n2, void *in_base, int in_
     int e = chain_encode(&cc->tm_in, in_base, 4, dims, str, box, p.cb_bytes);
     if (e) return e;
   }
-  static bool attr = false;
-  if (!attr) {
-    UYD_CUDA(cudaFuncSetAttribute(conv_chain_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    UYD_CUDA(cudaFuncSetAttribute(conv_chain_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    UYD_CUDA(cudaFuncSetAttribute(conv_chain_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    UYD_CUDA(cudaFuncSetAttribute(conv_chain_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
-  }
+  if (int e = smem_optin(conv_chain_kernel<2, 2>, 227 * 1024)) return e;
+  if (int e = smem_optin(conv_chain_kernel<2, 4>, 227 * 1024)) return e;
+  if (int e = smem_optin(conv_chain_kernel<4, 2>, 227 * 1024)) return e;
+  if (int e = smem_optin(conv_chain_kernel<4, 4>, 227 * 1024)) return e;
   return UYD_OK;
 }
 
@@ -595,6 +591,7 @@ int chain_launch(const ChainConv *cc, int nb, float *y, int sm_count, cudaStream
   UYD_REQUIRE(p.total_tiles < (1ll << 31), UYD_E_UNSUPPORTED, "conv_chain: %lld tiles exceed the kernel's 32-bit tile index", p.total_tiles);
   const unsigned grid = (unsigned)(p.total_tiles < sm_count ? p.total_tiles : sm_count);
   const int ks1 = p.cb_bytes / 32, ks2 = p.N1 * 2 / 32;
+#ifdef UYD_CHAIN_TIMELINE_BUILD  // debug build only (tools/chain_timeline.py): never in the shipped library path
   static long long *dbg_dev = nullptr;
   const bool timeline = getenv("UYD_CHAIN_TIMELINE") && p.total_tiles >= 64ll * grid;
   if (timeline) {
@@ -602,12 +599,14 @@ int chain_launch(const ChainConv *cc, int nb, float *y, int sm_count, cudaStream
     cudaMemsetAsync(dbg_dev, 0, 2 * 64 * 8 * sizeof(long long), s);
     p.dbg = dbg_dev;
   }
+#endif
 #define UYD_CHAIN_LAUNCH(A, B) UYD_CUDA(launch_pdl(conv_chain_kernel<A, B>, dim3(grid), dim3(kChainThreads), cc->smem, s, cc->tm_in, cc->tm_w1, cc->tm_w2, p))
   if (ks1 == 2 && ks2 == 2) UYD_CHAIN_LAUNCH(2, 2);
   else if (ks1 == 2 && ks2 == 4) UYD_CHAIN_LAUNCH(2, 4);
   else if (ks1 == 4 && ks2 == 2) UYD_CHAIN_LAUNCH(4, 2);
   else UYD_CHAIN_LAUNCH(4, 4);
 #undef UYD_CHAIN_LAUNCH
+#ifdef UYD_CHAIN_TIMELINE_BUILD
   if (timeline) {  // debug only: dump the stamps of CTA 0 (cycles relative to its first TMA issue)
     long long h[2 * 64 * 8];
     cudaStreamSynchronize(s);
@@ -621,6 +620,7 @@ int chain_launch(const ChainConv *cc, int nb, float *y, int sm_count, cudaStream
       fprintf(stderr, "\n");
     }
   }
+#endif
   return (int)cudaGetLastError();
 }
 

@@ -806,16 +806,12 @@ int tc_prepare(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int i
       if (e) return e;
     }
   }
-  static bool attr = false;
-  if (!attr) {
-    UYD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    UYD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    UYD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    UYD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    UYD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    UYD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
-  }
+  if (int e = smem_optin(conv_tc_kernel<false, 1>, 227 * 1024)) return e;
+  if (int e = smem_optin(conv_tc_kernel<false, 2>, 227 * 1024)) return e;
+  if (int e = smem_optin(conv_tc_kernel<false, 4>, 227 * 1024)) return e;
+  if (int e = smem_optin(conv_tc_kernel<true, 1>, 227 * 1024)) return e;
+  if (int e = smem_optin(conv_tc_kernel<true, 2>, 227 * 1024)) return e;
+  if (int e = smem_optin(conv_tc_kernel<true, 4>, 227 * 1024)) return e;
   return UYD_OK;
 }
 

@@ -11,6 +11,9 @@ namespace {
 constexpr int kThreads = 256;
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// The reference's device sigmoid, statement for statement (gpu_postprocess.cu:62-64): full-accuracy expf and an IEEE
+// division, so the TLBR confidences are bit-identical to what decode_yolo_head_kernel produces on the same GPU.
+__device__ __forceinline__ float sigmoid_ref(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
 
 // head: [batch, H, W, 4*16 + nc] fp32.  y: [batch, 4+nc, a_total].
 template <int REG_MAX>
@@ -91,7 +94,7 @@ __global__ void __launch_bounds__(kThreads) decode_tlbr_kernel(const float *__re
   int best = -1;
   if (g < hw) {
     for (int c = 0; c < nc; ++c) {
-      const float pr = sigmoidf_(cls[(long long)c * hw + g]);
+      const float pr = sigmoid_ref(cls[(long long)c * hw + g]);
       if (pr > mc) { mc = pr; best = c; }
     }
     has = strict ? (mc > thr) : (mc >= thr);

@@ -156,14 +156,14 @@ int sppf_pool_launch(__nv_bfloat16 *base, int n, int h, int w, int pitch, int c,
   const int gp = (c / 8) % 2 == 0 ? 2 : 1;
   const size_t plane = (size_t)2 * h * w * gp * sizeof(uint4);
   if (!rows_only && plane <= 110 * 1024) {  // two CTAs per SM
-    static bool attr = false;
-    if (!attr) { UYD_CUDA(cudaFuncSetAttribute(sppf_plane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); attr = true; }
+    if (int e = smem_optin(sppf_plane_kernel, 110 * 1024)) return e;
     sppf_plane_kernel<<<n * ((c / 8) / gp), kPlaneThreads, plane, s>>>(base, h, w, pitch, c, gp);
     return (int)cudaGetLastError();
   }
   const size_t smem = (size_t)3 * w * (c / 8) * sizeof(uint4);
   UYD_REQUIRE(smem <= 200 * 1024, UYD_E_UNSUPPORTED, "sppf row does not fit shared memory");
-  if (smem > 48 * 1024) cudaFuncSetAttribute(sppf_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (smem > 48 * 1024)
+    if (int e = smem_optin(sppf_pool_kernel, 200 * 1024)) return e;
   sppf_pool_kernel<<<n * h, kThreads, smem, s>>>(base, h, w, pitch, c);
   return (int)cudaGetLastError();
 }

@@ -506,16 +506,12 @@ static int stem_v2_launch(const StemArgs &a0, cudaStream_t s) {
   StemArgs a = a0;
   a.wfrag += (6 + 36) * 64;  // skip the legacy fragments
   static const bool persist = [] { const char *v = getenv("UYD_STEM_PERSIST"); return !(v && *v == '0'); }();
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    UYD_CUDA(cudaGetDevice(&dev));
-    UYD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int sms = current_sm_count();
+  UYD_REQUIRE(sms > 0, UYD_E_NOGPU, "stem: no current CUDA device");
   const int tiles = ceil_div(a.ow, stemv2::kTW) * ceil_div(a.oh, stemv2::kTH) * a.n;
   const size_t smem = stemv2::kSmemBytes;
   auto go = [&](auto kern, bool pers) -> int {
-    UYD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, stemv2::kSmemBytes));
+    if (int e = smem_optin(kern, stemv2::kSmemBytes)) return e;
     if (pers) kern<<<tiles < 2 * sms ? tiles : 2 * sms, stemv2::kThreads, smem, s>>>(a);
     else kern<<<dim3(ceil_div(a.ow, stemv2::kTW), ceil_div(a.oh, stemv2::kTH), a.n), stemv2::kThreads, smem, s>>>(a);
     return (int)cudaGetLastError();
@@ -535,12 +531,8 @@ int stem_fused_launch(const StemArgs &a, cudaStream_t s) {
   static const bool legacy = [] { const char *v = getenv("UYD_STEM_LEGACY"); return v && *v == '1'; }();
   if (!legacy || a.pw) return stem_v2_launch(a, s);
   const size_t smem = (size_t)2 * 3 * kInH * kInW * 2 + (size_t)(kL0Px + 19) * kL0Pitch * 2 + (6 + 36) * 64 * 4 + 48 * 4;
-  static bool attr = false;
-  if (!attr) {
-    UYD_CUDA(cudaFuncSetAttribute(stem_fused_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    UYD_CUDA(cudaFuncSetAttribute(stem_fused_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
+  if (int e = smem_optin(stem_fused_kernel<float>, smem)) return e;
+  if (int e = smem_optin(stem_fused_kernel<uint8_t>, smem)) return e;
   dim3 grid(ceil_div(a.ow, kTW), ceil_div(a.oh, kTH), a.n);
   if (a.u8) stem_fused_kernel<uint8_t><<<grid, kThreads, smem, s>>>(a);
   else stem_fused_kernel<float><<<grid, kThreads, smem, s>>>(a);

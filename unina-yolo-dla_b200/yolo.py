@@ -803,7 +803,8 @@ class UninaYoloB200(nn.Module):
         pinned).  Batch i+1 is copied host->device on a copy stream while batch i computes, so a
         steady-state step costs max(copy, compute) instead of their sum.  Yields, in order,
         ``(det[B,max_det,6], count[B])`` -- pinned host tensors (``to_host``) or device tensors;
-        either is valid until the generator is advanced twice more (two slots are recycled)."""
+        either stays valid while the generator is advanced twice more (the pinned result buffers rotate
+        through a ring of four, separate from the two input staging slots)."""
         if not torch.cuda.is_available():
             raise _lib.UydError("no CUDA device: the B200 path has no CPU fallback")
         prm = next(self.parameters())
@@ -828,15 +829,23 @@ class UninaYoloB200(nn.Module):
             for _ in range(2):
                 s = Slot()
                 s.x = torch.empty(first.shape, dtype=first.dtype if first.dtype == torch.uint8 else torch.float32, device=device)
-                s.ready, s.free, s.out = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
-                s.det = s.cnt = s.det_h = s.cnt_h = None
-                s.n = s.n_in = 0
-                if to_host:
-                    s.det_h = torch.empty(Bmax, max_det, 6, dtype=torch.float32).pin_memory()
-                    s.cnt_h = torch.empty(Bmax, dtype=torch.int32).pin_memory()
+                s.ready, s.free = torch.cuda.Event(), torch.cuda.Event()
+                s.n_in = 0
                 slots.append(s)
-            state = self._stream_state[skey] = (torch.cuda.Stream(device=device), slots)
-        copy_s, slots = state
+            # result ring: step i writes entry i % 4 and the result of step k is handed out during step k + 1, so the
+            # entry is next written by step k + 4 -- after the consumer advanced the generator three more times
+            outs = []
+            for _ in range(4):
+                r = Slot()
+                r.out = torch.cuda.Event()
+                r.det = r.cnt = r.det_h = r.cnt_h = None
+                r.n = 0
+                if to_host:
+                    r.det_h = torch.empty(Bmax, max_det, 6, dtype=torch.float32).pin_memory()
+                    r.cnt_h = torch.empty(Bmax, dtype=torch.int32).pin_memory()
+                outs.append(r)
+            state = self._stream_state[skey] = (torch.cuda.Stream(device=device), slots, outs)
+        copy_s, slots, outs = state
         copy_s.wait_stream(main_s)   # a previous generator's last step may still read the slots
         for s in slots:
             s.free.record(main_s)
@@ -844,7 +853,7 @@ class UninaYoloB200(nn.Module):
         def stage(s, xb):
             if xb.shape[0] > Bmax or xb.shape[1:] != first.shape[1:]:
                 raise ValueError("predict_stream: later batches must not exceed the first batch's shape")
-            s.n_in = xb.shape[0]  # (s.n belongs to the result still pending in this slot)
+            s.n_in = xb.shape[0]
             with torch.cuda.stream(copy_s):
                 copy_s.wait_event(s.free)  # the step that last read this slot has finished
                 s.x[: s.n_in].copy_(xb, non_blocking=True)
@@ -860,17 +869,18 @@ class UninaYoloB200(nn.Module):
                 nxt = None
             if nxt is not None:
                 stage(slots[(i + 1) % 2], nxt)
+            r = outs[i % 4]
             main_s.wait_event(s.ready)
-            s.n = s.n_in
-            s.det, s.cnt = self.predict_batched(s.x[: s.n], conf, iou, max_det, max_nms)
+            r.n = s.n_in
+            r.det, r.cnt = self.predict_batched(s.x[: r.n], conf, iou, max_det, max_nms)
             s.free.record(main_s)
             if to_host:
-                s.det_h[: s.n].copy_(s.det, non_blocking=True)
-                s.cnt_h[: s.n].copy_(s.cnt, non_blocking=True)
-            s.out.record(main_s)
+                r.det_h[: r.n].copy_(r.det, non_blocking=True)
+                r.cnt_h[: r.n].copy_(r.cnt, non_blocking=True)
+            r.out.record(main_s)
             if pending is not None:
                 yield self._stream_result(pending, to_host)
-            pending = s
+            pending = r
             i += 1
             if nxt is None:
                 break
