@@ -38,7 +38,15 @@ def _worker(rank, world, port, total, out_path):
     y = T.synth_predictions(total, 4, 2100, seed=3, frac_conf=0.3)
     b, e = shard_bounds(total, world, rank)
     det, cnt = _pack(pp.non_max_suppression(y[b:e], 0.25, 0.7, 300))
-    gd, gc = gather_detections(det, cnt)
+    gd, gc = gather_detections(det, cnt, total=total)   # ragged shards: sizes follow shard_bounds, nothing is exchanged
+    # the handle form used by bench.py: start now, consume later; a second exchange may start before the first is read
+    from unina_yolo_dla_b200.dp import DetectionGather
+    G = DetectionGather()
+    h1 = G.start(det, cnt, total)
+    h2 = G.start(det.flip(0), cnt.flip(0), total)
+    d1, c1 = h1.wait()
+    d2, c2 = h2.wait()
+    assert torch.equal(d1, gd) and torch.equal(c1, gc) and c2.shape == gc.shape and not torch.equal(d2, d1)
     if rank == 0:
         torch.save((gd, gc), out_path)
     dist.destroy_process_group()
