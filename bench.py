@@ -50,11 +50,17 @@ def parse():
     ap.add_argument("--size", type=int, default=640)
     ap.add_argument("--cpu-sample", type=int, default=32, help="frames of the bounded CPU sample")
     ap.add_argument("--profile-out", default="", help="write the per-op table (markdown) here")
-    ap.add_argument("--stress", type=int, default=0, metavar="BATCH",
-                    help="also time decode-free NMS on a synthetic dense 1280x1280 scene (134 400 anchors, ~100k candidates per "
-                         "image, BASELINE config 5) at this batch, e.g. 32")
-    ap.add_argument("--int8", type=int, default=0, metavar="BATCH",
-                    help="also time the INT8 graph (static max-calibrated scales, BASELINE config 3) at this batch, e.g. 256")
+    ap.add_argument("--stress", type=int, default=32, metavar="BATCH",
+                    help="N = 1: also time decode-free NMS on a synthetic dense 1280x1280 scene (134 400 anchors, ~100k candidates "
+                         "per image, BASELINE config 5) at this batch (0 = skip)")
+    ap.add_argument("--int8", type=int, default=256, metavar="BATCH",
+                    help="N = 1: also time the INT8 graph (static max-calibrated scales, BASELINE config 3) at this batch (0 = skip)")
+    ap.add_argument("--custom", type=int, default=64, metavar="BATCH",
+                    help="N = 1: also time the model.py variant (UninaCustomB200, the pinned-oracle network) at this batch (0 = skip)")
+    ap.add_argument("--c4-batch", type=int, default=256, metavar="BATCH",
+                    help="every N: also time BASELINE config 4's per-GPU batch (resident and e2e), 0 = skip")
+    ap.add_argument("--sustain", type=float, default=2.0, metavar="SECONDS",
+                    help="also run the resident step back to back for at least this long, with clocks (0 = skip)")
     return ap.parse_args()
 
 
@@ -62,8 +68,9 @@ def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
         d = json.loads(p.read_text())
-        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
-    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "src": "fallback"}
+        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "tflops_burst": d["bf16_tflops"],
+                "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "tflops_burst": 1600.0, "src": "fallback"}
 
 
 class ClockSampler(threading.Thread):
@@ -191,6 +198,100 @@ def bench_nms_stress(model, batch: int, dev, steps: int):
             "kept_per_image": float(cnt.float().mean()), "steps": steps}
 
 
+FAMILIES = (("stem", "stem"), ("c3k", "c3k"), ("chain", "chain"), ("conv_tc", " tc"), ("sppf", "sppf"))
+
+
+def family_of(text: str) -> str:
+    for name, key in FAMILIES:
+        if key in text:
+            return name
+    return "other"
+
+
+def family_table(plan, ms, batch, pk, nms_ms=None):
+    """Per-kernel-family share of the step and both roofline fractions (algorithmic flops / bytes of the ops in the
+    family over the family's summed CUDA-event time)."""
+    fam = {}
+    for i, t in enumerate(ms):
+        text, fl, by = plan.op_info(i)
+        f = fam.setdefault(family_of(text), {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+        f["launches"] += 1; f["ms"] += t; f["flops"] += fl * batch; f["bytes"] += by * batch
+    total = sum(ms) + (nms_ms or 0.0)
+    out = {}
+    for name, f in fam.items():
+        tf, gb = f["flops"] / (f["ms"] * 1e-3) / 1e12, f["bytes"] / (f["ms"] * 1e-3) / 1e9
+        out[name] = {"launches": f["launches"], "ms": f["ms"], "share": f["ms"] / total, "tflops": tf, "frac_tensor": tf / pk["tflops_burst"],
+                     "gbs": gb, "frac_hbm": gb / pk["hbm_gbs"]}
+    if nms_ms:
+        out["nms"] = {"launches": 1, "ms": nms_ms, "share": nms_ms / total}
+    return out
+
+
+def bench_custom(batch: int, size: int, dev, steps: int, pk, profile_out: str = ""):
+    """The model.py variant (UninaCustomB200, base_channels 32: 35.7 GFLOP per 640x640 frame, every 3x3 conv with
+    C >= 32): conv stack at `batch` resident frames + one-frame predict (forward + TLBR decode + postprocess.hpp NMS)."""
+    import unina_yolo_dla_b200 as uyd
+
+    m = uyd.UninaCustomB200(4, 32).init_synthetic(seed=0).to(dev)
+    g = torch.Generator(device=dev).manual_seed(700)
+    x = torch.rand(batch, 3, size, size, device=dev, generator=g)
+    plan = m.plan_for(x)
+    for _ in range(3):
+        plan.run(x)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        plan.run(x)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_step = e0.elapsed_time(e1) / steps
+    ms = plan.profile(x, None)
+    flops = sum(plan.op_info(i)[1] for i in range(plan.launches))
+    x1 = x[:1].contiguous()
+    for _ in range(3):
+        m.predict(x1, conf=0.5, iou=0.45)
+    lat = []
+    for _ in range(20):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        m.predict(x1, conf=0.5, iou=0.45)
+        torch.cuda.synchronize()
+        lat.append((time.perf_counter() - t0) * 1e3)
+    lat.sort()
+    tf = flops * batch / (ms_step * 1e-3) / 1e12
+    if profile_out:
+        rows = ["| # | op | ms | share | TFLOP/s | frac of burst peak | GB/s |", "|---|---|---|---|---|---|---|"]
+        for i in sorted(range(len(ms)), key=lambda i: -ms[i]):
+            t, fl, by = plan.op_info(i)
+            tfi = fl * batch / (ms[i] * 1e-3) / 1e12
+            rows.append(f"| {i} | {t} | {ms[i]:.4f} | {100 * ms[i] / sum(ms):.1f}% | {tfi:.1f} | {tfi / pk['tflops_burst']:.2f} | {by * batch / (ms[i] * 1e-3) / 1e9:.0f} |")
+        Path(profile_out).write_text(f"model.py variant (UninaCustomB200 bc32): per-op CUDA-event times, batch {batch}, {size}x{size}\n\n" + "\n".join(rows) + "\n")
+    return {"workload": f"model.py network (base_channels 32) conv stack, {size}x{size}, batch {batch}, bf16, resident frames",
+            "value": batch / (ms_step * 1e-3), "unit": UNIT, "ms_per_step": ms_step, "plan_launches": plan.launches,
+            "conv_gflop_per_image": flops / 1e9, "tflops": tf, "frac_of_tensor_peak_burst": tf / pk["tflops_burst"],
+            "frac_of_tensor_peak_sustained": tf / pk["tflops"], "families": family_table(plan, ms, batch, pk),
+            "predict_bs1_ms": {"p50": lat[len(lat) // 2], "min": lat[0],
+                               "note": "forward + TLBR decode x3 + record NMS + D2H of the kept count, one frame, host wall clock"}}
+
+
+def cpu_calibrate_cls_bias(ref, frames: torch.Tensor, per_image: int, conf: float) -> float:
+    """UninaYoloB200.calibrate_cls_bias restated on the CPU oracle (the reference arm must not touch libuyd.so):
+    shifts the class biases so that about `per_image` anchors per image clear `conf`."""
+    import math
+
+    det = ref.model[-1]
+    with torch.no_grad():
+        _, xs = ref(frames)
+        best = torch.cat([t[:, 4 * det.reg_max:].amax(1).flatten(1) for t in xs], 1)
+        k = max(1, min(best.shape[1] - 1, per_image))
+        kth = best.topk(k, dim=1).values[:, -1].mean().item()
+        shift = math.log(conf / (1 - conf)) - kth
+        for cls in det.cv3:
+            cls[-1].bias.add_(shift)
+    return shift
+
+
 def run_reference(a):
     """--impl reference: the reference's CPU implementation of the path on the host cores.
     ultralytics is not installable here (no network, unpinned, not vendored) and model.py is a
@@ -199,33 +300,36 @@ def run_reference(a):
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
-    model = build_models(a.size, True)
-    if torch.cuda.is_available():  # same NMS load as the GPU arm
-        try:
-            model = model.cuda()
-            g = torch.Generator(device="cuda").manual_seed(0)
-            model.calibrate_cls_bias(torch.rand(8, 3, a.size, a.size, device="cuda", generator=g), CANDIDATES_PER_IMAGE, CONF)
-        except Exception:
-            pass
+    model = build_models(a.size, True)          # CPU module only: same seeded weights as the GPU arm, libuyd.so is never loaded
     ref = oracle_from(model)
     chunk = 8
+    g = torch.Generator().manual_seed(0)
+    cpu_calibrate_cls_bias(ref, torch.rand(chunk, 3, a.size, a.size, generator=g), CANDIDATES_PER_IMAGE, CONF)  # same NMS load as the GPU arm
     frames = torch.rand(chunk, 3, a.size, a.size, generator=torch.Generator().manual_seed(1))
-    for _ in range(max(1, a.warmup)):
-        cpu_pass(ref, frames)
+    per_step = max(chunk, a.batch // chunk * chunk)   # the same batch-64 step as the GPU arm, walked in chunks of 8 frames
+
+    def one_step():
+        for _ in range(per_step // chunk):
+            cpu_pass(ref, frames)
+
+    cpu_pass(ref, frames)
+    for _ in range(max(0, a.warmup - 1)):
+        one_step()
     steps = max(1, a.steps)
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_pass(ref, frames)
+        one_step()
     dt = time.perf_counter() - t0
-    v = steps * chunk / dt
+    v = steps * per_step / dt
+    chunk = per_step
     cores = torch.get_num_threads()
-    sample = f"{chunk} frames per step ({steps} timed steps; bounded sample of the batch-{a.batch} workload)"
+    sample = f"{chunk} frames per step in chunks of 8 ({steps} timed steps of the batch-{a.batch} workload)"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": steps, "warmup": a.warmup,
         "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": f"unina-yolo-dla-m bf16 forward + DFL decode + NMS, {a.size}x{a.size}, batch {a.batch} per GPU",
-                   "reference_arm": f"oracle port, fp32 on the host cores, {chunk} frames per step (bounded sample of the same workload)"},
+                   "reference_arm": f"oracle port, fp32 on the host cores, {chunk} frames per step (chunks of 8 frames), class biases calibrated on the CPU oracle"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -267,26 +371,53 @@ def main():
         x_u8.copy_(x_host, non_blocking=True)
         det, cnt = model.predict_batched(x_u8, CONF, IOU, MAX_DET)
         if world > 1:  # batched-eval gather of the detections (the only collective of the path)
-            from unina_yolo_dla_b200.dp import gather_detections
-
-            det, cnt = gather_detections(det, cnt)
+            det, cnt = gatherer.start(det, cnt).wait()
             det, cnt = det[rank * B:(rank + 1) * B], cnt[rank * B:(rank + 1) * B]
         det_host.copy_(det, non_blocking=True)
         cnt_host.copy_(cnt, non_blocking=True)
 
-    def run_stream(steps):  # the streaming API: H2D of step i+1 overlaps the compute of step i
-        if world == 1:
-            for det_h, cnt_h in model.predict_stream((x_host for _ in range(steps)), CONF, IOU, MAX_DET, to_host=True):
-                pass
-            det_host.copy_(det_h)
-            cnt_host.copy_(cnt_h)
-        else:
-            from unina_yolo_dla_b200.dp import gather_detections
+    gatherer = None
+    if world > 1:
+        from unina_yolo_dla_b200.dp import DetectionGather
 
-            for det, cnt in model.predict_stream((x_host for _ in range(steps)), CONF, IOU, MAX_DET, to_host=False):
-                gd, gc = gather_detections(det, cnt)
-                det_host.copy_(gd[rank * B:(rank + 1) * B], non_blocking=True)
-                cnt_host.copy_(gc[rank * B:(rank + 1) * B], non_blocking=True)
+        gatherer = DetectionGather()
+
+    def run_stream(steps, xh=None, gather=True, h2d=True):
+        """The streaming API: H2D of step i+1 overlaps the compute of step i; with N > 1 every step's detections go
+        through ONE fixed-shape NCCL all_gather on a side stream (no host sync) and the rank's rows come back to the
+        host.  gather / h2d = False switch one stage off (e2e.bound_probe)."""
+        xh = x_host if xh is None else xh
+        dh = det_host if xh is x_host else torch.empty(xh.shape[0], MAX_DET, 6).pin_memory()
+        ch = cnt_host if xh is x_host else torch.empty(xh.shape[0], dtype=torch.int32).pin_memory()
+        nb = xh.shape[0]
+        src = (xh for _ in range(steps))
+        if not h2d:  # frames already on the device: the generator only slices them
+            xd = xh.to(dev)
+            for _ in range(steps):
+                det, cnt = model.predict_batched(xd, CONF, IOU, MAX_DET)
+                if world > 1 and gather:
+                    det, cnt = gatherer.start(det, cnt).wait()
+                    det, cnt = det[rank * nb:(rank + 1) * nb], cnt[rank * nb:(rank + 1) * nb]
+                dh.copy_(det, non_blocking=True)
+                ch.copy_(cnt, non_blocking=True)
+            return
+        if world == 1 or not gather:
+            for det_h, cnt_h in model.predict_stream(src, CONF, IOU, MAX_DET, to_host=True):
+                pass
+            dh.copy_(det_h)
+            ch.copy_(cnt_h)
+        else:
+            pending = None
+            for det, cnt in model.predict_stream(src, CONF, IOU, MAX_DET, to_host=False):
+                h = gatherer.start(det, cnt)
+                if pending is not None:  # consume step i - 1 while step i's exchange is in flight
+                    gd, gc = pending.wait()
+                    dh.copy_(gd[rank * nb:(rank + 1) * nb], non_blocking=True)
+                    ch.copy_(gc[rank * nb:(rank + 1) * nb], non_blocking=True)
+                pending = h
+            gd, gc = pending.wait()
+            dh.copy_(gd[rank * nb:(rank + 1) * nb], non_blocking=True)
+            ch.copy_(gc[rank * nb:(rank + 1) * nb], non_blocking=True)
 
     warm = max(3, a.warmup)
     for _ in range(warm):
@@ -331,6 +462,42 @@ def main():
     # staging buffers, a neighbour on the PCIe switch) lands entirely in it, so it is repeated and the best of three kept
     ms_e2e = min(timed(lambda: run_stream(a.steps), 1) for _ in range(3))
     n_det = int(cnt_host.sum().item())
+    # which stage bounds e2e: the same streamed run with one stage switched off
+    probe = {}
+    if world > 1:
+        probe["no_gather_ms_per_step"] = min(timed(lambda: run_stream(a.steps, gather=False), 1) for _ in range(2)) / a.steps
+    probe["no_h2d_ms_per_step"] = min(timed(lambda: run_stream(a.steps, h2d=False), 1) for _ in range(2)) / a.steps
+    # sustained: the resident step back to back for >= a.sustain seconds, clocks sampled throughout
+    sustained = None
+    if a.sustain > 0:
+        n_sus = max(a.steps, int(a.sustain * 1e3 / (ms_total / a.steps)) + 1)
+        smp = ClockSampler(local)
+        if rank == 0:
+            smp.start()
+        ms_sus = timed(step_resident, n_sus)
+        if rank == 0:
+            smp.stop_flag = True
+            smp.join(timeout=10)
+        sustained = {"steps": n_sus, "seconds": ms_sus * 1e-3, "value": world * B * n_sus / (ms_sus * 1e-3), "unit": UNIT,
+                     "ms_per_step": ms_sus / n_sus, "clocks": smp.summary() if rank == 0 else None}
+    # BASELINE config 4: 256 frames per GPU
+    c4 = None
+    if a.c4_batch > 0 and a.c4_batch != B:
+        B4 = a.c4_batch
+        x4 = torch.rand(B4, 3, S, S, device=dev, generator=gen)
+        x4_host = (torch.rand(B4, 3, S, S, generator=torch.Generator().manual_seed(400 + rank)) * 255).to(torch.uint8).pin_memory()
+        k4 = max(3, a.steps // 4)
+        for _ in range(2):
+            model.predict_batched(x4, CONF, IOU, MAX_DET)
+        ms4 = timed(lambda: model.predict_batched(x4, CONF, IOU, MAX_DET), k4)
+        run_stream(2, x4_host)
+        ms4_e2e = min(timed(lambda: run_stream(k4, x4_host), 1) for _ in range(2))
+        c4 = {"batch_per_gpu": B4, "steps": k4, "value": world * B4 * k4 / (ms4 * 1e-3), "unit": UNIT, "ms_per_step": ms4 / k4,
+              "e2e": {"value": world * B4 * k4 / (ms4_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms4_e2e / k4,
+                      "h2d_bytes_per_step": x4_host.numel(), "d2h_bytes_per_step": B4 * (MAX_DET * 6 + 1) * 4}}
+        del x4, x4_host
+        model._stream_state.clear()
+        torch.cuda.empty_cache()
 
     # stage split of one resident step and batch-1 latency (p50 over 50 synchronised calls)
     def span(fn, reps=5):
@@ -392,12 +559,16 @@ def main():
                 "d2h_bytes_per_step": det_host.numel() * 4 + cnt_host.numel() * 4, "ms_per_step": ms_e2e / a.steps,
                 "single_call_ms": ms_e2e_single / a.steps,
                 "api": "UninaYoloB200.predict_stream(pinned uint8 NCHW host batches): H2D of step i+1 overlaps step i (best of 3 runs of K steps); "
-                       "single_call_ms = one blocking predict_batched(host frames) per step"},
+                       "N > 1: + one fixed-shape NCCL all_gather of the detections per step on a side stream; "
+                       "single_call_ms = one blocking predict_batched(host frames) per step",
+                "bound_probe": dict(probe, note="the same streamed run with the gather (N > 1) or the H2D copy switched off: the stage "
+                                                "whose removal brings ms_per_step down to the resident step is the bound")},
         "gpu_launches": kernels_per_step * a.steps,
         "roofline": {"kernel": top_text, "bound": "tensor" if tensor_bound else "hbm", "achieved": achieved, "peak": peak,
                      "unit": unit, "frac": achieved / peak, "traffic": traffic, "peak_source": pk["src"],
                      "avg_launch_ms": top_ms, "launches_timed": top_n,
-                     "share_of_conv_stack": ms[top] / sum(ms)},
+                     "share_of_conv_stack": ms[top] / sum(ms),
+                     "families": family_table(plan, ms, B, pk, ms_nms)},
         "conv_stack": {"ms_per_step_profiled": sum(ms), "tflops": conv_flops * B / (sum(ms) * 1e-3) / 1e12,
                        "frac_of_tensor_peak": conv_flops * B / (sum(ms) * 1e-3) / 1e12 / pk["tflops"]},
         "stages_ms": {"conv_stack": ms_stack, "dfl_decode": ms_fwd_decode - ms_stack, "nms": ms_nms,
@@ -406,11 +577,20 @@ def main():
                            "note": "predict_batched on one resident frame (CUDA-graph replay), host-synchronised wall clock"},
         "clocks": sampler.summary(),
     }
-    if a.int8 > 0:
-        out["int8"] = bench_int8(model, a.int8, S, dev, max(3, a.steps // 2))
-    if a.stress > 0:
-        out["nms_stress_1280"] = bench_nms_stress(model, a.stress, dev, max(3, a.steps // 2))
+    if sustained:
+        out["sustained"] = sustained
+    if c4:
+        out["c4_batch256"] = c4
     if world == 1:
+        if a.stress > 0:
+            out["nms_stress_1280"] = bench_nms_stress(model, a.stress, dev, max(3, a.steps // 2))
+        if a.int8 > 0:
+            out["int8"] = bench_int8(model, a.int8, S, dev, max(3, a.steps // 4))
+        model._plans.clear() if hasattr(model, "_plans") else None
+        torch.cuda.empty_cache()
+        if a.custom > 0:
+            out["custom_variant"] = bench_custom(a.custom, S, dev, max(3, a.steps // 2), pk,
+                                                 a.profile_out.replace(".md", "_custom.md") if a.profile_out else "")
         out["cpu_baseline"] = cpu_baseline(model, S, a.cpu_sample)
     if a.profile_out:
         rows = ["| # | op | ms | share | TFLOP/s | GB/s |", "|---|---|---|---|---|---|"]
