@@ -68,6 +68,15 @@ TC_CASES = [
     (32, 32, 3, 2, 80, 80, dict(in_total=96, in_coff=32)),     # input is a channel slice (pair = 2 x 64 B at pitch 192 B)
     (32, 64, 3, 2, 160, 160, dict(out_total=128, out_coff=64)),  # more tiles than SMs, partial tiles on neither edge
     (32, 32, 3, 2, 36, 52, dict()),                              # partial tiles on both edges
+    # BIG variant (weights streamed through their own TMA pipeline, two M-tiles per CTA): the model.py layers
+    (128, 128, 3, 1, 40, 40, dict()),                            # halo, partial 16 x 16 regions on both edges
+    (128, 128, 3, 1, 48, 80, dict(residual=True)),               # more regions than one wave of the pipeline, residual
+    (256, 256, 3, 1, 24, 40, dict()),                            # N = 256: single accumulator pair
+    (128, 256, 3, 2, 48, 48, dict()),                            # stride 2: strided box per tap
+    (128, 128, 3, 2, 40, 72, dict(in_total=192, in_coff=64)),    # stride 2 from a channel slice
+    (512, 256, 1, 1, 20, 20, dict()),                            # 1x1, 8 channel blocks, ragged last 256-pixel tile
+    (256, 256, 1, 1, 40, 40, dict(out_total=512, out_coff=256)),
+    (128, 192, 3, 1, 20, 20, dict()),                            # N = 192 (not a power of two)
 ]
 
 

@@ -101,14 +101,14 @@ struct ChainConv;
 ChainConv *chain_new();
 void chain_delete(ChainConv *);
 bool chain_supported(int cin, int n1, int n2, int in_pitch, int in_coff);
-size_t chain_w1_bytes(int cin, int n1);
+size_t chain_w1_bytes(int cin, int n1, bool depthwise);
 size_t chain_w2_bytes(int n1, int n2);
 void chain_pack_w1(int cin, int n1, bool depthwise, const float *w, void *dst_host);
 void chain_pack_w2(int n1, int n2, const float *w, void *dst_host);
 int chain_prepare(ChainConv *cc, int cin, int n1, int n2, void *in_base, int in_pitch, int h, int w, int max_batch,
                   void *w1_dev, void *w2_dev, const float *bias1, const float *bias2, int relu2, int final_kind, int nc,
                   const float *w3_dev, const float *bias3_dev, void *out_base, int out_pitch, int out_f32, int a_total,
-                  int a_off, int y_ch0, int no, float stride_px);
+                  int a_off, int y_ch0, int no, float stride_px, int dw1);
 int chain_launch(const ChainConv *cc, int nb, float *y, int sm_count, cudaStream_t s);
 
 // stem_fused.cu
@@ -458,7 +458,7 @@ extern "C" int uyd_plan_add_chain(uyd_plan *plan, const uyd_chain *d, const floa
   Op op;
   op.kind = OP_CHAIN;
   op.chain = *d;
-  op.w_host.resize(chain_w1_bytes(d->cin, d->n1));
+  op.w_host.resize(chain_w1_bytes(d->cin, d->n1, d->dw1 != 0));
   chain_pack_w1(d->cin, d->n1, d->dw1 != 0, w1, op.w_host.data());
   op.w2_host.resize(chain_w2_bytes(d->n1, d->n2));
   chain_pack_w2(d->n1, d->n2, w2, op.w2_host.data());
@@ -642,7 +642,7 @@ extern "C" int uyd_plan_finalize(uyd_plan *plan) {
       o.cc = chain_new();
       int e = chain_prepare(o.cc, d.cin, d.n1, d.n2, slice_ptr(plan, d.in_buf, d.in_coff), ib.c, ib.h, ib.w, plan->max_batch, o.w_dev,
                             o.w2_dev, o.b_dev, o.b2_dev, d.relu2, d.final_kind, d.nc, o.w3_dev, o.b3_dev, out, out_pitch, out_f32,
-                            d.a_total, d.a_off, d.y_ch0, d.no, d.stride_px);
+                            d.a_total, d.a_off, d.y_ch0, d.no, d.stride_px, d.dw1);
       if (e) return e;
       continue;
     }

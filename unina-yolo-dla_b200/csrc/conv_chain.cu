@@ -13,9 +13,12 @@
 //
 // Box branch  : Conv(64,64,3) -> Conv2d(64,64,1) -> DFL                    = one launch, the 64 logits
 //               of an anchor stay in TMEM / registers.
-// Class branch: DWConv(c,c,3) runs as a dense 3x3 GEMM with diagonal weights (the tensor pipe is
-//               otherwise idle and the tap-shifted descriptors make the window free), followed by
-//               its 1x1 conv: [dw1, pw1] -> z1 (bf16) and [dw2, pw2, pw3] -> logits / scores.
+// Class branch: DWConv(c,c,3) + its 1x1 conv: [dw1, pw1] -> z1 (bf16) and [dw2, pw2, pw3] -> logits / scores.
+//               The depth-wise 3x3 runs on the CUDA cores of the epilogue groups (template DW): a thread owns one
+//               channel quad of one tile column, keeps its 36 weights in registers, walks the TMA halo box down
+//               the column (three 8-byte loads per input row, packed fp32 FFMA2) and writes the bf16 result
+//               straight into the swizzled K-major tile GEMM2 consumes.  (Round 1 ran it as a dense GEMM with a
+//               diagonal weight matrix: 18 tcgen05.mma per tile on a 97 %-zero operand, 1550 cycles per tile.)
 //
 // Warp roles (512 threads, persistent CTA per SM): warp 0 TMA producer, warp 1 TMEM allocator + GEMM1
 // issuer, warp 2 GEMM2 issuer, warps 4-15 three epilogue groups taking tiles round-robin.  GEMM1 of the
@@ -42,6 +45,7 @@ struct ChainParams {
   uint32_t idesc1, idesc2, layout1, layout2;
   int relu2, final_kind, nc;
   const float *bias1, *bias2, *bias3, *w3;  // w3: fp32 [nc][N2] holding bf16-rounded values
+  const float *dw_w;                        // DW: depth-wise weights fp32 [9][C] holding bf16-rounded values
   void *out;                                // raw store target (slice base of image 0) or null
   int out_pitch, out_f32;
   float *y;                                 // decoded output [B, no, a_total] or null
@@ -58,6 +62,16 @@ constexpr int kHaloRows = 18, kTileH = 16, kTileW = 8, kHaloPitch = kTileW + 2;
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
+// packed fp32 FMA (FFMA2 on sm_100): d = a * b + c on both halves
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+
 // 16 consecutive floats of a shared-memory vector as four 16-byte broadcast loads
 __device__ __forceinline__ void load_bias16(const float *s, float (&v)[16]) {
 #pragma unroll
@@ -72,7 +86,8 @@ __device__ __forceinline__ void stamp(const ChainParams &p, int it, int slot, in
 }
 
 // KS1 / KS2 = 32-byte k-steps per channel-block row of GEMM1 / GEMM2 (cb_bytes / 32, N1 * 2 / 32)
-template <int KS1, int KS2>
+// DW: the first conv is depth-wise (C = 16 * KS1 channels = N1) and runs on the CUDA cores of the epilogue groups
+template <int KS1, int KS2, bool DW>
 __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __grid_constant__ CUtensorMap tm_in,
                                                                       const __grid_constant__ CUtensorMap tm_w1,
                                                                       const __grid_constant__ CUtensorMap tm_w2,
@@ -100,7 +115,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full0 + 8u * s, 1);
-      mbar_init(empty0 + 8u * s, 1);
+      mbar_init(empty0 + 8u * s, DW ? 128 : 1);  // DW: released by the 128 threads that read the halo box
     }
     mbar_init(wfull, 1);
     for (int g = 0; g < kNG; ++g) {
@@ -113,7 +128,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     fence_barrier_init();
     // weights: part of the prologue that overlaps the previous kernel's tail
     mbar_expect_tx(wfull, p.w1_bytes + p.w2_bytes);
-    const int nblk = p.ncb * 9;
+    const int nblk = DW ? 0 : p.ncb * 9;
     for (int i = 0; i < nblk; ++i) tma_load_2d(w1_s + (uint32_t)i * p.N1 * p.cb_bytes, &tm_w1, wfull, 0, i * p.N1);
     tma_load_2d(w2_s, &tm_w2, wfull, 0, 0);
   }
@@ -163,7 +178,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
         if (++stage == stages) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && !DW) {
     // ================= GEMM1 issuer =================
     // tcgen05.mma issue is nearly synchronous with execution (the queue is a few instructions deep), so
     // every cycle this thread spends polling barriers is a tensor-pipe bubble: GEMM2 has its own issuing
@@ -235,6 +250,21 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     // restricted to the row width)
     const uint32_t swz = cb2_bytes == 128 ? (uint32_t)(m & 7) : (cb2_bytes == 64 ? (uint32_t)((m >> 1) & 3) : (uint32_t)((m >> 2) & 1));
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    // DW: this thread's channel quad (4 channels x 9 taps) and bias, in registers for the whole launch
+    float2 dw_wlo[9], dw_whi[9], dw_blo = make_float2(0.f, 0.f), dw_bhi = dw_blo;
+    if constexpr (DW) {
+      constexpr int C = KS1 * 16;
+      const int qd = m % (C / 4);
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const float4 w4 = *reinterpret_cast<const float4 *>(p.dw_w + t * C + 4 * qd);
+        dw_wlo[t] = make_float2(w4.x, w4.y);
+        dw_whi[t] = make_float2(w4.z, w4.w);
+      }
+      const float4 b4 = *reinterpret_cast<const float4 *>(p.bias1 + 4 * qd);
+      dw_blo = make_float2(b4.x, b4.y);
+      dw_bhi = make_float2(b4.z, b4.w);
+    }
     // group g takes tiles g, g + kNG, ... of this CTA's sequence; tile indices fit 32 bits (checked on the host)
     int it = g;
     uint32_t ph = 0;
@@ -244,38 +274,80 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
       const int n = p.n0 + (int)img;
       const int oy = (int)ty * kTileH + (m >> 3), ox = (int)tx * kTileW + (m & 7);
       const bool inside = oy < p.H && ox < p.W;
+      if constexpr (DW) {
+        // ---- stage 1 (depth-wise): halo box -> 3x3 depth-wise conv on CUDA cores -> bias, ReLU -> bf16 -> A of GEMM2 ----
+        constexpr int C = KS1 * 16, NQ = C / 4, NH = 128 / (NQ * 8), R = 16 / NH;  // rows per thread: 8 (C = 32) / 16 (C = 64)
+        const int qd = m % NQ, xx = (m / NQ) & 7, half = m / (NQ * 8);
+        const int sidx = it % stages;
+        mbar_wait(full0 + 8u * sidx, (uint32_t)(it / stages) & 1u);
+        const unsigned char *hb = smem_dyn + (a_s + (uint32_t)sidx * blk_bytes - raw);
+        unsigned char *a2_tile = smem_dyn + (a2_s + (uint32_t)g * p.a2_bytes - raw);
+        float2 a0[3], a1[3];  // accumulators of three output rows in flight, ring-indexed by row % 3
+#pragma unroll
+        for (int i = 0; i < R + 2; ++i) {
+          float2 v0[3], v1[3];
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            const int pi = (half * R + i) * kHaloPitch + xx + dx;
+            const uint32_t sw = C == 64 ? (uint32_t)(pi & 7) : (uint32_t)((pi >> 1) & 3);
+            const uint2 h2 = *reinterpret_cast<const uint2 *>(hb + pi * (C * 2) + ((((uint32_t)qd >> 1) ^ sw) << 4) + (qd & 1) * 8);
+            v0[dx] = make_float2(__uint_as_float(h2.x << 16), __uint_as_float(h2.x & 0xffff0000u));
+            v1[dx] = make_float2(__uint_as_float(h2.y << 16), __uint_as_float(h2.y & 0xffff0000u));
+          }
+#pragma unroll
+          for (int tr = 0; tr < 3; ++tr) {  // input row i is tap row tr of output row i - tr
+            const int r = i - tr;
+            if (r < 0 || r >= R) continue;
+            float2 &o0 = a0[r % 3], &o1 = a1[r % 3];
+            if (tr == 0) { o0 = dw_blo; o1 = dw_bhi; }
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+              o0 = ffma2(v0[dx], dw_wlo[tr * 3 + dx], o0);
+              o1 = ffma2(v1[dx], dw_whi[tr * 3 + dx], o1);
+            }
+            if (tr == 2) {
+              const int pm = (half * R + r) * 8 + xx;
+              const uint32_t sw2 = C == 64 ? (uint32_t)(pm & 7) : (uint32_t)((pm >> 1) & 3);
+              *reinterpret_cast<uint2 *>(a2_tile + pm * (C * 2) + ((((uint32_t)qd >> 1) ^ sw2) << 4) + (qd & 1) * 8) =
+                  make_uint2(relu_pack_bf16x2(o0.x, o0.y), relu_pack_bf16x2(o1.x, o1.y));
+            }
+          }
+        }
+        mbar_arrive(empty0 + 8u * sidx);  // this thread's reads of the halo box are done
+      } else {
       // ---- stage 1: acc1 -> bias, ReLU -> bf16 -> swizzled shared-memory tile (A of GEMM2) ----
-      mbar_wait(tfull1 + 8u * g, ph);
-      tc_fence_after();
-      if (q == 0) stamp(p, it, 3, lane);  // accumulator 1 complete
-      {
-        const uint32_t t1 = lane_base + (uint32_t)g * p.N1;
-        uint32_t cur[16], nxt[16];
-        tmem_ld16_issue(t1, cur);
-        tmem_ld_wait();
-        for (int c = 0; c < nch1; ++c) {
-          const bool more = c + 1 < nch1;
-          if (more) {
-            tmem_ld16_issue(t1 + 16u * (c + 1), nxt);
-          } else {
-            tc_fence_before();
-            mbar_arrive(tempty1 + 8u * g);
-          }
-          uint4 o0, o1;
-          uint32_t *w0 = reinterpret_cast<uint32_t *>(&o0), *w1 = reinterpret_cast<uint32_t *>(&o1);
-          float bv[16];
-          load_bias16(bias1_s + c * 16, bv);
+        mbar_wait(tfull1 + 8u * g, ph);
+        tc_fence_after();
+        if (q == 0) stamp(p, it, 3, lane);  // accumulator 1 complete
+        {
+          const uint32_t t1 = lane_base + (uint32_t)g * p.N1;
+          uint32_t cur[16], nxt[16];
+          tmem_ld16_issue(t1, cur);
+          tmem_ld_wait();
+          for (int c = 0; c < nch1; ++c) {
+            const bool more = c + 1 < nch1;
+            if (more) {
+              tmem_ld16_issue(t1 + 16u * (c + 1), nxt);
+            } else {
+              tc_fence_before();
+              mbar_arrive(tempty1 + 8u * g);
+            }
+            uint4 o0, o1;
+            uint32_t *w0 = reinterpret_cast<uint32_t *>(&o0), *w1 = reinterpret_cast<uint32_t *>(&o1);
+            float bv[16];
+            load_bias16(bias1_s + c * 16, bv);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {  // bias -> ReLU -> bf16 pair in one cvt.rn.relu.bf16x2
-            w0[i] = relu_pack_bf16x2(__uint_as_float(cur[2 * i]) + bv[2 * i], __uint_as_float(cur[2 * i + 1]) + bv[2 * i + 1]);
-            w1[i] = relu_pack_bf16x2(__uint_as_float(cur[8 + 2 * i]) + bv[8 + 2 * i], __uint_as_float(cur[8 + 2 * i + 1]) + bv[8 + 2 * i + 1]);
-          }
-          *reinterpret_cast<uint4 *>(a2_row + (((uint32_t)(2 * c) ^ swz) << 4)) = o0;
-          *reinterpret_cast<uint4 *>(a2_row + (((uint32_t)(2 * c + 1) ^ swz) << 4)) = o1;
-          if (more) {
-            tmem_ld_wait();
+            for (int i = 0; i < 4; ++i) {  // bias -> ReLU -> bf16 pair in one cvt.rn.relu.bf16x2
+              w0[i] = relu_pack_bf16x2(__uint_as_float(cur[2 * i]) + bv[2 * i], __uint_as_float(cur[2 * i + 1]) + bv[2 * i + 1]);
+              w1[i] = relu_pack_bf16x2(__uint_as_float(cur[8 + 2 * i]) + bv[8 + 2 * i], __uint_as_float(cur[8 + 2 * i + 1]) + bv[8 + 2 * i + 1]);
+            }
+            *reinterpret_cast<uint4 *>(a2_row + (((uint32_t)(2 * c) ^ swz) << 4)) = o0;
+            *reinterpret_cast<uint4 *>(a2_row + (((uint32_t)(2 * c + 1) ^ swz) << 4)) = o1;
+            if (more) {
+              tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
+              for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
+            }
           }
         }
       }
@@ -480,6 +552,7 @@ struct ChainConv {
   CUtensorMap tm_in, tm_w1, tm_w2;
   ChainParams p;
   size_t smem;
+  bool dw = false;
 };
 
 ChainConv *chain_new() { return new ChainConv(); }
@@ -491,20 +564,24 @@ bool chain_supported(int cin, int n1, int n2, int in_pitch, int in_coff) {
   return in_pitch % 8 == 0 && in_coff % 8 == 0;
 }
 
-size_t chain_w1_bytes(int cin, int n1) { return (size_t)9 * cin * n1 * 2; }
+size_t chain_w1_bytes(int cin, int n1, bool depthwise) { return depthwise ? (size_t)9 * cin * 4 : (size_t)9 * cin * n1 * 2; }
 size_t chain_w2_bytes(int n1, int n2) { return (size_t)n1 * ((n2 + 15) / 16 * 16) * 2; }
 
 // w1: [n1][cin][3][3] fp32 (dense) or, when depthwise, [n1][1][3][3] expanded to a diagonal dense matrix.
 // Layout: bf16 [tap][n (N1)][cin]   (one channel block)
+//         depth-wise: fp32 [tap][c] holding the bf16-rounded weights (CUDA-core stage of the DW kernel)
 void chain_pack_w1(int cin, int n1, bool depthwise, const float *w, void *dst_host) {
+  if (depthwise) {
+    float *f = reinterpret_cast<float *>(dst_host);
+    for (int t = 0; t < 9; ++t)
+      for (int c = 0; c < cin; ++c) f[t * cin + c] = __bfloat162float(__float2bfloat16_rn(w[(size_t)c * 9 + t]));
+    return;
+  }
   __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(dst_host);
   for (int t = 0; t < 9; ++t)
     for (int n = 0; n < n1; ++n)
       for (int c = 0; c < cin; ++c) {
-        float v;
-        if (depthwise) v = (n == c) ? w[(size_t)n * 9 + t] : 0.f;
-        else v = w[((size_t)n * cin + c) * 9 + t];
-        o[((size_t)t * n1 + n) * cin + c] = __float2bfloat16_rn(v);
+        o[((size_t)t * n1 + n) * cin + c] = __float2bfloat16_rn(w[((size_t)n * cin + c) * 9 + t]);
       }
 }
 
@@ -519,9 +596,11 @@ void chain_pack_w2(int n1, int n2, const float *w, void *dst_host) {
 int chain_prepare(ChainConv *cc, int cin, int n1, int n2, void *in_base, int in_pitch, int h, int w, int max_batch,
                   void *w1_dev, void *w2_dev, const float *bias1, const float *bias2, int relu2, int final_kind, int nc,
                   const float *w3_dev, const float *bias3_dev, void *out_base, int out_pitch, int out_f32, int a_total,
-                  int a_off, int y_ch0, int no, float stride_px) {
+                  int a_off, int y_ch0, int no, float stride_px, int dw1) {
   ChainParams &p = cc->p;
   memset(&p, 0, sizeof(p));
+  cc->dw = dw1 != 0;
+  p.dw_w = dw1 ? reinterpret_cast<const float *>(w1_dev) : nullptr;
   p.H = h; p.W = w;
   p.ncb = 1;
   p.cb_bytes = cin * 2;
@@ -534,7 +613,7 @@ int chain_prepare(ChainConv *cc, int cin, int n1, int n2, void *in_base, int in_
   p.tiles_y = ceil_div(h, kTileH);
   p.blk_bytes = ((uint32_t)kHaloRows * kHaloPitch * p.cb_bytes + 1023u) & ~1023u;
   p.tx_bytes = (uint32_t)kHaloRows * kHaloPitch * p.cb_bytes;
-  p.w1_bytes = (uint32_t)chain_w1_bytes(cin, n1);
+  p.w1_bytes = dw1 ? 0u : (uint32_t)chain_w1_bytes(cin, n1, false);
   p.w2_bytes = (uint32_t)chain_w2_bytes(n1, n2);
   p.a2_bytes = 128u * (uint32_t)n1 * 2u;
   p.layout1 = layout_code(p.cb_bytes);
@@ -553,12 +632,14 @@ int chain_prepare(ChainConv *cc, int cin, int n1, int n2, void *in_base, int in_
   if (stages > 6) stages = 6;
   p.stages = stages;
   cc->smem = fixed + (size_t)stages * p.blk_bytes;
-  {
+  if (!dw1) {
     const cuuint64_t dims[2] = {(cuuint64_t)cin, (cuuint64_t)9 * n1};
     const cuuint64_t str[1] = {(cuuint64_t)p.cb_bytes};
     const cuuint32_t box[2] = {(cuuint32_t)cin, (cuuint32_t)n1};
     int e = chain_encode(&cc->tm_w1, w1_dev, 2, dims, str, box, p.cb_bytes);
     if (e) return e;
+  } else {
+    cc->tm_w1 = cc->tm_w2;  // unused by the DW kernel
   }
   {
     const cuuint64_t dims[2] = {(cuuint64_t)n1, (cuuint64_t)p.N2};
@@ -574,10 +655,12 @@ int chain_prepare(ChainConv *cc, int cin, int n1, int n2, void *in_base, int in_
     int e = chain_encode(&cc->tm_in, in_base, 4, dims, str, box, p.cb_bytes);
     if (e) return e;
   }
-  if (int e = smem_optin(conv_chain_kernel<2, 2>, 227 * 1024)) return e;
-  if (int e = smem_optin(conv_chain_kernel<2, 4>, 227 * 1024)) return e;
-  if (int e = smem_optin(conv_chain_kernel<4, 2>, 227 * 1024)) return e;
-  if (int e = smem_optin(conv_chain_kernel<4, 4>, 227 * 1024)) return e;
+  if (int e = smem_optin(conv_chain_kernel<2, 2, false>, 227 * 1024)) return e;
+  if (int e = smem_optin(conv_chain_kernel<2, 4, false>, 227 * 1024)) return e;
+  if (int e = smem_optin(conv_chain_kernel<4, 2, false>, 227 * 1024)) return e;
+  if (int e = smem_optin(conv_chain_kernel<4, 4, false>, 227 * 1024)) return e;
+  if (int e = smem_optin(conv_chain_kernel<2, 2, true>, 227 * 1024)) return e;
+  if (int e = smem_optin(conv_chain_kernel<4, 4, true>, 227 * 1024)) return e;
   return UYD_OK;
 }
 
@@ -600,11 +683,14 @@ int chain_launch(const ChainConv *cc, int nb, float *y, int sm_count, cudaStream
     p.dbg = dbg_dev;
   }
 #endif
-#define UYD_CHAIN_LAUNCH(A, B) UYD_CUDA(launch_pdl(conv_chain_kernel<A, B>, dim3(grid), dim3(kChainThreads), cc->smem, s, cc->tm_in, cc->tm_w1, cc->tm_w2, p))
-  if (ks1 == 2 && ks2 == 2) UYD_CHAIN_LAUNCH(2, 2);
-  else if (ks1 == 2 && ks2 == 4) UYD_CHAIN_LAUNCH(2, 4);
-  else if (ks1 == 4 && ks2 == 2) UYD_CHAIN_LAUNCH(4, 2);
-  else UYD_CHAIN_LAUNCH(4, 4);
+#define UYD_CHAIN_LAUNCH(A, B, D) UYD_CUDA(launch_pdl(conv_chain_kernel<A, B, D>, dim3(grid), dim3(kChainThreads), cc->smem, s, cc->tm_in, cc->tm_w1, cc->tm_w2, p))
+  if (cc->dw) {  // cin == n1: ks1 == ks2
+    if (ks1 == 2) UYD_CHAIN_LAUNCH(2, 2, true);
+    else UYD_CHAIN_LAUNCH(4, 4, true);
+  } else if (ks1 == 2 && ks2 == 2) UYD_CHAIN_LAUNCH(2, 2, false);
+  else if (ks1 == 2 && ks2 == 4) UYD_CHAIN_LAUNCH(2, 4, false);
+  else if (ks1 == 4 && ks2 == 2) UYD_CHAIN_LAUNCH(4, 2, false);
+  else UYD_CHAIN_LAUNCH(4, 4, false);
 #undef UYD_CHAIN_LAUNCH
 #ifdef UYD_CHAIN_TIMELINE_BUILD
   if (timeline) {  // debug only: dump the stamps of CTA 0 (cycles relative to its first TMA issue)

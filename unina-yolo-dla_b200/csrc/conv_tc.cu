@@ -72,6 +72,12 @@ struct TcParams {
   const float *bias;
   int relu;
   const float *pre;      // fp32 [n, H/2, W/2, cout] partial sums added (nearest x2 upsampled) before the activation, or null
+  // ---- BIG variant (conv_tc_big_kernel: weights streamed, two M-tiles per CTA) ----
+  int big;               // 1: weights do not fit shared memory
+  int wstages;           // weight pipeline stages
+  uint32_t wblk_bytes;   // one weight block (N x 128 B) in shared memory
+  uint32_t tile_off;     // byte offset of the second M-tile inside an A block
+  int pairs_x;           // 16 x 16 pixel regions per image row (HALO / PERTAP)
 };
 
 namespace {
@@ -563,6 +569,196 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
+
+// =================================================================================================
+// BIG variant: convolutions whose weights do not fit shared memory (Cin * k * k * Cout * 2 B > 150 KB: the
+// 128 / 256 / 512-channel layers of the model.py network, model.py:274-303,308-365).
+//   * a CTA owns a PAIR of M-tiles (a 16 x 16 pixel region, or 256 consecutive pixels of a 1x1 conv) with
+//     two TMEM accumulators of N <= 256 columns: every weight block that crosses L2 -> SMEM feeds 2 x 128 rows;
+//   * weights stream through their own TMA pipeline, one (channel block, tap) block of N x 64 channels per stage;
+//   * activations: HALO (3x3 s1: one [18][18][64] box per channel block, nine tap-shifted descriptors per tile),
+//     PERTAP (3x3 s2: one strided [16][16][64] box per block and tap) or FLAT (1x1: [256][64]).
+// Warps: 0 = activation TMA, 1 = TMEM allocator + MMA issuer, 2 = weight TMA, 4..11 = two epilogue groups
+// (group g drains M-tile g).  When 4 N <= 512 the accumulator pairs are double-buffered.
+// =================================================================================================
+constexpr int kBigThreads = 128 + 256;
+constexpr int kBigHalo = 18;
+
+__global__ void __launch_bounds__(kBigThreads, 1) conv_tc_big_kernel(const __grid_constant__ CUtensorMap tm_in,
+                                                                     const __grid_constant__ CUtensorMap tm_w, const TcParams p) {
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t raw = smem_u32(smem_dyn);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t a_s = base;
+  const uint32_t w_s = a_s + (uint32_t)p.stages * p.blk_bytes;
+  const uint32_t bar0 = w_s + (uint32_t)p.wstages * p.wblk_bytes;
+  // barrier map: afull[4] aempty[4] wfull[8] wempty[8] tfull[2] tempty[2] | slot | bias[256]
+  const uint32_t afull = bar0, aempty = bar0 + 32, wfull = bar0 + 64, wempty = bar0 + 128, tfull = bar0 + 192, tempty = bar0 + 208;
+  const uint32_t slot = bar0 + 224;
+  uint32_t *slot_ptr = reinterpret_cast<uint32_t *>(smem_dyn + (slot - raw));
+  float *bias_s = reinterpret_cast<float *>(smem_dyn + (bar0 + 256u - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nacc = p.nacc;  // accumulator PAIRS
+  const uint32_t tmem_cols = 512;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(afull + 8u * s, 1); mbar_init(aempty + 8u * s, 1); }
+    for (int s = 0; s < p.wstages; ++s) { mbar_init(wfull + 8u * s, 1); mbar_init(wempty + 8u * s, 1); }
+    for (int a = 0; a < nacc; ++a) { mbar_init(tfull + 8u * a, 1); mbar_init(tempty + 8u * a, 256); }
+    fence_barrier_init();
+  }
+  griddep_trigger();
+  for (int i = threadIdx.x; i < 256; i += kBigThreads) bias_s[i] = i < p.cout ? p.bias[i] : 0.f;
+  if (warp == 1) tmem_alloc(slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *slot_ptr;
+  griddep_wait();
+
+  const int kblocks = p.ncb * p.taps;                                   // weight blocks per pair
+  const bool a_per_tap = p.mode == TC_PERTAP;                           // else one A block per channel block
+  const int pairs_per_img = p.pairs_x * p.tiles_y;
+  const long long total = p.total_tiles;                                // pairs of this launch
+
+  if (warp == 0) {
+    // ================= activation TMA =================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long pair = blockIdx.x; pair < total; pair += gridDim.x) {
+      int n = 0, x0 = 0, y0 = 0;
+      if (p.mode != TC_FLAT) {
+        const unsigned up = (unsigned)pair, img = up / (unsigned)pairs_per_img, t = up - img * (unsigned)pairs_per_img;
+        const unsigned ty = t / (unsigned)p.pairs_x;
+        n = p.n0 + (int)img;
+        y0 = (int)ty * 16;
+        x0 = (int)(t - ty * (unsigned)p.pairs_x) * 16;
+      }
+      const int nblk = a_per_tap ? kblocks : p.ncb;
+      for (int j = 0; j < nblk; ++j) {
+        mbar_wait(aempty + 8u * stage, phase ^ 1u);
+        if (lane == 0) {
+          const uint32_t dst = a_s + (uint32_t)stage * p.blk_bytes, fb = afull + 8u * stage;
+          mbar_expect_tx(fb, p.tx_bytes);
+          if (p.mode == TC_FLAT) {
+            tma_load_2d(dst, &tm_in, fb, j * 64, (int)((long long)p.n0 * p.H * p.W + pair * 256));
+          } else if (p.mode == TC_HALO) {
+            tma_load_4d(dst, &tm_in, fb, j * 64, x0 - 1, y0 - 1, n);
+          } else {
+            const int cb = j / 9, tap = j % 9;
+            tma_load_4d(dst, &tm_in, fb, cb * 64, x0 * p.stride + tap % 3 - 1, y0 * p.stride + tap / 3 - 1, n);
+          }
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 2) {
+    // ================= weight TMA =================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long pair = blockIdx.x; pair < total; pair += gridDim.x) {
+      for (int j = 0; j < kblocks; ++j) {
+        mbar_wait(wempty + 8u * stage, phase ^ 1u);
+        if (lane == 0) {
+          const uint32_t fb = wfull + 8u * stage;
+          mbar_expect_tx(fb, (uint32_t)p.N * 128u);
+          tma_load_2d(w_s + (uint32_t)stage * p.wblk_bytes, &tm_w, fb, 0, j * p.N);
+        }
+        __syncwarp();
+        if (++stage == p.wstages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    int astage = 0, wstage = 0, acc = 0;
+    uint32_t aphase = 0, wphase = 0, acc_phase = 0;
+    const uint64_t adesc0 = make_desc_base(p.sbo_a, 2u);   // 128-byte rows, SWIZZLE_128B
+    const uint64_t bdesc0 = make_desc_base(1024u, 2u);
+    const bool halo = p.mode == TC_HALO;
+    const uint32_t tile_units = p.tile_off >> 4;
+    for (long long pair = blockIdx.x; pair < total; pair += gridDim.x) {
+      mbar_wait(tempty + 8u * acc, acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d0 = tmem_base + (uint32_t)acc * 2u * p.N;
+      for (int j = 0; j < kblocks; ++j) {
+        const int tap = halo ? j % 9 : 0;
+        if (!halo || tap == 0) {
+          mbar_wait(afull + 8u * astage, aphase);
+        }
+        mbar_wait(wfull + 8u * wstage, wphase);
+        tc_fence_after();
+        if (elect_one()) {
+          uint64_t ad = adesc0 + (uint64_t)(((a_s + (uint32_t)astage * p.blk_bytes) & 0x3FFFFu) >> 4);
+          if (halo) ad += (uint64_t)(((tap / 3) * kBigHalo + (tap % 3)) * 8);   // (r * pitch + s) pixels of 128 bytes
+          const uint64_t wd = bdesc0 + (uint64_t)(((w_s + (uint32_t)wstage * p.wblk_bytes) & 0x3FFFFu) >> 4);
+          const uint32_t accum = j != 0;
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(d0 + (uint32_t)t * p.N, ad + (uint64_t)t * tile_units + 2 * k, wd + 2 * k, p.idesc, (accum | (uint32_t)k) ? 1u : 0u);
+          }
+          umma_commit(wempty + 8u * wstage);
+          if (!halo || tap == 8) umma_commit(aempty + 8u * astage);
+          if (j == kblocks - 1) umma_commit(tfull + 8u * acc);
+        }
+        __syncwarp();
+        if (++wstage == p.wstages) { wstage = 0; wphase ^= 1u; }
+        if (!halo || tap == 8) {
+          if (++astage == p.stages) { astage = 0; aphase ^= 1u; }
+        }
+      }
+      if (++acc == nacc) { acc = 0; acc_phase ^= 1u; }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue: group g drains M-tile g of every pair =================
+    const int q = warp & 3, g = (warp - 4) >> 2;
+    const int m = q * 32 + lane;
+    const int nchunks = p.N >> 4;
+    const unsigned hw = (unsigned)p.H * (unsigned)p.W;
+    int it = 0;
+    for (long long pair = blockIdx.x; pair < total; pair += gridDim.x, ++it) {
+      const int acc = nacc == 2 ? (it & 1) : 0;
+      const uint32_t acc_phase = (uint32_t)(nacc == 2 ? (it >> 1) : it) & 1u;
+      long long pix;
+      if (p.mode == TC_FLAT) {
+        const unsigned row = (unsigned)pair * 256u + (unsigned)g * 128u + (unsigned)m;
+        pix = row < (unsigned)p.nb * hw ? (long long)((unsigned)p.n0 * hw + row) : -1;
+      } else {
+        const unsigned up = (unsigned)pair, img = up / (unsigned)pairs_per_img, t = up - img * (unsigned)pairs_per_img;
+        const unsigned ty = t / (unsigned)p.pairs_x, tx = t - ty * (unsigned)p.pairs_x;
+        const int oy = (int)ty * 16 + (m >> 3), ox = (int)tx * 16 + g * 8 + (m & 7);
+        pix = (oy < p.H && ox < p.W) ? ((long long)(p.n0 + (int)img) * p.H + oy) * p.W + ox : -1;
+      }
+      mbar_wait(tfull + 8u * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 2u * p.N + (uint32_t)g * p.N;
+      uint32_t cur[16], nxt[16];
+      tmem_ld16_issue(taddr, cur);
+      tmem_ld_wait();
+      for (int c = 0; c < nchunks; ++c) {
+        const bool more = c + 1 < nchunks;
+        if (more) {
+          tmem_ld16_issue(taddr + 16u * (c + 1), nxt);
+        } else {
+          tc_fence_before();
+          mbar_arrive(tempty + 8u * acc);
+        }
+        if (pix >= 0 && c * 16 < p.cout) epilogue_chunk(cur, bias_s, c * 16, pix, p, -1);
+        if (more) {
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
 }  // namespace
 
 // ---- host side -----------------------------------------------------------------------------
@@ -608,14 +804,19 @@ static int pick_cb(int cin) { return cin % 64 == 0 ? 64 : (cin % 32 == 0 ? 32 : 
 // int8: channels (= bytes) per block
 static int pick_cb_s8(int cin) { return cin % 128 == 0 ? 128 : (cin % 64 == 0 ? 64 : (cin % 32 == 0 ? 32 : 0)); }
 
+// BIG variant (streamed weights): 64-channel blocks, Cout <= 256 in 16-column chunks, no partial sums
+static bool tc_big_supported(const uyd_conv &d) {
+  return d.cin % 64 == 0 && d.cout % 16 == 0 && d.cout <= 256 && !d.pre_buf_p1;
+}
+
 bool tc_supported(const uyd_conv &d, int in_pitch, int in_coff, int out_pitch, int out_coff, bool in_is_network_input) {
   if (in_is_network_input || d.depthwise) return false;
   if (!(d.k == 1 || d.k == 3) || !(d.stride == 1 || d.stride == 2)) return false;
   if (d.k == 1 && d.stride != 1) return false;
-  if (pick_cb(d.cin) == 0 || d.cout > 128 || d.cout < 4) return false;
+  if (pick_cb(d.cin) == 0 || d.cout < 4) return false;
   if (in_pitch % 8 || in_coff % 8 || out_pitch % 4 || out_coff % 4) return false;
   const int N = (d.cout + 15) / 16 * 16;
-  if ((size_t)d.cin * d.k * d.k * N * 2 > 150 * 1024) return false;
+  if (d.cout > 128 || (size_t)d.cin * d.k * d.k * N * 2 > 150 * 1024) return tc_big_supported(d);
   return true;
 }
 
@@ -663,6 +864,93 @@ void tc_pack_weights_s8(int cin, int cout, int k, const int8_t *w, void *dst_hos
           o[(((size_t)cb * taps + t) * N + n) * CB + c] = n < cout ? w[((size_t)n * cin + cb * CB + c) * taps + t] : (int8_t)0;
 }
 
+
+static int tc_prepare_big(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int ih, int iw, int max_batch, void *out_base,
+                          int out_pitch, int out_f32, const void *res_base, int res_pitch, void *w_dev, const float *bias_dev) {
+  TcParams &p = tc->p;
+  UYD_REQUIRE(tc_big_supported(d), UYD_E_UNSUPPORTED, "conv_tc big: cin %% 64, cout %% 16, cout <= 256");
+  UYD_REQUIRE(!res_base || ((res_pitch % 8) == 0 && (reinterpret_cast<uintptr_t>(res_base) & 15) == 0), UYD_E_UNSUPPORTED,
+              "conv_tc big: residual slice must be 16-byte aligned");
+  p.big = 1;
+  p.cb_bytes = 128;
+  p.ncb = d.cin / 64;
+  p.taps = d.k * d.k;
+  p.stride = d.stride;
+  p.N = d.cout;
+  p.cout = d.cout;
+  p.H = d.k == 1 ? ih : (ih + 2 - 3) / d.stride + 1;
+  p.W = d.k == 1 ? iw : (iw + 2 - 3) / d.stride + 1;
+  p.mode = d.k == 1 ? TC_FLAT : (d.stride == 1 ? TC_HALO : TC_PERTAP);
+  p.layout_type = 2u;
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  p.pairs_x = ceil_div(p.W, 16);
+  p.tiles_y = ceil_div(p.H, 16);
+  p.tiles_x = p.pairs_x;
+  if (p.mode == TC_HALO) {
+    p.tx_bytes = (uint32_t)kBigHalo * kBigHalo * 128u;
+    p.sbo_a = (uint32_t)kBigHalo * 128u;
+    p.tile_off = 8u * 128u;
+  } else if (p.mode == TC_PERTAP) {
+    p.tx_bytes = 256u * 128u;
+    p.sbo_a = 16u * 128u;
+    p.tile_off = 8u * 128u;
+  } else {
+    p.tx_bytes = 256u * 128u;
+    p.sbo_a = 1024u;
+    p.tile_off = 128u * 128u;
+  }
+  p.blk_bytes = (p.tx_bytes + 1023u) & ~1023u;
+  p.wblk_bytes = (uint32_t)p.N * 128u;   // N % 16 == 0 and >= 144: a multiple of 1024 whenever N % 8 == 0
+  p.wblk_bytes = (p.wblk_bytes + 1023u) & ~1023u;
+  const size_t tail = 256 + 1024 + 1024;  // barriers + bias
+  const size_t budget = 227 * 1024 - 1024 - tail;
+  int stages = p.mode == TC_HALO ? 2 : 3;
+  int wstages = (int)((budget - (size_t)stages * p.blk_bytes) / p.wblk_bytes);
+  if (wstages > 8) wstages = 8;
+  while (wstages < 3 && stages > 2) { --stages; wstages = (int)((budget - (size_t)stages * p.blk_bytes) / p.wblk_bytes); }
+  UYD_REQUIRE(wstages >= 2, UYD_E_UNSUPPORTED, "conv_tc big: no room for two weight stages (N = %d)", p.N);
+  // the space left after 3+ weight stages goes to activation stages
+  if (wstages > 4) {
+    const int extra = (int)((budget - (size_t)stages * p.blk_bytes - (size_t)4 * p.wblk_bytes) / p.blk_bytes);
+    if (extra > 0) { stages += extra > 2 ? 2 : extra; wstages = (int)((budget - (size_t)stages * p.blk_bytes) / p.wblk_bytes); if (wstages > 8) wstages = 8; }
+  }
+  if (stages > 4) stages = 4;
+  p.stages = stages;
+  p.wstages = wstages;
+  p.nacc = 4 * p.N <= 512 ? 2 : 1;
+  tc->smem = 1024 + (size_t)stages * p.blk_bytes + (size_t)wstages * p.wblk_bytes + tail;
+  p.out = out_base; p.out_pitch = out_pitch; p.out_f32 = out_f32;
+  p.res = reinterpret_cast<const __nv_bfloat16 *>(res_base); p.res_pitch = res_pitch;
+  p.bias = bias_dev; p.relu = d.relu;
+  tc->w_dev = w_dev;
+  const cuuint32_t one4[4] = {1, 1, 1, 1};
+  {  // weights [rows = ncb * taps * N][64 channels]: one box = one (channel block, tap) block
+    const cuuint64_t dims[2] = {64, (cuuint64_t)p.ncb * p.taps * p.N};
+    const cuuint64_t str[1] = {128};
+    const cuuint32_t box[2] = {64, (cuuint32_t)p.N};
+    if (int e = encode(&tc->tm_w, w_dev, 2, dims, str, box, one4, 128)) return e;
+  }
+  if (p.mode == TC_FLAT) {
+    const cuuint64_t dims[2] = {(cuuint64_t)d.cin, (cuuint64_t)max_batch * ih * iw};
+    const cuuint64_t str[1] = {(cuuint64_t)in_pitch * 2};
+    const cuuint32_t box[2] = {64, 256};
+    if (int e = encode(&tc->tm_in, in_base, 2, dims, str, box, one4, 128)) return e;
+  } else {
+    const cuuint64_t dims[4] = {(cuuint64_t)d.cin, (cuuint64_t)iw, (cuuint64_t)ih, (cuuint64_t)max_batch};
+    const cuuint64_t str[3] = {(cuuint64_t)in_pitch * 2, (cuuint64_t)iw * in_pitch * 2, (cuuint64_t)ih * iw * in_pitch * 2};
+    if (p.mode == TC_HALO) {
+      const cuuint32_t box[4] = {64, (cuuint32_t)kBigHalo, (cuuint32_t)kBigHalo, 1};
+      if (int e = encode(&tc->tm_in, in_base, 4, dims, str, box, one4, 128)) return e;
+    } else {
+      const cuuint32_t sd = (cuuint32_t)d.stride;
+      const cuuint32_t box[4] = {64, 16 * sd, 16 * sd, 1};
+      const cuuint32_t estr[4] = {1, sd, sd, 1};
+      if (int e = encode(&tc->tm_in, in_base, 4, dims, str, box, estr, 128)) return e;
+    }
+  }
+  return smem_optin(conv_tc_big_kernel, 227 * 1024);
+}
+
 // mode_override: -1 auto, else TC_*.  in_base/out_base/res_base: slice bases of image 0.
 // i8 != 0: int8 operands (weights already quantised), per-channel multiplier mult_dev,
 // out_kind 0/1/2 = bf16 / fp32 / int8 re-quantised with out_scale.
@@ -672,6 +960,11 @@ int tc_prepare(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int i
                float out_scale = 0.f, int out_kind = 0, int halo_pitch = 10) {
   TcParams &p = tc->p;
   memset(&p, 0, sizeof(p));
+  {
+    const int Np = (d.cout + 15) / 16 * 16;
+    if (!i8 && (d.cout > 128 || (size_t)d.cin * d.k * d.k * Np * 2 > 150 * 1024))
+      return tc_prepare_big(tc, d, in_base, in_pitch, ih, iw, max_batch, out_base, out_pitch, out_f32, res_base, res_pitch, w_dev, bias_dev);
+  }
   const int es = i8 ? 1 : 2;
   const int CB = i8 ? pick_cb_s8(d.cin) : pick_cb(d.cin);
   UYD_REQUIRE(CB, UYD_E_UNSUPPORTED, "conv_tc: cin %d is not a multiple of %d", d.cin, i8 ? 32 : 16);
@@ -819,6 +1112,15 @@ int tc_launch(const TcConv *tc, int n0, int nb, int sm_count, cudaStream_t s) {
   TcParams p = tc->p;
   p.n0 = n0;
   p.nb = nb;
+  if (p.big) {
+    p.total_tiles = p.mode == TC_FLAT ? ((long long)nb * p.H * p.W + 255) / 256 : (long long)nb * p.pairs_x * p.tiles_y;
+    if (p.total_tiles == 0) return UYD_OK;
+    UYD_REQUIRE((long long)(p.n0 + nb) * p.H * p.W < (1ll << 31) && p.total_tiles < (1ll << 24), UYD_E_UNSUPPORTED,
+                "conv_tc big: %d images of %dx%d exceed the kernel's 32-bit pixel index", p.n0 + nb, p.H, p.W);
+    const unsigned grid = (unsigned)(p.total_tiles < sm_count ? p.total_tiles : sm_count);
+    UYD_CUDA(launch_pdl(conv_tc_big_kernel, dim3(grid), dim3(kBigThreads), tc->smem, s, tc->tm_in, tc->tm_w, p));
+    return (int)cudaGetLastError();
+  }
   p.total_tiles = p.mode == TC_FLAT ? ((long long)nb * p.H * p.W + 127) / 128 : (long long)nb * p.tiles_x * p.tiles_y;
   if (p.total_tiles == 0) return UYD_OK;
   UYD_REQUIRE((long long)(p.n0 + nb) * p.H * p.W < (1ll << 31) && p.total_tiles < (1ll << 24), UYD_E_UNSUPPORTED,
@@ -839,6 +1141,7 @@ void tc_set_pre(TcConv *tc, const float *pre) { tc->p.pre = pre; }
 TcConv *tc_new() { return new TcConv(); }
 void tc_delete(TcConv *t) { delete t; }
 const char *tc_mode_name(const TcConv *t) {
+  if (t->p.big) return t->p.mode == TC_FLAT ? "big-flat" : (t->p.mode == TC_HALO ? "big-halo" : "big-pertap");
   return t->p.mode == TC_FLAT ? "flat" : (t->p.mode == TC_HALO ? "halo" : (t->p.mode == TC_PAIRS ? "pairs" : "pertap"));
 }
 
