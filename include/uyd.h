@@ -291,6 +291,13 @@ int uyd_compact_valid(uyd_ctx *ctx, const uyd_detection *dets, int n, uyd_detect
  * *d_bits with atomicMax (caller zeroes it): max calibration of the static input scales (qat.py:129-220). */
 int uyd_plan_slice_absmax(uyd_plan *plan, int buf, int coff, int c, int batch, unsigned int *d_bits, uyd_stream stream);
 
+/* Histogram of |x| over the first `batch` images of a bf16 slice, ADDED into d_hist[nbins] (caller zeroes it):
+ * bin = min(floor(|x| * inv_width), nbins - 1).  The collection step of the histogram / entropy calibrator that
+ * qat.py:91-126 configures by default (pytorch-quantization HistogramCalibrator: 2048 bins over [0, first max],
+ * the range grows by whole bins when a later batch exceeds it). */
+int uyd_plan_slice_histogram(uyd_plan *plan, int buf, int coff, int c, int batch, float inv_width, int nbins,
+                             unsigned int *d_hist, uyd_stream stream);
+
 /* Batched evaluation of the detections (the consumer of the gathered [N, 6] rows):
  *   counters[0..2] += small-object TP, FP, FN with the semantics of UninaValidator.update_metrics
  *     (trainer.py:210-265): boxes in pixels, "small" = width and height < size_thr, a match = same class
@@ -303,6 +310,14 @@ int uyd_plan_slice_absmax(uyd_plan *plan, int buf, int coff, int c, int batch, u
 int uyd_eval_update(uyd_ctx *ctx, const float *det, const int *count, int batch, int max_det, const float *gt,
                     const int *gt_count, int gt_max, float size_thr, float small_iou_thr, float match_iou_thr,
                     unsigned long long *counters, float *scores, uyd_stream stream);
+
+/* data_loader.SmallObjectMetric.update (data_loader.py:322-389), the training-time small-object metric, batched:
+ * pred [batch, max_det, 6] rows (x_c, y_c, w, h, conf, cls) and gt [batch, gt_max, 5] rows (cls, x_c, y_c, w, h), both
+ * normalised to the image, predictions in confidence order, count / gt_count valid rows per image.
+ * counters[0..2] += TP, FP, FN (greedy one-to-one matching in confidence order against the small ground truths). */
+int uyd_small_object_metric_update(uyd_ctx *ctx, const float *pred, const int *count, int batch, int max_det, const float *gt,
+                                   const int *gt_count, int gt_max, double size_thr, double iou_thr, double image_size,
+                                   unsigned long long *counters, uyd_stream stream);
 
 /* ------------------------------------------------------------------------------------
  * Camera-frame pre-processing in front of the plan (drop-in for cuda_preprocess.h:62-84; kernels

@@ -81,3 +81,49 @@ def conformal_scores(preds, gts, match_iou=0.5):
 
 def conformal_quantile(scores, alpha=0.10):
     return float(np.quantile(np.asarray(scores, np.float64), 1 - alpha))
+
+
+def small_object_metric_update(preds, gts, size_threshold=15, iou_threshold=0.5, image_size=640):
+    """data_loader.SmallObjectMetric.update (data_loader.py:322-389) restated with numpy fp32 scalars; returns
+    (tp, fp, fn) of the batch.  preds: list of [N,6] (x_c,y_c,w,h,conf,cls), gts: list of [G,5] (cls,x_c,y_c,w,h),
+    normalised.  PINNED: equal to the reference class imported from /root/reference and to
+    tests/golden/small_object_metric.npz generated from it (tests/test_oracle_pins.py)."""
+    f = np.float32
+
+    def small(w, h):
+        return float(w) * image_size < size_threshold and float(h) * image_size < size_threshold
+
+    def iou(a, b):
+        a1, a2, a3, a4 = a[0] - a[2] / f(2), a[1] - a[3] / f(2), a[0] + a[2] / f(2), a[1] + a[3] / f(2)
+        b1, b2, b3, b4 = b[0] - b[2] / f(2), b[1] - b[3] / f(2), b[0] + b[2] / f(2), b[1] + b[3] / f(2)
+        iw, ih = max(f(0), min(a3, b3) - max(a1, b1)), max(f(0), min(a4, b4) - max(a2, b2))
+        inter = iw * ih
+        union = (a3 - a1) * (a4 - a2) + (b3 - b1) * (b4 - b2) - inter
+        return 0.0 if union <= 0 else float(inter / union)
+
+    tp = fp = fn = 0
+    for p, g in zip(preds, gts):
+        p = np.asarray(p, f).reshape(-1, 6)
+        g = np.asarray(g, f).reshape(-1, 5)
+        sg = [r for r in g if small(r[3], r[4])]
+        if not sg:
+            continue
+        if len(p) == 0:
+            fn += len(sg)
+            continue
+        matched = set()
+        for r in p[np.argsort(-p[:, 4], kind="stable")]:
+            best, best_j = 0.0, -1
+            for j, q in enumerate(sg):
+                if j in matched or int(r[5]) != int(q[0]):
+                    continue
+                v = iou(r[:4], q[1:5])
+                if v > best:
+                    best, best_j = v, j
+            if best >= iou_threshold:
+                tp += 1
+                matched.add(best_j)
+            elif small(r[2], r[3]):
+                fp += 1
+        fn += len(sg) - len(matched)
+    return tp, fp, fn

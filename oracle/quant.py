@@ -65,3 +65,67 @@ def conv_int8(qx: np.ndarray, qw: np.ndarray, mult: np.ndarray, bias: np.ndarray
     if out_scale is not None:
         qy = np.clip(np.rint(y * np.float32(out_scale)), -127, 127).astype(np.int8)
     return acc32, y, qy
+
+
+# ---- histogram / entropy calibration, loop form (pytorch-quantization 2.1.2 calib/histogram.py restated) ----------------
+# PARITY UNPINNED: the library is not installable here; this follows its published algorithm statement by
+# statement and pins the product's vectorised version (unina-yolo-dla_b200/quant.py).
+def histogram_collect(batches, num_bins: int = 2048):
+    """HistogramCalibrator.collect over a list of arrays -> (hist int64, edges float64)."""
+    import numpy as np
+
+    hist, width = None, None
+    for x in batches:
+        a = np.abs(np.asarray(x, np.float32)).reshape(-1)
+        xmax = float(a.max())
+        if hist is None:
+            width = max(xmax, 1e-12) / num_bins
+            n = num_bins
+        else:
+            n = max(len(hist), int(np.ceil(xmax / width - 1e-9)))
+        idx = np.minimum((a * np.float32(1.0 / width)).astype(np.int64), n - 1)
+        h = np.bincount(idx, minlength=n).astype(np.int64)
+        if hist is not None:
+            h[: len(hist)] += hist
+        hist = h
+    return hist, np.arange(len(hist) + 1, dtype=np.float64) * width
+
+
+def amax_entropy_loops(hist, edges, num_bits=8, unsigned=False, stride=1, start_bin=128):
+    import numpy as np
+    from collections import Counter
+
+    bins = [float(v) for v in hist]
+    bins[0] = bins[1]
+    total = sum(bins)
+    nlev = 1 << (num_bits - 1 + int(unsigned))
+    divergences = []
+    for i in range(start_bin, len(bins) + 1, stride):
+        new_counts = [0.0] * nlev
+        space = np.linspace(0, i, num=nlev + 1)
+        dig = list(np.digitize(range(i), space) - 1)
+        for idx in range(i):
+            if bins[idx] == 0:
+                dig[idx] = -1
+        for idx, d in enumerate(dig):
+            if d != -1:
+                new_counts[d] += bins[idx]
+        for key, val in Counter(dig).items():
+            if key != -1:
+                new_counts[key] = new_counts[key] / val
+        new = [new_counts[d] if d != -1 else 0.0 for d in dig]
+        ref = list(bins[:i])
+        ref[-1] += sum(bins[i:])
+        assert round(sum(new) + sum(bins[i:])) == round(total) and round(sum(ref)) == round(total)
+        sn, sr = sum(new), sum(ref)
+        ent = 0.0
+        for p, q in zip(ref, new):
+            if p > 0:
+                if q == 0:
+                    ent = float("inf")
+                    break
+                ent += (p / sr) * np.log((p / sr) / (q / sn))
+        divergences.append(ent)
+    divergences = np.array(divergences)
+    last_argmin = len(divergences) - 1 - int(np.argmin(divergences[::-1]))
+    return float(edges[last_argmin * stride + start_bin])

@@ -536,6 +536,17 @@ extern "C" int uyd_plan_slice_absmax(uyd_plan *plan, int buf, int coff, int c, i
                        (cudaStream_t)stream);
 }
 
+extern "C" int uyd_plan_slice_histogram(uyd_plan *plan, int buf, int coff, int c, int batch, float inv_width, int nbins,
+                                        unsigned int *d_hist, uyd_stream stream) {
+  UYD_REQUIRE(plan && plan->finalized && d_hist, UYD_E_STATE, "uyd_plan_slice_histogram: plan not finalized / NULL output");
+  int e;
+  if ((e = check_slice(plan, buf, coff, c, "histogram"))) return e;
+  const Buffer &b = plan->bufs[buf];
+  UYD_REQUIRE(b.dtype == UYD_BF16 && batch > 0 && batch <= plan->max_batch, UYD_E_ARG, "histogram: bf16 slice, batch within the plan");
+  return abs_histogram_launch((const __nv_bfloat16 *)((char *)b.ptr + (size_t)coff * 2), b.c, (long long)batch * b.h * b.w, c, inv_width,
+                              nbins, d_hist, (cudaStream_t)stream);
+}
+
 extern "C" int uyd_plan_add_sppf_pool(uyd_plan *plan, int buf, int coff, int c) {
   UYD_REQUIRE(plan && !plan->finalized, UYD_E_STATE, "plan missing or finalized");
   int e;

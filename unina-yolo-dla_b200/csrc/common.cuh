@@ -115,6 +115,8 @@ int direct_conv_s8_dw_launch(const ConvArgs &a, const float *mult, float out_sca
 int quantize_s8_launch(const __nv_bfloat16 *in, int in_pitch, int8_t *out, int out_pitch, long long npix, int c, float scale,
                        cudaStream_t s);
 int absmax_launch(const __nv_bfloat16 *in, int in_pitch, long long npix, int c, unsigned int *out_bits, cudaStream_t s);
+int abs_histogram_launch(const __nv_bfloat16 *in, int in_pitch, long long npix, int c, float inv_width, int nbins, unsigned int *hist,
+                         cudaStream_t s);
 
 // pool_upsample.cu
 int sppf_pool_launch(__nv_bfloat16 *base, int n, int h, int w, int pitch, int c, cudaStream_t s);

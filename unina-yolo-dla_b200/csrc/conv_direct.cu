@@ -681,7 +681,44 @@ __global__ void __launch_bounds__(256) absmax_kernel(const __nv_bfloat16 *__rest
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out_bits, __float_as_uint(m));
 }
+
+// Histogram of |x| over a bf16 slice (histogram / entropy calibration, qat.py:91-126: the reference's default
+// calibrator is pytorch-quantization's HistogramCalibrator): bin = min(floor(|x| * inv_width), nbins - 1), counts
+// privatised per block in shared memory and flushed with one global atomic per non-empty bin.
+__global__ void __launch_bounds__(256) abs_histogram_kernel(const __nv_bfloat16 *__restrict__ in, int in_pitch, long long npix, int c,
+                                                            float inv_width, int nbins, unsigned int *__restrict__ hist) {
+  extern __shared__ unsigned int sh[];
+  for (int i = threadIdx.x; i < nbins; i += 256) sh[i] = 0u;
+  __syncthreads();
+  const int cg = c / 4;
+  for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < npix * cg; t += (long long)gridDim.x * 256) {
+    const int c0 = (int)(t % cg) * 4;
+    const uint2 raw = *reinterpret_cast<const uint2 *>(in + (t / cg) * in_pitch + c0);
+    const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&raw);
+    const float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]);
+    const float v[4] = {f0.x, f0.y, f1.x, f1.y};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int b = min((int)__fmul_rn(fabsf(v[i]), inv_width), nbins - 1);
+      atomicAdd(&sh[b], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nbins; i += 256)
+    if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
 }  // namespace
+
+int abs_histogram_launch(const __nv_bfloat16 *in, int in_pitch, long long npix, int c, float inv_width, int nbins, unsigned int *hist,
+                         cudaStream_t s) {
+  UYD_REQUIRE(c % 4 == 0 && in_pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 7) == 0, UYD_E_UNSUPPORTED,
+              "histogram: C %% 4 == 0 and 8-byte aligned slices");
+  UYD_REQUIRE(nbins > 0 && nbins <= 12288 && inv_width > 0.f, UYD_E_ARG, "histogram: 0 < nbins <= 12288, positive bin width");
+  long long blocks = (npix * (c / 4) + 255) / 256;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  abs_histogram_kernel<<<(unsigned)blocks, 256, (size_t)nbins * 4, s>>>(in, in_pitch, npix, c, inv_width, nbins, hist);
+  return (int)cudaGetLastError();
+}
 
 size_t direct_weight_bytes_s8(int cin, int cout, int k) { return (size_t)cin * cout * k * k; }
 

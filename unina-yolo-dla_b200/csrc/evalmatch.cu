@@ -123,8 +123,108 @@ __global__ void __launch_bounds__(kThreads) eval_update_kernel(const float *__re
   }
 }
 
+
+// ---- data_loader.SmallObjectMetric.update (data_loader.py:322-389), one CTA per image ------------------------
+// Rows in the reference's own format: pred (x_c, y_c, w, h, conf, cls) and gt (cls, x_c, y_c, w, h), normalised to the
+// image; predictions arrive in confidence order.  A "small" box has w * image_size and h * image_size below size_thr
+// (double arithmetic, like the Python floats of _is_small).  Per prediction: the best IoU (> 0, strict: the first
+// ground truth wins a tie) over the unmatched small ground truths of its class; IoU >= iou_thr -> TP and the ground
+// truth is matched, else FP iff the prediction itself is small.  FN = small ground truths left unmatched.
+__device__ __forceinline__ float iou_cxcywh(const float4 &a, const float4 &b) {  // data_loader.py:288-320, fp32 like the tensors
+  const float ax1 = __fsub_rn(a.x, __fmul_rn(a.z, 0.5f)), ay1 = __fsub_rn(a.y, __fmul_rn(a.w, 0.5f));
+  const float ax2 = __fadd_rn(a.x, __fmul_rn(a.z, 0.5f)), ay2 = __fadd_rn(a.y, __fmul_rn(a.w, 0.5f));
+  const float bx1 = __fsub_rn(b.x, __fmul_rn(b.z, 0.5f)), by1 = __fsub_rn(b.y, __fmul_rn(b.w, 0.5f));
+  const float bx2 = __fadd_rn(b.x, __fmul_rn(b.z, 0.5f)), by2 = __fadd_rn(b.y, __fmul_rn(b.w, 0.5f));
+  const float iw = fmaxf(0.f, __fsub_rn(fminf(ax2, bx2), fmaxf(ax1, bx1))), ih = fmaxf(0.f, __fsub_rn(fminf(ay2, by2), fmaxf(ay1, by1)));
+  const float inter = __fmul_rn(iw, ih);
+  const float uni = __fsub_rn(__fadd_rn(__fmul_rn(__fsub_rn(ax2, ax1), __fsub_rn(ay2, ay1)), __fmul_rn(__fsub_rn(bx2, bx1), __fsub_rn(by2, by1))), inter);
+  return uni <= 0.f ? 0.f : __fdiv_rn(inter, uni);
+}
+
+__global__ void __launch_bounds__(kThreads) small_object_metric_kernel(const float *__restrict__ pred, const int *__restrict__ cnt,
+                                                                       int max_det, const float *__restrict__ gt,
+                                                                       const int *__restrict__ gt_cnt, int gmax, double size_thr,
+                                                                       double iou_thr, double image_size,
+                                                                       unsigned long long *__restrict__ counters) {
+  __shared__ float4 gbox[kMaxGt];
+  __shared__ int gcls[kMaxGt];
+  __shared__ unsigned char gused[kMaxGt];
+  __shared__ int s_n;
+  __shared__ float w_iou[kThreads / 32];
+  __shared__ int w_idx[kThreads / 32];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int n = min(cnt[b], max_det), g = min(gt_cnt[b], min(gmax, kMaxGt));
+  if (tid == 0) {  // ordered compaction of the small ground truths (the order decides IoU ties)
+    int k = 0;
+    for (int j = 0; j < g; ++j) {
+      const float *q = gt + ((long long)b * gmax + j) * 5;
+      if ((double)q[3] * image_size < size_thr && (double)q[4] * image_size < size_thr) {
+        gbox[k] = make_float4(q[1], q[2], q[3], q[4]);
+        gcls[k] = (int)q[0];
+        gused[k] = 0;
+        ++k;
+      }
+    }
+    s_n = k;
+  }
+  __syncthreads();
+  const int ns = s_n;
+  if (ns == 0) return;  // no small objects in this image (data_loader.py:337-338)
+  int tp = 0, fp = 0;
+  for (int i = 0; i < n; ++i) {
+    const float *d = pred + ((long long)b * max_det + i) * 6;
+    const float4 pb = make_float4(d[0], d[1], d[2], d[3]);
+    const int pc = (int)d[5];
+    float best = 0.f;
+    int best_j = 0x7fffffff;
+    for (int j = tid; j < ns; j += kThreads) {
+      if (gused[j] || gcls[j] != pc) continue;
+      const float v = iou_cxcywh(pb, gbox[j]);
+      if (v > best) { best = v; best_j = j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oj = __shfl_xor_sync(0xffffffffu, best_j, o);
+      if (ov > best || (ov == best && oj < best_j)) { best = ov; best_j = oj; }
+    }
+    if ((tid & 31) == 0) { w_iou[tid >> 5] = best; w_idx[tid >> 5] = best_j; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < kThreads / 32; ++w)
+        if (w_iou[w] > best || (w_iou[w] == best && w_idx[w] < best_j)) { best = w_iou[w]; best_j = w_idx[w]; }
+      if ((double)best >= iou_thr) {
+        ++tp;
+        if (best_j != 0x7fffffff) gused[best_j] = 1;   // (iou_thr <= 0 with no candidate: the reference adds index -1)
+      } else if ((double)pb.z * image_size < size_thr && (double)pb.w * image_size < size_thr) {
+        ++fp;
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    int matched = 0;
+    for (int j = 0; j < ns; ++j) matched += gused[j];
+    atomicAdd(&counters[0], (unsigned long long)tp);
+    atomicAdd(&counters[1], (unsigned long long)fp);
+    atomicAdd(&counters[2], (unsigned long long)(ns - matched));
+  }
+}
+
 }  // namespace
 }  // namespace uyd
+
+extern "C" int uyd_small_object_metric_update(uyd_ctx *ctx, const float *pred, const int *count, int batch, int max_det, const float *gt,
+                                              const int *gt_count, int gt_max, double size_thr, double iou_thr, double image_size,
+                                              unsigned long long *counters, uyd_stream stream) {
+  (void)ctx;
+  UYD_REQUIRE(pred && count && gt && gt_count && counters && batch > 0 && max_det > 0 && gt_max > 0, UYD_E_ARG,
+              "uyd_small_object_metric_update: bad arguments");
+  UYD_REQUIRE(gt_max <= uyd::kMaxGt, UYD_E_UNSUPPORTED, "uyd_small_object_metric_update: at most %d ground truths per image", uyd::kMaxGt);
+  uyd::small_object_metric_kernel<<<batch, uyd::kThreads, 0, (cudaStream_t)stream>>>(pred, count, max_det, gt, gt_count, gt_max, size_thr,
+                                                                                      iou_thr, image_size, counters);
+  return (int)cudaGetLastError();
+}
 
 extern "C" int uyd_eval_update(uyd_ctx *ctx, const float *det, const int *count, int batch, int max_det, const float *gt,
                                const int *gt_count, int gt_max, float size_thr, float small_iou_thr, float match_iou_thr,

@@ -85,3 +85,84 @@ class DetectionEvaluator:
         return {"alpha": alpha, "coverage_target": 1 - alpha, "q_hat": q_hat, "dilation_factor": q_hat,
                 "num_calibration_samples": int(srt.numel()), "mean_nonconformity": float(s.mean()),
                 "std_nonconformity": float(s.std(unbiased=False))}
+
+
+class SmallObjectMetric:
+    """Drop-in for ``data_loader.SmallObjectMetric`` (data_loader.py:249-414): same constructor, ``reset`` /
+    ``update(predictions, ground_truths)`` / ``compute``, same keys; the matching runs on the GPU, one CTA per
+    image (csrc/evalmatch.cu ``small_object_metric_kernel``).  ``update`` takes the reference's lists
+    (``[N,6]`` rows x_c,y_c,w,h,conf,cls and ``[G,5]`` rows cls,x_c,y_c,w,h, normalised) or already padded device
+    tensors through ``update_batched``; ``from_xyxy_pixels`` converts ``predict`` rows."""
+
+    def __init__(self, size_threshold: int = 15, iou_threshold: float = 0.5, image_size: int = 640, device=None) -> None:
+        self.size_threshold, self.iou_threshold, self.image_size = size_threshold, iou_threshold, image_size
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.reset()
+
+    def reset(self) -> None:
+        self._counters = torch.zeros(3, dtype=torch.int64, device=self.device)
+
+    @property
+    def true_positives(self) -> int:
+        return int(self._counters[0])
+
+    @property
+    def false_positives(self) -> int:
+        return int(self._counters[1])
+
+    @property
+    def false_negatives(self) -> int:
+        return int(self._counters[2])
+
+    @staticmethod
+    def from_xyxy_pixels(det: torch.Tensor, image_size: float) -> torch.Tensor:
+        """[..., 6] rows (x1,y1,x2,y2,conf,cls) in pixels -> (x_c,y_c,w,h,conf,cls) normalised."""
+        out = det.clone()
+        out[..., 0] = (det[..., 0] + det[..., 2]) / 2 / image_size
+        out[..., 1] = (det[..., 1] + det[..., 3]) / 2 / image_size
+        out[..., 2] = (det[..., 2] - det[..., 0]) / image_size
+        out[..., 3] = (det[..., 3] - det[..., 1]) / image_size
+        return out
+
+    @torch.no_grad()
+    def update_batched(self, pred: torch.Tensor, cnt: torch.Tensor, gt: torch.Tensor, gt_cnt: torch.Tensor) -> None:
+        """pred [B, max_det, 6] in confidence order, cnt [B] int32, gt [B, G, 5], gt_cnt [B] int32: device tensors."""
+        assert pred.is_cuda and pred.dtype == torch.float32 and pred.is_contiguous() and pred.shape[2] == 6
+        assert gt.is_cuda and gt.dtype == torch.float32 and gt.is_contiguous() and gt.shape[2] == 5
+        assert cnt.dtype == torch.int32 and gt_cnt.dtype == torch.int32
+        dev = pred.device.index if pred.device.index is not None else torch.cuda.current_device()
+        check(_lib.lib().uyd_small_object_metric_update(
+            _lib.context(dev), C.c_void_p(pred.data_ptr()), C.c_void_p(cnt.data_ptr()), pred.shape[0], pred.shape[1],
+            C.c_void_p(gt.data_ptr()), C.c_void_p(gt_cnt.data_ptr()), gt.shape[1], float(self.size_threshold), float(self.iou_threshold),
+            float(self.image_size), C.c_void_p(self._counters.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+            "uyd_small_object_metric_update")
+
+    @torch.no_grad()
+    def update(self, predictions, ground_truths) -> None:
+        B = len(predictions)
+        if B == 0:
+            return
+        md = max(1, max(int(p.shape[0]) if p.numel() else 0 for p in predictions))
+        gm = max(1, max(int(g.shape[0]) if g.numel() else 0 for g in ground_truths))
+        pred = torch.zeros(B, md, 6, device=self.device)
+        gt = torch.zeros(B, gm, 5, device=self.device)
+        cnt = torch.zeros(B, dtype=torch.int32, device=self.device)
+        gcnt = torch.zeros(B, dtype=torch.int32, device=self.device)
+        for i, (p, g) in enumerate(zip(predictions, ground_truths)):
+            if p.numel():
+                p = p.to(self.device, torch.float32)
+                order = torch.sort(p[:, 4], descending=True, stable=True).indices   # data_loader.py:349-350
+                pred[i, : p.shape[0]] = p[order]
+                cnt[i] = p.shape[0]
+            if g.numel():
+                gt[i, : g.shape[0]] = g.to(self.device, torch.float32)
+                gcnt[i] = g.shape[0]
+        self.update_batched(pred, cnt, gt, gcnt)
+
+    def compute(self) -> dict:
+        tp, fp, fn = (int(v) for v in self._counters.tolist())
+        precision = tp / (tp + fp) if (tp + fp) > 0 else 0.0
+        recall = tp / (tp + fn) if (tp + fn) > 0 else 0.0
+        f1 = 2 * (precision * recall) / (precision + recall) if (precision + recall) > 0 else 0.0
+        return {"small_object_precision": precision, "small_object_recall": recall, "small_object_f1": f1,
+                "small_object_tp": tp, "small_object_fp": fp, "small_object_fn": fn}

@@ -120,6 +120,11 @@ class Plan:
         check(_lib.lib().uyd_plan_slice_absmax(self.handle, s.buf, s.coff, s.c, batch, C.c_void_p(out_bits.data_ptr()),
                                                self._stream()), "uyd_plan_slice_absmax")
 
+    def slice_histogram(self, s: Slice, batch: int, inv_width: float, hist: torch.Tensor) -> None:
+        """Adds the histogram of |x| over a bf16 slice into ``hist`` (int32 device vector, one entry per bin)."""
+        check(_lib.lib().uyd_plan_slice_histogram(self.handle, s.buf, s.coff, s.c, batch, inv_width, hist.numel(),
+                                                  C.c_void_p(hist.data_ptr()), self._stream()), "uyd_plan_slice_histogram")
+
     C3K_WIDTHS = (8, 16, 32)
 
     @staticmethod

@@ -649,34 +649,79 @@ class UninaYoloB200(nn.Module):
         return shift
 
     @torch.no_grad()
-    def calibrate_int8(self, frames: torch.Tensor, float_layers=(0, 1, 2), enable: bool = True) -> dict:
-        """Max calibration of the static INT8 scales (the reference's calibration pass, qat.py:129-220, never
-        materialises them): input amax of every conv = max |x| of its input over ``frames`` in the bf16
-        forward (one GPU reduction per conv input, uyd_plan_slice_absmax), weight amax = max |w|.  Returns
-        ``{conv name: (amax_in, amax_w)}`` and, with ``enable``, switches the INT8 path on."""
+    def calibrate_int8(self, frames: torch.Tensor, float_layers=(0, 1, 2), enable: bool = True, method: str = "max",
+                       batch_size: int = 8, percentile: float = 99.99) -> dict:
+        """Static INT8 scales from a calibration set (the reference's calibration pass, qat.py:129-220, never
+        materialises them).  ``frames`` [N,3,H,W] is walked in chunks of ``batch_size`` through the bf16 forward.
+          method "max"                     : amax = max |x| (one GPU reduction per conv input, uyd_plan_slice_absmax)
+          method "histogram" / "entropy"   : the reference's default (qat.py:91-126, 676-697): |x| histogram with 2048
+                                             bins per conv input on the GPU (uyd_plan_slice_histogram), KL-divergence
+                                             threshold search on the host (quant.amax_entropy)
+          method "percentile" / "mse"      : the other two amax rules of the same calibrator
+        Weights use the same method on the host.  Returns ``{conv name: (amax_in, amax_w)}`` and, with ``enable``,
+        switches the INT8 path on."""
+        from . import quant as Q
+
+        rule = {"histogram": "entropy"}.get(method, method)
+        if rule not in ("max", "entropy", "percentile", "mse"):
+            raise ValueError(f"unknown calibration method {method!r}")
         saved, self.quant = self.quant, None
         try:
-            x = self._prep(frames)
-            B, _, H, W = x.shape
-            dev = x.device.index if x.device.index is not None else torch.cuda.current_device()
+            x_all = self._prep(frames)
+            _, _, H, W = x_all.shape
+            B = min(batch_size, x_all.shape[0])
+            dev = x_all.device.index if x_all.device.index is not None else torch.cuda.current_device()
             p = self._build_plan(dev, B, H, W, fused=False, fusion=False, record_inputs=True)
-            p.run(x)
             names = [n for n, s in p.conv_inputs.items() if s.buf >= 0]
-            bits = torch.zeros(len(names), dtype=torch.int32, device=x.device)
-            for i, n in enumerate(names):
-                p.slice_absmax(p.conv_inputs[n], B, bits[i:i + 1])
-            vals = bits.view(torch.float32).cpu().tolist()
-            convs = {n: m for n, m in self.named_modules() if isinstance(m, nn.Conv2d)}
-            amax = {n: (max(v, 1e-6), float(convs[n].weight.detach().abs().max())) for n, v in zip(names, vals)}
             det = self.model[-1]
             dfl_name = getattr(det.dfl.conv, "_uyd_name", "")
-            if dfl_name in p.conv_inputs:  # input of the DFL projection: the softmax probabilities of the box logits
-                pm = 0.0
-                for lvl, h in enumerate(p.heads):
-                    t = torch.empty(B, h.c, h.h, h.w, dtype=torch.float32, device=x.device)
-                    p.export_head(lvl, t, B)
-                    pm = max(pm, float(t[:, :4 * det.reg_max].reshape(B, 4, det.reg_max, -1).softmax(2).max()))
-                amax[dfl_name] = (pm, float(det.reg_max - 1))
+            vmax = [0.0] * len(names)
+            cal = [Q.HistogramCalibrator() for _ in names] if rule != "max" else None
+            dfl_cal, dfl_max = (Q.HistogramCalibrator() if rule != "max" else None), 0.0
+            for b0 in range(0, x_all.shape[0], B):
+                x = x_all[b0:b0 + B].contiguous()
+                nb = x.shape[0]
+                p.run(x)
+                bits = torch.zeros(len(names), dtype=torch.int32, device=x.device)
+                for i, n in enumerate(names):
+                    p.slice_absmax(p.conv_inputs[n], nb, bits[i:i + 1])
+                vals = bits.view(torch.float32).cpu().tolist()
+                vmax = [max(a, b) for a, b in zip(vmax, vals)]
+                if cal is not None:
+                    nbins = [c.bins_for(v) for c, v in zip(cal, vals)]
+                    if max(nbins) > 12288:
+                        raise _lib.UydError("histogram calibration: a later batch exceeds 6x the first batch's range; "
+                                            "put representative frames first")
+                    offs = np.concatenate(([0], np.cumsum(nbins)))
+                    hist = torch.zeros(int(offs[-1]), dtype=torch.int32, device=x.device)
+                    for i, n in enumerate(names):
+                        p.slice_histogram(p.conv_inputs[n], nb, 1.0 / cal[i].width, hist[int(offs[i]):int(offs[i + 1])])
+                    h = hist.cpu().numpy()
+                    for i in range(len(names)):
+                        cal[i].add(h[int(offs[i]):int(offs[i + 1])])
+                if dfl_name in p.conv_inputs:  # input of the DFL projection: the softmax probabilities of the box logits
+                    for lvl, hd in enumerate(p.heads):
+                        t = torch.empty(nb, hd.c, hd.h, hd.w, dtype=torch.float32, device=x.device)
+                        p.export_head(lvl, t, nb)
+                        pr = t[:, :4 * det.reg_max].reshape(nb, 4, det.reg_max, -1).softmax(2)
+                        dfl_max = max(dfl_max, float(pr.max()))
+                        if dfl_cal is not None:
+                            dfl_cal.collect_host(pr.cpu().numpy())
+            convs = {n: m for n, m in self.named_modules() if isinstance(m, nn.Conv2d)}
+
+            def w_amax(w):
+                if rule == "max":
+                    return float(w.detach().abs().max())
+                c = Q.HistogramCalibrator()
+                c.collect_host(w.detach().float().cpu().numpy())
+                return c.compute_amax(rule, percentile)
+
+            amax = {}
+            for i, n in enumerate(names):
+                a_in = vmax[i] if rule == "max" else cal[i].compute_amax(rule, percentile)
+                amax[n] = (max(a_in, 1e-6), w_amax(convs[n].weight))
+            if dfl_name in p.conv_inputs:
+                amax[dfl_name] = (dfl_max if rule == "max" else dfl_cal.compute_amax(rule, percentile), float(det.reg_max - 1))
         finally:
             self.quant = saved
         if enable:
