@@ -342,6 +342,25 @@ int uyd_preprocess_bgra_resize_batch(const uint8_t *d_input, float *d_output, in
                                      int src_width, int src_height, int src_pitch, int dst_width, int dst_height,
                                      uyd_norm_params params, uyd_stream stream);
 
+/* f-1 as SURVEY 8f ranks it: camera bytes feed model.0 DIRECTLY.  The fused stem (uyd_plan_add_stem2 / _pw, which
+ * must be the plan's first op) reads the packed BGRA pixels -- bilinearly resampled with the half-pixel rule of
+ * preprocess_bgra_resize (cuda_preprocess.cu:140-199) when the frame extent differs from the plan's input -- or the
+ * NV12 planes (cuda_preprocess.cu:207-253, frame extent == plan input), normalises ((v / 255) - mean) / std on load
+ * and never writes a CHW fp32 tensor (4.9 MB written + read back per 640 x 640 frame otherwise).
+ * y: decoded output [batch, no, a_total] for plans whose head ops decode in their epilogue, else NULL. */
+enum { UYD_CAM_BGRA = 1, UYD_CAM_NV12 = 2 };
+typedef struct uyd_camera_frames {
+  int format;                 /* UYD_CAM_*                                                         */
+  int width, height;          /* camera frame extent in pixels                                     */
+  int pitch, uv_pitch;        /* row pitch in bytes of the BGRA pixels / Y plane, and of the UV plane */
+  long long frame_stride;     /* bytes between consecutive frames of the batch (data)              */
+  long long uv_frame_stride;  /* ... (uv)                                                          */
+  const uint8_t *data;        /* device: BGRA pixels, or the Y plane                               */
+  const uint8_t *uv;          /* device: interleaved U, V plane (NV12), else NULL                  */
+  uyd_norm_params norm;
+} uyd_camera_frames;
+int uyd_plan_run_camera(uyd_plan *plan, const uyd_camera_frames *frames, int batch, float *y, uyd_stream stream);
+
 /* Plain device-to-device copy on `stream` (lets a host binding without a CUDA runtime of
  * its own read plan buffers into memory it owns). */
 int uyd_memcpy_d2d(void *dst, const void *src, size_t bytes, uyd_stream stream);

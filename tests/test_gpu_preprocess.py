@@ -96,3 +96,49 @@ def test_preprocessed_camera_frame_feeds_the_model():
     d0, c0 = m.predict_batched(pre.bgra(cam), graph=False)
     d1, c1 = m.predict_batched(rgb, graph=False)
     assert int(c0.sum()) > 0 and torch.equal(c0, c1) and torch.equal(d0, d1)
+
+
+def test_camera_bytes_feed_the_stem_directly(ref):
+    """f-1: uyd_plan_run_camera (BGRA / BGRA + bilinear resize / NV12 read by the stem itself, no CHW fp32 tensor) vs
+    the two-step path through the REFERENCE's own pre-processing kernels + the fp32 forward."""
+    import unina_yolo_dla_b200 as uyd
+    from unina_yolo_dla_b200 import preprocess as pre
+
+    m = uyd.UninaYoloB200.from_yaml().init_synthetic(seed=0).cuda()
+    norm = pre.norm_params()                                        # ImageNet mean / std
+    # (a) BGRA at the model's extent: the same IEEE expression per pixel -> bit-identical prediction
+    cam = _frames(3, 320, 320, 7).cuda()
+    want_in = torch.empty(3, 3, 320, 320, device="cuda")
+    for b in range(3):
+        assert ref.preprocess_bgra(cam[b].data_ptr(), want_in[b].data_ptr(), 320, 320, 320 * 4, RefNorm(*IMAGENET), None) == 0
+    y_ref = m(want_in, raw_heads=False)
+    y_cam = m.forward_camera(cam, norm=norm)
+    torch.cuda.synchronize()
+    assert torch.equal(y_cam, y_ref)
+    # plain x / 255 (the YAML model's own pre-process) equals the uint8 NCHW path
+    rgb = cam[..., [2, 1, 0]].permute(0, 3, 1, 2).contiguous()
+    assert torch.equal(m.forward_camera(cam), m(rgb, raw_heads=False))
+    # (b) 1280 x 720 -> 640 x 640 bilinear inside the stem vs the reference resize kernel (fma contraction only)
+    big = _frames(2, 720, 1280, 8).cuda()
+    want_in = torch.empty(2, 3, 640, 640, device="cuda")
+    for b in range(2):
+        assert ref.preprocess_bgra_resize(big[b].data_ptr(), want_in[b].data_ptr(), 1280, 720, 1280 * 4, 640, 640, RefNorm(*IMAGENET), None) == 0
+    y_ref = m(want_in, raw_heads=False)
+    y_cam = m.forward_camera(big, size=(640, 640), norm=norm)
+    torch.cuda.synchronize()
+    assert float((y_cam[:, :4] - y_ref[:, :4]).abs().max() / y_ref[:, :4].abs().max()) <= 2e-3
+    assert float((y_cam[:, 4:] - y_ref[:, 4:]).abs().max()) <= 2e-3
+    # (c) NV12
+    g = torch.Generator().manual_seed(9)
+    yp = torch.randint(0, 256, (2, 320, 320), generator=g, dtype=torch.uint8).cuda()
+    uvp = torch.randint(0, 256, (2, 160, 320), generator=g, dtype=torch.uint8).cuda()
+    want_in = torch.empty(2, 3, 320, 320, device="cuda")
+    for b in range(2):
+        assert ref.preprocess_nv12(yp[b].data_ptr(), uvp[b].data_ptr(), want_in[b].data_ptr(), 320, 320, 320, 320, RefNorm(*IMAGENET), None) == 0
+    y_ref = m(want_in, raw_heads=False)
+    y_cam = m.forward_camera(yp, norm=norm, uv=uvp)
+    torch.cuda.synchronize()
+    assert float((y_cam[:, :4] - y_ref[:, :4]).abs().max() / y_ref[:, :4].abs().max()) <= 2e-3
+    assert float((y_cam[:, 4:] - y_ref[:, 4:]).abs().max()) <= 2e-3
+    det, cnt = m.predict_camera(cam, conf=0.05)
+    assert det.shape == (3, 300, 6) and cnt.shape == (3,)

@@ -47,6 +47,16 @@ class NormParams(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("mean_r", "mean_g", "mean_b", "std_r", "std_g", "std_b")]
 
 
+class CameraFrames(C.Structure):
+    """uyd_camera_frames (include/uyd.h)."""
+    _fields_ = [("format", C.c_int), ("width", C.c_int), ("height", C.c_int), ("pitch", C.c_int), ("uv_pitch", C.c_int),
+                ("frame_stride", C.c_longlong), ("uv_frame_stride", C.c_longlong), ("data", C.c_void_p), ("uv", C.c_void_p),
+                ("norm", NormParams)]
+
+
+CAM_BGRA, CAM_NV12 = 1, 2
+
+
 class Detection(C.Structure):
     """Layout-identical to the reference GpuDetection (gpu_postprocess.h:27-33)."""
     _fields_ = [("x1", C.c_float), ("y1", C.c_float), ("x2", C.c_float), ("y2", C.c_float),
@@ -118,6 +128,7 @@ SIGNATURES = {
                                   C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "uyd_small_object_metric_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                                  C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
+    "uyd_plan_run_camera": (C.c_int, [C.c_void_p, C.POINTER(CameraFrames), C.c_int, C.c_void_p, C.c_void_p]),
     "uyd_memcpy_d2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
 }
 

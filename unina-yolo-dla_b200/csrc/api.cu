@@ -118,6 +118,10 @@ struct StemArgs {
   const uint32_t *wfrag;
   const float *bias;
   int n, ih, iw, oh, ow, out_pitch, u8, pw;
+  int cam, src_w, src_h, src_pitch, uv_pitch;
+  long long frame_stride, uv_frame_stride;
+  const uint8_t *uv;
+  float mean[3], stdv[3];
 };
 bool stem_fused_supported(int c0, int c1, int ih, int iw, int out_pitch, int out_coff);
 void stem_fused_pack(const float *w0, const float *b0, const float *w1, const float *b1, const float *w2, const float *b2,
@@ -179,6 +183,7 @@ struct uyd_plan {
   size_t bytes = 0;
   void *arena = nullptr;
   float *profile_y = nullptr;          // decoded output used by uyd_plan_profile (uyd_plan_set_profile_output)
+  uyd_camera_frames cam{};            // frames of the running uyd_plan_run_camera call (x_kind 3)
   int timed_op = -1, timed_used = 0;  // uyd_plan_set_timed_op
   std::vector<cudaEvent_t> timed_ev;
 };
@@ -740,6 +745,13 @@ static int launch_op(uyd_plan *plan, const Op &o, const void *x, int x_kind, int
       a.in = x; a.out = (__nv_bfloat16 *)slice_ptr(plan, o.out_buf, o.out_coff);
       a.wfrag = (const uint32_t *)o.w_dev; a.bias = o.b_dev;
       a.n = batch; a.ih = plan->in_h; a.iw = plan->in_w; a.oh = ob.h; a.ow = ob.w; a.out_pitch = ob.c; a.u8 = x_kind == 2; a.pw = o.c;
+      if (x_kind == 3) {
+        const uyd_camera_frames &c = plan->cam;
+        a.cam = c.format; a.src_w = c.width; a.src_h = c.height; a.src_pitch = c.pitch; a.uv_pitch = c.uv_pitch;
+        a.frame_stride = c.frame_stride; a.uv_frame_stride = c.uv_frame_stride; a.uv = c.uv;
+        a.mean[0] = c.norm.mean_r; a.mean[1] = c.norm.mean_g; a.mean[2] = c.norm.mean_b;
+        a.stdv[0] = c.norm.std_r; a.stdv[1] = c.norm.std_g; a.stdv[2] = c.norm.std_b;
+      }
       e = stem_fused_launch(a, s);
     } else if (o.kind == OP_CHAIN) {
       UYD_REQUIRE(y || o.chain.out_buf >= 0, UYD_E_ARG, "this plan decodes in its head kernels: run it with uyd_plan_run_decoded");
@@ -810,6 +822,23 @@ extern "C" int uyd_plan_run_decoded(uyd_plan *plan, const void *x, int x_dtype, 
   UYD_REQUIRE(x_dtype == UYD_F32 || x_dtype == UYD_U8, UYD_E_ARG, "uyd_plan_run_decoded: x_dtype must be UYD_F32 or UYD_U8");
   UYD_REQUIRE(y, UYD_E_ARG, "uyd_plan_run_decoded: y is NULL");
   return run_ops(plan, x, x_dtype == UYD_F32 ? 1 : 2, batch, stream, y);
+}
+
+extern "C" int uyd_plan_run_camera(uyd_plan *plan, const uyd_camera_frames *f, int batch, float *y, uyd_stream stream) {
+  UYD_REQUIRE(plan && plan->finalized && f && f->data, UYD_E_ARG, "uyd_plan_run_camera: plan not finalized / NULL frames");
+  UYD_REQUIRE(!plan->ops.empty() && plan->ops[0].kind == OP_STEM2, UYD_E_UNSUPPORTED,
+              "uyd_plan_run_camera: the plan must start with the fused stem (uyd_plan_add_stem2 / _pw)");
+  UYD_REQUIRE(f->format == UYD_CAM_BGRA || f->format == UYD_CAM_NV12, UYD_E_ARG, "uyd_plan_run_camera: unknown frame format %d", f->format);
+  UYD_REQUIRE(f->width > 0 && f->height > 0 && f->norm.std_r != 0.f && f->norm.std_g != 0.f && f->norm.std_b != 0.f, UYD_E_ARG, "uyd_plan_run_camera: bad extent or zero std");
+  if (f->format == UYD_CAM_BGRA) {
+    UYD_REQUIRE(f->pitch >= 4 * f->width && f->pitch % 4 == 0 && f->frame_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(f->data) & 3) == 0,
+                UYD_E_ARG, "uyd_plan_run_camera: BGRA pixels must be 4-byte aligned (pitch %% 4 == 0)");
+  } else {
+    UYD_REQUIRE(f->uv && f->pitch >= f->width && f->uv_pitch >= f->width && f->width == plan->in_w && f->height == plan->in_h, UYD_E_ARG,
+                "uyd_plan_run_camera: NV12 needs the UV plane and a frame of the plan's input extent (%d x %d)", plan->in_w, plan->in_h);
+  }
+  plan->cam = *f;
+  return run_ops(plan, f->data, 3, batch, stream, y);
 }
 
 // Times every op separately with CUDA events on `stream` (one pass, ops serialised as in a

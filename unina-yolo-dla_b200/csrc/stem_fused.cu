@@ -26,6 +26,12 @@ struct StemArgs {
   const float *bias;      // [16 | 32]
   int n, ih, iw, oh, ow, out_pitch, u8;
   int pw;  // 1: the 1x1 Conv(32,16) follows in the same launch (second-generation kernel only); out has 16 channels
+  // camera frames straight into the patch (no CHW fp32 tensor in HBM): cam = 1 packed BGRA (bilinear
+  // resize when the frame extent differs from ih x iw), 2 = NV12; `in` = BGRA pixels / Y plane
+  int cam, src_w, src_h, src_pitch, uv_pitch;
+  long long frame_stride, uv_frame_stride;
+  const uint8_t *uv;
+  float mean[3], stdv[3];  // r, g, b
 };
 
 namespace {
@@ -53,6 +59,46 @@ __device__ __forceinline__ void split_bf16(float2 v, uint32_t &hi, uint32_t &lo)
   const float2 hf = __bfloat1622float2(h);
   hi = *reinterpret_cast<uint32_t *>(&h);
   lo = pack_bf16(v.x - hf.x, v.y - hf.y);
+}
+
+struct CamIn {};  // TIn tag of the camera instantiations of stem_v2_kernel
+
+// One model-input pixel (iy, ix) from the camera frame, normalised like cuda_preprocess.cu:99-253:
+// ((v / 255) - mean) / std with IEEE divisions; BGRA bilinear taps and BT.601 NV12 in the reference's operand order.
+__device__ __forceinline__ float cam_norm(float v, float mean, float stdv) { return __fdiv_rn(__fsub_rn(__fdiv_rn(v, 255.0f), mean), stdv); }
+
+__device__ __forceinline__ void cam_pixel(const StemArgs &a, const uint8_t *frame, const uint8_t *uvp, int iy, int ix, float (&rgb)[3]) {
+  float r, g, b;
+  if (a.cam == 2) {
+    const float Y = frame[(long long)iy * a.src_pitch + ix];
+    const uint8_t *q = uvp + (long long)(iy / 2) * a.uv_pitch + (ix / 2) * 2;
+    const float U = q[0] - 128.0f, V = q[1] - 128.0f;
+    r = Y + 1.402f * V;
+    g = Y - 0.344136f * U - 0.714136f * V;
+    b = Y + 1.772f * U;
+    r = fmaxf(0.0f, fminf(255.0f, r)); g = fmaxf(0.0f, fminf(255.0f, g)); b = fmaxf(0.0f, fminf(255.0f, b));
+  } else if (a.src_w == a.iw && a.src_h == a.ih) {
+    const uint32_t px = *reinterpret_cast<const uint32_t *>(frame + (long long)iy * a.src_pitch + 4 * ix);
+    b = (float)(px & 0xFF); g = (float)((px >> 8) & 0xFF); r = (float)((px >> 16) & 0xFF);
+  } else {
+    const float ratio_x = (float)a.src_w / a.iw, ratio_y = (float)a.src_h / a.ih;
+    const float sx = fmaxf(0.0f, fminf((ix + 0.5f) * ratio_x - 0.5f, a.src_w - 1.0f));
+    const float sy = fmaxf(0.0f, fminf((iy + 0.5f) * ratio_y - 0.5f, a.src_h - 1.0f));
+    const int xa = (int)sx, ya = (int)sy, xb = min(xa + 1, a.src_w - 1), yb = min(ya + 1, a.src_h - 1);
+    const float fx = sx - xa, fy = sy - ya;
+    const float waa = (1.0f - fx) * (1.0f - fy), wab = fx * (1.0f - fy), wba = (1.0f - fx) * fy, wbb = fx * fy;
+    const uint8_t *ra = frame + (long long)ya * a.src_pitch, *rb = frame + (long long)yb * a.src_pitch;
+    const uint32_t paa = *reinterpret_cast<const uint32_t *>(ra + 4 * xa), pab = *reinterpret_cast<const uint32_t *>(ra + 4 * xb);
+    const uint32_t pba = *reinterpret_cast<const uint32_t *>(rb + 4 * xa), pbb = *reinterpret_cast<const uint32_t *>(rb + 4 * xb);
+    auto mix = [&](int sh) {
+      return waa * (float)((paa >> sh) & 0xFF) + wab * (float)((pab >> sh) & 0xFF) + wba * (float)((pba >> sh) & 0xFF) +
+             wbb * (float)((pbb >> sh) & 0xFF);
+    };
+    r = mix(16); g = mix(8); b = mix(0);
+  }
+  rgb[0] = cam_norm(r, a.mean[0], a.stdv[0]);
+  rgb[1] = cam_norm(g, a.mean[1], a.stdv[1]);
+  rgb[2] = cam_norm(b, a.mean[2], a.stdv[2]);
 }
 
 template <typename TIn>
@@ -296,7 +342,8 @@ __global__ void __launch_bounds__(stemv2::kThreads, PERSIST ? 2 : 3) stem_v2_ker
   // thread (pj, prl): column vector pj of patch rows prl, prl + 15 and (prl < 5) prl + 30 of each channel
   constexpr int kVecPerRow = kInW / 4, kRowLanes = 15;  // 17 vectors per row, 255 loading threads
   static_assert(2 * kRowLanes <= kInH && 3 * kRowLanes >= kInH && kRowLanes * kVecPerRow <= kThreads, "patch load map");
-  const TIn *img = reinterpret_cast<const TIn *>(a.in) + (long long)n * 3 * a.ih * a.iw;
+  constexpr bool kCam = std::is_same<TIn, CamIn>::value;
+  const TIn *img = reinterpret_cast<const TIn *>(a.in) + (kCam ? 0ll : (long long)n * 3 * a.ih * a.iw);
   asm volatile("" : "+l"(img));  // keep the per-load address arithmetic 32-bit: one IMAD.WIDE.U32 on this base
   const int pj = tid % kVecPerRow, prl = tid / kVecPerRow;
   const int ix = ix0 + 4 * pj;
@@ -311,6 +358,22 @@ __global__ void __launch_bounds__(stemv2::kThreads, PERSIST ? 2 : 3) stem_v2_ker
     off[k] = (unsigned)(iy * a.iw + ix);  // meaningful only when ok[k]
   }
   uint4 pv[3][3];
+  if constexpr (kCam) {  // camera bytes -> normalised fp32 bit patterns of the four columns of every row this thread owns
+    const uint8_t *frame = reinterpret_cast<const uint8_t *>(a.in) + (long long)n * a.frame_stride;
+    const uint8_t *uvp = a.uv ? a.uv + (long long)n * a.uv_frame_stride : nullptr;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      float px[4][3];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        px[j][0] = px[j][1] = px[j][2] = 0.f;
+        if (ok[k]) cam_pixel(a, frame, uvp, iy0 + prl + kRowLanes * k, ix + j, px[j]);
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        pv[c][k] = make_uint4(__float_as_uint(px[0][c]), __float_as_uint(px[1][c]), __float_as_uint(px[2][c]), __float_as_uint(px[3][c]));
+    }
+  } else {
 #pragma unroll
   for (int c = 0; c < 3; ++c)
 #pragma unroll
@@ -322,6 +385,7 @@ __global__ void __launch_bounds__(stemv2::kThreads, PERSIST ? 2 : 3) stem_v2_ker
         else pv[c][k].x = __ldg(reinterpret_cast<const unsigned int *>(src));
       }
     }
+  }
 #pragma unroll
   for (int it = 0; it < kWIters; ++it) {
     const int i = tid + it * kThreads;
@@ -336,7 +400,7 @@ __global__ void __launch_bounds__(stemv2::kThreads, PERSIST ? 2 : 3) stem_v2_ker
       for (int c = 0; c < 3; ++c) {
         const uint4 v = pv[c][k];
         uint4 o;
-        if (sizeof(TIn) == 4) {  // round to nearest tf32: the mma reads the upper 19 bits
+        if (sizeof(TIn) == 4 || kCam) {  // round to nearest tf32: the mma reads the upper 19 bits
           o = ok[k] ? make_uint4(v.x + 0x1000u, v.y + 0x1000u, v.z + 0x1000u, v.w + 0x1000u) : v;
         } else {                 // x / 255 exactly as the float pre-process computes it, then the same rounding
           auto cv = [&](uint32_t b) { return ok[k] ? __float_as_uint(div255((float)b)) + 0x1000u : 0u; };
@@ -519,6 +583,10 @@ static int stem_v2_launch(const StemArgs &a0, cudaStream_t s) {
   // persistent CTAs pay off once there are several tiles per CTA (batch-1 frames keep one tile per CTA)
   const bool pers = persist && tiles >= 8 * sms;
   using namespace stemv2;
+  if (a.cam) {
+    if (a.pw) return pers ? go(stem_v2_kernel<CamIn, true, true>, true) : go(stem_v2_kernel<CamIn, true, false>, false);
+    return pers ? go(stem_v2_kernel<CamIn, false, true>, true) : go(stem_v2_kernel<CamIn, false, false>, false);
+  }
   if (a.u8) {
     if (a.pw) return pers ? go(stem_v2_kernel<uint8_t, true, true>, true) : go(stem_v2_kernel<uint8_t, true, false>, false);
     return pers ? go(stem_v2_kernel<uint8_t, false, true>, true) : go(stem_v2_kernel<uint8_t, false, false>, false);
@@ -529,7 +597,7 @@ static int stem_v2_launch(const StemArgs &a0, cudaStream_t s) {
 
 int stem_fused_launch(const StemArgs &a, cudaStream_t s) {
   static const bool legacy = [] { const char *v = getenv("UYD_STEM_LEGACY"); return v && *v == '1'; }();
-  if (!legacy || a.pw) return stem_v2_launch(a, s);
+  if (!legacy || a.pw || a.cam) return stem_v2_launch(a, s);
   const size_t smem = (size_t)2 * 3 * kInH * kInW * 2 + (size_t)(kL0Px + 19) * kL0Pitch * 2 + (6 + 36) * 64 * 4 + 48 * 4;
   if (int e = smem_optin(stem_fused_kernel<float>, smem)) return e;
   if (int e = smem_optin(stem_fused_kernel<uint8_t>, smem)) return e;

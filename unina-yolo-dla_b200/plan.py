@@ -242,6 +242,11 @@ class Plan:
         fn = _lib.lib().uyd_plan_run if x.dtype == torch.float32 else _lib.lib().uyd_plan_run_u8
         check(fn(self.handle, C.c_void_p(x.data_ptr()), x.shape[0], self._stream()), "uyd_plan_run")
 
+    def run_camera(self, frames: "_lib.CameraFrames", batch: int, y: torch.Tensor | None = None) -> None:
+        """Runs every op on camera frames (packed BGRA / NV12 device bytes): the stem normalises and resamples on load."""
+        check(_lib.lib().uyd_plan_run_camera(self.handle, C.byref(frames), batch, C.c_void_p(y.data_ptr()) if y is not None else None,
+                                             self._stream()), "uyd_plan_run_camera")
+
     def profile(self, x: torch.Tensor, y: torch.Tensor | None = None) -> list[float]:
         """Per-op milliseconds of one pass (CUDA events around every op)."""
         assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()

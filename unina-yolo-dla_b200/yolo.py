@@ -748,6 +748,47 @@ class UninaYoloB200(nn.Module):
             xs.append(t)
         return y, xs
 
+    @torch.no_grad()
+    def forward_camera(self, frames: torch.Tensor, size=None, norm=None, uv: torch.Tensor | None = None) -> torch.Tensor:
+        """Camera bytes straight into the stem (replaces preprocess_bgra_resize / preprocess_nv12 +
+        the CHW fp32 tensor, perception_node.cpp:604-612): ``frames`` uint8 device ``[B,H,W,4]`` packed BGRA, resampled
+        bilinearly to ``size=(H',W')`` when given, or -- with ``uv`` ``[B,H/2,W]`` -- the Y planes ``[B,H,W]`` of NV12
+        frames.  ``norm``: ``_lib.NormParams`` (default: plain x / 255, what the YAML model is fed).
+        Returns the decoded prediction ``y[B,4+nc,A]``."""
+        import types
+
+        if self.training:
+            raise RuntimeError("UninaYoloB200 implements the inference path only: call .eval()")
+        assert frames.is_cuda and frames.dtype == torch.uint8 and frames.is_contiguous()
+        nv12 = uv is not None
+        B, H, W = frames.shape[:3]
+        oh, ow = (H, W) if (nv12 or size is None) else size
+        p = self.plan_for(types.SimpleNamespace(shape=(B, 3, oh, ow), device=frames.device),
+                          fused=os.environ.get("UYD_NO_FUSED_DECODE", "0") != "1")
+        f = _lib.CameraFrames()
+        f.format = _lib.CAM_NV12 if nv12 else _lib.CAM_BGRA
+        f.width, f.height = W, H
+        f.pitch = frames.stride(1)
+        f.frame_stride = frames.stride(0)
+        f.data = frames.data_ptr()
+        if nv12:
+            assert uv.is_cuda and uv.dtype == torch.uint8 and uv.is_contiguous() and uv.shape[0] == B
+            f.uv, f.uv_pitch, f.uv_frame_stride = uv.data_ptr(), uv.stride(1), uv.stride(0)
+        f.norm = norm if norm is not None else _lib.NormParams(0.0, 0.0, 0.0, 1.0, 1.0, 1.0)
+        y = torch.empty(B, 4 + self.nc, self.num_anchors(oh, ow), dtype=torch.float32, device=frames.device)
+        if p.fused:
+            p.run_camera(f, B, y)
+        else:
+            p.run_camera(f, B)
+            p.decode(y, B)
+        return y
+
+    @torch.no_grad()
+    def predict_camera(self, frames: torch.Tensor, size=None, norm=None, uv=None, conf: float = 0.25, iou: float = 0.7,
+                       max_det: int = 300, max_nms: int = 30000):
+        """``forward_camera`` + NMS: (det[B,max_det,6], count[B]) on the device."""
+        return self.nms(self.forward_camera(frames, size, norm, uv), conf, iou, max_det, max_nms)
+
     def _nms_workspace(self, dev: int, B: int, A: int, device) -> torch.Tensor:
         need = int(_lib.lib().uyd_nms_workspace_bytes(B, A))
         ws = self._nms_ws.get(dev)
