@@ -467,6 +467,15 @@ def main():
     if world > 1:
         probe["no_gather_ms_per_step"] = min(timed(lambda: run_stream(a.steps, gather=False), 1) for _ in range(2)) / a.steps
     probe["no_h2d_ms_per_step"] = min(timed(lambda: run_stream(a.steps, h2d=False), 1) for _ in range(2)) / a.steps
+
+    def h2d_only():  # the pinned host -> device copies of the streamed run alone, all ranks at once: the platform's H2D rate
+        for _ in range(a.steps):
+            x_u8.copy_(x_host, non_blocking=True)
+
+    h2d_only()
+    h2d_ms = min(timed(h2d_only, 1) for _ in range(2)) / a.steps
+    probe["h2d_only_ms_per_step"] = h2d_ms
+    probe["h2d_only_gbs_per_gpu"] = x_host.numel() / (h2d_ms * 1e-3) / 1e9
     # sustained: the resident step back to back for >= a.sustain seconds, clocks sampled throughout
     sustained = None
     if a.sustain > 0:
@@ -561,8 +570,9 @@ def main():
                 "api": "UninaYoloB200.predict_stream(pinned uint8 NCHW host batches): H2D of step i+1 overlaps step i (best of 3 runs of K steps); "
                        "N > 1: + one fixed-shape NCCL all_gather of the detections per step on a side stream; "
                        "single_call_ms = one blocking predict_batched(host frames) per step",
-                "bound_probe": dict(probe, note="the same streamed run with the gather (N > 1) or the H2D copy switched off: the stage "
-                                                "whose removal brings ms_per_step down to the resident step is the bound")},
+                "bound_probe": dict(probe, note="the same streamed run with the gather (N > 1) or the H2D copy switched off, and the H2D copies "
+                                                "alone on all ranks at once: e2e ms_per_step ~ max(resident step, h2d_only) means the "
+                                                "host-to-device path of the box bounds e2e")},
         "gpu_launches": kernels_per_step * a.steps,
         "roofline": {"kernel": top_text, "bound": "tensor" if tensor_bound else "hbm", "achieved": achieved, "peak": peak,
                      "unit": unit, "frac": achieved / peak, "traffic": traffic, "peak_source": pk["src"],

@@ -44,7 +44,9 @@ M = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", 
      "sm__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
      "lts__throughput.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_tensor.sum", "smsp__inst_executed.sum",
      "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
-     "smsp__cycles_active.avg", "sm__pipe_tensor_op_hmma_cycles_active.avg.pct_of_peak_sustained_active"]
+     "smsp__cycles_active.avg", "sm__pipe_tensor_op_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+     "sm__inst_executed_pipe_uniform.sum", "smsp__inst_executed_pipe_tma.sum", "sm__inst_executed_pipe_tmem.sum"]
 suffixes = sys.argv[3:] or ["step"]
 rr = []
 for sfx in suffixes:
@@ -57,8 +59,8 @@ jx = {n: i for i, n in enumerate(hh)}
 cols = [m for m in M if m in jx]
 out = [f"# {name}: ncu --set full of the hot kernels of one predict step (batch 64, 640x640)", "",
        "`ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:... python tools/kernel_table.py --ncu`", "",
-       "| # | kernel | grid x block | regs | us | DRAM rd MB | DRAM wr MB | SM % | L1 % | L2 % | warps active % | warp inst |",
-       "|---|---|---|---|---|---|---|---|---|---|---|---|"]
+       "| # | kernel | grid x block | regs | us | DRAM rd MB | DRAM wr MB | SM % | L1 % | L2 % | tensor pipe % (active / elapsed) | warps active % | warp inst |",
+       "|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
 traffic = {}
 for i, r in enumerate(rr[2:]):
     g = lambda m: r[jx[m]] if m in jx else ""
@@ -68,6 +70,7 @@ for i, r in enumerate(rr[2:]):
                f"{f('gpu__time_duration.sum'):.1f} | {f('dram__bytes_read.sum'):.1f} | {f('dram__bytes_write.sum'):.1f} | "
                f"{f('sm__throughput.avg.pct_of_peak_sustained_elapsed'):.1f} | "
                f"{f('l1tex__throughput.avg.pct_of_peak_sustained_elapsed'):.1f} | {f('lts__throughput.avg.pct_of_peak_sustained_elapsed'):.1f} | "
+               f"{f('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active'):.1f} / {f('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed'):.1f} | "
                f"{f('sm__warps_active.avg.pct_of_peak_sustained_active'):.1f} | {f('smsp__inst_executed.sum'):.3g} |")
 out += ["", f"units: time {units[jx['gpu__time_duration.sum']]}, DRAM {units[jx['dram__bytes_read.sum']]}", ""]
 (out_dir / f"{name}_kernels.md").write_text("\n".join(out) + "\n")

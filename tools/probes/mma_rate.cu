@@ -17,10 +17,16 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t sbo) {
   d |= (uint64_t)2 << 61;  // SWIZZLE_128B
   return d;
 }
+template <bool I8>
 __device__ __forceinline__ void umma(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
-               "l"(a), "l"(b), "r"(idesc), "r"(acc)
-               : "memory");
+  if (I8)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
+                 "l"(a), "l"(b), "r"(idesc), "r"(acc)
+                 : "memory");
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
+                 "l"(a), "l"(b), "r"(idesc), "r"(acc)
+                 : "memory");
 }
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -28,7 +34,8 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-template <int MODE>  // 0: if (lane == 0), 1: elect.sync, 2: elect + alternate accumulators every 4 MMAs
+// I8: kind::i8 (int8 x int8 -> int32, K = 32 per instruction at the same 32 operand bytes per row)
+template <int MODE, bool I8 = false>  // 0: if (lane == 0), 1: elect.sync, 2: elect + alternate accumulators every 4 MMAs
 __global__ void __launch_bounds__(128, 1) probe(int N, int iters, long long *out) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint32_t slot;
@@ -49,7 +56,7 @@ __global__ void __launch_bounds__(128, 1) probe(int N, int iters, long long *out
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = slot;
-  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint32_t idesc = ((I8 ? 2u : 1u) << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   const uint64_t ad = make_desc(base, 1024), bd = make_desc(base + 16384, 1024);
   long long t0 = 0, t1 = 0, t2 = 0;
   if (warp == 1) {
@@ -59,7 +66,7 @@ __global__ void __launch_bounds__(128, 1) probe(int N, int iters, long long *out
 #pragma unroll 1
         for (int i = 0; i < iters; i += 4) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma(tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);
+          for (int k = 0; k < 4; ++k) umma<I8>(tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);
         }
       }
       __syncwarp();
@@ -69,7 +76,7 @@ __global__ void __launch_bounds__(128, 1) probe(int N, int iters, long long *out
         const uint32_t d = (MODE == 2 && (i & 4)) ? tmem + 256 : tmem;
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma(d, ad + 2 * k, bd + 2 * k, idesc, 1u);
+          for (int k = 0; k < 4; ++k) umma<I8>(d, ad + 2 * k, bd + 2 * k, idesc, 1u);
         }
         __syncwarp();
       }
@@ -105,5 +112,20 @@ int main() {
   };
   for (int mode = 0; mode < 3; ++mode)
     for (int N : {16, 32, 64, 128, 256}) run(mode, N);
+  // kind::i8 under elect.sync: cycles per MMA and the implied dense INT8 rate of the whole GPU
+  int dev = 0, clk_khz = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  for (int N : {16, 32, 64, 128, 256}) {
+    const size_t smem = 49 * 1024;
+    cudaFuncSetAttribute(probe<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    for (int rep = 0; rep < 2; ++rep) probe<1, true><<<148, 128, smem>>>(N, iters, d);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+    const double cyc = (double)h[1] / iters;
+    printf("i8   N %3d: %.1f cyc/mma -> %.0f dense INT8 TOP/s at %d SMs x %.3f GHz (max clock; %s)\n", N, cyc,
+           2.0 * 128 * N * 32 / cyc * sms * clk_khz * 1e3 / 1e12, sms, clk_khz / 1e6, cudaGetErrorString(e));
+  }
   return 0;
 }

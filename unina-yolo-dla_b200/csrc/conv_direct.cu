@@ -223,23 +223,24 @@ __global__ void __launch_bounds__(kThreads) conv_dw_kernel(ConvArgs a) {
   *reinterpret_cast<uint4 *>(op) = pk;
 }
 
-// Tiled stem for the shape the network actually has (3 -> 16, 3x3, stride 2): a CTA stages the
+// Tiled stem for the shapes the networks actually have (3 -> 16 of the YAML graph when it is not fused, 3 -> 32 of
+// model.py's backbone.stem, model.py:173): 3x3, stride 2.  A CTA stages the
 // 33 x 65 x 3 input patch of a 16 x 32 output tile in shared memory with coalesced row reads
 // (the frame is read once from HBM instead of 9x through L1); each thread computes two
 // horizontally adjacent output pixels x 16 channels so that every weight vector read from
 // shared memory feeds two FMAs (the kernel is FMA-bound, not LSU-bound).
 constexpr int kStemTH = 16, kStemTW = 32, kStemThreads = 256;
-template <typename TIn>
+template <typename TIn, int COUT>
 __global__ void __launch_bounds__(kStemThreads) conv_stem_tiled_kernel(ConvArgs a) {
   // shared tile column j holds image column ox0*2 - 4 + j (4-element aligned so that rows are fetched
   // as 16-byte / 4-byte vectors); the conv reads columns 3 .. 67
   constexpr int IH = 2 * kStemTH + 1, NV = (2 * kStemTW) / 4 + 2, IP = NV * 4;
   __shared__ __align__(16) float sx[3][IH][IP];
-  __shared__ __align__(16) float sw[27][16];
+  __shared__ __align__(16) float sw[27][COUT];
   const int tid = threadIdx.x;
   const int ox0 = blockIdx.x * kStemTW, oy0 = blockIdx.y * kStemTH, n = blockIdx.z;
-  for (int i = tid; i < 27 * 16; i += kStemThreads)
-    sw[i / 16][i % 16] = __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(a.w)[i]);
+  for (int i = tid; i < 27 * COUT; i += kStemThreads)
+    sw[i / COUT][i % COUT] = __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(a.w)[i]);
   const TIn *in = reinterpret_cast<const TIn *>(a.in) + (long long)n * 3 * a.ih * a.iw;
   const bool vec_ok = a.iw % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
 #pragma unroll 4
@@ -276,9 +277,9 @@ __global__ void __launch_bounds__(kStemThreads) conv_stem_tiled_kernel(ConvArgs 
   const int tx = tid % (kStemTW / 2), ty = tid / (kStemTW / 2);
   const int ox = ox0 + 2 * tx, oy = oy0 + ty;
   if (ox >= a.ow || oy >= a.oh) return;
-  float acc[2][16];
+  float acc[2][COUT];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) acc[0][i] = acc[1][i] = 0.f;
+  for (int i = 0; i < COUT; ++i) acc[0][i] = acc[1][i] = 0.f;
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
@@ -289,7 +290,7 @@ __global__ void __launch_bounds__(kStemThreads) conv_stem_tiled_kernel(ConvArgs 
       for (int kx = 0; kx < 3; ++kx) {
         const float4 *wr = reinterpret_cast<const float4 *>(sw[(ky * 3 + kx) * 3 + ci]);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < COUT / 4; ++q) {
           const float4 w4 = wr[q];
           acc[0][4 * q] = fmaf(x[kx], w4.x, acc[0][4 * q]);
           acc[0][4 * q + 1] = fmaf(x[kx], w4.y, acc[0][4 * q + 1]);
@@ -306,17 +307,17 @@ __global__ void __launch_bounds__(kStemThreads) conv_stem_tiled_kernel(ConvArgs 
   for (int px = 0; px < 2; ++px) {
     if (ox + px >= a.ow) break;
     __nv_bfloat16 *op = reinterpret_cast<__nv_bfloat16 *>(a.out) + (((long long)n * a.oh + oy) * a.ow + ox + px) * a.out_pitch;
-    uint4 o[2];
+    uint4 o[COUT / 8];
     uint32_t *pw = reinterpret_cast<uint32_t *>(o);
 #pragma unroll
-    for (int i = 0; i < 16; i += 2) {
+    for (int i = 0; i < COUT; i += 2) {
       float v0 = acc[px][i] + a.bias[i], v1 = acc[px][i + 1] + a.bias[i + 1];
       if (a.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
       __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
       pw[i / 2] = *reinterpret_cast<uint32_t *>(&h);
     }
-    reinterpret_cast<uint4 *>(op)[0] = o[0];
-    reinterpret_cast<uint4 *>(op)[1] = o[1];
+#pragma unroll
+    for (int i = 0; i < COUT / 8; ++i) reinterpret_cast<uint4 *>(op)[i] = o[i];
   }
 }
 
@@ -439,11 +440,16 @@ int direct_conv_launch(const ConvArgs &a, bool depthwise, cudaStream_t s) {
     const size_t wbytes = (size_t)a.k * a.k * a.cin * a.cout * 2;
     UYD_REQUIRE(wbytes <= 48 * 1024, UYD_E_UNSUPPORTED, "stem weights too large");
     const bool u8 = a.in_nchw_f32 == 2;
-    if (a.cin == 3 && a.cout == 16 && a.k == 3 && a.stride == 2 && a.out_pitch % 8 == 0 &&
+    if (a.cin == 3 && (a.cout == 16 || a.cout == 32) && a.k == 3 && a.stride == 2 && a.out_pitch % 8 == 0 &&
         (reinterpret_cast<uintptr_t>(a.out) & 15) == 0) {
       dim3 grid(ceil_div(a.ow, kStemTW), ceil_div(a.oh, kStemTH), a.n);
-      if (u8) conv_stem_tiled_kernel<uint8_t><<<grid, kStemThreads, 0, s>>>(a);
-      else conv_stem_tiled_kernel<float><<<grid, kStemThreads, 0, s>>>(a);
+      if (a.cout == 16) {
+        if (u8) conv_stem_tiled_kernel<uint8_t, 16><<<grid, kStemThreads, 0, s>>>(a);
+        else conv_stem_tiled_kernel<float, 16><<<grid, kStemThreads, 0, s>>>(a);
+      } else {
+        if (u8) conv_stem_tiled_kernel<uint8_t, 32><<<grid, kStemThreads, 0, s>>>(a);
+        else conv_stem_tiled_kernel<float, 32><<<grid, kStemThreads, 0, s>>>(a);
+      }
       return (int)cudaGetLastError();
     }
     if (a.cout % 16 == 0) {
