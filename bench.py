@@ -163,9 +163,20 @@ def bench_int8(model, batch: int, size: int, dev, steps: int):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     n_s8 = sum(1 for i in range(plan.launches) if plan.op_info(i)[0].startswith("conv_s8"))
+    s8_ops = sum(plan.op_info(i)[1] for i in range(plan.launches) if plan.op_info(i)[0].startswith("conv_s8"))
+    prof = plan.profile(x, None)
+    s8_ms = sum(t for i, t in enumerate(prof) if plan.op_info(i)[0].startswith("conv_s8"))
+    q_ms = sum(t for i, t in enumerate(prof) if plan.op_info(i)[0].startswith("quantize"))
+    pk8 = ROOT / "profiles" / "int8_peak.json"
+    peak8 = json.loads(pk8.read_text())["int8_tops_dense"] if pk8.exists() else 4500.0
+    tops = s8_ops * batch / (s8_ms * 1e-3) / 1e12
     out = {"value": batch / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "batch": batch, "steps": steps, "dtype": "s8 x s8 -> s32",
            "plan_launches": plan.launches, "int8_convs": n_s8, "activation_bytes": plan.bytes,
-           "note": "quantize ops are separate launches in this round (one int8 copy per activation slice and scale)"}
+           "roofline": {"bound": "tensor", "achieved": tops, "peak": peak8, "unit": "TOP/s", "frac": tops / peak8,
+                        "peak_source": "measured kind::i8 probe at the maximum SM clock (profiles/int8_peak.json)" if pk8.exists() else "nominal",
+                        "int8_conv_ms": s8_ms, "quantize_ms": q_ms,
+                        "note": "achieved = int8 conv ops of the plan x batch / the summed CUDA-event time of the conv_s8 launches"},
+           "note": "quantize ops are separate launches (one int8 copy per activation slice and scale); C3k interiors run as single int8 convs"}
     model.set_quantization(None)
     return out
 
