@@ -1,30 +1,15 @@
-// Fused C3k block (Ultralytics C3k with two 3x3 bottlenecks, the interior of every C3k2 of the
-// YAML graph):
-//
-//     a  = relu(cv1 x)            1x1  c  -> c_          (c_ = c / 2 = 4, 8 or 16)
-//     b  = relu(cv2 x)            1x1  c  -> c_
-//     t1 = relu(m0.cv1 a)         3x3  c_ -> c_
-//     u  = a + relu(m0.cv2 t1)    3x3  c_ -> c_
-//     t2 = relu(m1.cv1 u)         3x3  c_ -> c_
-//     v  = u + relu(m1.cv2 t2)    3x3  c_ -> c_
-//     y  = relu(cv3 [v | b])      1x1  2c_ -> c
-//
-// Unfused this is 7 launches and 12 HBM round trips of 4..32-channel tensors that are latency-
-// bound (12-70 us each at batch 64).  Here one CTA owns a TH x 40 output tile: the input tile with
-// a 4-pixel halo is staged once in shared memory, the six intermediates never leave it, and the
-// math runs on tensor cores through mma.sync.m16n8k16 (bf16, fp32 accumulate) -- tcgen05 cannot be
-// fed by K = 9*c_ = 36..144 and N = 4..16.  M = 16 consecutive pixels of a tile row; a 3x3 conv is
-// ceil(9*c_/16) k-steps whose A fragments are plain 32-bit loads at tap-shifted pixel addresses.
-// Every intermediate is rounded to bf16 exactly where the unfused path rounds it, and positions
-// outside the image are forced to zero (each conv zero-pads ITS input), so results equal the
-// unfused plan up to fp32 summation order.
+// Host side of the fused C3k block (shape rule, weight packing, tile-height choice, launch of the flat-frame kernel
+// in c3k_flat.cu) and the fused class-branch kernel of the Detect head that the unchained plans use
+// (UYD_NO_CHAIN=1, shapes conv_chain.cu does not take): DWConv -> 1x1 -> DWConv -> 1x1 -> 1x1 in one launch on
+// mma.sync.m16n8k16, the stage helpers below.  (The first-generation C3k kernel that lived here was removed after
+// a round of soak of c3k_flat_kernel.)
 #include <cstdlib>
 
 #include "common.cuh"
 
 namespace uyd {
 
-// c3k_flat.cu: the second-generation kernel (default); this file's c3k_fused_kernel stays behind UYD_C3K_LEGACY=1
+// c3k_flat.cu
 size_t c3k_flat_smem_bytes(int c_, int th);
 void c3k_flat_pack(int c, const float *const w[7], std::vector<uint32_t> &frags);
 struct C3kArgs;
@@ -230,91 +215,6 @@ __device__ __forceinline__ void stage_conv1(const __nv_bfloat16 *srcA, const __n
 template <int C> constexpr int frag_words_3() { return K3<C>::STEPS * ((C + 7) / 8) * 64; }
 constexpr int frag_words_1(int k, int cout) { return ((k + 15) / 16) * ((cout + 7) / 8) * 64; }
 
-template <int C>  // C = c_ (hidden width); block width c = 2C
-__global__ void __launch_bounds__(kThreadsC3k) c3k_fused_kernel(C3kArgs a) {
-  pdl_trigger();
-  extern __shared__ __align__(16) unsigned char smem[];
-  constexpr int CC = 2 * C;
-  const int TH = a.th;
-  const int frame_px = (TH + 8 + 1) * kPW;  // +1 slack row: over-reads of partial segments stay in bounds
-  __nv_bfloat16 *X = reinterpret_cast<__nv_bfloat16 *>(smem);  // [frame][2C]   (later: output tile [TH*40][2C])
-  __nv_bfloat16 *A = X + (size_t)frame_px * CC;                // [frame][C]    a -> u -> v
-  __nv_bfloat16 *T = A + (size_t)frame_px * C;                 // [frame][C]    t1 -> t2
-  __nv_bfloat16 *Bv = T + (size_t)frame_px * C;                // [TH*40][C]    b
-  __shared__ float sbias[7][32];
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tile = blockIdx.x;
-  const int n = tile / (a.tiles_x * a.tiles_y);
-  const int tr = tile % (a.tiles_x * a.tiles_y);
-  const int ty0 = (tr / a.tiles_x) * TH, tx0 = (tr % a.tiles_x) * kTW;
-  const int gy0 = ty0 - 4, gx0 = tx0 - 4;  // image coordinates of frame pixel (0,0)
-  const int H = a.h, W = a.w;
-
-  for (int i = tid; i < 7 * 32; i += kThreadsC3k) sbias[i / 32][i % 32] = a.bias[i];
-  // ---- stage 0: input tile + halo -> X (zero outside the image, zero slack row) ----------------
-  {
-    constexpr int CH16 = CC / 8;  // 16-byte chunks per pixel
-    const __nv_bfloat16 *img = a.in + (long long)n * H * W * a.in_pitch;
-    const int total = frame_px * CH16;
-    for (int i = tid; i < total; i += kThreadsC3k) {
-      const int px = i / CH16, ch = i % CH16;
-      const int ry = px / kPW, rx = px % kPW;
-      const int gy = gy0 + ry, gx = gx0 + rx;
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (ry < TH + 8 && (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W)
-        v = *reinterpret_cast<const uint4 *>(img + ((long long)gy * W + gx) * a.in_pitch + ch * 8);
-      reinterpret_cast<uint4 *>(X)[i] = v;
-    }
-    // slack rows of A and T are read (never stored) by partial segments: keep them finite
-    for (int i = tid; i < kPW * C / 2; i += kThreadsC3k) {
-      reinterpret_cast<uint32_t *>(A + (size_t)(TH + 8) * kPW * C)[i] = 0u;
-      reinterpret_cast<uint32_t *>(T + (size_t)(TH + 8) * kPW * C)[i] = 0u;
-    }
-  }
-  __syncthreads();
-
-  const uint32_t *wf = a.wfrag;
-  constexpr int W1 = frag_words_1(CC, C), W3 = frag_words_3<C>();
-  const Region R4{0, TH + 8, 0, kPW}, R3{1, TH + 7, 1, kPW - 1}, R2{2, TH + 6, 2, kPW - 2}, R1{3, TH + 5, 3, kPW - 3},
-      R0{4, TH + 4, 4, kPW - 4};
-  // ---- stage 1: a = cv1(x) on R4, b = cv2(x) on R0 ---------------------------------------------
-  stage_conv1<CC, 0, C>(X, nullptr, A, false, wf, sbias[0], R4, gy0, gx0, H, W, warp, lane);
-  stage_conv1<CC, 0, C>(X, nullptr, Bv, true, wf + W1, sbias[1], R0, gy0, gx0, H, W, warp, lane);
-  __syncthreads();
-  // ---- stages 2..5: the two bottlenecks ---------------------------------------------------------
-  stage_conv3<C>(A, T, nullptr, wf + 2 * W1, sbias[2], R3, gy0, gx0, H, W, warp, lane);
-  __syncthreads();
-  stage_conv3<C>(T, A, A, wf + 2 * W1 + W3, sbias[3], R2, gy0, gx0, H, W, warp, lane);
-  __syncthreads();
-  stage_conv3<C>(A, T, nullptr, wf + 2 * W1 + 2 * W3, sbias[4], R1, gy0, gx0, H, W, warp, lane);
-  __syncthreads();
-  stage_conv3<C>(T, A, A, wf + 2 * W1 + 3 * W3, sbias[5], R0, gy0, gx0, H, W, warp, lane);
-  __syncthreads();
-  // ---- stage 6: y = cv3([v | b]) on R0 -> output tile staged in X (compact), then coalesced copy
-  stage_conv1<C, C, CC>(A, Bv, X, true, wf + 2 * W1 + 4 * W3, sbias[6], R0, gy0, gx0, H, W, warp, lane);
-  __syncthreads();
-  {
-    constexpr int CH16 = CC / 8;
-    __nv_bfloat16 *img = a.out + (long long)n * H * W * a.out_pitch;
-    const int total = TH * kTW * CH16;
-    for (int i = tid; i < total; i += kThreadsC3k) {
-      const int px = i / CH16, ch = i % CH16;
-      const int gy = ty0 + px / kTW, gx = tx0 + px % kTW;
-      if (gy < H && gx < W)
-        *reinterpret_cast<uint4 *>(img + ((long long)gy * W + gx) * a.out_pitch + ch * 8) = reinterpret_cast<const uint4 *>(X)[i];
-    }
-  }
-}
-
-// =================================================================================================
-// Fused class branch of the Detect head (Ultralytics Detect.cv3[l], non-legacy):
-//     y1 = relu(dw3x3(x))   z1 = relu(pw(y1))   y2 = relu(dw3x3(z1))   z2 = relu(pw(z2))   out = pw(z2) + b
-// (DWConv(c,c,3) -> Conv(c,32,1) -> DWConv(32,32,3) -> Conv(32,32,1) -> Conv2d(32,nc,1)).
-// Unfused: five launches and ~10 HBM passes over 160x160x32 tensors per image.  Here a CTA owns an
-// 8 x 40 tile (+2 halo): depth-wise taps on CUDA cores out of shared memory, point-wise convs on
-// mma.sync, the nc logits go straight to the fp32 head buffer.
-// =================================================================================================
 constexpr int kClsTH = 8;
 constexpr int kClsWarps = 16, kClsThreads = kClsWarps * 32;
 
@@ -511,33 +411,7 @@ void c3k_pack(int c, const float *const w[7], const float *const b[7], std::vect
   const int couts[7] = {C, C, C, C, C, C, c};
   for (int i = 0; i < 7; ++i)
     for (int n = 0; n < couts[i]; ++n) bias[i * 32 + n] = b[i][n];
-  for (int i = 0; i < 2; ++i) {
-    const float *wi = w[i];
-    pack_frags(frags, (c + 15) / 16, (C + 7) / 8, C, [&](int s, int kk, int n) {
-      const int k = 16 * s + kk;
-      return k < c ? wi[(size_t)n * c + k] : 0.f;
-    });
-  }
-  const int tpk = 16 / C, steps3 = (9 + tpk - 1) / tpk;
-  for (int i = 2; i < 6; ++i) {
-    const float *wi = w[i];
-    pack_frags(frags, steps3, (C + 7) / 8, C, [&](int s, int kk, int n) {
-      const int tap = s * tpk + kk / C, ch = kk % C;
-      return tap < 9 ? wi[((size_t)n * C + ch) * 9 + tap] : 0.f;
-    });
-  }
-  const float *w6 = w[6];
-  pack_frags(frags, (c + 15) / 16, (c + 7) / 8, c, [&](int s, int kk, int n) {
-    const int k = 16 * s + kk;
-    return k < c ? w6[(size_t)n * c + k] : 0.f;
-  });
-  c3k_flat_pack(c, w, frags);  // the flat-frame kernel's fragments follow the legacy ones (c3k_legacy_words)
-}
-
-// words of legacy fragments in front of the flat-frame ones
-static int c3k_legacy_words(int c) {
-  const int C = c / 2, tpk = 16 / C, steps3 = (9 + tpk - 1) / tpk;
-  return 2 * frag_words_1(c, C) + 4 * steps3 * ((C + 7) / 8) * 64 + frag_words_1(c, c);
+  c3k_flat_pack(c, w, frags);
 }
 
 bool cls_branch_supported(int cin, int mid, int nc, int h, int w, int in_pitch, int in_coff, int out_pitch, int out_coff) {
@@ -609,21 +483,7 @@ int c3k_launch(int c, const C3kArgs &a0, cudaStream_t s) {
   a.th = c3k_launch_th(a.n, a.h, a.w);
   a.tiles_x = a.w / kTW;
   a.tiles_y = a.h / a.th;
-  static const bool legacy = [] { const char *v = getenv("UYD_C3K_LEGACY"); return v && *v == '1'; }();
-  if (!legacy) {
-    a.wfrag += c3k_legacy_words(c);
-    return c3k_flat_launch(c, a, s);
-  }
-  const size_t smem = c3k_smem_bytes(c / 2, a.th);
-  const unsigned grid = (unsigned)(a.n * a.tiles_x * a.tiles_y);
-  auto setup = [&](auto kern, int) -> int {
-    if (int e = smem_optin(kern, 220 * 1024)) return e;
-    kern<<<grid, kThreadsC3k, smem, s>>>(a);   // plain launch: measured, a PDL launch of this kernel gains nothing at batch 64
-    return (int)cudaGetLastError();             // and costs 20 us of batch-1 latency (early CTAs squat on the SMs)
-  };
-  if (c == 8) return setup(c3k_fused_kernel<4>, 0);
-  if (c == 16) return setup(c3k_fused_kernel<8>, 1);
-  return setup(c3k_fused_kernel<16>, 2);
+  return c3k_flat_launch(c, a, s);
 }
 
 }  // namespace uyd

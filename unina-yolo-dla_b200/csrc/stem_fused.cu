@@ -1,16 +1,8 @@
-// Fused stem: model.0 Conv(3,16,3,2) + model.1 Conv(16,32,3,2) (unina-yolo-dla-m.yaml:24-25, both
-// Conv+BN+ReLU, BN folded) in one launch.  Unfused, the 320x320x16 tensor between them costs 6.6 MB of
-// HBM traffic per frame and the 16-channel layer cannot feed tcgen05 efficiently (32-byte TMA rows).
-//
-// One CTA = 8 x 16 outputs of layer 1:
-//   * the 35 x 68 x 3 frame patch is staged in shared memory as two bf16 planes hi + lo (hi + lo == the
-//     fp32 value up to 2^-17, split once per element; uint8 frames: x / 255 first, the reference
-//     predictor's pre-process), so the frame itself is not rounded (weights are bf16 as everywhere);
-//   * layer 0 over the 17 x 33 region runs on tensor cores (mma.sync m16n8k16, bf16 x bf16 -> fp32):
-//     K = (ci, ky) x 4 column slots kx = -1..2 (slot -1 has zero weights and makes every slot pair a
-//     4-byte aligned shared-memory word);
-//   * its bf16 result (zero outside the image = layer 1's padding) never leaves shared memory;
-//   * layer 1 is nine k-steps of mma.sync (one filter tap = 16 channels per step).
+// Fused stem: model.0 Conv(3,16,3,2) + model.1 Conv(16,32,3,2) (unina-yolo-dla-m.yaml:24-25, both Conv+BN+ReLU, BN
+// folded), optionally + model.2.cv1, in one launch.  Unfused, the 320x320x16 tensor between them costs 6.6 MB of HBM
+// traffic per frame and a 16-channel layer cannot feed tcgen05 (32-byte TMA rows).  The design and the per-lane maps
+// are in stem_v2.cuh; this file holds the kernel, the camera-frame loaders (BGRA / NV12 read and normalised on load,
+// SURVEY 8f-1) and the host side.  (The first-generation hi/lo-split kernel was removed after a round of soak.)
 #include <type_traits>
 
 #include "stem_v2.cuh"
@@ -22,7 +14,7 @@ namespace uyd {
 struct StemArgs {
   const void *in;      // NCHW frames, fp32 or uint8
   __nv_bfloat16 *out;  // NHWC slice base of image 0
-  const uint32_t *wfrag;  // [L0: 3 k-steps x 2 n-tiles | L1: 9 k-steps x 4 n-tiles] x 32 lanes x 2 words
+  const uint32_t *wfrag;  // stemv2::pack fragments: [L0 | L1 | 1x1]
   const float *bias;      // [16 | 32]
   int n, ih, iw, oh, ow, out_pitch, u8;
   int pw;  // 1: the 1x1 Conv(32,16) follows in the same launch (second-generation kernel only); out has 16 channels
@@ -35,31 +27,6 @@ struct StemArgs {
 };
 
 namespace {
-
-constexpr int kTH = 8, kTW = 16;            // layer-1 output tile
-constexpr int kL0H = 2 * kTH + 1, kL0W = 2 * kTW + 1;   // 17 x 33 layer-0 region
-constexpr int kInH = 2 * kL0H + 1, kInW = 2 * kL0W + 2;  // 35 rows x 68 columns (frame columns 4*ox0 - 4 ...; column 0 only feeds the zero slot)
-constexpr int kL0Pitch = 20;                // bf16 per layer-0 pixel in shared memory (16 + 4: conflict-free stride-2 reads)
-constexpr int kL0Px = kL0H * kL0W;          // 561
-constexpr int kThreads = 256;
-
-__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t *>(&h);
-}
-// v -> (hi, lo) bf16 pairs with hi + lo == v up to 2^-17 relative
-__device__ __forceinline__ void split_bf16(float2 v, uint32_t &hi, uint32_t &lo) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
-  const float2 hf = __bfloat1622float2(h);
-  hi = *reinterpret_cast<uint32_t *>(&h);
-  lo = pack_bf16(v.x - hf.x, v.y - hf.y);
-}
 
 struct CamIn {};  // TIn tag of the camera instantiations of stem_v2_kernel
 
@@ -101,187 +68,6 @@ __device__ __forceinline__ void cam_pixel(const StemArgs &a, const uint8_t *fram
   rgb[2] = cam_norm(b, a.mean[2], a.stdv[2]);
 }
 
-template <typename TIn>
-__global__ void __launch_bounds__(kThreads) stem_fused_kernel(StemArgs a) {
-  pdl_trigger();
-  extern __shared__ __align__(16) unsigned char smem[];
-  __nv_bfloat16 *hi_s = reinterpret_cast<__nv_bfloat16 *>(smem);                   // [3][35][68] high parts
-  __nv_bfloat16 *lo_s = hi_s + 3 * kInH * kInW;                                     // [3][35][68] residuals
-  __nv_bfloat16 *l0_s = lo_s + 3 * kInH * kInW;                                     // [561 + 19][20]
-  uint32_t *w_s = reinterpret_cast<uint32_t *>(l0_s + (kL0Px + 19) * kL0Pitch);     // fragments (16-byte aligned)
-  float *b_s = reinterpret_cast<float *>(w_s + (6 + 36) * 64);                      // [48]
-  __nv_bfloat16 *stage_s = hi_s;                                                    // output staging aliases the frame patch
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int ox0 = blockIdx.x * kTW, oy0 = blockIdx.y * kTH, n = blockIdx.z;
-  const int ix0 = 4 * ox0 - 4, iy0 = 4 * oy0 - 3;  // frame coordinates of the patch origin (16-byte aligned columns)
-
-  // All global loads of a thread are issued before the first dependent store (the patch is 7 16-byte loads per
-  // thread: issued one by one they serialise 7 DRAM latencies, measured 28 % of all stall samples).
-  constexpr int kWVec = (6 + 36) * 64 / 4, kWIters = (kWVec + kThreads - 1) / kThreads;
-  uint4 wv[kWIters];
-#pragma unroll
-  for (int it = 0; it < kWIters; ++it) {
-    const int i = tid + it * kThreads;
-    wv[it] = i < kWVec ? reinterpret_cast<const uint4 *>(a.wfrag)[i] : make_uint4(0u, 0u, 0u, 0u);
-  }
-  // ---- frame patch -> shared fp32 (zero outside the frame) ----
-  const TIn *img = reinterpret_cast<const TIn *>(a.in) + (long long)n * 3 * a.ih * a.iw;
-  constexpr int kVecPerRow = kInW / 4, kPatchVec = 3 * kInH * kVecPerRow, kPIters = (kPatchVec + kThreads - 1) / kThreads;
-  float pv[kPIters][4];
-  const bool vec_ok = (a.iw & 3) == 0;
-#pragma unroll
-  for (int it = 0; it < kPIters; ++it) {
-    const int i = tid + it * kThreads;
-    const int c = i / (kInH * kVecPerRow), r = (i / kVecPerRow) % kInH, j = i % kVecPerRow;
-    const int iy = iy0 + r, ix = ix0 + 4 * j;
-    pv[it][0] = pv[it][1] = pv[it][2] = pv[it][3] = 0.f;
-    if (i < kPatchVec && iy >= 0 && iy < a.ih) {
-      const TIn *src = img + ((long long)c * a.ih + iy) * a.iw + ix;
-      if (vec_ok && ix >= 0 && ix + 3 < a.iw) {
-        if (sizeof(TIn) == 4) {
-          const float4 q = *reinterpret_cast<const float4 *>(src);
-          pv[it][0] = q.x; pv[it][1] = q.y; pv[it][2] = q.z; pv[it][3] = q.w;
-        } else {
-          const uchar4 q = *reinterpret_cast<const uchar4 *>(src);
-          pv[it][0] = (float)q.x; pv[it][1] = (float)q.y; pv[it][2] = (float)q.z; pv[it][3] = (float)q.w;
-        }
-      } else {
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (ix + e >= 0 && ix + e < a.iw) pv[it][e] = (float)src[e];
-      }
-    }
-  }
-  if (tid < 48) b_s[tid] = a.bias[tid];
-#pragma unroll
-  for (int it = 0; it < kWIters; ++it) {
-    const int i = tid + it * kThreads;
-    if (i < kWVec) reinterpret_cast<uint4 *>(w_s)[i] = wv[it];
-  }
-#pragma unroll
-  for (int it = 0; it < kPIters; ++it) {
-    const int i = tid + it * kThreads;
-    if (i >= kPatchVec) continue;
-    uint32_t h[2], l[2];
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      float2 v = make_float2(pv[it][2 * e], pv[it][2 * e + 1]);
-      if (sizeof(TIn) == 1) v = make_float2(__fdiv_rn(v.x, 255.f), __fdiv_rn(v.y, 255.f));
-      split_bf16(v, h[e], l[e]);
-    }
-    reinterpret_cast<uint2 *>(hi_s)[i] = make_uint2(h[0], h[1]);  // i enumerates (c, r, 4-column group) = the plane layout
-    reinterpret_cast<uint2 *>(lo_s)[i] = make_uint2(l[0], l[1]);
-  }
-  __syncthreads();
-
-  // ---- layer 0: 17 x 33 region, 16 channels, tensor cores ----
-  {
-    uint32_t bf[3][2][2];
-#pragma unroll
-    for (int s = 0; s < 3; ++s)
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const uint2 v = reinterpret_cast<const uint2 *>(w_s)[(s * 2 + j) * 32 + lane];
-        bf[s][j][0] = v.x; bf[s][j][1] = v.y;
-      }
-    // this thread's two (ci, ky) combinations per k-step and its column slot
-    int off0[3], off2[3];
-    const int kx = 2 * (t & 1);  // slot pair (-1, 0) or (1, 2) = patch columns 2x + kx, 2x + kx + 1
-#pragma unroll
-    for (int s = 0; s < 3; ++s) {
-      const int c0 = min(4 * s + (t >> 1), 8), c2 = min(4 * s + 2 + (t >> 1), 8);  // combos >= 9 carry zero weights
-      off0[s] = ((c0 / 3) * kInH + c0 % 3) * kInW + kx;
-      off2[s] = ((c2 / 3) * kInH + c2 % 3) * kInW + kx;
-    }
-    const int ly0 = 2 * oy0 - 1, lx0 = 2 * ox0 - 1;  // layer-0 coordinates of the region origin
-    constexpr int kSegs = (kL0Px + 15) / 16;
-    for (int seg = warp; seg < kSegs; seg += kThreads / 32) {
-      const int p0 = min(seg * 16 + g, kL0Px - 1), p1 = min(seg * 16 + g + 8, kL0Px - 1);
-      const int y0 = p0 / kL0W, x0 = p0 % kL0W, y1 = p1 / kL0W, x1 = p1 % kL0W;
-      const int r0 = 2 * y0 * kInW + 2 * x0, r1 = 2 * y1 * kInW + 2 * x1;
-      float acc[2][4];
-#pragma unroll
-      for (int j = 0; j < 2; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-#pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        uint32_t hi[4], lo[4];
-        hi[0] = *reinterpret_cast<const uint32_t *>(hi_s + r0 + off0[s]); lo[0] = *reinterpret_cast<const uint32_t *>(lo_s + r0 + off0[s]);
-        hi[1] = *reinterpret_cast<const uint32_t *>(hi_s + r1 + off0[s]); lo[1] = *reinterpret_cast<const uint32_t *>(lo_s + r1 + off0[s]);
-        hi[2] = *reinterpret_cast<const uint32_t *>(hi_s + r0 + off2[s]); lo[2] = *reinterpret_cast<const uint32_t *>(lo_s + r0 + off2[s]);
-        hi[3] = *reinterpret_cast<const uint32_t *>(hi_s + r1 + off2[s]); lo[3] = *reinterpret_cast<const uint32_t *>(lo_s + r1 + off2[s]);
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          mma16816(acc[j], hi, bf[s][j][0], bf[s][j][1]);
-          mma16816(acc[j], lo, bf[s][j][0], bf[s][j][1]);
-        }
-      }
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int p = seg * 16 + g + 8 * half;
-        if (p >= kL0Px) continue;
-        const int y = half ? y1 : y0, x = half ? x1 : x0;
-        const bool inside = (unsigned)(ly0 + y) < (unsigned)(a.ih / 2) && (unsigned)(lx0 + x) < (unsigned)(a.iw / 2);
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int c = 8 * j + 2 * t;
-          const float v0 = fmaxf(acc[j][2 * half] + b_s[c], 0.f), v1 = fmaxf(acc[j][2 * half + 1] + b_s[c + 1], 0.f);
-          *reinterpret_cast<uint32_t *>(l0_s + p * kL0Pitch + c) = inside ? pack_bf16(v0, v1) : 0u;
-        }
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- layer 1: warp w = output row oy0 + w, 16 pixels x 32 channels, one tap per k-step ----
-  {
-    float acc[4][4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-    const uint2 *wf = reinterpret_cast<const uint2 *>(w_s + 6 * 64);
-#pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      const int r = tap / 3, s = tap % 3;
-      const __nv_bfloat16 *p0 = l0_s + ((2 * warp + r) * kL0W + 2 * g + s) * kL0Pitch + 2 * t;
-      uint32_t af[4];
-      af[0] = *reinterpret_cast<const uint32_t *>(p0);
-      af[1] = *reinterpret_cast<const uint32_t *>(p0 + 16 * kL0Pitch);
-      af[2] = *reinterpret_cast<const uint32_t *>(p0 + 8);
-      af[3] = *reinterpret_cast<const uint32_t *>(p0 + 16 * kL0Pitch + 8);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint2 b = wf[(tap * 4 + j) * 32 + lane];
-        mma16816(acc[j], af, b.x, b.y);
-      }
-    }
-    // bias, ReLU, bf16 -> staging (the frame patch is dead: every warp passed the barrier above) -> 16-byte stores
-    __nv_bfloat16 *st = stage_s + warp * 16 * 32;
-#pragma unroll
-    for (int half = 0; half < 2; ++half)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c = 8 * j + 2 * t;
-        const float v0 = fmaxf(acc[j][2 * half] + b_s[16 + c], 0.f), v1 = fmaxf(acc[j][2 * half + 1] + b_s[16 + c + 1], 0.f);
-        *reinterpret_cast<uint32_t *>(st + (g + 8 * half) * 32 + c) = pack_bf16(v0, v1);
-      }
-    __syncwarp();
-    const int oy = oy0 + warp;
-    if (oy < a.oh) {
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int px = (lane >> 2) + 8 * i, ch = (lane & 3) * 8;
-        if (ox0 + px < a.ow)
-          *reinterpret_cast<uint4 *>(a.out + (((long long)n * a.oh + oy) * a.ow + ox0 + px) * a.out_pitch + ch) =
-              *reinterpret_cast<const uint4 *>(st + px * 32 + ch);
-      }
-    }
-  }
-}
-
-// =================================================================================================
-// Second generation (design and lane maps: stem_v2.cuh).  Lives in uyd::stemv2 so that the header's constants win
-// over the first generation's equally named ones above.
-// =================================================================================================
 }  // namespace
 namespace stemv2 {
 __device__ __forceinline__ void mma1688_tf32(float (&d)[4], const uint4 &a, uint32_t b0, uint32_t b1) {
@@ -519,46 +305,15 @@ __global__ void __launch_bounds__(stemv2::kThreads, PERSIST ? 2 : 3) stem_v2_ker
   }  // tile loop
 }
 }  // namespace stemv2
-namespace {
-
-uint32_t pack2(float lo, float hi) {
-  __nv_bfloat16 x = __float2bfloat16_rn(lo), y = __float2bfloat16_rn(hi);
-  uint16_t ux, uy;
-  memcpy(&ux, &x, 2);
-  memcpy(&uy, &y, 2);
-  return (uint32_t)ux | ((uint32_t)uy << 16);
-}
-
-// B fragments of mma.m16n8k16 for K x N weights given by wfun(k, n)
-template <class F>
-void pack_frags(std::vector<uint32_t> &out, int ksteps, int ntiles, F wfun) {
-  for (int s = 0; s < ksteps; ++s)
-    for (int j = 0; j < ntiles; ++j)
-      for (int lane = 0; lane < 32; ++lane) {
-        const int g = lane >> 2, t = lane & 3, n = 8 * j + g;
-        out.push_back(pack2(wfun(16 * s + 2 * t, n), wfun(16 * s + 2 * t + 1, n)));
-        out.push_back(pack2(wfun(16 * s + 2 * t + 8, n), wfun(16 * s + 2 * t + 9, n)));
-      }
-}
-
-}  // namespace
-
 bool stem_fused_supported(int c0, int c1, int ih, int iw, int out_pitch, int out_coff) {
   return c0 == 16 && c1 == 32 && ih % 4 == 0 && iw % 4 == 0 && out_pitch % 8 == 0 && out_coff % 8 == 0;
 }
 
 // w0 [16][3][3][3], w1 [32][16][3][3] (BN folded, PyTorch layout)
-// frags = [legacy | second generation (stem_v2.cuh)], bias = [16 | 32 | 16 (1x1, zero without w2)]
+// frags = stem_v2.cuh fragments, bias = [16 | 32 | 16 (1x1, zero without w2)]
 void stem_fused_pack(const float *w0, const float *b0, const float *w1, const float *b1, const float *w2, const float *b2,
                      std::vector<uint32_t> &frags, std::vector<float> &bias) {
   frags.clear();
-  pack_frags(frags, 3, 2, [&](int k, int n) {  // k = (ci * 3 + ky) * 4 + slot, slot <-> kx = slot - 1
-    const int combo = k / 4, kx = k % 4 - 1;
-    return (combo < 9 && kx >= 0) ? w0[((size_t)n * 3 + combo / 3) * 9 + (combo % 3) * 3 + kx] : 0.f;
-  });
-  pack_frags(frags, 9, 4, [&](int k, int n) {  // k = tap * 16 + ci
-    return w1[((size_t)n * 16 + k % 16) * 9 + k / 16];
-  });
   bias.assign(64, 0.f);
   for (int i = 0; i < 16; ++i) bias[i] = b0[i];
   for (int i = 0; i < 32; ++i) bias[16 + i] = b1[i];
@@ -568,7 +323,6 @@ void stem_fused_pack(const float *w0, const float *b0, const float *w1, const fl
 
 static int stem_v2_launch(const StemArgs &a0, cudaStream_t s) {
   StemArgs a = a0;
-  a.wfrag += (6 + 36) * 64;  // skip the legacy fragments
   static const bool persist = [] { const char *v = getenv("UYD_STEM_PERSIST"); return !(v && *v == '0'); }();
   const int sms = current_sm_count();
   UYD_REQUIRE(sms > 0, UYD_E_NOGPU, "stem: no current CUDA device");
@@ -595,16 +349,6 @@ static int stem_v2_launch(const StemArgs &a0, cudaStream_t s) {
   return pers ? go(stem_v2_kernel<float, false, true>, true) : go(stem_v2_kernel<float, false, false>, false);
 }
 
-int stem_fused_launch(const StemArgs &a, cudaStream_t s) {
-  static const bool legacy = [] { const char *v = getenv("UYD_STEM_LEGACY"); return v && *v == '1'; }();
-  if (!legacy || a.pw || a.cam) return stem_v2_launch(a, s);
-  const size_t smem = (size_t)2 * 3 * kInH * kInW * 2 + (size_t)(kL0Px + 19) * kL0Pitch * 2 + (6 + 36) * 64 * 4 + 48 * 4;
-  if (int e = smem_optin(stem_fused_kernel<float>, smem)) return e;
-  if (int e = smem_optin(stem_fused_kernel<uint8_t>, smem)) return e;
-  dim3 grid(ceil_div(a.ow, kTW), ceil_div(a.oh, kTH), a.n);
-  if (a.u8) stem_fused_kernel<uint8_t><<<grid, kThreads, smem, s>>>(a);
-  else stem_fused_kernel<float><<<grid, kThreads, smem, s>>>(a);
-  return (int)cudaGetLastError();
-}
+int stem_fused_launch(const StemArgs &a, cudaStream_t s) { return stem_v2_launch(a, s); }
 
 }  // namespace uyd
