@@ -51,6 +51,7 @@ struct ChainParams {
   float *y;                                 // decoded output [B, no, a_total] or null
   int a_total, a_off, y_ch0, no;
   float stride_px;
+  unsigned tpi, m_tpi, m_tx;  // tiles per image and the fastdiv magics of tiles-per-image / tiles_x
   long long *dbg;  // UYD_CHAIN_TIMELINE: clock64 stamps of CTA 0, [tile][8]
 };
 
@@ -60,7 +61,8 @@ constexpr int kNG = 3;                              // epilogue groups (4 warps 
 constexpr int kChainThreads = 128 + 128 * kNG;       // TMA, GEMM1 issuer, GEMM2 issuer, (idle), epilogue groups
 constexpr int kHaloRows = 18, kTileH = 16, kTileW = 8, kHaloPitch = kTileW + 2;
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// ex2.approx + rcp.approx (2 ulp): identical to decode.cu's, so the fused and the stand-alone decode agree bit for bit
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 // packed fp32 FMA (FFMA2 on sm_100): d = a * b + c on both halves
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
@@ -138,9 +140,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     bias2_s[i] = i < p.N2 ? p.bias2[i] : 0.f;
   }
   if (p.final_kind == CH_PW3) {
-    for (int i = threadIdx.x; i < 8 * 64; i += kChainThreads) {  // shared layout [k][8 classes]: one 16-byte load per 4 classes
-      const int k = i >> 3, c = i & 7;
-      w3_s[i] = (c < p.nc && k < p.N2) ? p.w3[c * p.N2 + k] : 0.f;
+    for (int i = threadIdx.x; i < 8 * 64; i += kChainThreads) {  // shared layout [channel pair][8 classes][2]: the FFMA2 operand
+      const int k = i >> 3, c = i & 7;                           // pairs (even, odd channel) of two classes per 16-byte load
+      w3_s[((k >> 1) * 8 + c) * 2 + (k & 1)] = (c < p.nc && k < p.N2) ? p.w3[c * p.N2 + k] : 0.f;
     }
     if (threadIdx.x < 8) bias3_s[threadIdx.x] = threadIdx.x < p.nc ? p.bias3[threadIdx.x] : 0.f;
   }
@@ -151,7 +153,6 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
   const uint32_t tmem_base = *slot_ptr;
   griddep_wait();  // from here on the activations written by the previous kernel are read
 
-  const int tiles_per_img = p.tiles_x * p.tiles_y;
   const int stages = p.stages;
   const uint32_t blk_bytes = p.blk_bytes, cb_bytes = p.cb_bytes;
   const uint32_t cb2_bytes = (uint32_t)p.N1 * 2u;  // one row of the GEMM2 A / B operands
@@ -162,8 +163,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     uint32_t phase = 0;
     const int cb_elems = (int)cb_bytes / 2;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const unsigned ut = (unsigned)tile, img = ut / (unsigned)tiles_per_img, t = ut - img * (unsigned)tiles_per_img;
-      const unsigned ty = t / (unsigned)p.tiles_x;
+      const unsigned ut = (unsigned)tile, img = fastdiv(ut, p.tpi, p.m_tpi), t = ut - img * p.tpi;
+      const unsigned ty = fastdiv(t, (unsigned)p.tiles_x, p.m_tx);
       const int n = p.n0 + (int)img;
       const int y0 = (int)ty * kTileH, x0 = (int)(t - ty * (unsigned)p.tiles_x) * kTileW;
       for (int j = 0; j < p.ncb; ++j) {
@@ -252,6 +253,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     // DW: this thread's channel quad (4 channels x 9 taps) and bias, in registers for the whole launch
     float2 dw_wlo[9], dw_whi[9], dw_blo = make_float2(0.f, 0.f), dw_bhi = dw_blo;
+    uint32_t dw_in_off[3][4] = {};
+    int dw_in_base = 0, dw_out_base = 0;
+    int dw_stage = g % stages;                       // pipeline stage / phase of this group's current tile (tile g, g + kNG, ...)
+    uint32_t dw_phase = (uint32_t)(g / stages) & 1u;
     if constexpr (DW) {
       constexpr int C = KS1 * 16;
       const int qd = m % (C / 4);
@@ -264,33 +269,50 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
       const float4 b4 = *reinterpret_cast<const float4 *>(p.bias1 + 4 * qd);
       dw_blo = make_float2(b4.x, b4.y);
       dw_bhi = make_float2(b4.z, b4.w);
+      // Shared-memory addressing of the depth-wise stage, hoisted out of the tile loop.  Halo pixel index of (input row
+      // i, column dx) = p0 + 10 i + dx with p0 = 10 R half + xx; the TMA / UMMA swizzle XORs the 16-byte chunk index
+      // with (pixel >> 1) & 3 (64-byte rows) or pixel & 7 (128-byte rows), and 10 i = 2 i (mod 8): the phase only
+      // depends on i & 3, so twelve byte offsets per thread cover every load and the row term is an immediate.
+      constexpr int NQ = C / 4, R = 16 / (128 / (NQ * 8));
+      const int xx = (m / NQ) & 7, half = m / (NQ * 8);
+      const int p0 = half * R * kHaloPitch + xx;
+      dw_in_base = p0 * (C * 2);
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+        for (int ph = 0; ph < 4; ++ph) {
+          const int pi = p0 + dx + kHaloPitch * ph;  // any row with i & 3 == ph has the same swizzle phase
+          const uint32_t sw = C == 64 ? (uint32_t)(pi & 7) : (uint32_t)((pi >> 1) & 3);
+          dw_in_off[dx][ph] = (uint32_t)(dx * (C * 2)) + ((((uint32_t)qd >> 1) ^ sw) << 4) + (uint32_t)(qd & 1) * 8u;
+        }
+      // output pixel pm = 8 (R half + r) + xx: its phase (pm & 7, resp. (pm >> 1) & 3) is xx's -> one constant + r * immediate
+      const int pm0 = half * R * 8 + xx;
+      const uint32_t sw2 = C == 64 ? (uint32_t)(pm0 & 7) : (uint32_t)((pm0 >> 1) & 3);
+      dw_out_base = pm0 * (C * 2) + (int)(((((uint32_t)qd >> 1) ^ sw2) << 4) + (uint32_t)(qd & 1) * 8u);
     }
     // group g takes tiles g, g + kNG, ... of this CTA's sequence; tile indices fit 32 bits (checked on the host)
     int it = g;
     uint32_t ph = 0;
     for (long long tile = blockIdx.x + (long long)g * gridDim.x; tile < p.total_tiles; tile += (long long)kNG * gridDim.x, it += kNG, ph ^= 1u) {
-      const unsigned ut = (unsigned)tile, img = ut / (unsigned)tiles_per_img, t = ut - img * (unsigned)tiles_per_img;
-      const unsigned ty = t / (unsigned)p.tiles_x, tx = t - ty * (unsigned)p.tiles_x;
+      const unsigned ut = (unsigned)tile, img = fastdiv(ut, p.tpi, p.m_tpi), t = ut - img * p.tpi;
+      const unsigned ty = fastdiv(t, (unsigned)p.tiles_x, p.m_tx), tx = t - ty * (unsigned)p.tiles_x;
       const int n = p.n0 + (int)img;
       const int oy = (int)ty * kTileH + (m >> 3), ox = (int)tx * kTileW + (m & 7);
       const bool inside = oy < p.H && ox < p.W;
       if constexpr (DW) {
         // ---- stage 1 (depth-wise): halo box -> 3x3 depth-wise conv on CUDA cores -> bias, ReLU -> bf16 -> A of GEMM2 ----
-        constexpr int C = KS1 * 16, NQ = C / 4, NH = 128 / (NQ * 8), R = 16 / NH;  // rows per thread: 8 (C = 32) / 16 (C = 64)
-        const int qd = m % NQ, xx = (m / NQ) & 7, half = m / (NQ * 8);
-        const int sidx = it % stages;
-        mbar_wait(full0 + 8u * sidx, (uint32_t)(it / stages) & 1u);
-        const unsigned char *hb = smem_dyn + (a_s + (uint32_t)sidx * blk_bytes - raw);
-        unsigned char *a2_tile = smem_dyn + (a2_s + (uint32_t)g * p.a2_bytes - raw);
+        constexpr int C = KS1 * 16, R = 16 / (128 / ((C / 4) * 8));  // rows per thread: 8 (C = 32) / 16 (C = 64)
+        mbar_wait(full0 + 8u * dw_stage, dw_phase);
+        const int sidx = dw_stage;
+        const unsigned char *hb = smem_dyn + (a_s + (uint32_t)sidx * blk_bytes - raw) + dw_in_base;
+        unsigned char *a2_out = smem_dyn + (a2_s + (uint32_t)g * p.a2_bytes - raw) + dw_out_base;
         float2 a0[3], a1[3];  // accumulators of three output rows in flight, ring-indexed by row % 3
 #pragma unroll
         for (int i = 0; i < R + 2; ++i) {
           float2 v0[3], v1[3];
 #pragma unroll
-          for (int dx = 0; dx < 3; ++dx) {
-            const int pi = (half * R + i) * kHaloPitch + xx + dx;
-            const uint32_t sw = C == 64 ? (uint32_t)(pi & 7) : (uint32_t)((pi >> 1) & 3);
-            const uint2 h2 = *reinterpret_cast<const uint2 *>(hb + pi * (C * 2) + ((((uint32_t)qd >> 1) ^ sw) << 4) + (qd & 1) * 8);
+          for (int dx = 0; dx < 3; ++dx) {  // address = tile base + per-thread constant (swizzle phase i & 3) + immediate
+            const uint2 h2 = *reinterpret_cast<const uint2 *>(hb + i * (kHaloPitch * C * 2) + dw_in_off[dx][i & 3]);
             v0[dx] = make_float2(__uint_as_float(h2.x << 16), __uint_as_float(h2.x & 0xffff0000u));
             v1[dx] = make_float2(__uint_as_float(h2.y << 16), __uint_as_float(h2.y & 0xffff0000u));
           }
@@ -305,15 +327,16 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
               o0 = ffma2(v0[dx], dw_wlo[tr * 3 + dx], o0);
               o1 = ffma2(v1[dx], dw_whi[tr * 3 + dx], o1);
             }
-            if (tr == 2) {
-              const int pm = (half * R + r) * 8 + xx;
-              const uint32_t sw2 = C == 64 ? (uint32_t)(pm & 7) : (uint32_t)((pm >> 1) & 3);
-              *reinterpret_cast<uint2 *>(a2_tile + pm * (C * 2) + ((((uint32_t)qd >> 1) ^ sw2) << 4) + (qd & 1) * 8) =
-                  make_uint2(relu_pack_bf16x2(o0.x, o0.y), relu_pack_bf16x2(o1.x, o1.y));
-            }
+            if (tr == 2)
+              *reinterpret_cast<uint2 *>(a2_out + r * (8 * C * 2)) = make_uint2(relu_pack_bf16x2(o0.x, o0.y), relu_pack_bf16x2(o1.x, o1.y));
           }
         }
         mbar_arrive(empty0 + 8u * sidx);  // this thread's reads of the halo box are done
+#pragma unroll
+        for (int w = 0, nx = dw_stage + kNG; w < kNG; ++w) {  // this group's next tile is kNG tiles on: at most kNG wraps
+          if (nx >= stages) { nx -= stages; dw_phase ^= 1u; }
+          dw_stage = nx;
+        }
       } else {
       // ---- stage 1: acc1 -> bias, ReLU -> bf16 -> swizzled shared-memory tile (A of GEMM2) ----
         mbar_wait(tfull1 + 8u * g, ph);
@@ -410,9 +433,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
           yo[3ll * p.a_total] = (y2 - y1) * p.stride_px;
         }
       } else if (p.final_kind == CH_PW3) {
-        float lg[8];
+        // logits: acc[c] = (sum over even channels, sum over odd channels) of z * w3[c]; a bf16 pair of z IS an FFMA2
+        // operand, so one packed FMA covers two channels of one class (64 instead of 128 FMAs for nc <= 4)
+        float2 acc[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) lg[c] = bias3_s[c];
+        for (int c = 0; c < 8; ++c) acc[c] = make_float2(bias3_s[c], 0.f);
         uint32_t cur[16], nxt[16];
         tmem_ld16_issue(t2, cur);
         tmem_ld_wait();
@@ -427,27 +452,23 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
           float bv[16];
           load_bias16(bias2_s + ch * 16, bv);
           // z2 is a bf16 activation in the unfused graph: ReLU + round it the same way before the last conv
-          // (one cvt.rn.relu.bf16x2 per pair, unpacked with a shift / mask); the nc > 4 half is a separate loop
+          // (one cvt.rn.relu.bf16x2 per pair, unpacked with a shift / mask)
 #pragma unroll
-          for (int h0 = 0; h0 < 16; h0 += 4) {
-            float z[4];
-#pragma unroll
-            for (int i = 0; i < 4; i += 2) {
-              const uint32_t pk = relu_pack_bf16x2(__uint_as_float(cur[h0 + i]) + bv[h0 + i], __uint_as_float(cur[h0 + i + 1]) + bv[h0 + i + 1]);
-              z[i] = __uint_as_float(pk << 16);
-              z[i + 1] = __uint_as_float(pk & 0xffff0000u);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 wa = *reinterpret_cast<const float4 *>(w3_s + (ch * 16 + h0 + i) * 8);
-              lg[0] = fmaf(z[i], wa.x, lg[0]); lg[1] = fmaf(z[i], wa.y, lg[1]); lg[2] = fmaf(z[i], wa.z, lg[2]); lg[3] = fmaf(z[i], wa.w, lg[3]);
-            }
+          for (int i = 0; i < 16; i += 2) {
+            const uint32_t pk = relu_pack_bf16x2(__uint_as_float(cur[i]) + bv[i], __uint_as_float(cur[i + 1]) + bv[i + 1]);
+            const float2 zz = make_float2(__uint_as_float(pk << 16), __uint_as_float(pk & 0xffff0000u));
+            const float4 *wp = reinterpret_cast<const float4 *>(w3_s + (ch * 8 + (i >> 1)) * 16);
+            const float4 w01 = wp[0], w23 = wp[1];
+            acc[0] = ffma2(zz, make_float2(w01.x, w01.y), acc[0]);
+            acc[1] = ffma2(zz, make_float2(w01.z, w01.w), acc[1]);
+            acc[2] = ffma2(zz, make_float2(w23.x, w23.y), acc[2]);
+            acc[3] = ffma2(zz, make_float2(w23.z, w23.w), acc[3]);
             if (p.nc > 4) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float4 wb = *reinterpret_cast<const float4 *>(w3_s + (ch * 16 + h0 + i) * 8 + 4);
-                lg[4] = fmaf(z[i], wb.x, lg[4]); lg[5] = fmaf(z[i], wb.y, lg[5]); lg[6] = fmaf(z[i], wb.z, lg[6]); lg[7] = fmaf(z[i], wb.w, lg[7]);
-              }
+              const float4 w45 = wp[2], w67 = wp[3];
+              acc[4] = ffma2(zz, make_float2(w45.x, w45.y), acc[4]);
+              acc[5] = ffma2(zz, make_float2(w45.z, w45.w), acc[5]);
+              acc[6] = ffma2(zz, make_float2(w67.x, w67.y), acc[6]);
+              acc[7] = ffma2(zz, make_float2(w67.z, w67.w), acc[7]);
             }
           }
           if (more) {
@@ -456,6 +477,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
             for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
           }
         }
+        float lg[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) lg[c] = acc[c].x + acc[c].y;
         if (inside) {
           if (p.out) {
             float *op = reinterpret_cast<float *>(p.out) + pix * p.out_pitch;
@@ -611,6 +635,9 @@ int chain_prepare(ChainConv *cc, int cin, int n1, int n2, void *in_base, int in_
   UYD_REQUIRE(final_kind != CH_PW3 || (nc >= 1 && nc <= 8 && w3_dev && bias3_dev), UYD_E_UNSUPPORTED, "conv_chain: PW3 needs nc <= 8");
   p.tiles_x = ceil_div(w, kTileW);
   p.tiles_y = ceil_div(h, kTileH);
+  p.tpi = (unsigned)(p.tiles_x * p.tiles_y);
+  p.m_tpi = fastdiv_magic(p.tpi);
+  p.m_tx = fastdiv_magic((unsigned)p.tiles_x);
   p.blk_bytes = ((uint32_t)kHaloRows * kHaloPitch * p.cb_bytes + 1023u) & ~1023u;
   p.tx_bytes = (uint32_t)kHaloRows * kHaloPitch * p.cb_bytes;
   p.w1_bytes = dw1 ? 0u : (uint32_t)chain_w1_bytes(cin, n1, false);

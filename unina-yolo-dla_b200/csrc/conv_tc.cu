@@ -78,6 +78,7 @@ struct TcParams {
   uint32_t wblk_bytes;   // one weight block (N x 128 B) in shared memory
   uint32_t tile_off;     // byte offset of the second M-tile inside an A block
   int pairs_x;           // 16 x 16 pixel regions per image row (HALO / PERTAP)
+  unsigned tpi, m_tpi, m_tx;  // tiles (pairs) per image and the fastdiv magics of tiles-per-image / tiles per row
 };
 
 namespace {
@@ -357,7 +358,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
   const int blocks_per_tile = p.mode == TC_PERTAP ? p.ncb * p.taps : p.ncb;  // HALO / PAIRS: all taps from one block
   const int cb_elems = I8 ? p.cb_bytes : p.cb_bytes / 2;
-  const int tiles_per_img = p.tiles_x * p.tiles_y;
   const int stages = p.stages;
   const uint32_t blk_bytes = p.blk_bytes, cb_bytes = p.cb_bytes;
 
@@ -368,8 +368,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       int n = 0, x0 = 0, y0 = 0;
       if (p.mode != TC_FLAT) {
-        const unsigned ut = (unsigned)tile, img = ut / (unsigned)tiles_per_img, t = ut - img * (unsigned)tiles_per_img;
-        const unsigned ty = t / (unsigned)p.tiles_x;
+        const unsigned ut = (unsigned)tile, img = fastdiv(ut, p.tpi, p.m_tpi), t = ut - img * p.tpi;
+        const unsigned ty = fastdiv(t, (unsigned)p.tiles_x, p.m_tx);
         n = p.n0 + (int)img;
         y0 = (int)ty * kTileH;
         x0 = (int)(t - ty * (unsigned)p.tiles_x) * kTileW;
@@ -510,8 +510,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           ppix = (long long)((img * (unsigned)(p.H >> 1) + (oy >> 1)) * (unsigned)(p.W >> 1) + (ox >> 1));
         }
       } else {
-        const unsigned ut = (unsigned)tile, img = ut / (unsigned)tiles_per_img, t = ut - img * (unsigned)tiles_per_img;
-        const unsigned ty = t / (unsigned)p.tiles_x, tx = t - ty * (unsigned)p.tiles_x;
+        const unsigned ut = (unsigned)tile, img = fastdiv(ut, p.tpi, p.m_tpi), t = ut - img * p.tpi;
+        const unsigned ty = fastdiv(t, (unsigned)p.tiles_x, p.m_tx), tx = t - ty * (unsigned)p.tiles_x;
         const int n = p.n0 + (int)img;
         const int oy = (int)ty * kTileH + (m >> 3), ox = (int)tx * kTileW + (m & 7);
         pix = (oy < p.H && ox < p.W) ? ((long long)n * p.H + oy) * p.W + ox : -1;
@@ -618,7 +618,6 @@ __global__ void __launch_bounds__(kBigThreads, 1) conv_tc_big_kernel(const __gri
 
   const int kblocks = p.ncb * p.taps;                                   // weight blocks per pair
   const bool a_per_tap = p.mode == TC_PERTAP;                           // else one A block per channel block
-  const int pairs_per_img = p.pairs_x * p.tiles_y;
   const long long total = p.total_tiles;                                // pairs of this launch
 
   if (warp == 0) {
@@ -628,8 +627,8 @@ __global__ void __launch_bounds__(kBigThreads, 1) conv_tc_big_kernel(const __gri
     for (long long pair = blockIdx.x; pair < total; pair += gridDim.x) {
       int n = 0, x0 = 0, y0 = 0;
       if (p.mode != TC_FLAT) {
-        const unsigned up = (unsigned)pair, img = up / (unsigned)pairs_per_img, t = up - img * (unsigned)pairs_per_img;
-        const unsigned ty = t / (unsigned)p.pairs_x;
+        const unsigned up = (unsigned)pair, img = fastdiv(up, p.tpi, p.m_tpi), t = up - img * p.tpi;
+        const unsigned ty = fastdiv(t, (unsigned)p.pairs_x, p.m_tx);
         n = p.n0 + (int)img;
         y0 = (int)ty * 16;
         x0 = (int)(t - ty * (unsigned)p.pairs_x) * 16;
@@ -726,8 +725,8 @@ __global__ void __launch_bounds__(kBigThreads, 1) conv_tc_big_kernel(const __gri
         const unsigned row = (unsigned)pair * 256u + (unsigned)g * 128u + (unsigned)m;
         pix = row < (unsigned)p.nb * hw ? (long long)((unsigned)p.n0 * hw + row) : -1;
       } else {
-        const unsigned up = (unsigned)pair, img = up / (unsigned)pairs_per_img, t = up - img * (unsigned)pairs_per_img;
-        const unsigned ty = t / (unsigned)p.pairs_x, tx = t - ty * (unsigned)p.pairs_x;
+        const unsigned up = (unsigned)pair, img = fastdiv(up, p.tpi, p.m_tpi), t = up - img * p.tpi;
+        const unsigned ty = fastdiv(t, (unsigned)p.pairs_x, p.m_tx), tx = t - ty * (unsigned)p.pairs_x;
         const int oy = (int)ty * 16 + (m >> 3), ox = (int)tx * 16 + g * 8 + (m & 7);
         pix = (oy < p.H && ox < p.W) ? ((long long)(p.n0 + (int)img) * p.H + oy) * p.W + ox : -1;
       }
@@ -1112,6 +1111,10 @@ int tc_launch(const TcConv *tc, int n0, int nb, int sm_count, cudaStream_t s) {
   TcParams p = tc->p;
   p.n0 = n0;
   p.nb = nb;
+  p.tpi = (unsigned)((p.big ? p.pairs_x : p.tiles_x) * p.tiles_y);
+  if (p.tpi == 0) p.tpi = 1;
+  p.m_tpi = fastdiv_magic(p.tpi);
+  p.m_tx = fastdiv_magic((unsigned)(p.big ? p.pairs_x : p.tiles_x));
   if (p.big) {
     p.total_tiles = p.mode == TC_FLAT ? ((long long)nb * p.H * p.W + 255) / 256 : (long long)nb * p.pairs_x * p.tiles_y;
     if (p.total_tiles == 0) return UYD_OK;

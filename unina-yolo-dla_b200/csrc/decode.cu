@@ -10,7 +10,7 @@ namespace {
 
 constexpr int kThreads = 256;
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }  // as in conv_chain.cu
 // The reference's device sigmoid, statement for statement (gpu_postprocess.cu:62-64): full-accuracy expf and an IEEE
 // division, so the TLBR confidences are bit-identical to what decode_yolo_head_kernel produces on the same GPU.
 __device__ __forceinline__ float sigmoid_ref(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }

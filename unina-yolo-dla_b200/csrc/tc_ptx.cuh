@@ -124,8 +124,19 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// n / d for a divisor fixed per launch: q = umulhi(n, floor(2^32 / d)) is the quotient or one below it, one
+// compare fixes it up (a runtime 32-bit division is ~20 instructions, and every epilogue warp splits its tile index
+// into (image, tile row, tile column) once per tile).  magic = fastdiv_magic(d) is computed on the host.
+__device__ __forceinline__ unsigned fastdiv(unsigned n, unsigned d, unsigned magic) {
+  unsigned q = __umulhi(n, magic);
+  if (n - q * d >= d) ++q;
+  return q;
+}
+
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 }  // namespace
+
+inline unsigned fastdiv_magic(unsigned d) { return d <= 1 ? 0xFFFFFFFFu : (unsigned)((1ull << 32) / d); }
 
 }  // namespace uyd
