@@ -35,3 +35,7 @@ for frac, cluster in ((0.02, False), (0.05, False), (0.05, True), (0.2, True), (
     det, cnt = m.nms(ys, 0.25, 0.7, 300)
     n = (ys[:, 4:].amax(1) > 0.25).sum(1).float().mean()
     print(f"synthetic frac {frac} cluster {cluster}: cand/img {float(n):.0f} kept/img {float(cnt.float().mean()):.0f} nms ms {t_ms(lambda: m.nms(ys, 0.25, 0.7, 300)):.3f}")
+# phase split on the bench prediction: a threshold nothing passes = the scan alone; max_det = 1 = scan + sort + one chunk
+print("scan only (conf 2.0): ms", t_ms(lambda: m.nms(y, 2.0, 0.7, 300)))
+print("scan + sort + first chunk (max_det 1): ms", t_ms(lambda: m.nms(y, 0.25, 0.7, 1)))
+print("iou 1.0 (nothing suppressed, stops at 300 kept): ms", t_ms(lambda: m.nms(y, 0.25, 1.0, 300)))
