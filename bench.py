@@ -59,6 +59,8 @@ def parse():
                     help="N = 1: also time the model.py variant (UninaCustomB200, the pinned-oracle network) at this batch (0 = skip)")
     ap.add_argument("--c4-batch", type=int, default=256, metavar="BATCH",
                     help="every N: also time BASELINE config 4's per-GPU batch (resident and e2e), 0 = skip")
+    ap.add_argument("--host-mem", default="pinned", choices=["pinned", "wc"],
+                    help="host staging buffers of the e2e run: torch pinned memory, or write-combined pinned memory (uyd_host_alloc)")
     ap.add_argument("--sustain", type=float, default=2.0, metavar="SECONDS",
                     help="also run the resident step back to back for at least this long, with clocks (0 = skip)")
     return ap.parse_args()
@@ -367,7 +369,15 @@ def main():
     model = build_models(S, False).to(dev)
     gen = torch.Generator(device=dev).manual_seed(100 + rank)
     x_dev = torch.rand(B, 3, S, S, device=dev, generator=gen)                       # resident fp32 frames
-    x_host = (torch.rand(B, 3, S, S, generator=torch.Generator().manual_seed(200 + rank)) * 255).to(torch.uint8).pin_memory()
+    x_host = (torch.rand(B, 3, S, S, generator=torch.Generator().manual_seed(200 + rank)) * 255).to(torch.uint8)
+    if a.host_mem == "wc":
+        from unina_yolo_dla_b200.hostmem import pinned_frames
+
+        wc = pinned_frames(x_host.shape, torch.uint8, write_combined=True)
+        wc.copy_(x_host)
+        x_host = wc
+    else:
+        x_host = x_host.pin_memory()
     x_u8 = torch.empty_like(x_host, device=dev)
     model.calibrate_cls_bias(x_dev[: min(B, 8)], CANDIDATES_PER_IMAGE, CONF)
     plan = model.plan_for(x_dev, fused=True)   # the plan predict runs: head kernels decode in their epilogue
@@ -487,6 +497,26 @@ def main():
     h2d_ms = min(timed(h2d_only, 1) for _ in range(2)) / a.steps
     probe["h2d_only_ms_per_step"] = h2d_ms
     probe["h2d_only_gbs_per_gpu"] = x_host.numel() / (h2d_ms * 1e-3) / 1e9
+    # the same streamed run fed with NV12 camera frames (1.5 bytes per pixel over PCIe; the stem converts on load)
+    nv_host = torch.randint(0, 256, (B, S * 3 // 2, S), dtype=torch.uint8, generator=torch.Generator().manual_seed(600 + rank)).pin_memory()
+
+    def run_stream_nv12(steps):
+        pending = None
+        for det, cnt in model.predict_stream((nv_host for _ in range(steps)), CONF, IOU, MAX_DET, to_host=world == 1, camera="nv12"):
+            if world > 1:
+                h = gatherer.start(det, cnt)
+                if pending is not None:
+                    gd, gc = pending.wait()
+                    det_host.copy_(gd[rank * B:(rank + 1) * B], non_blocking=True)
+                    cnt_host.copy_(gc[rank * B:(rank + 1) * B], non_blocking=True)
+                pending = h
+        if pending is not None:
+            gd, gc = pending.wait()
+            det_host.copy_(gd[rank * B:(rank + 1) * B], non_blocking=True)
+            cnt_host.copy_(gc[rank * B:(rank + 1) * B], non_blocking=True)
+
+    run_stream_nv12(2)
+    ms_nv12 = min(timed(lambda: run_stream_nv12(a.steps), 1) for _ in range(2))
     # sustained: the resident step back to back for >= a.sustain seconds, clocks sampled throughout
     sustained = None
     if a.sustain > 0:
@@ -584,6 +614,11 @@ def main():
                 "bound_probe": dict(probe, note="the same streamed run with the gather (N > 1) or the H2D copy switched off, and the H2D copies "
                                                 "alone on all ranks at once: e2e ms_per_step ~ max(resident step, h2d_only) means the "
                                                 "host-to-device path of the box bounds e2e")},
+        "e2e_nv12": {"value": world * B * a.steps / (ms_nv12 * 1e-3), "unit": UNIT, "ms_per_step": ms_nv12 / a.steps,
+                     "h2d_bytes_per_step": nv_host.numel(), "d2h_bytes_per_step": det_host.numel() * 4 + cnt_host.numel() * 4,
+                     "api": "predict_stream(camera='nv12'): pinned host NV12 frames (Y rows + interleaved UV rows) -> H2D -> the stem reads the "
+                            "planes itself (uyd_plan_run_camera) -> decode -> NMS -> D2H (+ gather at N > 1); an additional record, "
+                            "the headline e2e stays on uint8 NCHW frames"},
         "gpu_launches": kernels_per_step * a.steps,
         "roofline": {"kernel": top_text, "bound": "tensor" if tensor_bound else "hbm", "achieved": achieved, "peak": peak,
                      "unit": unit, "frac": achieved / peak, "traffic": traffic, "peak_source": pk["src"],

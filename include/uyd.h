@@ -361,6 +361,12 @@ typedef struct uyd_camera_frames {
 } uyd_camera_frames;
 int uyd_plan_run_camera(uyd_plan *plan, const uyd_camera_frames *frames, int batch, float *y, uyd_stream stream);
 
+/* Pinned host staging memory for frame batches (cudaHostAlloc).  write_combined != 0: write-combined pages -- the
+ * producer (camera driver, decoder) fills them sequentially, the GPU reads them over PCIe without cache snooping;
+ * do not read them back on the CPU. */
+int uyd_host_alloc(size_t bytes, int write_combined, void **out);
+int uyd_host_free(void *p);
+
 /* Plain device-to-device copy on `stream` (lets a host binding without a CUDA runtime of
  * its own read plan buffers into memory it owns). */
 int uyd_memcpy_d2d(void *dst, const void *src, size_t bytes, uyd_stream stream);

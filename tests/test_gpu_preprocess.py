@@ -142,3 +142,18 @@ def test_camera_bytes_feed_the_stem_directly(ref):
     assert float((y_cam[:, 4:] - y_ref[:, 4:]).abs().max()) <= 2e-3
     det, cnt = m.predict_camera(cam, conf=0.05)
     assert det.shape == (3, 300, 6) and cnt.shape == (3,)
+
+
+def test_predict_stream_nv12_equals_predict_camera():
+    """The streaming API on camera frames: NV12 host batches [B, 3H/2, W] -> same rows as predict_camera per batch."""
+    import unina_yolo_dla_b200 as uyd
+
+    m = uyd.UninaYoloB200.from_yaml().init_synthetic(seed=0).cuda()
+    g = torch.Generator().manual_seed(21)
+    batches = [torch.randint(0, 256, (n, 480, 320), generator=g, dtype=torch.uint8).pin_memory() for n in (6, 6, 3)]
+    got = [(d.clone(), c.clone()) for d, c in m.predict_stream(iter(batches), conf=0.05, camera="nv12")]
+    assert len(got) == 3
+    for (d, c), b in zip(got, batches):
+        bd = b.cuda()
+        wd, wc = m.predict_camera(bd[:, :320], uv=bd[:, 320:], conf=0.05)
+        assert torch.equal(c, wc.cpu()) and torch.equal(d, wd.cpu())

@@ -824,6 +824,19 @@ extern "C" int uyd_plan_run_decoded(uyd_plan *plan, const void *x, int x_dtype, 
   return run_ops(plan, x, x_dtype == UYD_F32 ? 1 : 2, batch, stream, y);
 }
 
+// Pinned host staging memory for frames (cudaHostAlloc): write_combined != 0 asks for write-combined pages, which the
+// CPU fills sequentially and the GPU reads over PCIe without snooping the CPU caches.
+extern "C" int uyd_host_alloc(size_t bytes, int write_combined, void **out) {
+  UYD_REQUIRE(out && bytes > 0, UYD_E_ARG, "uyd_host_alloc: bad arguments");
+  UYD_CUDA(cudaHostAlloc(out, bytes, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault));
+  return UYD_OK;
+}
+
+extern "C" int uyd_host_free(void *p) {
+  if (p) UYD_CUDA(cudaFreeHost(p));
+  return UYD_OK;
+}
+
 extern "C" int uyd_plan_run_camera(uyd_plan *plan, const uyd_camera_frames *f, int batch, float *y, uyd_stream stream) {
   UYD_REQUIRE(plan && plan->finalized && f && f->data, UYD_E_ARG, "uyd_plan_run_camera: plan not finalized / NULL frames");
   UYD_REQUIRE(!plan->ops.empty() && plan->ops[0].kind == OP_STEM2, UYD_E_UNSUPPORTED,

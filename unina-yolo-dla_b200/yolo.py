@@ -759,7 +759,7 @@ class UninaYoloB200(nn.Module):
 
         if self.training:
             raise RuntimeError("UninaYoloB200 implements the inference path only: call .eval()")
-        assert frames.is_cuda and frames.dtype == torch.uint8 and frames.is_contiguous()
+        assert frames.is_cuda and frames.dtype == torch.uint8 and frames.stride(-1) == 1
         nv12 = uv is not None
         B, H, W = frames.shape[:3]
         oh, ow = (H, W) if (nv12 or size is None) else size
@@ -772,7 +772,7 @@ class UninaYoloB200(nn.Module):
         f.frame_stride = frames.stride(0)
         f.data = frames.data_ptr()
         if nv12:
-            assert uv.is_cuda and uv.dtype == torch.uint8 and uv.is_contiguous() and uv.shape[0] == B
+            assert uv.is_cuda and uv.dtype == torch.uint8 and uv.stride(-1) == 1 and uv.shape[0] == B
             f.uv, f.uv_pitch, f.uv_frame_stride = uv.data_ptr(), uv.stride(1), uv.stride(0)
         f.norm = norm if norm is not None else _lib.NormParams(0.0, 0.0, 0.0, 1.0, 1.0, 1.0)
         y = torch.empty(B, 4 + self.nc, self.num_anchors(oh, ow), dtype=torch.float32, device=frames.device)
@@ -883,14 +883,19 @@ class UninaYoloB200(nn.Module):
 
     @torch.no_grad()
     def predict_stream(self, batches, conf: float = 0.25, iou: float = 0.7, max_det: int = 300, max_nms: int = 30000,
-                       to_host: bool = True):
+                       to_host: bool = True, camera: str | None = None, size=None, norm=None):
         """Generator form of ``predict`` (the reference consumes ``YOLO.predict(..., stream=True)``,
         train.py:396-423): ``batches`` yields host frame batches ``[B,3,H,W]`` (uint8 or float, ideally
         pinned).  Batch i+1 is copied host->device on a copy stream while batch i computes, so a
         steady-state step costs max(copy, compute) instead of their sum.  Yields, in order,
         ``(det[B,max_det,6], count[B])`` -- pinned host tensors (``to_host``) or device tensors;
         either stays valid while the generator is advanced twice more (the pinned result buffers rotate
-        through a ring of four, separate from the two input staging slots)."""
+        through a ring of four, separate from the two input staging slots).
+        ``camera``: the batches are camera frames read by the stem itself (``forward_camera``): ``"nv12"`` = uint8
+        ``[B, 3H/2, W]`` (the Y rows followed by the interleaved UV rows: 1.5 bytes per pixel over PCIe instead of 3),
+        ``"bgra"`` = uint8 ``[B, H, W, 4]`` (resampled to ``size`` when given); ``norm`` as in ``forward_camera``."""
+        if camera not in (None, "nv12", "bgra"):
+            raise ValueError("camera must be None, 'nv12' or 'bgra'")
         if not torch.cuda.is_available():
             raise _lib.UydError("no CUDA device: the B200 path has no CPU fallback")
         prm = next(self.parameters())
@@ -904,7 +909,7 @@ class UninaYoloB200(nn.Module):
         main_s = torch.cuda.current_stream(device)
         # staging slots, pinned result buffers, copy stream and events are allocated once per
         # (frame shape, dtype, max_det) and reused by later calls: cudaHostAlloc alone costs milliseconds
-        skey = (device, tuple(first.shape), first.dtype, max_det, to_host)
+        skey = (device, tuple(first.shape), first.dtype, max_det, to_host, camera)
         state = self.__dict__.setdefault("_stream_state", {}).get(skey)
         if state is None:
 
@@ -958,7 +963,13 @@ class UninaYoloB200(nn.Module):
             r = outs[i % 4]
             main_s.wait_event(s.ready)
             r.n = s.n_in
-            r.det, r.cnt = self.predict_batched(s.x[: r.n], conf, iou, max_det, max_nms)
+            if camera == "nv12":
+                hh = s.x.shape[1] * 2 // 3
+                r.det, r.cnt = self.predict_camera(s.x[: r.n, :hh], None, norm, s.x[: r.n, hh:], conf, iou, max_det, max_nms)
+            elif camera == "bgra":
+                r.det, r.cnt = self.predict_camera(s.x[: r.n], size, norm, None, conf, iou, max_det, max_nms)
+            else:
+                r.det, r.cnt = self.predict_batched(s.x[: r.n], conf, iou, max_det, max_nms)
             s.free.record(main_s)
             if to_host:
                 r.det_h[: r.n].copy_(r.det, non_blocking=True)
