@@ -30,42 +30,79 @@ namespace {
 
 struct CamIn {};  // TIn tag of the camera instantiations of stem_v2_kernel
 
-// One model-input pixel (iy, ix) from the camera frame, normalised like cuda_preprocess.cu:99-253:
-// ((v / 255) - mean) / std with IEEE divisions; BGRA bilinear taps and BT.601 NV12 in the reference's operand order.
-__device__ __forceinline__ float cam_norm(float v, float mean, float stdv) { return __fdiv_rn(__fsub_rn(__fdiv_rn(v, 255.0f), mean), stdv); }
-
-__device__ __forceinline__ void cam_pixel(const StemArgs &a, const uint8_t *frame, const uint8_t *uvp, int iy, int ix, float (&rgb)[3]) {
-  float r, g, b;
-  if (a.cam == 2) {
-    const float Y = frame[(long long)iy * a.src_pitch + ix];
-    const uint8_t *q = uvp + (long long)(iy / 2) * a.uv_pitch + (ix / 2) * 2;
-    const float U = q[0] - 128.0f, V = q[1] - 128.0f;
-    r = Y + 1.402f * V;
-    g = Y - 0.344136f * U - 0.714136f * V;
-    b = Y + 1.772f * U;
-    r = fmaxf(0.0f, fminf(255.0f, r)); g = fmaxf(0.0f, fminf(255.0f, g)); b = fmaxf(0.0f, fminf(255.0f, b));
-  } else if (a.src_w == a.iw && a.src_h == a.ih) {
-    const uint32_t px = *reinterpret_cast<const uint32_t *>(frame + (long long)iy * a.src_pitch + 4 * ix);
-    b = (float)(px & 0xFF); g = (float)((px >> 8) & 0xFF); r = (float)((px >> 16) & 0xFF);
-  } else {
-    const float ratio_x = (float)a.src_w / a.iw, ratio_y = (float)a.src_h / a.ih;
-    const float sx = fmaxf(0.0f, fminf((ix + 0.5f) * ratio_x - 0.5f, a.src_w - 1.0f));
-    const float sy = fmaxf(0.0f, fminf((iy + 0.5f) * ratio_y - 0.5f, a.src_h - 1.0f));
-    const int xa = (int)sx, ya = (int)sy, xb = min(xa + 1, a.src_w - 1), yb = min(ya + 1, a.src_h - 1);
-    const float fx = sx - xa, fy = sy - ya;
-    const float waa = (1.0f - fx) * (1.0f - fy), wab = fx * (1.0f - fy), wba = (1.0f - fx) * fy, wbb = fx * fy;
-    const uint8_t *ra = frame + (long long)ya * a.src_pitch, *rb = frame + (long long)yb * a.src_pitch;
-    const uint32_t paa = *reinterpret_cast<const uint32_t *>(ra + 4 * xa), pab = *reinterpret_cast<const uint32_t *>(ra + 4 * xb);
-    const uint32_t pba = *reinterpret_cast<const uint32_t *>(rb + 4 * xa), pbb = *reinterpret_cast<const uint32_t *>(rb + 4 * xb);
-    auto mix = [&](int sh) {
-      return waa * (float)((paa >> sh) & 0xFF) + wab * (float)((pab >> sh) & 0xFF) + wba * (float)((pba >> sh) & 0xFF) +
-             wbb * (float)((pbb >> sh) & 0xFF);
-    };
-    r = mix(16); g = mix(8); b = mix(0);
+// Camera frames -> normalised model-input values, semantics of cuda_preprocess.cu:99-253: ((v / 255) - mean) / std,
+// BGRA bilinear taps with the half-pixel rule, BT.601 NV12.  v / 255 is q = v * r corrected by one FMA step (the IEEE
+// quotient for every integer v, stemv2::div255; within an ulp otherwise -- the patch is rounded to tf32 right after);
+// the mean / std step is skipped for the unit normalisation the YAML model is fed with and uses an IEEE division
+// otherwise, so that a BGRA frame of the model's extent gives bit-identical results to the reference kernel's tensor.
+struct CamNorm {
+  float mean[3], stdv[3];
+  bool unit;
+  __device__ __forceinline__ float operator()(float v, int c) const {
+    const float q = stemv2::div255(v);
+    return unit ? q : __fdiv_rn(__fsub_rn(q, mean[c]), stdv[c]);
   }
-  rgb[0] = cam_norm(r, a.mean[0], a.stdv[0]);
-  rgb[1] = cam_norm(g, a.mean[1], a.stdv[1]);
-  rgb[2] = cam_norm(b, a.mean[2], a.stdv[2]);
+};
+
+// four horizontally adjacent model-input pixels (iy, ix .. ix + 3), ix % 4 == 0
+__device__ __forceinline__ void cam_row4(const StemArgs &a, const CamNorm &nm, const uint8_t *frame, const uint8_t *uvp, int iy, int ix,
+                                         float (&px)[4][3]) {
+  if (a.cam == 2) {  // NV12: 4 luma bytes + 2 (U, V) pairs = two 32-bit loads when the planes are 4-byte aligned
+    const uint8_t *yr = frame + (long long)iy * a.src_pitch + ix;
+    const uint8_t *ur = uvp + (long long)(iy / 2) * a.uv_pitch + ix;
+    uint32_t y4, uv4;
+    if (((a.src_pitch | a.uv_pitch) & 3) == 0 && ((reinterpret_cast<uintptr_t>(frame) | reinterpret_cast<uintptr_t>(uvp)) & 3) == 0) {
+      y4 = *reinterpret_cast<const uint32_t *>(yr);
+      uv4 = *reinterpret_cast<const uint32_t *>(ur);
+    } else {
+      y4 = yr[0] | (yr[1] << 8) | (yr[2] << 16) | ((uint32_t)yr[3] << 24);
+      uv4 = ur[0] | (ur[1] << 8) | (ur[2] << 16) | ((uint32_t)ur[3] << 24);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float Y = (float)((y4 >> (8 * j)) & 0xFF);
+      const float U = (float)((uv4 >> (16 * (j >> 1))) & 0xFF) - 128.0f, V = (float)((uv4 >> (16 * (j >> 1) + 8)) & 0xFF) - 128.0f;
+      float r = Y + 1.402f * V, g = Y - 0.344136f * U - 0.714136f * V, b = Y + 1.772f * U;
+      r = fmaxf(0.0f, fminf(255.0f, r)); g = fmaxf(0.0f, fminf(255.0f, g)); b = fmaxf(0.0f, fminf(255.0f, b));
+      px[j][0] = nm(r, 0); px[j][1] = nm(g, 1); px[j][2] = nm(b, 2);
+    }
+  } else if (a.src_w == a.iw && a.src_h == a.ih) {  // BGRA at the model's extent: one pixel = one 32-bit word
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(frame + (long long)iy * a.src_pitch + 4 * ix);
+    uint32_t w[4];
+    if (((a.src_pitch | (int)(a.frame_stride & 15)) & 15) == 0 && (reinterpret_cast<uintptr_t>(frame) & 15) == 0) {
+      const uint4 v = *reinterpret_cast<const uint4 *>(q);
+      w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) w[j] = q[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      px[j][0] = nm((float)((w[j] >> 16) & 0xFF), 0);
+      px[j][1] = nm((float)((w[j] >> 8) & 0xFF), 1);
+      px[j][2] = nm((float)(w[j] & 0xFF), 2);
+    }
+  } else {  // BGRA + bilinear resize: the row terms once, four taps of 32-bit pixels per output pixel
+    const float ratio_x = (float)a.src_w / a.iw, ratio_y = (float)a.src_h / a.ih;
+    const float sy = fmaxf(0.0f, fminf((iy + 0.5f) * ratio_y - 0.5f, a.src_h - 1.0f));
+    const int ya = (int)sy, yb = min(ya + 1, a.src_h - 1);
+    const float fy = sy - ya;
+    const uint8_t *ra = frame + (long long)ya * a.src_pitch, *rb = frame + (long long)yb * a.src_pitch;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float sx = fmaxf(0.0f, fminf((ix + j + 0.5f) * ratio_x - 0.5f, a.src_w - 1.0f));
+      const int xa = (int)sx, xb = min(xa + 1, a.src_w - 1);
+      const float fx = sx - xa;
+      const float waa = (1.0f - fx) * (1.0f - fy), wab = fx * (1.0f - fy), wba = (1.0f - fx) * fy, wbb = fx * fy;
+      const uint32_t paa = *reinterpret_cast<const uint32_t *>(ra + 4 * xa), pab = *reinterpret_cast<const uint32_t *>(ra + 4 * xb);
+      const uint32_t pba = *reinterpret_cast<const uint32_t *>(rb + 4 * xa), pbb = *reinterpret_cast<const uint32_t *>(rb + 4 * xb);
+      auto mix = [&](int sh) {
+        return waa * (float)((paa >> sh) & 0xFF) + wab * (float)((pab >> sh) & 0xFF) + wba * (float)((pba >> sh) & 0xFF) +
+               wbb * (float)((pbb >> sh) & 0xFF);
+      };
+      px[j][0] = nm(mix(16), 0); px[j][1] = nm(mix(8), 1); px[j][2] = nm(mix(0), 2);
+    }
+  }
 }
 
 }  // namespace
@@ -147,14 +184,16 @@ __global__ void __launch_bounds__(stemv2::kThreads, PERSIST ? 2 : 3) stem_v2_ker
   if constexpr (kCam) {  // camera bytes -> normalised fp32 bit patterns of the four columns of every row this thread owns
     const uint8_t *frame = reinterpret_cast<const uint8_t *>(a.in) + (long long)n * a.frame_stride;
     const uint8_t *uvp = a.uv ? a.uv + (long long)n * a.uv_frame_stride : nullptr;
+    CamNorm nm;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { nm.mean[c] = a.mean[c]; nm.stdv[c] = a.stdv[c]; }
+    nm.unit = a.mean[0] == 0.f && a.mean[1] == 0.f && a.mean[2] == 0.f && a.stdv[0] == 1.f && a.stdv[1] == 1.f && a.stdv[2] == 1.f;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       float px[4][3];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        px[j][0] = px[j][1] = px[j][2] = 0.f;
-        if (ok[k]) cam_pixel(a, frame, uvp, iy0 + prl + kRowLanes * k, ix + j, px[j]);
-      }
+      for (int j = 0; j < 4; ++j) px[j][0] = px[j][1] = px[j][2] = 0.f;
+      if (ok[k]) cam_row4(a, nm, frame, uvp, iy0 + prl + kRowLanes * k, ix, px);
 #pragma unroll
       for (int c = 0; c < 3; ++c)
         pv[c][k] = make_uint4(__float_as_uint(px[0][c]), __float_as_uint(px[1][c]), __float_as_uint(px[2][c]), __float_as_uint(px[3][c]));
