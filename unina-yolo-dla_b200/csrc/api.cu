@@ -40,19 +40,6 @@ int current_sm_count() {
   return sms[dev];
 }
 
-// Makes `device` current for the lifetime of the guard and restores the caller's device afterwards: no entry
-// point changes the caller's (or torch's) current device.
-struct DeviceGuard {
-  int prev = -1;
-  cudaError_t err = cudaSuccess;
-  explicit DeviceGuard(int device) {
-    err = cudaGetDevice(&prev);
-    if (err == cudaSuccess && prev != device) err = cudaSetDevice(device);
-    else if (err == cudaSuccess) prev = -1;
-  }
-  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
-};
-
 // conv_tc.cu
 struct TcConv;
 bool tc_supported(const uyd_conv &d, int in_pitch, int in_coff, int out_pitch, int out_coff, bool in_is_network_input);
@@ -187,6 +174,15 @@ struct uyd_plan {
   int timed_op = -1, timed_used = 0;  // uyd_plan_set_timed_op
   std::vector<cudaEvent_t> timed_ev;
 };
+
+namespace uyd {
+int ctx_device(const uyd_ctx *ctx) {
+  if (ctx) return ctx->device;
+  int d = 0;
+  cudaGetDevice(&d);
+  return d;
+}
+}  // namespace uyd
 
 extern "C" int uyd_version(void) { return 100; }
 extern "C" const char *uyd_last_error(void) { return g_err; }
@@ -537,6 +533,7 @@ extern "C" int uyd_plan_slice_absmax(uyd_plan *plan, int buf, int coff, int c, i
   if ((e = check_slice(plan, buf, coff, c, "absmax"))) return e;
   const Buffer &b = plan->bufs[buf];
   UYD_REQUIRE(b.dtype == UYD_BF16 && batch > 0 && batch <= plan->max_batch, UYD_E_ARG, "absmax: bf16 slice, batch within the plan");
+  uyd::DeviceGuard guard(plan->ctx->device);
   return absmax_launch((const __nv_bfloat16 *)((char *)b.ptr + (size_t)coff * 2), b.c, (long long)batch * b.h * b.w, c, d_bits,
                        (cudaStream_t)stream);
 }
@@ -548,6 +545,7 @@ extern "C" int uyd_plan_slice_histogram(uyd_plan *plan, int buf, int coff, int c
   if ((e = check_slice(plan, buf, coff, c, "histogram"))) return e;
   const Buffer &b = plan->bufs[buf];
   UYD_REQUIRE(b.dtype == UYD_BF16 && batch > 0 && batch <= plan->max_batch, UYD_E_ARG, "histogram: bf16 slice, batch within the plan");
+  uyd::DeviceGuard guard(plan->ctx->device);
   return abs_histogram_launch((const __nv_bfloat16 *)((char *)b.ptr + (size_t)coff * 2), b.c, (long long)batch * b.h * b.w, c, inv_width,
                               nbins, d_hist, (cudaStream_t)stream);
 }
@@ -984,6 +982,7 @@ extern "C" int uyd_plan_op_info(uyd_plan *plan, int op, char *text, size_t text_
 extern "C" int uyd_plan_run_decode(uyd_plan *plan, float *y, int batch, uyd_stream stream) {
   UYD_REQUIRE(plan && plan->finalized && !plan->heads.empty(), UYD_E_STATE, "plan has no heads / not finalized");
   UYD_REQUIRE(y && batch > 0 && batch <= plan->max_batch, UYD_E_ARG, "uyd_plan_run_decode: bad arguments");
+  uyd::DeviceGuard guard(plan->ctx->device);
   int a_total = 0;
   for (int h : plan->heads) a_total += plan->bufs[h].h * plan->bufs[h].w;
   int a_off = 0;
@@ -1007,11 +1006,16 @@ extern "C" int uyd_plan_export_head_nchw(uyd_plan *plan, int level, float *out, 
   UYD_REQUIRE(plan && plan->finalized && level >= 0 && level < (int)plan->heads.size() && out, UYD_E_ARG,
               "uyd_plan_export_head_nchw: bad arguments");
   const Buffer &b = plan->bufs[plan->heads[level]];
+  uyd::DeviceGuard guard(plan->ctx->device);
   return nhwc_to_nchw_f32_launch((const float *)b.ptr, out, batch, b.h, b.w, b.c, (cudaStream_t)stream);
 }
 
 extern "C" int uyd_memcpy_d2d(void *dst, const void *src, size_t bytes, uyd_stream stream) {
   UYD_REQUIRE(dst && src, UYD_E_ARG, "uyd_memcpy_d2d: NULL pointer");
+  cudaPointerAttributes at;  // run on the device that owns the destination (the stream must belong to it)
+  int dev = -1;
+  if (cudaPointerGetAttributes(&at, dst) == cudaSuccess && at.type == cudaMemoryTypeDevice) dev = at.device;
+  uyd::DeviceGuard guard(dev >= 0 ? dev : uyd::ctx_device(nullptr));
   UYD_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return UYD_OK;
 }

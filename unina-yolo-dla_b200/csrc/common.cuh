@@ -43,6 +43,20 @@ template <class K>
 inline int smem_optin(K *kernel, size_t bytes) { return smem_optin_impl(reinterpret_cast<const void *>(kernel), (int)bytes); }
 int current_sm_count();  // SM count of the current device (cached per device)
 
+// Makes `device` current for the lifetime of the guard and restores the caller's device afterwards: no entry
+// point changes the caller's (or torch's) current device.
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int device) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != device) err = cudaSetDevice(device);
+    else if (err == cudaSuccess) prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+int ctx_device(const uyd_ctx *ctx);  // the handle's device (the current device for a NULL handle)
+
 #ifdef __CUDACC__
 // Lets a successor launched with programmatic stream serialization (the tcgen05 kernels, tc_ptx.cuh) start its
 // prologue while this kernel is still running; the successor still waits for this kernel's completion before

@@ -148,17 +148,17 @@ int decode_dfl_launch(const float *head, int batch, int h, int w, int reg_max, i
 
 extern "C" int uyd_decode_dfl(uyd_ctx *ctx, const float *head, int batch, int h, int w, int reg_max, int nc,
                               float stride, float *y, int a_total, int a_off, uyd_stream stream) {
-  (void)ctx;
   UYD_REQUIRE(head && y && batch > 0 && h > 0 && w > 0, UYD_E_ARG, "uyd_decode_dfl: bad arguments");
+  uyd::DeviceGuard guard(uyd::ctx_device(ctx));
   return uyd::decode_dfl_launch(head, batch, h, w, reg_max, nc, stride, y, a_total, a_off, (cudaStream_t)stream, 0.f);
 }
 
 extern "C" int uyd_decode_tlbr(uyd_ctx *ctx, const float *d_cls, const float *d_reg, uyd_detection *dets, int *cell_idx,
                                int *d_count, int cap, int grid_w, int grid_h, int stride, int num_classes,
                                float conf_thr, float conformal_q, int strict, int cell_base, uyd_stream stream) {
-  (void)ctx;
   UYD_REQUIRE(d_cls && d_reg && dets && d_count && cap > 0 && grid_w > 0 && grid_h > 0, UYD_E_ARG,
               "uyd_decode_tlbr: bad arguments");
+  uyd::DeviceGuard guard(uyd::ctx_device(ctx));
   const int hw = grid_w * grid_h;
   uyd::decode_tlbr_kernel<<<uyd::ceil_div(hw, uyd::kThreads), uyd::kThreads, 0, (cudaStream_t)stream>>>(
       d_cls, d_reg, dets, cell_idx, d_count, cap, grid_w, grid_h, stride, num_classes, conf_thr, conformal_q, strict, cell_base);

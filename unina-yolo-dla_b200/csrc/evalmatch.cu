@@ -217,9 +217,9 @@ __global__ void __launch_bounds__(kThreads) small_object_metric_kernel(const flo
 extern "C" int uyd_small_object_metric_update(uyd_ctx *ctx, const float *pred, const int *count, int batch, int max_det, const float *gt,
                                               const int *gt_count, int gt_max, double size_thr, double iou_thr, double image_size,
                                               unsigned long long *counters, uyd_stream stream) {
-  (void)ctx;
   UYD_REQUIRE(pred && count && gt && gt_count && counters && batch > 0 && max_det > 0 && gt_max > 0, UYD_E_ARG,
               "uyd_small_object_metric_update: bad arguments");
+  uyd::DeviceGuard guard(uyd::ctx_device(ctx));
   UYD_REQUIRE(gt_max <= uyd::kMaxGt, UYD_E_UNSUPPORTED, "uyd_small_object_metric_update: at most %d ground truths per image", uyd::kMaxGt);
   uyd::small_object_metric_kernel<<<batch, uyd::kThreads, 0, (cudaStream_t)stream>>>(pred, count, max_det, gt, gt_count, gt_max, size_thr,
                                                                                       iou_thr, image_size, counters);
@@ -229,9 +229,9 @@ extern "C" int uyd_small_object_metric_update(uyd_ctx *ctx, const float *pred, c
 extern "C" int uyd_eval_update(uyd_ctx *ctx, const float *det, const int *count, int batch, int max_det, const float *gt,
                                const int *gt_count, int gt_max, float size_thr, float small_iou_thr, float match_iou_thr,
                                unsigned long long *counters, float *scores, uyd_stream stream) {
-  (void)ctx;
   UYD_REQUIRE(det && count && gt && gt_count && counters && batch > 0 && max_det > 0 && gt_max > 0, UYD_E_ARG,
               "uyd_eval_update: bad arguments");
+  uyd::DeviceGuard guard(uyd::ctx_device(ctx));
   UYD_REQUIRE(gt_max <= uyd::kMaxGt && max_det <= uyd::kMaxDet, UYD_E_UNSUPPORTED, "uyd_eval_update: at most %d ground truths / %d detections per image",
               uyd::kMaxGt, uyd::kMaxDet);
   uyd::eval_update_kernel<<<batch, uyd::kThreads, 0, (cudaStream_t)stream>>>(det, count, max_det, gt, gt_count, gt_max, size_thr,

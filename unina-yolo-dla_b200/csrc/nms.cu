@@ -609,8 +609,9 @@ extern "C" int uyd_nms(uyd_ctx *ctx, const float *y, int batch, int nc, int anch
                        int max_nms, int max_det, float max_wh, void *workspace, size_t workspace_bytes, float *out_det,
                        int *out_idx, int *out_count, uyd_stream stream) {
   using namespace uyd;
-  (void)ctx; (void)workspace; (void)workspace_bytes;
+  (void)workspace; (void)workspace_bytes;
   UYD_REQUIRE(y && out_det && out_count && batch > 0 && nc > 0 && anchors > 0, UYD_E_ARG, "uyd_nms: bad arguments");
+  DeviceGuard guard(ctx_device(ctx));
   UYD_REQUIRE(nc <= 256 && anchors < (1 << kAnchorBits), UYD_E_UNSUPPORTED, "uyd_nms: nc <= 256 and anchors < 4M per image");
   UYD_REQUIRE(max_det > 0 && max_det <= kMaxDetCap, UYD_E_UNSUPPORTED, "uyd_nms: max_det <= %d", kMaxDetCap);
   if (max_nms > anchors) max_nms = anchors;
@@ -630,8 +631,9 @@ extern "C" int uyd_nms_detections(uyd_ctx *ctx, const uyd_detection *dets, const
                                   float iou_thr, void *workspace, size_t workspace_bytes, uyd_detection *out,
                                   int *d_out_count, uyd_stream stream) {
   using namespace uyd;
-  (void)ctx; (void)workspace; (void)workspace_bytes;
+  (void)workspace; (void)workspace_bytes;
   UYD_REQUIRE(dets && d_count && out && d_out_count && cap > 0, UYD_E_ARG, "uyd_nms_detections: bad arguments");
+  DeviceGuard guard(ctx_device(ctx));
   UYD_REQUIRE(out != dets, UYD_E_ARG, "uyd_nms_detections: out must not alias dets (use uyd_nms_detections_inplace)");
   return launch_records<false>(const_cast<uyd_detection *>(dets), cell_idx, d_count, 0, cap, iou_thr, out, d_out_count,
                                (cudaStream_t)stream);
@@ -640,8 +642,8 @@ extern "C" int uyd_nms_detections(uyd_ctx *ctx, const uyd_detection *dets, const
 extern "C" int uyd_nms_detections_inplace(uyd_ctx *ctx, uyd_detection *dets, const int *cell_idx, int n, float iou_thr,
                                           int *d_out_count, uyd_stream stream) {
   using namespace uyd;
-  (void)ctx;
   UYD_REQUIRE(dets && n >= 0 && n <= kMaxDetCap, UYD_E_ARG, "uyd_nms_detections_inplace: 0 <= n <= %d", kMaxDetCap);
+  DeviceGuard guard(ctx_device(ctx));
   if (n == 0) return UYD_OK;
   return launch_records<true>(dets, cell_idx, nullptr, n, n, iou_thr, nullptr, d_out_count, (cudaStream_t)stream);
 }
@@ -649,8 +651,8 @@ extern "C" int uyd_nms_detections_inplace(uyd_ctx *ctx, uyd_detection *dets, con
 extern "C" int uyd_compact_valid(uyd_ctx *ctx, const uyd_detection *dets, int n, uyd_detection *out, int *d_out_count,
                                  uyd_stream stream) {
   using namespace uyd;
-  (void)ctx;
   UYD_REQUIRE(dets && out && d_out_count && n >= 0 && n <= kMaxDetCap, UYD_E_ARG, "uyd_compact_valid: 0 <= n <= %d", kMaxDetCap);
+  DeviceGuard guard(ctx_device(ctx));
   compact_valid_kernel<<<1, kRThreads, 0, (cudaStream_t)stream>>>(dets, n, out, d_out_count);
   return (int)cudaGetLastError();
 }

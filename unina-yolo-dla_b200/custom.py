@@ -261,7 +261,7 @@ class UninaCustomB200(nn.Module):
         cell = torch.zeros(cap, dtype=torch.int32, device=dev)
         cnt = torch.zeros(2, dtype=torch.int32, device=dev)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        stream = C.c_void_p(torch.cuda.current_stream(di).cuda_stream)
         results = []
         for b in range(B):
             cnt.zero_()

@@ -35,7 +35,7 @@ class DetectionEvaluator:
         check(_lib.lib().uyd_eval_update(_lib.context(dev), C.c_void_p(det.data_ptr()), C.c_void_p(cnt.data_ptr()), B, max_det,
                                          C.c_void_p(gt.data_ptr()), C.c_void_p(gt_cnt.data_ptr()), gt.shape[1], self.size_threshold,
                                          self.small_iou, self.match_iou, C.c_void_p(self.counters.data_ptr()),
-                                         C.c_void_p(scores.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                                         C.c_void_p(scores.data_ptr()), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
               "uyd_eval_update")
         self._scores.append(scores)
 
@@ -134,7 +134,7 @@ class SmallObjectMetric:
         check(_lib.lib().uyd_small_object_metric_update(
             _lib.context(dev), C.c_void_p(pred.data_ptr()), C.c_void_p(cnt.data_ptr()), pred.shape[0], pred.shape[1],
             C.c_void_p(gt.data_ptr()), C.c_void_p(gt_cnt.data_ptr()), gt.shape[1], float(self.size_threshold), float(self.iou_threshold),
-            float(self.image_size), C.c_void_p(self._counters.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+            float(self.image_size), C.c_void_p(self._counters.data_ptr()), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
             "uyd_small_object_metric_update")
 
     @torch.no_grad()

@@ -225,9 +225,8 @@ class Plan:
         return self
 
     # ---- execution ---------------------------------------------------------------------
-    @staticmethod
-    def _stream() -> C.c_void_p:
-        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    def _stream(self) -> C.c_void_p:
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)   # the plan's device, not the current one
 
     def run(self, x: torch.Tensor, y: torch.Tensor | None = None) -> None:
         """Runs every op; ``y`` ([B, no, A] fp32) receives the decoded prediction of plans whose head
@@ -292,7 +291,7 @@ class Plan:
         check(_lib.lib().uyd_memcpy_d2d(C.c_void_p(full.data_ptr()), ptr, nbytes, self._stream()), "uyd_memcpy_d2d")
         full[..., s.coff:s.coff + s.c] = nchw.to(full.device).permute(0, 2, 3, 1).to(tdt)
         check(_lib.lib().uyd_memcpy_d2d(ptr, C.c_void_p(full.data_ptr()), nbytes, self._stream()), "uyd_memcpy_d2d")
-        torch.cuda.current_stream().synchronize()
+        torch.cuda.current_stream(self.device).synchronize()
 
     def decode(self, y: torch.Tensor, batch: int) -> None:
         check(_lib.lib().uyd_plan_run_decode(self.handle, C.c_void_p(y.data_ptr()), batch, self._stream()),

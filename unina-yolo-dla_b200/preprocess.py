@@ -18,8 +18,8 @@ def norm_params(mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)) -> NormPa
 UNIT = NormParams(0.0, 0.0, 0.0, 1.0, 1.0, 1.0)   # plain x / 255
 
 
-def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(t: torch.Tensor):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
 
 def bgra(frames: torch.Tensor, params: NormParams = UNIT, size: tuple[int, int] | None = None) -> torch.Tensor:
@@ -30,12 +30,17 @@ def bgra(frames: torch.Tensor, params: NormParams = UNIT, size: tuple[int, int] 
     oh, ow = size or (H, W)
     out = torch.empty(B, 3, oh, ow, dtype=torch.float32, device=frames.device)
     L = _lib.lib()
+    with torch.cuda.device(frames.device):   # the reference entry points carry no device: they run on the current one
+        return _bgra(L, frames, out, params, size, B, H, W, oh, ow)
+
+
+def _bgra(L, frames, out, params, size, B, H, W, oh, ow):
     if size is None or (oh, ow) == (H, W):
         check(L.uyd_preprocess_bgra_batch(C.c_void_p(frames.data_ptr()), C.c_void_p(out.data_ptr()), B, H * W * 4, W, H, W * 4,
-                                          params, _stream()), "uyd_preprocess_bgra_batch")
+                                          params, _stream(frames)), "uyd_preprocess_bgra_batch")
     else:
         check(L.uyd_preprocess_bgra_resize_batch(C.c_void_p(frames.data_ptr()), C.c_void_p(out.data_ptr()), B, H * W * 4, W, H,
-                                                 W * 4, ow, oh, params, _stream()), "uyd_preprocess_bgra_resize_batch")
+                                                 W * 4, ow, oh, params, _stream(frames)), "uyd_preprocess_bgra_resize_batch")
     return out
 
 
@@ -44,6 +49,7 @@ def nv12(y_plane: torch.Tensor, uv_plane: torch.Tensor, params: NormParams = UNI
     assert y_plane.is_cuda and uv_plane.is_cuda and y_plane.dtype == torch.uint8 and uv_plane.dtype == torch.uint8
     H, W = y_plane.shape
     out = torch.empty(1, 3, H, W, dtype=torch.float32, device=y_plane.device)
-    check(_lib.lib().uyd_preprocess_nv12(C.c_void_p(y_plane.data_ptr()), C.c_void_p(uv_plane.data_ptr()), C.c_void_p(out.data_ptr()),
-                                         W, H, y_plane.stride(0), uv_plane.stride(0), params, _stream()), "uyd_preprocess_nv12")
+    with torch.cuda.device(y_plane.device):
+        check(_lib.lib().uyd_preprocess_nv12(C.c_void_p(y_plane.data_ptr()), C.c_void_p(uv_plane.data_ptr()), C.c_void_p(out.data_ptr()),
+                                             W, H, y_plane.stride(0), uv_plane.stride(0), params, _stream(y_plane)), "uyd_preprocess_nv12")
     return out

@@ -804,7 +804,7 @@ class UninaYoloB200(nn.Module):
         check(_lib.lib().uyd_nms(_lib.context(dev), C.c_void_p(y.data_ptr()), B, no - 4, A, conf, iou, max_nms, max_det,
                                  max_wh, C.c_void_p(ws.data_ptr()), ws.numel(), C.c_void_p(det.data_ptr()),
                                  C.c_void_p(idx.data_ptr()) if idx is not None else None, C.c_void_p(cnt.data_ptr()),
-                                 C.c_void_p(torch.cuda.current_stream().cuda_stream)), "uyd_nms")
+                                 C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "uyd_nms")
 
     @torch.no_grad()
     def nms(self, y: torch.Tensor, conf: float = 0.25, iou: float = 0.7, max_det: int = 300, max_nms: int = 30000,
@@ -846,10 +846,10 @@ class UninaYoloB200(nn.Module):
 
         xs.copy_(x)
         side = torch.cuda.Stream(device=x.device)
-        side.wait_stream(torch.cuda.current_stream())
+        side.wait_stream(torch.cuda.current_stream(x.device))
         with torch.cuda.stream(side):  # warm-up outside capture: one-time kernel attribute calls happen here
             body()
-        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.current_stream(x.device).wait_stream(side)
         torch.cuda.synchronize(x.device)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
@@ -867,10 +867,11 @@ class UninaYoloB200(nn.Module):
         if graph is None:
             graph = x.shape[0] <= self.GRAPH_MAX_BATCH and os.environ.get("UYD_NO_GRAPH", "0") != "1"
         if graph:
-            g, xs, det, cnt, _ = self._graph_for(x, conf, iou, max_det, max_nms)
-            xs.copy_(x)
-            g.replay()
-            return det.clone(), cnt.clone()
+            with torch.cuda.device(x.device):   # capture and replay on the frames' device, whatever the caller's current one is
+                g, xs, det, cnt, _ = self._graph_for(x, conf, iou, max_det, max_nms)
+                xs.copy_(x)
+                g.replay()
+                return det.clone(), cnt.clone()
         y = self.forward(x, raw_heads=False)
         return self.nms(y, conf, iou, max_det, max_nms)
 
