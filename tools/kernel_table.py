@@ -18,7 +18,30 @@ def main():
     ap.add_argument("--top", type=int, default=40)
     ap.add_argument("--cand", type=int, default=1500)
     ap.add_argument("--ncu", action="store_true", help="bracket ONE step with cudaProfilerStart/Stop (ncu --profile-from-start off)")
+    ap.add_argument("--custom", action="store_true", help="the model.py network (UninaCustomB200, base_channels 32) instead of the YAML one")
     a = ap.parse_args()
+    if a.custom:
+        c = uyd.UninaCustomB200(4, 32).init_synthetic(0).cuda()
+        xc = torch.rand(a.batch, 3, a.size, a.size, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+        plan = c.plan_for(xc)
+        for _ in range(3):
+            plan.run(xc)
+        torch.cuda.synchronize()
+        if a.ncu:
+            torch.cuda.profiler.start()
+            plan.run(xc)
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
+            return
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(3):
+                plan.run(xc)
+            torch.cuda.synchronize()
+        rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)
+        print(f"total CUDA time per step: {sum(e.device_time_total for e in rows) / 3 / 1e3:.3f} ms")
+        for e in rows[: a.top]:
+            print(f"{e.device_time_total / 3:10.1f} us  x{e.count // 3:3d}  {e.key[:110]}")
+        return
     m = uyd.UninaYoloB200.from_yaml().init_synthetic(0).cuda()
     x = torch.rand(a.batch, 3, a.size, a.size, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
     m.calibrate_cls_bias(x[:8], a.cand, 0.25)
