@@ -111,6 +111,8 @@ typedef struct uyd_conv_s8 {
   int impl;
   int depthwise;           /* 1: groups == cin == cout (weight [c][1][k][k])                              */
   int res_buf, res_coff;   /* bf16 residual slice added (fp32) AFTER the activation, res_buf = -1: none */
+  int out_round_bf16;      /* UYD_S8 output only: 1 = y is rounded to bf16 before the consumer's quantiser, i.e. the bytes a
+                              bf16 activation + uyd_plan_add_quantize would produce, without materialising the activation */
 } uyd_conv_s8;
 int uyd_plan_add_conv_s8(uyd_plan *plan, const uyd_conv_s8 *desc, const int8_t *weight_q, const float *mult,
                          const float *bias);

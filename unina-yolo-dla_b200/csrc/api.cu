@@ -351,7 +351,7 @@ extern "C" int uyd_plan_add_conv_s8(uyd_plan *plan, const uyd_conv_s8 *d, const 
     UYD_REQUIRE(rb.h == ob.h && rb.w == ob.w && rb.dtype == UYD_BF16, UYD_E_ARG, "conv_s8 residual must match the output extent (bf16)");
   }
   op.out_scale = d->out_scale;
-  op.out_kind = ob.dtype == UYD_S8 ? 2 : (ob.dtype == UYD_F32 ? 1 : 0);
+  op.out_kind = ob.dtype == UYD_S8 ? (d->out_round_bf16 ? 3 : 2) : (ob.dtype == UYD_F32 ? 1 : 0);
   bool tc_ok = !d->depthwise && tc_supported_s8(d->cin, d->cout, d->k, d->stride, ib.c, d->in_coff, ob.c, d->out_coff, (int)ob.elem_bytes());
   if (d->impl == UYD_IMPL_TC) {
     UYD_REQUIRE(tc_ok, UYD_E_UNSUPPORTED, "conv_s8 %d->%d k%d s%d cannot run on the tensor-core path", d->cin, d->cout, d->k, d->stride);

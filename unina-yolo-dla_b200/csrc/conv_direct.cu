@@ -485,7 +485,8 @@ namespace uyd {
 namespace {
 
 __device__ __forceinline__ void store_s8_result(const ConvArgs &a, long long o, float y, float out_scale, int out_kind) {
-  if (out_kind == 2) {
+  if (out_kind >= 2) {  // 3: the activation is a bf16 tensor in the graph -- round it to bf16 first, then the consumer's quantiser
+    if (out_kind == 3) y = __bfloat162float(__float2bfloat16_rn(y));
     const int q = max(-127, min(127, __float2int_rn(__fmul_rn(y, out_scale))));
     reinterpret_cast<int8_t *>(a.out)[o] = (int8_t)q;
   } else if (out_kind == 1) {
@@ -536,7 +537,9 @@ __global__ void __launch_bounds__(128) conv_s8_direct_kernel(ConvArgs a, const f
 // general kernel above spends its time on 64-bit index arithmetic, per-tap weight loads and four 2-byte stores
 // (0.27 ms per launch at batch 256 = 0.3 TB/s).  Here: 32-bit indices, the 36 weight words in registers, one 8-byte
 // store per pixel.  Identical arithmetic per element (exact int32 sums, the same fp32 epilogue ops in the same order).
-__global__ void __launch_bounds__(256) conv_s8_c4_kernel(ConvArgs a, const float *__restrict__ mult) {
+// Q8: the output is the int8 input of the next QuantConv2d (round to bf16, multiply by its scale, round, clamp): 4 bytes per pixel
+template <bool Q8>
+__global__ void __launch_bounds__(256) conv_s8_c4_kernel(ConvArgs a, const float *__restrict__ mult, float out_scale) {
   const unsigned npix = (unsigned)a.n * a.oh * a.ow;
   const unsigned p = blockIdx.x * 256u + threadIdx.x;
   int wr[9][4];
@@ -572,6 +575,17 @@ __global__ void __launch_bounds__(256) conv_s8_c4_kernel(ConvArgs a, const float
     const uint2 rv = *reinterpret_cast<const uint2 *>(reinterpret_cast<const __nv_bfloat16 *>(a.res) + (size_t)p * a.res_pitch);
     y[0] = __fadd_rn(y[0], __uint_as_float(rv.x << 16)); y[1] = __fadd_rn(y[1], __uint_as_float(rv.x & 0xffff0000u));
     y[2] = __fadd_rn(y[2], __uint_as_float(rv.y << 16)); y[3] = __fadd_rn(y[3], __uint_as_float(rv.y & 0xffff0000u));
+  }
+  if (Q8) {
+    uint32_t pk = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float yb = __bfloat162float(__float2bfloat16_rn(y[j]));
+      const int q = max(-127, min(127, __float2int_rn(__fmul_rn(yb, out_scale))));
+      pk |= (uint32_t)(q & 0xFF) << (8 * j);
+    }
+    *reinterpret_cast<uint32_t *>(reinterpret_cast<int8_t *>(a.out) + (size_t)p * a.out_pitch) = pk;
+    return;
   }
   const __nv_bfloat162 h0 = __floats2bfloat162_rn(y[0], y[1]), h1 = __floats2bfloat162_rn(y[2], y[3]);
   *reinterpret_cast<uint2 *>(reinterpret_cast<__nv_bfloat16 *>(a.out) + (size_t)p * a.out_pitch) =
@@ -749,9 +763,11 @@ int direct_conv_s8_launch(const ConvArgs &a, const float *mult, float out_scale,
               "int8 direct conv needs cin %% 4 == 0 and 4-byte aligned input slices");
   const long long npix = (long long)a.n * a.oh * a.ow;
   const auto al8 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 7) == 0; };
-  if (a.cin == 4 && a.cout == 4 && a.k == 3 && a.stride == 1 && out_kind == 0 && a.oh == a.ih && a.ow == a.iw && npix < (1ll << 31) &&
-      npix * a.in_pitch < (1ll << 32) && a.out_pitch % 4 == 0 && al8(a.out) && (!a.res || (a.res_pitch % 4 == 0 && al8(a.res)))) {
-    conv_s8_c4_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, s>>>(a, mult);
+  if (a.cin == 4 && a.cout == 4 && a.k == 3 && a.stride == 1 && (out_kind == 0 || out_kind == 3) && a.oh == a.ih && a.ow == a.iw &&
+      npix < (1ll << 31) && npix * a.in_pitch < (1ll << 32) && a.out_pitch % 4 == 0 && (out_kind == 3 || al8(a.out)) &&
+      (reinterpret_cast<uintptr_t>(a.out) & 3) == 0 && (!a.res || (a.res_pitch % 4 == 0 && al8(a.res)))) {
+    if (out_kind == 3) conv_s8_c4_kernel<true><<<(unsigned)((npix + 255) / 256), 256, 0, s>>>(a, mult, out_scale);
+    else conv_s8_c4_kernel<false><<<(unsigned)((npix + 255) / 256), 256, 0, s>>>(a, mult, out_scale);
     return (int)cudaGetLastError();
   }
   dim3 grid((unsigned)((npix + 127) / 128), (unsigned)ceil_div(a.cout, 4));

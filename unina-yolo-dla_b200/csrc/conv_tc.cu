@@ -55,7 +55,7 @@ struct TcParams {
   int halo_pitch;        // HALO: pixels per halo row in shared memory (10 = dense single TMA box, 16 = padded rows)
   int stage_pitch;       // bytes per row of the epilogue staging tile (0 = direct stores)
   int i8;                // 1: int8 operands, int32 accumulate (kind::i8), requant epilogue
-  int out_kind;          // i8 path: 0 = bf16, 1 = fp32, 2 = int8 (re-quantised with out_scale)
+  int out_kind;          // i8 path: 0 = bf16, 1 = fp32, 2 = int8 (re-quantised with out_scale), 3 = int8 of the bf16-rounded value
   float out_scale;
   const float *mult;     // i8 path: per-channel fp32 multiplier m_c
   uint32_t blk_bytes;    // one A block in shared memory
@@ -250,6 +250,24 @@ __device__ __forceinline__ void epilogue_chunk_i8_staged(const uint32_t (&raw)[1
     sp[1] = o1;
     return;
   }
+  if (p.relu && !p.res && p.out_kind == 3) {
+    // the consumer's int8 input straight from the accumulator: ReLU + bf16 rounding on one cvt per pair (the activation
+    // the graph defines), times the consumer's scale, F2I.S8 (round to nearest even, saturating: the values are >= 0,
+    // so [0, 127] is the narrow range), four results packed with three PRMT
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t p01 = relu_pack_bf16x2(v[4 * i], v[4 * i + 1]), p23 = relu_pack_bf16x2(v[4 * i + 2], v[4 * i + 3]);
+      int q[4];
+      const float f[4] = {__uint_as_float(p01 << 16), __uint_as_float(p01 & 0xffff0000u), __uint_as_float(p23 << 16),
+                          __uint_as_float(p23 & 0xffff0000u)};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(q[j]) : "f"(__fmul_rn(f[j], p.out_scale)));
+      w[i] = __byte_perm(__byte_perm(q[0], q[1], 0x0040), __byte_perm(q[2], q[3], 0x0040), 0x5410);
+    }
+    *reinterpret_cast<uint4 *>(srow + c0) = make_uint4(w[0], w[1], w[2], w[3]);
+    return;
+  }
   if (p.relu) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
@@ -272,14 +290,15 @@ __device__ __forceinline__ void epilogue_chunk_i8_staged(const uint32_t (&raw)[1
         if (c0 + i < p.cout) v[i] = __fadd_rn(v[i], __bfloat162float(rp[i]));
     }
   }
-  if (p.out_kind == 2) {
+  if (p.out_kind >= 2) {
     uint32_t w[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       uint32_t pk = 0;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        int q = __float2int_rn(__fmul_rn(v[4 * i + j], p.out_scale));
+        const float yv = p.out_kind == 3 ? __bfloat162float(__float2bfloat16_rn(v[4 * i + j])) : v[4 * i + j];
+        int q = __float2int_rn(__fmul_rn(yv, p.out_scale));
         q = max(-127, min(127, q));
         pk |= (uint32_t)(q & 0xFF) << (8 * j);
       }
@@ -476,7 +495,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int m = q * 32 + lane;
     const int nchunks = p.N >> 4;
     const bool staged = p.stage_pitch != 0;
-    const int esize = I8 ? (p.out_kind == 2 ? 1 : (p.out_kind == 1 ? 4 : 2)) : (p.out_f32 ? 4 : 2);
+    const int esize = I8 ? (p.out_kind >= 2 ? 1 : (p.out_kind == 1 ? 4 : 2)) : (p.out_f32 ? 4 : 2);
     const int lpr = staged ? (p.cout * esize) / 16 : 1;  // 16-byte lanes per output row
     const int lpr_shift = 31 - __clz(lpr);  // lpr is a power of two (host check)
     const int rows_per_it = 32 >> lpr_shift, sub = lane >> lpr_shift, chunk = lane & (lpr - 1);
@@ -1013,7 +1032,7 @@ int tc_prepare(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int i
   p.blk_bytes = (p.blk_bytes + 1023u) & ~1023u;
   // epilogue staging: rows of N * esize bytes (+16 B pad against bank conflicts); usable when a
   // row of real output is a power-of-two number of 16-byte lanes
-  const int esize = i8 ? (out_kind == 2 ? 1 : (out_kind == 1 ? 4 : 2)) : (out_f32 ? 4 : 2);
+  const int esize = i8 ? (out_kind >= 2 ? 1 : (out_kind == 1 ? 4 : 2)) : (out_f32 ? 4 : 2);
   const int row_bytes = d.cout * esize;
   const bool can_stage = row_bytes >= 16 && row_bytes <= 512 && (row_bytes & (row_bytes - 1)) == 0 &&
                          (out_pitch * esize) % 16 == 0 && (reinterpret_cast<uintptr_t>(out_base) & 15) == 0;

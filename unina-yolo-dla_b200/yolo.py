@@ -48,17 +48,25 @@ class Conv(nn.Module):
         self.act = nn.ReLU(inplace=True)
         self.k, self.s, self.g, self.c1, self.c2 = k, s, g, c1, c2
 
-    def emit(self, p: Plan, src: Slice, dst: Slice | None = None, res: Slice | None = None) -> Slice:
+    def emit(self, p: Plan, src: Slice, dst: Slice | None = None, res: Slice | None = None, feeds: nn.Conv2d | None = None,
+             feeds_f32: bool = False) -> Slice:
+        """``feeds``: the conv that is the ONLY consumer of this output (the caller owns that knowledge).  In the INT8
+        graph such an output is written directly as the consumer's int8 input (no bf16 tensor, no quantize launch);
+        ``feeds_f32``: that consumer writes into an fp32 head buffer (its tensor-core eligibility rule differs)."""
         oh, ow = (p.in_hw[0] // self.s, p.in_hw[1] // self.s) if src.buf < 0 else (
             (src.h + 2 * (self.k // 2) - self.k) // self.s + 1, (src.w + 2 * (self.k // 2) - self.k) // self.s + 1)
-        if dst is None:
+        dst_was_none = dst is None
+        name = getattr(self.conv, "_uyd_name", "")
+        private_s8 = (dst_was_none and feeds is not None and src.buf >= 0 and _quantized(p, name)
+                      and _quantized(p, getattr(feeds, "_uyd_name", "")) and os.environ.get("UYD_INT8_NO_DIRECT", "0") != "1")
+        if dst is None and not private_s8:
             dst = p.buffer(oh, ow, self.c2)
         dw = self.g > 1
         assert not dw or self.g == self.c1 == self.c2, "only depth-wise grouped convs occur in this graph"
-        name = getattr(self.conv, "_uyd_name", "")
         _record_input(p, name, src)
         if _quantized(p, name) and src.buf >= 0:
-            return emit_quant_conv(p, name, self.conv, self.bn, src, dst, relu=True, res=res)
+            return emit_quant_conv(p, name, self.conv, self.bn, src, dst, relu=True, res=res, feeds=feeds if private_s8 else None,
+                                   feeds_f32=feeds_f32)
         w, b = fold_bn(self.conv, self.bn)
         return p.conv(src, dst, w, b, self.k, self.s, relu=True, depthwise=dw, res=res)
 
@@ -78,8 +86,25 @@ def _record_input(p, name: str, src: Slice) -> None:
         rec[name] = src
 
 
-def emit_quant_conv(p: Plan, name: str, conv: nn.Conv2d, bn, src: Slice, dst: Slice, relu: bool, res: Slice | None = None) -> Slice:
-    """QuantConv2d as an integer convolution (quant.py): input quantiser -> int8 conv -> requant epilogue."""
+def _tc_rows(cout: int, dst_f32: bool) -> bool:
+    """Output rows the tcgen05 int8 kernel can store (a power-of-two number of 16-byte lanes)."""
+    return (cout >= 8 and cout & (cout - 1) == 0) or (cout == 4 and dst_f32)
+
+
+def _s8_width(c: int, tc_rows: bool) -> int:
+    """Channels of the int8 copy a quantised conv reads: padded with zero channels to a multiple of 32 for tcgen05."""
+    if tc_rows and os.environ.get("UYD_INT8_NO_PAD", "0") != "1":
+        return (c + 31) // 32 * 32
+    return c
+
+
+def emit_quant_conv(p: Plan, name: str, conv: nn.Conv2d, bn, src: Slice, dst: Slice | None, relu: bool, res: Slice | None = None,
+                    feeds: nn.Conv2d | None = None, feeds_f32: bool = False) -> Slice:
+    """QuantConv2d as an integer convolution (quant.py): input quantiser -> int8 conv -> requant epilogue.
+    ``src`` in a UYD_S8 buffer = the producer already wrote this conv's int8 input (see ``feeds``).
+    ``feeds`` (with ``dst`` None): this conv's output is consumed by that quantised conv only; it is written as ITS int8
+    input -- y rounded to bf16 (the activation the graph defines), times its input scale, rounded, clamped: the very
+    bytes ``quantize`` would produce from the bf16 tensor, which is never materialised."""
     ax, aw = p.quant.amax[name]
     scale = float(Q.scale_of(ax))
     qw = Q.quantize_weights(conv.weight, aw)
@@ -88,24 +113,47 @@ def emit_quant_conv(p: Plan, name: str, conv: nn.Conv2d, bn, src: Slice, dst: Sl
     # tensor-core (tcgen05 kind::i8) eligibility is a matter of layout, not of arithmetic (the int32 sums are
     # exact either way): the int8 copy of the input is ours, so it is padded with zero channels to a multiple
     # of 32, and a depth-wise conv runs as a dense conv with diagonal weights.
-    tc_rows = cout >= 8 and cout & (cout - 1) == 0 or (cout == 4 and p.shapes[dst.buf][3] == UYD_F32)
-    cpad = src.c
+    dst_f32 = dst is not None and p.shapes[dst.buf][3] == UYD_F32
+    tc_rows = _tc_rows(cout, dst_f32)
+    cpad = _s8_width(src.c, tc_rows)
+    s8_in = p.shapes[src.buf][3] == UYD_S8
+    if s8_in:
+        pscale, pwidth = p._s8_direct[src.buf]
+        assert pscale == scale and pwidth == cpad and src.coff == 0, "direct int8 input: producer / consumer disagree"
     if tc_rows and os.environ.get("UYD_INT8_NO_PAD", "0") != "1":
-        cpad = (src.c + 31) // 32 * 32
         if dw:
             dense = np.zeros((cout, cpad, qw.shape[2], qw.shape[3]), np.int8)
             dense[np.arange(cout), np.arange(cout)] = qw[:, 0]
             qw, dw = dense, False
         elif cpad != src.c:
             qw = np.concatenate((qw, np.zeros((cout, cpad - src.c, qw.shape[2], qw.shape[3]), np.int8)), 1)
-    cache = p.__dict__.setdefault("_qcache", {})
-    key = (src.buf, src.coff, src.c, scale, cpad)
-    qsrc = cache.get(key)
-    if qsrc is None:  # one int8 copy per (activation slice, scale, padded width): convs sharing them share the copy
-        qbuf = p.buffer(src.h, src.w, cpad, UYD_S8)          # zero-filled at finalize: the pad channels stay zero
-        p.quantize(src, qbuf.sub(0, src.c), scale)
-        qsrc = cache[key] = qbuf
-    return p.conv_s8(qsrc, dst, qw, mult, bias, conv.kernel_size[0], conv.stride[0], relu=relu, depthwise=dw, res=res)
+    if s8_in:
+        qsrc = Slice(src.buf, 0, cpad, src.h, src.w)
+    else:
+        cache = p.__dict__.setdefault("_qcache", {})
+        key = (src.buf, src.coff, src.c, scale, cpad)
+        qsrc = cache.get(key)
+        if qsrc is None:  # one int8 copy per (activation slice, scale, padded width): convs sharing them share the copy
+            qbuf = p.buffer(src.h, src.w, cpad, UYD_S8)          # zero-filled at finalize: the pad channels stay zero
+            p.quantize(src, qbuf.sub(0, src.c), scale)
+            qsrc = cache[key] = qbuf
+    k, st = conv.kernel_size[0], conv.stride[0]
+    if feeds is not None and dst is None:
+        fname = feeds._uyd_name
+        fscale = float(Q.scale_of(p.quant.amax[fname][0]))
+        fwidth = _s8_width(cout, _tc_rows(feeds.out_channels, feeds_f32))
+        oh, ow = (src.h + 2 * (k // 2) - k) // st + 1, (src.w + 2 * (k // 2) - k) // st + 1
+        obuf = p.buffer(oh, ow, fwidth, UYD_S8)
+        p.__dict__.setdefault("_s8_direct", {})[obuf.buf] = (fscale, fwidth)
+        wout = cout
+        if tc_rows and cout < 16 <= fwidth and not dw:  # 16-byte output rows for the tcgen05 store path: zero output channels
+            wout = 16
+            qw = np.concatenate((qw, np.zeros((wout - cout, *qw.shape[1:]), np.int8)), 0)
+            mult = np.concatenate((mult, np.zeros(wout - cout, np.float32)))
+            bias = np.concatenate((bias, np.zeros(wout - cout, np.float32)))
+        p.conv_s8(qsrc, obuf.sub(0, wout), qw, mult, bias, k, st, relu=relu, depthwise=dw, res=res, out_scale=fscale, out_round_bf16=True)
+        return Slice(obuf.buf, 0, cout, oh, ow)
+    return p.conv_s8(qsrc, dst, qw, mult, bias, k, st, relu=relu, depthwise=dw, res=res)
 
 
 def emit_plain_conv(p: Plan, conv: nn.Conv2d, src: Slice, dst: Slice) -> Slice:
@@ -128,7 +176,7 @@ class Bottleneck(nn.Module):
         self.add = shortcut and c1 == c2
 
     def emit(self, p, src, dst=None):
-        t = self.cv1.emit(p, src)
+        t = self.cv1.emit(p, src, feeds=self.cv2.conv)   # t has one consumer: in the INT8 graph it is written as cv2's int8 input
         return self.cv2.emit(p, t, dst, res=src if self.add else None)
 
 
@@ -288,8 +336,8 @@ class Detect(nn.Module):
             geo = dict(a_total=a_total, a_off=a_off, no=4 + self.nc, stride=float(self.stride[i]))
             head = None if fused else p.buffer(f.h, f.w, self.no, UYD_F32)
             # ---- box branch ----
-            t = self.cv2[i][0].emit(p, f)
             mid_conv, last = self.cv2[i][1], self.cv2[i][2]
+            t = self.cv2[i][0].emit(p, f, feeds=mid_conv.conv)
             if (use_chain and mid_conv.k == 3 and mid_conv.s == 1 and mid_conv.g == 1 and 4 * self.reg_max == 64
                     and p.chain_supported(t, mid_conv.c2, 64) and p.shapes[t.buf][2] % 8 == 0):
                 w1, b1 = fold_bn(mid_conv.conv, mid_conv.bn)
@@ -299,7 +347,7 @@ class Detect(nn.Module):
             elif fused:
                 raise _NoFuse
             else:
-                emit_plain_conv(p, last, mid_conv.emit(p, t), head.sub(0, 4 * self.reg_max))
+                emit_plain_conv(p, last, mid_conv.emit(p, t, feeds=last, feeds_f32=True), head.sub(0, 4 * self.reg_max))
             # ---- class branch ----
             b0, b1_, last = self.cv3[i][0], self.cv3[i][1], self.cv3[i][2]
             mid = b0[1].c2
@@ -309,7 +357,7 @@ class Detect(nn.Module):
                 w2, b2 = fold_bn(b0[1].conv, b0[1].bn)
                 z1 = p.chain(f, w1, b1, w2, b2, dw1=True, relu2=True, final=CHAIN_STORE, out=p.buffer(f.h, f.w, mid))
             else:
-                z1 = b0[1].emit(p, b0[0].emit(p, f))
+                z1 = b0[1].emit(p, b0[0].emit(p, f, feeds=b0[1].conv), feeds=b1_[0].conv)
             if use_chain and dw_ok(b1_, mid) and b1_[1].c2 == mid and p.chain_supported(z1, mid, mid) and self.nc <= 8:
                 w1, b1 = fold_bn(b1_[0].conv, b1_[0].bn)
                 w2, b2 = fold_bn(b1_[1].conv, b1_[1].bn)
@@ -319,7 +367,8 @@ class Detect(nn.Module):
             elif fused:
                 raise _NoFuse
             else:
-                emit_plain_conv(p, last, b1_[1].emit(p, b1_[0].emit(p, z1)), head.sub(4 * self.reg_max, self.nc))
+                emit_plain_conv(p, last, b1_[1].emit(p, b1_[0].emit(p, z1, feeds=b1_[1].conv), feeds=last, feeds_f32=True),
+                                head.sub(4 * self.reg_max, self.nc))
             heads.append(head if head is not None else Slice(-1, 0, self.no, f.h, f.w))
             a_off += f.h * f.w
         return heads
