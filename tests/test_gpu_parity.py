@@ -267,6 +267,47 @@ def test_fused_c3k_matches_torch(T, c, H, W):
     assert float(p.read(dst.sub(0, c), B).abs().max()) == 0.0   # nothing written outside the slice
 
 
+@pytest.mark.parametrize("c,H,W,B", [(16, 80, 80, 3), (16, 40, 80, 5), (32, 40, 40, 4), (16, 20, 40, 2), (32, 20, 80, 3), (16, 80, 80, 40), (32, 40, 40, 70)])
+def test_tcgen05_c3k_matches_torch_and_the_mma_sync_kernel(T, c, H, W, B, monkeypatch):
+    """Third-generation C3k block (csrc/c3k_tc.cu: tcgen05, no-swizzle two-tap descriptors over a flat frame, six stage
+    pipelines side by side): same seven convs as the torch reference with bf16 rounding at the same points; ragged strips (H not a
+    multiple of the strip height), widths that are not a multiple of anything, several CTAs per SM-wave."""
+    import torch.nn.functional as F
+    import unina_yolo_dla_b200 as uyd
+
+    g = torch.Generator().manual_seed(c + H + W)
+    h = c // 2
+    shapes = [(h, c, 1), (h, c, 1), (h, h, 3), (h, h, 3), (h, h, 3), (h, h, 3), (c, c, 1)]
+    ws = [torch.randn(co, ci, k, k, generator=g) / (ci * k * k) ** 0.5 for co, ci, k in shapes]
+    bs = [torch.randn(co, generator=g) * 0.1 for co, _, _ in shapes]
+    x = torch.randn(B, c, H, W, generator=g)
+    outs = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("UYD_C3K_TC", mode)
+        p = uyd.Plan(0, B)
+        src = p.buffer(H, W, 3 * c)
+        dst = p.buffer(H, W, 2 * c)
+        s_in, s_out = src.sub(c, c), dst.sub(c, c)
+        if not p.c3k_supported(s_in, s_out):
+            pytest.skip("shape outside the mma.sync kernel's rule; the tcgen05 kernel is checked against torch below")
+        p.c3k(s_in, s_out, [w.numpy() for w in ws], [b.numpy() for b in bs])
+        p.finalize()
+        p.write(s_in, x)
+        p.run_no_input(B)
+        torch.cuda.synchronize()
+        outs[mode] = p.read(s_out, B).cpu()
+        assert float(p.read(dst.sub(0, c), B).abs().max()) == 0.0
+    r = T.bf16_round
+    cb = lambda t, i: r(F.conv2d(t, r(ws[i]), bs[i], padding=ws[i].shape[2] // 2).relu())
+    xin = r(x)
+    a_, b_ = cb(xin, 0), cb(xin, 1)
+    u = r(a_ + F.conv2d(cb(a_, 2), r(ws[3]), bs[3], padding=1).relu())
+    v = r(u + F.conv2d(cb(u, 4), r(ws[5]), bs[5], padding=1).relu())
+    want = cb(torch.cat((v, b_), 1), 6)
+    assert T.rel_err(outs["1"], want) < 1e-2
+    assert T.rel_err(outs["1"], outs["0"]) < 1e-2
+
+
 def test_dense_scene_1280_nms_stress_is_bit_exact(T):
     """BASELINE config 5: 1280x1280 (134 400 anchors), ~100k candidates per image: exercises the
     top-30000 truncation and the early exit at 300 kept boxes."""

@@ -27,3 +27,6 @@ for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f"  {k:<20} x{n:3d}  {t:8.3f} ms")
 for i in sorted(range(len(ms)), key=lambda i: -ms[i])[:25]:
     print(f"  {ms[i]:7.4f} ms  {p.op_info(i)[0]}")
+print("quantize ops:")
+for i in sorted((i for i in range(len(ms)) if p.op_info(i)[0].startswith("quantize")), key=lambda i: -ms[i])[:30]:
+    print(f"  {ms[i]:7.4f} ms  {p.op_info(i)[0]}")

@@ -9,11 +9,11 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libuyd.so"
 COMPAT_LIB = HERE / "libuyd_compat.so"   # the reference's own extern "C" symbols (include/uyd_compat.h) on top of libuyd.so
-SOURCES = ["api.cu", "conv_direct.cu", "stem_fused.cu", "conv_tc.cu", "conv_chain.cu", "c3k_fused.cu", "c3k_flat.cu", "pool_upsample.cu", "decode.cu", "nms.cu", "preprocess.cu", "evalmatch.cu"]
+SOURCES = ["api.cu", "conv_direct.cu", "stem_fused.cu", "conv_tc.cu", "conv_chain.cu", "c3k_fused.cu", "c3k_flat.cu", "c3k_tc.cu", "pool_upsample.cu", "decode.cu", "nms.cu", "preprocess.cu", "evalmatch.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
-]
+] + os.environ.get("UYD_NVCC_EXTRA", "").split()   # debug builds only, e.g. -DUYD_C3K_TIMELINE_BUILD (tools/c3k_timeline.py)
 
 
 def _nvcc() -> str:

@@ -14,6 +14,13 @@ size_t c3k_flat_smem_bytes(int c_, int th);
 void c3k_flat_pack(int c, const float *const w[7], std::vector<uint32_t> &frags);
 struct C3kArgs;
 int c3k_flat_launch(int c, const C3kArgs &a, cudaStream_t s);
+int c3k_flat_words(int c);
+// c3k_tc.cu: the tcgen05 generation (c = 16 / 32, batches that fill the GPU with full-width strips)
+bool c3k_tc_supported(int c, int h, int w);
+void c3k_tc_pack(int c, const float *const w[7], std::vector<uint32_t> &out);
+int c3k_tc_launch(int c, const C3kArgs &a, const uint32_t *w_tc, cudaStream_t s);
+int c3k_tc_strips(int c, int h, int w, int n);
+bool c3k_tc_preferred(int c, int h, int w, int n);
 
 struct C3kArgs {
   const __nv_bfloat16 *in;
@@ -412,6 +419,7 @@ void c3k_pack(int c, const float *const w[7], const float *const b[7], std::vect
   for (int i = 0; i < 7; ++i)
     for (int n = 0; n < couts[i]; ++n) bias[i * 32 + n] = b[i][n];
   c3k_flat_pack(c, w, frags);
+  if (c == 16 || c == 32) c3k_tc_pack(c, w, frags);  // the tcgen05 kernel's weight blocks follow the flat fragments
 }
 
 bool cls_branch_supported(int cin, int mid, int nc, int h, int w, int in_pitch, int in_coff, int out_pitch, int out_coff) {
@@ -483,6 +491,10 @@ int c3k_launch(int c, const C3kArgs &a0, cudaStream_t s) {
   a.th = c3k_launch_th(a.n, a.h, a.w);
   a.tiles_x = a.w / kTW;
   a.tiles_y = a.h / a.th;
+  // tcgen05 generation: full-width strips, so it needs a batch that fills the GPU (small batches keep the 2-D tiles)
+  const char *force = getenv("UYD_C3K_TC");  // 1: always, 0: never (tests / experiments)
+  if ((c == 16 || c == 32) && c3k_tc_supported(c, a.h, a.w) && (force ? *force == '1' : c3k_tc_preferred(c, a.h, a.w, a.n)))
+    return c3k_tc_launch(c, a, a.wfrag + c3k_flat_words(c), s);
   return c3k_flat_launch(c, a, s);
 }
 
