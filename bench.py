@@ -475,6 +475,13 @@ def main():
         sampler.join(timeout=10)   # an nvidia-smi query still in flight stalls work submission for tens of ms
     top_ms_total, top_n = plan.timed_op_read()
     plan.set_timed_op(-1, 0)
+
+    def run_resident_stream(steps):  # the streaming API on resident frames: NMS of step i on a second stream under step i + 1
+        for _det, _cnt in model.predict_stream((x_dev for _ in range(steps)), CONF, IOU, MAX_DET, to_host=False):
+            pass
+
+    run_resident_stream(3)
+    ms_pipe = min(timed(lambda: run_resident_stream(a.steps), 1) for _ in range(2))
     for _ in range(2):
         step_e2e()
     ms_e2e_single = timed(step_e2e, a.steps)
@@ -619,6 +626,9 @@ def main():
                      "api": "predict_stream(camera='nv12'): pinned host NV12 frames (Y rows + interleaved UV rows) -> H2D -> the stem reads the "
                             "planes itself (uyd_plan_run_camera) -> decode -> NMS -> D2H (+ gather at N > 1); an additional record, "
                             "the headline e2e stays on uint8 NCHW frames"},
+        "resident_stream": {"value": world * B * a.steps / (ms_pipe * 1e-3), "unit": UNIT, "ms_per_step": ms_pipe / a.steps,
+                            "api": "predict_stream on device-resident frames: the same K steps, the per-image NMS kernel (one SM per frame) of "
+                                   "step i on a second stream under the forward of step i + 1"},
         "gpu_launches": kernels_per_step * a.steps,
         "roofline": {"kernel": top_text, "bound": "tensor" if tensor_bound else "hbm", "achieved": achieved, "peak": peak,
                      "unit": unit, "frac": achieved / peak, "traffic": traffic, "peak_source": pk["src"],

@@ -941,6 +941,9 @@ class UninaYoloB200(nn.Module):
         ``(det[B,max_det,6], count[B])`` -- pinned host tensors (``to_host``) or device tensors;
         either stays valid while the generator is advanced twice more (the pinned result buffers rotate
         through a ring of four, separate from the two input staging slots).
+        NMS (and the result copy) of step i run on a second stream: the per-image NMS kernel occupies one SM per frame, so
+        at batch 64 it leaves 84 of the 148 SMs idle -- the next step's forward fills them.  Batches that are already
+        device tensors are used in place (no staging copy).
         ``camera``: the batches are camera frames read by the stem itself (``forward_camera``): ``"nv12"`` = uint8
         ``[B, 3H/2, W]`` (the Y rows followed by the interleaved UV rows: 1.5 bytes per pixel over PCIe instead of 3),
         ``"bgra"`` = uint8 ``[B, H, W, 4]`` (resampled to ``size`` when given); ``norm`` as in ``forward_camera``."""
@@ -978,16 +981,17 @@ class UninaYoloB200(nn.Module):
             outs = []
             for _ in range(4):
                 r = Slot()
-                r.out = torch.cuda.Event()
+                r.out, r.fwd = torch.cuda.Event(), torch.cuda.Event()
                 r.det = r.cnt = r.det_h = r.cnt_h = None
                 r.n = 0
                 if to_host:
                     r.det_h = torch.empty(Bmax, max_det, 6, dtype=torch.float32).pin_memory()
                     r.cnt_h = torch.empty(Bmax, dtype=torch.int32).pin_memory()
                 outs.append(r)
-            state = self._stream_state[skey] = (torch.cuda.Stream(device=device), slots, outs)
-        copy_s, slots, outs = state
+            state = self._stream_state[skey] = (torch.cuda.Stream(device=device), slots, outs, torch.cuda.Stream(device=device))
+        copy_s, slots, outs, post_s = state
         copy_s.wait_stream(main_s)   # a previous generator's last step may still read the slots
+        post_s.wait_stream(main_s)
         for s in slots:
             s.free.record(main_s)
 
@@ -995,6 +999,10 @@ class UninaYoloB200(nn.Module):
             if xb.shape[0] > Bmax or xb.shape[1:] != first.shape[1:]:
                 raise ValueError("predict_stream: later batches must not exceed the first batch's shape")
             s.n_in = xb.shape[0]
+            s.direct = xb if xb.is_cuda else None
+            if xb.is_cuda:   # already resident: no staging copy
+                s.ready.record(main_s)
+                return
             with torch.cuda.stream(copy_s):
                 copy_s.wait_event(s.free)  # the step that last read this slot has finished
                 s.x[: s.n_in].copy_(xb, non_blocking=True)
@@ -1013,29 +1021,43 @@ class UninaYoloB200(nn.Module):
             r = outs[i % 4]
             main_s.wait_event(s.ready)
             r.n = s.n_in
+            xin = s.direct if s.direct is not None else s.x[: r.n]
             if camera == "nv12":
-                hh = s.x.shape[1] * 2 // 3
-                r.det, r.cnt = self.predict_camera(s.x[: r.n, :hh], None, norm, s.x[: r.n, hh:], conf, iou, max_det, max_nms)
+                hh = xin.shape[1] * 2 // 3
+                y = self.forward_camera(xin[:, :hh], None, norm, xin[:, hh:])
             elif camera == "bgra":
-                r.det, r.cnt = self.predict_camera(s.x[: r.n], size, norm, None, conf, iou, max_det, max_nms)
+                y = self.forward_camera(xin, size, norm, None)
+            elif r.n <= self.GRAPH_MAX_BATCH and os.environ.get("UYD_NO_GRAPH", "0") != "1":
+                y = None   # small batches replay the whole step as one CUDA graph
+                r.det, r.cnt = self.predict_batched(xin, conf, iou, max_det, max_nms)
             else:
-                r.det, r.cnt = self.predict_batched(s.x[: r.n], conf, iou, max_det, max_nms)
+                y = self.forward(xin, raw_heads=False)
             s.free.record(main_s)
-            if to_host:
-                r.det_h[: r.n].copy_(r.det, non_blocking=True)
-                r.cnt_h[: r.n].copy_(r.cnt, non_blocking=True)
-            r.out.record(main_s)
+            r.fwd.record(main_s)
+            with torch.cuda.stream(post_s):
+                post_s.wait_event(r.fwd)
+                if y is not None:
+                    y.record_stream(post_s)
+                    r.det, r.cnt = self.nms(y, conf, iou, max_det, max_nms)
+                if to_host:
+                    r.det_h[: r.n].copy_(r.det, non_blocking=True)
+                    r.cnt_h[: r.n].copy_(r.cnt, non_blocking=True)
+                r.out.record(post_s)
+            del y
             if pending is not None:
-                yield self._stream_result(pending, to_host)
+                yield self._stream_result(pending, to_host, main_s)
             pending = r
             i += 1
             if nxt is None:
                 break
-        yield self._stream_result(pending, to_host)
+        yield self._stream_result(pending, to_host, main_s)
 
     @staticmethod
-    def _stream_result(s, to_host):
+    def _stream_result(s, to_host, main_s):
         if to_host:
             s.out.synchronize()
             return s.det_h[: s.n], s.cnt_h[: s.n]
+        main_s.wait_event(s.out)   # device results were produced on the post-processing stream
+        s.det.record_stream(main_s)
+        s.cnt.record_stream(main_s)
         return s.det, s.cnt
