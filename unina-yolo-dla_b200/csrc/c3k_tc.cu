@@ -424,12 +424,12 @@ int c3k_tc_strips(int c, int h, int w, int n) {  // CTAs a launch would have
 }
 
 // Used only where it was measured faster than the 2-D-tiled mma.sync kernel (tools/c3k_sweep.sh: batch 48 ... 256 at 640^2, +2
-// to +4 % on the whole step; batch 32 was a wash): batches whose tall strips (>= 24 rows: little halo recompute, one
-// pipeline fill per many M-tiles) still make about one CTA per SM.
+// to +4 % on the whole step; batch 32 was a wash): batches whose tall strips (>= 24 rows or half the image: little halo
+// recompute, one pipeline fill per many M-tiles) still make about one CTA per SM.
 bool c3k_tc_preferred(int c, int h, int w, int n) {
   if (!c3k_tc_supported(c, h, w)) return false;
   const int sms = current_sm_count(), th = c3k_tc_pick_th(c, h, w, n, sms);
-  return th >= 24 && 4ll * n * ceil_div(h, th) >= 3ll * sms;
+  return (th >= 24 || 2 * th >= h) && 4ll * n * ceil_div(h, th) >= 3ll * sms;
 }
 
 size_t c3k_tc_weight_words(int c) {
