@@ -419,6 +419,15 @@ def test_predict_stream_equals_predict_batched(T):
                 hd, hc = held[k - back]
                 wd, wc = want[(k - back) % 3]
                 assert torch.equal(hc, wc) and torch.equal(hd, wd), f"result {k - back} was overwritten by step {k}"
+    # device-resident batches are used in place (no staging copy), results come back on the caller's stream although the
+    # NMS of step i runs on the post-processing stream under the forward of step i + 1
+    res = [b.cuda() for b in batches]
+    got_dev = [(d.cpu(), c.cpu()) for d, c in m.predict_stream(iter(res), to_host=False)]
+    assert len(got_dev) == len(want)
+    for (d, c), (wd, wc) in zip(got_dev, want):
+        assert torch.equal(c, wc) and torch.equal(d, wd)
+    got_mixed = [(d.clone(), c.clone()) for d, c in m.predict_stream(iter([res[0], res[1]]), to_host=True)]
+    assert torch.equal(got_mixed[1][0], want[1][0]) and torch.equal(got_mixed[1][1], want[1][1])
 
 
 CHAIN_CASES = [

@@ -546,11 +546,6 @@ int c3k_tc_launch(int c, const C3kArgs &a, const uint32_t *w_tc, cudaStream_t s)
     p.dbg = dbg_dev;
   }
 #endif
-  static std::once_flag carve;
-  std::call_once(carve, [] {  // two CTAs per SM need the full shared-memory carve-out
-    cudaFuncSetAttribute(c3k_tc_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(c3k_tc_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  });
   if (PA == 1) {
     if (int e = smem_optin(c3k_tc_kernel<1>, 227 * 1024)) return e;
     UYD_CUDA(launch_pdl(c3k_tc_kernel<1>, dim3(grid), dim3(kThreads), smem, s, tm, p));
