@@ -657,7 +657,8 @@ def main():
         if a.custom > 0:
             out["custom_variant"] = bench_custom(a.custom, S, dev, max(3, a.steps // 2), pk,
                                                  a.profile_out.replace(".md", "_custom.md") if a.profile_out else "")
-        out["cpu_baseline"] = cpu_baseline(model, S, a.cpu_sample)
+        if a.cpu_sample > 0:   # 0 only in the A/B tooling (tools/gpu_ab.sh); the driver's default run always carries it
+            out["cpu_baseline"] = cpu_baseline(model, S, a.cpu_sample)
     if a.profile_out:
         rows = ["| # | op | ms | share | TFLOP/s | GB/s |", "|---|---|---|---|---|---|"]
         for i in sorted(range(len(ms)), key=lambda i: -ms[i]):

@@ -7,9 +7,12 @@ import sys
 rep, rx = sys.argv[1], sys.argv[2]
 skip = sys.argv[3] if len(sys.argv) > 3 else "0"
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", f"regex:{rx}", "--launch-skip", skip,
-                      "--launch-count", "1"], capture_output=True, text=True).stdout
-rows = list(csv.reader(out.splitlines()))
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", f"regex:{rx}"], capture_output=True, text=True).stdout
+allrows = list(csv.reader(out.splitlines()))
+# one table per matching launch ("Kernel Name" row, header row, body); some ncu builds ignore --launch-skip on import
+starts = [i for i, r in enumerate(allrows) if r and r[0] == "Kernel Name"]
+k = int(skip)
+rows = allrows[starts[k]:(starts[k + 1] if k + 1 < len(starts) else len(allrows))]
 print(rows[0][1][:120])
 h = rows[1]
 ix = {n: i for i, n in enumerate(h)}

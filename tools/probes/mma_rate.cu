@@ -214,6 +214,69 @@ __global__ void __launch_bounds__(256, 1) probe_commit(int NW, int iters, long l
   if (warp == 7) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
+// Layout / stride / start-offset variant (conv_tc.cu HALO): A descriptor with layout code `lay` (2 = SWIZZLE_128B,
+// 4 = SWIZZLE_64B, 6 = SWIZZLE_32B), stride `sbo` bytes between 8-row groups, nine "taps" that shift the start by
+// row_b * (t / 3) + px_b * (t % 3) bytes and `ks` k-steps of 32 bytes each; B rows of px_b bytes (same layout code).
+__device__ __forceinline__ uint64_t make_desc_l(uint32_t addr, uint32_t sbo, uint32_t lay) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)lay << 61;
+  return d;
+}
+__global__ void __launch_bounds__(128, 1) probe_sw(int N, int iters, uint32_t lay, uint32_t sbo, uint32_t row_b, uint32_t px_b, int ks, long long *out) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint32_t slot;
+  __shared__ __align__(8) unsigned long long bar;
+  const uint32_t base = (smem_u32(smem) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 100 * 1024 / 4; i += 128) reinterpret_cast<uint32_t *>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = slot;
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint64_t ad = make_desc_l(base, sbo, lay), bd = make_desc_l(base + 65536, 8 * px_b, lay);
+  if (warp == 1) {
+    const long long t0 = clock64();
+    int n = 0;
+#pragma unroll 1
+    for (int i = 0; n < iters; ++i) {
+      if (elect_one()) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const uint64_t a = ad + ((row_b * (t / 3) + px_b * (t % 3)) >> 4), b = bd + ((uint32_t)(t % 3) * N * px_b >> 4);
+          for (int k = 0; k < ks; ++k) umma<false>(tmem, a + 2 * k, b + 2 * k, idesc, 1u);
+        }
+      }
+      __syncwarp();
+      n += 9 * ks;
+    }
+    if (elect_one()) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    __syncwarp();
+    uint32_t ok = 0;
+    while (!ok) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(&bar)) : "memory");
+    }
+    const long long t2 = clock64();
+    if ((threadIdx.x & 31) == 0 && blockIdx.x == 0) { out[0] = n; out[1] = t2 - t0; }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
 int main() {
   long long *d, h[2];
   cudaMalloc(&d, 16);
@@ -240,6 +303,29 @@ int main() {
       cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
       printf("no-swizzle N %3d LBO %5u: %.1f cyc/mma (%s)\n", N, lbo, (double)h[1] / iters, cudaGetErrorString(e));
     }
+  // conv_tc HALO geometry: swizzle code, 8-row-group stride, tap shifts
+  {
+    struct C { const char *name; uint32_t lay, sbo, row_b, px_b; int ks; };
+    const C cases[] = {
+        {"128B rows, aligned groups (sbo 1024), no tap shift", 2, 1024, 0, 128, 4},
+        {"128B rows, HALO dense box (sbo 1280, taps)        ", 2, 1280, 1280, 128, 4},
+        {"128B rows, HALO padded rows (sbo 2048, taps)      ", 2, 2048, 2048, 128, 4},
+        {" 64B rows, aligned groups (sbo 512), no tap shift ", 4, 512, 0, 64, 2},
+        {" 64B rows, HALO dense box (sbo 640, taps)         ", 4, 640, 640, 64, 2},
+        {" 64B rows, HALO padded rows (sbo 1024, taps)      ", 4, 1024, 1024, 64, 2},
+        {" 32B rows, aligned groups (sbo 256), no tap shift ", 6, 256, 0, 32, 1},
+        {" 32B rows, HALO dense box (sbo 320, taps)         ", 6, 320, 320, 32, 1},
+    };
+    const size_t smem = 200 * 1024;
+    cudaFuncSetAttribute(probe_sw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    for (const C &c : cases)
+      for (int N : {32, 64, 128}) {
+        for (int rep = 0; rep < 2; ++rep) probe_sw<<<148, 128, smem>>>(N, iters, c.lay, c.sbo, c.row_b, c.px_b, c.ks, d);
+        cudaError_t e = cudaDeviceSynchronize();
+        cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+        printf("geometry %s N %3d: %.1f cyc/mma (%s)\n", c.name, N, (double)h[1] / (double)h[0], cudaGetErrorString(e));
+      }
+  }
   // items of G MMAs + commit from NW warps
   auto run_commit = [&](void (*k)(int, int, long long *), const char *name, int G) {
     for (int NW : {1, 2, 6}) {

@@ -51,6 +51,9 @@ struct TcParams {
   long long total_tiles;
   int stages;
   int nacc;              // TMEM accumulator stages (nacc * N columns)
+  int relaxed_waits;     // 1: off-critical-path waits probe with test_wait + nanosleep (tc_ptx.cuh mbar_wait_relaxed)
+  int dual;              // 1: two MMA-issuing warps take alternate tiles (stages is a multiple of 2 x blocks per tile, so a
+                         // ring slot always belongs to the same issuer and each issuer runs the ordinary parity protocol)
   int ngroups;           // active epilogue warpgroups (1, 2 or 4: as many as the staging tiles leave room for)
   int halo_pitch;        // HALO: pixels per halo row in shared memory (10 = dense single TMA box, 16 = padded rows)
   int stage_pitch;       // bytes per row of the epilogue staging tile (0 = direct stores)
@@ -85,7 +88,10 @@ namespace {
 
 constexpr int kEpiGroups = 4;                   // epilogue warpgroups taking tiles round-robin (latency hiding: the epilogue
                                                 // of a tile is a long dependent chain: TMEM load -> math -> staging -> stores)
-constexpr int kThreads = 64 + 128 * kEpiGroups;  // TMA warp + MMA warp + kEpiGroups x 4 epilogue warps
+constexpr int kThreads = 64 + 128 * kEpiGroups + 32;  // TMA warp + MMA warp + kEpiGroups x 4 epilogue warps + second MMA warp
+constexpr int kIssuer2 = kThreads / 32 - 1;           // ncu (profiles/r03_issue.md): the single issuing warp executed ~230
+                                                      // instructions per 18-MMA tile and WAS the tile period (2135 cycles vs 864
+                                                      // of tensor time); two issuers take alternate tiles (different accumulators)
 constexpr uint32_t kTailFixed = 1536 + 8 * 128 * kEpiGroups;  // barriers + bias + mult | row -> pixel map
 constexpr int kHaloRows = 18, kTileH = 16, kTileW = 8;
 constexpr int kMaxAcc = 4;  // TMEM accumulator stages
@@ -379,6 +385,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const int cb_elems = I8 ? p.cb_bytes : p.cb_bytes / 2;
   const int stages = p.stages;
   const uint32_t blk_bytes = p.blk_bytes, cb_bytes = p.cb_bytes;
+  const bool relaxed = p.relaxed_waits != 0;
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -394,7 +401,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         x0 = (int)(t - ty * (unsigned)p.tiles_x) * kTileW;
       }
       for (int j = 0; j < blocks_per_tile; ++j) {
-        mbar_wait(empty0 + 8u * stage, phase ^ 1u);
+        if (relaxed) mbar_wait_relaxed(empty0 + 8u * stage, phase ^ 1u);
+        else mbar_wait(empty0 + 8u * stage, phase ^ 1u);
         const uint32_t dst = a_s + (uint32_t)stage * blk_bytes;
         const uint32_t fb = full0 + 8u * stage;
         if (lane == 0) mbar_expect_tx(fb, p.tx_bytes);
@@ -423,11 +431,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         if (++stage == stages) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
+  } else if (warp == 1 || warp == kIssuer2) {
+    // ================= MMA issuers: warp 1 takes the even tiles of this CTA's sequence, warp kIssuer2 the odd ones =================
     mbar_wait(wfull, 0);
-    int stage = 0, acc = 0;
-    uint32_t phase = 0, acc_phase = 0;
+    const int me = warp == 1 ? 0 : 1;
+    int stage = 0;
+    uint32_t phase = 0;
+    // the other issuer's tile occupies the next blocks_per_tile slots of the ring
+    auto skip_tile = [&]() {
+      stage += blocks_per_tile;
+      while (stage >= stages) { stage -= stages; phase ^= 1u; }
+    };
+    const int step = p.dual ? 2 : 1;
+    if (me) skip_tile();
+    const int nacc_mask = nacc - 1, nacc_shift = nacc == 4 ? 2 : 1;
+    int it = me;
     const bool pairs = p.mode == TC_PAIRS;
     const uint64_t adesc0 = make_desc_base(p.sbo_a, pairs ? 2u : p.layout_type);  // PAIRS: 128-byte A rows, SWIZZLE_128B
     const uint64_t bdesc0 = make_desc_base(8u * cb_bytes, p.layout_type);
@@ -435,7 +453,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const uint32_t idesc = p.idesc;
     const bool halo = p.mode == TC_HALO;
     const uint32_t px_units = cb_bytes >> 4, row_units = (uint32_t)p.halo_pitch * px_units, wblk_units = wblk_bytes >> 4;
-    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (long long tile = (me && !p.dual) ? p.total_tiles : blockIdx.x + (long long)me * gridDim.x; tile < p.total_tiles;
+         tile += (long long)step * gridDim.x, it += step) {
+      const int acc = it & nacc_mask;
+      const uint32_t acc_phase = (uint32_t)(it >> nacc_shift) & 1u;
       mbar_wait(tempty0 + 8u * acc, acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)acc * p.N;
@@ -487,7 +508,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         __syncwarp();
         if (++stage == stages) { stage = 0; phase ^= 1u; }
       }
-      if (++acc == nacc) { acc = 0; acc_phase ^= 1u; }
+      if (p.dual) skip_tile();
     }
   } else {
     // ================= epilogue =================
@@ -536,7 +557,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         pix = (oy < p.H && ox < p.W) ? ((long long)n * p.H + oy) * p.W + ox : -1;
         if (p.pre && pix >= 0) ppix = ((long long)n * (p.H >> 1) + (oy >> 1)) * (p.W >> 1) + (ox >> 1);
       }
-      mbar_wait(tfull0 + 8u * acc, acc_phase);
+      if (relaxed) mbar_wait_relaxed(tfull0 + 8u * acc, acc_phase);
+      else mbar_wait(tfull0 + 8u * acc, acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * p.N;
       uint32_t cur[16], nxt[16];
@@ -1070,7 +1092,14 @@ int tc_prepare(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int i
   const int want = p.mode == TC_HALO ? 4 : (p.mode == TC_PAIRS ? 4 : 12);
   if (stages > want) stages = want;
   if (stages_override > 0 && stages_override < stages) stages = stages_override;
+  {  // two issuing warps when the ring can be split between them (see TcParams::dual)
+    const int bpt = p.mode == TC_PERTAP ? p.ncb * p.taps : p.ncb;
+    const int even = stages - stages % (2 * bpt);  // never trade the third / fourth stage of a deep-latency ring for the second issuer
+    p.dual = even >= 2 * bpt && (even == stages || even >= 4) && getenv("UYD_TC_SINGLE_ISSUER") == nullptr;
+    if (p.dual) stages = even;
+  }
   p.stages = stages;
+  p.relaxed_waits = getenv("UYD_TC_RELAXED") != nullptr;  // measured: slower (PERTAP +8 %, FLAT 80->64 +10 %), kept as a probe
   p.nacc = 4 * p.N <= 512 ? 4 : 2;
   tc->smem = 1024 + wres + (size_t)stages * p.blk_bytes + tail;
   p.out = out_base;
