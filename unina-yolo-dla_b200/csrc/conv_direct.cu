@@ -7,6 +7,7 @@
 //   out = [res +] relu(sum_{tap,ci} x * w + bias)
 // One thread = one output pixel x CO_T output channels.
 #include "common.cuh"
+#include "stem_v2.cuh"
 
 namespace uyd {
 
@@ -321,6 +322,185 @@ __global__ void __launch_bounds__(kStemThreads) conv_stem_tiled_kernel(ConvArgs 
   }
 }
 
+// model.py's backbone.stem (Conv 3 -> 32, 3x3, stride 2, model.py:173) on the legacy tensor path.  The tiled CUDA-core
+// kernel above spent 0.59 ms per batch of 64 (19 TFLOP/s, 12 % of the model.py step).  Here the GEMM is TRANSPOSED as in
+// stem_v2.cuh: output channels are the mma rows (A = weights, 2 m-tiles of 16, kept in registers by persistent CTAs),
+// eight horizontally adjacent output pixels the columns (B = the frame patch), K = 9 (channel, ky) combinations of
+// four consecutive patch columns (image columns 2 ox - 2 .. 2 ox + 1; the first has zero weights), four combinations
+// per mma.m16n8k16.bf16 k-step, so a B register is ONE LDS.32 of the bf16 patch.
+//   * A first version on mma.m16n8k8.tf32 was bound by that instruction itself: ncu showed the HMMA pipe 78 % active at
+//     8 cycles per HMMA.1688.TF32 and SM (1024 MACs: an eighth of the bf16 rate), 232 us.  bf16 operands with the frame
+//     SPLIT into hi + lo (x = hi + lo up to 2^-17: finer than tf32) cost 12 HMMA.16816 per 8 pixels instead of 10
+//     HMMA.1688 -- 24 pipe cycles instead of 80 -- and leave the kernel to the memory system.
+//   * Rows of m-tile mt are assigned to channels 4 (r & 7) + 2 mt + (r >> 3), so lane (g, t) ends up with channels
+//     4g .. 4g + 3 of pixels 2t and 2t + 1: two 8-byte stores, 64 contiguous bytes per pixel across the warp.
+//   * The loads of tile i + 1 are issued before tile i is computed (tiles strided by the grid).
+constexpr int kSmTH = 8, kSmTW = 64, kSmThreads = 256;          // output tile: one row of 64 pixels per warp
+constexpr int kSmIH = 2 * kSmTH + 1, kSmNV = (2 * kSmTW) / 4 + 2;
+constexpr int kSmIP = 152;  // bf16 per patch row (>= 4 kSmNV): row / plane strides of 12 and 20 banks keep the two
+                            // combinations one LDS.32 touches in disjoint banks
+static_assert(kSmIP >= 4 * kSmNV && kSmIP % 4 == 0, "patch pitch");
+
+template <typename TIn, bool SPLIT>
+__global__ void __launch_bounds__(kSmThreads) conv_stem_mma_kernel(ConvArgs a, int tiles_x, int tiles_y, int total_tiles) {
+  constexpr int NP = SPLIT ? 2 : 1;  // planes: hi (| lo)
+  __shared__ __align__(16) __nv_bfloat16 sx[NP][3][kSmIH][kSmIP];
+  __shared__ float sw[27][32];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  for (int i = tid; i < 27 * 32; i += kSmThreads) sw[i / 32][i % 32] = __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(a.w)[i]);
+  const bool vec_ok = a.iw % 4 == 0 && (reinterpret_cast<uintptr_t>(a.in) & 15) == 0 && ((long long)a.ih * a.iw * sizeof(TIn)) % 16 == 0;
+  // Patch staging: every load of a thread is issued before the first is used (7 x 16 B in flight per thread); the
+  // (channel, row, vector) of element i = tid + 256 k advances incrementally (256 = 7 * 34 + 18)
+  constexpr int kIters = (3 * kSmIH * kSmNV + kSmThreads - 1) / kSmThreads;
+  static_assert(kSmThreads / kSmNV < kSmIH, "incremental (c, r, j) update");
+  float4 pv[kIters];
+  auto tile_origin = [&](int tile, int &n, int &oy0, int &ox0) {
+    n = tile / (tiles_x * tiles_y);
+    const int tr = tile - n * tiles_x * tiles_y;
+    oy0 = (tr / tiles_x) * kSmTH;
+    ox0 = (tr % tiles_x) * kSmTW;
+  };
+  auto issue = [&](int tile) {
+    int n, oy0, ox0;
+    tile_origin(tile, n, oy0, ox0);
+    const TIn *in = reinterpret_cast<const TIn *>(a.in) + (long long)n * 3 * a.ih * a.iw;
+    int j = tid % kSmNV, r = tid / kSmNV, c = 0;
+#pragma unroll
+    for (int k = 0; k < kIters; ++k) {
+      const int iy = oy0 * 2 - 1 + r, ix = ox0 * 2 - 4 + 4 * j;  // patch column 4 j = image column 2 ox0 - 4 + 4 j
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < 3 && iy >= 0 && iy < a.ih) {
+        const TIn *src = in + ((long long)c * a.ih + iy) * a.iw + ix;
+        if (vec_ok && ix >= 0 && ix + 3 < a.iw) {
+          if (sizeof(TIn) == 4) {
+            v = __ldg(reinterpret_cast<const float4 *>(src));
+          } else {
+            const uchar4 u = __ldg(reinterpret_cast<const uchar4 *>(src));
+            v = make_float4((float)u.x, (float)u.y, (float)u.z, (float)u.w);
+          }
+        } else {
+          float e4[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) e4[e] = (ix + e >= 0 && ix + e < a.iw) ? (float)src[e] : 0.f;
+          v = make_float4(e4[0], e4[1], e4[2], e4[3]);
+        }
+      }
+      pv[k] = v;
+      j += kSmThreads % kSmNV;
+      r += kSmThreads / kSmNV;
+      if (j >= kSmNV) { j -= kSmNV; ++r; }
+      if (r >= kSmIH) { r -= kSmIH; ++c; }
+    }
+  };
+  __nv_bfloat16 *sx0 = &sx[0][0][0][0];
+  constexpr int kPlane = 3 * kSmIH * kSmIP;  // bf16 elements of the hi plane set
+  auto stage = [&]() {
+    int j = tid % kSmNV, r = tid / kSmNV, c = 0;
+#pragma unroll
+    for (int k = 0; k < kIters; ++k) {
+      float4 v = pv[k];
+      if (sizeof(TIn) == 1) v = make_float4(stemv2::div255(v.x), stemv2::div255(v.y), stemv2::div255(v.z), stemv2::div255(v.w));
+      if (c < 3) {
+        const uint32_t h01 = c3kf::pack_bf16(v.x, v.y), h23 = c3kf::pack_bf16(v.z, v.w);
+        __nv_bfloat16 *d = sx0 + (c * kSmIH + r) * kSmIP + 4 * j;
+        *reinterpret_cast<uint2 *>(d) = make_uint2(h01, h23);
+        if (SPLIT) {  // lo = bf16(x - hi): x = hi + lo up to 2^-17 relative
+          const uint32_t l01 = c3kf::pack_bf16(v.x - c3kf::bf16_lo(h01), v.y - c3kf::bf16_hi(h01));
+          const uint32_t l23 = c3kf::pack_bf16(v.z - c3kf::bf16_lo(h23), v.w - c3kf::bf16_hi(h23));
+          *reinterpret_cast<uint2 *>(d + kPlane) = make_uint2(l01, l23);
+        }
+      }
+      j += kSmThreads % kSmNV;
+      r += kSmThreads / kSmNV;
+      if (j >= kSmNV) { j -= kSmNV; ++r; }
+      if (r >= kSmIH) { r -= kSmIH; ++c; }
+    }
+  };
+  int tile = blockIdx.x;
+  if (tile < total_tiles) issue(tile);
+  __syncthreads();  // sw
+  // A fragments (m16n8k16): a0 (g, 2t..) a1 (g + 8, 2t..) a2 (g, 2t + 8..) a3 (g + 8, 2t + 8..); logical k = 4 cl + slot with
+  // cl = the combination inside the k-step (combination 4 s + cl = 3 channel + ky) and slot = kx + 1: registers a0 / a1
+  // pair with the LDS.32 of combination 4 s + (t >> 1), a2 / a3 with that of combination 4 s + 2 + (t >> 1)
+  uint32_t af[3][2][4];
+  float bz[2][2];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) bz[mt][h] = a.bias[4 * g + 2 * mt + h];
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int co = 4 * g + 2 * mt + (i & 1), combo = 4 * s + 2 * (i >> 1) + (t >> 1);
+        float w[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int kx = 2 * (t & 1) + e - 1;
+          w[e] = (combo < 9 && kx >= 0) ? sw[((combo % 3) * 3 + kx) * 3 + combo / 3][co] : 0.f;
+        }
+        af[s][mt][i] = c3kf::pack_bf16(w[0], w[1]);  // already bf16 values: exact
+      }
+  }
+  // bf16 offset of this lane's two LDS.32 in k-step s, relative to 2 (8 grp + g): patch column 2 ox - 2 = 2 (ox - ox0) + 2
+  int koff[3][2];
+#pragma unroll
+  for (int s = 0; s < 3; ++s)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      int combo = 4 * s + 2 * h + (t >> 1);
+      if (combo > 8) combo = 8;  // zero-weight combinations re-read the last real one
+      koff[s][h] = ((combo / 3) * kSmIH + 2 * warp + combo % 3) * kSmIP + 2 + 2 * (t & 1);
+    }
+  for (; tile < total_tiles; tile += gridDim.x) {
+    stage();
+    __syncthreads();
+    if (tile + (int)gridDim.x < total_tiles) issue(tile + gridDim.x);  // in flight while this tile is computed
+    int n, oy0, ox0;
+    tile_origin(tile, n, oy0, ox0);
+    const int oy = oy0 + warp;
+    if (oy < a.oh) {
+      __nv_bfloat16 *orow = reinterpret_cast<__nv_bfloat16 *>(a.out) + ((long long)n * a.oh + oy) * a.ow * a.out_pitch + 4 * g;
+      __nv_bfloat16 *po = orow + (long long)(ox0 + 2 * t) * a.out_pitch;
+#pragma unroll 4
+      for (int grp = 0; grp < kSmTW / 8; ++grp) {
+        float acc[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) { acc[mt][0] = acc[mt][1] = bz[mt][0]; acc[mt][2] = acc[mt][3] = bz[mt][1]; }
+        const __nv_bfloat16 *px = sx0 + 2 * (8 * grp + g);
+#pragma unroll
+        for (int pl = 0; pl < NP; ++pl)
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            const uint32_t b0 = *reinterpret_cast<const uint32_t *>(px + pl * kPlane + koff[s][0]);
+            const uint32_t b1 = *reinterpret_cast<const uint32_t *>(px + pl * kPlane + koff[s][1]);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+              asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                  : "+f"(acc[mt][0]), "+f"(acc[mt][1]), "+f"(acc[mt][2]), "+f"(acc[mt][3])
+                  : "r"(af[s][mt][0]), "r"(af[s][mt][1]), "r"(af[s][mt][2]), "r"(af[s][mt][3]), "r"(b0), "r"(b1));  // not volatile: the chains of unrolled groups interleave
+          }
+        // lane (g, t): channels 4g .. 4g + 3 = (mt 0 row g, mt 0 row g + 8, mt 1 row g, mt 1 row g + 8) of pixels 2t | 2t + 1
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int ox = ox0 + 8 * grp + 2 * t + e;
+          if (ox >= a.ow) continue;
+          uint32_t h0, h1;
+          if (a.relu) {
+            h0 = c3kf::relu_pack_bf16(acc[0][e], acc[0][2 + e]);
+            h1 = c3kf::relu_pack_bf16(acc[1][e], acc[1][2 + e]);
+          } else {
+            h0 = c3kf::pack_bf16(acc[0][e], acc[0][2 + e]);
+            h1 = c3kf::pack_bf16(acc[1][e], acc[1][2 + e]);
+          }
+          *reinterpret_cast<uint2 *>(po + (8 * grp + e) * a.out_pitch) = make_uint2(h0, h1);
+        }
+      }
+    }
+    __syncthreads();  // the patch is overwritten by the next stage()
+  }
+}
+
 // Depth-wise 3x3 stride 1, four horizontally adjacent pixels x 8 channels per thread: the 3 x 6
 // input window is loaded once (18 x 16 B) for 4 outputs instead of 36 loads.
 __global__ void __launch_bounds__(kThreads) conv_dw4_kernel(ConvArgs a) {
@@ -442,6 +622,20 @@ int direct_conv_launch(const ConvArgs &a, bool depthwise, cudaStream_t s) {
     const bool u8 = a.in_nchw_f32 == 2;
     if (a.cin == 3 && (a.cout == 16 || a.cout == 32) && a.k == 3 && a.stride == 2 && a.out_pitch % 8 == 0 &&
         (reinterpret_cast<uintptr_t>(a.out) & 15) == 0) {
+      if (a.cout == 32 && a.out_pitch % 4 == 0 && getenv("UYD_STEM_TILED") == nullptr) {
+        const int tx = ceil_div(a.ow, kSmTW), ty = ceil_div(a.oh, kSmTH), total = tx * ty * a.n;
+        const int resident = 2 * current_sm_count();  // 256 threads x ~110 registers: two CTAs per SM
+        const unsigned mgrid = (unsigned)(total < resident ? total : resident);
+        static const bool split = getenv("UYD_STEM_NO_SPLIT") == nullptr;  // probe: hi plane only (bf16-rounded frame)
+        if (split) {
+          if (u8) conv_stem_mma_kernel<uint8_t, true><<<mgrid, kSmThreads, 0, s>>>(a, tx, ty, total);
+          else conv_stem_mma_kernel<float, true><<<mgrid, kSmThreads, 0, s>>>(a, tx, ty, total);
+        } else {
+          if (u8) conv_stem_mma_kernel<uint8_t, false><<<mgrid, kSmThreads, 0, s>>>(a, tx, ty, total);
+          else conv_stem_mma_kernel<float, false><<<mgrid, kSmThreads, 0, s>>>(a, tx, ty, total);
+        }
+        return (int)cudaGetLastError();
+      }
       dim3 grid(ceil_div(a.ow, kStemTW), ceil_div(a.oh, kStemTH), a.n);
       if (a.cout == 16) {
         if (u8) conv_stem_tiled_kernel<uint8_t, 16><<<grid, kStemThreads, 0, s>>>(a);

@@ -51,7 +51,6 @@ struct TcParams {
   long long total_tiles;
   int stages;
   int nacc;              // TMEM accumulator stages (nacc * N columns)
-  int relaxed_waits;     // 1: off-critical-path waits probe with test_wait + nanosleep (tc_ptx.cuh mbar_wait_relaxed)
   int dual;              // 1: two MMA-issuing warps take alternate tiles (stages is a multiple of 2 x blocks per tile, so a
                          // ring slot always belongs to the same issuer and each issuer runs the ordinary parity protocol)
   int ngroups;           // active epilogue warpgroups (1, 2 or 4: as many as the staging tiles leave room for)
@@ -385,7 +384,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const int cb_elems = I8 ? p.cb_bytes : p.cb_bytes / 2;
   const int stages = p.stages;
   const uint32_t blk_bytes = p.blk_bytes, cb_bytes = p.cb_bytes;
-  const bool relaxed = p.relaxed_waits != 0;
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -401,8 +399,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         x0 = (int)(t - ty * (unsigned)p.tiles_x) * kTileW;
       }
       for (int j = 0; j < blocks_per_tile; ++j) {
-        if (relaxed) mbar_wait_relaxed(empty0 + 8u * stage, phase ^ 1u);
-        else mbar_wait(empty0 + 8u * stage, phase ^ 1u);
+        mbar_wait(empty0 + 8u * stage, phase ^ 1u);
         const uint32_t dst = a_s + (uint32_t)stage * blk_bytes;
         const uint32_t fb = full0 + 8u * stage;
         if (lane == 0) mbar_expect_tx(fb, p.tx_bytes);
@@ -557,8 +554,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         pix = (oy < p.H && ox < p.W) ? ((long long)n * p.H + oy) * p.W + ox : -1;
         if (p.pre && pix >= 0) ppix = ((long long)n * (p.H >> 1) + (oy >> 1)) * (p.W >> 1) + (ox >> 1);
       }
-      if (relaxed) mbar_wait_relaxed(tfull0 + 8u * acc, acc_phase);
-      else mbar_wait(tfull0 + 8u * acc, acc_phase);
+      mbar_wait(tfull0 + 8u * acc, acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * p.N;
       uint32_t cur[16], nxt[16];
@@ -1099,7 +1095,6 @@ int tc_prepare(TcConv *tc, const uyd_conv &d, void *in_base, int in_pitch, int i
     if (p.dual) stages = even;
   }
   p.stages = stages;
-  p.relaxed_waits = getenv("UYD_TC_RELAXED") != nullptr;  // measured: slower (PERTAP +8 %, FLAT 80->64 +10 %), kept as a probe
   p.nacc = 4 * p.N <= 512 ? 4 : 2;
   tc->smem = 1024 + wres + (size_t)stages * p.blk_bytes + tail;
   p.out = out_base;

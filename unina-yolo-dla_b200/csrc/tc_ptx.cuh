@@ -53,18 +53,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
-// Wait of a warp that is OFF the critical path (epilogue groups waiting for an accumulator, the TMA producer waiting
-// for a free slot): one non-blocking probe per ~64 ns instead of try_wait, whose suspended form keeps polling the
-// barrier word through the shared-memory pipe the tensor core reads its operands from (ncu, profiles/r03_issue.md).
-__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
-  for (uint32_t it = 0; !mbar_test_wait(bar, parity); ++it) {
-    __nanosleep(64);
-    if (it > (1u << 24)) {
-      printf("uyd conv_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
-      __trap();
-    }
-  }
-}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
