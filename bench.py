@@ -504,6 +504,9 @@ def main():
     h2d_ms = min(timed(h2d_only, 1) for _ in range(2)) / a.steps
     probe["h2d_only_ms_per_step"] = h2d_ms
     probe["h2d_only_gbs_per_gpu"] = x_host.numel() / (h2d_ms * 1e-3) / 1e9
+    # ceiling the host-to-device path of the box puts on e2e with 3-byte pixels (all ranks copying at once;
+    # tools/h2d_probe.py: pinned, write-combined, two streams and chunked copies all give the same figure)
+    probe["h2d_cap_images_per_s"] = world * B / (h2d_ms * 1e-3)
     # the same streamed run fed with NV12 camera frames (1.5 bytes per pixel over PCIe; the stem converts on load)
     nv_host = torch.randint(0, 256, (B, S * 3 // 2, S), dtype=torch.uint8, generator=torch.Generator().manual_seed(600 + rank)).pin_memory()
 
@@ -615,6 +618,7 @@ def main():
         "e2e": {"value": world * B * a.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": x_host.numel(),
                 "d2h_bytes_per_step": det_host.numel() * 4 + cnt_host.numel() * 4, "ms_per_step": ms_e2e / a.steps,
                 "single_call_ms": ms_e2e_single / a.steps,
+                "frac_of_h2d_cap": (world * B * a.steps / (ms_e2e * 1e-3)) / probe["h2d_cap_images_per_s"],
                 "api": "UninaYoloB200.predict_stream(pinned uint8 NCHW host batches): H2D of step i+1 overlaps step i (best of 3 runs of K steps); "
                        "N > 1: + one fixed-shape NCCL all_gather of the detections per step on a side stream; "
                        "single_call_ms = one blocking predict_batched(host frames) per step",
