@@ -587,6 +587,41 @@ def test_fused_stem_persistent_ctas(T, u8, pw):
     test_fused_stem_matches_torch(T, 640, 640, u8, pw, B=8)
 
 
+@pytest.mark.parametrize("H,W,u8,B", [(64, 96, False, 2), (70, 94, False, 1), (70, 94, True, 2), (256, 256, True, 3),
+                                       (640, 640, False, 8), (34, 258, False, 2), (36, 260, True, 2)])
+def test_model_py_stem_3_to_32_on_mma_sync_matches_torch(T, H, W, u8, B):
+    """model.py:173 backbone.stem, Conv(3, 32, 3, 2) (conv_stem_mma_kernel): the frame enters as hi + lo bf16 planes
+    (2^-17 relative), weights are bf16, fp32 accumulation, one rounding to bf16.  Odd extents take the scalar staging
+    path, extents that are not multiples of the 8 x 64 tile the partial-tile stores, 8 x 640 x 640 the persistent
+    loop with the register prefetch (more tiles than resident CTAs)."""
+    import torch.nn.functional as F
+    import unina_yolo_dla_b200 as uyd
+    from unina_yolo_dla_b200.plan import NETWORK_INPUT
+
+    g = torch.Generator().manual_seed(H * 7 + W)
+    r = T.bf16_round
+    w, b = torch.randn(32, 3, 3, 3, generator=g) / 27 ** 0.5, torch.randn(32, generator=g) * 0.1
+    if u8:
+        xin = (torch.rand(B, 3, H, W, generator=g) * 255).to(torch.uint8)
+        xf = xin.float() / 255
+    else:
+        xin = xf = torch.rand(B, 3, H, W, generator=g)
+    oh, ow = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+    p = uyd.Plan(0, B)
+    dst = p.buffer(oh, ow, 48).sub(8, 32)
+    p.conv(NETWORK_INPUT, dst, w.numpy(), b.numpy(), 3, 2, relu=True)
+    p.finalize()
+    p.run(xin.cuda())
+    torch.cuda.synchronize()
+    got = p.read(dst, B).cpu()
+    want = F.conv2d(xf, r(w), b, stride=2, padding=1).relu()
+    # the bf16 rounding of the output is the only error source that matters: compare before rounding the reference too
+    assert float((got - want).abs().max()) <= 2.0 ** -8 * float(want.abs().max()) + 1e-6
+    assert T.rel_err(got, r(want)) < 4e-3
+    assert float(p.read(p.buffer_slice(dst.buf, 0, 8), B).abs().max()) == 0.0      # nothing outside the slice
+    assert float(p.read(p.buffer_slice(dst.buf, 40, 8), B).abs().max()) == 0.0
+
+
 def test_plan_errors_are_reported_not_thrown(T):
     """The C ABI returns an error code + message (gpu_postprocess.h convention: cudaError_t-like int, no exceptions
     across the boundary); the Python host turns it into UydError.  Misaligned / misplaced ops are refused at build time."""

@@ -18,8 +18,8 @@ ncu --set full --clock-control none --import-source on --profile-from-start off 
 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"c3k_flat|c3k_tc|conv_tc_kernel|sppf|conv_dw" -c 16 \
     -o gpurun_out/${TAG}_b -f python tools/kernel_table.py --ncu > gpurun_out/${TAG}_full_b.log 2>&1; echo "full set b exit=$?"
 python tools/kernel_table.py --custom --top 20 > gpurun_out/${TAG}_ktable_custom.log 2>&1
-ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"conv_tc_big|conv_stem_tiled" -c 8 \
+ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"conv_tc_big|conv_stem_mma" -c 8 \
     -o gpurun_out/${TAG}_c -f python tools/kernel_table.py --custom --ncu > gpurun_out/${TAG}_full_c.log 2>&1; echo "full set c exit=$?"
-tools/probes/mma_rate > gpurun_out/${TAG}_mma_rate.txt 2>&1; echo "mma_rate exit=$?"
-bash tools/c3k_sweep.sh > gpurun_out/${TAG}_c3k_sweep.txt 2>&1; echo "c3k sweep exit=$?"
+[ -n "$UYD_EVIDENCE_FAST" ] || { tools/probes/mma_rate > gpurun_out/${TAG}_mma_rate.txt 2>&1; echo "mma_rate exit=$?"; }
+[ -n "$UYD_EVIDENCE_FAST" ] || { bash tools/c3k_sweep.sh > gpurun_out/${TAG}_c3k_sweep.txt 2>&1; echo "c3k sweep exit=$?"; }
 du -sh gpurun_out
