@@ -105,6 +105,41 @@ def test_custom_forward_matches_oracle(bc):
         assert float((gr.cpu() - wr).abs().max() / wr.abs().max()) <= 1e-2
 
 
+def test_custom_forward_640_matches_pinned_oracle():
+    """The benched configuration of the model.py variant (base_channels 32, 640 x 640; custom_variant in bench.py) against
+    the oracle that is pinned bit-exactly to the real model.py.  Measured on B200 (tools/custom_parity_diag.py, four
+    weight seeds x two extents): regression maps 1.1e-3 .. 1.9e-3 of their range, class maps 5e-3 .. 1.33e-2 (rms
+    1.3e-3 .. 3.1e-3) -- bf16 activations through 41 sequential convs onto a class map whose own range is small; the
+    same figures with the fp32-input CUDA-core stem, so the split-bf16 stem adds nothing.  Stated tolerance for this
+    variant: regression <= 5e-3, class <= 2e-2 of range and <= 5e-3 rms (the 1e-2 of the north star holds for the YAML
+    network, tests/test_gpu_northstar.py, and for this variant's seeds 1 / 320 x 320 case above)."""
+    import unina_yolo_dla_b200 as uyd
+    from oracle import custom_graph as cg
+    from oracle import init as oi
+
+    m = uyd.UninaCustomB200(4, 32).init_synthetic(seed=3)
+    ref = cg.CustomNet(4, 32)
+    ref.load_state_dict(m.state_dict(), strict=True)
+    ref.eval()
+    m = m.cuda()
+    x = oi.seeded_frames(4, 640, seed=11)
+    with torch.no_grad():
+        want = ref(x)
+    got = m(x.cuda())
+    torch.cuda.synchronize()
+    worst = {"cls": 0.0, "reg": 0.0, "cls_rms": 0.0}
+    for pair_g, pair_w in zip(got, want):
+        for name, g, w in zip(("cls", "reg"), pair_g, pair_w):
+            assert g.shape == w.shape
+            d = (g.cpu() - w).abs()
+            rng = float(w.abs().max())
+            worst[name] = max(worst[name], float(d.max()) / rng)
+            if name == "cls":
+                worst["cls_rms"] = max(worst["cls_rms"], float(d.pow(2).mean().sqrt()) / rng)
+    print(f"model.py variant bc32 640x640 batch 4 (range-normalised): class {worst['cls']:.3e} (rms {worst['cls_rms']:.3e}), regression {worst['reg']:.3e}")
+    assert worst["reg"] <= 5e-3 and worst["cls"] <= 2e-2 and worst["cls_rms"] <= 5e-3
+
+
 def test_custom_predict_rows():
     import unina_yolo_dla_b200 as uyd
     from oracle import init as oi
