@@ -564,6 +564,89 @@ __global__ void __launch_bounds__(kThreads) conv_dw4_kernel(ConvArgs a) {
   }
 }
 
+// Depth-wise 3x3 stride 1, column formulation (the P4 class branch's 128-channel conv at 40 x 40): a thread owns a
+// channel QUAD of one output column over R rows.  The 36 weights stay in registers as fp32 pairs, every input row is
+// loaded once (three 8-byte loads: columns x - 1, x, x + 1) and feeds the three output rows it is a tap row of,
+// accumulators of three rows in flight (ring-indexed), packed FFMA2.  Per 32 outputs: 30 x 8 bytes loaded, 60
+// unpack and 144 FFMA2 instructions -- conv_dw4_kernel above needs 29 x 16 bytes, 216 unpacks and 288 FFMAs.
+// Lanes run over the channel quads first: a warp reads / writes whole pixels (256 contiguous bytes at C = 128).
+__device__ __forceinline__ float2 dw_ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+template <int R>
+__global__ void __launch_bounds__(kThreads) conv_dw_col_kernel(ConvArgs a) {
+  pdl_trigger();
+  const int nq = a.cin / 4, segs = (a.oh + R - 1) / R;
+  const long long total = (long long)a.n * segs * a.ow * nq;
+  const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (t >= total) return;
+  const int q = (int)(t % nq);
+  long long p = t / nq;
+  const int x = (int)(p % a.ow);
+  p /= a.ow;
+  const int oy0 = (int)(p % segs) * R, n = (int)(p / segs);
+  const __nv_bfloat16 *in = reinterpret_cast<const __nv_bfloat16 *>(a.in) + (long long)n * a.ih * a.iw * a.in_pitch + 4 * q;
+  __nv_bfloat16 *out = reinterpret_cast<__nv_bfloat16 *>(a.out) + (long long)n * a.oh * a.ow * a.out_pitch + 4 * q;
+  const __nv_bfloat16 *w = reinterpret_cast<const __nv_bfloat16 *>(a.w) + 4 * q;
+  auto lo2 = [](uint32_t v) { return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u)); };
+  float2 wlo[9], whi[9];
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const uint2 h = __ldg(reinterpret_cast<const uint2 *>(w + (size_t)tap * a.cin));
+    wlo[tap] = lo2(h.x);
+    whi[tap] = lo2(h.y);
+  }
+  const float4 b4 = __ldg(reinterpret_cast<const float4 *>(a.bias + 4 * q));
+  const float2 blo = make_float2(b4.x, b4.y), bhi = make_float2(b4.z, b4.w);
+  const bool left = x > 0, right = x + 1 < a.iw;
+  auto load_row = [&](int i, uint2 (&h)[3]) {  // input row oy0 - 1 + i, columns x - 1 .. x + 1 (zero outside the image)
+    const int iy = oy0 - 1 + i;
+    h[0] = h[1] = h[2] = make_uint2(0u, 0u);
+    if (iy >= 0 && iy < a.ih) {
+      const __nv_bfloat16 *r = in + ((long long)iy * a.iw + x) * a.in_pitch;
+      if (left) h[0] = __ldg(reinterpret_cast<const uint2 *>(r - a.in_pitch));
+      h[1] = __ldg(reinterpret_cast<const uint2 *>(r));
+      if (right) h[2] = __ldg(reinterpret_cast<const uint2 *>(r + a.in_pitch));
+    }
+  };
+  float2 a0[3], a1[3];
+  uint2 cur[3], nxt[3];
+  load_row(0, cur);
+#pragma unroll
+  for (int i = 0; i < R + 2; ++i) {
+    if (i + 1 < R + 2) load_row(i + 1, nxt);  // in flight while row i is consumed
+    float2 v0[3], v1[3];
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) { v0[dx] = lo2(cur[dx].x); v1[dx] = lo2(cur[dx].y); }
+#pragma unroll
+    for (int tr = 0; tr < 3; ++tr) {  // input row i is tap row tr of output row i - tr
+      const int r = i - tr;
+      if (r < 0 || r >= R) continue;
+      float2 &o0 = a0[r % 3], &o1 = a1[r % 3];
+      if (tr == 0) { o0 = blo; o1 = bhi; }
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        o0 = dw_ffma2(v0[dx], wlo[tr * 3 + dx], o0);
+        o1 = dw_ffma2(v1[dx], whi[tr * 3 + dx], o1);
+      }
+      if (tr == 2 && oy0 + r < a.oh) {
+        float2 y0 = o0, y1 = o1;
+        if (a.relu) { y0.x = fmaxf(y0.x, 0.f); y0.y = fmaxf(y0.y, 0.f); y1.x = fmaxf(y1.x, 0.f); y1.y = fmaxf(y1.y, 0.f); }
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(y0.x, y0.y), h1 = __floats2bfloat162_rn(y1.x, y1.y);
+        *reinterpret_cast<uint2 *>(out + ((long long)(oy0 + r) * a.ow + x) * a.out_pitch) =
+            make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
+      }
+    }
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) cur[dx] = nxt[dx];
+  }
+}
+
 template <int CO_T, int IN_VEC>
 int launch_generic(const ConvArgs &a, cudaStream_t s) {
   const long long npix = (long long)a.n * a.oh * a.ow;
@@ -605,6 +688,19 @@ int direct_conv_launch(const ConvArgs &a, bool depthwise, cudaStream_t s) {
     UYD_REQUIRE(a.cin % 8 == 0 && a.in_pitch % 8 == 0 && a.out_pitch % 8 == 0 && !a.out_f32 && !a.res &&
                     (reinterpret_cast<uintptr_t>(a.in) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0,
                 UYD_E_UNSUPPORTED, "depthwise conv needs C %% 8 == 0 and 16-byte aligned slices");
+    if (a.k == 3 && a.stride == 1 && a.ih == a.oh && a.iw == a.ow && getenv("UYD_DW_OLD") == nullptr) {
+      auto go = [&](auto kern, int R) {
+        const long long totalc = (long long)a.n * ((a.oh + R - 1) / R) * a.ow * (a.cin / 4);
+        kern<<<(unsigned)((totalc + kThreads - 1) / kThreads), kThreads, 0, s>>>(a);
+        return (int)cudaGetLastError();
+      };
+      // rows per thread (measured at 64 x 40 x 40 x 128: R = 4 / 8 / 10 / 20 -> 30.8 / 25.6 / 24.6 / 23.4 us): the tallest
+      // strip that still leaves 1024 threads per SM
+      const long long cols = (long long)a.n * a.ow * (a.cin / 4), want = 1024ll * current_sm_count();
+      if (a.oh % 20 == 0 && cols * (a.oh / 20) >= want) return go(conv_dw_col_kernel<20>, 20);
+      if (a.oh % 10 == 0 && cols * (a.oh / 10) >= want) return go(conv_dw_col_kernel<10>, 10);
+      return go(conv_dw_col_kernel<8>, 8);
+    }
     if (a.k == 3 && a.stride == 1 && a.ow % 4 == 0) {
       const long long total4 = (long long)a.n * a.oh * (a.ow / 4) * (a.cin / 8);
       conv_dw4_kernel<<<(unsigned)((total4 + kThreads - 1) / kThreads), kThreads, 0, s>>>(a);
