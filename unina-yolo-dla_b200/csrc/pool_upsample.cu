@@ -115,18 +115,25 @@ __global__ void __launch_bounds__(kPlaneThreads) sppf_plane_kernel(__nv_bfloat16
   }
 }
 
+// One thread per INPUT element (8 channels of one pixel): one 16-byte load, four 16-byte stores (was one load per
+// output element: 4x the load instructions for the same bytes; c64 -> 160 x 160 at batch 64: 84 us).
 __global__ void __launch_bounds__(kThreads) upsample2x_kernel(const __nv_bfloat16 *in, int in_pitch, __nv_bfloat16 *out,
-                                                              int out_pitch, long long total, int oh, int ow, int cg) {
+                                                              int out_pitch, long long total_in, int oh, int ow, int cg) {
   const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
-  if (t >= total) return;
-  const int g = (int)(t % cg);
-  const long long p = t / cg;
-  const int ox = (int)(p % ow);
-  const int oy = (int)((p / ow) % oh);
-  const long long n = p / ((long long)ow * oh);
+  if (t >= total_in) return;
   const int ih = oh / 2, iw = ow / 2;
-  const uint4 v = *reinterpret_cast<const uint4 *>(in + ((n * ih + oy / 2) * iw + ox / 2) * in_pitch + g * 8);
-  *reinterpret_cast<uint4 *>(out + p * out_pitch + g * 8) = v;
+  const int g = (int)(t % cg);
+  const long long p = t / cg;   // input pixel (n, iy, ix)
+  const int ix = (int)(p % iw);
+  const int iy = (int)((p / iw) % ih);
+  const long long n = p / ((long long)iw * ih);
+  const uint4 v = __ldg(reinterpret_cast<const uint4 *>(in + p * in_pitch + g * 8));
+  __nv_bfloat16 *o = out + ((n * oh + 2 * iy) * ow + 2 * ix) * out_pitch + g * 8;
+  *reinterpret_cast<uint4 *>(o) = v;
+  *reinterpret_cast<uint4 *>(o + out_pitch) = v;
+  o += (long long)ow * out_pitch;
+  *reinterpret_cast<uint4 *>(o) = v;
+  *reinterpret_cast<uint4 *>(o + out_pitch) = v;
 }
 
 // [n,h,w,c] fp32 -> [n,c,h,w] fp32 through a 32x32 shared-memory transpose of (hw, c).
@@ -173,7 +180,7 @@ int upsample2x_launch(const __nv_bfloat16 *in, int in_pitch, __nv_bfloat16 *out,
   UYD_REQUIRE(c % 8 == 0 && in_pitch % 8 == 0 && out_pitch % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(out) & 15) == 0,
               UYD_E_UNSUPPORTED, "upsample needs C %% 8 == 0 and 16-byte aligned slices");
-  const long long total = (long long)n * ih * 2 * iw * 2 * (c / 8);
+  const long long total = (long long)n * ih * iw * (c / 8);   // input elements
   upsample2x_kernel<<<(unsigned)((total + kThreads - 1) / kThreads), kThreads, 0, s>>>(in, in_pitch, out, out_pitch,
                                                                                         total, ih * 2, iw * 2, c / 8);
   return (int)cudaGetLastError();
