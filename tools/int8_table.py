@@ -7,13 +7,24 @@ import torch
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import unina_yolo_dla_b200 as uyd  # noqa: E402
 
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+B = int(args[0]) if args else 64
 m = uyd.UninaYoloB200.from_yaml().init_synthetic(0).cuda()
 x = torch.rand(B, 3, 640, 640, device="cuda")
 m.calibrate_int8(x[:8])
 p = m.plan_for(x)
 m(x)
+if "--ncu" in sys.argv:   # ncu --profile-from-start off: one run of the INT8 plan
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    p.run(x)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+    sys.exit(0)
 ms = p.profile(x)
+if "--all" in sys.argv:   # plan order
+    for i, t in enumerate(ms):
+        print(f"  {i:3d} {t:7.4f} ms  {p.op_info(i)[0]}")
 agg = {}
 for i, t in enumerate(ms):
     txt = p.op_info(i)[0]
