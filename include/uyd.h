@@ -131,6 +131,15 @@ typedef struct uyd_c3k {
 } uyd_c3k;
 int uyd_plan_add_c3k(uyd_plan *plan, const uyd_c3k *desc, const float *const weights[7], const float *const biases[7]);
 
+/* The same block of the INT8 (fake-quant) graph, qat.py:109-124: every one of the seven convs is a QuantConv2d.
+ * weights[i]: int8 codes of conv i (layouts as above), mult[i] / biases[i]: its per-channel requant pair
+ * (y = float(acc) * m_c + b_c), in_scale[i] = 127 / amax of its input quantiser (i in the order cv1, cv2, m0.cv1, m0.cv2,
+ * m1.cv1, m1.cv2, cv3).  Input and output slices are bf16 (the activations the graph defines); all integer sums are
+ * exact, every rounding is the one the unfused ops (uyd_plan_add_quantize + uyd_plan_add_conv_s8) perform: the output
+ * equals theirs bit for bit.  One launch instead of seven convs and four to five quantize passes. */
+int uyd_plan_add_c3k_s8(uyd_plan *plan, const uyd_c3k *desc, const int8_t *const weights[7], const float *const mult[7],
+                        const float *const biases[7], const float *in_scale);
+
 /* Fused class branch of the Detect head (Detect.cv3[l], non-legacy): DWConv(cin,cin,3) -> Conv(cin,mid,1)
  * -> DWConv(mid,mid,3) -> Conv(mid,mid,1) -> Conv2d(mid,nc,1) in one launch; the nc logits are
  * written as fp32 into a slice of the head buffer.  weights/biases (BN folded): [0] dw1 [cin][1][3][3],

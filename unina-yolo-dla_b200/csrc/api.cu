@@ -68,6 +68,9 @@ struct C3kArgs {
 };
 bool c3k_supported(int c, int h, int w, int in_pitch, int in_coff, int out_pitch, int out_coff);
 void c3k_pack(int c, const float *const w[7], const float *const b[7], std::vector<uint32_t> &frags, std::vector<float> &bias);
+void c3k_pack_q(int c, const int8_t *const wq[7], const float *const mult[7], const float *const bias[7], const float in_scale[7],
+                std::vector<uint32_t> &frags, std::vector<float> &table);
+int c3k_launch_q(int c, const C3kArgs &a, cudaStream_t s);
 int c3k_launch(int c, const C3kArgs &a, cudaStream_t s);
 
 struct ClsArgs {
@@ -153,6 +156,7 @@ struct Op {
   ChainConv *cc = nullptr;
   std::vector<float> b2_host, w3_host, b3_host;
   float *b2_dev = nullptr, *w3_dev = nullptr, *b3_dev = nullptr;
+  bool quant = false;  // OP_C3K: INT8 (fake-quant) variant, b_host = [7][32] bias | [7][32] multiplier | 7 input scales
   // sppf / upsample
   int buf = -1, coff = 0, c = 0, out_buf = -1, out_coff = 0;
 };
@@ -393,6 +397,33 @@ extern "C" int uyd_plan_add_c3k(uyd_plan *plan, const uyd_c3k *d, const float *c
   op.buf = d->in_buf; op.coff = d->in_coff; op.out_buf = d->out_buf; op.out_coff = d->out_coff; op.c = d->c;
   std::vector<uint32_t> frags;
   c3k_pack(d->c, weights, biases, frags, op.b_host);
+  op.w_host.resize(frags.size() * 4);
+  memcpy(op.w_host.data(), frags.data(), op.w_host.size());
+  plan->ops.push_back(std::move(op));
+  return UYD_OK;
+}
+
+extern "C" int uyd_plan_add_c3k_s8(uyd_plan *plan, const uyd_c3k *d, const int8_t *const weights[7], const float *const mult[7],
+                                   const float *const biases[7], const float *in_scale) {
+  UYD_REQUIRE(plan && d && weights && mult && biases && in_scale, UYD_E_ARG, "uyd_plan_add_c3k_s8: NULL argument");
+  UYD_REQUIRE(!plan->finalized, UYD_E_STATE, "plan already finalized");
+  int e;
+  if ((e = check_slice(plan, d->in_buf, d->in_coff, d->c, "c3k input"))) return e;
+  if ((e = check_slice(plan, d->out_buf, d->out_coff, d->c, "c3k output"))) return e;
+  const Buffer &ib = plan->bufs[d->in_buf], &ob = plan->bufs[d->out_buf];
+  UYD_REQUIRE(ib.dtype == UYD_BF16 && ob.dtype == UYD_BF16 && ib.h == ob.h && ib.w == ob.w, UYD_E_ARG,
+              "int8 c3k needs bf16 buffers of equal extent (the block quantises its input itself)");
+  UYD_REQUIRE(c3k_supported(d->c, ib.h, ib.w, ib.c, d->in_coff, ob.c, d->out_coff), UYD_E_UNSUPPORTED,
+              "fused int8 c3k: c=%d %dx%d is not supported (c in {8,16,32}, W %% 40 == 0, H %% 32|20|16 == 0, 16-byte slices)",
+              d->c, ib.h, ib.w);
+  for (int i = 0; i < 7; ++i)
+    UYD_REQUIRE(weights[i] && mult[i] && biases[i], UYD_E_ARG, "uyd_plan_add_c3k_s8: array %d is NULL", i);
+  Op op;
+  op.kind = OP_C3K;
+  op.quant = true;
+  op.buf = d->in_buf; op.coff = d->in_coff; op.out_buf = d->out_buf; op.out_coff = d->out_coff; op.c = d->c;
+  std::vector<uint32_t> frags;
+  c3k_pack_q(d->c, weights, mult, biases, in_scale, frags, op.b_host);
   op.w_host.resize(frags.size() * 4);
   memcpy(op.w_host.data(), frags.data(), op.w_host.size());
   plan->ops.push_back(std::move(op));
@@ -735,7 +766,7 @@ static int launch_op(uyd_plan *plan, const Op &o, const void *x, int x_kind, int
       a.out = (__nv_bfloat16 *)slice_ptr(plan, o.out_buf, o.out_coff);
       a.wfrag = (const uint32_t *)o.w_dev; a.bias = o.b_dev;
       a.n = batch; a.h = ib.h; a.w = ib.w; a.in_pitch = ib.c; a.out_pitch = ob.c;
-      e = c3k_launch(o.c, a, s);
+      e = o.quant ? c3k_launch_q(o.c, a, s) : c3k_launch(o.c, a, s);
     } else if (o.kind == OP_STEM2) {
       UYD_REQUIRE(x, UYD_E_ARG, "uyd_plan_run: x is NULL");
       const Buffer &ob = plan->bufs[o.out_buf];
@@ -964,7 +995,7 @@ extern "C" int uyd_plan_op_info(uyd_plan *plan, int op, char *text, size_t text_
     const double c = o.c, h = c / 2;
     fl = 2.0 * b.h * b.w * (2 * c * h + 4 * 9 * h * h + c * c);
     by = (double)b.h * b.w * c * 2 * 2;
-    snprintf(text, text_len, "c3k_fused c%d %dx%d (7 convs)", o.c, b.h, b.w);
+    snprintf(text, text_len, "%s c%d %dx%d (7 convs)", o.quant ? "c3k_fused_s8" : "c3k_fused", o.c, b.h, b.w);
   } else if (o.kind == OP_SPPF) {
     const Buffer &b = plan->bufs[o.buf];
     by = (double)b.h * b.w * o.c * 2 * 4;

@@ -385,6 +385,113 @@ struct Stage6 {
   }
 };
 
+// ---- INT8 (fake-quant, qat.py:109-124) variant of the block: exact integers in bf16 containers ---------------------------
+// Every conv input of the QAT graph is q = clamp(rne(x * s), -127, 127) and every weight an int8 code.  Both are exact in
+// bf16, and with K * 127^2 < 2^24 (K <= 144 here) the fp32 accumulation of mma.sync is exact too: acc IS the int32 sum of
+// the integer convolution.  The epilogues then follow the integer reference step by step: y = float(acc) * m_c + b_c
+// (separate round-to-nearest multiply and add), ReLU, + residual (the bf16 activation, added in fp32), ONE rounding to
+// bf16 -- the activation the graph defines -- and, for the conv that consumes it, its int8 code stored as a bf16 value.
+#if defined(__CUDACC__)
+namespace q8 {
+__device__ __forceinline__ float rq(float acc, float m, float b) { return __fadd_rn(__fmul_rn(acc, m), b); }
+__device__ __forceinline__ float qv(float y, float s) { return fminf(fmaxf(rintf(__fmul_rn(y, s)), -127.f), 127.f); }
+// two bf16 activations (packed) -> their int8 codes for input scale s, as packed bf16 values
+__device__ __forceinline__ uint32_t qpack(uint32_t y2, float s) { return pack_bf16(qv(bf16_lo(y2), s), qv(bf16_hi(y2), s)); }
+
+// Stage 1, a half (tiles j < NT / 2 of Stage1): real a -> A (residual of m0), its code for m0.cv1 -> Aq
+template <int C>
+__device__ __forceinline__ void store_a(unsigned char *A, unsigned char *Aq, int f, int lane, int mt, const float (&acc)[Geo<C>::N1][4],
+                                        const float (&bz)[Geo<C>::N1][2], const float (&mz)[Geo<C>::N1][2], uint32_t mw, float s_next) {
+  using G = Geo<C>;
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    auto y2 = [&](int j) { return relu_pack_bf16(rq(acc[j][2 * h], mz[j][0], bz[j][0]), rq(acc[j][2 * h + 1], mz[j][1], bz[j][1])); };
+    if (C == 4 || C == 8) {
+      const int bit = C == 4 ? 2 * g + (t >> 1) + 16 * h : 16 * mt + 8 * h + g;
+      const int o = C == 4 ? (f + 2 * g + 16 * h) * G::PXA + 4 * t : (f + bit) * G::PXA + 4 * t;
+      const bool in = (mw >> bit) & 1u;
+      const uint32_t ya = y2(0);
+      st32(A + o, in ? ya : 0u);
+      st32(Aq + o, in ? qpack(ya, s_next) : 0u);
+    } else {
+      const int bit = 16 * mt + 8 * h + g;
+      const int o = (f + bit) * G::PXA + 8 * t;
+      const bool in = (mw >> bit) & 1u;
+      const uint32_t v0 = y2(0), v1 = y2(1);
+      st64(A + o, in ? v0 : 0u, in ? v1 : 0u);
+      st64(Aq + o, in ? qpack(v0, s_next) : 0u, in ? qpack(v1, s_next) : 0u);
+    }
+  }
+}
+// Stage 1, b half (tiles j >= NT / 2): only cv3 reads b -> its code for cv3's input scale
+template <int C>
+__device__ __forceinline__ void store_b(unsigned char *Bv, int f, int lane, int mt, const float (&acc)[Geo<C>::N1][4],
+                                        const float (&bz)[Geo<C>::N1][2], const float (&mz)[Geo<C>::N1][2], float s_cv3) {
+  using G = Geo<C>;
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    auto y2 = [&](int j) { return relu_pack_bf16(rq(acc[j][2 * h], mz[j][0], bz[j][0]), rq(acc[j][2 * h + 1], mz[j][1], bz[j][1])); };
+    if (C == 4) {
+      st32(Bv + (f + 2 * g + 16 * h - kB0) * G::PXA + 4 * t, qpack(y2(1), s_cv3));
+    } else if (C == 8) {
+      st32(Bv + (f + 16 * mt + 8 * h + g - kB0) * G::PXA + 4 * t, qpack(y2(1), s_cv3));
+    } else {
+      st64(Bv + (f + 16 * mt + 8 * h + g - kB0) * G::PXA + 8 * t, qpack(y2(2), s_cv3), qpack(y2(3), s_cv3));
+    }
+  }
+}
+// 3x3 stages.  !RES (t1, t2: read by one conv only): the code for that conv -> Dq.  RES (u, v): y = bf16(relu(.) + r) with
+// r the bf16 residual in Dr (a, resp. u): y -> Dr (the next residual), its code -> Dq.
+template <int C, bool RES>
+__device__ __forceinline__ void store_3(unsigned char *Dr, unsigned char *Dq, int f, int lane, int mt, const float (&acc)[Geo<C>::N3][4],
+                                        const float (&bz)[Geo<C>::N3][2], const float (&mz)[Geo<C>::N3][2], uint32_t mw, float s_next) {
+  using G = Geo<C>;
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    auto y2 = [&](int j, uint32_t r) {
+      const float lo = rq(acc[j][2 * h], mz[j][0], bz[j][0]), hi = rq(acc[j][2 * h + 1], mz[j][1], bz[j][1]);
+      if (RES) return pack_bf16(__fadd_rn(relu(lo), bf16_lo(r)), __fadd_rn(relu(hi), bf16_hi(r)));
+      return relu_pack_bf16(lo, hi);
+    };
+    if (C == 4 || C == 8) {
+      const int bit = C == 4 ? 2 * g + (t >> 1) + 16 * h : 16 * mt + 8 * h + g;
+      const int o = C == 4 ? (f + 2 * g + 16 * h) * G::PXA + 4 * t : (f + bit) * G::PXA + 4 * t;
+      const bool in = (mw >> bit) & 1u;
+      const uint32_t v = y2(0, RES ? ld32(Dr + o) : 0u);
+      if (RES) st32(Dr + o, in ? v : 0u);
+      st32(Dq + o, in ? qpack(v, s_next) : 0u);
+    } else {
+      const int bit = 16 * mt + 8 * h + g;
+      const int o = (f + bit) * G::PXA + 8 * t;
+      const bool in = (mw >> bit) & 1u;
+      uint2 r = make_uint2(0u, 0u);
+      if (RES) r = ld64(Dr + o);
+      const uint32_t v0 = y2(0, r.x), v1 = y2(1, r.y);
+      if (RES) st64(Dr + o, in ? v0 : 0u, in ? v1 : 0u);
+      st64(Dq + o, in ? qpack(v0, s_next) : 0u, in ? qpack(v1, s_next) : 0u);
+    }
+  }
+}
+// Stage 6: y = bf16(relu(float(acc) m + b)) -> staged output tile (the block's bf16 output; no consumer code here)
+template <int C>
+__device__ __forceinline__ void store_y(unsigned char *Y, int f, int lane, int mt, const float (&acc)[Geo<C>::N6][4],
+                                        const float (&bz)[Geo<C>::N6][2], const float (&mz)[Geo<C>::N6][2]) {
+  using G = Geo<C>;
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    auto y2 = [&](int j) { return relu_pack_bf16(rq(acc[j][2 * h], mz[j][0], bz[j][0]), rq(acc[j][2 * h + 1], mz[j][1], bz[j][1])); };
+    if (C == 4) st64(Y + (f - kB0 + 2 * g + 16 * h) * G::PXX + 8 * t, y2(0), y2(1));
+    else if (C == 8) st64(Y + (f - kB0 + 16 * mt + 8 * h + g) * G::PXX + 8 * t, y2(0), y2(1));
+    else st128(Y + (f - kB0 + 16 * mt + 8 * h + g) * G::PXX + 16 * t, y2(0), y2(1), y2(2), y2(3));
+  }
+}
+}  // namespace q8
+#endif
+
 // ---- host-side packing: B fragments of every stage (m16n8k16: lane (g, t) holds B[2t, 2t+1][g] and B[2t+8, 2t+9][g])
 // ldsm: the stage loads A with ldmatrix (logical k = physical column), otherwise with LDS.64 (phys_col permutation)
 template <class F>

@@ -14,6 +14,9 @@ size_t c3k_flat_smem_bytes(int c_, int th);
 void c3k_flat_pack(int c, const float *const w[7], std::vector<uint32_t> &frags);
 struct C3kArgs;
 int c3k_flat_launch(int c, const C3kArgs &a, cudaStream_t s);
+int c3k_flat_q_launch(int c, const C3kArgs &a, cudaStream_t s);   // INT8 (fake-quant) variant
+size_t c3k_flat_q_smem_bytes(int c_, int th);
+void c3k_flat_pack(int c, const float *const w[7], std::vector<uint32_t> &frags);
 int c3k_flat_words(int c);
 // c3k_tc.cu: the tcgen05 generation (c = 16 / 32, batches that fill the GPU with full-width strips)
 bool c3k_tc_supported(int c, int h, int w);
@@ -496,6 +499,58 @@ int c3k_launch(int c, const C3kArgs &a0, cudaStream_t s) {
   if ((c == 16 || c == 32) && c3k_tc_supported(c, a.h, a.w) && (force ? *force == '1' : c3k_tc_preferred(c, a.h, a.w, a.n)))
     return c3k_tc_launch(c, a, a.wfrag + c3k_flat_words(c), s);
   return c3k_flat_launch(c, a, s);
+}
+
+
+// INT8 variant: the extra code frame makes a tile bigger, so the tile height is chosen per shape: the tallest of
+// {40, 32, 20, 16} rows that lets three, else two CTAs share an SM, else the tallest that fits at all (then 8 / 4 rows).
+// Never the tcgen05 kernel.
+int c3k_launch_q(int c, const C3kArgs &a0, cudaStream_t s) {
+  C3kArgs a = a0;
+  const int first = c3k_launch_th(a.n, a.h, a.w);
+  int th = 0;
+  if (const char *v = getenv("UYD_C3K_Q_TH")) {  // experiment hook
+    const int t = atoi(v);
+    if (t > 0 && a.h % t == 0 && c3k_flat_q_smem_bytes(c / 2, t) <= 226 * 1024) th = t;
+  }
+  const size_t limits[3] = {75 * 1024, 112 * 1024, 226 * 1024};
+  const int tall[4] = {40, 32, 20, 16}, shorter[2] = {8, 4};
+  for (int l = 0; l < 3 && !th; ++l)
+    for (int i = 0; i < 4 && !th; ++i)
+      if (tall[i] <= (first > 20 ? first : 20) && a.h % tall[i] == 0 && c3k_flat_q_smem_bytes(c / 2, tall[i]) <= limits[l]) th = tall[i];
+  for (int i = 0; i < 2 && !th; ++i)
+    if (a.h % shorter[i] == 0 && c3k_flat_q_smem_bytes(c / 2, shorter[i]) <= limits[2]) th = shorter[i];
+  UYD_REQUIRE(th > 0, UYD_E_UNSUPPORTED, "fused int8 c3k: no tile height fits shared memory (c = %d, h = %d)", c, a.h);
+  a.th = th;
+  a.tiles_x = a.w / kTW;
+  a.tiles_y = a.h / a.th;
+  return c3k_flat_q_launch(c, a, s);
+}
+
+// Host side of uyd_plan_add_c3k_s8: int8 weight codes -> the flat kernel's bf16 fragments (exact), and the table the
+// kernel reads behind C3kArgs::bias: [7][32] bias | [7][32] multiplier | 7 input scales (+ 1 pad).
+void c3k_pack_q(int c, const int8_t *const wq[7], const float *const mult[7], const float *const bias[7], const float in_scale[7],
+                std::vector<uint32_t> &frags, std::vector<float> &table) {
+  const int C = c / 2;
+  const int couts[7] = {C, C, C, C, C, C, c};
+  const size_t sizes[7] = {(size_t)C * c, (size_t)C * c, (size_t)C * C * 9, (size_t)C * C * 9, (size_t)C * C * 9, (size_t)C * C * 9, (size_t)c * c};
+  std::vector<std::vector<float>> wf(7);
+  const float *wp[7];
+  for (int i = 0; i < 7; ++i) {
+    wf[i].resize(sizes[i]);
+    for (size_t k = 0; k < sizes[i]; ++k) wf[i][k] = (float)wq[i][k];
+    wp[i] = wf[i].data();
+  }
+  frags.clear();
+  c3k_flat_pack(c, wp, frags);
+  table.assign(14 * 32 + 8, 0.f);
+  for (int i = 0; i < 7; ++i) {
+    for (int n = 0; n < couts[i]; ++n) {
+      table[i * 32 + n] = bias[i][n];
+      table[7 * 32 + i * 32 + n] = mult[i][n];
+    }
+    table[14 * 32 + i] = in_scale[i];
+  }
 }
 
 }  // namespace uyd

@@ -144,6 +144,21 @@ class Plan:
         check(_lib.lib().uyd_plan_add_c3k(self.handle, C.byref(d), wp, bp), "uyd_plan_add_c3k")
         return dst
 
+    def c3k_s8(self, src: Slice, dst: Slice, weights_q: list, mults: list, biases: list, in_scales: list) -> Slice:
+        """Fused C3k block of the INT8 graph (uyd_plan_add_c3k_s8): per conv [cv1, cv2, m0.cv1, m0.cv2, m1.cv1, m1.cv2, cv3]
+        its int8 weight codes, requant pair (m_c, b_c) and input scale; src / dst are bf16 slices."""
+        ws = [np.ascontiguousarray(w, dtype=np.int8) for w in weights_q]
+        ms = [np.ascontiguousarray(m, dtype=np.float32) for m in mults]
+        bs = [np.ascontiguousarray(b, dtype=np.float32) for b in biases]
+        assert len(ws) == 7 and len(ms) == 7 and len(bs) == 7 and len(in_scales) == 7
+        wp = (C.c_void_p * 7)(*[w.ctypes.data_as(C.c_void_p) for w in ws])
+        mp = (C.c_void_p * 7)(*[m.ctypes.data_as(C.c_void_p) for m in ms])
+        bp = (C.c_void_p * 7)(*[b.ctypes.data_as(C.c_void_p) for b in bs])
+        sc = (C.c_float * 7)(*[float(x) for x in in_scales])
+        d = C3kDesc(src.buf, src.coff, dst.buf, dst.coff, src.c, 0)
+        check(_lib.lib().uyd_plan_add_c3k_s8(self.handle, C.byref(d), wp, mp, bp, sc), "uyd_plan_add_c3k_s8")
+        return dst
+
     @staticmethod
     def cls_branch_supported(src: Slice, mid: int, nc: int) -> bool:
         return src.c in (32, 64) and mid == 32 and nc <= 8 and src.w % 40 == 0 and src.h % 8 == 0 and src.coff % 8 == 0

@@ -202,6 +202,27 @@ class C3k(nn.Module):
                 folded = [fold_bn(m.conv, m.bn) for m in (self.cv1, self.cv2, self.m[0].cv1, self.m[0].cv2,
                                                           self.m[1].cv1, self.m[1].cv2, self.cv3)]
                 return p.c3k(src, dst, [w for w, _ in folded], [b for _, b in folded])
+        convs = (self.cv1, self.cv2, self.m[0].cv1, self.m[0].cv2, self.m[1].cv1, self.m[1].cv2, self.cv3) if len(self.m) == 2 else ()
+        names = [getattr(m.conv, "_uyd_name", "") for m in convs]
+        fusable_q = (len(convs) == 7 and all(b.add and b.cv1.k == 3 and b.cv2.k == 3 for b in self.m) and self.cv3.c2 == src.c
+                     and 2 * self.c_ == src.c and getattr(p, "fusion", True) and os.environ.get("UYD_INT8_NO_C3K_FUSION", "0") != "1"
+                     and all(_quantized(p, n) for n in names) and getattr(p, "conv_inputs", None) is None)
+        if fusable_q:
+            # INT8 graph: the whole block in one launch (uyd_plan_add_c3k_s8) -- the seven QuantConv2d with their input
+            # quantisers inside the kernel, bit-identical to the quantize + conv_s8 ops emitted below
+            dst = dst or p.buffer(src.h, src.w, self.cv3.c2)
+            if p.c3k_supported(src, dst) and p.shapes[src.buf][2] % 8 == 0 and p.shapes[dst.buf][2] % 8 == 0:
+                wq, mu, bi, sc = [], [], [], []
+                for m, n in zip(convs, names):
+                    ax, aw = p.quant.amax[n]
+                    wq.append(Q.quantize_weights(m.conv.weight, aw))
+                    mm, bb = Q.requant_params(ax, aw, m.bn, m.conv.bias)
+                    mu.append(mm)
+                    bi.append(bb)
+                    sc.append(float(Q.scale_of(ax)))
+                for m, n in zip(convs, names):
+                    _record_input(p, n, src)
+                return p.c3k_s8(src, dst, wq, mu, bi, sc)
         cat = p.buffer(src.h, src.w, 2 * self.c_)
         t = self.cv1.emit(p, src)
         for i, b in enumerate(self.m):
