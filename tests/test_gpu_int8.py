@@ -179,3 +179,53 @@ def test_int8_network_is_bit_exact_from_the_last_float_layer():
     m2 = uyd.UninaYoloB200.from_yaml()
     m2.load_state_dict(sd)
     assert m2.quant is not None and m2.quant.amax.keys() == amax.keys()
+
+
+@pytest.mark.parametrize("c,H,W,B", [(8, 40, 80, 3), (16, 40, 40, 2), (32, 20, 40, 2), (8, 160, 160, 2), (16, 80, 80, 5), (32, 40, 40, 9)])
+def test_fused_int8_c3k_block_equals_the_unfused_ops(c, H, W, B, monkeypatch):
+    """uyd_plan_add_c3k_s8 (one launch: int8 codes as exact bf16 values on the flat-frame mma.sync kernel, requantisation
+    in the stage epilogues) against the seven conv_s8 + quantize ops the same C3k emits when the fusion is switched off:
+    the bf16 output bytes must be identical (the unfused ops are the ones pinned to the integer oracle above).  Channel
+    slices of wider buffers, tiles at every image border, several tiles per image."""
+    import torch.nn as nn
+    import unina_yolo_dla_b200 as uyd
+    from unina_yolo_dla_b200 import quant as Q
+    from unina_yolo_dla_b200 import yolo as Y
+
+    g = torch.Generator().manual_seed(100 * c + H)
+    blk = Y.C3k(c, c, 2)
+    amax = {}
+    for name, mod in blk.named_modules():
+        if isinstance(mod, nn.Conv2d):
+            mod._uyd_name = "model.9." + name
+            mod.weight.data = torch.randn(mod.weight.shape, generator=g) / (mod.weight[0].numel() ** 0.5)
+            amax[mod._uyd_name] = (float(torch.empty(1).uniform_(2.0, 5.0, generator=g)), float(mod.weight.detach().abs().max()))
+        if isinstance(mod, nn.BatchNorm2d):
+            mod.weight.data = torch.empty(mod.num_features).uniform_(0.6, 1.4, generator=g)
+            mod.bias.data = torch.randn(mod.num_features, generator=g) * 0.2
+            mod.running_mean = torch.randn(mod.num_features, generator=g) * 0.2
+            mod.running_var = torch.empty(mod.num_features).uniform_(0.5, 1.5, generator=g)
+    blk.eval()
+    x = (torch.randn(B, c, H, W, generator=g) * 1.5).relu()
+
+    def run(fused: bool):
+        monkeypatch.setenv("UYD_INT8_NO_C3K_FUSION", "0" if fused else "1")
+        p = uyd.Plan(0, B)
+        p.quant = Q.QuantSpec(dict(amax), ())
+        p.fusion = True
+        src = p.buffer(H, W, 3 * c).sub(c, c)
+        dst = p.buffer(H, W, 2 * c).sub(c, c)
+        blk.emit(p, src, dst)
+        p.finalize()
+        p.write(src, x)
+        p.run_no_input(B)
+        torch.cuda.synchronize()
+        texts = [p.op_info(i)[0] for i in range(p.launches)]
+        return p.read(dst, B).cpu(), texts, float(p.read(p.buffer_slice(dst.buf, 0, c), B).abs().max())
+
+    got, t_fused, outside = run(True)
+    want, t_unfused, _ = run(False)
+    assert len(t_fused) == 1 and t_fused[0].startswith("c3k_fused_s8") and len(t_unfused) >= 11
+    assert outside == 0.0
+    assert float(want.abs().max()) > 0.1
+    assert got.numpy().tobytes() == want.numpy().tobytes()

@@ -307,8 +307,9 @@ __global__ void __launch_bounds__(NW * 32) c3k_flat_q_kernel(C3kArgs a) {
   auto stage_x = [&](float s, bool first) {
     constexpr int CH16 = G::CC / 8, UN = 8;
     const __nv_bfloat16 *img = a.in + (long long)n * H * W * a.in_pitch;
-    const int total = L.FR * CH16;
-    for (int base = 0; base < total; base += UN * NT) {
+    // the second pass (cv2's scale) only feeds stage 1b, which reads the output rows: frame rows 4 .. TH + 3
+    const int total = (first ? L.FR : (TH + 4) * kPW) * CH16;
+    for (int base = first ? 0 : 4 * kPW * CH16; base < total; base += UN * NT) {
       uint4 v[UN];
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
