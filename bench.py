@@ -165,7 +165,8 @@ def bench_int8(model, batch: int, size: int, dev, steps: int):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     n_blk = sum(1 for i in range(plan.launches) if plan.op_info(i)[0].startswith("c3k_fused_s8"))
-    n_s8 = sum(1 for i in range(plan.launches) if plan.op_info(i)[0].startswith("conv_s8")) + 7 * n_blk
+    n_fold = sum(1 for i in range(plan.launches) if plan.op_info(i)[0].startswith("conv_s8") and "+up(partial)" in plan.op_info(i)[0])
+    n_s8 = sum(1 for i in range(plan.launches) if plan.op_info(i)[0].startswith("conv_s8")) - n_fold + 7 * n_blk
     s8_ops = sum(plan.op_info(i)[1] for i in range(plan.launches) if plan.op_info(i)[0].startswith("conv_s8"))
     prof = plan.profile(x, None)
     s8_ms = sum(t for i, t in enumerate(prof) if plan.op_info(i)[0].startswith("conv_s8"))

@@ -113,6 +113,10 @@ typedef struct uyd_conv_s8 {
   int res_buf, res_coff;   /* bf16 residual slice added (fp32) AFTER the activation, res_buf = -1: none */
   int out_round_bf16;      /* UYD_S8 output only: 1 = y is rounded to bf16 before the consumer's quantiser, i.e. the bytes a
                               bf16 activation + uyd_plan_add_quantize would produce, without materialising the activation */
+  int pre_buf_p1;          /* 0: none; b + 1: fp32 buffer b [h/2, w/2, cout] of INTEGER partial sums (an int8 1x1 conv with
+                              m = 1, b = 0 into a UYD_F32 buffer) added, nearest-x2 upsampled, to the accumulator before the
+                              requant: Upsample + Concat + QuantConv2d(1x1) without the upsampled tensor (exact: the sums
+                              stay below 2^24).  1x1 convs on the tensor-core path, cout % 16 == 0 */
 } uyd_conv_s8;
 int uyd_plan_add_conv_s8(uyd_plan *plan, const uyd_conv_s8 *desc, const int8_t *weight_q, const float *mult,
                          const float *bias);

@@ -26,7 +26,8 @@ class ConvDesc(C.Structure):
 class ConvS8Desc(C.Structure):
     _fields_ = [("in_buf", C.c_int), ("in_coff", C.c_int), ("out_buf", C.c_int), ("out_coff", C.c_int), ("cin", C.c_int),
                 ("cout", C.c_int), ("k", C.c_int), ("stride", C.c_int), ("relu", C.c_int), ("out_scale", C.c_float),
-                ("impl", C.c_int), ("depthwise", C.c_int), ("res_buf", C.c_int), ("res_coff", C.c_int), ("out_round_bf16", C.c_int)]
+                ("impl", C.c_int), ("depthwise", C.c_int), ("res_buf", C.c_int), ("res_coff", C.c_int), ("out_round_bf16", C.c_int),
+                ("pre_buf_p1", C.c_int)]
 
 
 class C3kDesc(C.Structure):

@@ -354,6 +354,15 @@ extern "C" int uyd_plan_add_conv_s8(uyd_plan *plan, const uyd_conv_s8 *d, const 
     const Buffer &rb = plan->bufs[d->res_buf];
     UYD_REQUIRE(rb.h == ob.h && rb.w == ob.w && rb.dtype == UYD_BF16, UYD_E_ARG, "conv_s8 residual must match the output extent (bf16)");
   }
+  if (d->pre_buf_p1) {
+    const int pb = d->pre_buf_p1 - 1;
+    UYD_REQUIRE(pb >= 0 && pb < (int)plan->bufs.size(), UYD_E_ARG, "conv_s8: partial-sum buffer id out of range");
+    const Buffer &b = plan->bufs[pb];
+    UYD_REQUIRE(b.dtype == UYD_F32 && b.c == d->cout && b.h * 2 == ob.h && b.w * 2 == ob.w && d->cout % 16 == 0 && d->k == 1 &&
+                    d->stride == 1 && d->res_buf < 0,
+                UYD_E_ARG, "conv_s8: partial sums need an fp32 [h/2, w/2, cout] buffer, a 1x1 conv, cout %% 16 == 0, no residual");
+    op.conv.pre_buf_p1 = d->pre_buf_p1;
+  }
   op.out_scale = d->out_scale;
   op.out_kind = ob.dtype == UYD_S8 ? (d->out_round_bf16 ? 3 : 2) : (ob.dtype == UYD_F32 ? 1 : 0);
   bool tc_ok = !d->depthwise && tc_supported_s8(d->cin, d->cout, d->k, d->stride, ib.c, d->in_coff, ob.c, d->out_coff, (int)ob.elem_bytes());
@@ -363,6 +372,7 @@ extern "C" int uyd_plan_add_conv_s8(uyd_plan *plan, const uyd_conv_s8 *d, const 
   } else if (d->impl == UYD_IMPL_AUTO) {
     op.use_tc = tc_ok;
   }
+  UYD_REQUIRE(!d->pre_buf_p1 || op.use_tc, UYD_E_UNSUPPORTED, "conv_s8: partial sums are only added on the tensor-core path");
   if (op.use_tc) {
     op.w_host.resize(tc_weight_bytes_s8(d->cin, d->cout, d->k));
     tc_pack_weights_s8(d->cin, d->cout, d->k, weight_q, op.w_host.data());
@@ -704,6 +714,7 @@ extern "C" int uyd_plan_finalize(uyd_plan *plan) {
                            slice_ptr(plan, d.out_buf, d.out_coff), ob.c, 0, res, d.res_buf >= 0 ? plan->bufs[d.res_buf].c : 0, o.w_dev,
                            o.b_dev, halo_fallback ? 2 : -1, bo_mode, stages, 1, o.m_dev, o.out_scale, o.out_kind, halo_pitch);
         if (e) return e;
+        if (d.pre_buf_p1) tc_set_pre(o.tc, (const float *)plan->bufs[d.pre_buf_p1 - 1].ptr);
       }
       continue;
     }
@@ -964,7 +975,7 @@ extern "C" int uyd_plan_op_info(uyd_plan *plan, int op, char *text, size_t text_
          (d.res_buf >= 0 ? (double)ob.h * ob.w * d.cout * 2 : 0);
     snprintf(text, text_len, "conv%s %d->%d k%d s%d%s %dx%d %s%s%s", o.kind == OP_CONV_S8 ? "_s8" : "", d.cin, d.cout, d.k, d.stride,
              d.depthwise ? " dw" : "", ob.h, ob.w, o.use_tc ? "tc:" : "direct", o.use_tc ? tc_mode_name(o.tc) : "",
-             d.res_buf >= 0 ? " +res" : (o.kind == OP_CONV && d.pre_buf_p1 ? " +up(partial)" : ""));
+             d.res_buf >= 0 ? " +res" : (d.pre_buf_p1 ? " +up(partial)" : ""));
   } else if (o.kind == OP_QUANT) {
     const Buffer &b = plan->bufs[o.buf];
     by = (double)b.h * b.w * o.c * 3;

@@ -232,7 +232,7 @@ __device__ __forceinline__ void epilogue_chunk_staged(const uint32_t (&raw)[16],
 // INT8 path: y = float(acc) * m_c + b_c with separate round-to-nearest multiply and add (the
 // oracle's integer reference, oracle/quant.py), ReLU, then bf16 / fp32 / re-quantised int8.
 __device__ __forceinline__ void epilogue_chunk_i8_staged(const uint32_t (&raw)[16], const float *bias_s, const float *mult_s,
-                                                         int c0, long long pix, const TcParams &p, unsigned char *srow) {
+                                                         int c0, long long pix, const TcParams &p, unsigned char *srow, long long ppix) {
   float v[16], mv[16], bv[16];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {  // 16-byte broadcast loads of the multiplier / bias vectors
@@ -240,8 +240,19 @@ __device__ __forceinline__ void epilogue_chunk_i8_staged(const uint32_t (&raw)[1
     mv[4 * i] = m4.x; mv[4 * i + 1] = m4.y; mv[4 * i + 2] = m4.z; mv[4 * i + 3] = m4.w;
     bv[4 * i] = b4.x; bv[4 * i + 1] = b4.y; bv[4 * i + 2] = b4.z; bv[4 * i + 3] = b4.w;
   }
+  if (ppix >= 0) {  // integer partial sums of the low-resolution half (fp32 holds them exactly): acc = acc_skip + up(acc_low)
+    const float4 *pp = reinterpret_cast<const float4 *>(p.pre + ppix * p.cout + c0);
 #pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __fadd_rn(__fmul_rn(__int2float_rn((int)raw[i]), mv[i]), bv[i]);
+    for (int i = 0; i < 4; ++i) {
+      const float4 q = pp[i];
+      v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __fadd_rn(__fmul_rn(__fadd_rn(__int2float_rn((int)raw[i]), v[i]), mv[i]), bv[i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __fadd_rn(__fmul_rn(__int2float_rn((int)raw[i]), mv[i]), bv[i]);
+  }
   if (p.relu && !p.res && p.out_kind == 0) {  // the common case: ReLU rides on the bf16 conversion
     uint4 o0, o1;
     uint32_t *w0 = reinterpret_cast<uint32_t *>(&o0), *w1 = reinterpret_cast<uint32_t *>(&o1);
@@ -571,7 +582,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
         if (staged) {
           if (c * 16 < p.cout) {
-            if (I8) epilogue_chunk_i8_staged(cur, bias_s, mult_s, c * 16, pix, p, srow);
+            if (I8) epilogue_chunk_i8_staged(cur, bias_s, mult_s, c * 16, pix, p, srow, ppix);
             else epilogue_chunk_staged(cur, bias_s, c * 16, pix, p, srow, ppix);
           }
         } else if (pix >= 0 && c * 16 < p.cout) {

@@ -91,7 +91,7 @@ class Plan:
 
     def conv_s8(self, src: Slice, dst: Slice, weight_q: np.ndarray, mult: np.ndarray, bias: np.ndarray, k: int,
                 stride: int = 1, relu: bool = True, out_scale: float = 0.0, impl: int = IMPL_AUTO, depthwise: bool = False,
-                res: Slice | None = None, out_round_bf16: bool = False) -> Slice:
+                res: Slice | None = None, out_round_bf16: bool = False, pre: Slice | None = None) -> Slice:
         """INT8 conv: src in a UYD_S8 buffer, weight_q int8 [cout][cin][k][k] (depth-wise: [c][1][k][k]); the dtype
         of dst's buffer selects the epilogue (int8 re-quantised with out_scale, or fp32 / bf16); ``res`` is a bf16
         slice added after the activation."""
@@ -102,7 +102,8 @@ class Plan:
         cin = cout if depthwise else weight_q.shape[1]
         assert dst.c == cout and src.c == cin and mult.shape == (cout,) and bias.shape == (cout,)
         d = ConvS8Desc(src.buf, src.coff, dst.buf, dst.coff, cin, cout, k, stride, int(relu), float(out_scale), impl,
-                       int(depthwise), res.buf if res else -1, res.coff if res else 0, int(out_round_bf16))
+                       int(depthwise), res.buf if res else -1, res.coff if res else 0, int(out_round_bf16),
+                       (pre.buf + 1) if pre is not None else 0)
         check(_lib.lib().uyd_plan_add_conv_s8(self.handle, C.byref(d), weight_q.ctypes.data_as(C.c_void_p),
                                               mult.ctypes.data_as(C.c_void_p), bias.ctypes.data_as(C.c_void_p)),
               "uyd_plan_add_conv_s8")

@@ -98,6 +98,19 @@ def _s8_width(c: int, tc_rows: bool) -> int:
     return c
 
 
+def _s8_copy(p: Plan, src: Slice, scale: float, cpad: int) -> Slice:
+    """The int8 copy of a bf16 activation slice for input scale ``scale``, ``cpad`` channels wide (zero pad channels):
+    one copy per (slice, scale, width), shared by the convs that agree on them."""
+    cache = p.__dict__.setdefault("_qcache", {})
+    key = (src.buf, src.coff, src.c, scale, cpad)
+    q = cache.get(key)
+    if q is None:
+        q = p.buffer(src.h, src.w, cpad, UYD_S8)          # zero-filled at finalize: the pad channels stay zero
+        p.quantize(src, q.sub(0, src.c), scale)
+        cache[key] = q
+    return q
+
+
 def emit_quant_conv(p: Plan, name: str, conv: nn.Conv2d, bn, src: Slice, dst: Slice | None, relu: bool, res: Slice | None = None,
                     feeds: nn.Conv2d | None = None, feeds_f32: bool = False) -> Slice:
     """QuantConv2d as an integer convolution (quant.py): input quantiser -> int8 conv -> requant epilogue.
@@ -130,13 +143,7 @@ def emit_quant_conv(p: Plan, name: str, conv: nn.Conv2d, bn, src: Slice, dst: Sl
     if s8_in:
         qsrc = Slice(src.buf, 0, cpad, src.h, src.w)
     else:
-        cache = p.__dict__.setdefault("_qcache", {})
-        key = (src.buf, src.coff, src.c, scale, cpad)
-        qsrc = cache.get(key)
-        if qsrc is None:  # one int8 copy per (activation slice, scale, padded width): convs sharing them share the copy
-            qbuf = p.buffer(src.h, src.w, cpad, UYD_S8)          # zero-filled at finalize: the pad channels stay zero
-            p.quantize(src, qbuf.sub(0, src.c), scale)
-            qsrc = cache[key] = qbuf
+        qsrc = _s8_copy(p, src, scale, cpad)
     k, st = conv.kernel_size[0], conv.stride[0]
     if feeds is not None and dst is None:
         fname = feeds._uyd_name
@@ -263,7 +270,24 @@ class C3k2(nn.Module):
     def emit(self, p, src, dst=None):
         c, n = self.c, len(self.m)
         cat = p.buffer(src.h, src.w, (2 + n) * c)
-        if isinstance(src, UpCat):
+        if isinstance(src, UpCat) and _quantized(p, getattr(self.cv1.conv, "_uyd_name", "")):
+            # INT8 graph: the input quantiser is element-wise, so q(cat(up(a), b)) = cat(up(q(a)), q(b)), and the integer
+            # sums split the same way: acc = up(W_a q(a)) + W_b q(b).  W_a q(a) is computed at HALF resolution into an fp32
+            # buffer (exact: |sum| < 2^24) and added to the accumulator of the skip conv before its requant epilogue --
+            # bit-identical to upsample -> concat -> quantize -> conv, without the upsampled tensor and its int8 copy.
+            name = self.cv1.conv._uyd_name
+            ax, aw = p.quant.amax[name]
+            scale = float(Q.scale_of(ax))
+            qw = Q.quantize_weights(self.cv1.conv.weight, aw)
+            mult, bias = Q.requant_params(ax, aw, self.cv1.bn, self.cv1.conv.bias)
+            ca, cb = src.low.c, src.skip.c
+            pad32 = lambda n: (n + 31) // 32 * 32
+            qa, qb = _s8_copy(p, src.low, scale, pad32(ca)), _s8_copy(p, src.skip, scale, pad32(cb))
+            wpad = lambda w, n: np.concatenate((w, np.zeros((w.shape[0], n - w.shape[1], 1, 1), np.int8)), 1) if n != w.shape[1] else w
+            part = p.buffer(src.low.h, src.low.w, 2 * c, UYD_F32)
+            p.conv_s8(qa, part, wpad(qw[:, :ca], pad32(ca)), np.ones(2 * c, np.float32), np.zeros(2 * c, np.float32), 1, 1, relu=False)
+            p.conv_s8(qb, cat.sub(0, 2 * c), wpad(qw[:, ca:], pad32(cb)), mult, bias, 1, 1, relu=True, pre=part)
+        elif isinstance(src, UpCat):
             # cv1 is linear and 1x1, nearest upsampling commutes with it:
             #   cv1(cat(up(a), b)) = relu(up(W_a a) + W_b b + bias)
             # W_a a is computed at HALF resolution into an fp32 buffer and added inside cv1's epilogue, so
@@ -566,7 +590,8 @@ class UninaYoloB200(nn.Module):
                 if (isinstance(u, nn.Upsample) and isinstance(c, Concat) and isinstance(k, C3k2) and isinstance(c.f, list)
                         and len(c.f) == 2 and c.f[0] == -1 and c.f[1] != -1 and k.f == -1 and u.i not in self.save
                         and c.i not in self.save and (2 * k.c) % 16 == 0 and shape[u.i][0] % 16 == 0
-                        and shape[c.f[1] % c.i][0] % 16 == 0 and not _quantized(p, getattr(k.cv1.conv, "_uyd_name", ""))):
+                        and shape[c.f[1] % c.i][0] % 16 == 0
+                        and (not _quantized(p, getattr(k.cv1.conv, "_uyd_name", "")) or os.environ.get("UYD_INT8_NO_UPFOLD", "0") != "1")):
                     folded[c.i] = (u.i, c.f[1] % c.i)
         # pass 2: every tensor consumed by a Concat lives inside that Concat's buffer
         home = {}
