@@ -328,10 +328,11 @@ __global__ void __launch_bounds__(kStemThreads) conv_stem_tiled_kernel(ConvArgs 
 // eight horizontally adjacent output pixels the columns (B = the frame patch), K = 9 (channel, ky) combinations of
 // four consecutive patch columns (image columns 2 ox - 2 .. 2 ox + 1; the first has zero weights), four combinations
 // per mma.m16n8k16.bf16 k-step, so a B register is ONE LDS.32 of the bf16 patch.
-//   * A first version on mma.m16n8k8.tf32 was bound by that instruction itself: ncu showed the HMMA pipe 78 % active at
-//     8 cycles per HMMA.1688.TF32 and SM (1024 MACs: an eighth of the bf16 rate), 232 us.  bf16 operands with the frame
-//     SPLIT into hi + lo (x = hi + lo up to 2^-17: finer than tf32) cost 12 HMMA.16816 per 8 pixels instead of 10
-//     HMMA.1688 -- 24 pipe cycles instead of 80 -- and leave the kernel to the memory system.
+//   * A first version on mma.m16n8k8.tf32 (fp32 patch, 10 HMMA.1688 + 5 LDS.64 per 8 pixels) took 232 us; bf16 operands with
+//     the frame SPLIT into hi + lo planes (x = hi + lo up to 2^-17: finer than tf32) take 212 us (12 HMMA.16816 + 12 LDS.32).
+//     Both instructions issue at 2.0 cycles per SM (ncu, profiles/r03_issue.md section 4) and the HMMA pipe is 20-36 % busy:
+//     the kernel is bound by its integer / staging instructions; the bf16 form stages half the bytes and keeps 24 instead
+//     of 40 weight registers.
 //   * Rows of m-tile mt are assigned to channels 4 (r & 7) + 2 mt + (r >> 3), so lane (g, t) ends up with channels
 //     4g .. 4g + 3 of pixels 2t and 2t + 1: two 8-byte stores, 64 contiguous bytes per pixel across the warp.
 //   * The loads of tile i + 1 are issued before tile i is computed (tiles strided by the grid).
