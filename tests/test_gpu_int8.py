@@ -231,3 +231,22 @@ def test_fused_int8_c3k_block_equals_the_unfused_ops(c, H, W, B, monkeypatch):
     assert outside == 0.0
     assert float(want.abs().max()) > 0.1
     assert got.numpy().tobytes() == want.numpy().tobytes()
+
+
+def test_int8_predict_is_batch_independent_and_survives_graph_replay():
+    """The INT8 plan (fused C3k blocks, folded Upsample + Concat) through predict_batched: a batch of 2 takes the
+    CUDA-graph replay path, a batch of 12 the stream path with different tile heights and grid sizes -- the detections
+    of the same frames must be identical bytes (no batch coupling, no dependence on the tiling)."""
+    import unina_yolo_dla_b200 as uyd
+
+    m = uyd.UninaYoloB200.from_yaml().init_synthetic(0).cuda()
+    x = torch.rand(12, 3, 640, 640, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
+    m.calibrate_cls_bias(x[:8], 300, 0.25)
+    m.calibrate_int8(x[:8])
+    d12, c12 = (t.clone() for t in m.predict_batched(x, 0.25, 0.7, 300))
+    for _ in range(3):
+        d2, c2 = m.predict_batched(x[:2].contiguous(), 0.25, 0.7, 300)
+    torch.cuda.synchronize()
+    assert int(c2.min()) > 0 and torch.equal(c2, c12[:2]) and torch.equal(d2, d12[:2])
+    p = m.plan_for(x)
+    assert sum(1 for i in range(p.launches) if p.op_info(i)[0].startswith("c3k_fused_s8")) == 14
