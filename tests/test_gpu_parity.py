@@ -96,6 +96,23 @@ def test_tensor_core_conv_many_tiles_and_partial_batch(T):
     assert T.rel_err(got, ref) < 6e-3
 
 
+@pytest.mark.parametrize("stages", [0, 2, 3, 4, 5, 7])
+@pytest.mark.parametrize("single", [False, True])
+def test_tensor_core_conv_issuer_split_for_every_ring_size(T, stages, single, monkeypatch):
+    """conv_tc's two MMA-issuing warps take alternate tiles only when the stage ring splits evenly between them
+    (TcParams::dual); an odd ring, or one too short to halve, must fall back to one issuer.  Every ring size, with and
+    without the second issuer, over enough tiles per CTA (15-31) for the ring to wrap several times -- 1x1 (one block
+    per tile), 1x1 with three channel blocks per tile, 3x3 HALO with two, and the stride-2 PERTAP / PAIRS forms."""
+    if stages:
+        monkeypatch.setenv("UYD_TC_STAGES", str(stages))
+    if single:
+        monkeypatch.setenv("UYD_TC_SINGLE_ISSUER", "1")
+    for cin, cout, k, s, H, W, B in ((64, 32, 1, 1, 160, 160, 12), (192, 64, 1, 1, 80, 80, 48), (128, 64, 3, 1, 80, 80, 48),
+                                     (64, 64, 3, 2, 160, 160, 24), (32, 64, 3, 2, 160, 160, 24)):
+        got, ref = T.run_single_conv(cin, cout, k, s, H, W, batch=B, impl=T.IMPL_TC)
+        assert T.rel_err(got, ref) < 6e-3, (cin, cout, k, s, stages, single)
+
+
 def test_sppf_pool_and_upsample_are_exact(T):
     import torch.nn.functional as F
     import unina_yolo_dla_b200 as uyd
