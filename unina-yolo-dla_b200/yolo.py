@@ -267,7 +267,7 @@ class C3k2(nn.Module):
         self.m = nn.ModuleList(
             C3k(self.c, self.c, 2, shortcut, g) if c3k else Bottleneck(self.c, self.c, shortcut, g) for _ in range(n))
 
-    def emit(self, p, src, dst=None):
+    def emit(self, p, src, dst=None, feeds=None):
         c, n = self.c, len(self.m)
         cat = p.buffer(src.h, src.w, (2 + n) * c)
         if isinstance(src, UpCat) and _quantized(p, getattr(self.cv1.conv, "_uyd_name", "")):
@@ -304,7 +304,7 @@ class C3k2(nn.Module):
             self.cv1.emit(p, src, cat.sub(0, 2 * c))
         for i, m in enumerate(self.m):
             m.emit(p, cat.sub((1 + i) * c, c), cat.sub((2 + i) * c, c))
-        return self.cv2.emit(p, cat, dst)
+        return self.cv2.emit(p, cat, dst, feeds=feeds)
 
 
 class SPPF_DLA(nn.Module):
@@ -635,7 +635,18 @@ class UninaYoloB200(nn.Module):
                 assert isinstance(m, Conv), "the first layer must be a Conv reading the frame"
                 outs.append(m.emit(p, NETWORK_INPUT, dst))
             elif isinstance(m, (Conv, C3k2, SPPF_DLA)):
-                outs.append(m.emit(p, src_of(m.f), dst))
+                # INT8 graph: a layer whose output is read by the next layer only (not saved for a Concat / Detect) writes it
+                # directly as the int8 input of that layer's first conv -- no bf16 tensor, no quantize launch
+                feeds = None
+                nxt = layers[m.i + 1] if m.i + 1 < len(layers) else None
+                if (self.quant is not None and fusion and not record_inputs and dst is None and m.i not in self.save
+                        and isinstance(m, (Conv, C3k2)) and isinstance(nxt, (Conv, C3k2, SPPF_DLA)) and nxt.f == -1
+                        and os.environ.get("UYD_INT8_NO_LAYER_FEEDS", "0") != "1"):
+                    first = nxt.conv if isinstance(nxt, Conv) else nxt.cv1.conv
+                    last = m.conv if isinstance(m, Conv) else m.cv2.conv
+                    if _quantized(p, getattr(first, "_uyd_name", "")) and _quantized(p, getattr(last, "_uyd_name", "")):
+                        feeds = first
+                outs.append(m.emit(p, src_of(m.f), dst, feeds=feeds) if feeds is not None else m.emit(p, src_of(m.f), dst))
             elif isinstance(m, nn.Upsample):
                 s = src_of(m.f)
                 if any(u == m.i for u, _ in folded.values()):
